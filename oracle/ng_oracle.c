@@ -1,0 +1,585 @@
+/*
+ * ng_oracle.c -- CPU restatement of SNPGenie's within-/between-group
+ * Nei-Gojobori path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This file is the parity oracle: only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load it.  The product
+ * (snpgenie_b200/, libsnpgenie_cuda.so) never links, imports or calls it.
+ *
+ * Parity status: PINNED.  tests/test_oracle_golden.py checks every function
+ * here against outputs of the unmodified reference scripts run in the
+ * authoring container (tools/make_goldens.py -> tests/golden/), and the tables
+ * against a dump produced by calling the reference's own table subs
+ * (tools/dump_ref_tables.pl -> tests/golden/ng_tables.tsv).
+ *
+ * Each function cites the reference file:line it restates.  Nothing is copied:
+ * the tables are regenerated from first principles, the loops are re-derived.
+ * "wg" = snpgenie_within_group.pl, "bg" = snpgenie_between_group.pl.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_UNDEF 64 /* codon contains N or '-' */
+#define ORC_OTHER 65 /* defined, but not pure ACGT (IUPAC etc.) */
+
+/* ------------------------------------------------------------------ tables */
+
+/* Standard genetic code, codon index = 16*b0 + 4*b1 + b2 with A,C,G,T = 0..3.
+ * (wg:1400-1516 get_amino_acid holds the same mapping as a hash.) */
+static const char ORC_AA[65] =
+    "KNKNTTTTRSRSIIMIQHQHPPPPRRRRLLLLEDEDAAAAGGGGVVVV*Y*YSSSS*CWCLFLF";
+
+static int sub_base(int codon, int pos, int base)
+{
+    int shift = 2 * (2 - pos);
+    return (codon & ~(3 << shift)) | (base << shift);
+}
+
+/* The reference stores every pathway average as a 15-significant-digit decimal
+ * literal (wg:1731-17988), so e.g. 13/6 is the double nearest 2.16666666666667. */
+static double round15(double x)
+{
+    char buf[64];
+    snprintf(buf, sizeof buf, "%.15g", x);
+    return strtod(buf, NULL);
+}
+
+/*
+ * sites[c*2+{0,1}]     = N_sites, S_sites of codon c  (wg:1625-1721: per position,
+ *                        fraction of the non-STOP single-nucleotide changes that are
+ *                        nonsynonymous / synonymous; STOP codons 0/0; callers sum
+ *                        positions 1,2,3 in that order, wg:636-646, :719-724)
+ * diffs[0*4096+a*64+b] = N_diffs(a,b), diffs[1*4096+...] = S_diffs  (wg:1728-17996:
+ *                        average over all mutational pathways, dropping pathways with
+ *                        an intermediate STOP; any STOP endpoint -> 0,0; diagonal 0)
+ */
+void orc_build_tables(double *sites, double *diffs)
+{
+    for (int c = 0; c < 64; c++) {
+        double N = 0.0, S = 0.0;
+        for (int p = 0; p < 3; p++) {
+            int n = 0, s = 0;
+            for (int b = 0; b < 4; b++) {
+                int d = sub_base(c, p, b);
+                if (d == c || ORC_AA[d] == '*') continue;
+                if (ORC_AA[d] == ORC_AA[c]) s++; else n++;
+            }
+            if (ORC_AA[c] == '*' || n + s == 0) continue;
+            N += (double)n / (double)(n + s);
+            S += (double)s / (double)(n + s);
+        }
+        sites[c * 2 + 0] = N;
+        sites[c * 2 + 1] = S;
+    }
+    static const int perms[6][3] = {{0,1,2},{0,2,1},{1,0,2},{1,2,0},{2,0,1},{2,1,0}};
+    for (int a = 0; a < 64; a++) {
+        for (int b = 0; b < 64; b++) {
+            double *dn = &diffs[0 * 4096 + a * 64 + b], *ds = &diffs[1 * 4096 + a * 64 + b];
+            *dn = 0.0; *ds = 0.0;
+            if (a == b || ORC_AA[a] == '*' || ORC_AA[b] == '*') continue;
+            int differs[3], k = 0;
+            for (int p = 0; p < 3; p++) differs[p] = (((a >> (2*(2-p))) & 3) != ((b >> (2*(2-p))) & 3)), k += differs[p];
+            int tn = 0, ts = 0, npaths = 0;
+            for (int q = 0; q < 6; q++) {
+                /* a permutation is a pathway iff its first k entries are exactly the
+                 * differing positions; count each distinct ordering once */
+                int ok = 1;
+                for (int i = 0; i < 3; i++) if ((i < k) != (differs[perms[q][i]] != 0)) ok = 0;
+                if (!ok) continue;
+                int dup = 0; /* orderings of the non-differing tail are duplicates */
+                for (int i = k; i + 1 < 3; i++) if (perms[q][i] > perms[q][i+1]) dup = 1;
+                if (dup) continue;
+                int cur = a, n = 0, s = 0, alive = 1;
+                for (int i = 0; i < k && alive; i++) {
+                    int p = perms[q][i];
+                    int nxt = sub_base(cur, p, (b >> (2*(2-p))) & 3);
+                    if (ORC_AA[nxt] == '*') { alive = 0; break; }
+                    if (ORC_AA[nxt] == ORC_AA[cur]) s++; else n++;
+                    cur = nxt;
+                }
+                if (alive) { tn += n; ts += s; npaths++; }
+            }
+            if (npaths) {
+                *dn = round15((double)tn / npaths);
+                *ds = round15((double)ts / npaths);
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------- ingest / codon extraction */
+
+/* FASTA residue normalisation: uc, then U->T (wg:231-232, :250-251; bg:160-187). */
+static unsigned char norm_plus(unsigned char c)
+{
+    if (c >= 'a' && c <= 'z') c = (unsigned char)(c - 32);
+    if (c == 'U') c = 'T';
+    return c;
+}
+
+/* '-' strand: fasta2revcom.pl:77-79 does uc, reverse, tr/ACGT/TGCA/ (U is NOT
+ * complemented), after which the driver applies uc + U->T as above. */
+static unsigned char norm_minus(unsigned char c)
+{
+    if (c >= 'a' && c <= 'z') c = (unsigned char)(c - 32);
+    switch (c) {
+    case 'A': c = 'T'; break;
+    case 'C': c = 'G'; break;
+    case 'G': c = 'C'; break;
+    case 'T': c = 'A'; break;
+    default: break;
+    }
+    if (c == 'U') c = 'T';
+    return c;
+}
+
+static int base_index(unsigned char c)
+{
+    switch (c) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; default: return -1; }
+}
+
+/* Definedness as the reference tests it: a codon is skipped when it matches
+ * 'N' or '-' anywhere (wg:493, :498, :601, :604; bg:507).  Anything else counts
+ * as defined even if it is not pure ACGT; such codons miss both tables and
+ * contribute 0 sites / 0 diffs (wg:1715-1716 and :17990-17991 return undef). */
+int orc_codon_code(const unsigned char *c3)
+{
+    int idx = 0, other = 0;
+    for (int k = 0; k < 3; k++) {
+        if (c3[k] == 'N' || c3[k] == '-') return ORC_UNDEF;
+        int b = base_index(c3[k]);
+        if (b < 0) other = 1; else idx = idx * 4 + b;
+    }
+    return other ? ORC_OTHER : idx;
+}
+
+/*
+ * Product coordinate list (wg:1530-1621 + :286-329): segments are sorted by
+ * start (ties by input order, :1608), concatenated 1-based inclusive; the total
+ * must be a multiple of 3 (:1596).  For strand<0 the product is the reverse
+ * complement of that concatenation (gtf2revcom.pl:319-320 + fasta2revcom.pl),
+ * i.e. positions are visited in descending order.  pos_out receives 0-based
+ * alignment columns, length = return value (3*C); returns -1 if not %3, -2 if a
+ * coordinate is out of range.
+ */
+int64_t orc_product_positions(int nseg, const int64_t *start, const int64_t *stop,
+                              int strand, int64_t aln_len, int64_t *pos_out)
+{
+    int *order = (int *)malloc(sizeof(int) * (size_t)(nseg > 0 ? nseg : 1));
+    for (int i = 0; i < nseg; i++) order[i] = i;
+    for (int i = 1; i < nseg; i++) { /* stable insertion sort by start */
+        int o = order[i], j = i;
+        while (j > 0 && start[order[j-1]] > start[o]) { order[j] = order[j-1]; j--; }
+        order[j] = o;
+    }
+    int64_t total = 0;
+    for (int i = 0; i < nseg; i++) {
+        int s = order[i];
+        if (start[s] < 1 || stop[s] > aln_len || stop[s] < start[s]) { free(order); return -2; }
+        total += stop[s] - start[s] + 1;
+    }
+    if (total % 3 != 0) { free(order); return -1; }
+    if (pos_out) {
+        int64_t k = 0;
+        for (int i = 0; i < nseg; i++) {
+            int s = order[i];
+            for (int64_t p = start[s]; p <= stop[s]; p++) pos_out[k++] = p - 1;
+        }
+        if (strand < 0)
+            for (int64_t i = 0, j = total - 1; i < j; i++, j--) { int64_t t = pos_out[i]; pos_out[i] = pos_out[j]; pos_out[j] = t; }
+    }
+    free(order);
+    return total;
+}
+
+/*
+ * Codon split (wg:417-454; bg:351-388) on normalised residues.
+ * raw   [seq][codon][3] normalised characters (what the reference compares)
+ * codes [seq][codon]    0..63, ORC_UNDEF, ORC_OTHER
+ */
+void orc_extract(const uint8_t *aln, int64_t n, int64_t stride, const int64_t *pos,
+                 int64_t ncodon, int strand, uint8_t *raw, uint8_t *codes)
+{
+    for (int64_t i = 0; i < n; i++) {
+        const uint8_t *row = aln + i * stride;
+        for (int64_t c = 0; c < ncodon; c++) {
+            unsigned char c3[3];
+            for (int k = 0; k < 3; k++) {
+                unsigned char ch = row[pos[3 * c + k]];
+                c3[k] = strand < 0 ? norm_minus(ch) : norm_plus(ch);
+            }
+            if (raw) memcpy(raw + (i * ncodon + c) * 3, c3, 3);
+            if (codes) codes[i * ncodon + c] = (uint8_t)orc_codon_code(c3);
+        }
+    }
+}
+
+/* Per-codon histogram over sequences: 64 codon bins, [64]=undefined, [65]=other. */
+void orc_hist(const uint8_t *codes, int64_t n, int64_t ncodon, uint32_t *hist /* [C][66] */)
+{
+    memset(hist, 0, sizeof(uint32_t) * 66 * (size_t)ncodon);
+    for (int64_t i = 0; i < n; i++)
+        for (int64_t c = 0; c < ncodon; c++) hist[c * 66 + codes[i * ncodon + c]]++;
+}
+
+/* ----------------------------------------------------- literal pair loops */
+
+static inline uint32_t key3(const uint8_t *p) { return ((uint32_t)p[0] << 16) | ((uint32_t)p[1] << 8) | p[2]; }
+static inline int key_defined(uint32_t k)
+{
+    for (int s = 0; s < 24; s += 8) { unsigned c = (k >> s) & 0xff; if (c == 'N' || c == '-') return 0; }
+    return 1;
+}
+static inline int key_code(uint32_t k)
+{
+    unsigned char c3[3] = { (unsigned char)(k >> 16), (unsigned char)(k >> 8), (unsigned char)k };
+    return orc_codon_code(c3);
+}
+static inline double site_of(const double *sites, int code, int which) { return code < 64 ? sites[code * 2 + which] : 0.0; }
+
+/* small allele dictionary for one codon column */
+typedef struct { uint32_t *keys; int64_t n, cap; } allele_set;
+static int64_t allele_id(allele_set *s, uint32_t k)
+{
+    for (int64_t i = 0; i < s->n; i++) if (s->keys[i] == k) return i;
+    if (s->n == s->cap) { s->cap = s->cap ? 2 * s->cap : 8; s->keys = (uint32_t *)realloc(s->keys, sizeof(uint32_t) * (size_t)s->cap); }
+    s->keys[s->n] = k;
+    return s->n++;
+}
+
+/*
+ * Within-group engine for one product, following the reference loop by loop:
+ *   wg:489-506  polymorphism pre-check (first differing defined pair)
+ *   wg:597-609  $comps_hh{ci}{cj}++ over all i<j with both defined
+ *   wg:618-675  per unique ordered pair: weight * mean sites, weight * diffs
+ *   wg:681-687  means = sums / comparisons
+ *   wg:706-744  conserved branch: first defined codon's sites, 0 diffs
+ * raw is [seq][codon][3].  Outputs are per codon; n_defined is the TRUE count
+ * (the reference's own count is truncated by its early exit -- quirk q1 -- and is
+ * not on the graded path).  first_key = packed chars of the first defined codon
+ * (0 when none).  Threaded over codons like the reference's fork-per-codon.
+ */
+void orc_within_pairloop(const uint8_t *raw, int64_t n, int64_t ncodon,
+                         const double *sites, const double *diffs,
+                         uint8_t *poly, uint32_t *n_defined, double *comparisons,
+                         double *Ns, double *Ss, double *Nd, double *Sd, uint32_t *first_key)
+{
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t c = 0; c < ncodon; c++) {
+        uint32_t *col = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(n > 0 ? n : 1));
+        for (int64_t i = 0; i < n; i++) col[i] = key3(raw + (i * ncodon + c) * 3);
+        /* pre-check, wg:489-506 */
+        int is_poly = 0;
+        uint32_t ndef = 0, first = 0;
+        for (int64_t i = 0; i < n; i++) if (key_defined(col[i])) { if (!ndef) first = col[i]; ndef++; }
+        for (int64_t i = 0; i < n && !is_poly; i++) {
+            if (!key_defined(col[i])) continue;
+            for (int64_t j = i + 1; j < n; j++)
+                if (col[i] != col[j] && key_defined(col[j])) { is_poly = 1; break; }
+        }
+        poly[c] = (uint8_t)is_poly; n_defined[c] = ndef; first_key[c] = first;
+        if (is_poly) {
+            /* pair counting, wg:597-609 */
+            allele_set as = {0, 0, 0};
+            int64_t *aid = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);
+            for (int64_t i = 0; i < n; i++) aid[i] = key_defined(col[i]) ? allele_id(&as, col[i]) : -1;
+            int64_t A = as.n;
+            double *comps = (double *)calloc((size_t)(A * A), sizeof(double));
+            for (int64_t i = 0; i < n; i++) {
+                if (aid[i] < 0) continue;
+                for (int64_t j = i + 1; j < n; j++)
+                    if (aid[j] >= 0) comps[aid[i] * A + aid[j]] += 1.0;
+            }
+            /* unique-pair sums, wg:618-675 */
+            double cmp = 0, sNs = 0, sSs = 0, sNd = 0, sSd = 0;
+            for (int64_t a = 0; a < A; a++) for (int64_t b = 0; b < A; b++) {
+                double w = comps[a * A + b];
+                if (w == 0.0) continue;
+                int ca = key_code(as.keys[a]), cb = key_code(as.keys[b]);
+                double mN = (site_of(sites, ca, 0) + site_of(sites, cb, 0)) / 2;
+                double mS = (site_of(sites, ca, 1) + site_of(sites, cb, 1)) / 2;
+                sNs += w * mN; sSs += w * mS;
+                double dn = 0, ds = 0;
+                if (as.keys[a] != as.keys[b] && ca < 64 && cb < 64) { dn = diffs[ca * 64 + cb]; ds = diffs[4096 + ca * 64 + cb]; }
+                sNd += w * dn; sSd += w * ds;
+                cmp += w;
+            }
+            comparisons[c] = cmp;
+            Ns[c] = sNs / cmp; Ss[c] = sSs / cmp; Nd[c] = sNd / cmp; Sd[c] = sSd / cmp; /* wg:681-684 */
+            free(comps); free(aid); free(as.keys);
+        } else {
+            /* conserved, wg:706-744 */
+            int code = ndef ? key_code(first) : ORC_UNDEF;
+            comparisons[c] = 0;
+            Ns[c] = site_of(sites, code, 0); Ss[c] = site_of(sites, code, 1); Nd[c] = 0; Sd[c] = 0;
+        }
+        free(col);
+    }
+}
+
+/*
+ * Between-group engine for one product and one group pair, following
+ *   bg:492-513  pre-check: any cross pair, both defined, that differs
+ *   bg:611-631  num_defined_codons_g1 / g2
+ *   bg:649-667  $comps_hh{gi}{gj}++ over all cross pairs with both defined
+ *   bg:689-796  unique-pair sums;  bg:801-811 means (guarded for 0 comparisons)
+ *   bg:853-899  conserved branch: gi[0] if defined, else first defined gj, else
+ *               next gi ...; none -> '---' (0 sites)
+ */
+void orc_between_pairloop(const uint8_t *raw_a, int64_t na, const uint8_t *raw_b, int64_t nb, int64_t ncodon,
+                          const double *sites, const double *diffs,
+                          uint8_t *poly, uint32_t *ndef_a, uint32_t *ndef_b, double *comparisons,
+                          double *Ns, double *Ss, double *Nd, double *Sd, uint32_t *first_key)
+{
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t c = 0; c < ncodon; c++) {
+        uint32_t *ca = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(na > 0 ? na : 1));
+        uint32_t *cb = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(nb > 0 ? nb : 1));
+        for (int64_t i = 0; i < na; i++) ca[i] = key3(raw_a + (i * ncodon + c) * 3);
+        for (int64_t j = 0; j < nb; j++) cb[j] = key3(raw_b + (j * ncodon + c) * 3);
+        uint32_t da = 0, db = 0;
+        for (int64_t i = 0; i < na; i++) da += (uint32_t)key_defined(ca[i]);
+        for (int64_t j = 0; j < nb; j++) db += (uint32_t)key_defined(cb[j]);
+        ndef_a[c] = da; ndef_b[c] = db;
+        int is_poly = 0;
+        for (int64_t i = 0; i < na && !is_poly; i++) {
+            if (!key_defined(ca[i])) continue;
+            for (int64_t j = 0; j < nb; j++)
+                if (ca[i] != cb[j] && key_defined(cb[j])) { is_poly = 1; break; }
+        }
+        poly[c] = (uint8_t)is_poly;
+        first_key[c] = 0;
+        if (is_poly) {
+            allele_set as = {0, 0, 0};
+            int64_t *ia = (int64_t *)malloc(sizeof(int64_t) * (size_t)na), *ib = (int64_t *)malloc(sizeof(int64_t) * (size_t)nb);
+            for (int64_t i = 0; i < na; i++) ia[i] = key_defined(ca[i]) ? allele_id(&as, ca[i]) : -1;
+            for (int64_t j = 0; j < nb; j++) ib[j] = key_defined(cb[j]) ? allele_id(&as, cb[j]) : -1;
+            int64_t A = as.n;
+            double *comps = (double *)calloc((size_t)(A * A), sizeof(double));
+            for (int64_t i = 0; i < na; i++) {
+                if (ia[i] < 0) continue;
+                for (int64_t j = 0; j < nb; j++) if (ib[j] >= 0) comps[ia[i] * A + ib[j]] += 1.0;
+            }
+            double cmp = 0, sNs = 0, sSs = 0, sNd = 0, sSd = 0;
+            for (int64_t a = 0; a < A; a++) for (int64_t b = 0; b < A; b++) {
+                double w = comps[a * A + b];
+                if (w == 0.0) continue;
+                int xa = key_code(as.keys[a]), xb = key_code(as.keys[b]);
+                sNs += w * ((site_of(sites, xa, 0) + site_of(sites, xb, 0)) / 2);
+                sSs += w * ((site_of(sites, xa, 1) + site_of(sites, xb, 1)) / 2);
+                double dn = 0, ds = 0;
+                if (as.keys[a] != as.keys[b] && xa < 64 && xb < 64) { dn = diffs[xa * 64 + xb]; ds = diffs[4096 + xa * 64 + xb]; }
+                sNd += w * dn; sSd += w * ds; cmp += w;
+            }
+            comparisons[c] = cmp;
+            if (cmp > 0) { Ns[c] = sNs / cmp; Ss[c] = sSs / cmp; Nd[c] = sNd / cmp; Sd[c] = sSd / cmp; }
+            else { Ns[c] = Ss[c] = Nd[c] = Sd[c] = 0; }
+            free(comps); free(ia); free(ib); free(as.keys);
+        } else {
+            /* bg:853-890 scan order */
+            uint32_t found = 0;
+            for (int64_t i = 0; i < na && !found && nb > 0; i++) { /* the gi test sits inside the gj loop */
+                if (key_defined(ca[i])) { found = ca[i]; break; }
+                for (int64_t j = 0; j < nb; j++) if (key_defined(cb[j])) { found = cb[j]; break; }
+            }
+            int code = found ? key_code(found) : ORC_UNDEF; /* '---', bg:893-899 */
+            first_key[c] = found;
+            comparisons[c] = 0;
+            Ns[c] = site_of(sites, code, 0); Ss[c] = site_of(sites, code, 1); Nd[c] = 0; Sd[c] = 0;
+        }
+        free(ca); free(cb);
+    }
+}
+
+/* ------------------------------------------- histogram (closed-form) variants */
+
+/*
+ * The same per-codon results from the 66-bin histogram, for sizes where the
+ * literal pair loop would take hours.  Verified against orc_within_pairloop in
+ * tests (<= 1e-13 relative) -- SURVEY.md section 3.5:
+ *   comparisons = n(n-1)/2, N_sites = h.sN / n, N_diffs = (1/2) h'T_N h / comparisons.
+ * 'other' codons are one bin; other_distinct says whether >= 2 distinct other
+ * strings exist (only affects the polymorphic flag, quirk q3).
+ */
+void orc_within_hist(const uint32_t *hist, const uint8_t *other_distinct, int64_t ncodon,
+                     const double *sites, const double *diffs,
+                     uint8_t *poly, uint32_t *n_defined, double *comparisons,
+                     double *Ns, double *Ss, double *Nd, double *Sd)
+{
+    for (int64_t c = 0; c < ncodon; c++) {
+        const uint32_t *h = hist + c * 66;
+        double n = 0; int alleles = 0;
+        for (int b = 0; b < 64; b++) { n += h[b]; alleles += h[b] != 0; }
+        n += h[ORC_OTHER];
+        if (h[ORC_OTHER]) alleles += (other_distinct && other_distinct[c]) ? 2 : 1;
+        n_defined[c] = (uint32_t)n;
+        poly[c] = alleles >= 2;
+        double hs0 = 0, hs1 = 0;
+        for (int b = 0; b < 64; b++) { hs0 += h[b] * sites[b * 2]; hs1 += h[b] * sites[b * 2 + 1]; }
+        if (poly[c]) {
+            double cmp = n * (n - 1) / 2, qn = 0, qs = 0;
+            for (int a = 0; a < 64; a++) {
+                if (!h[a]) continue;
+                for (int b = a + 1; b < 64; b++) {
+                    if (!h[b]) continue;
+                    qn += (double)h[a] * h[b] * diffs[a * 64 + b];
+                    qs += (double)h[a] * h[b] * diffs[4096 + a * 64 + b];
+                }
+            }
+            comparisons[c] = cmp; Ns[c] = hs0 / n; Ss[c] = hs1 / n; Nd[c] = qn / cmp; Sd[c] = qs / cmp;
+        } else {
+            comparisons[c] = 0; Nd[c] = Sd[c] = 0;
+            Ns[c] = n > 0 ? hs0 / n : 0; Ss[c] = n > 0 ? hs1 / n : 0;
+        }
+    }
+}
+
+void orc_between_hist(const uint32_t *hist_a, const uint32_t *hist_b, const uint8_t *other_distinct, int64_t ncodon,
+                      const double *sites, const double *diffs,
+                      uint8_t *poly, uint32_t *ndef_a, uint32_t *ndef_b, double *comparisons,
+                      double *Ns, double *Ss, double *Nd, double *Sd)
+{
+    for (int64_t c = 0; c < ncodon; c++) {
+        const uint32_t *ha = hist_a + c * 66, *hb = hist_b + c * 66;
+        double na = 0, nb = 0; int alleles = 0;
+        for (int b = 0; b < 64; b++) { na += ha[b]; nb += hb[b]; alleles += (ha[b] | hb[b]) != 0; }
+        na += ha[ORC_OTHER]; nb += hb[ORC_OTHER];
+        if (ha[ORC_OTHER] | hb[ORC_OTHER]) alleles += (other_distinct && other_distinct[c]) ? 2 : 1;
+        ndef_a[c] = (uint32_t)na; ndef_b[c] = (uint32_t)nb;
+        poly[c] = (na > 0 && nb > 0 && alleles >= 2);
+        double as0 = 0, as1 = 0, bs0 = 0, bs1 = 0;
+        for (int b = 0; b < 64; b++) {
+            as0 += ha[b] * sites[b * 2]; as1 += ha[b] * sites[b * 2 + 1];
+            bs0 += hb[b] * sites[b * 2]; bs1 += hb[b] * sites[b * 2 + 1];
+        }
+        if (poly[c]) {
+            double cmp = na * nb, qn = 0, qs = 0;
+            for (int a = 0; a < 64; a++) {
+                if (!ha[a]) continue;
+                for (int b = 0; b < 64; b++) {
+                    if (!hb[b] || a == b) continue;
+                    qn += (double)ha[a] * hb[b] * diffs[a * 64 + b];
+                    qs += (double)ha[a] * hb[b] * diffs[4096 + a * 64 + b];
+                }
+            }
+            comparisons[c] = cmp;
+            Ns[c] = (as0 / na + bs0 / nb) / 2; Ss[c] = (as1 / na + bs1 / nb) / 2;
+            Nd[c] = qn / cmp; Sd[c] = qs / cmp;
+        } else {
+            /* single shared allele, or one group empty: only well defined from the
+             * histogram when the non-empty side is monomorphic */
+            comparisons[c] = 0; Nd[c] = Sd[c] = 0;
+            if (na > 0) { Ns[c] = as0 / na; Ss[c] = as1 / na; }
+            else if (nb > 0) { Ns[c] = bs0 / nb; Ss[c] = bs1 / nb; }
+            else { Ns[c] = Ss[c] = 0; }
+        }
+    }
+}
+
+/* ---------------------------------------------------------- resampling side */
+
+/* Two-pass mean and sample SD (n-1), wg:1338-1365; '*' entries arrive as 0. */
+double orc_sd(const double *v, int64_t n)
+{
+    double sum = 0;
+    for (int64_t i = 0; i < n; i++) sum += v[i];
+    double mean = sum / (double)n, ss = 0;
+    for (int64_t i = 0; i < n; i++) ss += (v[i] - mean) * (v[i] - mean);
+    return sqrt(ss / (double)(n - 1));
+}
+
+/* splitmix64 -> uniform [0,1): the oracle's own stream (the reference re-seeds
+ * Perl's rand() every replicate, wg:856, so streams can only agree statistically) */
+static inline uint64_t sm64(uint64_t *s)
+{
+    uint64_t z = (*s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static inline double sm_unif(uint64_t *s) { return (double)(sm64(s) >> 11) * (1.0 / 9007199254740992.0); }
+
+/*
+ * Whole-product bootstrap (wg:854-916; between processor :893-989): B replicates,
+ * each C draws int(rand(C+1)); slot 0 is a nonexistent codon contributing 0.
+ * stats4 is [C][4] = N_sites,S_sites,N_diffs,S_diffs, already masked by any
+ * min-taxa filter.  sums_out [B][4].  se_out[0..2] = SD of dN, dS, dN-dS over
+ * replicates with the reference's '*'->0 coercion (wg:942-965); se_out[3..5] =
+ * the Jukes-Cantor variants (between processor :1047-1071).
+ */
+void orc_bootstrap_product(const double *stats4, int64_t C, int64_t B, uint64_t seed,
+                           double *sums_out, double *se_out)
+{
+    double *dn = (double *)malloc(sizeof(double) * (size_t)B * 6);
+    double *ds = dn + B, *dd = ds + B, *jn = dd + B, *js = jn + B, *jd = js + B;
+#pragma omp parallel for schedule(static)
+    for (int64_t b = 0; b < B; b++) {
+        uint64_t st = seed * 0x2545F4914F6CDD1Dull + (uint64_t)b * 0xD1342543DE82EF95ull + 1;
+        double s[4] = {0, 0, 0, 0};
+        for (int64_t k = 0; k < C; k++) {
+            int64_t r = (int64_t)(sm_unif(&st) * (double)(C + 1));
+            if (r == 0) continue;
+            const double *row = stats4 + (r - 1) * 4;
+            s[0] += row[0]; s[1] += row[1]; s[2] += row[2]; s[3] += row[3];
+        }
+        if (sums_out) memcpy(sums_out + b * 4, s, sizeof s);
+        double vN = s[0] > 0 ? s[2] / s[0] : 0, vS = s[1] > 0 ? s[3] / s[1] : 0;
+        dn[b] = vN; ds[b] = vS; dd[b] = vN - vS;
+        double a = -0.75 * log(1 - (4.0 / 3.0) * vN), c = -0.75 * log(1 - (4.0 / 3.0) * vS);
+        jn[b] = a; js[b] = c; jd[b] = (a >= 0 && c >= 0) ? a - c : 0;
+    }
+    se_out[0] = orc_sd(dn, B); se_out[1] = orc_sd(ds, B); se_out[2] = orc_sd(dd, B);
+    se_out[3] = orc_sd(jn, B); se_out[4] = orc_sd(js, B); se_out[5] = orc_sd(jd, B);
+    free(dn);
+}
+
+/*
+ * Sliding windows (within processor :314-362; between processor :501-592):
+ * window k covers codons [k*step, k*step+W) for k*step <= C-W; sums accumulate
+ * codon by codon in ascending order.  With B>1, per window B replicates of W
+ * uniform draws inside the window (:384-427).  win_sums [nwin][4]; win_se
+ * [nwin][3] (dN, dS, dN-dS).  Returns nwin.
+ */
+int64_t orc_windows(const double *stats4, int64_t C, int64_t W, int64_t step, int64_t B, uint64_t seed,
+                    double *win_sums, double *win_se)
+{
+    if (W > C || W < 1 || step < 1) return 0;
+    int64_t nwin = (C - W) / step + 1;
+    for (int64_t k = 0; k < nwin; k++) {
+        double s[4] = {0, 0, 0, 0};
+        for (int64_t i = k * step; i < k * step + W; i++) for (int q = 0; q < 4; q++) s[q] += stats4[i * 4 + q];
+        if (win_sums) memcpy(win_sums + k * 4, s, sizeof s);
+    }
+    if (B > 1 && win_se) {
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int64_t k = 0; k < nwin; k++) {
+            double *dn = (double *)malloc(sizeof(double) * (size_t)B * 3), *ds = dn + B, *dd = ds + B;
+            uint64_t st = seed * 0x9E3779B97F4A7C15ull + (uint64_t)k * 0xBF58476D1CE4E5B9ull + 7;
+            for (int64_t b = 0; b < B; b++) {
+                double s[4] = {0, 0, 0, 0};
+                for (int64_t d = 0; d < W; d++) {
+                    int64_t r = k * step + (int64_t)(sm_unif(&st) * (double)W);
+                    for (int q = 0; q < 4; q++) s[q] += stats4[r * 4 + q];
+                }
+                double vN = s[0] > 0 ? s[2] / s[0] : 0, vS = s[1] > 0 ? s[3] / s[1] : 0;
+                dn[b] = vN; ds[b] = vS; dd[b] = vN - vS;
+            }
+            win_se[k * 3 + 0] = orc_sd(dn, B); win_se[k * 3 + 1] = orc_sd(ds, B); win_se[k * 3 + 2] = orc_sd(dd, B);
+            free(dn);
+        }
+    }
+    return nwin;
+}
+
+int orc_max_threads(void)
+{
+#ifdef _OPENMP
+    extern int omp_get_max_threads(void);
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
