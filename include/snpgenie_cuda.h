@@ -1,0 +1,172 @@
+/*
+ * snpgenie_cuda.h -- C ABI of libsnpgenie_cuda.so
+ *
+ * B200-native engine for SNPGenie's within-/between-group Nei-Gojobori dN/dS
+ * path.  The reference (chasewnelson/SNPGenie) has no FFI seam: the engine is
+ * inline in the Perl product loop.  Each entry point below names the reference
+ * block it replaces ("wg" = snpgenie_within_group.pl, "bg" =
+ * snpgenie_between_group.pl, "wgp"/"bgp" = the two *_processor.pl scripts).
+ * INTEGRATION.md shows the XS binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ or torch types cross this boundary
+ *   - every call returns SNPG_OK (0) or a negative SNPG_E_* code and never
+ *     aborts, throws or exits; text via snpg_last_error()
+ *   - the caller owns every buffer; inputs are copied to the device before the
+ *     call returns, outputs are complete when it returns (calls synchronise)
+ *   - one ctx = one CUDA device, used from one host thread at a time
+ *   - do not fork() after snpg_create(): CUDA contexts do not survive fork, so
+ *     the reference's fork-per-codon (wg:470-541) has no counterpart here
+ *   - there is NO CPU fallback: without a usable device snpg_create() fails
+ *
+ * Codon codes (1 byte per sequence per codon): 0..63 = 16*b0+4*b1+b2 with
+ * A,C,G,T = 0..3 after the reference's normalisation (uc, U->T; wg:231-232);
+ * 64 = undefined (any N or '-'; wg:493,498); 65 = other (defined but not pure
+ * ACGT, e.g. IUPAC -- misses both tables, contributes 0; wg:1715, :17990).
+ */
+#ifndef SNPGENIE_CUDA_H
+#define SNPGENIE_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNPG_CODE_UNDEF 64
+#define SNPG_CODE_OTHER 65
+#define SNPG_HIST_BINS 66 /* 64 codons, undefined, other */
+
+#define SNPG_OK 0
+#define SNPG_E_ARG (-1)     /* bad argument / out of range */
+#define SNPG_E_STATE (-2)   /* call order (e.g. no products set) */
+#define SNPG_E_INPUT (-3)   /* input the reference would die() on (CDS not %3 ...) */
+#define SNPG_E_CUDA (-4)    /* CUDA runtime failure, incl. "no device" */
+#define SNPG_E_NOMEM (-5)
+
+typedef struct snpg_ctx snpg_ctx;
+
+/* ---- lifecycle --------------------------------------------------------- */
+int snpg_create(snpg_ctx **out, int device, uint64_t seed);
+void snpg_destroy(snpg_ctx *ctx);
+const char *snpg_last_error(const snpg_ctx *ctx); /* ctx may be NULL: error of the last failed snpg_create */
+const char *snpg_version(void);
+
+/* ---- Nei-Gojobori tables (host only, no device needed) ------------------
+ * Replaces get_number_of_sites (wg:1625-1721; positions summed 1+2+3 as at
+ * wg:636-646) and return_avg_diffs (wg:1728-17996).
+ * sites [64][2] = N_sites,S_sites; diffs [2][64][64] = N_diffs, S_diffs. */
+int snpg_get_tables(double *sites, double *diffs);
+
+/* ---- annotation ---------------------------------------------------------
+ * Replaces get_product_coordinates (wg:1530-1621) + product extraction
+ * (wg:286-329; bg:238-298) + codon split (wg:417-454; bg:351-388).
+ * Products as CSR: segments seg_ofs[p]..seg_ofs[p+1], 1-based inclusive
+ * coordinates on the '+' strand; strand[p] = +1/-1.  Segments are sorted by
+ * start inside (wg:1608).  A '-' product is the reverse complement of the
+ * concatenation (== fasta2revcom.pl + gtf2revcom.pl:319-320).
+ * SNPG_E_INPUT if a product's length is not a multiple of 3 (wg:1596). */
+int snpg_set_products(snpg_ctx *ctx, int n_products, const int64_t *seg_ofs,
+                      const int64_t *seg_start, const int64_t *seg_stop,
+                      const int8_t *strand, int64_t aln_len);
+int snpg_n_products(const snpg_ctx *ctx);
+int snpg_n_codons(const snpg_ctx *ctx, int product, int64_t *out);
+
+/* Multi-GPU: this ctx owns the slice [first, first+count) of the global codon
+ * axis (all products concatenated in set_products order).  rank/world as in
+ * torch.distributed; default 0/1.  Call before snpg_set_products. */
+int snpg_set_shard(snpg_ctx *ctx, int rank, int world);
+int snpg_shard_range(const snpg_ctx *ctx, int64_t *first, int64_t *count, int64_t *total);
+
+/* ---- alignment ingest: pack + per-codon histogram ------------------------
+ * Replaces FASTA normalisation (wg:231-232) and, through the histogram, the
+ * polymorphism pre-check (wg:469-541; bg:472-544) and the O(n^2) pair counting
+ * (wg:596-609; bg:649-667).  bases: row-major, one row per sequence, raw FASTA
+ * residues (any case, U allowed).  _host copies from host memory (pinned or
+ * pageable) in row blocks overlapped with packing; _device takes a device
+ * pointer.  Up to SNPG_MAX_GROUPS groups; reloading a group replaces it. */
+#define SNPG_MAX_GROUPS 64
+int snpg_load_group(snpg_ctx *ctx, int group, const uint8_t *bases, uint64_t n_seqs,
+                    uint64_t aln_len, uint64_t row_stride);
+int snpg_load_group_device(snpg_ctx *ctx, int group, const uint8_t *d_bases, uint64_t n_seqs,
+                           uint64_t aln_len, uint64_t row_stride);
+int snpg_drop_group(snpg_ctx *ctx, int group);
+int snpg_group_size(const snpg_ctx *ctx, int group, uint64_t *n_seqs);
+
+/* Options: SNPG_OPT_KEEP_CODES (default 1) keeps the packed codon matrix on the
+ * device (needed by snpg_get_codon_indices and the between-group first-defined
+ * rule); 0 frees it after the histogram pass. */
+#define SNPG_OPT_KEEP_CODES 1
+int snpg_set_option(snpg_ctx *ctx, int option, int64_t value);
+
+/* ---- test hooks for the bit-exact checks ---------------------------------
+ * codes out: [n_seqs][C] row-major (sequence-major, like the reference's
+ * $products_seqs_hh); hist out: [C][SNPG_HIST_BINS]; other_distinct out: [C],
+ * 1 if >= 2 distinct 'other' codon strings occur (affects only the
+ * polymorphic flag).  Only the codons of this ctx's shard are filled when
+ * world > 1 (C = shard slice of the product). */
+int snpg_get_codon_indices(snpg_ctx *ctx, int group, int product, uint8_t *out);
+int snpg_get_hist(snpg_ctx *ctx, int group, int product, uint32_t *out, uint8_t *other_distinct);
+
+/* ---- per-codon engine ------------------------------------------------------
+ * Replaces wg:586-751 (within) and bg:573-955 (between): per codon the
+ * variability flag, number of defined sequences, number of comparisons, mean
+ * N/S sites and mean N/S differences, and for conserved codons the code of the
+ * conserved codon (SNPG_CODE_UNDEF when none is defined: wg prints an empty
+ * codon, bg prints '---').  All outputs have length C (product's codons in this
+ * shard); any output pointer may be NULL.  stats4 [C][4] = N_sites, S_sites,
+ * N_diffs, S_diffs (the layout the resampling calls take). */
+int snpg_within(snpg_ctx *ctx, int group, int product, uint8_t *poly, uint32_t *n_defined,
+                uint64_t *comparisons, double *stats4, uint8_t *conserved_code);
+int snpg_between(snpg_ctx *ctx, int group_a, int group_b, int product, uint8_t *poly,
+                 uint32_t *n_defined_a, uint32_t *n_defined_b, uint64_t *comparisons,
+                 double *stats4, uint8_t *conserved_code);
+
+/* ---- resampling -------------------------------------------------------------
+ * snpg_bootstrap_product replaces wg:831-978 and bgp:869-1102: B replicates of C
+ * draws from C+1 slots (slot 0 = the reference's nonexistent codon 0, wg:885).
+ * keep (or NULL) is the min-taxa mask of bgp:412-467 (0 = codon contributes 0).
+ * sums_out [B][4] or NULL (the <product>_bootstrap_results.txt rows).
+ * se_out [6] = sample SD (n-1, two-pass; wg:1351-1365) over replicates of dN,
+ * dS, dN-dS and their Jukes-Cantor forms (bgp:1047-1071), with the reference's
+ * '*' -> 0 coercion.  Streams are Philox4x32-10 keyed by the ctx seed; results
+ * agree with the reference statistically, not bitwise. */
+int snpg_bootstrap_product(snpg_ctx *ctx, const double *stats4, const uint8_t *keep, int64_t C,
+                           int64_t B, double *sums_out, double *se_out);
+
+/* snpg_windows replaces wgp:293-465 and bgp:501-736.  Window k covers codons
+ * [k*step, k*step+W) for k*step <= C-W.  win_sums [nwin][4] accumulate in
+ * ascending codon order (bitwise the reference's order); win_se [nwin][3] = SD
+ * of dN, dS, dN-dS over B replicates of W uniform draws inside the window
+ * (NULL or B < 2: skipped).  *nwin_out receives the number of windows. */
+int snpg_windows(snpg_ctx *ctx, const double *stats4, const uint8_t *keep, int64_t C, int64_t W,
+                 int64_t step, int64_t B, double *win_sums, double *win_se, int64_t *nwin_out);
+
+/* ---- whole-job entry (what bench.py times) ---------------------------------
+ * For every product of a loaded group, entirely on the device: per-codon stats
+ * (as snpg_within), product sums (wg:690-693) and bootstrap SEs (wg:831-978).
+ * prod_sums [P][4]; prod_se [P][6] (NULL or B < 2: no bootstrap).
+ * Under a shard (world > 1) this covers the local codon slice only and callers
+ * combine slices (see snpg_stats_device / bench.py). */
+int snpg_within_all(snpg_ctx *ctx, int group, int64_t B, double *prod_sums, double *prod_se);
+
+/* Device-pointer variants for multi-GPU plumbing (torch.distributed moves the
+ * buffers): d_stats4 is a DEVICE buffer [count][4] for this shard's codons. */
+int snpg_within_stats_device(snpg_ctx *ctx, int group, double *d_stats4);
+/* Bootstrap all products from a full-length DEVICE stats buffer [total][4];
+ * replicates [b_first, b_first+b_count) only; d_rep_out DEVICE [P][b_count][4]. */
+int snpg_bootstrap_all_device(snpg_ctx *ctx, const double *d_stats4_full, int64_t b_first,
+                              int64_t b_count, double *d_rep_out);
+
+/* Product sums (wg:690-693) from a full-length DEVICE stats buffer -> host prod_sums [P][4]. */
+int snpg_product_sums_device(snpg_ctx *ctx, const double *d_stats4_full, double *prod_sums);
+/* SD over replicates from a DEVICE buffer rep [n_items][B][4] -> host se_out [n_items][6]. */
+int snpg_rep_moments_device(snpg_ctx *ctx, const double *d_rep, int64_t n_items, int64_t B, double *se_out);
+
+/* Kernel launches issued by this ctx since creation (bench.py's gpu_launches). */
+int64_t snpg_launch_count(const snpg_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNPGENIE_CUDA_H */

@@ -1,0 +1,68 @@
+"""ctypes binding of libsnpgenie_cuda.so (see include/snpgenie_cuda.h).
+
+The library is built in-tree by __graft_entry__.build() / snpgenie_b200/csrc/Makefile.
+There is no fallback: if the shared object is missing, importing this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsnpgenie_cuda.so")
+
+OK, E_ARG, E_STATE, E_INPUT, E_CUDA, E_NOMEM = 0, -1, -2, -3, -4, -5
+CODE_UNDEF, CODE_OTHER, HIST_BINS = 64, 65, 66
+OPT_KEEP_CODES = 1
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(snpgenie_b200 has no CPU fallback)"
+    )
+
+lib = C.CDLL(LIB_PATH)
+
+_u8p, _u32p, _u64p, _i64p, _i8p, _f64p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint32, C.c_uint64, C.c_int64, C.c_int8, C.c_double))
+_ctx = C.c_void_p
+
+# every exported symbol of include/snpgenie_cuda.h with its signature
+SIGNATURES = {
+    "snpg_create": (C.c_int, [C.POINTER(_ctx), C.c_int, C.c_uint64]),
+    "snpg_destroy": (None, [_ctx]),
+    "snpg_last_error": (C.c_char_p, [_ctx]),
+    "snpg_version": (C.c_char_p, []),
+    "snpg_get_tables": (C.c_int, [_f64p, _f64p]),
+    "snpg_set_products": (C.c_int, [_ctx, C.c_int, _i64p, _i64p, _i64p, _i8p, C.c_int64]),
+    "snpg_n_products": (C.c_int, [_ctx]),
+    "snpg_n_codons": (C.c_int, [_ctx, C.c_int, _i64p]),
+    "snpg_set_shard": (C.c_int, [_ctx, C.c_int, C.c_int]),
+    "snpg_shard_range": (C.c_int, [_ctx, _i64p, _i64p, _i64p]),
+    "snpg_load_group": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "snpg_load_group_device": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "snpg_drop_group": (C.c_int, [_ctx, C.c_int]),
+    "snpg_group_size": (C.c_int, [_ctx, C.c_int, _u64p]),
+    "snpg_set_option": (C.c_int, [_ctx, C.c_int, C.c_int64]),
+    "snpg_get_codon_indices": (C.c_int, [_ctx, C.c_int, C.c_int, _u8p]),
+    "snpg_get_hist": (C.c_int, [_ctx, C.c_int, C.c_int, _u32p, _u8p]),
+    "snpg_within": (C.c_int, [_ctx, C.c_int, C.c_int, _u8p, _u32p, _u64p, _f64p, _u8p]),
+    "snpg_between": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, _u8p, _u32p, _u32p, _u64p, _f64p, _u8p]),
+    "snpg_bootstrap_product": (C.c_int, [_ctx, _f64p, _u8p, C.c_int64, C.c_int64, _f64p, _f64p]),
+    "snpg_windows": (C.c_int, [_ctx, _f64p, _u8p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _f64p, _f64p, _i64p]),
+    "snpg_within_all": (C.c_int, [_ctx, C.c_int, C.c_int64, _f64p, _f64p]),
+    "snpg_within_stats_device": (C.c_int, [_ctx, C.c_int, C.c_void_p]),
+    "snpg_bootstrap_all_device": (C.c_int, [_ctx, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "snpg_product_sums_device": (C.c_int, [_ctx, C.c_void_p, _f64p]),
+    "snpg_rep_moments_device": (C.c_int, [_ctx, C.c_void_p, C.c_int64, C.c_int64, _f64p]),
+    "snpg_launch_count": (C.c_int64, [_ctx]),
+}
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+class SnpgError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libsnpgenie_cuda error {code}: {message}")
+        self.code = code

@@ -1,0 +1,640 @@
+// C-ABI of libsnpgenie_cuda.so: context, device memory, streams, and the
+// sequencing of kernels.  See include/snpgenie_cuda.h for the contract and the
+// reference blocks each entry point replaces.  There is no CPU fallback here:
+// every compute entry point runs the CUDA kernels or fails with SNPG_E_CUDA.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/snpgenie_cuda.h"
+#include "snpg_internal.h"
+
+using namespace snpg;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {  // grow-only device scratch
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct Group {
+    bool loaded = false;
+    uint64_t n = 0;
+    int64_t n_pad = 0;
+    DevBuf codes, hist, other;   // other: [2][count] min then max
+    bool has_codes = false;
+};
+
+}  // namespace
+
+struct snpg_ctx {
+    int device = 0;
+    uint64_t seed = 0;
+    std::string err;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_packed[2] = {nullptr, nullptr};
+    int rank = 0, world = 1;
+    bool keep_codes = true;
+    // annotation
+    int n_products = 0;
+    int64_t aln_len = 0;
+    std::vector<int64_t> full_ofs;    // [P+1] offsets on the global codon axis
+    std::vector<int64_t> local_ofs;   // [P+1] offsets inside this shard (clamped)
+    int64_t shard_first = 0, shard_count = 0;
+    int64_t col_lo = 0, col_hi = 0;   // alignment columns this shard touches, [lo, hi)
+    DevBuf d_map, d_local_ofs, d_full_ofs, d_tables;
+    // groups
+    Group groups[SNPG_MAX_GROUPS];
+    // scratch
+    DevBuf staging[2], s_stats, s_poly, s_nda, s_ndb, s_cmp, s_cons, s_sums, s_rep, s_se, s_misc, s_in;
+    int64_t launches = 0;
+    uint32_t call_id = 0;
+};
+
+namespace {
+
+int fail(snpg_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(ctx, call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail(ctx, SNPG_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define NEED(ctx, cond, code, ...) do { if (!(cond)) return fail(ctx, code, __VA_ARGS__); } while (0)
+
+int bind(snpg_ctx *ctx) {
+    CU(ctx, cudaSetDevice(ctx->device));
+    return SNPG_OK;
+}
+
+int check_group(snpg_ctx *ctx, int g) {
+    NEED(ctx, g >= 0 && g < SNPG_MAX_GROUPS, SNPG_E_ARG, "group %d out of range", g);
+    NEED(ctx, ctx->groups[g].loaded, SNPG_E_STATE, "group %d is not loaded", g);
+    return SNPG_OK;
+}
+int check_product(snpg_ctx *ctx, int p) {
+    NEED(ctx, ctx->n_products > 0, SNPG_E_STATE, "no products set");
+    NEED(ctx, p >= 0 && p < ctx->n_products, SNPG_E_ARG, "product %d out of range", p);
+    return SNPG_OK;
+}
+
+GroupView view_of(const snpg_ctx *ctx, const Group &g, int64_t c0) {
+    GroupView v;
+    v.hist = g.hist.as<uint32_t>() + c0 * kHistBins;
+    v.other_min = g.other.as<uint32_t>() + c0;
+    v.other_max = g.other.as<uint32_t>() + ctx->shard_count + c0;
+    v.codes = g.has_codes ? g.codes.as<uint8_t>() + c0 * g.n_pad : nullptr;
+    v.n = (int64_t)g.n;
+    v.n_pad = g.n_pad;
+    return v;
+}
+
+int prepare_group(snpg_ctx *ctx, Group &g, uint64_t n_seqs) {
+    g.loaded = false;
+    g.n = n_seqs;
+    g.n_pad = (int64_t)((n_seqs + kRowPad - 1) / kRowPad) * kRowPad;
+    const int64_t cnt = ctx->shard_count;
+    CU(ctx, g.codes.ensure((size_t)std::max<int64_t>(1, cnt * g.n_pad)));
+    CU(ctx, g.hist.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, cnt * kHistBins)));
+    CU(ctx, g.other.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, 2 * cnt)));
+    CU(ctx, cudaMemsetAsync(g.hist.p, 0, sizeof(uint32_t) * (size_t)(cnt * kHistBins), ctx->stream));
+    CU(ctx, cudaMemsetAsync(g.other.p, 0xFF, sizeof(uint32_t) * (size_t)cnt, ctx->stream));
+    CU(ctx, cudaMemsetAsync(g.other.as<uint32_t>() + cnt, 0, sizeof(uint32_t) * (size_t)cnt, ctx->stream));
+    g.has_codes = true;
+    return SNPG_OK;
+}
+
+int finish_group(snpg_ctx *ctx, Group &g) {
+    launch_hist(g.codes.as<uint8_t>(), g.n_pad, ctx->shard_count, g.hist.as<uint32_t>(), ctx->stream);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!ctx->keep_codes) { g.codes.release(); g.has_codes = false; }
+    g.loaded = true;
+    return SNPG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *snpg_version(void) { return "snpgenie-b200 0.1 (sm_100a)"; }
+
+const char *snpg_last_error(const snpg_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int snpg_get_tables(double *sites, double *diffs) {
+    if (!sites || !diffs) return SNPG_E_ARG;
+    build_tables(sites, diffs);
+    return SNPG_OK;
+}
+
+int snpg_create(snpg_ctx **out, int device, uint64_t seed) {
+    if (!out) return fail(nullptr, SNPG_E_ARG, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, SNPG_E_CUDA, "no CUDA device available (%s); libsnpgenie_cuda has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, SNPG_E_ARG, "device %d out of range (have %d)", device, count);
+    snpg_ctx *ctx = new snpg_ctx();
+    ctx->device = device;
+    ctx->seed = seed;
+    auto bail = [&](const char *what, cudaError_t ce) {
+        fail(nullptr, SNPG_E_CUDA, "%s failed: %s", what, cudaGetErrorString(ce));
+        delete ctx;
+        return SNPG_E_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    for (int i = 0; i < 2; i++) {
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_packed[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    }
+    std::vector<double> tab(128 + 8192);
+    build_tables(tab.data(), tab.data() + 128);
+    if ((e = ctx->d_tables.ensure(sizeof(double) * tab.size())) != cudaSuccess) return bail("cudaMalloc(tables)", e);
+    if ((e = cudaMemcpy(ctx->d_tables.p, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+        return bail("cudaMemcpy(tables)", e);
+    *out = ctx;
+    return SNPG_OK;
+}
+
+void snpg_destroy(snpg_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    for (auto &g : ctx->groups) { g.codes.release(); g.hist.release(); g.other.release(); }
+    DevBuf *bufs[] = {&ctx->d_map, &ctx->d_local_ofs, &ctx->d_full_ofs, &ctx->d_tables, &ctx->staging[0], &ctx->staging[1],
+                      &ctx->s_stats, &ctx->s_poly, &ctx->s_nda, &ctx->s_ndb, &ctx->s_cmp, &ctx->s_cons, &ctx->s_sums,
+                      &ctx->s_rep, &ctx->s_se, &ctx->s_misc, &ctx->s_in};
+    for (DevBuf *b : bufs) b->release();
+    for (int i = 0; i < 2; i++) {
+        if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
+        if (ctx->ev_packed[i]) cudaEventDestroy(ctx->ev_packed[i]);
+    }
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+}
+
+int snpg_set_option(snpg_ctx *ctx, int option, int64_t value) {
+    if (!ctx) return SNPG_E_ARG;
+    if (option == SNPG_OPT_KEEP_CODES) { ctx->keep_codes = value != 0; return SNPG_OK; }
+    return fail(ctx, SNPG_E_ARG, "unknown option %d", option);
+}
+
+int snpg_set_shard(snpg_ctx *ctx, int rank, int world) {
+    if (!ctx) return SNPG_E_ARG;
+    NEED(ctx, world >= 1 && rank >= 0 && rank < world, SNPG_E_ARG, "bad shard %d/%d", rank, world);
+    NEED(ctx, ctx->n_products == 0, SNPG_E_STATE, "set_shard must precede set_products");
+    ctx->rank = rank;
+    ctx->world = world;
+    return SNPG_OK;
+}
+
+int snpg_set_products(snpg_ctx *ctx, int n_products, const int64_t *seg_ofs, const int64_t *seg_start,
+                      const int64_t *seg_stop, const int8_t *strand, int64_t aln_len) {
+    if (!ctx) return SNPG_E_ARG;
+    NEED(ctx, n_products > 0 && seg_ofs && seg_start && seg_stop && strand, SNPG_E_ARG, "bad product arguments");
+    NEED(ctx, aln_len > 0 && aln_len < (int64_t)1 << 31, SNPG_E_ARG, "alignment length %lld unsupported", (long long)aln_len);
+    if (int rc = bind(ctx)) return rc;
+    for (auto &g : ctx->groups) g.loaded = false;  // maps change: loaded groups are stale
+
+    std::vector<CodonMap> map_all;
+    std::vector<int64_t> full_ofs(n_products + 1, 0);
+    for (int p = 0; p < n_products; p++) {
+        const int64_t s0 = seg_ofs[p], s1 = seg_ofs[p + 1];
+        NEED(ctx, s1 > s0, SNPG_E_INPUT, "product %d has no CDS segment", p);
+        std::vector<int> order((size_t)(s1 - s0));
+        for (size_t i = 0; i < order.size(); i++) order[i] = (int)(s0 + i);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return seg_start[a] < seg_start[b]; });  // wg:1608
+        std::vector<int32_t> pos;
+        for (int s : order) {
+            NEED(ctx, seg_start[s] >= 1 && seg_stop[s] >= seg_start[s] && seg_stop[s] <= aln_len, SNPG_E_INPUT,
+                 "product %d: segment %lld..%lld outside the alignment (length %lld)", p, (long long)seg_start[s],
+                 (long long)seg_stop[s], (long long)aln_len);
+            for (int64_t x = seg_start[s]; x <= seg_stop[s]; x++) pos.push_back((int32_t)(x - 1));
+        }
+        NEED(ctx, pos.size() % 3 == 0, SNPG_E_INPUT,
+             "product %d: the CDS coordinates do not yield a set of complete codons (%zu nucleotides)", p, pos.size());  // wg:1596
+        const bool minus = strand[p] < 0;
+        if (minus) std::reverse(pos.begin(), pos.end());
+        for (size_t k = 0; k < pos.size(); k += 3) map_all.push_back(CodonMap{pos[k], pos[k + 1], pos[k + 2], minus ? 1 : 0});
+        full_ofs[p + 1] = (int64_t)map_all.size();
+    }
+    const int64_t total = (int64_t)map_all.size();
+    ctx->shard_first = total * ctx->rank / ctx->world;
+    ctx->shard_count = total * (ctx->rank + 1) / ctx->world - ctx->shard_first;
+    ctx->n_products = n_products;
+    ctx->aln_len = aln_len;
+    ctx->full_ofs = full_ofs;
+    ctx->local_ofs.assign(n_products + 1, 0);
+    for (int p = 0; p <= n_products; p++)
+        ctx->local_ofs[p] = std::min(std::max(full_ofs[p] - ctx->shard_first, (int64_t)0), ctx->shard_count);
+
+    // columns this shard reads; positions become relative to col_lo
+    int64_t lo = aln_len, hi = 0;
+    for (int64_t c = ctx->shard_first; c < ctx->shard_first + ctx->shard_count; c++) {
+        const CodonMap &m = map_all[(size_t)c];
+        lo = std::min<int64_t>(lo, std::min(m.p0, std::min(m.p1, m.p2)));
+        hi = std::max<int64_t>(hi, std::max(m.p0, std::max(m.p1, m.p2)) + 1);
+    }
+    if (ctx->shard_count == 0) { lo = 0; hi = 0; }
+    ctx->col_lo = lo;
+    ctx->col_hi = hi;
+    std::vector<CodonMap> local(map_all.begin() + ctx->shard_first, map_all.begin() + ctx->shard_first + ctx->shard_count);
+    for (auto &m : local) { m.p0 -= (int32_t)lo; m.p1 -= (int32_t)lo; m.p2 -= (int32_t)lo; }
+
+    CU(ctx, ctx->d_map.ensure(sizeof(CodonMap) * std::max<size_t>(1, local.size())));
+    CU(ctx, ctx->d_local_ofs.ensure(sizeof(int64_t) * (n_products + 1)));
+    CU(ctx, ctx->d_full_ofs.ensure(sizeof(int64_t) * (n_products + 1)));
+    if (!local.empty()) CU(ctx, cudaMemcpy(ctx->d_map.p, local.data(), sizeof(CodonMap) * local.size(), cudaMemcpyHostToDevice));
+    CU(ctx, cudaMemcpy(ctx->d_local_ofs.p, ctx->local_ofs.data(), sizeof(int64_t) * (n_products + 1), cudaMemcpyHostToDevice));
+    CU(ctx, cudaMemcpy(ctx->d_full_ofs.p, full_ofs.data(), sizeof(int64_t) * (n_products + 1), cudaMemcpyHostToDevice));
+    return SNPG_OK;
+}
+
+int snpg_n_products(const snpg_ctx *ctx) { return ctx ? ctx->n_products : SNPG_E_ARG; }
+
+int snpg_n_codons(const snpg_ctx *ctx, int product, int64_t *out) {
+    if (!ctx || !out || product < 0 || product >= ctx->n_products) return SNPG_E_ARG;
+    *out = ctx->full_ofs[product + 1] - ctx->full_ofs[product];
+    return SNPG_OK;
+}
+
+int snpg_shard_range(const snpg_ctx *ctx, int64_t *first, int64_t *count, int64_t *total) {
+    if (!ctx || ctx->n_products == 0) return SNPG_E_STATE;
+    if (first) *first = ctx->shard_first;
+    if (count) *count = ctx->shard_count;
+    if (total) *total = ctx->full_ofs[ctx->n_products];
+    return SNPG_OK;
+}
+
+// Local slice [c0, c0+C) of a product inside this shard.
+static void product_slice(const snpg_ctx *ctx, int product, int64_t *c0, int64_t *C) {
+    *c0 = ctx->local_ofs[product];
+    *C = ctx->local_ofs[product + 1] - ctx->local_ofs[product];
+}
+
+int snpg_load_group(snpg_ctx *ctx, int group, const uint8_t *bases, uint64_t n_seqs, uint64_t aln_len, uint64_t row_stride) {
+    if (!ctx) return SNPG_E_ARG;
+    NEED(ctx, ctx->n_products > 0, SNPG_E_STATE, "set products before loading a group");
+    NEED(ctx, group >= 0 && group < SNPG_MAX_GROUPS, SNPG_E_ARG, "group %d out of range", group);
+    NEED(ctx, bases && n_seqs > 0 && n_seqs < ((uint64_t)1 << 31), SNPG_E_ARG, "bad alignment arguments");
+    NEED(ctx, (int64_t)aln_len == ctx->aln_len, SNPG_E_INPUT,
+         "alignment length %llu differs from the annotation's %lld", (unsigned long long)aln_len, (long long)ctx->aln_len);
+    NEED(ctx, row_stride >= aln_len, SNPG_E_ARG, "row_stride < aln_len");
+    if (int rc = bind(ctx)) return rc;
+    Group &g = ctx->groups[group];
+    if (int rc = prepare_group(ctx, g, n_seqs)) return rc;
+
+    // Row blocks: H2D of block i+1 overlaps packing of block i (two staging buffers).
+    const int64_t width = ctx->col_hi - ctx->col_lo;
+    if (width > 0) {
+        const int64_t pitch = (width + 127) / 128 * 128;
+        int64_t rows_per = std::max<int64_t>(kRowPad, ((int64_t)48 << 20) / pitch / kRowPad * kRowPad);
+        rows_per = std::min<int64_t>(rows_per, (int64_t)((n_seqs + kRowPad - 1) / kRowPad * kRowPad));
+        for (int i = 0; i < 2; i++) CU(ctx, ctx->staging[i].ensure((size_t)(rows_per * pitch)));
+        int64_t blk = 0;
+        for (int64_t r0 = 0; r0 < (int64_t)n_seqs; r0 += rows_per, blk++) {
+            const int b = (int)(blk & 1);
+            const int64_t rows = std::min<int64_t>(rows_per, (int64_t)n_seqs - r0);
+            if (blk >= 2) CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_packed[b], 0));
+            CU(ctx, cudaMemcpy2DAsync(ctx->staging[b].p, (size_t)pitch, bases + (size_t)r0 * row_stride + ctx->col_lo,
+                                      (size_t)row_stride, (size_t)width, (size_t)rows, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CU(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
+            CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
+            launch_pack(ctx->staging[b].as<uint8_t>(), pitch, rows, r0, ctx->d_map.as<CodonMap>(), ctx->shard_count,
+                        g.codes.as<uint8_t>(), g.n_pad, g.other.as<uint32_t>(), g.other.as<uint32_t>() + ctx->shard_count,
+                        ctx->stream);
+            ctx->launches++;
+            CU(ctx, cudaGetLastError());
+            CU(ctx, cudaEventRecord(ctx->ev_packed[b], ctx->stream));
+        }
+    }
+    return finish_group(ctx, g);
+}
+
+int snpg_load_group_device(snpg_ctx *ctx, int group, const uint8_t *d_bases, uint64_t n_seqs, uint64_t aln_len,
+                           uint64_t row_stride) {
+    if (!ctx) return SNPG_E_ARG;
+    NEED(ctx, ctx->n_products > 0, SNPG_E_STATE, "set products before loading a group");
+    NEED(ctx, group >= 0 && group < SNPG_MAX_GROUPS, SNPG_E_ARG, "group %d out of range", group);
+    NEED(ctx, d_bases && n_seqs > 0 && n_seqs < ((uint64_t)1 << 31), SNPG_E_ARG, "bad alignment arguments");
+    NEED(ctx, (int64_t)aln_len == ctx->aln_len, SNPG_E_INPUT,
+         "alignment length %llu differs from the annotation's %lld", (unsigned long long)aln_len, (long long)ctx->aln_len);
+    NEED(ctx, row_stride >= aln_len, SNPG_E_ARG, "row_stride < aln_len");
+    if (int rc = bind(ctx)) return rc;
+    Group &g = ctx->groups[group];
+    if (int rc = prepare_group(ctx, g, n_seqs)) return rc;
+    const int64_t rows_per = (int64_t)4 << 20;  // keeps gridDim.y < 65536
+    for (int64_t r0 = 0; r0 < (int64_t)n_seqs && ctx->shard_count > 0; r0 += rows_per) {
+        const int64_t rows = std::min<int64_t>(rows_per, (int64_t)n_seqs - r0);
+        launch_pack(d_bases + (size_t)r0 * row_stride + ctx->col_lo, (int64_t)row_stride, rows, r0, ctx->d_map.as<CodonMap>(),
+                    ctx->shard_count, g.codes.as<uint8_t>(), g.n_pad, g.other.as<uint32_t>(),
+                    g.other.as<uint32_t>() + ctx->shard_count, ctx->stream);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
+    }
+    return finish_group(ctx, g);
+}
+
+int snpg_drop_group(snpg_ctx *ctx, int group) {
+    if (!ctx || group < 0 || group >= SNPG_MAX_GROUPS) return SNPG_E_ARG;
+    if (int rc = bind(ctx)) return rc;
+    Group &g = ctx->groups[group];
+    g.codes.release(); g.hist.release(); g.other.release();
+    g.loaded = false; g.has_codes = false;
+    return SNPG_OK;
+}
+
+int snpg_group_size(const snpg_ctx *ctx, int group, uint64_t *n_seqs) {
+    if (!ctx || group < 0 || group >= SNPG_MAX_GROUPS || !n_seqs || !ctx->groups[group].loaded) return SNPG_E_ARG;
+    *n_seqs = ctx->groups[group].n;
+    return SNPG_OK;
+}
+
+int snpg_get_codon_indices(snpg_ctx *ctx, int group, int product, uint8_t *out) {
+    if (!ctx || !out) return SNPG_E_ARG;
+    if (int rc = check_group(ctx, group)) return rc;
+    if (int rc = check_product(ctx, product)) return rc;
+    if (int rc = bind(ctx)) return rc;
+    Group &g = ctx->groups[group];
+    NEED(ctx, g.has_codes, SNPG_E_STATE, "codon matrix was not kept (SNPG_OPT_KEEP_CODES=0)");
+    int64_t c0, C;
+    product_slice(ctx, product, &c0, &C);
+    if (C == 0) return SNPG_OK;
+    const size_t bytes = (size_t)g.n * (size_t)C;
+    CU(ctx, ctx->s_misc.ensure(bytes));
+    launch_untranspose(g.codes.as<uint8_t>(), g.n_pad, (int64_t)g.n, c0, C, ctx->s_misc.as<uint8_t>(), ctx->stream);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(out, ctx->s_misc.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SNPG_OK;
+}
+
+int snpg_get_hist(snpg_ctx *ctx, int group, int product, uint32_t *out, uint8_t *other_distinct) {
+    if (!ctx || !out) return SNPG_E_ARG;
+    if (int rc = check_group(ctx, group)) return rc;
+    if (int rc = check_product(ctx, product)) return rc;
+    if (int rc = bind(ctx)) return rc;
+    Group &g = ctx->groups[group];
+    int64_t c0, C;
+    product_slice(ctx, product, &c0, &C);
+    if (C == 0) return SNPG_OK;
+    CU(ctx, cudaMemcpyAsync(out, g.hist.as<uint32_t>() + c0 * kHistBins, sizeof(uint32_t) * (size_t)(C * kHistBins),
+                            cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<uint32_t> lo, hi;
+    if (other_distinct) {
+        lo.resize((size_t)C); hi.resize((size_t)C);
+        CU(ctx, cudaMemcpyAsync(lo.data(), g.other.as<uint32_t>() + c0, sizeof(uint32_t) * (size_t)C, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(hi.data(), g.other.as<uint32_t>() + ctx->shard_count + c0, sizeof(uint32_t) * (size_t)C,
+                                cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (other_distinct)
+        for (int64_t c = 0; c < C; c++) other_distinct[c] = (lo[(size_t)c] != kOtherNone && lo[(size_t)c] != hi[(size_t)c]) ? 1 : 0;
+    return SNPG_OK;
+}
+
+// shared by snpg_within / snpg_between: run K3 on [c0, c0+C) and copy what was asked for
+static int run_stats(snpg_ctx *ctx, bool between, const Group &ga, const Group &gb, int64_t c0, int64_t C, uint8_t *poly,
+                     uint32_t *nda, uint32_t *ndb, uint64_t *cmp, double *stats4, uint8_t *cons) {
+    if (C == 0) return SNPG_OK;
+    CU(ctx, ctx->s_poly.ensure((size_t)C));
+    CU(ctx, ctx->s_cons.ensure((size_t)C));
+    CU(ctx, ctx->s_nda.ensure(sizeof(uint32_t) * (size_t)C));
+    CU(ctx, ctx->s_ndb.ensure(sizeof(uint32_t) * (size_t)C));
+    CU(ctx, ctx->s_cmp.ensure(sizeof(uint64_t) * (size_t)C));
+    CU(ctx, ctx->s_stats.ensure(sizeof(double) * 4 * (size_t)C));
+    StatsOut o{ctx->s_poly.as<uint8_t>(), ctx->s_nda.as<uint32_t>(), ctx->s_ndb.as<uint32_t>(),
+               ctx->s_cmp.as<unsigned long long>(), ctx->s_stats.as<double>(), ctx->s_cons.as<uint8_t>()};
+    if (between) launch_between_stats(view_of(ctx, ga, c0), view_of(ctx, gb, c0), C, ctx->d_tables.as<double>(), o, ctx->stream);
+    else launch_within_stats(view_of(ctx, ga, c0), C, ctx->d_tables.as<double>(), o, ctx->stream);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    if (poly) CU(ctx, cudaMemcpyAsync(poly, o.poly, (size_t)C, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cons) CU(ctx, cudaMemcpyAsync(cons, o.conserved, (size_t)C, cudaMemcpyDeviceToHost, ctx->stream));
+    if (nda) CU(ctx, cudaMemcpyAsync(nda, o.ndef_a, sizeof(uint32_t) * (size_t)C, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ndb) CU(ctx, cudaMemcpyAsync(ndb, o.ndef_b, sizeof(uint32_t) * (size_t)C, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cmp) CU(ctx, cudaMemcpyAsync(cmp, o.comparisons, sizeof(uint64_t) * (size_t)C, cudaMemcpyDeviceToHost, ctx->stream));
+    if (stats4) CU(ctx, cudaMemcpyAsync(stats4, o.stats4, sizeof(double) * 4 * (size_t)C, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SNPG_OK;
+}
+
+int snpg_within(snpg_ctx *ctx, int group, int product, uint8_t *poly, uint32_t *n_defined, uint64_t *comparisons,
+                double *stats4, uint8_t *conserved_code) {
+    if (!ctx) return SNPG_E_ARG;
+    if (int rc = check_group(ctx, group)) return rc;
+    if (int rc = check_product(ctx, product)) return rc;
+    if (int rc = bind(ctx)) return rc;
+    int64_t c0, C;
+    product_slice(ctx, product, &c0, &C);
+    const Group &g = ctx->groups[group];
+    return run_stats(ctx, false, g, g, c0, C, poly, n_defined, nullptr, comparisons, stats4, conserved_code);
+}
+
+int snpg_between(snpg_ctx *ctx, int group_a, int group_b, int product, uint8_t *poly, uint32_t *n_defined_a,
+                 uint32_t *n_defined_b, uint64_t *comparisons, double *stats4, uint8_t *conserved_code) {
+    if (!ctx) return SNPG_E_ARG;
+    if (int rc = check_group(ctx, group_a)) return rc;
+    if (int rc = check_group(ctx, group_b)) return rc;
+    if (int rc = check_product(ctx, product)) return rc;
+    if (int rc = bind(ctx)) return rc;
+    int64_t c0, C;
+    product_slice(ctx, product, &c0, &C);
+    return run_stats(ctx, true, ctx->groups[group_a], ctx->groups[group_b], c0, C, poly, n_defined_a, n_defined_b, comparisons,
+                     stats4, conserved_code);
+}
+
+// host stats4 (+ optional keep mask) -> device scratch s_in, masked
+static int upload_stats(snpg_ctx *ctx, const double *stats4, const uint8_t *keep, int64_t C) {
+    CU(ctx, ctx->s_in.ensure(sizeof(double) * 4 * (size_t)C));
+    if (keep) {
+        std::vector<double> m((size_t)C * 4);
+        for (int64_t c = 0; c < C; c++)
+            for (int q = 0; q < 4; q++) m[(size_t)(4 * c + q)] = keep[c] ? stats4[4 * c + q] : 0.0;
+        CU(ctx, cudaMemcpy(ctx->s_in.p, m.data(), sizeof(double) * m.size(), cudaMemcpyHostToDevice));
+    } else {
+        CU(ctx, cudaMemcpy(ctx->s_in.p, stats4, sizeof(double) * 4 * (size_t)C, cudaMemcpyHostToDevice));
+    }
+    return SNPG_OK;
+}
+
+int snpg_bootstrap_product(snpg_ctx *ctx, const double *stats4, const uint8_t *keep, int64_t C, int64_t B, double *sums_out,
+                           double *se_out) {
+    if (!ctx) return SNPG_E_ARG;
+    NEED(ctx, stats4 && C > 0 && C < ((int64_t)1 << 31) - 1 && B >= 2, SNPG_E_ARG, "bad bootstrap arguments (C=%lld, B=%lld)",
+         (long long)C, (long long)B);
+    if (int rc = bind(ctx)) return rc;
+    if (int rc = upload_stats(ctx, stats4, keep, C)) return rc;
+    const int64_t ofs[2] = {0, C};
+    CU(ctx, ctx->s_misc.ensure(sizeof ofs));
+    CU(ctx, cudaMemcpy(ctx->s_misc.p, ofs, sizeof ofs, cudaMemcpyHostToDevice));
+    CU(ctx, ctx->s_rep.ensure(sizeof(double) * 4 * (size_t)B));
+    CU(ctx, ctx->s_se.ensure(sizeof(double) * 6));
+    const uint32_t sid = 0x10000u + ctx->call_id++;
+    launch_bootstrap(ctx->s_in.as<double>(), ctx->s_misc.as<int64_t>(), 1, 0, B, ctx->seed, sid, ctx->s_rep.as<double>(), ctx->stream);
+    launch_rep_moments(ctx->s_rep.as<double>(), 1, B, ctx->s_se.as<double>(), ctx->stream);
+    ctx->launches += 2;
+    CU(ctx, cudaGetLastError());
+    if (sums_out) CU(ctx, cudaMemcpyAsync(sums_out, ctx->s_rep.p, sizeof(double) * 4 * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+    if (se_out) CU(ctx, cudaMemcpyAsync(se_out, ctx->s_se.p, sizeof(double) * 6, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SNPG_OK;
+}
+
+int snpg_windows(snpg_ctx *ctx, const double *stats4, const uint8_t *keep, int64_t C, int64_t W, int64_t step, int64_t B,
+                 double *win_sums, double *win_se, int64_t *nwin_out) {
+    if (!ctx) return SNPG_E_ARG;
+    NEED(ctx, stats4 && C > 0 && W >= 1 && step >= 1, SNPG_E_ARG, "bad window arguments");
+    NEED(ctx, W <= C, SNPG_E_INPUT, "not enough codons (%lld) for a sliding window of %lld", (long long)C, (long long)W);  // wgp:300
+    NEED(ctx, W < ((int64_t)1 << 31), SNPG_E_ARG, "window too large");
+    if (int rc = bind(ctx)) return rc;
+    const int64_t nwin = (C - W) / step + 1;
+    if (nwin_out) *nwin_out = nwin;
+    if (!win_sums && !win_se) return SNPG_OK;
+    if (int rc = upload_stats(ctx, stats4, keep, C)) return rc;
+    if (win_sums) {
+        CU(ctx, ctx->s_sums.ensure(sizeof(double) * 4 * (size_t)nwin));
+        launch_window_sums(ctx->s_in.as<double>(), W, step, nwin, ctx->s_sums.as<double>(), ctx->stream);
+        ctx->launches++;
+        CU(ctx, cudaGetLastError());
+        CU(ctx, cudaMemcpyAsync(win_sums, ctx->s_sums.p, sizeof(double) * 4 * (size_t)nwin, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (win_se && B >= 2) {
+        const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(nwin, ((int64_t)256 << 20) / (32 * B)));
+        CU(ctx, ctx->s_rep.ensure(sizeof(double) * 4 * (size_t)(batch * B)));
+        CU(ctx, ctx->s_se.ensure(sizeof(double) * 6 * (size_t)batch));
+        std::vector<double> se6((size_t)batch * 6);
+        const uint32_t sid = 0x20000u + ctx->call_id++;
+        for (int64_t w0 = 0; w0 < nwin; w0 += batch) {
+            const int64_t nb = std::min(batch, nwin - w0);
+            launch_window_bootstrap(ctx->s_in.as<double>(), W, step, w0, nb, B, ctx->seed, sid, ctx->s_rep.as<double>(), ctx->stream);
+            launch_rep_moments(ctx->s_rep.as<double>(), nb, B, ctx->s_se.as<double>(), ctx->stream);
+            ctx->launches += 2;
+            CU(ctx, cudaGetLastError());
+            CU(ctx, cudaMemcpyAsync(se6.data(), ctx->s_se.p, sizeof(double) * 6 * (size_t)nb, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            for (int64_t k = 0; k < nb; k++)
+                for (int q = 0; q < 3; q++) win_se[3 * (w0 + k) + q] = se6[(size_t)(6 * k + q)];
+        }
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SNPG_OK;
+}
+
+int snpg_within_stats_device(snpg_ctx *ctx, int group, double *d_stats4) {
+    if (!ctx || !d_stats4) return SNPG_E_ARG;
+    if (int rc = check_group(ctx, group)) return rc;
+    if (int rc = bind(ctx)) return rc;
+    const Group &g = ctx->groups[group];
+    StatsOut o{nullptr, nullptr, nullptr, nullptr, d_stats4, nullptr};
+    launch_within_stats(view_of(ctx, g, 0), ctx->shard_count, ctx->d_tables.as<double>(), o, ctx->stream);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SNPG_OK;
+}
+
+int snpg_bootstrap_all_device(snpg_ctx *ctx, const double *d_stats4_full, int64_t b_first, int64_t b_count, double *d_rep_out) {
+    if (!ctx || !d_stats4_full || !d_rep_out) return SNPG_E_ARG;
+    NEED(ctx, ctx->n_products > 0, SNPG_E_STATE, "no products set");
+    NEED(ctx, b_first >= 0 && b_count > 0, SNPG_E_ARG, "bad replicate range");
+    if (int rc = bind(ctx)) return rc;
+    launch_bootstrap(d_stats4_full, ctx->d_full_ofs.as<int64_t>(), ctx->n_products, b_first, b_count, ctx->seed, 0x30000u, d_rep_out,
+                     ctx->stream);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SNPG_OK;
+}
+
+int snpg_product_sums_device(snpg_ctx *ctx, const double *d_stats4_full, double *prod_sums) {
+    if (!ctx || !d_stats4_full || !prod_sums) return SNPG_E_ARG;
+    NEED(ctx, ctx->n_products > 0, SNPG_E_STATE, "no products set");
+    if (int rc = bind(ctx)) return rc;
+    CU(ctx, ctx->s_sums.ensure(sizeof(double) * 4 * (size_t)ctx->n_products));
+    launch_product_sums(d_stats4_full, ctx->d_full_ofs.as<int64_t>(), ctx->n_products, ctx->s_sums.as<double>(), ctx->stream);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(prod_sums, ctx->s_sums.p, sizeof(double) * 4 * (size_t)ctx->n_products, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SNPG_OK;
+}
+
+int snpg_rep_moments_device(snpg_ctx *ctx, const double *d_rep, int64_t n_items, int64_t B, double *se_out) {
+    if (!ctx || !d_rep || !se_out || n_items <= 0 || B < 2) return SNPG_E_ARG;
+    if (int rc = bind(ctx)) return rc;
+    CU(ctx, ctx->s_se.ensure(sizeof(double) * 6 * (size_t)n_items));
+    launch_rep_moments(d_rep, n_items, B, ctx->s_se.as<double>(), ctx->stream);
+    ctx->launches++;
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(se_out, ctx->s_se.p, sizeof(double) * 6 * (size_t)n_items, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SNPG_OK;
+}
+
+int snpg_within_all(snpg_ctx *ctx, int group, int64_t B, double *prod_sums, double *prod_se) {
+    if (!ctx) return SNPG_E_ARG;
+    if (int rc = check_group(ctx, group)) return rc;
+    if (int rc = bind(ctx)) return rc;
+    const Group &g = ctx->groups[group];
+    const int P = ctx->n_products;
+    const int64_t cnt = ctx->shard_count;
+    CU(ctx, ctx->s_stats.ensure(sizeof(double) * 4 * (size_t)std::max<int64_t>(1, cnt)));
+    CU(ctx, ctx->s_sums.ensure(sizeof(double) * 4 * (size_t)P));
+    StatsOut o{nullptr, nullptr, nullptr, nullptr, ctx->s_stats.as<double>(), nullptr};
+    launch_within_stats(view_of(ctx, g, 0), cnt, ctx->d_tables.as<double>(), o, ctx->stream);
+    launch_product_sums(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), P, ctx->s_sums.as<double>(), ctx->stream);
+    ctx->launches += 2;
+    const bool boot = prod_se && B >= 2;
+    if (boot) {
+        CU(ctx, ctx->s_rep.ensure(sizeof(double) * 4 * (size_t)(B * P)));
+        CU(ctx, ctx->s_se.ensure(sizeof(double) * 6 * (size_t)P));
+        launch_bootstrap(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), P, 0, B, ctx->seed, 0x40000u + ctx->call_id++,
+                         ctx->s_rep.as<double>(), ctx->stream);
+        launch_rep_moments(ctx->s_rep.as<double>(), P, B, ctx->s_se.as<double>(), ctx->stream);
+        ctx->launches += 2;
+    }
+    CU(ctx, cudaGetLastError());
+    if (prod_sums) CU(ctx, cudaMemcpyAsync(prod_sums, ctx->s_sums.p, sizeof(double) * 4 * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+    if (boot) CU(ctx, cudaMemcpyAsync(prod_se, ctx->s_se.p, sizeof(double) * 6 * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SNPG_OK;
+}
+
+int64_t snpg_launch_count(const snpg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,640 @@
+// sm_100a kernels for SNPGenie's within-/between-group Nei-Gojobori path.
+//
+// K1 k_pack        alignment bytes -> 1-byte codon codes (transposed [codon][seq])
+// K2 k_hist        per-codon 66-bin histogram over sequences
+// K3 k_stats       per-codon N/S sites and differences from histograms
+// K4 k_bootstrap   whole-product codon resampling (Philox4x32-10)
+// K5 k_window_*    sliding-window sums and per-window resampling
+// K6 k_rep_moments two-pass SD of per-replicate dN, dS, dN-dS (+ Jukes-Cantor)
+//
+// The reference blocks each kernel replaces are cited at the kernels.  All
+// arithmetic that reaches an output table is FP64; K1/K2 are byte/integer work
+// and HBM-bound (see DESIGN.md for the algorithmic bytes of each).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "snpg_internal.h"
+
+namespace snpg {
+
+namespace {
+
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint4 ld_stream_v4(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------
+// Residue classification.  Normalisation follows the reference ingest: uc, then
+// U->T (snpgenie_within_group.pl:231-232); on the '-' strand the residue is
+// first complemented with tr/ACGT/TGCA/ exactly as fasta2revcom.pl:77-79 does
+// (so U is NOT complemented there and then becomes T).
+// class: 0..3 = A,C,G,T; 4 = undefined (N or '-'; wg:493,498); 5 = other.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint8_t norm_char(uint8_t c, int minus) {
+    if (c >= 'a' && c <= 'z') c -= 32;
+    if (minus) {
+        if (c == 'A') c = 'T';
+        else if (c == 'C') c = 'G';
+        else if (c == 'G') c = 'C';
+        else if (c == 'T') c = 'A';
+    }
+    if (c == 'U') c = 'T';
+    return c;
+}
+__device__ __forceinline__ uint8_t class_of(uint8_t n) {
+    return n == 'A' ? 0 : n == 'C' ? 1 : n == 'G' ? 2 : n == 'T' ? 3 : (n == 'N' || n == '-') ? 4 : 5;
+}
+
+// ---------------------------------------------------------------------------
+// K1: codon packing.  Replaces product extraction + codon split
+// (wg:286-329, :417-454; bg:238-298, :351-388) and the per-comparison
+// definedness regexes (wg:493,498,601,604).  A block handles 32 codons x 128
+// sequences: lanes run along codons when reading (a '+' CDS makes the three byte
+// loads of a warp fall in one or two 128-B lines of the row), the tile is
+// turned in shared memory, and each codon's 128 codes leave as 16-B stores.
+// ---------------------------------------------------------------------------
+constexpr int kPackCodons = 32;
+constexpr int kPackRows = 128;
+constexpr int kPackPitch = 144;  // bytes, multiple of 16
+
+__global__ void __launch_bounds__(256)
+k_pack(const uint8_t *__restrict__ aln, int64_t stride, int64_t n_rows, int64_t row0,
+       const CodonMap *__restrict__ map, int64_t n_codons, uint8_t *__restrict__ codes, int64_t n_pad,
+       uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max)
+{
+    __shared__ uint8_t lut_chr[2][256];
+    __shared__ uint8_t lut_cls[2][256];
+    __shared__ __align__(16) uint8_t tile[kPackCodons][kPackPitch];
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int s = 0; s < 2; s++) {
+        uint8_t n = norm_char((uint8_t)t, s);
+        lut_chr[s][t] = n;
+        lut_cls[s][t] = class_of(n);
+    }
+    __syncthreads();
+
+    const int64_t c = (int64_t)blockIdx.x * kPackCodons + lane;
+    const int64_t tile_row0 = (int64_t)blockIdx.y * kPackRows;
+    const bool live = c < n_codons;
+    CodonMap m = {0, 0, 0, 0};
+    if (live) m = map[c];
+    const int s = m.minus ? 1 : 0;
+
+#pragma unroll 4
+    for (int i = 0; i < 16; i++) {
+        const int lr = warp * 16 + i;
+        const int64_t r = tile_row0 + lr;
+        uint8_t code = kCodePad;
+        if (live && r < n_rows) {
+            const uint8_t *row = aln + r * stride;
+            const uint8_t b0 = row[m.p0], b1 = row[m.p1], b2 = row[m.p2];
+            const uint8_t k0 = lut_cls[s][b0], k1 = lut_cls[s][b1], k2 = lut_cls[s][b2];
+            const uint8_t worst = max(k0, max(k1, k2));
+            if (worst < 4) {
+                code = (uint8_t)(k0 * 16 + k1 * 4 + k2);
+            } else if (k0 == 4 || k1 == 4 || k2 == 4) {
+                code = kCodeUndef;
+            } else {
+                code = kCodeOther;
+                const uint32_t key = ((uint32_t)lut_chr[s][b0] << 16) | ((uint32_t)lut_chr[s][b1] << 8) | lut_chr[s][b2];
+                atomicMin(&other_min[c], key);
+                atomicMax(&other_max[c], key);
+            }
+        }
+        tile[lane][lr] = code;
+    }
+    __syncthreads();
+
+    const int j = t >> 3, v = t & 7;
+    const int64_t cj = (int64_t)blockIdx.x * kPackCodons + j;
+    if (cj < n_codons) {
+        const uint4 val = *reinterpret_cast<const uint4 *>(&tile[j][v * 16]);
+        *reinterpret_cast<uint4 *>(codes + cj * n_pad + row0 + tile_row0 + v * 16) = val;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2: per-codon histogram.  Replaces the polymorphism pre-check (wg:469-541;
+// bg:472-544) and the O(n^2) pair counting (wg:596-609; bg:649-667): the 66
+// counts of a column determine every per-codon output.
+// One warp owns (column, row chunk).  Lanes stream 16-byte vectors of the
+// column; each 4-code word is XORed with the chunk's first code replicated,
+// and only the bytes that differ go to the warp's private shared-memory
+// histogram.  The matching code's count is rows - mismatches, so a conserved
+// column costs three ALU ops per 4 sequences and no atomics at all.
+// Algorithmic traffic: 1 byte per (sequence, codon) read + 264 B per codon written.
+// ---------------------------------------------------------------------------
+constexpr int kHistWarps = 8;
+constexpr int kHistChunkRows = 8192;
+
+__device__ __forceinline__ void hist_word(uint32_t w, uint32_t g4, uint32_t *wh, uint32_t &mism) {
+    const uint32_t d = w ^ g4;                                   // codes < 128, so no byte has bit 7
+    uint32_t m = (d + 0x7F7F7F7Fu) & 0x80808080u;                // bit 7 of every byte that differs
+    if (m) {
+        mism += __popc(m);
+        do {
+            const int bit = __ffs(m) - 1;                        // 7, 15, 23 or 31
+            atomicAdd(&wh[(w >> (bit - 7)) & 0xFFu], 1u);
+            m &= m - 1;
+        } while (m);
+    }
+}
+
+__global__ void __launch_bounds__(kHistWarps * 32)
+k_hist(const uint8_t *__restrict__ codes, int64_t n_pad, int64_t n_codons, int chunks, int64_t chunk_rows,
+       uint32_t *__restrict__ hist)
+{
+    __shared__ uint32_t wh_all[kHistWarps][128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *wh = wh_all[warp];
+    for (int i = lane; i < 128; i += 32) wh[i] = 0;
+    __syncwarp();
+
+    const int64_t item = (int64_t)blockIdx.x * kHistWarps + warp;
+    if (item >= n_codons * chunks) return;
+    const int64_t col = item / chunks;
+    const int64_t r0 = (item % chunks) * chunk_rows;
+    const int64_t r1 = min(n_pad, r0 + chunk_rows);
+    if (r0 >= r1) return;
+    const uint8_t *base = codes + col * n_pad + r0;
+    const uint4 *p = reinterpret_cast<const uint4 *>(base);
+    const int nvec = (int)((r1 - r0) >> 4);
+    const uint32_t guess = base[0];
+    const uint32_t g4 = guess * 0x01010101u;
+    uint32_t mism = 0;
+
+    for (int v0 = 0; v0 < nvec; v0 += 128) {
+        uint4 x[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int v = v0 + k * 32 + lane;
+            x[k] = v < nvec ? ld_stream_v4(p + v) : make_uint4(g4, g4, g4, g4);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            hist_word(x[k].x, g4, wh, mism);
+            hist_word(x[k].y, g4, wh, mism);
+            hist_word(x[k].z, g4, wh, mism);
+            hist_word(x[k].w, g4, wh, mism);
+        }
+    }
+    mism = warp_sum_u32(mism);
+    __syncwarp();
+    const uint32_t matched = (uint32_t)(r1 - r0) - mism;
+    for (int b = lane; b < kHistBins; b += 32) {
+        const uint32_t cnt = wh[b] + ((uint32_t)b == guess ? matched : 0u);
+        if (cnt) atomicAdd(&hist[col * kHistBins + b], cnt);
+    }
+}
+
+// transposed codes -> sequence-major block [n][C] for product columns [c0, c0+C)
+__global__ void k_untranspose(const uint8_t *__restrict__ codes, int64_t n_pad, int64_t n, int64_t c0, int64_t C,
+                              uint8_t *__restrict__ out)
+{
+    __shared__ uint8_t tile[32][33];
+    const int64_t cb = (int64_t)blockIdx.x * 32, rb = (int64_t)blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    if (cb + ty < C && rb + tx < n) tile[ty][tx] = codes[(c0 + cb + ty) * n_pad + rb + tx];
+    __syncthreads();
+    if (rb + ty < n && cb + tx < C) out[(rb + ty) * C + cb + tx] = tile[tx][ty];
+}
+
+// ---------------------------------------------------------------------------
+// K3: per-codon statistics from histograms (one warp per codon).
+// within  (wg:611-744):  comparisons = n(n-1)/2, sites = h.s/n,
+//                        diffs = (1/2) h'Th / comparisons   
+// between (bg:680-947):  comparisons = na*nb, sites = (ha.s/na + hb.s/nb)/2,
+//                        diffs = ha'T hb / comparisons
+// Conserved codons take the table sites of the conserved codon and 0 diffs
+// (wg:706-744; bg:834-947).  'other' codons (IUPAC...) are defined alleles with
+// 0 sites and 0 diffs; two distinct 'other' strings make a column polymorphic
+// (tracked by K1's min/max signature).
+// ---------------------------------------------------------------------------
+constexpr int kStatsWarps = 8;
+
+__device__ __forceinline__ int first_defined_code(const uint8_t *col, int64_t n, int lane) {
+    // lowest sequence index whose codon is defined (bg:853-890 scan order)
+    for (int64_t r0 = 0; r0 < n; r0 += 32) {
+        const int64_t r = r0 + lane;
+        const int code = r < n ? col[r] : kCodeUndef;
+        const unsigned hit = __ballot_sync(kFull, code != kCodeUndef && code != kCodePad);
+        if (hit) return __shfl_sync(kFull, code, __ffs(hit) - 1);
+    }
+    return kCodeUndef;
+}
+
+template <bool BETWEEN>
+__global__ void __launch_bounds__(kStatsWarps * 32)
+k_stats(GroupView A, GroupView B, int64_t n_codons, const double *__restrict__ tables, StatsOut out)
+{
+    __shared__ int s_bin[kStatsWarps][64];
+    __shared__ double s_ca[kStatsWarps][64];
+    __shared__ double s_cb[kStatsWarps][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t c = (int64_t)blockIdx.x * kStatsWarps + warp;
+    if (c >= n_codons) return;
+
+    const double *sites = tables;            // [64][2]
+    const double *TN = tables + 128;         // [64][64]
+    const double *TS = tables + 128 + 4096;
+
+    const uint32_t *ha = A.hist + c * kHistBins;
+    const uint32_t a0 = ha[lane], a1 = ha[lane + 32], ao = ha[kCodeOther];
+    uint32_t b0 = a0, b1 = a1, bo = ao;
+    if (BETWEEN) {
+        const uint32_t *hb = B.hist + c * kHistBins;
+        b0 = hb[lane]; b1 = hb[lane + 32]; bo = hb[kCodeOther];
+    }
+    const uint32_t na_u = warp_sum_u32(a0 + a1) + ao;
+    const uint32_t nb_u = BETWEEN ? warp_sum_u32(b0 + b1) + bo : na_u;
+    const double na = (double)na_u, nb = (double)nb_u;
+
+    const unsigned m0 = __ballot_sync(kFull, (a0 | b0) != 0), m1 = __ballot_sync(kFull, (a1 | b1) != 0);
+    const int n_acgt = __popc(m0) + __popc(m1);
+    int n_other = 0;
+    if (ao | bo) {
+        uint32_t lo = kOtherNone, hi = 0;
+        if (ao) { lo = min(lo, A.other_min[c]); hi = max(hi, A.other_max[c]); }
+        if (BETWEEN && bo) { lo = min(lo, B.other_min[c]); hi = max(hi, B.other_max[c]); }
+        n_other = lo != hi ? 2 : 1;
+    }
+    const int alleles = n_acgt + n_other;
+    const bool poly = BETWEEN ? (na_u > 0 && nb_u > 0 && alleles >= 2) : (alleles >= 2);
+
+    double r_ns = 0, r_ss = 0, r_nd = 0, r_sd = 0;
+    unsigned long long cmp = 0;
+    int conserved = kCodeUndef;
+
+    if (poly) {
+        const double sn0 = sites[2 * lane], ss0 = sites[2 * lane + 1];
+        const double sn1 = sites[2 * (lane + 32)], ss1 = sites[2 * (lane + 32) + 1];
+        const double hsn_a = warp_sum((double)a0 * sn0 + (double)a1 * sn1);
+        const double hss_a = warp_sum((double)a0 * ss0 + (double)a1 * ss1);
+        // compact the occupied ACGT bins
+        const unsigned lt = (1u << lane) - 1;
+        if ((a0 | b0) != 0) { const int k = __popc(m0 & lt); s_bin[warp][k] = lane; s_ca[warp][k] = a0; s_cb[warp][k] = b0; }
+        if ((a1 | b1) != 0) { const int k = __popc(m0) + __popc(m1 & lt); s_bin[warp][k] = lane + 32; s_ca[warp][k] = a1; s_cb[warp][k] = b1; }
+        __syncwarp();
+        double qn = 0, qs = 0;
+        if (BETWEEN) {
+            for (int i = 0; i < n_acgt; i++) {
+                const double wi = s_ca[warp][i];
+                if (wi == 0) continue;
+                const int bi = s_bin[warp][i];
+                for (int j = lane; j < n_acgt; j += 32) {
+                    if (j == i) continue;
+                    const double w = wi * s_cb[warp][j];
+                    const int bj = s_bin[warp][j];
+                    qn += w * TN[bi * 64 + bj];
+                    qs += w * TS[bi * 64 + bj];
+                }
+            }
+        } else {
+            for (int i = 0; i < n_acgt; i++) {
+                const double wi = s_ca[warp][i];
+                const int bi = s_bin[warp][i];
+                for (int j = i + 1 + lane; j < n_acgt; j += 32) {
+                    const double w = wi * s_ca[warp][j];
+                    const int bj = s_bin[warp][j];
+                    qn += w * TN[bi * 64 + bj];
+                    qs += w * TS[bi * 64 + bj];
+                }
+            }
+        }
+        qn = warp_sum(qn);
+        qs = warp_sum(qs);
+        if (BETWEEN) {
+            const double hsn_b = warp_sum((double)b0 * sn0 + (double)b1 * sn1);
+            const double hss_b = warp_sum((double)b0 * ss0 + (double)b1 * ss1);
+            cmp = (unsigned long long)na_u * (unsigned long long)nb_u;
+            r_ns = (hsn_a / na + hsn_b / nb) / 2;
+            r_ss = (hss_a / na + hss_b / nb) / 2;
+        } else {
+            cmp = (unsigned long long)na_u * (unsigned long long)(na_u - 1) / 2;
+            r_ns = hsn_a / na;
+            r_ss = hss_a / na;
+        }
+        const double dc = (double)cmp;
+        r_nd = qn / dc;
+        r_sd = qs / dc;
+    } else {
+        // conserved: which codon?
+        if (!BETWEEN || (na_u > 0 && nb_u > 0)) {
+            if (n_acgt == 1) conserved = m0 ? __ffs(m0) - 1 : 32 + __ffs(m1) - 1;
+            else if (n_other) conserved = kCodeOther;
+        } else if (na_u > 0 || nb_u > 0) {
+            // one group has no defined codon here; the reference takes the first
+            // defined codon of the other group in sequence order (bg:853-890)
+            const bool use_a = na_u > 0;
+            const GroupView &G = use_a ? A : B;
+            const uint8_t *codes = G.codes;
+            if (alleles == 1) {
+                conserved = n_acgt == 1 ? (m0 ? __ffs(m0) - 1 : 32 + __ffs(m1) - 1) : kCodeOther;
+            } else if (codes) {
+                conserved = first_defined_code(codes + c * G.n_pad, G.n, lane);
+            } else {
+                conserved = n_acgt ? (m0 ? __ffs(m0) - 1 : 32 + __ffs(m1) - 1) : kCodeOther;
+            }
+        }
+        if (conserved < 64) { r_ns = sites[2 * conserved]; r_ss = sites[2 * conserved + 1]; }
+    }
+
+    if (lane == 0) {
+        if (out.poly) out.poly[c] = poly ? 1 : 0;
+        if (out.ndef_a) out.ndef_a[c] = na_u;
+        if (out.ndef_b) out.ndef_b[c] = nb_u;
+        if (out.comparisons) out.comparisons[c] = cmp;
+        if (out.conserved) out.conserved[c] = (uint8_t)(poly ? kCodeUndef : conserved);
+        if (out.stats4) {
+            double2 *o = reinterpret_cast<double2 *>(out.stats4 + 4 * c);
+            o[0] = make_double2(r_ns, r_ss);
+            o[1] = make_double2(r_nd, r_sd);
+        }
+    }
+}
+
+// product sums (wg:690-693; bg:984-1005): fixed-shape tree, deterministic
+__global__ void __launch_bounds__(256)
+k_product_sums(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, double *__restrict__ sums)
+{
+    __shared__ double red[4][256];
+    const int p = blockIdx.x, t = threadIdx.x;
+    const int64_t c0 = ofs[p], c1 = ofs[p + 1];
+    double s[4] = {0, 0, 0, 0};
+    for (int64_t c = c0 + t; c < c1; c += 256) {
+        const double2 x = reinterpret_cast<const double2 *>(stats4 + 4 * c)[0];
+        const double2 y = reinterpret_cast<const double2 *>(stats4 + 4 * c)[1];
+        s[0] += x.x; s[1] += x.y; s[2] += y.x; s[3] += y.y;
+    }
+    for (int q = 0; q < 4; q++) red[q][t] = s[q];
+    __syncthreads();
+    for (int h = 128; h > 0; h >>= 1) {
+        if (t < h) for (int q = 0; q < 4; q++) red[q][t] += red[q][t + h];
+        __syncthreads();
+    }
+    if (t < 4) sums[4 * p + t] = red[t][0];
+}
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), counter-based: any (replicate, draw) pair
+// regenerates its numbers independently of launch geometry.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+
+// ---------------------------------------------------------------------------
+// K4: whole-product bootstrap (wg:854-916; bgp:893-989).  One warp per
+// replicate; lanes share the C draws.  A draw is int(rand(C+1)) (wg:885): slot 0
+// is the reference's nonexistent codon 0 and contributes nothing.
+// ---------------------------------------------------------------------------
+constexpr int kBootWarps = 8;
+
+__global__ void __launch_bounds__(kBootWarps * 32)
+k_bootstrap(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, int64_t b_first, int64_t b_count,
+            uint2 key, uint32_t stream_id, double *__restrict__ rep)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t bl = (int64_t)blockIdx.x * kBootWarps + warp;
+    if (bl >= b_count) return;
+    const int p = blockIdx.y;
+    const int64_t c0 = ofs[p];
+    const uint32_t C = (uint32_t)(ofs[p + 1] - c0);
+    const double *S = stats4 + 4 * c0;
+    const uint64_t b = (uint64_t)(b_first + bl);
+    const uint32_t nquad = (C + 3) >> 2;
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    for (uint32_t q = lane; q < nquad; q += 32) {
+        const uint4 u = philox4x32_10(make_uint4(q, (uint32_t)b, (uint32_t)(b >> 32) ^ ((uint32_t)p << 8), stream_id), key);
+        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (4 * q + j < C) {
+                const uint32_t r = __umulhi(uu[j], C + 1);
+                if (r) {
+                    const double2 x = __ldg(reinterpret_cast<const double2 *>(S + 4 * (size_t)(r - 1)));
+                    const double2 y = __ldg(reinterpret_cast<const double2 *>(S + 4 * (size_t)(r - 1)) + 1);
+                    s0 += x.x; s1 += x.y; s2 += y.x; s3 += y.y;
+                }
+            }
+        }
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+    if (lane == 0) {
+        double2 *o = reinterpret_cast<double2 *>(rep + 4 * ((size_t)p * b_count + bl));
+        o[0] = make_double2(s0, s1);
+        o[1] = make_double2(s2, s3);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K6: moments over replicates.  Per replicate dN = Nd/Ns if Ns > 0 else the
+// reference's '*' which its arithmetic reads as 0 (wg:942-961); JC as
+// bgp:1047-1071.  SD is the reference's two-pass form with n-1 (wg:1351-1365).
+// One block per (product | window).  se[6] = dN, dS, dN-dS, JC dN, JC dS, JC dN-dS.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double rep_value(const double *rep4, int which) {
+    const double2 x = reinterpret_cast<const double2 *>(rep4)[0];
+    const double2 y = reinterpret_cast<const double2 *>(rep4)[1];
+    const double dn = x.x > 0 ? y.x / x.x : 0.0;
+    const double ds = x.y > 0 ? y.y / x.y : 0.0;
+    if (which == 0) return dn;
+    if (which == 1) return ds;
+    if (which == 2) return dn - ds;
+    const double jn = -0.75 * log(1.0 - (4.0 / 3.0) * dn);
+    const double js = -0.75 * log(1.0 - (4.0 / 3.0) * ds);
+    if (which == 3) return jn;
+    if (which == 4) return js;
+    return (jn >= 0 && js >= 0) ? jn - js : 0.0;
+}
+
+__device__ __forceinline__ double block_sum_256(double v, double *red) {
+    const int t = threadIdx.x;
+    __syncthreads();
+    red[t] = v;
+    __syncthreads();
+    for (int h = 128; h > 0; h >>= 1) {
+        if (t < h) red[t] += red[t + h];
+        __syncthreads();
+    }
+    return red[0];
+}
+
+__global__ void __launch_bounds__(256)
+k_rep_moments(const double *__restrict__ rep, int64_t B, double *__restrict__ se)
+{
+    __shared__ double red[256];
+    const int p = blockIdx.x, t = threadIdx.x;
+    const double *R = rep + 4 * (size_t)p * B;
+    for (int which = 0; which < 6; which++) {
+        double s = 0;
+        for (int64_t b = t; b < B; b += 256) s += rep_value(R + 4 * b, which);
+        const double mean = block_sum_256(s, red) / (double)B;
+        double ss = 0;
+        for (int64_t b = t; b < B; b += 256) { const double d = rep_value(R + 4 * b, which) - mean; ss += d * d; }
+        const double tot = block_sum_256(ss, red);
+        if (t == 0) se[6 * p + which] = sqrt(tot / (double)(B - 1));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K5: sliding windows (wgp:314-362; bgp:501-592).  Sums run codon by codon in
+// ascending order, one thread per (window, statistic): the same additions in
+// the same order as the reference, so window sums are bitwise reproducible and
+// an all-zero window stays exactly 0 (a prefix-sum difference would not).
+// ---------------------------------------------------------------------------
+__global__ void k_window_sums(const double *__restrict__ stats4, int64_t W, int64_t step, int64_t nwin,
+                              double *__restrict__ win_sums)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nwin * 4) return;
+    const int64_t k = i >> 2;
+    const int q = (int)(i & 3);
+    const double *p = stats4 + 4 * k * step + q;
+    double s = 0;
+    for (int64_t j = 0; j < W; j++) s += p[4 * j];
+    win_sums[i] = s;
+}
+
+// per-window bootstrap (wgp:384-427; bgp:604-736): one thread per (window,
+// replicate), W draws uniform over the window's codons
+__global__ void __launch_bounds__(256)
+k_window_bootstrap(const double *__restrict__ stats4, int64_t W, int64_t step, int64_t win0, int64_t nwin, int64_t B,
+                   uint2 key, uint32_t stream_id, double *__restrict__ rep)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nwin * B) return;
+    const int64_t wl = i / B, b = i % B;
+    const uint64_t k = (uint64_t)(win0 + wl);
+    const double *S = stats4 + 4 * k * step;
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    const uint32_t Wu = (uint32_t)W;
+    for (uint32_t q = 0; 4 * q < Wu; q++) {
+        const uint4 u = philox4x32_10(make_uint4(q, (uint32_t)b, (uint32_t)k, stream_id ^ ((uint32_t)(k >> 32) << 16) ^ ((uint32_t)(b >> 32))), key);
+        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (4 * q + j < Wu) {
+                const uint32_t r = __umulhi(uu[j], Wu);
+                const double2 x = __ldg(reinterpret_cast<const double2 *>(S + 4 * (size_t)r));
+                const double2 y = __ldg(reinterpret_cast<const double2 *>(S + 4 * (size_t)r) + 1);
+                s0 += x.x; s1 += x.y; s2 += y.x; s3 += y.y;
+            }
+        }
+    }
+    double2 *o = reinterpret_cast<double2 *>(rep + 4 * (size_t)i);
+    o[0] = make_double2(s0, s1);
+    o[1] = make_double2(s2, s3);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ launchers
+
+void launch_pack(const uint8_t *d_aln, int64_t row_stride, int64_t n_rows, int64_t row0, const CodonMap *d_map,
+                 int64_t n_codons, uint8_t *d_codes, int64_t n_pad, uint32_t *d_other_min, uint32_t *d_other_max,
+                 cudaStream_t stream)
+{
+    if (n_codons <= 0 || n_rows <= 0) return;
+    dim3 grid((unsigned)((n_codons + kPackCodons - 1) / kPackCodons), (unsigned)((n_rows + kPackRows - 1) / kPackRows));
+    k_pack<<<grid, 256, 0, stream>>>(d_aln, row_stride, n_rows, row0, d_map, n_codons, d_codes, n_pad, d_other_min,
+                                     d_other_max);
+}
+
+void launch_hist(const uint8_t *d_codes, int64_t n_pad, int64_t n_codons, uint32_t *d_hist, cudaStream_t stream)
+{
+    if (n_codons <= 0 || n_pad <= 0) return;
+    int chunks = (int)((n_pad + kHistChunkRows - 1) / kHistChunkRows);
+    int64_t chunk_rows = ((n_pad + chunks - 1) / chunks + 15) & ~(int64_t)15;
+    const int64_t items = n_codons * chunks;
+    k_hist<<<(unsigned)((items + kHistWarps - 1) / kHistWarps), kHistWarps * 32, 0, stream>>>(d_codes, n_pad, n_codons, chunks,
+                                                                                               chunk_rows, d_hist);
+}
+
+void launch_untranspose(const uint8_t *d_codes, int64_t n_pad, int64_t n, int64_t c0, int64_t C, uint8_t *d_out,
+                        cudaStream_t stream)
+{
+    if (C <= 0 || n <= 0) return;
+    dim3 grid((unsigned)((C + 31) / 32), (unsigned)((n + 31) / 32)), block(32, 32);
+    k_untranspose<<<grid, block, 0, stream>>>(d_codes, n_pad, n, c0, C, d_out);
+}
+
+void launch_within_stats(GroupView A, int64_t n_codons, const double *d_tables, StatsOut out, cudaStream_t stream)
+{
+    if (n_codons <= 0) return;
+    k_stats<false><<<(unsigned)((n_codons + kStatsWarps - 1) / kStatsWarps), kStatsWarps * 32, 0, stream>>>(A, A, n_codons,
+                                                                                                           d_tables, out);
+}
+
+void launch_between_stats(GroupView A, GroupView B, int64_t n_codons, const double *d_tables, StatsOut out,
+                          cudaStream_t stream)
+{
+    if (n_codons <= 0) return;
+    k_stats<true><<<(unsigned)((n_codons + kStatsWarps - 1) / kStatsWarps), kStatsWarps * 32, 0, stream>>>(A, B, n_codons,
+                                                                                                          d_tables, out);
+}
+
+void launch_product_sums(const double *d_stats4, const int64_t *d_prod_ofs, int n_products, double *d_sums,
+                         cudaStream_t stream)
+{
+    if (n_products <= 0) return;
+    k_product_sums<<<n_products, 256, 0, stream>>>(d_stats4, d_prod_ofs, d_sums);
+}
+
+void launch_bootstrap(const double *d_stats4, const int64_t *d_prod_ofs, int n_products, int64_t b_first, int64_t b_count,
+                      uint64_t seed, uint32_t stream_id, double *d_rep, cudaStream_t stream)
+{
+    if (n_products <= 0 || b_count <= 0) return;
+    dim3 grid((unsigned)((b_count + kBootWarps - 1) / kBootWarps), (unsigned)n_products);
+    k_bootstrap<<<grid, kBootWarps * 32, 0, stream>>>(d_stats4, d_prod_ofs, b_first, b_count,
+                                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), stream_id, d_rep);
+}
+
+void launch_rep_moments(const double *d_rep, int64_t n_items, int64_t B, double *d_se, cudaStream_t stream)
+{
+    if (n_items <= 0) return;
+    k_rep_moments<<<(unsigned)n_items, 256, 0, stream>>>(d_rep, B, d_se);
+}
+
+void launch_window_sums(const double *d_stats4, int64_t W, int64_t step, int64_t nwin, double *d_win_sums,
+                        cudaStream_t stream)
+{
+    if (nwin <= 0) return;
+    k_window_sums<<<(unsigned)((nwin * 4 + 127) / 128), 128, 0, stream>>>(d_stats4, W, step, nwin, d_win_sums);
+}
+
+void launch_window_bootstrap(const double *d_stats4, int64_t W, int64_t step, int64_t win0, int64_t nwin, int64_t B,
+                             uint64_t seed, uint32_t stream_id, double *d_rep, cudaStream_t stream)
+{
+    if (nwin <= 0 || B <= 0) return;
+    const int64_t total = nwin * B;
+    k_window_bootstrap<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+        d_stats4, W, step, win0, nwin, B, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), stream_id, d_rep);
+}
+
+}  // namespace snpg

@@ -1,0 +1,75 @@
+// Internal declarations shared by the kernels and the C-ABI layer.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace snpg {
+
+constexpr int kHistBins = 66;      // 64 codons, undefined, other
+constexpr int kCodeUndef = 64;
+constexpr int kCodeOther = 65;
+constexpr int kCodePad = 127;      // fills rows >= n_seqs up to the padded row count; never counted
+constexpr int kRowPad = 128;       // packed matrix row count is padded to a multiple of this
+constexpr uint32_t kOtherNone = 0xFFFFFFFFu;
+
+// One entry of the codon index map: the alignment columns of the codon's three
+// nucleotides and the strand (minus = 1 for '-': complement while classifying).
+// Built on the host from the CDS segments (frame, multi-segment, strand).
+struct CodonMap { int32_t p0, p1, p2, minus; };
+
+// Device view of one loaded group, offset to the first codon a kernel works on.
+struct GroupView {
+    const uint32_t *hist;        // [codons][66]
+    const uint32_t *other_min;   // [codons] min packed chars over 'other' codons (kOtherNone if none)
+    const uint32_t *other_max;   // [codons] max ...
+    const uint8_t *codes;        // [codons][n_pad] or null
+    int64_t n, n_pad;
+};
+
+// host (ng_tables.cu)
+void build_tables(double *sites, double *diffs);
+
+// ---- kernel launch wrappers; all asynchronous on `stream` -------------------
+
+// K1 pack: raw alignment rows -> 1-byte codon codes, TRANSPOSED: codes[c][row],
+// row pitch n_pad (multiple of kRowPad; rows >= n hold kCodePad).  row0 (multiple
+// of kRowPad) is the position of d_aln's first row inside the group.
+void launch_pack(const uint8_t *d_aln, int64_t row_stride, int64_t n_rows, int64_t row0, const CodonMap *d_map,
+                 int64_t n_codons, uint8_t *d_codes, int64_t n_pad, uint32_t *d_other_min, uint32_t *d_other_max,
+                 cudaStream_t stream);
+
+// K2 histogram: codes[c][0..n_pad) -> hist[c][66] (u32, zeroed by the caller)
+void launch_hist(const uint8_t *d_codes, int64_t n_pad, int64_t n_codons, uint32_t *d_hist, cudaStream_t stream);
+
+// transposed codes -> sequence-major [n][C] (test hook)
+void launch_untranspose(const uint8_t *d_codes, int64_t n_pad, int64_t n, int64_t c0, int64_t C, uint8_t *d_out,
+                        cudaStream_t stream);
+
+// K3 per-codon Nei-Gojobori statistics from histograms.
+// d_tables: [64*2 sites][2*64*64 diffs] doubles.  Any output may be null.
+struct StatsOut {
+    uint8_t *poly; uint32_t *ndef_a; uint32_t *ndef_b; unsigned long long *comparisons;
+    double *stats4; uint8_t *conserved;
+};
+void launch_within_stats(GroupView A, int64_t n_codons, const double *d_tables, StatsOut out, cudaStream_t stream);
+void launch_between_stats(GroupView A, GroupView B, int64_t n_codons, const double *d_tables, StatsOut out,
+                          cudaStream_t stream);
+
+// product sums: sums[p][4] = sum over codons [ofs[p], ofs[p+1]) of stats4
+void launch_product_sums(const double *d_stats4, const int64_t *d_prod_ofs, int n_products, double *d_sums,
+                         cudaStream_t stream);
+
+// K4 whole-product bootstrap: rep[p][b - b_first][4] for b in [b_first, b_first+b_count)
+void launch_bootstrap(const double *d_stats4, const int64_t *d_prod_ofs, int n_products, int64_t b_first, int64_t b_count,
+                      uint64_t seed, uint32_t stream_id, double *d_rep, cudaStream_t stream);
+// K6 moments: rep[item][B][4] -> se[item][6] (SD of dN, dS, dN-dS, JC dN, JC dS, JC dN-dS)
+void launch_rep_moments(const double *d_rep, int64_t n_items, int64_t B, double *d_se, cudaStream_t stream);
+
+// K5 windows
+void launch_window_sums(const double *d_stats4, int64_t W, int64_t step, int64_t nwin, double *d_win_sums,
+                        cudaStream_t stream);
+void launch_window_bootstrap(const double *d_stats4, int64_t W, int64_t step, int64_t win0, int64_t nwin, int64_t B,
+                             uint64_t seed, uint32_t stream_id, double *d_rep, cudaStream_t stream);
+
+}  // namespace snpg

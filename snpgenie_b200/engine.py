@@ -1,0 +1,195 @@
+"""Host-side mirror of the reference's within-/between-group engine, over the C ABI.
+
+`Engine` owns one snpg_ctx (one GPU).  Method names follow the reference's
+vocabulary (products, groups, codons, windows, bootstraps); every compute call
+goes through libsnpgenie_cuda.so -- there is no Python or CPU implementation
+behind these methods.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from .hostio import Product, products_to_csr
+
+STATS = ("N_sites", "S_sites", "N_diffs", "S_diffs")
+CODONS = [a + b + c for a in "ACGT" for b in "ACGT" for c in "ACGT"]
+
+
+def _ptr(a, t):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+def ng_tables():
+    """(sites [64,2], diffs [2,64,64]) as the kernels use them (host-built, no GPU needed)."""
+    sites = np.zeros((64, 2))
+    diffs = np.zeros((2, 64, 64))
+    rc = _abi.lib.snpg_get_tables(_ptr(sites, C.c_double), _ptr(diffs, C.c_double))
+    if rc:
+        raise _abi.SnpgError(rc, "snpg_get_tables")
+    return sites, diffs
+
+
+class Engine:
+    def __init__(self, device: int = 0, seed: int = 20261019, rank: int = 0, world: int = 1):
+        self._ctx = C.c_void_p()
+        rc = _abi.lib.snpg_create(C.byref(self._ctx), device, seed)
+        if rc:
+            raise _abi.SnpgError(rc, (_abi.lib.snpg_last_error(None) or b"").decode())
+        self.products: list[Product] = []
+        self.rank, self.world = rank, world
+        if world > 1:
+            self._ck(_abi.lib.snpg_set_shard(self._ctx, rank, world))
+
+    # -- plumbing ---------------------------------------------------------
+    def _ck(self, rc):
+        if rc:
+            raise _abi.SnpgError(rc, (_abi.lib.snpg_last_error(self._ctx) or b"").decode())
+
+    def close(self):
+        if self._ctx:
+            _abi.lib.snpg_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(_abi.lib.snpg_launch_count(self._ctx))
+
+    def set_option(self, option: int, value: int):
+        self._ck(_abi.lib.snpg_set_option(self._ctx, option, value))
+
+    # -- annotation ---------------------------------------------------------
+    def set_products(self, products: list[Product], aln_len: int):
+        seg_ofs, starts, stops, strand = products_to_csr(products)
+        self._ck(_abi.lib.snpg_set_products(self._ctx, len(products), _ptr(seg_ofs, C.c_int64), _ptr(starts, C.c_int64),
+                                            _ptr(stops, C.c_int64), _ptr(strand, C.c_int8), aln_len))
+        self.products = list(products)
+
+    def n_codons(self, product: int) -> int:
+        out = C.c_int64()
+        self._ck(_abi.lib.snpg_n_codons(self._ctx, product, C.byref(out)))
+        return out.value
+
+    def shard_range(self):
+        f, c, t = C.c_int64(), C.c_int64(), C.c_int64()
+        self._ck(_abi.lib.snpg_shard_range(self._ctx, C.byref(f), C.byref(c), C.byref(t)))
+        return f.value, c.value, t.value
+
+    def local_codons(self, product: int) -> int:
+        """Codons of `product` inside this ctx's shard (== n_codons when world == 1)."""
+        first, count, _ = self.shard_range()
+        ofs = np.cumsum([0] + [self.n_codons(p) for p in range(len(self.products))])
+        lo = min(max(ofs[product] - first, 0), count)
+        hi = min(max(ofs[product + 1] - first, 0), count)
+        return int(hi - lo)
+
+    # -- ingest -------------------------------------------------------------
+    def load_group(self, group: int, aln: np.ndarray):
+        """aln: uint8 [n_seqs, aln_len] host array (raw FASTA residues)."""
+        assert aln.dtype == np.uint8 and aln.ndim == 2 and aln.strides[1] == 1
+        self._ck(_abi.lib.snpg_load_group(self._ctx, group, aln.ctypes.data, aln.shape[0], aln.shape[1], aln.strides[0]))
+
+    def load_group_ptr(self, group: int, ptr: int, n_seqs: int, aln_len: int, row_stride: int, device: bool):
+        fn = _abi.lib.snpg_load_group_device if device else _abi.lib.snpg_load_group
+        self._ck(fn(self._ctx, group, ptr, n_seqs, aln_len, row_stride))
+
+    def group_size(self, group: int) -> int:
+        n = C.c_uint64()
+        self._ck(_abi.lib.snpg_group_size(self._ctx, group, C.byref(n)))
+        return n.value
+
+    # -- test hooks -----------------------------------------------------------
+    def codon_indices(self, group: int, product: int) -> np.ndarray:
+        out = np.zeros((self.group_size(group), self.local_codons(product)), dtype=np.uint8)
+        self._ck(_abi.lib.snpg_get_codon_indices(self._ctx, group, product, _ptr(out, C.c_uint8)))
+        return out
+
+    def hist(self, group: int, product: int):
+        nc = self.local_codons(product)
+        h = np.zeros((nc, _abi.HIST_BINS), dtype=np.uint32)
+        od = np.zeros(nc, dtype=np.uint8)
+        self._ck(_abi.lib.snpg_get_hist(self._ctx, group, product, _ptr(h, C.c_uint32), _ptr(od, C.c_uint8)))
+        return h, od
+
+    # -- per-codon engine -------------------------------------------------------
+    def within(self, group: int, product: int) -> dict:
+        nc = self.local_codons(product)
+        r = dict(poly=np.zeros(nc, np.uint8), n_defined=np.zeros(nc, np.uint32), comparisons=np.zeros(nc, np.uint64),
+                 stats4=np.zeros((nc, 4)), conserved=np.zeros(nc, np.uint8))
+        self._ck(_abi.lib.snpg_within(self._ctx, group, product, _ptr(r["poly"], C.c_uint8), _ptr(r["n_defined"], C.c_uint32),
+                                      _ptr(r["comparisons"], C.c_uint64), _ptr(r["stats4"], C.c_double), _ptr(r["conserved"], C.c_uint8)))
+        for q, k in enumerate(STATS):
+            r[k] = r["stats4"][:, q]
+        return r
+
+    def between(self, group_a: int, group_b: int, product: int) -> dict:
+        nc = self.local_codons(product)
+        r = dict(poly=np.zeros(nc, np.uint8), ndef_a=np.zeros(nc, np.uint32), ndef_b=np.zeros(nc, np.uint32),
+                 comparisons=np.zeros(nc, np.uint64), stats4=np.zeros((nc, 4)), conserved=np.zeros(nc, np.uint8))
+        self._ck(_abi.lib.snpg_between(self._ctx, group_a, group_b, product, _ptr(r["poly"], C.c_uint8), _ptr(r["ndef_a"], C.c_uint32),
+                                       _ptr(r["ndef_b"], C.c_uint32), _ptr(r["comparisons"], C.c_uint64), _ptr(r["stats4"], C.c_double),
+                                       _ptr(r["conserved"], C.c_uint8)))
+        for q, k in enumerate(STATS):
+            r[k] = r["stats4"][:, q]
+        return r
+
+    # -- resampling -------------------------------------------------------------
+    def bootstrap_product(self, stats4: np.ndarray, B: int, keep: np.ndarray | None = None, want_sums: bool = False):
+        stats4 = np.ascontiguousarray(stats4, dtype=np.float64)
+        keep8 = None if keep is None else np.ascontiguousarray(keep, dtype=np.uint8)
+        sums = np.zeros((B, 4)) if want_sums else None
+        se = np.zeros(6)
+        self._ck(_abi.lib.snpg_bootstrap_product(self._ctx, _ptr(stats4, C.c_double), _ptr(keep8, C.c_uint8), stats4.shape[0], B,
+                                                 _ptr(sums, C.c_double), _ptr(se, C.c_double)))
+        return sums, se
+
+    def windows(self, stats4: np.ndarray, W: int, step: int, B: int = 0, keep: np.ndarray | None = None):
+        stats4 = np.ascontiguousarray(stats4, dtype=np.float64)
+        keep8 = None if keep is None else np.ascontiguousarray(keep, dtype=np.uint8)
+        nwin = C.c_int64()
+        self._ck(_abi.lib.snpg_windows(self._ctx, _ptr(stats4, C.c_double), _ptr(keep8, C.c_uint8), stats4.shape[0], W, step, 0,
+                                       None, None, C.byref(nwin)))
+        sums = np.zeros((nwin.value, 4))
+        se = np.zeros((nwin.value, 3)) if B >= 2 else None
+        self._ck(_abi.lib.snpg_windows(self._ctx, _ptr(stats4, C.c_double), _ptr(keep8, C.c_uint8), stats4.shape[0], W, step, B,
+                                       _ptr(sums, C.c_double), _ptr(se, C.c_double), C.byref(nwin)))
+        return sums, se
+
+    # -- whole job ----------------------------------------------------------------
+    def within_all(self, group: int, B: int = 0):
+        P = len(self.products)
+        sums = np.zeros((P, 4))
+        se = np.zeros((P, 6)) if B >= 2 else None
+        self._ck(_abi.lib.snpg_within_all(self._ctx, group, B, _ptr(sums, C.c_double), _ptr(se, C.c_double)))
+        return sums, se
+
+    # -- device-pointer plumbing for multi-GPU ------------------------------------
+    def within_stats_device(self, group: int, d_stats4_ptr: int):
+        self._ck(_abi.lib.snpg_within_stats_device(self._ctx, group, d_stats4_ptr))
+
+    def bootstrap_all_device(self, d_stats4_full_ptr: int, b_first: int, b_count: int, d_rep_ptr: int):
+        self._ck(_abi.lib.snpg_bootstrap_all_device(self._ctx, d_stats4_full_ptr, b_first, b_count, d_rep_ptr))
+
+    def product_sums_device(self, d_stats4_full_ptr: int) -> np.ndarray:
+        sums = np.zeros((len(self.products), 4))
+        self._ck(_abi.lib.snpg_product_sums_device(self._ctx, d_stats4_full_ptr, _ptr(sums, C.c_double)))
+        return sums
+
+    def rep_moments_device(self, d_rep_ptr: int, n_items: int, B: int) -> np.ndarray:
+        se = np.zeros((n_items, 6))
+        self._ck(_abi.lib.snpg_rep_moments_device(self._ctx, d_rep_ptr, n_items, B, _ptr(se, C.c_double)))
+        return se

@@ -1,0 +1,384 @@
+"""GPU parity: libsnpgenie_cuda.so (through the C ABI) against the oracle and the reference goldens.
+
+Bars (BASELINE.json north_star): codon indices and histograms bit-exact; per-codon
+and per-product N/S sites and differences within 1e-12 relative; window sums
+bitwise (same additions in the same order); bootstrap SE statistically.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from snpgenie_b200 import hostio, synth
+from tests import refio
+from tests.refio import STATS
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def close(a, b, rtol=RTOL, atol=1e-15):
+    return np.allclose(a, b, rtol=rtol, atol=atol)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from snpgenie_b200.engine import Engine
+    e = Engine(device=0, seed=1234)
+    yield e
+    e.close()
+
+
+def _oracle_product(aln, p):
+    pos = orc.product_positions(p.starts, p.stops, p.strand, aln.shape[1])
+    raw, codes = orc.extract(aln, pos, p.strand)
+    return raw, codes
+
+
+# ----------------------------------------------------------------- K1 / K2 bit-exact
+
+@pytest.mark.parametrize("case,minus", [("w_cfg1", False), ("w_gaps", False), ("w_heavy", False), ("w_minus", True)])
+def test_codon_indices_and_histograms_bit_exact(eng, case, minus):
+    d, aln, _, _ = refio.within_case(case)
+    products = hostio.read_gtf_products(os.path.join(d, "cds.gtf"), include_minus=minus)
+    eng.set_products(products, aln.shape[1])
+    eng.load_group(0, aln)
+    for i, p in enumerate(products):
+        raw, codes = _oracle_product(aln, p)
+        assert (eng.codon_indices(0, i) == codes).all(), (case, p.name)
+        h, od = eng.hist(0, i)
+        assert (h == orc.hist(codes)).all(), (case, p.name)
+        assert (od == orc.other_distinct(raw, codes)).all(), (case, p.name)
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 127, 128, 129, 1000, 8191, 8192, 8193, 20000])
+def test_histogram_ragged_row_counts(eng, n):
+    """Row counts around every padding / chunking boundary, uniform random codons (worst case for K2)."""
+    rng = np.random.default_rng(n)
+    L = 3 * 70 + 5
+    aln = np.frombuffer(b"ACGTNacgtu-RY", dtype=np.uint8)[rng.integers(0, 13, size=(n, L))]
+    aln[:, :60] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=(n, 60))]
+    products = [hostio.Product("p", 1, [3], [212])]
+    eng.set_products(products, L)
+    eng.load_group(0, aln)
+    raw, codes = _oracle_product(aln, products[0])
+    assert (eng.codon_indices(0, 0) == codes).all()
+    h, od = eng.hist(0, 0)
+    assert (h == orc.hist(codes)).all()
+    assert (h.sum(axis=1) == n).all()
+    assert (od == orc.other_distinct(raw, codes)).all()
+
+
+def test_device_resident_and_strided_input_match_host_input(eng):
+    import torch
+    products = synth.hiv_products()
+    aln = synth.make_alignment(700, 9719, products, 77, gap_frac=0.025, n_frac=0.02, iupac_frac=0.005)
+    eng.set_products(products, 9719)
+    eng.load_group(0, aln)
+    ref = [eng.hist(0, i)[0] for i in range(len(products))]
+    # device buffer with a padded row pitch
+    pitch = 9728
+    d = torch.zeros((700, pitch), dtype=torch.uint8, device="cuda:0")
+    d[:, :9719] = torch.from_numpy(aln).cuda()
+    eng.load_group_ptr(1, d.data_ptr(), 700, 9719, pitch, device=True)
+    for i in range(len(products)):
+        assert (eng.hist(1, i)[0] == ref[i]).all()
+        assert (eng.codon_indices(1, i) == eng.codon_indices(0, i)).all()
+    # host buffer with a row stride (a view into a wider matrix)
+    wide = np.zeros((700, 10000), dtype=np.uint8)
+    wide[:, :9719] = aln
+    eng.load_group(2, wide[:, :9719])
+    for i in range(len(products)):
+        assert (eng.hist(2, i)[0] == ref[i]).all()
+
+
+# ----------------------------------------------------------------- K3 vs reference goldens
+
+def _check_within_case(eng, case, products, aln, codon_rows, prod_rows):
+    eng.set_products(products, aln.shape[1])
+    eng.load_group(0, aln)
+    sums, _ = eng.within_all(0)
+    for i, p in enumerate(products):
+        gold = refio.codon_arrays(codon_rows, p.name, p.n_codons)
+        r = eng.within(0, i)
+        assert (r["poly"] == gold["poly"]).all(), (case, p.name)
+        for k in STATS:
+            assert close(r[k], gold[k]), (case, p.name, k)
+        raw, codes = _oracle_product(aln, p)
+        res = orc.within_pairloop(raw)
+        assert (r["n_defined"] == res["n_defined"]).all()
+        nd = res["n_defined"].astype(np.uint64)
+        assert (r["comparisons"] == np.where(gold["poly"] == 1, nd * (nd - 1) // 2, 0)).all()
+        # conserved codon column (wg:726): the codon string, empty when nothing is defined
+        for c in np.flatnonzero(gold["poly"] == 0):
+            code = int(r["conserved"][c])
+            want = gold["comparisons_str"][c]
+            if code < 64:
+                assert "ACGT"[code >> 4] + "ACGT"[(code >> 2) & 3] + "ACGT"[code & 3] == want
+            elif code == 64:
+                assert want == ""
+            else:
+                assert want != "" and any(ch not in "ACGT" for ch in want)
+        pr = prod_rows[p.name]
+        for q, k in enumerate(STATS):
+            assert close(sums[i, q], float(pr[k])), (case, p.name, k)
+        assert close(sums[i, 2] / sums[i, 0], float(pr["dN"])) and close(sums[i, 3] / sums[i, 1], float(pr["dS"]))
+
+
+@pytest.mark.parametrize("case", ["w_cfg1", "w_gaps", "w_heavy"])
+def test_within_matches_reference(eng, case):
+    d, aln, codon_rows, prod_rows = refio.within_case(case)
+    products = hostio.read_gtf_products(os.path.join(d, "cds.gtf"))
+    _check_within_case(eng, case, products, aln, codon_rows, prod_rows)
+
+
+def test_minus_strand_matches_revcom_route(eng):
+    d, aln, codon_rows, prod_rows = refio.within_case("w_minus")
+    products = [p for p in hostio.read_gtf_products(os.path.join(d, "cds.gtf"), include_minus=True) if p.strand < 0]
+    _check_within_case(eng, "w_minus", products, aln, codon_rows, prod_rows)
+
+
+def test_between_matches_reference(eng):
+    d = os.path.join(refio.GOLD, "b_3groups")
+    names = ("grpA.fasta", "grpB.fasta", "grpC.fasta")
+    groups = {g: hostio.read_fasta(os.path.join(d, g))[1] for g in names}
+    products = hostio.read_gtf_products(os.path.join(d, "cds.gtf"))
+    _, rows = refio.read_tsv(os.path.join(d, "between_group_codon_results.txt"))
+    maps = refio.between_label_maps(os.path.join(d, "stdout.log"))
+    eng.set_products(products, groups[names[0]].shape[1])
+    for gi, g in enumerate(names):
+        eng.load_group(gi, groups[g])
+    checked = 0
+    for i, p in enumerate(products):
+        prow = [r for r in rows if r["product"] == p.name]
+        for lab1, lab2 in sorted({(r["group_1"], r["group_2"]) for r in prow}):
+            g1, g2 = maps[p.name][lab1], maps[p.name][lab2]
+            r = eng.between(names.index(g1), names.index(g2), i)
+            ra, rb = _oracle_product(groups[g1], p), _oracle_product(groups[g2], p)
+            res = orc.between_pairloop(ra[0], rb[0])     # sequence order = file order (deterministic tie-break)
+            for row in (x for x in prow if (x["group_1"], x["group_2"]) == (lab1, lab2)):
+                c = int(row["codon"].replace("codon_", "")) - 1
+                assert int(row["num_defined_codons_g1"] or 0) == r["ndef_a"][c]
+                assert int(row["num_defined_codons_g2"] or 0) == r["ndef_b"][c]
+                assert (row["variability"] == "polymorphic") == bool(r["poly"][c])
+                for k in STATS:
+                    # always equal to the oracle run in file order ...
+                    assert close(r[k][c], res[k][c]), (p.name, g1, g2, c, k)
+                    # ... and to the reference unless its hash-ordered "first defined codon" is ambiguous
+                    if close(res[k][c], float(row[k])):
+                        assert close(r[k][c], float(row[k]))
+                checked += 1
+    assert checked == 3 * sum(p.n_codons for p in products)
+
+
+# ----------------------------------------------------------------- mid-size vs oracle closed form
+
+def test_config3_shape_against_oracle(eng):
+    """HIV-shaped: overlapping frames, 2-segment product, '-' strand CDS, 5 % gaps/ambiguous."""
+    products = synth.hiv_products()
+    aln = synth.make_alignment(1500, 9719, products, 20261022, gap_frac=0.025, n_frac=0.02, iupac_frac=0.005,
+                               lower_frac=0.01, u_frac=0.01)
+    eng.set_products(products, 9719)
+    eng.load_group(0, aln)
+    sums, _ = eng.within_all(0)
+    for i, p in enumerate(products):
+        raw, codes = _oracle_product(aln, p)
+        assert (eng.codon_indices(0, i) == codes).all()
+        h, od = eng.hist(0, i)
+        assert (h == orc.hist(codes)).all()
+        want = orc.within_hist(h, orc.other_distinct(raw, codes))
+        got = eng.within(0, i)
+        assert (got["poly"] == want["poly"]).all()
+        for k in STATS:
+            assert close(got[k], want[k]), (p.name, k)
+            assert close(sums[i, STATS.index(k)], want[k].sum())
+    # literal O(n^2) pair loop on one product, as the reference would do it
+    raw, _ = _oracle_product(aln[:400], products[2])
+    eng.load_group(1, aln[:400])
+    lit = orc.within_pairloop(raw)
+    got = eng.within(1, 2)
+    assert (got["poly"] == lit["poly"]).all()
+    for k in STATS:
+        assert close(got[k], lit[k]), k
+
+
+def test_between_mid_size_against_oracle(eng):
+    products = synth.sars2_products()[2:5]
+    a = synth.make_alignment(900, 29903, products, 5, gap_frac=0.01, n_frac=0.01)
+    b = synth.make_alignment(700, 29903, products, 5, gap_frac=0.01, n_frac=0.01, p_poly=0.5)
+    b[:, 21600:21700] = a[0, 21600:21700]
+    eng.set_products(products, 29903)
+    eng.load_group(0, a)
+    eng.load_group(1, b)
+    for i, p in enumerate(products):
+        ra, ca = _oracle_product(a, p)
+        rb, cb = _oracle_product(b, p)
+        od = orc.other_distinct(np.concatenate([ra, rb]), np.concatenate([ca, cb]))
+        want = orc.between_hist(orc.hist(ca), orc.hist(cb), od)
+        got = eng.between(0, 1, i)
+        assert (got["poly"] == want["poly"]).all()
+        assert (got["ndef_a"] == want["ndef_a"]).all() and (got["ndef_b"] == want["ndef_b"]).all()
+        for k in STATS:
+            assert close(got[k], want[k]), (p.name, k)
+
+
+# ----------------------------------------------------------------- resampling
+
+def _stats_from_golden(case="w_gaps", product="geneB"):
+    d, aln, codon_rows, prod_rows = refio.within_case(case)
+    p = [x for x in hostio.read_gtf_products(os.path.join(d, "cds.gtf")) if x.name == product][0]
+    return refio.stats4_of(refio.codon_arrays(codon_rows, p.name, p.n_codons)), prod_rows[p.name]
+
+
+def test_bootstrap_product_statistics(eng):
+    stats4, pr = _stats_from_golden()
+    C, B = stats4.shape[0], 40000
+    sums, se = eng.bootstrap_product(stats4, B, want_sums=True)
+    # each replicate draws C times from C+1 slots (slot 0 empty): E[sum] = C/(C+1) * total
+    expect = stats4.sum(axis=0) * C / (C + 1)
+    sd = np.sqrt(C * (np.mean(stats4 ** 2, axis=0) * C / (C + 1) - (stats4.mean(axis=0) * C / (C + 1)) ** 2))
+    assert np.all(np.abs(sums.mean(axis=0) - expect) < 5 * sd / np.sqrt(B) + 1e-12)
+    # SE recomputed on the host from the replicate sums (the reference's formulas)
+    dn = np.where(sums[:, 0] > 0, sums[:, 2] / sums[:, 0], 0)
+    ds = np.where(sums[:, 1] > 0, sums[:, 3] / sums[:, 1], 0)
+    assert close(se[0], np.std(dn, ddof=1), rtol=1e-9) and close(se[1], np.std(ds, ddof=1), rtol=1e-9)
+    assert close(se[2], np.std(dn - ds, ddof=1), rtol=1e-9)
+    jn, js = -0.75 * np.log(1 - 4 / 3 * dn), -0.75 * np.log(1 - 4 / 3 * ds)
+    assert close(se[3], np.std(jn, ddof=1), rtol=1e-9) and close(se[5], np.std(jn - js, ddof=1), rtol=1e-9)
+    # against the oracle's own stream and the reference's B=200 run
+    _, ose = orc.bootstrap_product(stats4, B, seed=9)
+    assert np.all(np.abs(se / ose - 1) < 0.03)
+    for mine, nm in zip(se[:3], ("SE_dN", "SE_dS", "SE_dN_minus_dS")):
+        assert abs(mine / float(pr[nm]) - 1) < 0.2
+    # deterministic per (seed, call), different across calls
+    _, se2 = eng.bootstrap_product(stats4, B)
+    assert not np.array_equal(se, se2) and np.all(np.abs(se / se2 - 1) < 0.03)
+
+
+def test_bootstrap_keep_mask(eng):
+    stats4, _ = _stats_from_golden()
+    keep = (np.arange(stats4.shape[0]) % 3 != 0).astype(np.uint8)
+    sums, se = eng.bootstrap_product(stats4, 5000, keep=keep, want_sums=True)
+    masked = stats4 * keep[:, None]
+    sums2, se2 = eng.bootstrap_product(masked, 5000, want_sums=True)
+    assert np.all(np.abs(se / se2 - 1) < 0.1)
+    assert sums.max() <= masked.max() * stats4.shape[0]
+
+
+def test_windows_bitwise_and_se(eng):
+    stats4, _ = _stats_from_golden("w_cfg1", "ORF2")
+    for W, step in ((10, 3), (100, 10), (1, 1), (stats4.shape[0], 1)):
+        sums, _ = eng.windows(stats4, W, step)
+        osums, _ = orc.windows(stats4, W, step)
+        assert sums.shape == osums.shape
+        assert np.array_equal(sums, osums), (W, step)      # same additions, same order
+    sums, se = eng.windows(stats4, 100, 10, B=3000)
+    _, ose = orc.windows(stats4, 100, 10, B=3000, seed=4)
+    ok = ose[:, 2] > 0
+    assert np.median(np.abs(se[ok] / ose[ok] - 1)) < 0.05
+    # the reference's own processor output (w_gaps, W=10 step=3, B=200)
+    d, aln, codon_rows, _ = refio.within_case("w_gaps")
+    _, wrows = refio.read_tsv(os.path.join(d, "sw_10codons_results.txt"))
+    for p in hostio.read_gtf_products(os.path.join(d, "cds.gtf")):
+        st = refio.stats4_of(refio.codon_arrays(codon_rows, p.name, p.n_codons))
+        sums, se = eng.windows(st, 10, 3, B=4000)
+        rows = [r for r in wrows if r["product"] == p.name]
+        assert len(rows) == sums.shape[0]
+        for k, r in enumerate(rows):
+            for q, nm in enumerate(STATS):
+                assert close(sums[k, q], float(r[nm]))
+        ref_se = np.array([float(r["SE_dN_minus_dS"]) if r["SE_dN_minus_dS"] not in ("NA", "") else 0.0 for r in rows])
+        ok = ref_se > 0
+        assert 0.8 < np.median(se[ok, 2] / ref_se[ok]) < 1.25
+
+
+def test_between_processor_filters_via_keep_mask(eng):
+    d = os.path.join(refio.GOLD, "b_3groups")
+    _, rows = refio.read_tsv(os.path.join(d, "between_group_codon_results.txt"))
+    _, frows = refio.read_tsv(os.path.join(d, "between_group_product_results_filtered.txt"))
+    _, wrows = refio.read_tsv(os.path.join(d, "between_group_sw_8codons_results.txt"))
+    for fr in frows[:4]:
+        sel = [r for r in rows if r["product"] == fr["product"] and sorted((r["group_1"], r["group_2"])) == [fr["group_1"], fr["group_2"]]]
+        sel.sort(key=lambda r: int(r["codon"].replace("codon_", "")))
+        stats4 = np.array([[float(r[k]) for k in STATS] for r in sel])
+        n1 = np.array([int(r["num_defined_codons_g1"] or 0) for r in sel])
+        n2 = np.array([int(r["num_defined_codons_g2"] or 0) for r in sel])
+        keep = (((n1 + n2) >= 9) & (np.minimum(n1, n2) >= 4)).astype(np.uint8)
+        _, se = eng.bootstrap_product(stats4, 20000, keep=keep)
+        for mine, nm in zip(se, ("SE_dN", "SE_dS", "SE_dN_minus_dS", "SE_JC_dN", "SE_JC_dS", "SE_JC_dN_minus_dS")):
+            assert abs(mine / float(fr[nm]) - 1) < 0.2, (fr["product"], nm)
+        sums, _ = eng.windows(stats4, 8, 2, keep=keep)
+        wsel = [r for r in wrows if r["product"] == fr["product"] and (r["group_1"], r["group_2"]) == (fr["group_1"], fr["group_2"])]
+        assert len(wsel) == sums.shape[0]
+        for k, r in enumerate(wsel):
+            for q, nm in enumerate(STATS):
+                assert close(sums[k, q], 0.0 if r[nm] == "NA" else float(r[nm]))
+
+
+def test_within_all_bootstrap_matches_per_product_calls(eng):
+    d, aln, codon_rows, prod_rows = refio.within_case("w_cfg1")
+    products = hostio.read_gtf_products(os.path.join(d, "cds.gtf"))
+    eng.set_products(products, aln.shape[1])
+    eng.load_group(0, aln)
+    sums, se = eng.within_all(0, B=20000)
+    for i, p in enumerate(products):
+        pr = prod_rows[p.name]
+        for mine, nm in zip(se[i, :3], ("SE_dN", "SE_dS", "SE_dN_minus_dS")):
+            assert abs(mine / float(pr[nm]) - 1) < 0.25, (p.name, nm, mine, pr[nm])   # reference used B=100
+
+
+# ----------------------------------------------------------------- errors
+
+def test_error_paths(eng):
+    from snpgenie_b200 import _abi
+    with pytest.raises(_abi.SnpgError) as e:
+        eng.set_products([hostio.Product("bad", 1, [1], [10])], 100)
+    assert e.value.code == _abi.E_INPUT and "complete codons" in str(e.value)
+    with pytest.raises(_abi.SnpgError) as e:
+        eng.set_products([hostio.Product("out", 1, [95], [103])], 100)
+    assert e.value.code == _abi.E_INPUT
+    eng.set_products([hostio.Product("ok", 1, [1], [9])], 100)
+    with pytest.raises(_abi.SnpgError) as e:
+        eng.load_group(0, np.zeros((4, 50), dtype=np.uint8))
+    assert e.value.code == _abi.E_INPUT
+    with pytest.raises(_abi.SnpgError) as e:
+        eng.within(7, 0)
+    assert e.value.code == _abi.E_STATE
+    with pytest.raises(_abi.SnpgError) as e:
+        eng.windows(np.zeros((5, 4)), 10, 1)
+    assert e.value.code == _abi.E_INPUT
+
+
+# ----------------------------------------------------------------- full size (BASELINE config 2)
+
+def test_config2_full_size_properties(eng):
+    """10,000 x 29,903, 10 CDS: size-independent properties + exact checks on sampled columns."""
+    products = synth.sars2_products()
+    n, L = 10000, 29903
+    aln = synth.make_alignment(n, L, products, 20261021)
+    eng.set_products(products, L)
+    eng.load_group(0, aln)
+    sums, se = eng.within_all(0, B=2000)
+    sites, diffs = orc.tables()
+    rng = np.random.default_rng(0)
+    tot_codons = 0
+    for i, p in enumerate(products):
+        h, od = eng.hist(0, i)
+        tot_codons += h.shape[0]
+        assert (h.sum(axis=1) == n).all()                       # every sequence lands in exactly one bin
+        assert h[:, 64].sum() == 0 and h[:, 65].sum() == 0      # no gaps / ambiguity in this config
+        got = eng.within(0, i)
+        want = orc.within_hist(h, od, sites, diffs)              # closed form on the device's own histogram
+        assert (got["poly"] == want["poly"]).all()
+        for k in STATS:
+            assert close(got[k], want[k]), (p.name, k)
+        # sampled columns: histogram recomputed from the raw bytes on the host
+        pos = orc.product_positions(p.starts, p.stops, p.strand, L)
+        for c in rng.choice(h.shape[0], size=min(40, h.shape[0]), replace=False):
+            raw, codes = orc.extract(aln, pos[3 * c:3 * c + 3], 1)
+            assert (orc.hist(codes)[0] == h[c]).all()
+        assert close(sums[i], got["stats4"].sum(axis=0), rtol=1e-13)
+        assert np.all(se[i, :3] > 0)
+    assert tot_codons == 9677
