@@ -97,6 +97,9 @@ int snpg_group_size(const snpg_ctx *ctx, int group, uint64_t *n_seqs);
  * device (needed by snpg_get_codon_indices and the between-group first-defined
  * rule); 0 frees it after the histogram pass. */
 #define SNPG_OPT_KEEP_CODES 1
+/* SNPG_OPT_PROFILE (default 0): bracket every kernel launch with CUDA events on
+ * the launch stream and accumulate per-kernel milliseconds (snpg_get_profile). */
+#define SNPG_OPT_PROFILE 2
 int snpg_set_option(snpg_ctx *ctx, int option, int64_t value);
 
 /* ---- test hooks for the bit-exact checks ---------------------------------
@@ -162,6 +165,22 @@ int snpg_bootstrap_all_device(snpg_ctx *ctx, const double *d_stats4_full, int64_
 int snpg_product_sums_device(snpg_ctx *ctx, const double *d_stats4_full, double *prod_sums);
 /* SD over replicates from a DEVICE buffer rep [n_items][B][4] -> host se_out [n_items][6]. */
 int snpg_rep_moments_device(snpg_ctx *ctx, const double *d_rep, int64_t n_items, int64_t B, double *se_out);
+
+/* Launch all kernels on a caller-owned CUDA stream (a cudaStream_t, e.g. torch's
+ * current stream) instead of the ctx's own; NULL restores an internal stream. */
+int snpg_set_stream(snpg_ctx *ctx, void *cuda_stream);
+
+/* Per-kernel device time measured with CUDA events (needs SNPG_OPT_PROFILE=1). */
+#define SNPG_K_PACK 0
+#define SNPG_K_HIST 1
+#define SNPG_K_STATS 2
+#define SNPG_K_SUMS 3
+#define SNPG_K_BOOT 4
+#define SNPG_K_MOMENTS 5
+#define SNPG_K_WINDOW 6
+#define SNPG_K_OTHER 7
+#define SNPG_N_KERNEL_KINDS 8
+int snpg_get_profile(snpg_ctx *ctx, double *ms /*[8]*/, int64_t *calls /*[8]*/, int reset);
 
 /* Kernel launches issued by this ctx since creation (bench.py's gpu_launches). */
 int64_t snpg_launch_count(const snpg_ctx *ctx);

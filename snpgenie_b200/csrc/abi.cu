@@ -65,6 +65,14 @@ struct snpg_ctx {
     DevBuf staging[2], s_stats, s_poly, s_nda, s_ndb, s_cmp, s_cons, s_sums, s_rep, s_se, s_misc, s_in;
     int64_t launches = 0;
     uint32_t call_id = 0;
+    // optional per-kernel timing (CUDA events on the launch stream)
+    bool profile = false;
+    bool own_stream = true;
+    struct Span { cudaEvent_t e0, e1; int kind; };
+    std::vector<Span> spans;        // recorded, not yet resolved
+    std::vector<cudaEvent_t> free_events;
+    double kernel_ms[SNPG_N_KERNEL_KINDS] = {0};
+    int64_t kernel_calls[SNPG_N_KERNEL_KINDS] = {0};
 };
 
 namespace {
@@ -77,6 +85,42 @@ int fail(snpg_ctx *ctx, int code, const char *fmt, ...) {
     va_end(ap);
     if (ctx) ctx->err = buf; else g_create_error = buf;
     return code;
+}
+
+cudaEvent_t take_event(snpg_ctx *ctx) {
+    if (!ctx->free_events.empty()) { cudaEvent_t e = ctx->free_events.back(); ctx->free_events.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+// Brackets one kernel launch with events when profiling is on; counts it always.
+struct Launch {
+    snpg_ctx *ctx; int kind; cudaEvent_t e0 = nullptr;
+    Launch(snpg_ctx *c, int k) : ctx(c), kind(k) {
+        ctx->launches++;
+        if (ctx->profile) { e0 = take_event(ctx); cudaEventRecord(e0, ctx->stream); }
+    }
+    ~Launch() {
+        if (e0) { cudaEvent_t e1 = take_event(ctx); cudaEventRecord(e1, ctx->stream); ctx->spans.push_back({e0, e1, kind}); }
+    }
+};
+
+// after a stream synchronise: turn recorded spans into accumulated milliseconds
+void resolve_spans(snpg_ctx *ctx) {
+    for (auto &sp : ctx->spans) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, sp.e0, sp.e1) == cudaSuccess) { ctx->kernel_ms[sp.kind] += ms; ctx->kernel_calls[sp.kind]++; }
+        ctx->free_events.push_back(sp.e0);
+        ctx->free_events.push_back(sp.e1);
+    }
+    ctx->spans.clear();
+}
+
+cudaError_t sync_stream(snpg_ctx *ctx) {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && !ctx->spans.empty()) resolve_spans(ctx);
+    return e;
 }
 
 #define CU(ctx, call)                                                                                   \
@@ -131,10 +175,9 @@ int prepare_group(snpg_ctx *ctx, Group &g, uint64_t n_seqs) {
 }
 
 int finish_group(snpg_ctx *ctx, Group &g) {
-    launch_hist(g.codes.as<uint8_t>(), g.n_pad, ctx->shard_count, g.hist.as<uint32_t>(), ctx->stream);
-    ctx->launches++;
+    { Launch l(ctx, SNPG_K_HIST); launch_hist(g.codes.as<uint8_t>(), g.n_pad, ctx->shard_count, g.hist.as<uint32_t>(), ctx->stream); }
     CU(ctx, cudaGetLastError());
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     if (!ctx->keep_codes) { g.codes.release(); g.has_codes = false; }
     g.loaded = true;
     return SNPG_OK;
@@ -201,7 +244,9 @@ void snpg_destroy(snpg_ctx *ctx) {
         if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
         if (ctx->ev_packed[i]) cudaEventDestroy(ctx->ev_packed[i]);
     }
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    resolve_spans(ctx);
+    for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
+    if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     delete ctx;
 }
@@ -209,6 +254,7 @@ void snpg_destroy(snpg_ctx *ctx) {
 int snpg_set_option(snpg_ctx *ctx, int option, int64_t value) {
     if (!ctx) return SNPG_E_ARG;
     if (option == SNPG_OPT_KEEP_CODES) { ctx->keep_codes = value != 0; return SNPG_OK; }
+    if (option == SNPG_OPT_PROFILE) { ctx->profile = value != 0; return SNPG_OK; }
     return fail(ctx, SNPG_E_ARG, "unknown option %d", option);
 }
 
@@ -333,10 +379,12 @@ int snpg_load_group(snpg_ctx *ctx, int group, const uint8_t *bases, uint64_t n_s
                                       (size_t)row_stride, (size_t)width, (size_t)rows, cudaMemcpyHostToDevice, ctx->copy_stream));
             CU(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
             CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
-            launch_pack(ctx->staging[b].as<uint8_t>(), pitch, rows, r0, ctx->d_map.as<CodonMap>(), ctx->shard_count,
-                        g.codes.as<uint8_t>(), g.n_pad, g.other.as<uint32_t>(), g.other.as<uint32_t>() + ctx->shard_count,
-                        ctx->stream);
-            ctx->launches++;
+            {
+                Launch l(ctx, SNPG_K_PACK);
+                launch_pack(ctx->staging[b].as<uint8_t>(), pitch, rows, r0, ctx->d_map.as<CodonMap>(), ctx->shard_count,
+                            g.codes.as<uint8_t>(), g.n_pad, g.other.as<uint32_t>(), g.other.as<uint32_t>() + ctx->shard_count,
+                            ctx->stream);
+            }
             CU(ctx, cudaGetLastError());
             CU(ctx, cudaEventRecord(ctx->ev_packed[b], ctx->stream));
         }
@@ -359,10 +407,12 @@ int snpg_load_group_device(snpg_ctx *ctx, int group, const uint8_t *d_bases, uin
     const int64_t rows_per = (int64_t)4 << 20;  // keeps gridDim.y < 65536
     for (int64_t r0 = 0; r0 < (int64_t)n_seqs && ctx->shard_count > 0; r0 += rows_per) {
         const int64_t rows = std::min<int64_t>(rows_per, (int64_t)n_seqs - r0);
-        launch_pack(d_bases + (size_t)r0 * row_stride + ctx->col_lo, (int64_t)row_stride, rows, r0, ctx->d_map.as<CodonMap>(),
-                    ctx->shard_count, g.codes.as<uint8_t>(), g.n_pad, g.other.as<uint32_t>(),
-                    g.other.as<uint32_t>() + ctx->shard_count, ctx->stream);
-        ctx->launches++;
+        {
+            Launch l(ctx, SNPG_K_PACK);
+            launch_pack(d_bases + (size_t)r0 * row_stride + ctx->col_lo, (int64_t)row_stride, rows, r0, ctx->d_map.as<CodonMap>(),
+                        ctx->shard_count, g.codes.as<uint8_t>(), g.n_pad, g.other.as<uint32_t>(),
+                        g.other.as<uint32_t>() + ctx->shard_count, ctx->stream);
+        }
         CU(ctx, cudaGetLastError());
     }
     return finish_group(ctx, g);
@@ -395,11 +445,10 @@ int snpg_get_codon_indices(snpg_ctx *ctx, int group, int product, uint8_t *out) 
     if (C == 0) return SNPG_OK;
     const size_t bytes = (size_t)g.n * (size_t)C;
     CU(ctx, ctx->s_misc.ensure(bytes));
-    launch_untranspose(g.codes.as<uint8_t>(), g.n_pad, (int64_t)g.n, c0, C, ctx->s_misc.as<uint8_t>(), ctx->stream);
-    ctx->launches++;
+    { Launch l(ctx, SNPG_K_OTHER); launch_untranspose(g.codes.as<uint8_t>(), g.n_pad, (int64_t)g.n, c0, C, ctx->s_misc.as<uint8_t>(), ctx->stream); }
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaMemcpyAsync(out, ctx->s_misc.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     return SNPG_OK;
 }
 
@@ -421,7 +470,7 @@ int snpg_get_hist(snpg_ctx *ctx, int group, int product, uint32_t *out, uint8_t 
         CU(ctx, cudaMemcpyAsync(hi.data(), g.other.as<uint32_t>() + ctx->shard_count + c0, sizeof(uint32_t) * (size_t)C,
                                 cudaMemcpyDeviceToHost, ctx->stream));
     }
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     if (other_distinct)
         for (int64_t c = 0; c < C; c++) other_distinct[c] = (lo[(size_t)c] != kOtherNone && lo[(size_t)c] != hi[(size_t)c]) ? 1 : 0;
     return SNPG_OK;
@@ -439,9 +488,11 @@ static int run_stats(snpg_ctx *ctx, bool between, const Group &ga, const Group &
     CU(ctx, ctx->s_stats.ensure(sizeof(double) * 4 * (size_t)C));
     StatsOut o{ctx->s_poly.as<uint8_t>(), ctx->s_nda.as<uint32_t>(), ctx->s_ndb.as<uint32_t>(),
                ctx->s_cmp.as<unsigned long long>(), ctx->s_stats.as<double>(), ctx->s_cons.as<uint8_t>()};
-    if (between) launch_between_stats(view_of(ctx, ga, c0), view_of(ctx, gb, c0), C, ctx->d_tables.as<double>(), o, ctx->stream);
-    else launch_within_stats(view_of(ctx, ga, c0), C, ctx->d_tables.as<double>(), o, ctx->stream);
-    ctx->launches++;
+    {
+        Launch l(ctx, SNPG_K_STATS);
+        if (between) launch_between_stats(view_of(ctx, ga, c0), view_of(ctx, gb, c0), C, ctx->d_tables.as<double>(), o, ctx->stream);
+        else launch_within_stats(view_of(ctx, ga, c0), C, ctx->d_tables.as<double>(), o, ctx->stream);
+    }
     CU(ctx, cudaGetLastError());
     if (poly) CU(ctx, cudaMemcpyAsync(poly, o.poly, (size_t)C, cudaMemcpyDeviceToHost, ctx->stream));
     if (cons) CU(ctx, cudaMemcpyAsync(cons, o.conserved, (size_t)C, cudaMemcpyDeviceToHost, ctx->stream));
@@ -449,7 +500,7 @@ static int run_stats(snpg_ctx *ctx, bool between, const Group &ga, const Group &
     if (ndb) CU(ctx, cudaMemcpyAsync(ndb, o.ndef_b, sizeof(uint32_t) * (size_t)C, cudaMemcpyDeviceToHost, ctx->stream));
     if (cmp) CU(ctx, cudaMemcpyAsync(cmp, o.comparisons, sizeof(uint64_t) * (size_t)C, cudaMemcpyDeviceToHost, ctx->stream));
     if (stats4) CU(ctx, cudaMemcpyAsync(stats4, o.stats4, sizeof(double) * 4 * (size_t)C, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     return SNPG_OK;
 }
 
@@ -505,13 +556,12 @@ int snpg_bootstrap_product(snpg_ctx *ctx, const double *stats4, const uint8_t *k
     CU(ctx, ctx->s_rep.ensure(sizeof(double) * 4 * (size_t)B));
     CU(ctx, ctx->s_se.ensure(sizeof(double) * 6));
     const uint32_t sid = 0x10000u + ctx->call_id++;
-    launch_bootstrap(ctx->s_in.as<double>(), ctx->s_misc.as<int64_t>(), 1, 0, B, ctx->seed, sid, ctx->s_rep.as<double>(), ctx->stream);
-    launch_rep_moments(ctx->s_rep.as<double>(), 1, B, ctx->s_se.as<double>(), ctx->stream);
-    ctx->launches += 2;
+    { Launch l(ctx, SNPG_K_BOOT); launch_bootstrap(ctx->s_in.as<double>(), ctx->s_misc.as<int64_t>(), 1, 0, B, ctx->seed, sid, ctx->s_rep.as<double>(), ctx->stream); }
+    { Launch l(ctx, SNPG_K_MOMENTS); launch_rep_moments(ctx->s_rep.as<double>(), 1, B, ctx->s_se.as<double>(), ctx->stream); }
     CU(ctx, cudaGetLastError());
     if (sums_out) CU(ctx, cudaMemcpyAsync(sums_out, ctx->s_rep.p, sizeof(double) * 4 * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
     if (se_out) CU(ctx, cudaMemcpyAsync(se_out, ctx->s_se.p, sizeof(double) * 6, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     return SNPG_OK;
 }
 
@@ -528,8 +578,7 @@ int snpg_windows(snpg_ctx *ctx, const double *stats4, const uint8_t *keep, int64
     if (int rc = upload_stats(ctx, stats4, keep, C)) return rc;
     if (win_sums) {
         CU(ctx, ctx->s_sums.ensure(sizeof(double) * 4 * (size_t)nwin));
-        launch_window_sums(ctx->s_in.as<double>(), W, step, nwin, ctx->s_sums.as<double>(), ctx->stream);
-        ctx->launches++;
+        { Launch l(ctx, SNPG_K_WINDOW); launch_window_sums(ctx->s_in.as<double>(), W, step, nwin, ctx->s_sums.as<double>(), ctx->stream); }
         CU(ctx, cudaGetLastError());
         CU(ctx, cudaMemcpyAsync(win_sums, ctx->s_sums.p, sizeof(double) * 4 * (size_t)nwin, cudaMemcpyDeviceToHost, ctx->stream));
     }
@@ -541,17 +590,16 @@ int snpg_windows(snpg_ctx *ctx, const double *stats4, const uint8_t *keep, int64
         const uint32_t sid = 0x20000u + ctx->call_id++;
         for (int64_t w0 = 0; w0 < nwin; w0 += batch) {
             const int64_t nb = std::min(batch, nwin - w0);
-            launch_window_bootstrap(ctx->s_in.as<double>(), W, step, w0, nb, B, ctx->seed, sid, ctx->s_rep.as<double>(), ctx->stream);
-            launch_rep_moments(ctx->s_rep.as<double>(), nb, B, ctx->s_se.as<double>(), ctx->stream);
-            ctx->launches += 2;
+            { Launch l(ctx, SNPG_K_WINDOW); launch_window_bootstrap(ctx->s_in.as<double>(), W, step, w0, nb, B, ctx->seed, sid, ctx->s_rep.as<double>(), ctx->stream); }
+            { Launch l(ctx, SNPG_K_MOMENTS); launch_rep_moments(ctx->s_rep.as<double>(), nb, B, ctx->s_se.as<double>(), ctx->stream); }
             CU(ctx, cudaGetLastError());
             CU(ctx, cudaMemcpyAsync(se6.data(), ctx->s_se.p, sizeof(double) * 6 * (size_t)nb, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            CU(ctx, sync_stream(ctx));
             for (int64_t k = 0; k < nb; k++)
                 for (int q = 0; q < 3; q++) win_se[3 * (w0 + k) + q] = se6[(size_t)(6 * k + q)];
         }
     }
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     return SNPG_OK;
 }
 
@@ -561,10 +609,9 @@ int snpg_within_stats_device(snpg_ctx *ctx, int group, double *d_stats4) {
     if (int rc = bind(ctx)) return rc;
     const Group &g = ctx->groups[group];
     StatsOut o{nullptr, nullptr, nullptr, nullptr, d_stats4, nullptr};
-    launch_within_stats(view_of(ctx, g, 0), ctx->shard_count, ctx->d_tables.as<double>(), o, ctx->stream);
-    ctx->launches++;
+    { Launch l(ctx, SNPG_K_STATS); launch_within_stats(view_of(ctx, g, 0), ctx->shard_count, ctx->d_tables.as<double>(), o, ctx->stream); }
     CU(ctx, cudaGetLastError());
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     return SNPG_OK;
 }
 
@@ -573,11 +620,13 @@ int snpg_bootstrap_all_device(snpg_ctx *ctx, const double *d_stats4_full, int64_
     NEED(ctx, ctx->n_products > 0, SNPG_E_STATE, "no products set");
     NEED(ctx, b_first >= 0 && b_count > 0, SNPG_E_ARG, "bad replicate range");
     if (int rc = bind(ctx)) return rc;
-    launch_bootstrap(d_stats4_full, ctx->d_full_ofs.as<int64_t>(), ctx->n_products, b_first, b_count, ctx->seed, 0x30000u, d_rep_out,
-                     ctx->stream);
-    ctx->launches++;
+    {
+        Launch l(ctx, SNPG_K_BOOT);
+        launch_bootstrap(d_stats4_full, ctx->d_full_ofs.as<int64_t>(), ctx->n_products, b_first, b_count, ctx->seed, 0x30000u, d_rep_out,
+                         ctx->stream);
+    }
     CU(ctx, cudaGetLastError());
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     return SNPG_OK;
 }
 
@@ -586,11 +635,10 @@ int snpg_product_sums_device(snpg_ctx *ctx, const double *d_stats4_full, double 
     NEED(ctx, ctx->n_products > 0, SNPG_E_STATE, "no products set");
     if (int rc = bind(ctx)) return rc;
     CU(ctx, ctx->s_sums.ensure(sizeof(double) * 4 * (size_t)ctx->n_products));
-    launch_product_sums(d_stats4_full, ctx->d_full_ofs.as<int64_t>(), ctx->n_products, ctx->s_sums.as<double>(), ctx->stream);
-    ctx->launches++;
+    { Launch l(ctx, SNPG_K_SUMS); launch_product_sums(d_stats4_full, ctx->d_full_ofs.as<int64_t>(), ctx->n_products, ctx->s_sums.as<double>(), ctx->stream); }
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaMemcpyAsync(prod_sums, ctx->s_sums.p, sizeof(double) * 4 * (size_t)ctx->n_products, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     return SNPG_OK;
 }
 
@@ -598,11 +646,10 @@ int snpg_rep_moments_device(snpg_ctx *ctx, const double *d_rep, int64_t n_items,
     if (!ctx || !d_rep || !se_out || n_items <= 0 || B < 2) return SNPG_E_ARG;
     if (int rc = bind(ctx)) return rc;
     CU(ctx, ctx->s_se.ensure(sizeof(double) * 6 * (size_t)n_items));
-    launch_rep_moments(d_rep, n_items, B, ctx->s_se.as<double>(), ctx->stream);
-    ctx->launches++;
+    { Launch l(ctx, SNPG_K_MOMENTS); launch_rep_moments(d_rep, n_items, B, ctx->s_se.as<double>(), ctx->stream); }
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaMemcpyAsync(se_out, ctx->s_se.p, sizeof(double) * 6 * (size_t)n_items, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     return SNPG_OK;
 }
 
@@ -616,25 +663,46 @@ int snpg_within_all(snpg_ctx *ctx, int group, int64_t B, double *prod_sums, doub
     CU(ctx, ctx->s_stats.ensure(sizeof(double) * 4 * (size_t)std::max<int64_t>(1, cnt)));
     CU(ctx, ctx->s_sums.ensure(sizeof(double) * 4 * (size_t)P));
     StatsOut o{nullptr, nullptr, nullptr, nullptr, ctx->s_stats.as<double>(), nullptr};
-    launch_within_stats(view_of(ctx, g, 0), cnt, ctx->d_tables.as<double>(), o, ctx->stream);
-    launch_product_sums(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), P, ctx->s_sums.as<double>(), ctx->stream);
-    ctx->launches += 2;
+    { Launch l(ctx, SNPG_K_STATS); launch_within_stats(view_of(ctx, g, 0), cnt, ctx->d_tables.as<double>(), o, ctx->stream); }
+    { Launch l(ctx, SNPG_K_SUMS); launch_product_sums(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), P, ctx->s_sums.as<double>(), ctx->stream); }
     const bool boot = prod_se && B >= 2;
     if (boot) {
         CU(ctx, ctx->s_rep.ensure(sizeof(double) * 4 * (size_t)(B * P)));
         CU(ctx, ctx->s_se.ensure(sizeof(double) * 6 * (size_t)P));
-        launch_bootstrap(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), P, 0, B, ctx->seed, 0x40000u + ctx->call_id++,
-                         ctx->s_rep.as<double>(), ctx->stream);
-        launch_rep_moments(ctx->s_rep.as<double>(), P, B, ctx->s_se.as<double>(), ctx->stream);
-        ctx->launches += 2;
+        {
+            Launch l(ctx, SNPG_K_BOOT);
+            launch_bootstrap(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), P, 0, B, ctx->seed, 0x40000u + ctx->call_id++,
+                             ctx->s_rep.as<double>(), ctx->stream);
+        }
+        { Launch l(ctx, SNPG_K_MOMENTS); launch_rep_moments(ctx->s_rep.as<double>(), P, B, ctx->s_se.as<double>(), ctx->stream); }
     }
     CU(ctx, cudaGetLastError());
     if (prod_sums) CU(ctx, cudaMemcpyAsync(prod_sums, ctx->s_sums.p, sizeof(double) * 4 * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
     if (boot) CU(ctx, cudaMemcpyAsync(prod_se, ctx->s_se.p, sizeof(double) * 6 * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, sync_stream(ctx));
     return SNPG_OK;
 }
 
 int64_t snpg_launch_count(const snpg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int snpg_set_stream(snpg_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return SNPG_E_ARG;
+    if (int rc = bind(ctx)) return rc;
+    CU(ctx, sync_stream(ctx));
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (cuda_stream) { ctx->stream = static_cast<cudaStream_t>(cuda_stream); ctx->own_stream = false; }
+    else { CU(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    return SNPG_OK;
+}
+
+int snpg_get_profile(snpg_ctx *ctx, double *ms, int64_t *calls, int reset) {
+    if (!ctx) return SNPG_E_ARG;
+    for (int k = 0; k < SNPG_N_KERNEL_KINDS; k++) {
+        if (ms) ms[k] = ctx->kernel_ms[k];
+        if (calls) calls[k] = ctx->kernel_calls[k];
+        if (reset) { ctx->kernel_ms[k] = 0; ctx->kernel_calls[k] = 0; }
+    }
+    return SNPG_OK;
+}
 
 }  // extern "C"

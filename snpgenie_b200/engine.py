@@ -72,6 +72,16 @@ class Engine:
     def set_option(self, option: int, value: int):
         self._ck(_abi.lib.snpg_set_option(self._ctx, option, value))
 
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self._ck(_abi.lib.snpg_set_stream(self._ctx, cuda_stream_ptr))
+
+    def profile(self, reset: bool = True) -> dict:
+        """{kernel kind: (milliseconds, launches)} accumulated since the last reset (needs OPT_PROFILE)."""
+        ms = np.zeros(len(_abi.KERNEL_KINDS))
+        calls = np.zeros(len(_abi.KERNEL_KINDS), dtype=np.int64)
+        self._ck(_abi.lib.snpg_get_profile(self._ctx, _ptr(ms, C.c_double), _ptr(calls, C.c_int64), int(reset)))
+        return {k: (float(ms[i]), int(calls[i])) for i, k in enumerate(_abi.KERNEL_KINDS)}
+
     # -- annotation ---------------------------------------------------------
     def set_products(self, products: list[Product], aln_len: int):
         seg_ofs, starts, stops, strand = products_to_csr(products)
