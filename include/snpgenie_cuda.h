@@ -93,9 +93,11 @@ int snpg_load_group_device(snpg_ctx *ctx, int group, const uint8_t *d_bases, uin
 int snpg_drop_group(snpg_ctx *ctx, int group);
 int snpg_group_size(const snpg_ctx *ctx, int group, uint64_t *n_seqs);
 
-/* Options: SNPG_OPT_KEEP_CODES (default 1) keeps the packed codon matrix on the
- * device (needed by snpg_get_codon_indices and the between-group first-defined
- * rule); 0 frees it after the histogram pass. */
+/* Options: SNPG_OPT_KEEP_CODES (default 1) materialises the packed codon matrix
+ * on the device (K1 then K2; needed by snpg_get_codon_indices and by the
+ * between-group "first defined codon" rule, bg:853-890).  With 0 the histogram
+ * is built straight from the alignment bytes by the fused kernel and no code
+ * matrix exists.  Set before loading a group. */
 #define SNPG_OPT_KEEP_CODES 1
 /* SNPG_OPT_PROFILE (default 0): bracket every kernel launch with CUDA events on
  * the launch stream and accumulate per-kernel milliseconds (snpg_get_profile). */
@@ -179,8 +181,9 @@ int snpg_set_stream(snpg_ctx *ctx, void *cuda_stream);
 #define SNPG_K_MOMENTS 5
 #define SNPG_K_WINDOW 6
 #define SNPG_K_OTHER 7
-#define SNPG_N_KERNEL_KINDS 8
-int snpg_get_profile(snpg_ctx *ctx, double *ms /*[8]*/, int64_t *calls /*[8]*/, int reset);
+#define SNPG_K_FUSED 8   /* pack + histogram in one pass (no code matrix kept) */
+#define SNPG_N_KERNEL_KINDS 9
+int snpg_get_profile(snpg_ctx *ctx, double *ms /*[9]*/, int64_t *calls /*[9]*/, int reset);
 
 /* Kernel launches issued by this ctx since creation (bench.py's gpu_launches). */
 int64_t snpg_launch_count(const snpg_ctx *ctx);

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libsnpgenie_cuda.so")
 OK, E_ARG, E_STATE, E_INPUT, E_CUDA, E_NOMEM = 0, -1, -2, -3, -4, -5
 CODE_UNDEF, CODE_OTHER, HIST_BINS = 64, 65, 66
 OPT_KEEP_CODES, OPT_PROFILE = 1, 2
-KERNEL_KINDS = ("pack", "hist", "stats", "sums", "bootstrap", "moments", "window", "other")
+KERNEL_KINDS = ("pack", "hist", "stats", "sums", "bootstrap", "moments", "window", "other", "fused")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

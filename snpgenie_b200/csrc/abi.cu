@@ -59,6 +59,11 @@ struct snpg_ctx {
     int64_t shard_first = 0, shard_count = 0;
     int64_t col_lo = 0, col_hi = 0;   // alignment columns this shard touches, [lo, hi)
     DevBuf d_map, d_local_ofs, d_full_ofs, d_tables;
+    // fused path (no code matrix): 16-byte column spans starting at base_al
+    int64_t base_al = 0, n_spans = 0;     // base_al = col_lo rounded down to 16
+    int64_t n_irr = 0;                    // codons the span runs cannot express
+    DevBuf d_runs, d_regular, d_irr_map, d_irr_idx, d_cons;
+    DevBuf t_codes, t_hist, t_other;      // irregular codons: compact K1+K2 scratch
     // groups
     Group groups[SNPG_MAX_GROUPS];
     // scratch
@@ -164,21 +169,72 @@ int prepare_group(snpg_ctx *ctx, Group &g, uint64_t n_seqs) {
     g.n = n_seqs;
     g.n_pad = (int64_t)((n_seqs + kRowPad - 1) / kRowPad) * kRowPad;
     const int64_t cnt = ctx->shard_count;
-    CU(ctx, g.codes.ensure((size_t)std::max<int64_t>(1, cnt * g.n_pad)));
+    if (ctx->keep_codes) CU(ctx, g.codes.ensure((size_t)std::max<int64_t>(1, cnt * g.n_pad)));
     CU(ctx, g.hist.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, cnt * kHistBins)));
     CU(ctx, g.other.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, 2 * cnt)));
     CU(ctx, cudaMemsetAsync(g.hist.p, 0, sizeof(uint32_t) * (size_t)(cnt * kHistBins), ctx->stream));
     CU(ctx, cudaMemsetAsync(g.other.p, 0xFF, sizeof(uint32_t) * (size_t)cnt, ctx->stream));
     CU(ctx, cudaMemsetAsync(g.other.as<uint32_t>() + cnt, 0, sizeof(uint32_t) * (size_t)cnt, ctx->stream));
-    g.has_codes = true;
+    g.has_codes = ctx->keep_codes;
+    if (!ctx->keep_codes && ctx->n_irr) {
+        CU(ctx, ctx->t_codes.ensure((size_t)(ctx->n_irr * g.n_pad)));
+        CU(ctx, ctx->t_hist.ensure(sizeof(uint32_t) * (size_t)(ctx->n_irr * kHistBins)));
+        CU(ctx, ctx->t_other.ensure(sizeof(uint32_t) * (size_t)(2 * ctx->n_irr)));
+        CU(ctx, cudaMemsetAsync(ctx->t_hist.p, 0, sizeof(uint32_t) * (size_t)(ctx->n_irr * kHistBins), ctx->stream));
+        CU(ctx, cudaMemsetAsync(ctx->t_other.p, 0xFF, sizeof(uint32_t) * (size_t)ctx->n_irr, ctx->stream));
+        CU(ctx, cudaMemsetAsync(ctx->t_other.as<uint32_t>() + ctx->n_irr, 0, sizeof(uint32_t) * (size_t)ctx->n_irr, ctx->stream));
+    }
+    return SNPG_OK;
+}
+
+// One block of rows [r0, r0+rows) whose bytes start at column base_al: d_block points at
+// (row r0, column base_al); row_bytes = readable bytes per row from there.
+int pack_block(snpg_ctx *ctx, Group &g, const uint8_t *d_block, int64_t pitch, int64_t rows, int64_t r0, int64_t row_bytes) {
+    uint32_t *omin = g.other.as<uint32_t>(), *omax = g.other.as<uint32_t>() + ctx->shard_count;
+    if (ctx->keep_codes) {
+        Launch l(ctx, SNPG_K_PACK);
+        launch_pack(d_block + (ctx->col_lo - ctx->base_al), pitch, rows, r0, ctx->d_map.as<CodonMap>(), ctx->shard_count,
+                    g.codes.as<uint8_t>(), g.n_pad, omin, omax, ctx->stream);
+    } else {
+        if (r0 == 0)   // the group's first sequence is the consensus every row is compared with
+            CU(ctx, cudaMemcpyAsync(ctx->d_cons.p, d_block, (size_t)std::min<int64_t>(row_bytes, ctx->n_spans * 16 + 16),
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
+        {
+            Launch l(ctx, SNPG_K_FUSED);
+            launch_fused_hist(d_block, pitch, rows, ctx->d_cons.as<uint8_t>(), ctx->n_spans, row_bytes, ctx->d_runs.as<SpanRun>(),
+                              g.hist.as<uint32_t>(), omin, omax, ctx->stream);
+        }
+        if (ctx->n_irr) {
+            Launch l(ctx, SNPG_K_PACK);
+            launch_pack(d_block, pitch, rows, r0, ctx->d_irr_map.as<CodonMap>(), ctx->n_irr, ctx->t_codes.as<uint8_t>(), g.n_pad,
+                        ctx->t_other.as<uint32_t>(), ctx->t_other.as<uint32_t>() + ctx->n_irr, ctx->stream);
+        }
+    }
+    CU(ctx, cudaGetLastError());
     return SNPG_OK;
 }
 
 int finish_group(snpg_ctx *ctx, Group &g) {
-    { Launch l(ctx, SNPG_K_HIST); launch_hist(g.codes.as<uint8_t>(), g.n_pad, ctx->shard_count, g.hist.as<uint32_t>(), ctx->stream); }
+    uint32_t *omin = g.other.as<uint32_t>(), *omax = g.other.as<uint32_t>() + ctx->shard_count;
+    if (ctx->keep_codes) {
+        Launch l(ctx, SNPG_K_HIST);
+        launch_hist(g.codes.as<uint8_t>(), g.n_pad, ctx->shard_count, g.hist.as<uint32_t>(), ctx->stream);
+    } else {
+        {
+            Launch l(ctx, SNPG_K_OTHER);
+            launch_fused_fixup(ctx->d_cons.as<uint8_t>(), ctx->col_lo - ctx->base_al, ctx->d_map.as<CodonMap>(),
+                               ctx->d_regular.as<uint8_t>(), ctx->shard_count, (uint32_t)g.n, g.hist.as<uint32_t>(), omin, omax,
+                               ctx->stream);
+        }
+        if (ctx->n_irr) {
+            { Launch l(ctx, SNPG_K_HIST); launch_hist(ctx->t_codes.as<uint8_t>(), g.n_pad, ctx->n_irr, ctx->t_hist.as<uint32_t>(), ctx->stream); }
+            Launch l(ctx, SNPG_K_OTHER);
+            launch_scatter_irregular(ctx->t_hist.as<uint32_t>(), ctx->t_other.as<uint32_t>(), ctx->t_other.as<uint32_t>() + ctx->n_irr,
+                                     ctx->d_irr_idx.as<int32_t>(), ctx->n_irr, g.hist.as<uint32_t>(), omin, omax, ctx->stream);
+        }
+    }
     CU(ctx, cudaGetLastError());
     CU(ctx, sync_stream(ctx));
-    if (!ctx->keep_codes) { g.codes.release(); g.has_codes = false; }
     g.loaded = true;
     return SNPG_OK;
 }
@@ -237,6 +293,8 @@ void snpg_destroy(snpg_ctx *ctx) {
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     for (auto &g : ctx->groups) { g.codes.release(); g.hist.release(); g.other.release(); }
     DevBuf *bufs[] = {&ctx->d_map, &ctx->d_local_ofs, &ctx->d_full_ofs, &ctx->d_tables, &ctx->staging[0], &ctx->staging[1],
+                      &ctx->d_runs, &ctx->d_regular, &ctx->d_irr_map, &ctx->d_irr_idx, &ctx->d_cons, &ctx->t_codes, &ctx->t_hist,
+                      &ctx->t_other,
                       &ctx->s_stats, &ctx->s_poly, &ctx->s_nda, &ctx->s_ndb, &ctx->s_cmp, &ctx->s_cons, &ctx->s_sums,
                       &ctx->s_rep, &ctx->s_se, &ctx->s_misc, &ctx->s_in};
     for (DevBuf *b : bufs) b->release();
@@ -320,6 +378,66 @@ int snpg_set_products(snpg_ctx *ctx, int n_products, const int64_t *seg_ofs, con
     std::vector<CodonMap> local(map_all.begin() + ctx->shard_first, map_all.begin() + ctx->shard_first + ctx->shard_count);
     for (auto &m : local) { m.p0 -= (int32_t)lo; m.p1 -= (int32_t)lo; m.p2 -= (int32_t)lo; }
 
+    // Fused-path description: which codons start in which 16-byte span.
+    {
+        const int64_t base = lo & ~(int64_t)15;
+        const int64_t n_spans = (hi - base + 15) / 16;
+        ctx->base_al = base;
+        ctx->n_spans = n_spans;
+        std::vector<SpanRun> runs((size_t)std::max<int64_t>(1, n_spans) * kSpanRuns, SpanRun{0, 0, 0, 0, 0});
+        std::vector<int> used((size_t)std::max<int64_t>(1, n_spans), 0);
+        std::vector<uint8_t> regular(std::max<size_t>(1, local.size()), 0);
+        std::vector<CodonMap> irr_map;
+        std::vector<int32_t> irr_idx;
+        const int64_t shift = lo - base;            // map positions are relative to lo
+        for (size_t c = 0; c < local.size(); c++) {
+            const CodonMap &m = local[c];
+            // contiguous bytes q, q+1, q+2: ascending for '+', descending for '-'
+            const bool contiguous = m.minus ? (m.p1 == m.p0 - 1 && m.p2 == m.p0 - 2) : (m.p1 == m.p0 + 1 && m.p2 == m.p0 + 2);
+            bool placed = false;
+            if (contiguous) {
+                const int64_t q = (m.minus ? m.p2 : m.p0) + shift;   // lowest byte, relative to base
+                const int64_t sp = q / 16;
+                const int off = (int)(q % 16);
+                const int dir = m.minus ? -1 : 1;
+                SpanRun *r = &runs[(size_t)sp * kSpanRuns];
+                // extend a run of the same product if this codon is its next element
+                for (int l = 0; l < used[(size_t)sp] && !placed; l++) {
+                    if (r[l].minus == m.minus && r[l].dir == dir && r[l].off + 3 * r[l].cnt == off &&
+                        (int64_t)r[l].codon0 + (int64_t)dir * r[l].cnt == (int64_t)c) { r[l].cnt++; placed = true; }
+                    // '-' strand codons arrive in descending position order: prepend
+                    else if (r[l].minus == m.minus && r[l].dir == dir && r[l].off - 3 == off && (int64_t)r[l].codon0 - dir == (int64_t)c) {
+                        r[l].off = (int8_t)off; r[l].codon0 = (int32_t)c; r[l].cnt++; placed = true;
+                    }
+                }
+                if (!placed && used[(size_t)sp] < kSpanRuns) {
+                    r[used[(size_t)sp]++] = SpanRun{(int32_t)c, (int8_t)off, 1, (int8_t)dir, (int8_t)m.minus};
+                    placed = true;
+                }
+            }
+            if (placed) regular[c] = 1;
+            else {
+                CodonMap mm = m;
+                mm.p0 += (int32_t)shift; mm.p1 += (int32_t)shift; mm.p2 += (int32_t)shift;   // relative to base
+                irr_map.push_back(mm);
+                irr_idx.push_back((int32_t)c);
+            }
+        }
+        ctx->n_irr = (int64_t)irr_map.size();
+        CU(ctx, ctx->d_runs.ensure(sizeof(SpanRun) * runs.size()));
+        CU(ctx, ctx->d_regular.ensure(regular.size()));
+        CU(ctx, ctx->d_cons.ensure((size_t)(n_spans * 16 + 128)));
+        CU(ctx, cudaMemcpy(ctx->d_runs.p, runs.data(), sizeof(SpanRun) * runs.size(), cudaMemcpyHostToDevice));
+        CU(ctx, cudaMemcpy(ctx->d_regular.p, regular.data(), regular.size(), cudaMemcpyHostToDevice));
+        CU(ctx, cudaMemset(ctx->d_cons.p, 0, (size_t)(n_spans * 16 + 128)));
+        if (ctx->n_irr) {
+            CU(ctx, ctx->d_irr_map.ensure(sizeof(CodonMap) * irr_map.size()));
+            CU(ctx, ctx->d_irr_idx.ensure(sizeof(int32_t) * irr_idx.size()));
+            CU(ctx, cudaMemcpy(ctx->d_irr_map.p, irr_map.data(), sizeof(CodonMap) * irr_map.size(), cudaMemcpyHostToDevice));
+            CU(ctx, cudaMemcpy(ctx->d_irr_idx.p, irr_idx.data(), sizeof(int32_t) * irr_idx.size(), cudaMemcpyHostToDevice));
+        }
+    }
+
     CU(ctx, ctx->d_map.ensure(sizeof(CodonMap) * std::max<size_t>(1, local.size())));
     CU(ctx, ctx->d_local_ofs.ensure(sizeof(int64_t) * (n_products + 1)));
     CU(ctx, ctx->d_full_ofs.ensure(sizeof(int64_t) * (n_products + 1)));
@@ -364,28 +482,28 @@ int snpg_load_group(snpg_ctx *ctx, int group, const uint8_t *bases, uint64_t n_s
     if (int rc = prepare_group(ctx, g, n_seqs)) return rc;
 
     // Row blocks: H2D of block i+1 overlaps packing of block i (two staging buffers).
-    const int64_t width = ctx->col_hi - ctx->col_lo;
-    if (width > 0) {
-        const int64_t pitch = (width + 127) / 128 * 128;
+    // Staged columns start at base_al (16-byte aligned); the pitch leaves room for the
+    // fused kernel's 16-byte vectors and look-ahead past the last CDS column.
+    const int64_t width = ctx->col_hi - ctx->base_al;
+    if (ctx->shard_count > 0 && width > 0) {
+        const int64_t pitch = (ctx->n_spans * 16 + 16 + 127) / 128 * 128;
         int64_t rows_per = std::max<int64_t>(kRowPad, ((int64_t)48 << 20) / pitch / kRowPad * kRowPad);
         rows_per = std::min<int64_t>(rows_per, (int64_t)((n_seqs + kRowPad - 1) / kRowPad * kRowPad));
-        for (int i = 0; i < 2; i++) CU(ctx, ctx->staging[i].ensure((size_t)(rows_per * pitch)));
+        for (int i = 0; i < 2; i++) {
+            const size_t before = ctx->staging[i].cap;
+            CU(ctx, ctx->staging[i].ensure((size_t)(rows_per * pitch)));
+            if (ctx->staging[i].cap != before) CU(ctx, cudaMemset(ctx->staging[i].p, 0, ctx->staging[i].cap));  // pad bytes defined
+        }
         int64_t blk = 0;
         for (int64_t r0 = 0; r0 < (int64_t)n_seqs; r0 += rows_per, blk++) {
             const int b = (int)(blk & 1);
             const int64_t rows = std::min<int64_t>(rows_per, (int64_t)n_seqs - r0);
             if (blk >= 2) CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_packed[b], 0));
-            CU(ctx, cudaMemcpy2DAsync(ctx->staging[b].p, (size_t)pitch, bases + (size_t)r0 * row_stride + ctx->col_lo,
+            CU(ctx, cudaMemcpy2DAsync(ctx->staging[b].p, (size_t)pitch, bases + (size_t)r0 * row_stride + ctx->base_al,
                                       (size_t)row_stride, (size_t)width, (size_t)rows, cudaMemcpyHostToDevice, ctx->copy_stream));
             CU(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
             CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
-            {
-                Launch l(ctx, SNPG_K_PACK);
-                launch_pack(ctx->staging[b].as<uint8_t>(), pitch, rows, r0, ctx->d_map.as<CodonMap>(), ctx->shard_count,
-                            g.codes.as<uint8_t>(), g.n_pad, g.other.as<uint32_t>(), g.other.as<uint32_t>() + ctx->shard_count,
-                            ctx->stream);
-            }
-            CU(ctx, cudaGetLastError());
+            if (int rc = pack_block(ctx, g, ctx->staging[b].as<uint8_t>(), pitch, rows, r0, pitch)) return rc;
             CU(ctx, cudaEventRecord(ctx->ev_packed[b], ctx->stream));
         }
     }
@@ -404,18 +522,25 @@ int snpg_load_group_device(snpg_ctx *ctx, int group, const uint8_t *d_bases, uin
     if (int rc = bind(ctx)) return rc;
     Group &g = ctx->groups[group];
     if (int rc = prepare_group(ctx, g, n_seqs)) return rc;
-    const int64_t rows_per = (int64_t)4 << 20;  // keeps gridDim.y < 65536
-    for (int64_t r0 = 0; r0 < (int64_t)n_seqs && ctx->shard_count > 0; r0 += rows_per) {
-        const int64_t rows = std::min<int64_t>(rows_per, (int64_t)n_seqs - r0);
-        {
-            Launch l(ctx, SNPG_K_PACK);
-            launch_pack(d_bases + (size_t)r0 * row_stride + ctx->col_lo, (int64_t)row_stride, rows, r0, ctx->d_map.as<CodonMap>(),
-                        ctx->shard_count, g.codes.as<uint8_t>(), g.n_pad, g.other.as<uint32_t>(),
-                        g.other.as<uint32_t>() + ctx->shard_count, ctx->stream);
-        }
-        CU(ctx, cudaGetLastError());
+    // The fused path reads whole 16-byte vectors: it needs an aligned base and a row
+    // pitch that covers the last span; anything else keeps the code matrix path.
+    const bool fused_ok = ((uintptr_t)d_bases % 16 == 0) && (row_stride % 16 == 0) &&
+                          ((int64_t)row_stride >= ctx->base_al + ctx->n_spans * 16);
+    const bool saved_keep = ctx->keep_codes;
+    if (!saved_keep && !fused_ok) {
+        ctx->keep_codes = true;                                    // fall back to K1+K2 for this load
+        if (int rc = prepare_group(ctx, g, n_seqs)) { ctx->keep_codes = saved_keep; return rc; }
     }
-    return finish_group(ctx, g);
+    const int64_t rows_per = (int64_t)1 << 20;  // keeps gridDim.y < 65536 for both paths
+    int rc = SNPG_OK;
+    for (int64_t r0 = 0; r0 < (int64_t)n_seqs && ctx->shard_count > 0 && rc == SNPG_OK; r0 += rows_per) {
+        const int64_t rows = std::min<int64_t>(rows_per, (int64_t)n_seqs - r0);
+        rc = pack_block(ctx, g, d_bases + (size_t)r0 * row_stride + ctx->base_al, (int64_t)row_stride, rows, r0,
+                        (int64_t)aln_len - ctx->base_al);
+    }
+    if (rc == SNPG_OK) rc = finish_group(ctx, g);
+    if (!saved_keep && !fused_ok) { ctx->keep_codes = saved_keep; g.codes.release(); g.has_codes = false; }
+    return rc;
 }
 
 int snpg_drop_group(snpg_ctx *ctx, int group) {

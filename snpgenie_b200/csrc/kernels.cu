@@ -204,6 +204,169 @@ k_hist(const uint8_t *__restrict__ codes, int64_t n_pad, int64_t n_codons, int c
     }
 }
 
+// ---------------------------------------------------------------------------
+// K1+K2 fused: histogram straight from the alignment bytes, no code matrix.
+// Used when the packed codon matrix is not kept (SNPG_OPT_KEEP_CODES = 0).
+//
+// A thread owns one 16-byte column span of the alignment and walks down the
+// rows; a warp therefore reads 512 contiguous bytes of each row.  Every row's
+// span is XORed against the same span of a consensus row (the group's first
+// sequence).  If the 16 bytes (plus the 2 bytes a codon may reach into the next
+// span) equal the consensus -- the common case in real alignments -- every codon
+// starting in the span equals the consensus codon and nothing is recorded.
+// Otherwise only the codons that contain a differing byte are decoded and
+// counted with a global reduction (RED) into hist[codon][code].  k_fused_fixup
+// then credits each codon's consensus code with (rows - recorded).  Bytes are
+// compared raw, so a lower-case or 'U' residue simply takes the decode path.
+// Algorithmic traffic: every alignment byte of the CDS span read once.
+// ---------------------------------------------------------------------------
+constexpr int kFusedWarps = 8;
+constexpr int kFusedRowsPerWarp = 32;
+constexpr int kFusedUnroll = 4;
+
+__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t d) {       // bit 7 of every nonzero byte
+    return (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t gather_msb(uint32_t m) {           // bits 7,15,23,31 -> bits 0..3
+    return ((m >> 7) * 0x00204081u >> 21) & 0xFu;                        // 1 + 2^7 + 2^14 + 2^21
+}
+
+__device__ __noinline__ void fused_slow(uint4 v, uint32_t v4, uint4 c, uint32_t c4, const SpanRun *__restrict__ runs,
+                                        uint32_t *__restrict__ hist, uint32_t *__restrict__ other_min,
+                                        uint32_t *__restrict__ other_max, const uint8_t (*lut_cls)[256],
+                                        const uint8_t (*lut_chr)[256], uint8_t *scratch)
+{
+    const uint32_t m20 = gather_msb(nonzero_bytes(v.x ^ c.x)) | (gather_msb(nonzero_bytes(v.y ^ c.y)) << 4) |
+                         (gather_msb(nonzero_bytes(v.z ^ c.z)) << 8) | (gather_msb(nonzero_bytes(v.w ^ c.w)) << 12) |
+                         (gather_msb(nonzero_bytes(v4 ^ c4)) << 16);
+    uint32_t *sw = reinterpret_cast<uint32_t *>(scratch);
+    sw[0] = v.x; sw[1] = v.y; sw[2] = v.z; sw[3] = v.w; sw[4] = v4;
+#pragma unroll 1
+    for (int l = 0; l < kSpanRuns; l++) {
+        const SpanRun run = runs[l];
+        if (run.cnt == 0) break;
+        const uint32_t w = m20 >> run.off;
+        uint32_t cm = (w | (w >> 1) | (w >> 2)) & 0x9249u & ((1u << (3 * run.cnt)) - 1u);
+        while (cm) {
+            const int j = __ffs(cm) - 1;
+            cm &= cm - 1;
+            const int s0 = run.off + j;
+            const uint8_t r0 = scratch[s0], r1 = scratch[s0 + 1], r2 = scratch[s0 + 2];
+            const int mi = run.minus ? 1 : 0;
+            const uint8_t b0 = mi ? r2 : r0, b2 = mi ? r0 : r2;          // '-' strand reads the codon right to left
+            const uint8_t k0 = lut_cls[mi][b0], k1 = lut_cls[mi][r1], k2 = lut_cls[mi][b2];
+            const int64_t cidx = (int64_t)run.codon0 + (int64_t)run.dir * (j / 3);
+            uint32_t code;
+            if (max(k0, max(k1, k2)) < 4) code = k0 * 16 + k1 * 4 + k2;
+            else if (k0 == 4 || k1 == 4 || k2 == 4) code = kCodeUndef;
+            else {
+                code = kCodeOther;
+                const uint32_t key = ((uint32_t)lut_chr[mi][b0] << 16) | ((uint32_t)lut_chr[mi][r1] << 8) | lut_chr[mi][b2];
+                atomicMin(&other_min[cidx], key);
+                atomicMax(&other_max[cidx], key);
+            }
+            atomicAdd(&hist[cidx * kHistBins + code], 1u);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kFusedWarps * 32)
+k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, int64_t n_rows, const uint8_t *__restrict__ cons,
+             int64_t n_spans, int64_t row_bytes, const SpanRun *__restrict__ runs, uint32_t *__restrict__ hist,
+             uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max)
+{
+    __shared__ uint8_t lut_chr[2][256];
+    __shared__ uint8_t lut_cls[2][256];
+    __shared__ __align__(4) uint8_t scratch_all[kFusedWarps * 32][20];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int s = 0; s < 2; s++) {
+        const uint8_t n = norm_char((uint8_t)t, s);
+        lut_chr[s][t] = n;
+        lut_cls[s][t] = class_of(n);
+    }
+    __syncthreads();
+
+    const int64_t span = (int64_t)blockIdx.x * 32 + lane;
+    const bool live = span < n_spans;
+    const int64_t sp = live ? span : n_spans - 1;
+    const int64_t row_begin = ((int64_t)blockIdx.y * kFusedWarps + warp) * kFusedRowsPerWarp;
+    const int64_t row_end = min(n_rows, row_begin + kFusedRowsPerWarp);
+    const uint4 c = *reinterpret_cast<const uint4 *>(cons + sp * 16);
+    const uint32_t c4 = *reinterpret_cast<const uint32_t *>(cons + sp * 16 + 16);
+    // lane 31 has no right-hand neighbour in the warp: it fetches its own look-ahead bytes
+    // (only those inside the row; the rest count as equal to the consensus)
+    const int tail_avail = lane == 31 ? (int)max((int64_t)0, min((int64_t)4, row_bytes - (sp * 16 + 16))) : 0;
+    const uint8_t *p = aln + sp * 16;
+
+    for (int64_t r = row_begin; r < row_end; r += kFusedUnroll) {
+        uint4 v[kFusedUnroll];
+        uint32_t tail[kFusedUnroll];
+#pragma unroll
+        for (int u = 0; u < kFusedUnroll; u++) {
+            const bool ok = r + u < row_end;
+            const uint8_t *q = p + (ok ? r + u : row_begin) * pitch;
+            v[u] = ld_stream_v4(reinterpret_cast<const uint4 *>(q));
+            uint32_t tw = c4;
+            if (tail_avail == 4) tw = *reinterpret_cast<const uint32_t *>(q + 16);
+            else for (int k = 0; k < tail_avail; k++) tw = (tw & ~(0xFFu << (8 * k))) | ((uint32_t)q[16 + k] << (8 * k));
+            tail[u] = tw;
+        }
+#pragma unroll
+        for (int u = 0; u < kFusedUnroll; u++) {
+            const uint32_t nxt = __shfl_down_sync(kFull, v[u].x, 1);
+            const uint32_t v4 = lane == 31 ? tail[u] : nxt;
+            const uint32_t d = (v[u].x ^ c.x) | (v[u].y ^ c.y) | (v[u].z ^ c.z) | (v[u].w ^ c.w) | ((v4 ^ c4) & 0xFFFFu);
+            if (d != 0 && live && r + u < row_end)
+                fused_slow(v[u], v4, c, c4, runs + sp * kSpanRuns, hist, other_min, other_max, lut_cls, lut_chr, scratch_all[t]);
+        }
+    }
+}
+
+// After all row blocks: credit the consensus codon of every regular codon with the
+// rows that never reached the decode path.
+__global__ void k_fused_fixup(const uint8_t *__restrict__ cons, int64_t cons_shift, const CodonMap *__restrict__ map,
+                              const uint8_t *__restrict__ regular, int64_t n_codons, uint32_t n_rows,
+                              uint32_t *__restrict__ hist, uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_codons || !regular[c]) return;
+    const CodonMap m = map[c];
+    const uint8_t n0 = norm_char(cons[m.p0 + cons_shift], m.minus), n1 = norm_char(cons[m.p1 + cons_shift], m.minus),
+                  n2 = norm_char(cons[m.p2 + cons_shift], m.minus);
+    const uint8_t k0 = class_of(n0), k1 = class_of(n1), k2 = class_of(n2);
+    uint32_t code;
+    if (max(k0, max(k1, k2)) < 4) code = k0 * 16 + k1 * 4 + k2;
+    else if (k0 == 4 || k1 == 4 || k2 == 4) code = kCodeUndef;
+    else code = kCodeOther;
+    uint32_t *h = hist + c * kHistBins;
+    uint32_t seen = 0;
+    for (int b = 0; b < kHistBins; b++) seen += h[b];
+    const uint32_t rest = n_rows - seen;
+    if (rest) {
+        h[code] += rest;
+        if (code == kCodeOther) {
+            const uint32_t key = ((uint32_t)n0 << 16) | ((uint32_t)n1 << 8) | n2;
+            other_min[c] = min(other_min[c], key);
+            other_max[c] = max(other_max[c], key);
+        }
+    }
+}
+
+// irregular codons (split across CDS segments, or beyond the run capacity of a span) go
+// through K1+K2 on a compact list; this adds their histograms into place
+__global__ void k_scatter_irregular(const uint32_t *__restrict__ tmp_hist, const uint32_t *__restrict__ tmp_min,
+                                    const uint32_t *__restrict__ tmp_max, const int32_t *__restrict__ idx, int64_t n_irr,
+                                    uint32_t *__restrict__ hist, uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_irr * kHistBins) return;
+    const int64_t k = i / kHistBins;
+    const int b = (int)(i % kHistBins);
+    const int64_t c = idx[k];
+    hist[c * kHistBins + b] = tmp_hist[i];
+    if (b == 0) { other_min[c] = tmp_min[k]; other_max[c] = tmp_max[k]; }
+}
+
 // transposed codes -> sequence-major block [n][C] for product columns [c0, c0+C)
 __global__ void k_untranspose(const uint8_t *__restrict__ codes, int64_t n_pad, int64_t n, int64_t c0, int64_t C,
                               uint8_t *__restrict__ out)
@@ -489,17 +652,15 @@ __global__ void __launch_bounds__(256)
 k_rep_moments(const double *__restrict__ rep, int64_t B, double *__restrict__ se)
 {
     __shared__ double red[256];
-    const int p = blockIdx.x, t = threadIdx.x;
+    const int p = blockIdx.x, which = blockIdx.y, t = threadIdx.x;   // one block per (item, statistic)
     const double *R = rep + 4 * (size_t)p * B;
-    for (int which = 0; which < 6; which++) {
-        double s = 0;
-        for (int64_t b = t; b < B; b += 256) s += rep_value(R + 4 * b, which);
-        const double mean = block_sum_256(s, red) / (double)B;
-        double ss = 0;
-        for (int64_t b = t; b < B; b += 256) { const double d = rep_value(R + 4 * b, which) - mean; ss += d * d; }
-        const double tot = block_sum_256(ss, red);
-        if (t == 0) se[6 * p + which] = sqrt(tot / (double)(B - 1));
-    }
+    double s = 0;
+    for (int64_t b = t; b < B; b += 256) s += rep_value(R + 4 * b, which);
+    const double mean = block_sum_256(s, red) / (double)B;
+    double ss = 0;
+    for (int64_t b = t; b < B; b += 256) { const double d = rep_value(R + 4 * b, which) - mean; ss += d * d; }
+    const double tot = block_sum_256(ss, red);
+    if (t == 0) se[6 * p + which] = sqrt(tot / (double)(B - 1));
 }
 
 // ---------------------------------------------------------------------------
@@ -576,6 +737,35 @@ void launch_hist(const uint8_t *d_codes, int64_t n_pad, int64_t n_codons, uint32
                                                                                                chunk_rows, d_hist);
 }
 
+void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, const uint8_t *d_cons, int64_t n_spans,
+                       int64_t row_bytes, const SpanRun *d_runs, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max,
+                       cudaStream_t stream)
+{
+    if (n_spans <= 0 || n_rows <= 0) return;
+    const int64_t rows_per_block = (int64_t)kFusedWarps * kFusedRowsPerWarp;
+    dim3 grid((unsigned)((n_spans + 31) / 32), (unsigned)((n_rows + rows_per_block - 1) / rows_per_block));
+    k_fused_hist<<<grid, kFusedWarps * 32, 0, stream>>>(d_aln, pitch, n_rows, d_cons, n_spans, row_bytes, d_runs, d_hist,
+                                                        d_other_min, d_other_max);
+}
+
+void launch_fused_fixup(const uint8_t *d_cons, int64_t cons_shift, const CodonMap *d_map, const uint8_t *d_regular,
+                        int64_t n_codons, uint32_t n_rows, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max,
+                        cudaStream_t stream)
+{
+    if (n_codons <= 0) return;
+    k_fused_fixup<<<(unsigned)((n_codons + 127) / 128), 128, 0, stream>>>(d_cons, cons_shift, d_map, d_regular, n_codons, n_rows,
+                                                                           d_hist, d_other_min, d_other_max);
+}
+
+void launch_scatter_irregular(const uint32_t *d_tmp_hist, const uint32_t *d_tmp_min, const uint32_t *d_tmp_max,
+                              const int32_t *d_idx, int64_t n_irr, uint32_t *d_hist, uint32_t *d_other_min,
+                              uint32_t *d_other_max, cudaStream_t stream)
+{
+    if (n_irr <= 0) return;
+    k_scatter_irregular<<<(unsigned)((n_irr * kHistBins + 255) / 256), 256, 0, stream>>>(d_tmp_hist, d_tmp_min, d_tmp_max, d_idx,
+                                                                                          n_irr, d_hist, d_other_min, d_other_max);
+}
+
 void launch_untranspose(const uint8_t *d_codes, int64_t n_pad, int64_t n, int64_t c0, int64_t C, uint8_t *d_out,
                         cudaStream_t stream)
 {
@@ -618,7 +808,7 @@ void launch_bootstrap(const double *d_stats4, const int64_t *d_prod_ofs, int n_p
 void launch_rep_moments(const double *d_rep, int64_t n_items, int64_t B, double *d_se, cudaStream_t stream)
 {
     if (n_items <= 0) return;
-    k_rep_moments<<<(unsigned)n_items, 256, 0, stream>>>(d_rep, B, d_se);
+    k_rep_moments<<<dim3((unsigned)n_items, 6), 256, 0, stream>>>(d_rep, B, d_se);
 }
 
 void launch_window_sums(const double *d_stats4, int64_t W, int64_t step, int64_t nwin, double *d_win_sums,

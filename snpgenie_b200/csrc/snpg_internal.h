@@ -18,6 +18,12 @@ constexpr uint32_t kOtherNone = 0xFFFFFFFFu;
 // Built on the host from the CDS segments (frame, multi-segment, strand).
 struct CodonMap { int32_t p0, p1, p2, minus; };
 
+// Fused path: the codons that START inside one 16-byte column span, as up to
+// kSpanRuns runs of consecutive codons of one product (start offsets off,
+// off+3, ...; codon index codon0 + dir*j).  cnt == 0 ends the list.
+constexpr int kSpanRuns = 4;
+struct SpanRun { int32_t codon0; int8_t off, cnt, dir, minus; };
+
 // Device view of one loaded group, offset to the first codon a kernel works on.
 struct GroupView {
     const uint32_t *hist;        // [codons][66]
@@ -41,6 +47,21 @@ void launch_pack(const uint8_t *d_aln, int64_t row_stride, int64_t n_rows, int64
 
 // K2 histogram: codes[c][0..n_pad) -> hist[c][66] (u32, zeroed by the caller)
 void launch_hist(const uint8_t *d_codes, int64_t n_pad, int64_t n_codons, uint32_t *d_hist, cudaStream_t stream);
+
+// K1+K2 fused (no code matrix): d_aln points at the first span's bytes of the first
+// row; spans are 16-byte aligned; d_cons holds the consensus row for the same
+// columns (+ 16 readable bytes past the last span); row_bytes = bytes readable
+// in a row counted from the first span.  hist must be zeroed before the first
+// row block; launch_fused_fixup runs once after the last.
+void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, const uint8_t *d_cons, int64_t n_spans,
+                       int64_t row_bytes, const SpanRun *d_runs, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max,
+                       cudaStream_t stream);
+void launch_fused_fixup(const uint8_t *d_cons, int64_t cons_shift, const CodonMap *d_map, const uint8_t *d_regular,
+                        int64_t n_codons, uint32_t n_rows, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max,
+                        cudaStream_t stream);
+void launch_scatter_irregular(const uint32_t *d_tmp_hist, const uint32_t *d_tmp_min, const uint32_t *d_tmp_max,
+                              const int32_t *d_idx, int64_t n_irr, uint32_t *d_hist, uint32_t *d_other_min,
+                              uint32_t *d_other_max, cudaStream_t stream);
 
 // transposed codes -> sequence-major [n][C] (test hook)
 void launch_untranspose(const uint8_t *d_codes, int64_t n_pad, int64_t n, int64_t c0, int64_t C, uint8_t *d_out,

@@ -31,6 +31,18 @@ def eng():
     e.close()
 
 
+@pytest.fixture(scope="module", params=["codes", "fused"])
+def eng2(request):
+    """Both histogram routes: K1 pack + K2 hist over the kept code matrix, and the fused kernel."""
+    from snpgenie_b200 import _abi
+    from snpgenie_b200.engine import Engine
+    e = Engine(device=0, seed=1234)
+    e.has_codes = request.param == "codes"
+    e.set_option(_abi.OPT_KEEP_CODES, 1 if e.has_codes else 0)
+    yield e
+    e.close()
+
+
 def _oracle_product(aln, p):
     pos = orc.product_positions(p.starts, p.stops, p.strand, aln.shape[1])
     raw, codes = orc.extract(aln, pos, p.strand)
@@ -40,22 +52,25 @@ def _oracle_product(aln, p):
 # ----------------------------------------------------------------- K1 / K2 bit-exact
 
 @pytest.mark.parametrize("case,minus", [("w_cfg1", False), ("w_gaps", False), ("w_heavy", False), ("w_minus", True)])
-def test_codon_indices_and_histograms_bit_exact(eng, case, minus):
+def test_codon_indices_and_histograms_bit_exact(eng2, case, minus):
+    eng = eng2
     d, aln, _, _ = refio.within_case(case)
     products = hostio.read_gtf_products(os.path.join(d, "cds.gtf"), include_minus=minus)
     eng.set_products(products, aln.shape[1])
     eng.load_group(0, aln)
     for i, p in enumerate(products):
         raw, codes = _oracle_product(aln, p)
-        assert (eng.codon_indices(0, i) == codes).all(), (case, p.name)
+        if eng.has_codes:
+            assert (eng.codon_indices(0, i) == codes).all(), (case, p.name)
         h, od = eng.hist(0, i)
         assert (h == orc.hist(codes)).all(), (case, p.name)
         assert (od == orc.other_distinct(raw, codes)).all(), (case, p.name)
 
 
 @pytest.mark.parametrize("n", [1, 2, 31, 127, 128, 129, 1000, 8191, 8192, 8193, 20000])
-def test_histogram_ragged_row_counts(eng, n):
+def test_histogram_ragged_row_counts(eng2, n):
     """Row counts around every padding / chunking boundary, uniform random codons (worst case for K2)."""
+    eng = eng2
     rng = np.random.default_rng(n)
     L = 3 * 70 + 5
     aln = np.frombuffer(b"ACGTNacgtu-RY", dtype=np.uint8)[rng.integers(0, 13, size=(n, L))]
@@ -64,15 +79,17 @@ def test_histogram_ragged_row_counts(eng, n):
     eng.set_products(products, L)
     eng.load_group(0, aln)
     raw, codes = _oracle_product(aln, products[0])
-    assert (eng.codon_indices(0, 0) == codes).all()
+    if eng.has_codes:
+        assert (eng.codon_indices(0, 0) == codes).all()
     h, od = eng.hist(0, 0)
     assert (h == orc.hist(codes)).all()
     assert (h.sum(axis=1) == n).all()
     assert (od == orc.other_distinct(raw, codes)).all()
 
 
-def test_device_resident_and_strided_input_match_host_input(eng):
+def test_device_resident_and_strided_input_match_host_input(eng2):
     import torch
+    eng = eng2
     products = synth.hiv_products()
     aln = synth.make_alignment(700, 9719, products, 77, gap_frac=0.025, n_frac=0.02, iupac_frac=0.005)
     eng.set_products(products, 9719)
@@ -85,7 +102,15 @@ def test_device_resident_and_strided_input_match_host_input(eng):
     eng.load_group_ptr(1, d.data_ptr(), 700, 9719, pitch, device=True)
     for i in range(len(products)):
         assert (eng.hist(1, i)[0] == ref[i]).all()
-        assert (eng.codon_indices(1, i) == eng.codon_indices(0, i)).all()
+        assert (ref[i] == orc.hist(_oracle_product(aln, products[i])[1])).all()
+        if eng.has_codes:
+            assert (eng.codon_indices(1, i) == eng.codon_indices(0, i)).all()
+    # a device buffer the fused kernel cannot take (odd pitch): same result through the fallback
+    d2 = torch.zeros((700, 9719 + 5), dtype=torch.uint8, device="cuda:0")
+    d2[:, :9719] = torch.from_numpy(aln).cuda()
+    eng.load_group_ptr(3, d2.data_ptr(), 700, 9719, 9719 + 5, device=True)
+    for i in range(len(products)):
+        assert (eng.hist(3, i)[0] == ref[i]).all()
     # host buffer with a row stride (a view into a wider matrix)
     wide = np.zeros((700, 10000), dtype=np.uint8)
     wide[:, :9719] = aln
@@ -128,13 +153,15 @@ def _check_within_case(eng, case, products, aln, codon_rows, prod_rows):
 
 
 @pytest.mark.parametrize("case", ["w_cfg1", "w_gaps", "w_heavy"])
-def test_within_matches_reference(eng, case):
+def test_within_matches_reference(eng2, case):
+    eng = eng2
     d, aln, codon_rows, prod_rows = refio.within_case(case)
     products = hostio.read_gtf_products(os.path.join(d, "cds.gtf"))
     _check_within_case(eng, case, products, aln, codon_rows, prod_rows)
 
 
-def test_minus_strand_matches_revcom_route(eng):
+def test_minus_strand_matches_revcom_route(eng2):
+    eng = eng2
     d, aln, codon_rows, prod_rows = refio.within_case("w_minus")
     products = [p for p in hostio.read_gtf_products(os.path.join(d, "cds.gtf"), include_minus=True) if p.strand < 0]
     _check_within_case(eng, "w_minus", products, aln, codon_rows, prod_rows)
@@ -175,8 +202,9 @@ def test_between_matches_reference(eng):
 
 # ----------------------------------------------------------------- mid-size vs oracle closed form
 
-def test_config3_shape_against_oracle(eng):
+def test_config3_shape_against_oracle(eng2):
     """HIV-shaped: overlapping frames, 2-segment product, '-' strand CDS, 5 % gaps/ambiguous."""
+    eng = eng2
     products = synth.hiv_products()
     aln = synth.make_alignment(1500, 9719, products, 20261022, gap_frac=0.025, n_frac=0.02, iupac_frac=0.005,
                                lower_frac=0.01, u_frac=0.01)
@@ -185,9 +213,11 @@ def test_config3_shape_against_oracle(eng):
     sums, _ = eng.within_all(0)
     for i, p in enumerate(products):
         raw, codes = _oracle_product(aln, p)
-        assert (eng.codon_indices(0, i) == codes).all()
+        if eng.has_codes:
+            assert (eng.codon_indices(0, i) == codes).all()
         h, od = eng.hist(0, i)
         assert (h == orc.hist(codes)).all()
+        assert (od == orc.other_distinct(raw, codes)).all()
         want = orc.within_hist(h, orc.other_distinct(raw, codes))
         got = eng.within(0, i)
         assert (got["poly"] == want["poly"]).all()
@@ -289,8 +319,10 @@ def test_windows_bitwise_and_se(eng):
         assert np.array_equal(sums, osums), (W, step)      # same additions, same order
     sums, se = eng.windows(stats4, 100, 10, B=3000)
     _, ose = orc.windows(stats4, 100, 10, B=3000, seed=4)
-    ok = ose[:, 2] > 0
-    assert np.median(np.abs(se[ok] / ose[ok] - 1)) < 0.05
+    for q in range(3):
+        ok = ose[:, q] > 0
+        assert np.median(np.abs(se[ok, q] / ose[ok, q] - 1)) < 0.05
+        assert np.all(se[~ok, q] == 0)
     # the reference's own processor output (w_gaps, W=10 step=3, B=200)
     d, aln, codon_rows, _ = refio.within_case("w_gaps")
     _, wrows = refio.read_tsv(os.path.join(d, "sw_10codons_results.txt"))
@@ -366,8 +398,9 @@ def test_error_paths(eng):
 
 # ----------------------------------------------------------------- full size (BASELINE config 2)
 
-def test_config2_full_size_properties(eng):
+def test_config2_full_size_properties(eng2):
     """10,000 x 29,903, 10 CDS: size-independent properties + exact checks on sampled columns."""
+    eng = eng2
     products = synth.sars2_products()
     n, L = 10000, 29903
     aln = synth.make_alignment(n, L, products, 20261021)
@@ -395,3 +428,35 @@ def test_config2_full_size_properties(eng):
         assert close(sums[i], got["stats4"].sum(axis=0), rtol=1e-13)
         assert np.all(se[i, :3] > 0)
     assert tot_codons == 9677
+
+
+def test_fused_route_irregular_codons_and_many_layers():
+    """Codons split across CDS segments and > 4 products over one span take the compact K1+K2 route."""
+    from snpgenie_b200 import _abi
+    from snpgenie_b200.engine import Engine
+    rng = np.random.default_rng(3)
+    L, n = 400, 300
+    aln = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=(n, L))]
+    aln[rng.random((n, L)) < 0.03] = ord("-")
+    aln[rng.random((n, L)) < 0.01] = ord("R")
+    aln[1:, 100:200] = aln[0, 100:200]                     # a conserved stretch (fast path) ...
+    aln[5, 120] = ord("a")                                  # ... with one lower-case byte (decode path, same code)
+    products = [
+        hostio.Product("split", 1, [11, 40, 70], [20, 47, 78]),     # 10+8+9 nt: two codons straddle segment joins
+        hostio.Product("f0", 1, [101], [190]), hostio.Product("f1", 1, [102], [191]), hostio.Product("f2", 1, [103], [192]),
+        hostio.Product("r0", -1, [101], [190]), hostio.Product("r1", -1, [102], [191]), hostio.Product("r2", -1, [103], [192]),
+        hostio.Product("tiny", 1, [300, 310, 320], [301, 311, 324]),  # 2+2+5 nt
+        hostio.Product("end", 1, [392], [400]),                      # touches the last alignment column
+    ]
+    with Engine(device=0) as e:
+        e.set_option(_abi.OPT_KEEP_CODES, 0)
+        e.set_products(products, L)
+        e.load_group(0, aln)
+        for i, p in enumerate(products):
+            raw, codes = _oracle_product(aln, p)
+            h, od = e.hist(0, i)
+            assert (h == orc.hist(codes)).all(), p.name
+            assert (od == orc.other_distinct(raw, codes)).all(), p.name
+        with pytest.raises(_abi.SnpgError) as err:
+            e.codon_indices(0, 0)
+        assert err.value.code == _abi.E_STATE
