@@ -62,11 +62,13 @@ struct snpg_ctx {
     // fused path (no code matrix): 16-byte column spans starting at base_al
     int64_t base_al = 0, n_spans = 0;     // base_al = col_lo rounded down to 16
     int64_t n_irr = 0;                    // codons the span runs cannot express
-    DevBuf d_runs, d_regular, d_irr_map, d_irr_idx, d_cons;
+    DevBuf d_runs, d_regular, d_irr_map, d_irr_idx, d_cons, d_cons_code, d_cons_key;
     DevBuf t_codes, t_hist, t_other;      // irregular codons: compact K1+K2 scratch
     // groups
     Group groups[SNPG_MAX_GROUPS];
     // scratch
+    DevBuf s_vals, d_order_local, d_order_full;
+    int64_t max_codons_local = 0, max_codons_full = 0;
     DevBuf staging[2], s_stats, s_poly, s_nda, s_ndb, s_cmp, s_cons, s_sums, s_rep, s_se, s_misc, s_in;
     int64_t launches = 0;
     uint32_t call_id = 0;
@@ -196,13 +198,17 @@ int pack_block(snpg_ctx *ctx, Group &g, const uint8_t *d_block, int64_t pitch, i
         launch_pack(d_block + (ctx->col_lo - ctx->base_al), pitch, rows, r0, ctx->d_map.as<CodonMap>(), ctx->shard_count,
                     g.codes.as<uint8_t>(), g.n_pad, omin, omax, ctx->stream);
     } else {
-        if (r0 == 0)   // the group's first sequence is the consensus every row is compared with
+        if (r0 == 0) {   // the group's first sequence is the consensus every row is compared with
             CU(ctx, cudaMemcpyAsync(ctx->d_cons.p, d_block, (size_t)std::min<int64_t>(row_bytes, ctx->n_spans * 16 + 16),
                                     cudaMemcpyDeviceToDevice, ctx->stream));
+            Launch l(ctx, SNPG_K_OTHER);
+            launch_cons_codes(ctx->d_cons.as<uint8_t>(), ctx->col_lo - ctx->base_al, ctx->d_map.as<CodonMap>(), ctx->shard_count,
+                              ctx->d_cons_code.as<uint8_t>(), ctx->d_cons_key.as<uint32_t>(), ctx->stream);
+        }
         {
             Launch l(ctx, SNPG_K_FUSED);
-            launch_fused_hist(d_block, pitch, rows, ctx->d_cons.as<uint8_t>(), ctx->n_spans, row_bytes, ctx->d_runs.as<SpanRun>(),
-                              g.hist.as<uint32_t>(), omin, omax, ctx->stream);
+            launch_fused_hist(d_block, pitch, rows, ctx->d_cons.as<uint8_t>(), ctx->n_spans, ctx->d_runs.as<SpanRun>(),
+                              ctx->d_cons_code.as<uint8_t>(), g.hist.as<uint32_t>(), omin, omax, ctx->stream);
         }
         if (ctx->n_irr) {
             Launch l(ctx, SNPG_K_PACK);
@@ -222,9 +228,8 @@ int finish_group(snpg_ctx *ctx, Group &g) {
     } else {
         {
             Launch l(ctx, SNPG_K_OTHER);
-            launch_fused_fixup(ctx->d_cons.as<uint8_t>(), ctx->col_lo - ctx->base_al, ctx->d_map.as<CodonMap>(),
-                               ctx->d_regular.as<uint8_t>(), ctx->shard_count, (uint32_t)g.n, g.hist.as<uint32_t>(), omin, omax,
-                               ctx->stream);
+            launch_fused_fixup(ctx->d_cons_code.as<uint8_t>(), ctx->d_cons_key.as<uint32_t>(), ctx->d_regular.as<uint8_t>(),
+                               ctx->shard_count, (uint32_t)g.n, g.hist.as<uint32_t>(), omin, omax, ctx->stream);
         }
         if (ctx->n_irr) {
             { Launch l(ctx, SNPG_K_HIST); launch_hist(ctx->t_codes.as<uint8_t>(), g.n_pad, ctx->n_irr, ctx->t_hist.as<uint32_t>(), ctx->stream); }
@@ -293,10 +298,10 @@ void snpg_destroy(snpg_ctx *ctx) {
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     for (auto &g : ctx->groups) { g.codes.release(); g.hist.release(); g.other.release(); }
     DevBuf *bufs[] = {&ctx->d_map, &ctx->d_local_ofs, &ctx->d_full_ofs, &ctx->d_tables, &ctx->staging[0], &ctx->staging[1],
-                      &ctx->d_runs, &ctx->d_regular, &ctx->d_irr_map, &ctx->d_irr_idx, &ctx->d_cons, &ctx->t_codes, &ctx->t_hist,
+                      &ctx->d_runs, &ctx->d_regular, &ctx->d_irr_map, &ctx->d_irr_idx, &ctx->d_cons, &ctx->d_cons_code, &ctx->d_cons_key, &ctx->t_codes, &ctx->t_hist,
                       &ctx->t_other,
                       &ctx->s_stats, &ctx->s_poly, &ctx->s_nda, &ctx->s_ndb, &ctx->s_cmp, &ctx->s_cons, &ctx->s_sums,
-                      &ctx->s_rep, &ctx->s_se, &ctx->s_misc, &ctx->s_in};
+                      &ctx->s_rep, &ctx->s_se, &ctx->s_misc, &ctx->s_in, &ctx->s_vals, &ctx->d_order_local, &ctx->d_order_full};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
@@ -427,6 +432,8 @@ int snpg_set_products(snpg_ctx *ctx, int n_products, const int64_t *seg_ofs, con
         CU(ctx, ctx->d_runs.ensure(sizeof(SpanRun) * runs.size()));
         CU(ctx, ctx->d_regular.ensure(regular.size()));
         CU(ctx, ctx->d_cons.ensure((size_t)(n_spans * 16 + 128)));
+        CU(ctx, ctx->d_cons_code.ensure(regular.size()));
+        CU(ctx, ctx->d_cons_key.ensure(sizeof(uint32_t) * regular.size()));
         CU(ctx, cudaMemcpy(ctx->d_runs.p, runs.data(), sizeof(SpanRun) * runs.size(), cudaMemcpyHostToDevice));
         CU(ctx, cudaMemcpy(ctx->d_regular.p, regular.data(), regular.size(), cudaMemcpyHostToDevice));
         CU(ctx, cudaMemset(ctx->d_cons.p, 0, (size_t)(n_spans * 16 + 128)));
@@ -436,6 +443,22 @@ int snpg_set_products(snpg_ctx *ctx, int n_products, const int64_t *seg_ofs, con
             CU(ctx, cudaMemcpy(ctx->d_irr_map.p, irr_map.data(), sizeof(CodonMap) * irr_map.size(), cudaMemcpyHostToDevice));
             CU(ctx, cudaMemcpy(ctx->d_irr_idx.p, irr_idx.data(), sizeof(int32_t) * irr_idx.size(), cudaMemcpyHostToDevice));
         }
+    }
+
+    // bootstrap schedules the largest products first
+    {
+        std::vector<int> ord_l(n_products), ord_f(n_products);
+        for (int p = 0; p < n_products; p++) ord_l[p] = ord_f[p] = p;
+        auto len_l = [&](int p) { return ctx->local_ofs[p + 1] - ctx->local_ofs[p]; };
+        auto len_f = [&](int p) { return full_ofs[p + 1] - full_ofs[p]; };
+        std::stable_sort(ord_l.begin(), ord_l.end(), [&](int a, int b) { return len_l(a) > len_l(b); });
+        std::stable_sort(ord_f.begin(), ord_f.end(), [&](int a, int b) { return len_f(a) > len_f(b); });
+        ctx->max_codons_local = len_l(ord_l[0]);
+        ctx->max_codons_full = len_f(ord_f[0]);
+        CU(ctx, ctx->d_order_local.ensure(sizeof(int) * n_products));
+        CU(ctx, ctx->d_order_full.ensure(sizeof(int) * n_products));
+        CU(ctx, cudaMemcpy(ctx->d_order_local.p, ord_l.data(), sizeof(int) * n_products, cudaMemcpyHostToDevice));
+        CU(ctx, cudaMemcpy(ctx->d_order_full.p, ord_f.data(), sizeof(int) * n_products, cudaMemcpyHostToDevice));
     }
 
     CU(ctx, ctx->d_map.ensure(sizeof(CodonMap) * std::max<size_t>(1, local.size())));
@@ -525,7 +548,7 @@ int snpg_load_group_device(snpg_ctx *ctx, int group, const uint8_t *d_bases, uin
     // The fused path reads whole 16-byte vectors: it needs an aligned base and a row
     // pitch that covers the last span; anything else keeps the code matrix path.
     const bool fused_ok = ((uintptr_t)d_bases % 16 == 0) && (row_stride % 16 == 0) &&
-                          ((int64_t)row_stride >= ctx->base_al + ctx->n_spans * 16);
+                          ((int64_t)row_stride >= ctx->base_al + ctx->n_spans * 16 + 4);
     const bool saved_keep = ctx->keep_codes;
     if (!saved_keep && !fused_ok) {
         ctx->keep_codes = true;                                    // fall back to K1+K2 for this load
@@ -681,8 +704,13 @@ int snpg_bootstrap_product(snpg_ctx *ctx, const double *stats4, const uint8_t *k
     CU(ctx, ctx->s_rep.ensure(sizeof(double) * 4 * (size_t)B));
     CU(ctx, ctx->s_se.ensure(sizeof(double) * 6));
     const uint32_t sid = 0x10000u + ctx->call_id++;
-    { Launch l(ctx, SNPG_K_BOOT); launch_bootstrap(ctx->s_in.as<double>(), ctx->s_misc.as<int64_t>(), 1, 0, B, ctx->seed, sid, ctx->s_rep.as<double>(), ctx->stream); }
-    { Launch l(ctx, SNPG_K_MOMENTS); launch_rep_moments(ctx->s_rep.as<double>(), 1, B, ctx->s_se.as<double>(), ctx->stream); }
+    CU(ctx, ctx->s_vals.ensure(sizeof(double) * 6 * (size_t)B));
+    {
+        Launch l(ctx, SNPG_K_BOOT);
+        launch_bootstrap(ctx->s_in.as<double>(), ctx->s_misc.as<int64_t>(), nullptr, 1, C, 0, B, ctx->seed, sid,
+                         sums_out ? ctx->s_rep.as<double>() : nullptr, ctx->s_vals.as<double>(), ctx->stream);
+    }
+    { Launch l(ctx, SNPG_K_MOMENTS); launch_moments(ctx->s_vals.as<double>(), 1, B, ctx->s_se.as<double>(), ctx->stream); }
     CU(ctx, cudaGetLastError());
     if (sums_out) CU(ctx, cudaMemcpyAsync(sums_out, ctx->s_rep.p, sizeof(double) * 4 * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
     if (se_out) CU(ctx, cudaMemcpyAsync(se_out, ctx->s_se.p, sizeof(double) * 6, cudaMemcpyDeviceToHost, ctx->stream));
@@ -711,12 +739,14 @@ int snpg_windows(snpg_ctx *ctx, const double *stats4, const uint8_t *keep, int64
         const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(nwin, ((int64_t)256 << 20) / (32 * B)));
         CU(ctx, ctx->s_rep.ensure(sizeof(double) * 4 * (size_t)(batch * B)));
         CU(ctx, ctx->s_se.ensure(sizeof(double) * 6 * (size_t)batch));
+        CU(ctx, ctx->s_vals.ensure(sizeof(double) * 6 * (size_t)(batch * B)));
         std::vector<double> se6((size_t)batch * 6);
         const uint32_t sid = 0x20000u + ctx->call_id++;
         for (int64_t w0 = 0; w0 < nwin; w0 += batch) {
             const int64_t nb = std::min(batch, nwin - w0);
             { Launch l(ctx, SNPG_K_WINDOW); launch_window_bootstrap(ctx->s_in.as<double>(), W, step, w0, nb, B, ctx->seed, sid, ctx->s_rep.as<double>(), ctx->stream); }
-            { Launch l(ctx, SNPG_K_MOMENTS); launch_rep_moments(ctx->s_rep.as<double>(), nb, B, ctx->s_se.as<double>(), ctx->stream); }
+            { Launch l(ctx, SNPG_K_MOMENTS); launch_rep_values(ctx->s_rep.as<double>(), nb, B, ctx->s_vals.as<double>(), ctx->stream); }
+            { Launch l(ctx, SNPG_K_MOMENTS); launch_moments(ctx->s_vals.as<double>(), nb, B, ctx->s_se.as<double>(), ctx->stream); }
             CU(ctx, cudaGetLastError());
             CU(ctx, cudaMemcpyAsync(se6.data(), ctx->s_se.p, sizeof(double) * 6 * (size_t)nb, cudaMemcpyDeviceToHost, ctx->stream));
             CU(ctx, sync_stream(ctx));
@@ -747,8 +777,8 @@ int snpg_bootstrap_all_device(snpg_ctx *ctx, const double *d_stats4_full, int64_
     if (int rc = bind(ctx)) return rc;
     {
         Launch l(ctx, SNPG_K_BOOT);
-        launch_bootstrap(d_stats4_full, ctx->d_full_ofs.as<int64_t>(), ctx->n_products, b_first, b_count, ctx->seed, 0x30000u, d_rep_out,
-                         ctx->stream);
+        launch_bootstrap(d_stats4_full, ctx->d_full_ofs.as<int64_t>(), ctx->d_order_full.as<int>(), ctx->n_products, ctx->max_codons_full,
+                         b_first, b_count, ctx->seed, 0x30000u, d_rep_out, nullptr, ctx->stream);
     }
     CU(ctx, cudaGetLastError());
     CU(ctx, sync_stream(ctx));
@@ -771,7 +801,9 @@ int snpg_rep_moments_device(snpg_ctx *ctx, const double *d_rep, int64_t n_items,
     if (!ctx || !d_rep || !se_out || n_items <= 0 || B < 2) return SNPG_E_ARG;
     if (int rc = bind(ctx)) return rc;
     CU(ctx, ctx->s_se.ensure(sizeof(double) * 6 * (size_t)n_items));
-    { Launch l(ctx, SNPG_K_MOMENTS); launch_rep_moments(d_rep, n_items, B, ctx->s_se.as<double>(), ctx->stream); }
+    CU(ctx, ctx->s_vals.ensure(sizeof(double) * 6 * (size_t)(n_items * B)));
+    { Launch l(ctx, SNPG_K_MOMENTS); launch_rep_values(d_rep, n_items, B, ctx->s_vals.as<double>(), ctx->stream); }
+    { Launch l(ctx, SNPG_K_MOMENTS); launch_moments(ctx->s_vals.as<double>(), n_items, B, ctx->s_se.as<double>(), ctx->stream); }
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaMemcpyAsync(se_out, ctx->s_se.p, sizeof(double) * 6 * (size_t)n_items, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, sync_stream(ctx));
@@ -792,14 +824,15 @@ int snpg_within_all(snpg_ctx *ctx, int group, int64_t B, double *prod_sums, doub
     { Launch l(ctx, SNPG_K_SUMS); launch_product_sums(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), P, ctx->s_sums.as<double>(), ctx->stream); }
     const bool boot = prod_se && B >= 2;
     if (boot) {
-        CU(ctx, ctx->s_rep.ensure(sizeof(double) * 4 * (size_t)(B * P)));
+        CU(ctx, ctx->s_vals.ensure(sizeof(double) * 6 * (size_t)(B * P)));
         CU(ctx, ctx->s_se.ensure(sizeof(double) * 6 * (size_t)P));
         {
             Launch l(ctx, SNPG_K_BOOT);
-            launch_bootstrap(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), P, 0, B, ctx->seed, 0x40000u + ctx->call_id++,
-                             ctx->s_rep.as<double>(), ctx->stream);
+            launch_bootstrap(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), ctx->d_order_local.as<int>(), P,
+                             ctx->max_codons_local, 0, B, ctx->seed, 0x40000u + ctx->call_id++, nullptr, ctx->s_vals.as<double>(),
+                             ctx->stream);
         }
-        { Launch l(ctx, SNPG_K_MOMENTS); launch_rep_moments(ctx->s_rep.as<double>(), P, B, ctx->s_se.as<double>(), ctx->stream); }
+        { Launch l(ctx, SNPG_K_MOMENTS); launch_moments(ctx->s_vals.as<double>(), P, B, ctx->s_se.as<double>(), ctx->stream); }
     }
     CU(ctx, cudaGetLastError());
     if (prod_sums) CU(ctx, cudaMemcpyAsync(prod_sums, ctx->s_sums.p, sizeof(double) * 4 * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));

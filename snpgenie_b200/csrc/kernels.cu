@@ -224,60 +224,67 @@ constexpr int kFusedWarps = 8;
 constexpr int kFusedRowsPerWarp = 32;
 constexpr int kFusedUnroll = 4;
 
-__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t d) {       // bit 7 of every nonzero byte
-    return (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
-}
-__device__ __forceinline__ uint32_t gather_msb(uint32_t m) {           // bits 7,15,23,31 -> bits 0..3
-    return ((m >> 7) * 0x00204081u >> 21) & 0xFu;                        // 1 + 2^7 + 2^14 + 2^21
+__device__ __forceinline__ uint32_t differing_bytes(uint32_t d) {     // 4-bit mask of the nonzero bytes of d
+    const uint32_t m = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
+    return ((m >> 7) * 0x00204081u) >> 21 & 0xFu;                        // bits 0,8,16,24 -> 0..3
 }
 
-__device__ __noinline__ void fused_slow(uint4 v, uint32_t v4, uint4 c, uint32_t c4, const SpanRun *__restrict__ runs,
-                                        uint32_t *__restrict__ hist, uint32_t *__restrict__ other_min,
-                                        uint32_t *__restrict__ other_max, const uint8_t (*lut_cls)[256],
-                                        const uint8_t (*lut_chr)[256], uint8_t *scratch)
+// One parked (span, row): decode and count exactly the codons that contain a byte
+// differing from the consensus.  e = 5 raw words + span index.
+__device__ __forceinline__ void fused_decode(const uint32_t *e, const uint8_t *__restrict__ cons,
+                                             const SpanRun *__restrict__ runs, uint32_t *__restrict__ hist,
+                                             uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max,
+                                             const uint8_t (*lut_cls)[256], const uint8_t (*lut_chr)[256])
 {
-    const uint32_t m20 = gather_msb(nonzero_bytes(v.x ^ c.x)) | (gather_msb(nonzero_bytes(v.y ^ c.y)) << 4) |
-                         (gather_msb(nonzero_bytes(v.z ^ c.z)) << 8) | (gather_msb(nonzero_bytes(v.w ^ c.w)) << 12) |
-                         (gather_msb(nonzero_bytes(v4 ^ c4)) << 16);
-    uint32_t *sw = reinterpret_cast<uint32_t *>(scratch);
-    sw[0] = v.x; sw[1] = v.y; sw[2] = v.z; sw[3] = v.w; sw[4] = v4;
+    const uint32_t sp = e[5];
+    const uint4 c = __ldg(reinterpret_cast<const uint4 *>(cons + (size_t)sp * 16));
+    const uint32_t c4 = __ldg(reinterpret_cast<const uint32_t *>(cons + (size_t)sp * 16 + 16));
+    const uint32_t m20 = differing_bytes(e[0] ^ c.x) | (differing_bytes(e[1] ^ c.y) << 4) | (differing_bytes(e[2] ^ c.z) << 8) |
+                         (differing_bytes(e[3] ^ c.w) << 12) | (differing_bytes(e[4] ^ c4) << 16);
+    const uint8_t *raw = reinterpret_cast<const uint8_t *>(e);
+    const uint2 *rp = reinterpret_cast<const uint2 *>(runs + (size_t)sp * kSpanRuns);
 #pragma unroll 1
     for (int l = 0; l < kSpanRuns; l++) {
-        const SpanRun run = runs[l];
-        if (run.cnt == 0) break;
-        const uint32_t w = m20 >> run.off;
-        uint32_t cm = (w | (w >> 1) | (w >> 2)) & 0x9249u & ((1u << (3 * run.cnt)) - 1u);
+        const uint2 rw = __ldg(rp + l);
+        const int cnt = (int)((rw.y >> 8) & 0xFF);
+        if (cnt == 0) break;
+        const int off = (int)(rw.y & 0xFF), dir = (int)(int8_t)((rw.y >> 16) & 0xFF), mi = (int)((rw.y >> 24) & 1);
+        const uint32_t w = m20 >> off;
+        uint32_t cm = (w | (w >> 1) | (w >> 2)) & 0x9249u & ((1u << (3 * cnt)) - 1u);
+        const uint8_t *cls = lut_cls[mi];
         while (cm) {
-            const int j = __ffs(cm) - 1;
+            const int j = __ffs(cm) - 1;                                  // 3 * codon ordinal
             cm &= cm - 1;
-            const int s0 = run.off + j;
-            const uint8_t r0 = scratch[s0], r1 = scratch[s0 + 1], r2 = scratch[s0 + 2];
-            const int mi = run.minus ? 1 : 0;
+            const uint8_t *rb = raw + off + j;
+            const uint8_t r0 = rb[0], r1 = rb[1], r2 = rb[2];
             const uint8_t b0 = mi ? r2 : r0, b2 = mi ? r0 : r2;          // '-' strand reads the codon right to left
-            const uint8_t k0 = lut_cls[mi][b0], k1 = lut_cls[mi][r1], k2 = lut_cls[mi][b2];
-            const int64_t cidx = (int64_t)run.codon0 + (int64_t)run.dir * (j / 3);
-            uint32_t code;
-            if (max(k0, max(k1, k2)) < 4) code = k0 * 16 + k1 * 4 + k2;
-            else if (k0 == 4 || k1 == 4 || k2 == 4) code = kCodeUndef;
-            else {
-                code = kCodeOther;
-                const uint32_t key = ((uint32_t)lut_chr[mi][b0] << 16) | ((uint32_t)lut_chr[mi][r1] << 8) | lut_chr[mi][b2];
-                atomicMin(&other_min[cidx], key);
-                atomicMax(&other_max[cidx], key);
+            const uint32_t k0 = cls[b0], k1 = cls[r1], k2 = cls[b2];
+            const int cidx = (int)rw.x + dir * (int)((uint32_t)j * 0xABu >> 9);   // j / 3 for j < 48
+            uint32_t code = k0 * 16 + k1 * 4 + k2;
+            if (max(k0, max(k1, k2)) >= 4) {
+                code = (k0 == 4 || k1 == 4 || k2 == 4) ? kCodeUndef : kCodeOther;
+                if (code == kCodeOther) {
+                    const uint32_t key = ((uint32_t)lut_chr[mi][b0] << 16) | ((uint32_t)lut_chr[mi][r1] << 8) | lut_chr[mi][b2];
+                    atomicMin(&other_min[cidx], key);
+                    atomicMax(&other_max[cidx], key);
+                }
             }
-            atomicAdd(&hist[cidx * kHistBins + code], 1u);
+            atomicAdd(&hist[(size_t)cidx * kHistBins + code], 1u);
         }
     }
 }
 
+constexpr int kFusedQueue = 128;     // entries per warp (ring, power of two)
+constexpr int kFusedEntryWords = 7;  // 5 raw + span + pad: odd stride, conflict-free across lanes
+
 __global__ void __launch_bounds__(kFusedWarps * 32)
 k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, int64_t n_rows, const uint8_t *__restrict__ cons,
-             int64_t n_spans, int64_t row_bytes, const SpanRun *__restrict__ runs, uint32_t *__restrict__ hist,
-             uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max)
+             int64_t n_spans, const SpanRun *__restrict__ runs, uint32_t *__restrict__ hist, uint32_t *__restrict__ other_min,
+             uint32_t *__restrict__ other_max)
 {
     __shared__ uint8_t lut_chr[2][256];
     __shared__ uint8_t lut_cls[2][256];
-    __shared__ __align__(4) uint8_t scratch_all[kFusedWarps * 32][20];
+    __shared__ uint32_t queue_all[kFusedWarps][kFusedQueue * kFusedEntryWords];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     for (int s = 0; s < 2; s++) {
         const uint8_t n = norm_char((uint8_t)t, s);
@@ -286,50 +293,66 @@ k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, int64_t n_rows, con
     }
     __syncthreads();
 
+    uint32_t *queue = queue_all[warp];
+    uint32_t q_head = 0, q_count = 0;    // warp-uniform
+    const unsigned lt = (1u << lane) - 1;
+
     const int64_t span = (int64_t)blockIdx.x * 32 + lane;
     const bool live = span < n_spans;
-    const int64_t sp = live ? span : n_spans - 1;
+    const uint32_t sp = (uint32_t)(live ? span : n_spans - 1);
     const int64_t row_begin = ((int64_t)blockIdx.y * kFusedWarps + warp) * kFusedRowsPerWarp;
     const int64_t row_end = min(n_rows, row_begin + kFusedRowsPerWarp);
-    const uint4 c = *reinterpret_cast<const uint4 *>(cons + sp * 16);
-    const uint32_t c4 = *reinterpret_cast<const uint32_t *>(cons + sp * 16 + 16);
-    // lane 31 has no right-hand neighbour in the warp: it fetches its own look-ahead bytes
-    // (only those inside the row; the rest count as equal to the consensus)
-    const int tail_avail = lane == 31 ? (int)max((int64_t)0, min((int64_t)4, row_bytes - (sp * 16 + 16))) : 0;
-    const uint8_t *p = aln + sp * 16;
+    const uint4 c = *reinterpret_cast<const uint4 *>(cons + (int64_t)sp * 16);
+    const uint32_t c4 = *reinterpret_cast<const uint32_t *>(cons + (int64_t)sp * 16 + 16);
+    const uint8_t *p = aln + (int64_t)sp * 16 + row_begin * pitch;
 
-    for (int64_t r = row_begin; r < row_end; r += kFusedUnroll) {
+    for (int64_t r = row_begin; r < row_end; r += kFusedUnroll, p += kFusedUnroll * pitch) {
         uint4 v[kFusedUnroll];
         uint32_t tail[kFusedUnroll];
 #pragma unroll
         for (int u = 0; u < kFusedUnroll; u++) {
-            const bool ok = r + u < row_end;
-            const uint8_t *q = p + (ok ? r + u : row_begin) * pitch;
+            const uint8_t *q = p + (r + u < row_end ? u : 0) * pitch;
             v[u] = ld_stream_v4(reinterpret_cast<const uint4 *>(q));
-            uint32_t tw = c4;
-            if (tail_avail == 4) tw = *reinterpret_cast<const uint32_t *>(q + 16);
-            else for (int k = 0; k < tail_avail; k++) tw = (tw & ~(0xFFu << (8 * k))) | ((uint32_t)q[16 + k] << (8 * k));
-            tail[u] = tw;
+            tail[u] = c4;
+            // lane 31 has no right-hand neighbour in the warp: it fetches its own look-ahead word
+            if (lane == 31) tail[u] = *reinterpret_cast<const uint32_t *>(q + 16);
         }
 #pragma unroll
         for (int u = 0; u < kFusedUnroll; u++) {
             const uint32_t nxt = __shfl_down_sync(kFull, v[u].x, 1);
             const uint32_t v4 = lane == 31 ? tail[u] : nxt;
             const uint32_t d = (v[u].x ^ c.x) | (v[u].y ^ c.y) | (v[u].z ^ c.z) | (v[u].w ^ c.w) | ((v4 ^ c4) & 0xFFFFu);
-            if (d != 0 && live && r + u < row_end)
-                fused_slow(v[u], v4, c, c4, runs + sp * kSpanRuns, hist, other_min, other_max, lut_cls, lut_chr, scratch_all[t]);
+            const bool differs = d != 0 && live && r + u < row_end;
+            const unsigned bal = __ballot_sync(kFull, differs);
+            if (differs) {   // park the bytes; a full warp decodes 32 parked spans at a time
+                uint32_t *e = queue + ((q_head + q_count + __popc(bal & lt)) & (kFusedQueue - 1)) * kFusedEntryWords;
+                e[0] = v[u].x; e[1] = v[u].y; e[2] = v[u].z; e[3] = v[u].w; e[4] = v4; e[5] = sp;
+            }
+            q_count += __popc(bal);
+            if (u & 1) {     // at most 31 + 64 parked entries between drains
+                while (q_count >= 32) {
+                    __syncwarp();
+                    fused_decode(queue + ((q_head + lane) & (kFusedQueue - 1)) * kFusedEntryWords, cons, runs, hist, other_min,
+                                 other_max, lut_cls, lut_chr);
+                    __syncwarp();
+                    q_head += 32;
+                    q_count -= 32;
+                }
+            }
         }
     }
+    __syncwarp();
+    if ((uint32_t)lane < q_count)
+        fused_decode(queue + ((q_head + lane) & (kFusedQueue - 1)) * kFusedEntryWords, cons, runs, hist, other_min, other_max,
+                     lut_cls, lut_chr);
 }
 
-// After all row blocks: credit the consensus codon of every regular codon with the
-// rows that never reached the decode path.
-__global__ void k_fused_fixup(const uint8_t *__restrict__ cons, int64_t cons_shift, const CodonMap *__restrict__ map,
-                              const uint8_t *__restrict__ regular, int64_t n_codons, uint32_t n_rows,
-                              uint32_t *__restrict__ hist, uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max)
+// Code of the consensus row's codon for every codon (the fused kernel's reference point).
+__global__ void k_cons_codes(const uint8_t *__restrict__ cons, int64_t cons_shift, const CodonMap *__restrict__ map,
+                             int64_t n_codons, uint8_t *__restrict__ cons_code, uint32_t *__restrict__ cons_key)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_codons || !regular[c]) return;
+    if (c >= n_codons) return;
     const CodonMap m = map[c];
     const uint8_t n0 = norm_char(cons[m.p0 + cons_shift], m.minus), n1 = norm_char(cons[m.p1 + cons_shift], m.minus),
                   n2 = norm_char(cons[m.p2 + cons_shift], m.minus);
@@ -338,16 +361,28 @@ __global__ void k_fused_fixup(const uint8_t *__restrict__ cons, int64_t cons_shi
     if (max(k0, max(k1, k2)) < 4) code = k0 * 16 + k1 * 4 + k2;
     else if (k0 == 4 || k1 == 4 || k2 == 4) code = kCodeUndef;
     else code = kCodeOther;
+    cons_code[c] = (uint8_t)code;
+    cons_key[c] = ((uint32_t)n0 << 16) | ((uint32_t)n1 << 8) | n2;
+}
+
+// After all row blocks: credit the consensus codon of every regular codon with the
+// rows that never reached the decode path.
+__global__ void k_fused_fixup(const uint8_t *__restrict__ cons_code, const uint32_t *__restrict__ cons_key,
+                              const uint8_t *__restrict__ regular, int64_t n_codons, uint32_t n_rows,
+                              uint32_t *__restrict__ hist, uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_codons || !regular[c]) return;
     uint32_t *h = hist + c * kHistBins;
     uint32_t seen = 0;
     for (int b = 0; b < kHistBins; b++) seen += h[b];
-    const uint32_t rest = n_rows - seen;
+    const uint32_t rest = n_rows - seen;       // rows that were never parked, or decoded to the consensus code
     if (rest) {
+        const uint32_t code = cons_code[c];
         h[code] += rest;
-        if (code == kCodeOther) {
-            const uint32_t key = ((uint32_t)n0 << 16) | ((uint32_t)n1 << 8) | n2;
-            other_min[c] = min(other_min[c], key);
-            other_max[c] = max(other_max[c], key);
+        if (code == kCodeOther) {              // their codon string is the consensus string
+            other_min[c] = min(other_min[c], cons_key[c]);
+            other_max[c] = max(other_max[c], cons_key[c]);
         }
     }
 }
@@ -572,60 +607,13 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 }
 
 // ---------------------------------------------------------------------------
-// K4: whole-product bootstrap (wg:854-916; bgp:893-989).  One warp per
-// replicate; lanes share the C draws.  A draw is int(rand(C+1)) (wg:885): slot 0
-// is the reference's nonexistent codon 0 and contributes nothing.
+// Per-replicate values.  dN = Nd/Ns if Ns > 0, else the reference's '*' which its
+// arithmetic reads as 0 (wg:942-961); Jukes-Cantor as bgp:1047-1071.
+// which: 0 dN, 1 dS, 2 dN-dS, 3 JC dN, 4 JC dS, 5 JC dN-dS.
 // ---------------------------------------------------------------------------
-constexpr int kBootWarps = 8;
-
-__global__ void __launch_bounds__(kBootWarps * 32)
-k_bootstrap(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, int64_t b_first, int64_t b_count,
-            uint2 key, uint32_t stream_id, double *__restrict__ rep)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t bl = (int64_t)blockIdx.x * kBootWarps + warp;
-    if (bl >= b_count) return;
-    const int p = blockIdx.y;
-    const int64_t c0 = ofs[p];
-    const uint32_t C = (uint32_t)(ofs[p + 1] - c0);
-    const double *S = stats4 + 4 * c0;
-    const uint64_t b = (uint64_t)(b_first + bl);
-    const uint32_t nquad = (C + 3) >> 2;
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    for (uint32_t q = lane; q < nquad; q += 32) {
-        const uint4 u = philox4x32_10(make_uint4(q, (uint32_t)b, (uint32_t)(b >> 32) ^ ((uint32_t)p << 8), stream_id), key);
-        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (4 * q + j < C) {
-                const uint32_t r = __umulhi(uu[j], C + 1);
-                if (r) {
-                    const double2 x = __ldg(reinterpret_cast<const double2 *>(S + 4 * (size_t)(r - 1)));
-                    const double2 y = __ldg(reinterpret_cast<const double2 *>(S + 4 * (size_t)(r - 1)) + 1);
-                    s0 += x.x; s1 += x.y; s2 += y.x; s3 += y.y;
-                }
-            }
-        }
-    }
-    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
-    if (lane == 0) {
-        double2 *o = reinterpret_cast<double2 *>(rep + 4 * ((size_t)p * b_count + bl));
-        o[0] = make_double2(s0, s1);
-        o[1] = make_double2(s2, s3);
-    }
-}
-
-// ---------------------------------------------------------------------------
-// K6: moments over replicates.  Per replicate dN = Nd/Ns if Ns > 0 else the
-// reference's '*' which its arithmetic reads as 0 (wg:942-961); JC as
-// bgp:1047-1071.  SD is the reference's two-pass form with n-1 (wg:1351-1365).
-// One block per (product | window).  se[6] = dN, dS, dN-dS, JC dN, JC dS, JC dN-dS.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ double rep_value(const double *rep4, int which) {
-    const double2 x = reinterpret_cast<const double2 *>(rep4)[0];
-    const double2 y = reinterpret_cast<const double2 *>(rep4)[1];
-    const double dn = x.x > 0 ? y.x / x.x : 0.0;
-    const double ds = x.y > 0 ? y.y / x.y : 0.0;
+__device__ __forceinline__ double rep_value(double ns, double ss, double nd, double sd, int which) {
+    const double dn = ns > 0 ? nd / ns : 0.0;
+    const double ds = ss > 0 ? sd / ss : 0.0;
     if (which == 0) return dn;
     if (which == 1) return ds;
     if (which == 2) return dn - ds;
@@ -636,6 +624,95 @@ __device__ __forceinline__ double rep_value(const double *rep4, int which) {
     return (jn >= 0 && js >= 0) ? jn - js : 0.0;
 }
 
+// ---------------------------------------------------------------------------
+// K4: whole-product bootstrap (wg:854-916; bgp:893-989).  One warp per
+// replicate; lanes share the C draws.  A draw is int(rand(C+1)) (wg:885): slot 0
+// is the reference's nonexistent codon 0 and contributes nothing.
+// The product's table is staged in shared memory as two 16-byte arrays,
+// (N_sites, S_sites) and (N_diffs, S_diffs); the sign bit of N_sites marks the
+// codons that have differences at all, so a draw on a conserved codon (most of
+// an alignment) costs one 16-byte gather instead of two.
+// Outputs: rep[p][b][4] replicate sums (optional) and vals[which][p][b].
+// ---------------------------------------------------------------------------
+constexpr int kBootWarps = 32;
+constexpr int kBootRepsPerWarp = 2;
+constexpr int kBootSmemLimit = 200 * 1024;
+
+template <bool SMEM>
+__global__ void __launch_bounds__(kBootWarps * 32)
+k_bootstrap(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, const int *__restrict__ order, int n_products,
+            int64_t b_first, int64_t b_count, uint2 key, uint32_t stream_id, double *__restrict__ rep, double *__restrict__ vals)
+{
+    extern __shared__ double2 s_tab[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int p = order ? order[blockIdx.y] : blockIdx.y;
+    const int64_t c0 = ofs[p];
+    const uint32_t C = (uint32_t)(ofs[p + 1] - c0);
+    const double2 *G = reinterpret_cast<const double2 *>(stats4 + 4 * c0);
+    // shared table rows 0..C: row 0 is the empty slot, row r is codon r
+    double2 *A = s_tab, *D = s_tab + (C + 1);
+    if (SMEM) {
+        if (threadIdx.x == 0) { A[0] = make_double2(0.0, 0.0); D[0] = make_double2(0.0, 0.0); }
+        for (uint32_t i = threadIdx.x; i < C; i += blockDim.x) {
+            double2 a = G[2 * i];
+            const double2 d = G[2 * i + 1];
+            if (d.x != 0.0 || d.y != 0.0) a.x = -a.x;        // flag: this codon has differences (-0.0 also carries it)
+            A[i + 1] = a;
+            D[i + 1] = d;
+        }
+        __syncthreads();
+    }
+    const uint32_t nquad = (C + 3) >> 2, full_quads = C >> 2;
+    for (int k = 0; k < kBootRepsPerWarp; k++) {
+        const int64_t bl = ((int64_t)blockIdx.x * kBootWarps + warp) * kBootRepsPerWarp + k;
+        if (bl >= b_count) break;
+        const uint64_t b = (uint64_t)(b_first + bl);
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        for (uint32_t q = lane; q < nquad; q += 32) {
+            const uint4 u = philox4x32_10(make_uint4(q, (uint32_t)b, (uint32_t)(b >> 32) ^ ((uint32_t)p << 8), stream_id), key);
+            const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+            const int nd = q < full_quads ? 4 : (int)(C & 3);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (j < nd) {
+                    const uint32_t r = __umulhi(uu[j], C + 1);
+                    if (SMEM) {
+                        const double2 a = A[r];
+                        s0 += fabs(a.x); s1 += a.y;
+                        if (__double2hiint(a.x) < 0) { const double2 d = D[r]; s2 += d.x; s3 += d.y; }
+                    } else if (r) {
+                        const double2 a = __ldg(G + 2 * (size_t)(r - 1));
+                        const double2 d = __ldg(G + 2 * (size_t)(r - 1) + 1);
+                        s0 += a.x; s1 += a.y; s2 += d.x; s3 += d.y;
+                    }
+                }
+            }
+        }
+        s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+        if (lane == 0 && rep) {
+            double2 *o = reinterpret_cast<double2 *>(rep + 4 * ((size_t)p * b_count + bl));
+            o[0] = make_double2(s0, s1);
+            o[1] = make_double2(s2, s3);
+        }
+        if (lane < 6 && vals) vals[((size_t)lane * n_products + p) * b_count + bl] = rep_value(s0, s1, s2, s3, lane);
+    }
+}
+
+// rep[item][B][4] -> vals[which][item][B]  (paths that gathered replicate sums first)
+__global__ void k_rep_values(const double *__restrict__ rep, int64_t n_items, int64_t B, double *__restrict__ vals)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items * B) return;
+    const double2 x = reinterpret_cast<const double2 *>(rep + 4 * i)[0];
+    const double2 y = reinterpret_cast<const double2 *>(rep + 4 * i)[1];
+    const int which = blockIdx.y;
+    vals[(size_t)which * n_items * B + i] = rep_value(x.x, x.y, y.x, y.y, which);
+}
+
+// ---------------------------------------------------------------------------
+// K6: SD over replicates in the reference's two-pass form with n-1
+// (wg:1351-1365).  One block per (item, statistic); se[item][6].
+// ---------------------------------------------------------------------------
 __device__ __forceinline__ double block_sum_256(double v, double *red) {
     const int t = threadIdx.x;
     __syncthreads();
@@ -649,16 +726,16 @@ __device__ __forceinline__ double block_sum_256(double v, double *red) {
 }
 
 __global__ void __launch_bounds__(256)
-k_rep_moments(const double *__restrict__ rep, int64_t B, double *__restrict__ se)
+k_moments(const double *__restrict__ vals, int64_t n_items, int64_t B, double *__restrict__ se)
 {
     __shared__ double red[256];
-    const int p = blockIdx.x, which = blockIdx.y, t = threadIdx.x;   // one block per (item, statistic)
-    const double *R = rep + 4 * (size_t)p * B;
+    const int p = blockIdx.x, which = blockIdx.y, t = threadIdx.x;
+    const double *V = vals + ((size_t)which * n_items + p) * B;
     double s = 0;
-    for (int64_t b = t; b < B; b += 256) s += rep_value(R + 4 * b, which);
+    for (int64_t b = t; b < B; b += 256) s += V[b];
     const double mean = block_sum_256(s, red) / (double)B;
     double ss = 0;
-    for (int64_t b = t; b < B; b += 256) { const double d = rep_value(R + 4 * b, which) - mean; ss += d * d; }
+    for (int64_t b = t; b < B; b += 256) { const double d = V[b] - mean; ss += d * d; }
     const double tot = block_sum_256(ss, red);
     if (t == 0) se[6 * p + which] = sqrt(tot / (double)(B - 1));
 }
@@ -737,24 +814,31 @@ void launch_hist(const uint8_t *d_codes, int64_t n_pad, int64_t n_codons, uint32
                                                                                                chunk_rows, d_hist);
 }
 
+void launch_cons_codes(const uint8_t *d_cons, int64_t cons_shift, const CodonMap *d_map, int64_t n_codons, uint8_t *d_cons_code,
+                       uint32_t *d_cons_key, cudaStream_t stream)
+{
+    if (n_codons <= 0) return;
+    k_cons_codes<<<(unsigned)((n_codons + 127) / 128), 128, 0, stream>>>(d_cons, cons_shift, d_map, n_codons, d_cons_code, d_cons_key);
+}
+
 void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, const uint8_t *d_cons, int64_t n_spans,
-                       int64_t row_bytes, const SpanRun *d_runs, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max,
-                       cudaStream_t stream)
+                       const SpanRun *d_runs, const uint8_t *d_cons_code, uint32_t *d_hist, uint32_t *d_other_min,
+                       uint32_t *d_other_max, cudaStream_t stream)
 {
     if (n_spans <= 0 || n_rows <= 0) return;
     const int64_t rows_per_block = (int64_t)kFusedWarps * kFusedRowsPerWarp;
     dim3 grid((unsigned)((n_spans + 31) / 32), (unsigned)((n_rows + rows_per_block - 1) / rows_per_block));
-    k_fused_hist<<<grid, kFusedWarps * 32, 0, stream>>>(d_aln, pitch, n_rows, d_cons, n_spans, row_bytes, d_runs, d_hist,
-                                                        d_other_min, d_other_max);
+    (void)d_cons_code;
+    k_fused_hist<<<grid, kFusedWarps * 32, 0, stream>>>(d_aln, pitch, n_rows, d_cons, n_spans, d_runs, d_hist, d_other_min,
+                                                        d_other_max);
 }
 
-void launch_fused_fixup(const uint8_t *d_cons, int64_t cons_shift, const CodonMap *d_map, const uint8_t *d_regular,
-                        int64_t n_codons, uint32_t n_rows, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max,
-                        cudaStream_t stream)
+void launch_fused_fixup(const uint8_t *d_cons_code, const uint32_t *d_cons_key, const uint8_t *d_regular, int64_t n_codons,
+                        uint32_t n_rows, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max, cudaStream_t stream)
 {
     if (n_codons <= 0) return;
-    k_fused_fixup<<<(unsigned)((n_codons + 127) / 128), 128, 0, stream>>>(d_cons, cons_shift, d_map, d_regular, n_codons, n_rows,
-                                                                           d_hist, d_other_min, d_other_max);
+    k_fused_fixup<<<(unsigned)((n_codons + 127) / 128), 128, 0, stream>>>(d_cons_code, d_cons_key, d_regular, n_codons, n_rows, d_hist,
+                                                                           d_other_min, d_other_max);
 }
 
 void launch_scatter_irregular(const uint32_t *d_tmp_hist, const uint32_t *d_tmp_min, const uint32_t *d_tmp_max,
@@ -796,19 +880,36 @@ void launch_product_sums(const double *d_stats4, const int64_t *d_prod_ofs, int 
     k_product_sums<<<n_products, 256, 0, stream>>>(d_stats4, d_prod_ofs, d_sums);
 }
 
-void launch_bootstrap(const double *d_stats4, const int64_t *d_prod_ofs, int n_products, int64_t b_first, int64_t b_count,
-                      uint64_t seed, uint32_t stream_id, double *d_rep, cudaStream_t stream)
+void launch_bootstrap(const double *d_stats4, const int64_t *d_prod_ofs, const int *d_order, int n_products, int64_t max_codons,
+                      int64_t b_first, int64_t b_count, uint64_t seed, uint32_t stream_id, double *d_rep, double *d_vals,
+                      cudaStream_t stream)
 {
     if (n_products <= 0 || b_count <= 0) return;
-    dim3 grid((unsigned)((b_count + kBootWarps - 1) / kBootWarps), (unsigned)n_products);
-    k_bootstrap<<<grid, kBootWarps * 32, 0, stream>>>(d_stats4, d_prod_ofs, b_first, b_count,
-                                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), stream_id, d_rep);
+    const int64_t per_block = (int64_t)kBootWarps * kBootRepsPerWarp;
+    dim3 grid((unsigned)((b_count + per_block - 1) / per_block), (unsigned)n_products);
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    const size_t smem = (size_t)(max_codons + 1) * 32;
+    if (smem <= (size_t)kBootSmemLimit) {
+        cudaFuncSetAttribute(k_bootstrap<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBootSmemLimit);  // per device
+        k_bootstrap<true><<<grid, kBootWarps * 32, smem, stream>>>(d_stats4, d_prod_ofs, d_order, n_products, b_first, b_count, key,
+                                                                    stream_id, d_rep, d_vals);
+    } else {
+        k_bootstrap<false><<<grid, kBootWarps * 32, 0, stream>>>(d_stats4, d_prod_ofs, d_order, n_products, b_first, b_count, key,
+                                                                  stream_id, d_rep, d_vals);
+    }
 }
 
-void launch_rep_moments(const double *d_rep, int64_t n_items, int64_t B, double *d_se, cudaStream_t stream)
+void launch_rep_values(const double *d_rep, int64_t n_items, int64_t B, double *d_vals, cudaStream_t stream)
+{
+    if (n_items <= 0 || B <= 0) return;
+    dim3 grid((unsigned)((n_items * B + 255) / 256), 6);
+    k_rep_values<<<grid, 256, 0, stream>>>(d_rep, n_items, B, d_vals);
+}
+
+void launch_moments(const double *d_vals, int64_t n_items, int64_t B, double *d_se, cudaStream_t stream)
 {
     if (n_items <= 0) return;
-    k_rep_moments<<<dim3((unsigned)n_items, 6), 256, 0, stream>>>(d_rep, B, d_se);
+    k_moments<<<dim3((unsigned)n_items, 6), 256, 0, stream>>>(d_vals, n_items, B, d_se);
 }
 
 void launch_window_sums(const double *d_stats4, int64_t W, int64_t step, int64_t nwin, double *d_win_sums,

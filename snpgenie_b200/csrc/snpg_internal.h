@@ -49,16 +49,17 @@ void launch_pack(const uint8_t *d_aln, int64_t row_stride, int64_t n_rows, int64
 void launch_hist(const uint8_t *d_codes, int64_t n_pad, int64_t n_codons, uint32_t *d_hist, cudaStream_t stream);
 
 // K1+K2 fused (no code matrix): d_aln points at the first span's bytes of the first
-// row; spans are 16-byte aligned; d_cons holds the consensus row for the same
-// columns (+ 16 readable bytes past the last span); row_bytes = bytes readable
-// in a row counted from the first span.  hist must be zeroed before the first
-// row block; launch_fused_fixup runs once after the last.
+// row; spans are 16-byte aligned and every row must have >= n_spans*16 + 4 readable
+// bytes from there; d_cons holds the consensus row for the same columns.
+// Sequence: launch_cons_codes once per group (after the consensus row is known),
+// launch_fused_hist per row block (hist zeroed before the first), launch_fused_fixup once.
+void launch_cons_codes(const uint8_t *d_cons, int64_t cons_shift, const CodonMap *d_map, int64_t n_codons, uint8_t *d_cons_code,
+                       uint32_t *d_cons_key, cudaStream_t stream);
 void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, const uint8_t *d_cons, int64_t n_spans,
-                       int64_t row_bytes, const SpanRun *d_runs, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max,
-                       cudaStream_t stream);
-void launch_fused_fixup(const uint8_t *d_cons, int64_t cons_shift, const CodonMap *d_map, const uint8_t *d_regular,
-                        int64_t n_codons, uint32_t n_rows, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max,
-                        cudaStream_t stream);
+                       const SpanRun *d_runs, const uint8_t *d_cons_code, uint32_t *d_hist, uint32_t *d_other_min,
+                       uint32_t *d_other_max, cudaStream_t stream);
+void launch_fused_fixup(const uint8_t *d_cons_code, const uint32_t *d_cons_key, const uint8_t *d_regular, int64_t n_codons,
+                        uint32_t n_rows, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max, cudaStream_t stream);
 void launch_scatter_irregular(const uint32_t *d_tmp_hist, const uint32_t *d_tmp_min, const uint32_t *d_tmp_max,
                               const int32_t *d_idx, int64_t n_irr, uint32_t *d_hist, uint32_t *d_other_min,
                               uint32_t *d_other_max, cudaStream_t stream);
@@ -81,11 +82,18 @@ void launch_between_stats(GroupView A, GroupView B, int64_t n_codons, const doub
 void launch_product_sums(const double *d_stats4, const int64_t *d_prod_ofs, int n_products, double *d_sums,
                          cudaStream_t stream);
 
-// K4 whole-product bootstrap: rep[p][b - b_first][4] for b in [b_first, b_first+b_count)
-void launch_bootstrap(const double *d_stats4, const int64_t *d_prod_ofs, int n_products, int64_t b_first, int64_t b_count,
-                      uint64_t seed, uint32_t stream_id, double *d_rep, cudaStream_t stream);
-// K6 moments: rep[item][B][4] -> se[item][6] (SD of dN, dS, dN-dS, JC dN, JC dS, JC dN-dS)
-void launch_rep_moments(const double *d_rep, int64_t n_items, int64_t B, double *d_se, cudaStream_t stream);
+// K4 whole-product bootstrap over products [0, n_products): replicates
+// [b_first, b_first+b_count).  d_order (or null) lists products largest first.
+// max_codons = largest product (sizes the shared-memory table; larger than the
+// limit falls back to gathers from global memory).  Outputs (either may be null):
+// d_rep[p][b][4] replicate sums, d_vals[which][p][b] per-replicate dN, dS, dN-dS, JC x3.
+void launch_bootstrap(const double *d_stats4, const int64_t *d_prod_ofs, const int *d_order, int n_products, int64_t max_codons,
+                      int64_t b_first, int64_t b_count, uint64_t seed, uint32_t stream_id, double *d_rep, double *d_vals,
+                      cudaStream_t stream);
+// rep[item][B][4] -> vals[which][item][B]
+void launch_rep_values(const double *d_rep, int64_t n_items, int64_t B, double *d_vals, cudaStream_t stream);
+// K6 moments: vals[which][item][B] -> se[item][6] (sample SD, n-1, two-pass)
+void launch_moments(const double *d_vals, int64_t n_items, int64_t B, double *d_se, cudaStream_t stream);
 
 // K5 windows
 void launch_window_sums(const double *d_stats4, int64_t W, int64_t step, int64_t nwin, double *d_win_sums,

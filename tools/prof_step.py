@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Small driver for ncu captures: a few device-resident steps of the config-2 hot path.
+
+    python tools/prof_step.py [--steps 3] [--route fused|codes] [--n 10000]
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from snpgenie_b200 import _abi, synth  # noqa: E402
+from snpgenie_b200.engine import Engine  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--route", default="fused")
+ap.add_argument("--n", type=int, default=10000)
+ap.add_argument("--boot", type=int, default=10000)
+a = ap.parse_args()
+products = synth.sars2_products()
+L = 29903
+aln = synth.make_alignment(a.n, L, products, 20261021)
+pitch = (L + 127) // 128 * 128
+d = torch.zeros((a.n, pitch), dtype=torch.uint8, device="cuda:0")
+d[:, :L] = torch.from_numpy(aln).cuda()
+with Engine(device=0) as eng:
+    eng.set_option(_abi.OPT_KEEP_CODES, 1 if a.route == "codes" else 0)
+    eng.set_products(products, L)
+    for _ in range(a.steps):
+        eng.load_group_ptr(0, d.data_ptr(), a.n, L, pitch, device=True)
+        sums, se = eng.within_all(0, B=a.boot)
+    print("ok", sums[0], se[0][:3])
