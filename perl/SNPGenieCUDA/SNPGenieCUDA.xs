@@ -1,0 +1,220 @@
+/*
+ * SNPGenieCUDA.xs -- Perl XS glue over the C ABI of libsnpgenie_cuda.so
+ * (include/snpgenie_cuda.h).  Arrays cross the boundary as packed Perl strings
+ * (pack "q*", "d*", ...): the caller packs inputs, the glue sizes output SVs and
+ * lets the library write straight into them.  Errors croak with the library's
+ * message, which is what the reference's die() calls look like to a user.
+ */
+#define PERL_NO_GET_CONTEXT
+#include "EXTERN.h"
+#include "perl.h"
+#include "XSUB.h"
+
+#include "snpgenie_cuda.h"
+
+static snpg_ctx *ctx_of(pTHX_ IV h) {
+    if (!h) croak("SNPGenieCUDA: null context");
+    return INT2PTR(snpg_ctx *, h);
+}
+
+static void check(pTHX_ snpg_ctx *ctx, int rc, const char *what) {
+    if (rc != SNPG_OK) croak("\n### SNPGenieCUDA %s failed (%d): %s\n", what, rc, snpg_last_error(ctx));
+}
+
+/* a fresh mortal string SV with room for n bytes, length already set */
+static SV *out_buf(pTHX_ STRLEN n) {
+    SV *sv = sv_2mortal(newSV(n ? n : 1));
+    SvPOK_only(sv);
+    SvCUR_set(sv, n);
+    if (n) memset(SvPVX(sv), 0, n);
+    *SvEND(sv) = '\0';
+    return sv;
+}
+
+static const void *in_buf(pTHX_ SV *sv, STRLEN need, const char *name) {
+    STRLEN len;
+    const char *p = SvPVbyte(sv, len);
+    if (len < need) croak("SNPGenieCUDA: %s holds %lu bytes, %lu needed", name, (unsigned long)len, (unsigned long)need);
+    return p;
+}
+
+MODULE = SNPGenieCUDA    PACKAGE = SNPGenieCUDA
+
+PROTOTYPES: DISABLE
+
+const char *
+version()
+  CODE:
+    RETVAL = snpg_version();
+  OUTPUT:
+    RETVAL
+
+IV
+create(device, seed)
+    int device
+    UV seed
+  CODE:
+    snpg_ctx *ctx = NULL;
+    int rc = snpg_create(&ctx, device, (uint64_t)seed);
+    if (rc != SNPG_OK) croak("\n### SNPGenieCUDA could not start (%d): %s\n", rc, snpg_last_error(NULL));
+    RETVAL = PTR2IV(ctx);
+  OUTPUT:
+    RETVAL
+
+void
+destroy(h)
+    IV h
+  CODE:
+    if (h) snpg_destroy(INT2PTR(snpg_ctx *, h));
+
+void
+set_option(h, option, value)
+    IV h
+    int option
+    IV value
+  CODE:
+    snpg_ctx *ctx = ctx_of(aTHX_ h);
+    check(aTHX_ ctx, snpg_set_option(ctx, option, (int64_t)value), "set_option");
+
+void
+set_products(h, n_products, seg_ofs, seg_start, seg_stop, strand, aln_len)
+    IV h
+    int n_products
+    SV *seg_ofs
+    SV *seg_start
+    SV *seg_stop
+    SV *strand
+    IV aln_len
+  CODE:
+    snpg_ctx *ctx = ctx_of(aTHX_ h);
+    const int64_t *ofs = (const int64_t *)in_buf(aTHX_ seg_ofs, sizeof(int64_t) * (n_products + 1), "seg_ofs");
+    STRLEN nseg = (STRLEN)ofs[n_products];
+    check(aTHX_ ctx, snpg_set_products(ctx, n_products, ofs,
+                                       (const int64_t *)in_buf(aTHX_ seg_start, sizeof(int64_t) * nseg, "seg_start"),
+                                       (const int64_t *)in_buf(aTHX_ seg_stop, sizeof(int64_t) * nseg, "seg_stop"),
+                                       (const int8_t *)in_buf(aTHX_ strand, n_products, "strand"), (int64_t)aln_len),
+          "set_products");
+
+IV
+n_codons(h, product)
+    IV h
+    int product
+  CODE:
+    int64_t n = 0;
+    snpg_ctx *ctx = ctx_of(aTHX_ h);
+    check(aTHX_ ctx, snpg_n_codons(ctx, product, &n), "n_codons");
+    RETVAL = (IV)n;
+  OUTPUT:
+    RETVAL
+
+void
+load_group(h, group, bases, n_seqs, aln_len)
+    IV h
+    int group
+    SV *bases
+    UV n_seqs
+    UV aln_len
+  CODE:
+    snpg_ctx *ctx = ctx_of(aTHX_ h);
+    const uint8_t *p = (const uint8_t *)in_buf(aTHX_ bases, (STRLEN)(n_seqs * aln_len), "bases");
+    check(aTHX_ ctx, snpg_load_group(ctx, group, p, n_seqs, aln_len, aln_len), "load_group");
+
+void
+hist(h, group, product)
+    IV h
+    int group
+    int product
+  PPCODE:
+    snpg_ctx *ctx = ctx_of(aTHX_ h);
+    int64_t C = 0;
+    check(aTHX_ ctx, snpg_n_codons(ctx, product, &C), "n_codons");
+    SV *hs = out_buf(aTHX_ sizeof(uint32_t) * SNPG_HIST_BINS * (STRLEN)C), *od = out_buf(aTHX_ (STRLEN)C);
+    check(aTHX_ ctx, snpg_get_hist(ctx, group, product, (uint32_t *)SvPVX(hs), (uint8_t *)SvPVX(od)), "get_hist");
+    EXTEND(SP, 2);
+    PUSHs(hs);
+    PUSHs(od);
+
+void
+within(h, group, product)
+    IV h
+    int group
+    int product
+  PPCODE:
+    snpg_ctx *ctx = ctx_of(aTHX_ h);
+    int64_t C = 0;
+    check(aTHX_ ctx, snpg_n_codons(ctx, product, &C), "n_codons");
+    SV *poly = out_buf(aTHX_ (STRLEN)C), *ndef = out_buf(aTHX_ 4 * (STRLEN)C), *cmp = out_buf(aTHX_ 8 * (STRLEN)C),
+       *st = out_buf(aTHX_ 32 * (STRLEN)C), *cons = out_buf(aTHX_ (STRLEN)C);
+    check(aTHX_ ctx, snpg_within(ctx, group, product, (uint8_t *)SvPVX(poly), (uint32_t *)SvPVX(ndef), (uint64_t *)SvPVX(cmp),
+                                 (double *)SvPVX(st), (uint8_t *)SvPVX(cons)), "within");
+    EXTEND(SP, 5);
+    PUSHs(poly); PUSHs(ndef); PUSHs(cmp); PUSHs(st); PUSHs(cons);
+
+void
+between(h, group_a, group_b, product)
+    IV h
+    int group_a
+    int group_b
+    int product
+  PPCODE:
+    snpg_ctx *ctx = ctx_of(aTHX_ h);
+    int64_t C = 0;
+    check(aTHX_ ctx, snpg_n_codons(ctx, product, &C), "n_codons");
+    SV *poly = out_buf(aTHX_ (STRLEN)C), *nda = out_buf(aTHX_ 4 * (STRLEN)C), *ndb = out_buf(aTHX_ 4 * (STRLEN)C),
+       *cmp = out_buf(aTHX_ 8 * (STRLEN)C), *st = out_buf(aTHX_ 32 * (STRLEN)C), *cons = out_buf(aTHX_ (STRLEN)C);
+    check(aTHX_ ctx, snpg_between(ctx, group_a, group_b, product, (uint8_t *)SvPVX(poly), (uint32_t *)SvPVX(nda),
+                                  (uint32_t *)SvPVX(ndb), (uint64_t *)SvPVX(cmp), (double *)SvPVX(st), (uint8_t *)SvPVX(cons)),
+          "between");
+    EXTEND(SP, 6);
+    PUSHs(poly); PUSHs(nda); PUSHs(ndb); PUSHs(cmp); PUSHs(st); PUSHs(cons);
+
+void
+bootstrap_product(h, stats4, keep, C, B, want_sums)
+    IV h
+    SV *stats4
+    SV *keep
+    IV C
+    IV B
+    int want_sums
+  PPCODE:
+    snpg_ctx *ctx = ctx_of(aTHX_ h);
+    const double *st = (const double *)in_buf(aTHX_ stats4, 32 * (STRLEN)C, "stats4");
+    const uint8_t *kp = SvOK(keep) ? (const uint8_t *)in_buf(aTHX_ keep, (STRLEN)C, "keep") : NULL;
+    SV *se = out_buf(aTHX_ 6 * sizeof(double)), *sums = out_buf(aTHX_ want_sums ? 32 * (STRLEN)B : 0);
+    check(aTHX_ ctx, snpg_bootstrap_product(ctx, st, kp, (int64_t)C, (int64_t)B, want_sums ? (double *)SvPVX(sums) : NULL,
+                                            (double *)SvPVX(se)), "bootstrap_product");
+    EXTEND(SP, 2);
+    PUSHs(se);
+    PUSHs(sums);
+
+void
+windows(h, stats4, keep, C, W, step, B)
+    IV h
+    SV *stats4
+    SV *keep
+    IV C
+    IV W
+    IV step
+    IV B
+  PPCODE:
+    snpg_ctx *ctx = ctx_of(aTHX_ h);
+    const double *st = (const double *)in_buf(aTHX_ stats4, 32 * (STRLEN)C, "stats4");
+    const uint8_t *kp = SvOK(keep) ? (const uint8_t *)in_buf(aTHX_ keep, (STRLEN)C, "keep") : NULL;
+    int64_t nwin = 0;
+    check(aTHX_ ctx, snpg_windows(ctx, st, kp, (int64_t)C, (int64_t)W, (int64_t)step, 0, NULL, NULL, &nwin), "windows");
+    SV *sums = out_buf(aTHX_ 32 * (STRLEN)nwin), *se = out_buf(aTHX_ B >= 2 ? 24 * (STRLEN)nwin : 0);
+    check(aTHX_ ctx, snpg_windows(ctx, st, kp, (int64_t)C, (int64_t)W, (int64_t)step, (int64_t)B, (double *)SvPVX(sums),
+                                  B >= 2 ? (double *)SvPVX(se) : NULL, &nwin), "windows");
+    EXTEND(SP, 3);
+    PUSHs(sv_2mortal(newSViv((IV)nwin)));
+    PUSHs(sums);
+    PUSHs(se);
+
+void
+tables()
+  PPCODE:
+    SV *sites = out_buf(aTHX_ 128 * sizeof(double)), *diffs = out_buf(aTHX_ 8192 * sizeof(double));
+    if (snpg_get_tables((double *)SvPVX(sites), (double *)SvPVX(diffs)) != SNPG_OK) croak("SNPGenieCUDA: get_tables failed");
+    EXTEND(SP, 2);
+    PUSHs(sites);
+    PUSHs(diffs);

@@ -1,0 +1,17 @@
+package SNPGenieCUDA;
+# Perl binding of libsnpgenie_cuda.so (the B200 engine behind the within-/between-group
+# SNPGenie drivers).  Thin on purpose: the XS layer maps one-to-one onto
+# include/snpgenie_cuda.h; arrays travel as packed strings.
+use strict;
+use warnings;
+require XSLoader;
+our $VERSION = '0.1';
+XSLoader::load('SNPGenieCUDA', $VERSION);
+
+use constant { CODE_UNDEF => 64, CODE_OTHER => 65, HIST_BINS => 66, OPT_KEEP_CODES => 1 };
+
+my @NT = qw(A C G T);
+# codon string of a code 0..63
+sub codon_of { my ($c) = @_; return $NT[$c >> 4] . $NT[($c >> 2) & 3] . $NT[$c & 3]; }
+
+1;
