@@ -76,6 +76,9 @@ int snpg_n_codons(const snpg_ctx *ctx, int product, int64_t *out);
  * axis (all products concatenated in set_products order).  rank/world as in
  * torch.distributed; default 0/1.  Call before snpg_set_products. */
 int snpg_set_shard(snpg_ctx *ctx, int rank, int world);
+/* The split itself (pure, no ctx, no device): rank r of w owns [first, first+count) of `total` units.
+ * Used for codon ranges (snpg_set_shard) and for bootstrap replicate ranges. */
+int snpg_shard_plan(int64_t total, int rank, int world, int64_t *first, int64_t *count);
 int snpg_shard_range(const snpg_ctx *ctx, int64_t *first, int64_t *count, int64_t *total);
 
 /* ---- alignment ingest: pack + per-codon histogram ------------------------

@@ -38,6 +38,7 @@ SIGNATURES = {
     "snpg_n_products": (C.c_int, [_ctx]),
     "snpg_n_codons": (C.c_int, [_ctx, C.c_int, _i64p]),
     "snpg_set_shard": (C.c_int, [_ctx, C.c_int, C.c_int]),
+    "snpg_shard_plan": (C.c_int, [C.c_int64, C.c_int, C.c_int, _i64p, _i64p]),
     "snpg_shard_range": (C.c_int, [_ctx, _i64p, _i64p, _i64p]),
     "snpg_load_group": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
     "snpg_load_group_device": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),

@@ -321,6 +321,13 @@ int snpg_set_option(snpg_ctx *ctx, int option, int64_t value) {
     return fail(ctx, SNPG_E_ARG, "unknown option %d", option);
 }
 
+int snpg_shard_plan(int64_t total, int rank, int world, int64_t *first, int64_t *count) {
+    if (total < 0 || world < 1 || rank < 0 || rank >= world || !first || !count) return SNPG_E_ARG;
+    *first = total * rank / world;
+    *count = total * (rank + 1) / world - *first;
+    return SNPG_OK;
+}
+
 int snpg_set_shard(snpg_ctx *ctx, int rank, int world) {
     if (!ctx) return SNPG_E_ARG;
     NEED(ctx, world >= 1 && rank >= 0 && rank < world, SNPG_E_ARG, "bad shard %d/%d", rank, world);
@@ -361,8 +368,7 @@ int snpg_set_products(snpg_ctx *ctx, int n_products, const int64_t *seg_ofs, con
         full_ofs[p + 1] = (int64_t)map_all.size();
     }
     const int64_t total = (int64_t)map_all.size();
-    ctx->shard_first = total * ctx->rank / ctx->world;
-    ctx->shard_count = total * (ctx->rank + 1) / ctx->world - ctx->shard_first;
+    snpg_shard_plan(total, ctx->rank, ctx->world, &ctx->shard_first, &ctx->shard_count);
     ctx->n_products = n_products;
     ctx->aln_len = aln_len;
     ctx->full_ofs = full_ofs;

@@ -1,0 +1,58 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/*.h declares."""
+import ctypes
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    names = set()
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        text = re.sub(r"/\*.*?\*/", "", open(h).read(), flags=re.S)
+        names |= set(re.findall(r"\b(snpg_[a-z0-9_]+)\s*\(", text))
+    return names
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    from snpgenie_b200 import _abi
+    decl = declared_symbols()
+    assert len(decl) >= 30
+    for name in decl:
+        assert hasattr(_abi.lib, name), f"{name} declared in include/ but not exported"
+    assert decl == set(_abi.SIGNATURES), (decl ^ set(_abi.SIGNATURES))
+
+
+def test_host_only_entry_points_work_without_a_gpu():
+    from oracle import oracle as orc
+    from snpgenie_b200 import _abi, engine
+    assert b"sm_100a" in _abi.lib.snpg_version()
+    sites, diffs = engine.ng_tables()                      # the product's own table builder ...
+    osites, odiffs = orc.tables()                          # ... against the oracle's (independent code)
+    assert np.array_equal(sites, osites) and np.array_equal(diffs, odiffs)
+    f, c = ctypes.c_int64(), ctypes.c_int64()
+    assert _abi.lib.snpg_shard_plan(9677, 3, 8, ctypes.byref(f), ctypes.byref(c)) == 0
+    assert (f.value, c.value) == (9677 * 3 // 8, 9677 * 4 // 8 - 9677 * 3 // 8)
+    assert _abi.lib.snpg_shard_plan(10, 2, 2, ctypes.byref(f), ctypes.byref(c)) == _abi.E_ARG
+
+
+def test_no_silent_cpu_fallback():
+    """Without a device the product must fail loudly, never compute on the host."""
+    import torch
+    from snpgenie_b200 import _abi, engine
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_abi.SnpgError) as e:
+        engine.Engine()
+    assert e.value.code == _abi.E_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    for path in glob.glob(os.path.join(ROOT, "snpgenie_b200", "**", "*"), recursive=True) + glob.glob(os.path.join(ROOT, "perl", "**", "*"), recursive=True):
+        if os.path.isfile(path) and path.endswith((".py", ".cu", ".h", ".cpp", ".pl", ".pm", ".xs")):
+            text = open(path, errors="ignore").read()
+            assert "oracle" not in text.replace("the oracle's", ""), path

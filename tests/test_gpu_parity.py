@@ -460,3 +460,39 @@ def test_fused_route_irregular_codons_and_many_layers():
         with pytest.raises(_abi.SnpgError) as err:
             e.codon_indices(0, 0)
         assert err.value.code == _abi.E_STATE
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("keep", [1, 0])
+def test_codon_range_shards_reassemble(world, keep):
+    """Every rank's ctx owns a slice of the global codon axis; concatenated slices == the unsharded run.
+
+    (Ranks are emulated as successive contexts on one GPU; the exchange itself is tested with gloo on CPU.)"""
+    from snpgenie_b200 import _abi
+    from snpgenie_b200.engine import Engine
+    products = synth.hiv_products()
+    aln = synth.make_alignment(600, 9719, products, 31, gap_frac=0.02, n_frac=0.02, iupac_frac=0.004)
+    with Engine(device=0) as full:
+        full.set_products(products, 9719)
+        full.load_group(0, aln)
+        ref_hist = [full.hist(0, i)[0] for i in range(len(products))]
+        ref_stats = [full.within(0, i)["stats4"] for i in range(len(products))]
+    got_hist = [[] for _ in products]
+    got_stats = [[] for _ in products]
+    covered = 0
+    for r in range(world):
+        with Engine(device=0, rank=r, world=world) as e:
+            e.set_option(_abi.OPT_KEEP_CODES, keep)
+            e.set_products(products, 9719)
+            first, count, total = e.shard_range()
+            assert total == sum(p.n_codons for p in products)
+            covered += count
+            e.load_group(0, aln)
+            for i in range(len(products)):
+                if e.local_codons(i):
+                    got_hist[i].append(e.hist(0, i)[0])
+                    got_stats[i].append(e.within(0, i)["stats4"])
+    assert covered == sum(p.n_codons for p in products)
+    for i in range(len(products)):
+        assert np.array_equal(np.concatenate(got_hist[i]), ref_hist[i])
+        assert np.array_equal(np.concatenate(got_stats[i]), ref_stats[i])
