@@ -107,7 +107,7 @@ def cpu_pair_rate(target_s=12.0):
     from oracle import oracle as orc
     from snpgenie_b200 import synth
     products = synth.sars2_products()
-    threads = orc.max_threads()
+    threads = orc.use_all_cores()
     # the sample keeps all n sequences (cost is quadratic in n) and takes the first k codons of CDS3 (spike-shaped)
     p = products[2]
     k_probe = max(threads, 8)
@@ -191,17 +191,19 @@ def run_ours(args):
     eng = Engine(device=local, seed=SEED)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
-    eng.set_option(_abi.OPT_PROFILE, 1)
+    # timed passes bracket only the dominant HBM kernel with events (a pair costs ~3 us of stream time);
+    # a separate untimed pass of the same steps brackets every launch for the per-kernel table
+    hbm_kinds = ["fused"] if args.route == "fused" else ["pack", "hist"]
+    narrow = sum(1 << _abi.KERNEL_KINDS.index(k) for k in hbm_kinds)
+    eng.set_option(_abi.OPT_PROFILE, 0 if args.no_profile else narrow)
     eng.set_option(_abi.OPT_KEEP_CODES, 1 if args.route == "codes" else 0)
     eng.set_products(products, ALN_LEN)
 
     def step_resident():
-        eng.load_group_ptr(0, d_aln.data_ptr(), N_SEQS, ALN_LEN, pitch, device=True)
-        return eng.within_all(0, B=N_BOOT)
+        return eng.within_job(0, d_aln.data_ptr(), N_SEQS, ALN_LEN, pitch, True, B=N_BOOT)
 
     def step_e2e():
-        eng.load_group_ptr(0, h_aln.data_ptr(), N_SEQS, ALN_LEN, ALN_LEN, device=False)
-        return eng.within_all(0, B=N_BOOT)
+        return eng.within_job(0, h_aln.data_ptr(), N_SEQS, ALN_LEN, ALN_LEN, False, B=N_BOOT)
 
     def barrier():
         if world > 1:
@@ -227,9 +229,13 @@ def run_ours(args):
             ms = float(t.item())
         return ms / steps, eng.profile(reset=True), eng.launches - l0, out
 
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local) as clocks:      # clocks are sampled across both timed regions
         ms_res, prof, launches, (sums, se) = timed(step_resident, args.steps, args.warmup)
-    ms_e2e, prof_e2e, _, _ = timed(step_e2e, max(1, args.steps), max(3, min(args.warmup, 3)))
+        ms_e2e, prof_e2e, _, _ = timed(step_e2e, max(1, args.steps), max(3, min(args.warmup, 3)))
+    prof_all = {}
+    if not args.no_profile:
+        eng.set_option(_abi.OPT_PROFILE, -1)
+        _, prof_all, _, _ = timed(step_resident, args.steps, 1)
 
     # one small gather of the per-product results (the only exchange on this path)
     res = torch.tensor(np.concatenate([sums, se], axis=1), device=dev)
@@ -249,14 +255,16 @@ def run_ours(args):
         alg = {"pack": 4.0 * N_SEQS * codons, "hist": 1.0 * N_SEQS * codons + 264.0 * codons,
                "fused": 3.0 * N_SEQS * codons + 264.0 * codons}   # fused: the CDS bytes read once, histograms written
         kern = {}
-        for k, (ms, calls) in prof.items():
+        merged = dict(prof_all)
+        merged.update({k: v for k, v in prof.items() if v[1]})       # HBM kernels: from the timed pass itself
+        for k, (ms, calls) in merged.items():
             if calls:
                 kern[k] = {"ms_per_launch": ms / calls, "launches_per_step": calls / args.steps, "ms_per_step": ms / args.steps}
                 if k in alg:
                     kern[k]["achieved_gbs"] = alg[k] / (ms / calls * 1e-3) / 1e9   # one launch covers the whole matrix
         hbm_kernels = {k: v for k, v in kern.items() if k in alg}
-        dom = max(hbm_kernels, key=lambda k: hbm_kernels[k]["ms_per_step"])
-        achieved = kern[dom]["achieved_gbs"]
+        dom = max(hbm_kernels, key=lambda k: hbm_kernels[k]["ms_per_step"]) if hbm_kernels else ("fused" if args.route == "fused" else "pack")
+        achieved = kern[dom]["achieved_gbs"] if dom in kern else float("nan")
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
@@ -277,6 +285,8 @@ def run_ours(args):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg[dom]},
             "kernels": kern,
+            "kernel_timing": "CUDA events inside the library on the launch stream: " + "/".join(hbm_kinds)
+                             + " during the timed steps; the other kernels in a separate pass of the same steps",
             "bootstrap": {"value": N_BOOT * len(products) * world / (boot_ms * 1e-3) if boot_ms else None, "unit": "bootstrap reps/s",
                           "note": "B x products per step / (bootstrap + moments kernel time)"},
             "clocks": clocks.summary(),
@@ -294,10 +304,11 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-profile", action="store_true", help="do not bracket kernels with CUDA events (no roofline block)")
     ap.add_argument("--route", default="fused", choices=["fused", "codes"],
                     help="histogram route: fused kernel (default) or K1 pack + K2 hist over a kept code matrix")
     args = ap.parse_args()

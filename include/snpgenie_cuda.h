@@ -102,8 +102,10 @@ int snpg_group_size(const snpg_ctx *ctx, int group, uint64_t *n_seqs);
  * is built straight from the alignment bytes by the fused kernel and no code
  * matrix exists.  Set before loading a group. */
 #define SNPG_OPT_KEEP_CODES 1
-/* SNPG_OPT_PROFILE (default 0): bracket every kernel launch with CUDA events on
- * the launch stream and accumulate per-kernel milliseconds (snpg_get_profile). */
+/* SNPG_OPT_PROFILE (default 0): bit mask over SNPG_K_* kinds (-1 = all).  Launches of a
+ * selected kind are bracketed with CUDA events on the launch stream and their device
+ * time is accumulated (snpg_get_profile).  Each pair of events costs a few
+ * microseconds of stream time, so time whole jobs with a narrow mask. */
 #define SNPG_OPT_PROFILE 2
 int snpg_set_option(snpg_ctx *ctx, int option, int64_t value);
 
@@ -157,6 +159,13 @@ int snpg_windows(snpg_ctx *ctx, const double *stats4, const uint8_t *keep, int64
  * Under a shard (world > 1) this covers the local codon slice only and callers
  * combine slices (see snpg_stats_device / bench.py). */
 int snpg_within_all(snpg_ctx *ctx, int group, int64_t B, double *prod_sums, double *prod_se);
+
+/* Load + snpg_within_all as ONE call with a single synchronisation at the end: the
+ * whole within-group job for a product-level answer (what the within driver's product
+ * table needs).  bases is a host pointer (bases_on_device = 0; must stay valid until
+ * the call returns) or a device pointer (1). */
+int snpg_within_job(snpg_ctx *ctx, int group, const uint8_t *bases, int bases_on_device, uint64_t n_seqs,
+                    uint64_t aln_len, uint64_t row_stride, int64_t B, double *prod_sums, double *prod_se);
 
 /* Device-pointer variants for multi-GPU plumbing (torch.distributed moves the
  * buffers): d_stats4 is a DEVICE buffer [count][4] for this shard's codons. */

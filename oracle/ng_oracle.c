@@ -574,6 +574,17 @@ int64_t orc_windows(const double *stats4, int64_t C, int64_t W, int64_t step, in
     return nwin;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline must still use every host core */
+void orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    extern void omp_set_num_threads(int);
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_max_threads(void)
 {
 #ifdef _OPENMP

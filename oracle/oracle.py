@@ -190,3 +190,13 @@ def windows(stats4: np.ndarray, W: int, step: int, B: int = 0, seed: int = 1):
 
 def max_threads() -> int:
     return int(lib().orc_max_threads())
+
+
+def use_all_cores() -> int:
+    """Pin the OpenMP team to every core this process may run on (ignores OMP_NUM_THREADS)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().orc_set_threads(C.c_int(n))
+    return max_threads()

@@ -51,6 +51,7 @@ struct snpg_ctx {
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_packed[2] = {nullptr, nullptr};
     int rank = 0, world = 1;
     bool keep_codes = true;
+    bool defer_load_sync = false;   // set inside snpg_within_job*: the load's kernels stay queued behind the analysis
     // annotation
     int n_products = 0;
     int64_t aln_len = 0;
@@ -73,7 +74,7 @@ struct snpg_ctx {
     int64_t launches = 0;
     uint32_t call_id = 0;
     // optional per-kernel timing (CUDA events on the launch stream)
-    bool profile = false;
+    uint32_t profile_mask = 0;      // bit k set: bracket launches of kernel kind k with timing events
     bool own_stream = true;
     struct Span { cudaEvent_t e0, e1; int kind; };
     std::vector<Span> spans;        // recorded, not yet resolved
@@ -106,7 +107,7 @@ struct Launch {
     snpg_ctx *ctx; int kind; cudaEvent_t e0 = nullptr;
     Launch(snpg_ctx *c, int k) : ctx(c), kind(k) {
         ctx->launches++;
-        if (ctx->profile) { e0 = take_event(ctx); cudaEventRecord(e0, ctx->stream); }
+        if ((ctx->profile_mask >> kind) & 1u) { e0 = take_event(ctx); cudaEventRecord(e0, ctx->stream); }
     }
     ~Launch() {
         if (e0) { cudaEvent_t e1 = take_event(ctx); cudaEventRecord(e1, ctx->stream); ctx->spans.push_back({e0, e1, kind}); }
@@ -239,7 +240,7 @@ int finish_group(snpg_ctx *ctx, Group &g) {
         }
     }
     CU(ctx, cudaGetLastError());
-    CU(ctx, sync_stream(ctx));
+    if (!ctx->defer_load_sync) CU(ctx, sync_stream(ctx));
     g.loaded = true;
     return SNPG_OK;
 }
@@ -317,7 +318,7 @@ void snpg_destroy(snpg_ctx *ctx) {
 int snpg_set_option(snpg_ctx *ctx, int option, int64_t value) {
     if (!ctx) return SNPG_E_ARG;
     if (option == SNPG_OPT_KEEP_CODES) { ctx->keep_codes = value != 0; return SNPG_OK; }
-    if (option == SNPG_OPT_PROFILE) { ctx->profile = value != 0; return SNPG_OK; }
+    if (option == SNPG_OPT_PROFILE) { ctx->profile_mask = value < 0 ? 0xFFFFFFFFu : (uint32_t)value; return SNPG_OK; }
     return fail(ctx, SNPG_E_ARG, "unknown option %d", option);
 }
 
@@ -845,6 +846,17 @@ int snpg_within_all(snpg_ctx *ctx, int group, int64_t B, double *prod_sums, doub
     if (boot) CU(ctx, cudaMemcpyAsync(prod_se, ctx->s_se.p, sizeof(double) * 6 * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, sync_stream(ctx));
     return SNPG_OK;
+}
+
+int snpg_within_job(snpg_ctx *ctx, int group, const uint8_t *bases, int bases_on_device, uint64_t n_seqs, uint64_t aln_len,
+                    uint64_t row_stride, int64_t B, double *prod_sums, double *prod_se) {
+    if (!ctx) return SNPG_E_ARG;
+    ctx->defer_load_sync = true;     // one synchronisation for the whole job, at the end of snpg_within_all
+    int rc = bases_on_device ? snpg_load_group_device(ctx, group, bases, n_seqs, aln_len, row_stride)
+                             : snpg_load_group(ctx, group, bases, n_seqs, aln_len, row_stride);
+    ctx->defer_load_sync = false;
+    if (rc != SNPG_OK) { sync_stream(ctx); return rc; }
+    return snpg_within_all(ctx, group, B, prod_sums, prod_se);
 }
 
 int64_t snpg_launch_count(const snpg_ctx *ctx) { return ctx ? ctx->launches : 0; }

@@ -672,17 +672,29 @@ k_bootstrap(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, 
             const uint4 u = philox4x32_10(make_uint4(q, (uint32_t)b, (uint32_t)(b >> 32) ^ ((uint32_t)p << 8), stream_id), key);
             const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
             const int nd = q < full_quads ? 4 : (int)(C & 3);
+            uint32_t r[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (j < nd) {
-                    const uint32_t r = __umulhi(uu[j], C + 1);
-                    if (SMEM) {
-                        const double2 a = A[r];
-                        s0 += fabs(a.x); s1 += a.y;
-                        if (__double2hiint(a.x) < 0) { const double2 d = D[r]; s2 += d.x; s3 += d.y; }
-                    } else if (r) {
-                        const double2 a = __ldg(G + 2 * (size_t)(r - 1));
-                        const double2 d = __ldg(G + 2 * (size_t)(r - 1) + 1);
+            for (int j = 0; j < 4; j++) r[j] = j < nd ? __umulhi(uu[j], C + 1) : 0u;     // slot 0 adds nothing
+            if (SMEM) {
+                // all gathers of the quad are issued before any is consumed
+                double2 a[4], d[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) a[j] = A[r[j]];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    d[j] = make_double2(0.0, 0.0);
+                    if (__double2hiint(a[j].x) < 0) d[j] = D[r[j]];
+                }
+                s0 += (fabs(a[0].x) + fabs(a[1].x)) + (fabs(a[2].x) + fabs(a[3].x));
+                s1 += (a[0].y + a[1].y) + (a[2].y + a[3].y);
+                s2 += (d[0].x + d[1].x) + (d[2].x + d[3].x);
+                s3 += (d[0].y + d[1].y) + (d[2].y + d[3].y);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (r[j]) {
+                        const double2 a = __ldg(G + 2 * (size_t)(r[j] - 1));
+                        const double2 d = __ldg(G + 2 * (size_t)(r[j] - 1) + 1);
                         s0 += a.x; s1 += a.y; s2 += d.x; s3 += d.y;
                     }
                 }

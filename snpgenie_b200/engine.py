@@ -76,7 +76,7 @@ class Engine:
         self._ck(_abi.lib.snpg_set_stream(self._ctx, cuda_stream_ptr))
 
     def profile(self, reset: bool = True) -> dict:
-        """{kernel kind: (milliseconds, launches)} accumulated since the last reset (needs OPT_PROFILE)."""
+        """{kernel kind: (milliseconds, launches)} accumulated since the last reset (kinds selected by OPT_PROFILE)."""
         ms = np.zeros(len(_abi.KERNEL_KINDS))
         calls = np.zeros(len(_abi.KERNEL_KINDS), dtype=np.int64)
         self._ck(_abi.lib.snpg_get_profile(self._ctx, _ptr(ms, C.c_double), _ptr(calls, C.c_int64), int(reset)))
@@ -185,6 +185,15 @@ class Engine:
         sums = np.zeros((P, 4))
         se = np.zeros((P, 6)) if B >= 2 else None
         self._ck(_abi.lib.snpg_within_all(self._ctx, group, B, _ptr(sums, C.c_double), _ptr(se, C.c_double)))
+        return sums, se
+
+    def within_job(self, group: int, ptr: int, n_seqs: int, aln_len: int, row_stride: int, device: bool, B: int = 0):
+        """Load + within_all in one ABI call (one synchronisation): per-product sums [P,4], SEs [P,6]."""
+        P = len(self.products)
+        sums = np.zeros((P, 4))
+        se = np.zeros((P, 6)) if B >= 2 else None
+        self._ck(_abi.lib.snpg_within_job(self._ctx, group, ptr, int(device), n_seqs, aln_len, row_stride, B,
+                                          _ptr(sums, C.c_double), _ptr(se, C.c_double)))
         return sums, se
 
     # -- device-pointer plumbing for multi-GPU ------------------------------------
