@@ -102,6 +102,10 @@ int snpg_group_size(const snpg_ctx *ctx, int group, uint64_t *n_seqs);
  * is built straight from the alignment bytes by the fused kernel and no code
  * matrix exists.  Set before loading a group. */
 #define SNPG_OPT_KEEP_CODES 1
+/* SNPG_OPT_SITE_COUNTS (default 0): while a group is loaded also count A, C, G, T per
+ * alignment column (snpg_get_site_counts) -- the whole row is then staged, not only the
+ * CDS columns.  Set before snpg_set_products. */
+#define SNPG_OPT_SITE_COUNTS 3
 /* SNPG_OPT_PROFILE (default 0): bit mask over SNPG_K_* kinds (-1 = all).  Launches of a
  * selected kind are bracketed with CUDA events on the launch stream and their device
  * time is accumulated (snpg_get_profile).  Each pair of events costs a few
@@ -117,6 +121,10 @@ int snpg_set_option(snpg_ctx *ctx, int option, int64_t value);
  * world > 1 (C = shard slice of the product). */
 int snpg_get_codon_indices(snpg_ctx *ctx, int group, int product, uint8_t *out);
 int snpg_get_hist(snpg_ctx *ctx, int group, int product, uint32_t *out, uint8_t *other_distinct);
+
+/* Per-site nucleotide counts out [aln_len][4] = A, C, G, T after uc and U->T; everything else is
+ * not counted (replaces the site pass wg:1203-1237; pi and majority follow from the counts). */
+int snpg_get_site_counts(snpg_ctx *ctx, int group, uint32_t *out);
 
 /* ---- per-codon engine ------------------------------------------------------
  * Replaces wg:586-751 (within) and bg:573-955 (between): per codon the
@@ -194,8 +202,9 @@ int snpg_set_stream(snpg_ctx *ctx, void *cuda_stream);
 #define SNPG_K_WINDOW 6
 #define SNPG_K_OTHER 7
 #define SNPG_K_FUSED 8   /* pack + histogram in one pass (no code matrix kept) */
-#define SNPG_N_KERNEL_KINDS 9
-int snpg_get_profile(snpg_ctx *ctx, double *ms /*[9]*/, int64_t *calls /*[9]*/, int reset);
+#define SNPG_K_SITES 9   /* per-site A/C/G/T counts */
+#define SNPG_N_KERNEL_KINDS 10
+int snpg_get_profile(snpg_ctx *ctx, double *ms /*[10]*/, int64_t *calls /*[10]*/, int reset);
 
 /* Kernel launches issued by this ctx since creation (bench.py's gpu_launches). */
 int64_t snpg_launch_count(const snpg_ctx *ctx);

@@ -200,3 +200,12 @@ def use_all_cores() -> int:
         n = os.cpu_count() or 1
     lib().orc_set_threads(C.c_int(n))
     return max_threads()
+
+
+def site_counts(aln: np.ndarray) -> np.ndarray:
+    """[L,4] counts of A,C,G,T per alignment column after uc and U->T (snpgenie_within_group.pl:1222-1237)."""
+    a = np.asarray(aln, dtype=np.uint8).copy()
+    lower = (a >= ord("a")) & (a <= ord("z"))
+    a[lower] -= 32
+    a[a == ord("U")] = ord("T")
+    return np.stack([(a == ord(ch)).sum(axis=0) for ch in "ACGT"], axis=1).astype(np.uint32)

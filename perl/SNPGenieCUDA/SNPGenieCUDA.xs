@@ -134,6 +134,23 @@ hist(h, group, product)
     PUSHs(hs);
     PUSHs(od);
 
+SV *
+site_counts(h, group, aln_len)
+    IV h
+    int group
+    UV aln_len
+  CODE:
+    snpg_ctx *ctx = ctx_of(aTHX_ h);
+    SV *out = newSV(16 * (STRLEN)aln_len + 1);
+    SvPOK_only(out);
+    SvCUR_set(out, 16 * (STRLEN)aln_len);
+    *SvEND(out) = '\0';
+    int rc = snpg_get_site_counts(ctx, group, (uint32_t *)SvPVX(out));
+    if (rc != SNPG_OK) { SvREFCNT_dec(out); check(aTHX_ ctx, rc, "site_counts"); }
+    RETVAL = out;
+  OUTPUT:
+    RETVAL
+
 void
 within(h, group, product)
     IV h

@@ -9,7 +9,7 @@ package SNPGenieHost;
 use strict;
 use warnings;
 use Exporter 'import';
-our @EXPORT_OK = qw(read_gtf read_fasta pack_products ratio stars codon_of other_alleles fmt_pairs);
+our @EXPORT_OK = qw(read_gtf read_fasta pack_products ratio stars codon_of other_alleles fmt_pairs amino_acid variant_line site_lines);
 
 my @NT = qw(A C G T);
 sub codon_of { my ($c) = @_; return $NT[$c >> 4] . $NT[($c >> 2) & 3] . $NT[$c & 3]; }
@@ -143,6 +143,45 @@ sub fmt_pairs {
         for my $j ($i + 1 .. $#$alleles) { $out .= "($alleles->[$i][0]-$alleles->[$j][0])"; }
     }
     return $out;
+}
+
+# get_amino_acid (wg:1400-1516): standard code, '?' for anything that is not a pure ACGT codon
+my @AA = split //, 'KNKNTTTTRSRSIIMIQHQHPPPPRRRRLLLLEDEDAAAAGGGGVVVV*Y*YSSSS*CWCLFLF';
+my %AA_OF = map { codon_of($_) => $AA[$_] } 0 .. 63;
+sub amino_acid { my ($c) = @_; return exists $AA_OF{$c} ? $AA_OF{$c} : '?'; }
+
+# one within_group_variant_results.txt row (wg:1061-1167) from a codon's alleles [[string, count], ...];
+# counts are the true integer counts (the reference's are distorted by gaps, quirk q1)
+sub variant_line {
+    my ($file, $product, $codon_num, $alleles) = @_;
+    my @al = sort { $a->[0] cmp $b->[0] } @$alleles;
+    my ($consensus, $best, $total) = ('', 0, 0);
+    for my $a (@al) { $total += $a->[1]; if ($a->[1] > $best) { $best = $a->[1]; $consensus = $a->[0]; } }
+    my @aas = map { amino_acid($_->[0]) } @al;
+    my ($syn, $non) = (0, 0);
+    for my $i (0 .. $#aas) { for my $j ($i + 1 .. $#aas) { if ($aas[$i] eq $aas[$j]) { $syn++ } else { $non++ } } }
+    my $type = ($non > 0 && $syn > 0) ? 'Ambiguous' : $non > 0 ? 'Nonsynonymous' : 'Synonymous';
+    return join("\t", $file, $product, $codon_num, $consensus, scalar(@al), join(',', map { $_->[0] } @al), join(',', @aas), $type,
+                join(',', map { $_->[1] } @al), $total, join(',', map { sprintf('%.3f', $_->[1] / $total) } @al), $best,
+                $total - $best, $total) . "\n";
+}
+
+# within_group_site_results.txt rows (wg:1242-1293) from packed [L][4] u32 counts
+sub site_lines {
+    my ($file, $counts_packed, $fh) = @_;
+    my @c = unpack('L*', $counts_packed);
+    for my $pos (0 .. @c / 4 - 1) {
+        my ($A, $C, $G, $T) = @c[4 * $pos .. 4 * $pos + 3];
+        my ($maj, $maj_count) = ('A', $A);
+        ($maj, $maj_count) = ('C', $C) if $C > $maj_count;
+        ($maj, $maj_count) = ('G', $G) if $G > $maj_count;
+        ($maj, $maj_count) = ('T', $T) if $T > $maj_count;
+        my $pw = $A * $C + $A * $G + $A * $T + $C * $G + $C * $T + $G * $T;
+        my $cov = $A + $C + $G + $T;
+        my $comps = ($cov**2 - $cov) / 2;
+        my $pi = $comps > 0 ? $pw / $comps : 'NA';
+        print $fh join("\t", $file, $pos + 1, $maj, $maj_count, $pi, $cov, $A, $C, $G, $T) . "\n";
+    }
 }
 
 1;

@@ -15,7 +15,7 @@ use FindBin;
 use lib "$FindBin::Bin/lib", "$FindBin::Bin/SNPGenieCUDA/lib";
 use Getopt::Long;
 use SNPGenieCUDA;
-use SNPGenieHost qw(read_gtf read_fasta pack_products ratio stars codon_of other_alleles fmt_pairs);
+use SNPGenieHost qw(read_gtf read_fasta pack_products ratio stars codon_of other_alleles fmt_pairs variant_line site_lines);
 
 STDOUT->autoflush(1);
 my $time1 = time;
@@ -50,12 +50,17 @@ print "\nRecording coding sequence data for $fasta_file_name...\n";
 my ($seqs, $n_seqs, $aln_len) = read_fasta($fasta_file_name);
 
 my $ctx = SNPGenieCUDA::create($device, $seed);
+SNPGenieCUDA::set_option($ctx, SNPGenieCUDA::OPT_KEEP_CODES, 0);        # histograms straight from the alignment bytes
+SNPGenieCUDA::set_option($ctx, SNPGenieCUDA::OPT_SITE_COUNTS, 1);       # per-site A/C/G/T in the same load
 SNPGenieCUDA::set_products($ctx, scalar @$products, pack_products($products), $aln_len);
 SNPGenieCUDA::load_group($ctx, 0, $seqs, $n_seqs, $aln_len);
 
 # headers, append mode like the reference (wg:337-361)
 open(my $codon_fh, '>>', 'within_group_codon_results.txt') or die "cannot write codon results: $!";
 print $codon_fh "file\tproduct\tcodon\tvariability\tcomparisons\tN_sites\tS_sites\tN_diffs\tS_diffs\n";
+open(my $var_fh, '>>', 'within_group_variant_results.txt') or die "cannot write variant results: $!";
+print $var_fh "file\tproduct_name\tcodon_num\tconsensus_codon\tnum_alleles\tcodons\tamino_acids\tvariant_type\tcodon_counts\t"
+            . "count_total\tcodon_freqs\tmax_codon_count\tmin_codon_count\tnum_defined_seqs\n";
 open(my $prod_fh, '>>', 'within_group_product_results.txt') or die "cannot write product results: $!";
 print $prod_fh "file\tproduct\tN_sites\tS_sites\tN_diffs\tS_diffs\tdN\tdS\t";
 print $prod_fh "SE_dN\tSE_dS\t" if $num_bootstraps > 1;
@@ -84,6 +89,7 @@ for my $pi (0 .. $#$products) {
                 push @alleles, map { [ $_, $others->{$_} ] } sort keys %$others;
             }
             print $codon_fh "polymorphic\t" . fmt_pairs(\@alleles) . "\t$Ns\t$Ss\t$Nd\t$Sd\n";
+            print $var_fh variant_line($fasta_file_name, $name, $c + 1, \@alleles);
             # product sums accumulate codon by codon like wg:690-693
             $sum_Nd += $Nd; $sum_Sd += $Sd; $sum_Ns += $Ns; $sum_Ss += $Ss;
         } else {
@@ -140,5 +146,11 @@ for my $pi (0 .. $#$products) {
 }
 close $codon_fh;
 close $prod_fh;
+close $var_fh;
+# per-site nucleotide counts and pi (wg:1203-1295)
+open(my $site_fh, '>>', 'within_group_site_results.txt') or die "cannot write site results: $!";
+print $site_fh "file\tsite\tmaj_nt\tmaj_nt_count\tpi\tcoverage\tA\tC\tG\tT\n";
+site_lines($fasta_file_name, SNPGenieCUDA::site_counts($ctx, 0, $aln_len), $site_fh);
+close $site_fh;
 SNPGenieCUDA::destroy($ctx);
 printf "\nSNPGenie completed in %d seconds.\n\n", time - $time1;

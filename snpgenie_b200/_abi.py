@@ -13,8 +13,8 @@ LIB_PATH = os.path.join(_HERE, "libsnpgenie_cuda.so")
 
 OK, E_ARG, E_STATE, E_INPUT, E_CUDA, E_NOMEM = 0, -1, -2, -3, -4, -5
 CODE_UNDEF, CODE_OTHER, HIST_BINS = 64, 65, 66
-OPT_KEEP_CODES, OPT_PROFILE = 1, 2
-KERNEL_KINDS = ("pack", "hist", "stats", "sums", "bootstrap", "moments", "window", "other", "fused")
+OPT_KEEP_CODES, OPT_PROFILE, OPT_SITE_COUNTS = 1, 2, 3
+KERNEL_KINDS = ("pack", "hist", "stats", "sums", "bootstrap", "moments", "window", "other", "fused", "sites")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -46,6 +46,7 @@ SIGNATURES = {
     "snpg_group_size": (C.c_int, [_ctx, C.c_int, _u64p]),
     "snpg_set_option": (C.c_int, [_ctx, C.c_int, C.c_int64]),
     "snpg_get_codon_indices": (C.c_int, [_ctx, C.c_int, C.c_int, _u8p]),
+    "snpg_get_site_counts": (C.c_int, [_ctx, C.c_int, _u32p]),
     "snpg_get_hist": (C.c_int, [_ctx, C.c_int, C.c_int, _u32p, _u8p]),
     "snpg_within": (C.c_int, [_ctx, C.c_int, C.c_int, _u8p, _u32p, _u64p, _f64p, _u8p]),
     "snpg_between": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, _u8p, _u32p, _u32p, _u64p, _f64p, _u8p]),

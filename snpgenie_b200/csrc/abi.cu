@@ -38,6 +38,8 @@ struct Group {
     uint64_t n = 0;
     int64_t n_pad = 0;
     DevBuf codes, hist, other;   // other: [2][count] min then max
+    DevBuf sites;                // [aln_len][5] per-site A,C,G,T,other (SNPG_OPT_SITE_COUNTS)
+    bool has_sites = false;
     bool has_codes = false;
 };
 
@@ -51,6 +53,7 @@ struct snpg_ctx {
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_packed[2] = {nullptr, nullptr};
     int rank = 0, world = 1;
     bool keep_codes = true;
+    bool site_counts = false;       // also count A/C/G/T per alignment column while loading (whole rows are staged)
     bool defer_load_sync = false;   // set inside snpg_within_job*: the load's kernels stay queued behind the analysis
     // annotation
     int n_products = 0;
@@ -179,6 +182,11 @@ int prepare_group(snpg_ctx *ctx, Group &g, uint64_t n_seqs) {
     CU(ctx, cudaMemsetAsync(g.other.p, 0xFF, sizeof(uint32_t) * (size_t)cnt, ctx->stream));
     CU(ctx, cudaMemsetAsync(g.other.as<uint32_t>() + cnt, 0, sizeof(uint32_t) * (size_t)cnt, ctx->stream));
     g.has_codes = ctx->keep_codes;
+    g.has_sites = ctx->site_counts;
+    if (ctx->site_counts) {
+        CU(ctx, g.sites.ensure(sizeof(uint32_t) * 5 * (size_t)ctx->aln_len));
+        CU(ctx, cudaMemsetAsync(g.sites.p, 0, sizeof(uint32_t) * 5 * (size_t)ctx->aln_len, ctx->stream));
+    }
     if (!ctx->keep_codes && ctx->n_irr) {
         CU(ctx, ctx->t_codes.ensure((size_t)(ctx->n_irr * g.n_pad)));
         CU(ctx, ctx->t_hist.ensure(sizeof(uint32_t) * (size_t)(ctx->n_irr * kHistBins)));
@@ -194,14 +202,19 @@ int prepare_group(snpg_ctx *ctx, Group &g, uint64_t n_seqs) {
 // (row r0, column base_al); row_bytes = readable bytes per row from there.
 int pack_block(snpg_ctx *ctx, Group &g, const uint8_t *d_block, int64_t pitch, int64_t rows, int64_t r0, int64_t row_bytes) {
     uint32_t *omin = g.other.as<uint32_t>(), *omax = g.other.as<uint32_t>() + ctx->shard_count;
+    if (r0 == 0 && (!ctx->keep_codes || ctx->site_counts))   // the group's first sequence is the consensus every row is compared with
+        CU(ctx, cudaMemcpyAsync(ctx->d_cons.p, d_block, (size_t)std::min<int64_t>(row_bytes, ctx->n_spans * 16 + 16),
+                                cudaMemcpyDeviceToDevice, ctx->stream));
+    if (ctx->site_counts) {
+        Launch l(ctx, SNPG_K_SITES);
+        launch_site_hist(d_block, pitch, rows, ctx->d_cons.as<uint8_t>(), ctx->aln_len, g.sites.as<uint32_t>(), ctx->stream);
+    }
     if (ctx->keep_codes) {
         Launch l(ctx, SNPG_K_PACK);
         launch_pack(d_block + (ctx->col_lo - ctx->base_al), pitch, rows, r0, ctx->d_map.as<CodonMap>(), ctx->shard_count,
                     g.codes.as<uint8_t>(), g.n_pad, omin, omax, ctx->stream);
     } else {
-        if (r0 == 0) {   // the group's first sequence is the consensus every row is compared with
-            CU(ctx, cudaMemcpyAsync(ctx->d_cons.p, d_block, (size_t)std::min<int64_t>(row_bytes, ctx->n_spans * 16 + 16),
-                                    cudaMemcpyDeviceToDevice, ctx->stream));
+        if (r0 == 0) {
             Launch l(ctx, SNPG_K_OTHER);
             launch_cons_codes(ctx->d_cons.as<uint8_t>(), ctx->col_lo - ctx->base_al, ctx->d_map.as<CodonMap>(), ctx->shard_count,
                               ctx->d_cons_code.as<uint8_t>(), ctx->d_cons_key.as<uint32_t>(), ctx->stream);
@@ -223,6 +236,10 @@ int pack_block(snpg_ctx *ctx, Group &g, const uint8_t *d_block, int64_t pitch, i
 
 int finish_group(snpg_ctx *ctx, Group &g) {
     uint32_t *omin = g.other.as<uint32_t>(), *omax = g.other.as<uint32_t>() + ctx->shard_count;
+    if (ctx->site_counts) {
+        Launch l(ctx, SNPG_K_SITES);
+        launch_site_fixup(ctx->d_cons.as<uint8_t>(), ctx->aln_len, (uint32_t)g.n, g.sites.as<uint32_t>(), ctx->stream);
+    }
     if (ctx->keep_codes) {
         Launch l(ctx, SNPG_K_HIST);
         launch_hist(g.codes.as<uint8_t>(), g.n_pad, ctx->shard_count, g.hist.as<uint32_t>(), ctx->stream);
@@ -297,7 +314,7 @@ void snpg_destroy(snpg_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
-    for (auto &g : ctx->groups) { g.codes.release(); g.hist.release(); g.other.release(); }
+    for (auto &g : ctx->groups) { g.codes.release(); g.hist.release(); g.other.release(); g.sites.release(); }
     DevBuf *bufs[] = {&ctx->d_map, &ctx->d_local_ofs, &ctx->d_full_ofs, &ctx->d_tables, &ctx->staging[0], &ctx->staging[1],
                       &ctx->d_runs, &ctx->d_regular, &ctx->d_irr_map, &ctx->d_irr_idx, &ctx->d_cons, &ctx->d_cons_code, &ctx->d_cons_key, &ctx->t_codes, &ctx->t_hist,
                       &ctx->t_other,
@@ -318,6 +335,11 @@ void snpg_destroy(snpg_ctx *ctx) {
 int snpg_set_option(snpg_ctx *ctx, int option, int64_t value) {
     if (!ctx) return SNPG_E_ARG;
     if (option == SNPG_OPT_KEEP_CODES) { ctx->keep_codes = value != 0; return SNPG_OK; }
+    if (option == SNPG_OPT_SITE_COUNTS) {
+        NEED(ctx, ctx->n_products == 0, SNPG_E_STATE, "SNPG_OPT_SITE_COUNTS must be set before snpg_set_products");
+        ctx->site_counts = value != 0;
+        return SNPG_OK;
+    }
     if (option == SNPG_OPT_PROFILE) { ctx->profile_mask = value < 0 ? 0xFFFFFFFFu : (uint32_t)value; return SNPG_OK; }
     return fail(ctx, SNPG_E_ARG, "unknown option %d", option);
 }
@@ -385,6 +407,7 @@ int snpg_set_products(snpg_ctx *ctx, int n_products, const int64_t *seg_ofs, con
         hi = std::max<int64_t>(hi, std::max(m.p0, std::max(m.p1, m.p2)) + 1);
     }
     if (ctx->shard_count == 0) { lo = 0; hi = 0; }
+    if (ctx->site_counts) { lo = 0; hi = aln_len; }     // every column is read: stage whole rows
     ctx->col_lo = lo;
     ctx->col_hi = hi;
     std::vector<CodonMap> local(map_all.begin() + ctx->shard_first, map_all.begin() + ctx->shard_first + ctx->shard_count);
@@ -556,6 +579,8 @@ int snpg_load_group_device(snpg_ctx *ctx, int group, const uint8_t *d_bases, uin
     // pitch that covers the last span; anything else keeps the code matrix path.
     const bool fused_ok = ((uintptr_t)d_bases % 16 == 0) && (row_stride % 16 == 0) &&
                           ((int64_t)row_stride >= ctx->base_al + ctx->n_spans * 16 + 4);
+    NEED(ctx, !ctx->site_counts || fused_ok, SNPG_E_ARG,
+         "site counts from a device buffer need a 16-byte aligned base and a row pitch that is a multiple of 16 and covers the last 16-byte span");
     const bool saved_keep = ctx->keep_codes;
     if (!saved_keep && !fused_ok) {
         ctx->keep_codes = true;                                    // fall back to K1+K2 for this load
@@ -577,8 +602,8 @@ int snpg_drop_group(snpg_ctx *ctx, int group) {
     if (!ctx || group < 0 || group >= SNPG_MAX_GROUPS) return SNPG_E_ARG;
     if (int rc = bind(ctx)) return rc;
     Group &g = ctx->groups[group];
-    g.codes.release(); g.hist.release(); g.other.release();
-    g.loaded = false; g.has_codes = false;
+    g.codes.release(); g.hist.release(); g.other.release(); g.sites.release();
+    g.loaded = false; g.has_codes = false; g.has_sites = false;
     return SNPG_OK;
 }
 
@@ -628,6 +653,21 @@ int snpg_get_hist(snpg_ctx *ctx, int group, int product, uint32_t *out, uint8_t 
     CU(ctx, sync_stream(ctx));
     if (other_distinct)
         for (int64_t c = 0; c < C; c++) other_distinct[c] = (lo[(size_t)c] != kOtherNone && lo[(size_t)c] != hi[(size_t)c]) ? 1 : 0;
+    return SNPG_OK;
+}
+
+int snpg_get_site_counts(snpg_ctx *ctx, int group, uint32_t *out) {
+    if (!ctx || !out) return SNPG_E_ARG;
+    if (int rc = check_group(ctx, group)) return rc;
+    if (int rc = bind(ctx)) return rc;
+    Group &g = ctx->groups[group];
+    NEED(ctx, g.has_sites, SNPG_E_STATE, "site counts were not requested (SNPG_OPT_SITE_COUNTS) when the group was loaded");
+    const int64_t L = ctx->aln_len;
+    std::vector<uint32_t> tmp((size_t)L * 5);
+    CU(ctx, cudaMemcpyAsync(tmp.data(), g.sites.p, sizeof(uint32_t) * tmp.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, sync_stream(ctx));
+    for (int64_t c = 0; c < L; c++)
+        for (int k = 0; k < 4; k++) out[4 * c + k] = tmp[(size_t)(5 * c + k)];
     return SNPG_OK;
 }
 

@@ -402,6 +402,72 @@ __global__ void k_scatter_irregular(const uint32_t *__restrict__ tmp_hist, const
     if (b == 0) { other_min[c] = tmp_min[k]; other_max[c] = tmp_max[k]; }
 }
 
+// ---------------------------------------------------------------------------
+// Per-site nucleotide counts (the "next" row f1: within_group_site_results.txt,
+// snpgenie_within_group.pl:1203-1295).  For every alignment column the number of
+// A, C, G, T after the reference's normalisation (uc, U->T; anything else is not
+// counted).  Same plan as the fused histogram: a thread owns a 16-byte column span
+// and walks the rows; rows equal to the consensus row cost one compare, differing
+// bytes are classified and RED-added into sites[col][class] (class 4 = not ACGT),
+// and k_site_fixup credits the consensus residue with (rows - recorded).
+// Algorithmic traffic: 1 byte per (sequence, site) read + 20 B per site written.
+// ---------------------------------------------------------------------------
+constexpr int kSiteWarps = 8;
+constexpr int kSiteRowsPerWarp = 32;
+
+__global__ void __launch_bounds__(kSiteWarps * 32)
+k_site_hist(const uint8_t *__restrict__ aln, int64_t pitch, int64_t n_rows, const uint8_t *__restrict__ cons, int64_t n_spans,
+            int64_t n_cols, uint32_t *__restrict__ sites)
+{
+    __shared__ uint8_t lut[256];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    {
+        const uint8_t k = class_of(norm_char((uint8_t)t, 0));
+        lut[t] = k < 4 ? k : 4;
+    }
+    __syncthreads();
+    const int64_t span = (int64_t)blockIdx.x * 32 + lane;
+    if (span >= n_spans) return;
+    const int64_t row_begin = ((int64_t)blockIdx.y * kSiteWarps + warp) * kSiteRowsPerWarp;
+    const int n_my = (int)max((int64_t)0, min((int64_t)kSiteRowsPerWarp, n_rows - row_begin));
+    const uint4 c = *reinterpret_cast<const uint4 *>(cons + span * 16);
+    const uint32_t cw[4] = {c.x, c.y, c.z, c.w};
+    const uint8_t *p = aln + span * 16 + row_begin * pitch;
+    const int64_t col0 = span * 16;
+    for (int i = 0; i < n_my; i += 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) v[u] = ld_stream_v4(reinterpret_cast<const uint4 *>(p + (size_t)(i + u < n_my ? i + u : i) * pitch));
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (i + u >= n_my) break;
+            const uint32_t vw[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                uint32_t d = vw[w] ^ cw[w];
+                if (d == 0) continue;
+                uint32_t m = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;   // bit 7 of every differing byte
+                while (m) {
+                    const int bit = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int64_t col = col0 + 4 * w + (bit >> 3);
+                    if (col < n_cols) atomicAdd(&sites[col * 5 + lut[(vw[w] >> (bit - 7)) & 0xFF]], 1u);
+                }
+            }
+        }
+    }
+}
+
+__global__ void k_site_fixup(const uint8_t *__restrict__ cons, int64_t n_cols, uint32_t n_rows, uint32_t *__restrict__ sites)
+{
+    const int64_t col = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= n_cols) return;
+    uint32_t *s = sites + col * 5;
+    const uint32_t seen = s[0] + s[1] + s[2] + s[3] + s[4];
+    const uint8_t k = class_of(norm_char(cons[col], 0));
+    s[k < 4 ? k : 4] += n_rows - seen;
+}
+
 // transposed codes -> sequence-major block [n][C] for product columns [c0, c0+C)
 __global__ void k_untranspose(const uint8_t *__restrict__ codes, int64_t n_pad, int64_t n, int64_t c0, int64_t C,
                               uint8_t *__restrict__ out)
@@ -860,6 +926,22 @@ void launch_scatter_irregular(const uint32_t *d_tmp_hist, const uint32_t *d_tmp_
     if (n_irr <= 0) return;
     k_scatter_irregular<<<(unsigned)((n_irr * kHistBins + 255) / 256), 256, 0, stream>>>(d_tmp_hist, d_tmp_min, d_tmp_max, d_idx,
                                                                                           n_irr, d_hist, d_other_min, d_other_max);
+}
+
+void launch_site_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, const uint8_t *d_cons, int64_t n_cols, uint32_t *d_sites,
+                      cudaStream_t stream)
+{
+    if (n_cols <= 0 || n_rows <= 0) return;
+    const int64_t n_spans = (n_cols + 15) / 16;
+    const int64_t rows_per_block = (int64_t)kSiteWarps * kSiteRowsPerWarp;
+    dim3 grid((unsigned)((n_spans + 31) / 32), (unsigned)((n_rows + rows_per_block - 1) / rows_per_block));
+    k_site_hist<<<grid, kSiteWarps * 32, 0, stream>>>(d_aln, pitch, n_rows, d_cons, n_spans, n_cols, d_sites);
+}
+
+void launch_site_fixup(const uint8_t *d_cons, int64_t n_cols, uint32_t n_rows, uint32_t *d_sites, cudaStream_t stream)
+{
+    if (n_cols <= 0) return;
+    k_site_fixup<<<(unsigned)((n_cols + 127) / 128), 128, 0, stream>>>(d_cons, n_cols, n_rows, d_sites);
 }
 
 void launch_untranspose(const uint8_t *d_codes, int64_t n_pad, int64_t n, int64_t c0, int64_t C, uint8_t *d_out,

@@ -64,6 +64,13 @@ void launch_scatter_irregular(const uint32_t *d_tmp_hist, const uint32_t *d_tmp_
                               const int32_t *d_idx, int64_t n_irr, uint32_t *d_hist, uint32_t *d_other_min,
                               uint32_t *d_other_max, cudaStream_t stream);
 
+// Per-site A/C/G/T counts: sites[col][5] (A, C, G, T, other-but-recorded), zeroed before the
+// first row block; d_aln points at column 0 (16-byte aligned, pitch covers 16*ceil(n_cols/16));
+// d_cons = the group's first row.  launch_site_fixup once after the last block.
+void launch_site_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, const uint8_t *d_cons, int64_t n_cols, uint32_t *d_sites,
+                      cudaStream_t stream);
+void launch_site_fixup(const uint8_t *d_cons, int64_t n_cols, uint32_t n_rows, uint32_t *d_sites, cudaStream_t stream);
+
 // transposed codes -> sequence-major [n][C] (test hook)
 void launch_untranspose(const uint8_t *d_codes, int64_t n_pad, int64_t n, int64_t c0, int64_t C, uint8_t *d_out,
                         cudaStream_t stream);

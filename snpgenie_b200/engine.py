@@ -135,6 +135,12 @@ class Engine:
         self._ck(_abi.lib.snpg_get_hist(self._ctx, group, product, _ptr(h, C.c_uint32), _ptr(od, C.c_uint8)))
         return h, od
 
+    def site_counts(self, group: int, aln_len: int) -> np.ndarray:
+        """[aln_len, 4] counts of A, C, G, T per alignment column (needs OPT_SITE_COUNTS before set_products)."""
+        out = np.zeros((aln_len, 4), dtype=np.uint32)
+        self._ck(_abi.lib.snpg_get_site_counts(self._ctx, group, _ptr(out, C.c_uint32)))
+        return out
+
     # -- per-codon engine -------------------------------------------------------
     def within(self, group: int, product: int) -> dict:
         nc = self.local_codons(product)

@@ -496,3 +496,101 @@ def test_codon_range_shards_reassemble(world, keep):
     for i in range(len(products)):
         assert np.array_equal(np.concatenate(got_hist[i]), ref_hist[i])
         assert np.array_equal(np.concatenate(got_stats[i]), ref_stats[i])
+
+
+# ----------------------------------------------------------------- "next" rows f1: site and variant tables
+
+@pytest.mark.parametrize("keep", [1, 0])
+@pytest.mark.parametrize("case", ["w_cfg1", "w_gaps", "w_heavy"])
+def test_site_counts_match_reference_site_table(case, keep):
+    from snpgenie_b200 import _abi, report
+    from snpgenie_b200.engine import Engine
+    d, aln, _, _ = refio.within_case(case)
+    products = hostio.read_gtf_products(os.path.join(d, "cds.gtf"))
+    with Engine(device=0) as e:
+        e.set_option(_abi.OPT_KEEP_CODES, keep)
+        e.set_option(_abi.OPT_SITE_COUNTS, 1)
+        e.set_products(products, aln.shape[1])
+        e.load_group(0, aln)
+        counts = e.site_counts(0, aln.shape[1])
+        for i, p in enumerate(products):                       # the codon path is unaffected by the wider staging
+            assert (e.hist(0, i)[0] == orc.hist(_oracle_product(aln, p)[1])).all()
+    assert np.array_equal(counts, orc.site_counts(aln))
+    tab = report.site_table(counts)
+    _, rows = refio.read_tsv(os.path.join(d, "within_group_site_results.txt"))
+    assert len(rows) == aln.shape[1]
+    for k, r in enumerate(rows):
+        assert [int(r[x]) for x in "ACGT"] == list(counts[k])
+        assert r["maj_nt"] == tab["maj_nt"][k] and int(r["maj_nt_count"]) == tab["maj_nt_count"][k]
+        assert int(r["coverage"]) == tab["coverage"][k]
+        if r["pi"] == "NA":
+            assert np.isnan(tab["pi"][k])
+        else:
+            assert close(tab["pi"][k], float(r["pi"]))
+
+
+def test_site_counts_large_random_and_device_input():
+    import torch
+    from snpgenie_b200 import _abi
+    from snpgenie_b200.engine import Engine
+    rng = np.random.default_rng(8)
+    n, L = 3001, 1003
+    aln = np.frombuffer(b"ACGTacgtUuNn-RY", dtype=np.uint8)[rng.integers(0, 15, size=(n, L))]
+    aln[:, 100:400] = aln[0, 100:400]                          # long conserved stretch
+    products = [hostio.Product("p", 1, [4], [1002])]
+    pitch = 1008
+    dbuf = torch.zeros((n, pitch), dtype=torch.uint8, device="cuda:0")
+    dbuf[:, :L] = torch.from_numpy(aln).cuda()
+    with Engine(device=0) as e:
+        e.set_option(_abi.OPT_KEEP_CODES, 0)
+        e.set_option(_abi.OPT_SITE_COUNTS, 1)
+        e.set_products(products, L)
+        e.load_group(0, aln)
+        e.load_group_ptr(1, dbuf.data_ptr(), n, L, pitch, device=True)
+        want = orc.site_counts(aln)
+        assert np.array_equal(e.site_counts(0, L), want)
+        assert np.array_equal(e.site_counts(1, L), want)
+        assert (e.hist(0, 0)[0] == e.hist(1, 0)[0]).all()
+    with Engine(device=0) as e2:                                # not requested -> loud error
+        e2.set_products(products, L)
+        e2.load_group(0, aln)
+        with pytest.raises(_abi.SnpgError) as err:
+            e2.site_counts(0, L)
+        assert err.value.code == _abi.E_STATE
+
+
+def test_variant_table_from_histograms(eng):
+    from snpgenie_b200 import report
+    for case, exact_counts in (("w_cfg1", True), ("w_gaps", False)):
+        d, aln, codon_rows, _ = refio.within_case(case)
+        products = hostio.read_gtf_products(os.path.join(d, "cds.gtf"))
+        _, vrows = refio.read_tsv(os.path.join(d, "within_group_variant_results.txt"))
+        gold = {(r["product_name"], int(r["codon_num"])): r for r in vrows}
+        eng.set_products(products, aln.shape[1])
+        eng.load_group(0, aln)
+        n_rows = 0
+        for i, p in enumerate(products):
+            h, _ = eng.hist(0, i)
+            res = eng.within(0, i)
+            raw, codes = _oracle_product(aln, p)
+            for c in np.flatnonzero(res["poly"]):
+                others = {}
+                for s in range(raw.shape[0]):
+                    if codes[s, c] == orc.OTHER:
+                        k = bytes(raw[s, c]).decode()
+                        others[k] = others.get(k, 0) + 1
+                row = report.variant_row(h[c], others)
+                g = gold[(p.name, c + 1)]
+                assert g["codons"].split(",") == row["codons"]
+                assert g["amino_acids"].split(",") == row["amino_acids"]
+                assert g["variant_type"] == row["variant_type"] and int(g["num_alleles"]) == row["num_alleles"]
+                if exact_counts:      # without gaps the reference's counts are the true counts
+                    assert [int(x) for x in g["codon_counts"].split(",")] == row["codon_counts"]
+                    assert g["consensus_codon"] == row["consensus_codon"]
+                    assert int(g["max_codon_count"]) == row["max_codon_count"] and int(g["min_codon_count"]) == row["min_codon_count"]
+                    assert int(g["num_defined_seqs"]) == row["num_defined_seqs"]
+                    assert g["codon_freqs"] == ",".join("%.3f" % f for f in row["codon_freqs"])
+                else:                 # quirk q1: the reference's counts are scaled by (n_true-1)/(n_truncated-1); ours are integers
+                    assert row["num_defined_seqs"] == int(res["n_defined"][c])
+                n_rows += 1
+        assert n_rows == len(gold)

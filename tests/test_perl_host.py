@@ -110,6 +110,25 @@ def test_within_cli_matches_reference_tables(tmp_path, case):
     for r in prow:
         _, b = refio.read_tsv(os.path.join(tmp_path, f"{r['product']}_bootstrap_results.txt"))
         assert len(b) == 4000 and list(b[0])[:3] == ["file", "product_name", "bootstrap_num"]
+    # "next" rows f1: the site table is identical, the variant table too wherever the reference's counts are sane
+    gh, gs = refio.read_tsv(os.path.join(d, "within_group_site_results.txt"))
+    mh, ms = refio.read_tsv(os.path.join(tmp_path, "within_group_site_results.txt"))
+    assert gh == mh and len(gs) == len(ms)
+    for g, m in zip(gs, ms):
+        for col in ("site", "maj_nt", "maj_nt_count", "coverage", "A", "C", "G", "T"):
+            assert g[col] == m[col], (g["site"], col)
+        assert g["pi"] == m["pi"] or close(float(m["pi"]), float(g["pi"]))
+    gh, gv = refio.read_tsv(os.path.join(d, "within_group_variant_results.txt"))
+    mh, mv = refio.read_tsv(os.path.join(tmp_path, "within_group_variant_results.txt"))
+    assert gh == mh and len(gv) == len(mv)
+    mvd = {(r["product_name"], r["codon_num"]): r for r in mv}
+    for g in gv:
+        m = mvd[(g["product_name"], g["codon_num"])]
+        cols = ["num_alleles", "codons", "amino_acids", "variant_type"]
+        if case == "w_cfg1":          # no gaps: the reference's counts are exact (quirk q1 does not bite)
+            cols += ["consensus_codon", "codon_counts", "count_total", "codon_freqs", "max_codon_count", "min_codon_count", "num_defined_seqs"]
+        for col in cols:
+            assert g[col] == m[col], (g["product_name"], g["codon_num"], col)
 
 
 @pytest.mark.gpu

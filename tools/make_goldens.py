@@ -77,7 +77,8 @@ def case_w_cfg1():
         synth.write_fasta(os.path.join(tmp, "aln.fasta"), aln, width=80)
         shutil.copy(os.path.join(REF, "EXAMPLE_files", "CDS_EXAMPLE.gtf"), os.path.join(tmp, "cds.gtf"))
         perl("snpgenie_within_group.pl", ["--fasta_file_name=aln.fasta", "--gtf_file_name=cds.gtf", "--num_bootstraps=100", "--procs_per_node=8"], tmp)
-        keep(tmp, "w_cfg1", ["aln.fasta", "cds.gtf", "within_group_codon_results.txt", "within_group_product_results.txt"])
+        keep(tmp, "w_cfg1", ["aln.fasta", "cds.gtf", "within_group_codon_results.txt", "within_group_product_results.txt",
+                             "within_group_variant_results.txt", "within_group_site_results.txt"])
 
 
 def _within_small(case, seed, **damage):
@@ -91,7 +92,8 @@ def _within_small(case, seed, **damage):
         synth.write_fasta(os.path.join(tmp, "aln.fasta"), aln)
         synth.write_gtf(os.path.join(tmp, "cds.gtf"), prods)
         perl("snpgenie_within_group.pl", ["--fasta_file_name=aln.fasta", "--gtf_file_name=cds.gtf", "--num_bootstraps=200", "--procs_per_node=8"], tmp)
-        names = ["aln.fasta", "cds.gtf", "within_group_codon_results.txt", "within_group_product_results.txt"]
+        names = ["aln.fasta", "cds.gtf", "within_group_codon_results.txt", "within_group_product_results.txt",
+                 "within_group_variant_results.txt", "within_group_site_results.txt"]
         if case == "w_gaps":
             perl("snpgenie_within_group_processor.pl", ["--codon_file=within_group_codon_results.txt", "--sliding_window_size=10",
                                                         "--sliding_window_step=3", "--num_bootstraps=200"], tmp, log="processor.log")
