@@ -538,7 +538,7 @@ def test_site_counts_large_random_and_device_input():
     aln = np.frombuffer(b"ACGTacgtUuNn-RY", dtype=np.uint8)[rng.integers(0, 15, size=(n, L))]
     aln[:, 100:400] = aln[0, 100:400]                          # long conserved stretch
     products = [hostio.Product("p", 1, [4], [1002])]
-    pitch = 1008
+    pitch = 1024      # 16-byte multiple that covers the last span plus the 4 look-ahead bytes
     dbuf = torch.zeros((n, pitch), dtype=torch.uint8, device="cuda:0")
     dbuf[:, :L] = torch.from_numpy(aln).cuda()
     with Engine(device=0) as e:
