@@ -202,9 +202,12 @@ int prepare_group(snpg_ctx *ctx, Group &g, uint64_t n_seqs) {
 // (row r0, column base_al); row_bytes = readable bytes per row from there.
 int pack_block(snpg_ctx *ctx, Group &g, const uint8_t *d_block, int64_t pitch, int64_t rows, int64_t r0, int64_t row_bytes) {
     uint32_t *omin = g.other.as<uint32_t>(), *omax = g.other.as<uint32_t>() + ctx->shard_count;
-    if (r0 == 0 && (!ctx->keep_codes || ctx->site_counts))   // the group's first sequence is the consensus every row is compared with
-        CU(ctx, cudaMemcpyAsync(ctx->d_cons.p, d_block, (size_t)std::min<int64_t>(row_bytes, ctx->n_spans * 16 + 16),
-                                cudaMemcpyDeviceToDevice, ctx->stream));
+    if (r0 == 0 && (!ctx->keep_codes || ctx->site_counts)) {
+        // consensus row every row is compared with: majority vote over the group's first rows
+        Launch l(ctx, SNPG_K_OTHER);
+        launch_vote_consensus(d_block, pitch, (int)std::min<int64_t>(rows, 16), row_bytes, ctx->n_spans * 16 + 16, ctx->d_cons.as<uint8_t>(),
+                              ctx->stream);
+    }
     if (ctx->site_counts) {
         Launch l(ctx, SNPG_K_SITES);
         launch_site_hist(d_block, pitch, rows, ctx->d_cons.as<uint8_t>(), ctx->aln_len, g.sites.as<uint32_t>(), ctx->stream);

@@ -347,6 +347,44 @@ k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, int64_t n_rows, con
                      lut_cls, lut_chr);
 }
 
+// Consensus row for the compare-with-consensus kernels: per alignment column the Boyer-Moore
+// majority vote over the first rows of the group.  ANY row is a valid consensus (the kernels are
+// exact for every choice); a majority-like row just minimises how many spans take the decode path
+// (a first sequence carrying minor alleles would make most rows differ at those codons).
+__global__ void k_vote_consensus(const uint8_t *__restrict__ aln, int64_t pitch, int n_vote, int64_t row_bytes, int64_t n_out,
+                                 uint8_t *__restrict__ cons)
+{
+    // one thread votes on 4 adjacent columns (one aligned 32-bit word per row)
+    const int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (col >= n_out) return;
+    uint32_t cand[4] = {0, 0, 0, 0};
+    if (col + 4 <= row_bytes) {
+        int cnt[4] = {0, 0, 0, 0};
+        for (int r0 = 0; r0 < n_vote; r0 += 16) {
+            uint32_t w[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++)      // 16 independent loads in flight (rows past the end repeat the last row)
+                w[k] = *reinterpret_cast<const uint32_t *>(aln + (size_t)min(r0 + k, n_vote - 1) * pitch + col);
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const bool valid = r0 + k < n_vote;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t b = (w[k] >> (8 * j)) & 0xFF;
+                    const bool same = b == cand[j];
+                    const bool take = cnt[j] == 0;
+                    if (valid) {
+                        cand[j] = take ? b : cand[j];
+                        cnt[j] = take ? 1 : (same ? cnt[j] + 1 : cnt[j] - 1);
+                    }
+                }
+            }
+        }
+    }
+    for (int j = 0; j < 4; j++)
+        if (col + j < n_out) cons[col + j] = (uint8_t)cand[j];
+}
+
 // Code of the consensus row's codon for every codon (the fused kernel's reference point).
 __global__ void k_cons_codes(const uint8_t *__restrict__ cons, int64_t cons_shift, const CodonMap *__restrict__ map,
                              int64_t n_codons, uint8_t *__restrict__ cons_code, uint32_t *__restrict__ cons_key)
@@ -890,6 +928,13 @@ void launch_hist(const uint8_t *d_codes, int64_t n_pad, int64_t n_codons, uint32
     const int64_t items = n_codons * chunks;
     k_hist<<<(unsigned)((items + kHistWarps - 1) / kHistWarps), kHistWarps * 32, 0, stream>>>(d_codes, n_pad, n_codons, chunks,
                                                                                                chunk_rows, d_hist);
+}
+
+void launch_vote_consensus(const uint8_t *d_aln, int64_t pitch, int n_vote, int64_t row_bytes, int64_t n_out, uint8_t *d_cons,
+                           cudaStream_t stream)
+{
+    if (n_out <= 0 || n_vote <= 0) return;
+    k_vote_consensus<<<(unsigned)((n_out / 4 + 1 + 127) / 128), 128, 0, stream>>>(d_aln, pitch, n_vote, row_bytes, n_out, d_cons);
 }
 
 void launch_cons_codes(const uint8_t *d_cons, int64_t cons_shift, const CodonMap *d_map, int64_t n_codons, uint8_t *d_cons_code,

@@ -53,6 +53,9 @@ void launch_hist(const uint8_t *d_codes, int64_t n_pad, int64_t n_codons, uint32
 // bytes from there; d_cons holds the consensus row for the same columns.
 // Sequence: launch_cons_codes once per group (after the consensus row is known),
 // launch_fused_hist per row block (hist zeroed before the first), launch_fused_fixup once.
+// consensus row = per-column majority vote over the first n_vote rows (cons[0..n_out), zero past row_bytes)
+void launch_vote_consensus(const uint8_t *d_aln, int64_t pitch, int n_vote, int64_t row_bytes, int64_t n_out, uint8_t *d_cons,
+                           cudaStream_t stream);
 void launch_cons_codes(const uint8_t *d_cons, int64_t cons_shift, const CodonMap *d_map, int64_t n_codons, uint8_t *d_cons_code,
                        uint32_t *d_cons_key, cudaStream_t stream);
 void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, const uint8_t *d_cons, int64_t n_spans,
