@@ -594,3 +594,41 @@ def test_variant_table_from_histograms(eng):
                     assert row["num_defined_seqs"] == int(res["n_defined"][c])
                 n_rows += 1
         assert n_rows == len(gold)
+
+
+def test_config4_full_size_between_properties(eng):
+    """BASELINE config 4: 4 groups x 5,000 x 29,903, all 6 group pairs, every product."""
+    products = synth.sars2_products()
+    L, n = 29903, 5000
+    base = synth.make_alignment(n, L, products, 404)
+    rng = np.random.default_rng(4)
+    nt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    eng.set_products(products, L)
+    for g in range(4):
+        a = base if g == 0 else synth.make_alignment(n, L, products, 404, p_poly=0.3 + 0.05 * g)
+        if g:
+            cols = rng.integers(300, 29500, size=200)            # group-specific fixed differences
+            a[:, cols] = nt[rng.integers(0, 4, size=200)]
+        eng.load_group(g, a)
+        del a
+    sites, diffs = orc.tables()
+    hists = {g: [eng.hist(g, i) for i in range(len(products))] for g in range(4)}
+    for i, p in enumerate(products):
+        w0 = eng.within(0, i)
+        self_pair = eng.between(0, 0, i)
+        pol = w0["poly"] == 1
+        # a group against itself counts every ordered pair incl. (s,s): n^2 comparisons vs C(n,2)
+        assert close(self_pair["N_diffs"][pol] * n / (n - 1), w0["N_diffs"][pol]) and close(self_pair["S_diffs"][pol] * n / (n - 1), w0["S_diffs"][pol])
+        for a in range(4):
+            for b in range(a + 1, 4):
+                ab, ba = eng.between(a, b, i), eng.between(b, a, i)
+                assert (ab["ndef_a"] == n).all() and (ab["ndef_b"] == n).all()
+                assert (ab["poly"] == ba["poly"]).all()
+                assert (ab["comparisons"][ab["poly"] == 1] == n * n).all()
+                for k in STATS:
+                    assert close(ab[k], ba[k], rtol=1e-13), (p.name, a, b, k)
+                (ha, oa), (hb, ob) = hists[a][i], hists[b][i]
+                want = orc.between_hist(ha, hb, np.maximum(oa, ob), sites, diffs)
+                assert (ab["poly"] == want["poly"]).all()
+                for k in STATS:
+                    assert close(ab[k], want[k]), (p.name, a, b, k)
