@@ -96,11 +96,12 @@ int snpg_load_group_device(snpg_ctx *ctx, int group, const uint8_t *d_bases, uin
 int snpg_drop_group(snpg_ctx *ctx, int group);
 int snpg_group_size(const snpg_ctx *ctx, int group, uint64_t *n_seqs);
 
-/* Options: SNPG_OPT_KEEP_CODES (default 1) materialises the packed codon matrix
- * on the device (K1 then K2; needed by snpg_get_codon_indices and by the
- * between-group "first defined codon" rule, bg:853-890).  With 0 the histogram
- * is built straight from the alignment bytes by the fused kernel and no code
- * matrix exists.  Set before loading a group. */
+/* Options: SNPG_OPT_KEEP_CODES (default 0).  With 0 the histograms are built straight
+ * from the alignment bytes by the fused kernel and no code matrix exists.  With 1 the
+ * packed codon matrix is materialised on the device (K1 then K2): needed by
+ * snpg_get_codon_indices and by the between-group "first defined codon" rule
+ * (bg:853-890; without codes that rare case takes the lowest allele code).
+ * Set before loading a group. */
 #define SNPG_OPT_KEEP_CODES 1
 /* SNPG_OPT_SITE_COUNTS (default 0): while a group is loaded also count A, C, G, T per
  * alignment column (snpg_get_site_counts) -- the whole row is then staged, not only the

@@ -49,6 +49,7 @@ for my $g (0 .. $#fasta_files) {
     print "\ngroup index $g is group $fasta_files[$g]\n";
 }
 my $ctx = SNPGenieCUDA::create($device, $seed);
+SNPGenieCUDA::set_option($ctx, SNPGenieCUDA::OPT_KEEP_CODES, 1);   # the "first defined codon" rule (bg:853-890) needs sequence order
 SNPGenieCUDA::set_products($ctx, scalar @$products, pack_products($products), $aln_len);
 SNPGenieCUDA::load_group($ctx, $_, $seqs[$_], $n_seqs[$_], $aln_len) for 0 .. $#fasta_files;
 

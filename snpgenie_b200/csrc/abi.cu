@@ -52,7 +52,7 @@ struct snpg_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_packed[2] = {nullptr, nullptr};
     int rank = 0, world = 1;
-    bool keep_codes = true;
+    bool keep_codes = false;        // default route: fused histogram, no code matrix
     bool site_counts = false;       // also count A/C/G/T per alignment column while loading (whole rows are staged)
     bool defer_load_sync = false;   // set inside snpg_within_job*: the load's kernels stay queued behind the analysis
     // annotation

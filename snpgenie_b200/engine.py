@@ -33,7 +33,9 @@ def ng_tables():
 
 
 class Engine:
-    def __init__(self, device: int = 0, seed: int = 20261019, rank: int = 0, world: int = 1):
+    def __init__(self, device: int = 0, seed: int = 20261019, rank: int = 0, world: int = 1, keep_codes: bool = False):
+        """keep_codes=True materialises the packed codon matrix (K1+K2 route: codon_indices(), exact
+        between-group first-defined rule); the default builds histograms with the fused kernel."""
         self._ctx = C.c_void_p()
         rc = _abi.lib.snpg_create(C.byref(self._ctx), device, seed)
         if rc:
@@ -42,6 +44,8 @@ class Engine:
         self.rank, self.world = rank, world
         if world > 1:
             self._ck(_abi.lib.snpg_set_shard(self._ctx, rank, world))
+        if keep_codes:
+            self.set_option(_abi.OPT_KEEP_CODES, 1)
 
     # -- plumbing ---------------------------------------------------------
     def _ck(self, rc):

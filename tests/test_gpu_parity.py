@@ -26,7 +26,7 @@ def close(a, b, rtol=RTOL, atol=1e-15):
 @pytest.fixture(scope="module")
 def eng():
     from snpgenie_b200.engine import Engine
-    e = Engine(device=0, seed=1234)
+    e = Engine(device=0, seed=1234, keep_codes=True)
     yield e
     e.close()
 
@@ -472,7 +472,7 @@ def test_codon_range_shards_reassemble(world, keep):
     from snpgenie_b200.engine import Engine
     products = synth.hiv_products()
     aln = synth.make_alignment(600, 9719, products, 31, gap_frac=0.02, n_frac=0.02, iupac_frac=0.004)
-    with Engine(device=0) as full:
+    with Engine(device=0, keep_codes=True) as full:
         full.set_products(products, 9719)
         full.load_group(0, aln)
         ref_hist = [full.hist(0, i)[0] for i in range(len(products))]
