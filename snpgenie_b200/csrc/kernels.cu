@@ -848,12 +848,15 @@ k_moments(const double *__restrict__ vals, int64_t n_items, int64_t B, double *_
     const int p = blockIdx.x, which = blockIdx.y, t = threadIdx.x;
     const double *V = vals + ((size_t)which * n_items + p) * B;
     double s = 0;
-    for (int64_t b = t; b < B; b += 256) s += V[b];
+    int differs = 0;                       // replicates that are all identical have SD exactly 0, whatever
+    const double v0 = V[0];                // rounding the mean of B equal numbers picks up
+    for (int64_t b = t; b < B; b += 256) { const double v = V[b]; s += v; differs |= (v != v0); }
     const double mean = block_sum_256(s, red) / (double)B;
     double ss = 0;
     for (int64_t b = t; b < B; b += 256) { const double d = V[b] - mean; ss += d * d; }
     const double tot = block_sum_256(ss, red);
-    if (t == 0) se[6 * p + which] = sqrt(tot / (double)(B - 1));
+    const int any = __syncthreads_or(differs);
+    if (t == 0) se[6 * p + which] = any ? sqrt(tot / (double)(B - 1)) : 0.0;
 }
 
 // ---------------------------------------------------------------------------

@@ -632,3 +632,58 @@ def test_config4_full_size_between_properties(eng):
                 assert (ab["poly"] == want["poly"]).all()
                 for k in STATS:
                     assert close(ab[k], want[k]), (p.name, a, b, k)
+
+
+# ----------------------------------------------------------------- edge cases
+
+@pytest.mark.parametrize("keep", [True, False])
+def test_tiny_and_degenerate_inputs(keep):
+    from snpgenie_b200.engine import Engine
+    with Engine(device=0, keep_codes=keep) as e:
+        # one codon, one sequence; alignment shorter than one 16-byte span
+        e.set_products([hostio.Product("one", 1, [2], [4])], 7)
+        e.load_group(0, np.frombuffer(b"GATGCAT", dtype=np.uint8).reshape(1, 7).copy())
+        h, _ = e.hist(0, 0)
+        assert h.sum() == 1 and h[0, 14] == 1                      # ATG = 0*16 + 3*4 + 2
+        r = e.within(0, 0)
+        assert r["poly"][0] == 0 and r["conserved"][0] == 14 and r["N_sites"][0] == 3 and r["comparisons"][0] == 0
+        # every sequence undefined at a codon; a CR inside the sequence is an 'other' residue (chomp strips LF only)
+        aln = np.frombuffer(b"NNNACG\rAA" + b"---ACG\rAA" + b"nnnACGTAA", dtype=np.uint8).reshape(3, 9).copy()
+        e.set_products([hostio.Product("p", 1, [1], [9])], 9)
+        e.load_group(0, aln)
+        raw, codes = _oracle_product(aln, hostio.Product("p", 1, [1], [9]))
+        h, od = e.hist(0, 0)
+        assert (h == orc.hist(codes)).all() and h[0, 64] == 3 and h[2, 65] == 2 and h[2, 48] == 1
+        r = e.within(0, 0)
+        assert r["conserved"][0] == 64 and (r["stats4"][0] == 0).all() and r["n_defined"][0] == 0
+        assert r["poly"][2] == 1 and r["N_diffs"][2] == 0 and r["comparisons"][2] == 3      # TAA vs '\rAA': defined, 0 sites
+        lit = orc.within_pairloop(raw)
+        for k in STATS:
+            assert close(r[k], lit[k])
+        # two identical groups: between-group sees conserved codons only where a single allele exists
+        e.load_group(1, aln)
+        b = e.between(0, 1, 0)
+        assert b["poly"][0] == 0 and b["conserved"][0] == 64 and b["ndef_a"][0] == 0
+        assert b["poly"][1] == 0 and b["conserved"][1] == 6                                   # ACG
+
+
+def test_reload_group_with_different_sizes(eng2):
+    eng = eng2
+    products = synth.hiv_products()
+    eng.set_products(products, 9719)
+    for n, seed in ((400, 1), (33, 2), (900, 3)):
+        aln = synth.make_alignment(n, 9719, products, seed, gap_frac=0.02, n_frac=0.01)
+        eng.load_group(0, aln)                                     # same slot, new size: buffers are reused
+        for i in (0, 4, 7):
+            assert (eng.hist(0, i)[0] == orc.hist(_oracle_product(aln, products[i])[1])).all(), (n, i)
+
+
+def test_windows_edge_shapes(eng):
+    stats4 = np.arange(40, dtype=np.float64).reshape(10, 4) / 7
+    for W, step, nwin in ((10, 1, 1), (1, 1, 10), (3, 4, 2), (4, 100, 1)):
+        sums, se = eng.windows(stats4, W, step, B=50)
+        osums, _ = orc.windows(stats4, W, step)
+        assert sums.shape == (nwin, 4) and np.array_equal(sums, osums)
+        assert se.shape == (nwin, 3) and np.all(np.isfinite(se))
+        if W == 1:
+            assert np.all(se == 0)                                 # one codon resampled with itself never varies
