@@ -96,6 +96,20 @@ int snpg_load_group_device(snpg_ctx *ctx, int group, const uint8_t *d_bases, uin
 int snpg_drop_group(snpg_ctx *ctx, int group);
 int snpg_group_size(const snpg_ctx *ctx, int group, uint64_t *n_seqs);
 
+/* ---- FASTA ingest ("next" row f3) -----------------------------------------
+ * Native reader with the reference's semantics (wg:204-253; bg:133-187): every line
+ * that contains '>' starts a record, other lines are chomp'ed (LF only: a CR stays
+ * in the sequence) and concatenated, all records must have one length
+ * (SNPG_E_INPUT otherwise).  The residues land row-major in a PINNED host buffer
+ * owned by the ctx (slot = group id; replaced by the next read into the same slot),
+ * so snpg_load_group() on it streams at full PCIe rate.  No device needed for
+ * the parse itself, but a ctx is (it owns the buffer). */
+int snpg_read_fasta(snpg_ctx *ctx, int slot, const char *path, const uint8_t **bases, uint64_t *n_seqs, uint64_t *aln_len);
+/* The three normalised characters of one codon for every sequence of a FASTA slot
+ * (out [n_seqs][3]; uc, U->T, complemented on the '-' strand) -- what the host needs to
+ * print the strings of 'other' alleles.  Product/codon as in snpg_within. */
+int snpg_codon_strings(snpg_ctx *ctx, int slot, int product, int64_t codon, uint8_t *out);
+
 /* Options: SNPG_OPT_KEEP_CODES (default 0).  With 0 the histograms are built straight
  * from the alignment bytes by the fused kernel and no code matrix exists.  With 1 the
  * packed codon matrix is materialised on the device (K1 then K2): needed by

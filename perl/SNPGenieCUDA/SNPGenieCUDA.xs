@@ -120,6 +120,51 @@ load_group(h, group, bases, n_seqs, aln_len)
     check(aTHX_ ctx, snpg_load_group(ctx, group, p, n_seqs, aln_len, aln_len), "load_group");
 
 void
+read_fasta(h, slot, path)
+    IV h
+    int slot
+    const char *path
+  PPCODE:
+    snpg_ctx *ctx = ctx_of(aTHX_ h);
+    const uint8_t *bases = NULL;
+    uint64_t n = 0, len = 0;
+    check(aTHX_ ctx, snpg_read_fasta(ctx, slot, path, &bases, &n, &len), "read_fasta");
+    EXTEND(SP, 3);
+    PUSHs(sv_2mortal(newSViv(PTR2IV(bases))));
+    PUSHs(sv_2mortal(newSVuv((UV)n)));
+    PUSHs(sv_2mortal(newSVuv((UV)len)));
+
+void
+load_group_ptr(h, group, ptr, n_seqs, aln_len)
+    IV h
+    int group
+    IV ptr
+    UV n_seqs
+    UV aln_len
+  CODE:
+    snpg_ctx *ctx = ctx_of(aTHX_ h);
+    check(aTHX_ ctx, snpg_load_group(ctx, group, INT2PTR(const uint8_t *, ptr), n_seqs, aln_len, aln_len), "load_group");
+
+SV *
+codon_strings(h, slot, product, codon, n_seqs)
+    IV h
+    int slot
+    int product
+    IV codon
+    UV n_seqs
+  CODE:
+    snpg_ctx *ctx = ctx_of(aTHX_ h);
+    SV *out = newSV(3 * (STRLEN)n_seqs + 1);
+    SvPOK_only(out);
+    SvCUR_set(out, 3 * (STRLEN)n_seqs);
+    *SvEND(out) = '\0';
+    int rc = snpg_codon_strings(ctx, slot, product, (int64_t)codon, (uint8_t *)SvPVX(out));
+    if (rc != SNPG_OK) { SvREFCNT_dec(out); check(aTHX_ ctx, rc, "codon_strings"); }
+    RETVAL = out;
+  OUTPUT:
+    RETVAL
+
+void
 hist(h, group, product)
     IV h
     int group

@@ -9,7 +9,7 @@ package SNPGenieHost;
 use strict;
 use warnings;
 use Exporter 'import';
-our @EXPORT_OK = qw(read_gtf read_fasta pack_products ratio stars codon_of other_alleles fmt_pairs amino_acid variant_line site_lines);
+our @EXPORT_OK = qw(read_gtf read_fasta pack_products ratio stars codon_of other_alleles fmt_pairs amino_acid variant_line site_lines other_from_strings);
 
 my @NT = qw(A C G T);
 sub codon_of { my ($c) = @_; return $NT[$c >> 4] . $NT[($c >> 2) & 3] . $NT[$c & 3]; }
@@ -128,6 +128,18 @@ sub other_alleles {
         $codon =~ tr/U/T/;
         next if $codon =~ /N/ || $codon =~ /-/;
         next if $codon =~ /^[ACGT]{3}$/;
+        $count{$codon}++;
+    }
+    return \%count;
+}
+
+# same from the packed [n][3] normalised characters SNPGenieCUDA::codon_strings returns
+sub other_from_strings {
+    my ($packed) = @_;
+    my %count;
+    for my $s (0 .. length($packed) / 3 - 1) {
+        my $codon = substr($packed, 3 * $s, 3);
+        next if $codon =~ /N/ || $codon =~ /-/ || $codon =~ /^[ACGT]{3}$/;
         $count{$codon}++;
     }
     return \%count;

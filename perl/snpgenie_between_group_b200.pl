@@ -12,7 +12,7 @@ use FindBin;
 use lib "$FindBin::Bin/lib", "$FindBin::Bin/SNPGenieCUDA/lib";
 use Getopt::Long;
 use SNPGenieCUDA;
-use SNPGenieHost qw(read_gtf read_fasta pack_products ratio codon_of other_alleles fmt_pairs);
+use SNPGenieHost qw(read_gtf pack_products ratio codon_of other_from_strings fmt_pairs);
 
 STDOUT->autoflush(1);
 my $time1 = time;
@@ -39,19 +39,19 @@ print "\n#######################################################################
     . "\n################################################################################\n";
 
 my $products = read_gtf($gtf_file, $minus_strand);
-my (@seqs, @n_seqs, $aln_len);
+my $ctx = SNPGenieCUDA::create($device, $seed);
+SNPGenieCUDA::set_option($ctx, SNPGenieCUDA::OPT_KEEP_CODES, 1);   # the "first defined codon" rule (bg:853-890) needs sequence order
+my (@ptr, @n_seqs, $aln_len);
 for my $g (0 .. $#fasta_files) {
-    my ($s, $n, $len) = read_fasta($fasta_files[$g]);
+    my ($ptr, $n, $len) = SNPGenieCUDA::read_fasta($ctx, $g, $fasta_files[$g]);      # native reader, pinned memory
     die "\n\nDIE: The sequences must be aligned, i.e., must be the same length. TERMINATED.\n\n" if defined $aln_len && $len != $aln_len;
     $aln_len = $len;
-    push @seqs, $s;
+    push @ptr, $ptr;
     push @n_seqs, $n;
     print "\ngroup index $g is group $fasta_files[$g]\n";
 }
-my $ctx = SNPGenieCUDA::create($device, $seed);
-SNPGenieCUDA::set_option($ctx, SNPGenieCUDA::OPT_KEEP_CODES, 1);   # the "first defined codon" rule (bg:853-890) needs sequence order
 SNPGenieCUDA::set_products($ctx, scalar @$products, pack_products($products), $aln_len);
-SNPGenieCUDA::load_group($ctx, $_, $seqs[$_], $n_seqs[$_], $aln_len) for 0 .. $#fasta_files;
+SNPGenieCUDA::load_group_ptr($ctx, $_, $ptr[$_], $n_seqs[$_], $aln_len) for 0 .. $#fasta_files;
 
 open(my $codon_fh, '>>', 'between_group_codon_results.txt') or die "cannot write codon results: $!";
 print $codon_fh "analysis\tproduct\tgroup_1\tgroup_2\tcodon\tvariability\tnum_defined_codons_g1\tnum_defined_codons_g2\t"
@@ -88,7 +88,7 @@ for my $pi (0 .. $#$products) {
                     for my $g ($i, $j) {
                         my @h = unpack('L*', substr($hist[$g], 4 * 66 * $c, 4 * 66));
                         my @al = map { codon_of($_) } grep { $h[$_] > 0 } 0 .. 63;
-                        push @al, sort keys %{ other_alleles(\$seqs[$g], $n_seqs[$g], $aln_len, $p, $c) } if $h[65] > 0;
+                        push @al, sort keys %{ other_from_strings(SNPGenieCUDA::codon_strings($ctx, $g, $pi, $c, $n_seqs[$g])) } if $h[65] > 0;
                         push @side, \@al;
                     }
                     my $pairs = join('', map { my $a = $_; map { "($a-$_)" } @{ $side[1] } } @{ $side[0] });
@@ -99,7 +99,7 @@ for my $pi (0 .. $#$products) {
                     if ($cons[$c] < 64) { $codon = codon_of($cons[$c]); }
                     elsif ($cons[$c] == 65) {
                         my $g = $nda[$c] > 0 ? $i : $j;
-                        ($codon) = sort keys %{ other_alleles(\$seqs[$g], $n_seqs[$g], $aln_len, $p, $c) };
+                        ($codon) = sort keys %{ other_from_strings(SNPGenieCUDA::codon_strings($ctx, $g, $pi, $c, $n_seqs[$g])) };
                     }
                     $row .= "conserved\t$nda[$c]\t$ndb[$c]\t$codon\t$Ns\t$Ss\t0\t0";
                     $sum[0] += $Ns; $sum[1] += $Ss;

@@ -15,7 +15,7 @@ use FindBin;
 use lib "$FindBin::Bin/lib", "$FindBin::Bin/SNPGenieCUDA/lib";
 use Getopt::Long;
 use SNPGenieCUDA;
-use SNPGenieHost qw(read_gtf read_fasta pack_products ratio stars codon_of other_alleles fmt_pairs variant_line site_lines);
+use SNPGenieHost qw(read_gtf pack_products ratio stars codon_of other_from_strings fmt_pairs variant_line site_lines);
 
 STDOUT->autoflush(1);
 my $time1 = time;
@@ -47,13 +47,13 @@ print "\n# " . SNPGenieCUDA::version() . "; --procs_per_node is ignored on this 
 
 my $products = read_gtf($gtf_file_name, $minus_strand);
 print "\nRecording coding sequence data for $fasta_file_name...\n";
-my ($seqs, $n_seqs, $aln_len) = read_fasta($fasta_file_name);
-
 my $ctx = SNPGenieCUDA::create($device, $seed);
+# native reader: same record rules as wg:204-253, straight into pinned memory
+my ($bases_ptr, $n_seqs, $aln_len) = SNPGenieCUDA::read_fasta($ctx, 0, $fasta_file_name);
 SNPGenieCUDA::set_option($ctx, SNPGenieCUDA::OPT_KEEP_CODES, 0);        # histograms straight from the alignment bytes
 SNPGenieCUDA::set_option($ctx, SNPGenieCUDA::OPT_SITE_COUNTS, 1);       # per-site A/C/G/T in the same load
 SNPGenieCUDA::set_products($ctx, scalar @$products, pack_products($products), $aln_len);
-SNPGenieCUDA::load_group($ctx, 0, $seqs, $n_seqs, $aln_len);
+SNPGenieCUDA::load_group_ptr($ctx, 0, $bases_ptr, $n_seqs, $aln_len);
 
 # headers, append mode like the reference (wg:337-361)
 open(my $codon_fh, '>>', 'within_group_codon_results.txt') or die "cannot write codon results: $!";
@@ -85,7 +85,7 @@ for my $pi (0 .. $#$products) {
             my @h = unpack('L*', substr($hist_s, 4 * 66 * $c, 4 * 66));
             my @alleles = map { [ codon_of($_), $h[$_] ] } grep { $h[$_] > 0 } 0 .. 63;
             if ($h[65] > 0) {
-                my $others = other_alleles(\$seqs, $n_seqs, $aln_len, $p, $c);
+                my $others = other_from_strings(SNPGenieCUDA::codon_strings($ctx, 0, $pi, $c, $n_seqs));
                 push @alleles, map { [ $_, $others->{$_} ] } sort keys %$others;
             }
             print $codon_fh "polymorphic\t" . fmt_pairs(\@alleles) . "\t$Ns\t$Ss\t$Nd\t$Sd\n";
@@ -95,7 +95,7 @@ for my $pi (0 .. $#$products) {
         } else {
             my $codon = '';
             if ($cons[$c] < 64) { $codon = codon_of($cons[$c]); }
-            elsif ($cons[$c] == 65) { ($codon) = sort keys %{ other_alleles(\$seqs, $n_seqs, $aln_len, $p, $c) }; }
+            elsif ($cons[$c] == 65) { ($codon) = sort keys %{ other_from_strings(SNPGenieCUDA::codon_strings($ctx, 0, $pi, $c, $n_seqs)) }; }
             print $codon_fh "conserved\t$codon\t$Ns\t$Ss\t0\t0\n";
             $sum_Ns += $Ns; $sum_Ss += $Ss;
         }

@@ -42,6 +42,8 @@ SIGNATURES = {
     "snpg_shard_range": (C.c_int, [_ctx, _i64p, _i64p, _i64p]),
     "snpg_load_group": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
     "snpg_load_group_device": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "snpg_read_fasta": (C.c_int, [_ctx, C.c_int, C.c_char_p, C.POINTER(C.c_void_p), _u64p, _u64p]),
+    "snpg_codon_strings": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int64, _u8p]),
     "snpg_drop_group": (C.c_int, [_ctx, C.c_int]),
     "snpg_group_size": (C.c_int, [_ctx, C.c_int, _u64p]),
     "snpg_set_option": (C.c_int, [_ctx, C.c_int, C.c_int64]),

@@ -2,6 +2,11 @@
 // sequencing of kernels.  See include/snpgenie_cuda.h for the contract and the
 // reference blocks each entry point replaces.  There is no CPU fallback here:
 // every compute entry point runs the CUDA kernels or fails with SNPG_E_CUDA.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -70,6 +75,9 @@ struct snpg_ctx {
     DevBuf t_codes, t_hist, t_other;      // irregular codons: compact K1+K2 scratch
     // groups
     Group groups[SNPG_MAX_GROUPS];
+    // FASTA slots: pinned host copies [n][len] read by snpg_read_fasta
+    struct HostAln { uint8_t *p = nullptr; size_t cap = 0; uint64_t n = 0, len = 0; } host_aln[SNPG_MAX_GROUPS];
+    std::vector<CodonMap> host_map;   // full codon map (absolute columns), for snpg_codon_strings
     // scratch
     DevBuf s_vals, d_order_local, d_order_full;
     int64_t max_codons_local = 0, max_codons_full = 0;
@@ -318,6 +326,7 @@ void snpg_destroy(snpg_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     for (auto &g : ctx->groups) { g.codes.release(); g.hist.release(); g.other.release(); g.sites.release(); }
+    for (auto &h : ctx->host_aln) if (h.p) cudaFreeHost(h.p);
     DevBuf *bufs[] = {&ctx->d_map, &ctx->d_local_ofs, &ctx->d_full_ofs, &ctx->d_tables, &ctx->staging[0], &ctx->staging[1],
                       &ctx->d_runs, &ctx->d_regular, &ctx->d_irr_map, &ctx->d_irr_idx, &ctx->d_cons, &ctx->d_cons_code, &ctx->d_cons_key, &ctx->t_codes, &ctx->t_hist,
                       &ctx->t_other,
@@ -394,6 +403,7 @@ int snpg_set_products(snpg_ctx *ctx, int n_products, const int64_t *seg_ofs, con
         full_ofs[p + 1] = (int64_t)map_all.size();
     }
     const int64_t total = (int64_t)map_all.size();
+    ctx->host_map = map_all;
     snpg_shard_plan(total, ctx->rank, ctx->world, &ctx->shard_first, &ctx->shard_count);
     ctx->n_products = n_products;
     ctx->aln_len = aln_len;
@@ -599,6 +609,92 @@ int snpg_load_group_device(snpg_ctx *ctx, int group, const uint8_t *d_bases, uin
     if (rc == SNPG_OK) rc = finish_group(ctx, g);
     if (!saved_keep && !fused_ok) { ctx->keep_codes = saved_keep; g.codes.release(); g.has_codes = false; }
     return rc;
+}
+
+int snpg_read_fasta(snpg_ctx *ctx, int slot, const char *path, const uint8_t **bases, uint64_t *n_seqs, uint64_t *aln_len) {
+    if (!ctx || !path || !bases || !n_seqs || !aln_len) return SNPG_E_ARG;
+    NEED(ctx, slot >= 0 && slot < SNPG_MAX_GROUPS, SNPG_E_ARG, "slot %d out of range", slot);
+    if (int rc = bind(ctx)) return rc;
+    const int fd = open(path, O_RDONLY);
+    NEED(ctx, fd >= 0, SNPG_E_INPUT, "Could not open file %s", path);
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size == 0) { close(fd); return fail(ctx, SNPG_E_INPUT, "%s is empty or unreadable", path); }
+    const size_t size = (size_t)st.st_size;
+    const char *f = static_cast<const char *>(mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0));
+    close(fd);
+    NEED(ctx, f != MAP_FAILED, SNPG_E_INPUT, "cannot map %s", path);
+    madvise(const_cast<char *>(f), size, MADV_SEQUENTIAL);
+    struct Unmap { const char *p; size_t n; ~Unmap() { munmap(const_cast<char *>(p), n); } } unmap{f, size};
+
+    // pass 1: count records and measure the first one
+    uint64_t n = 0, first_len = 0;
+    bool in_first = false;
+    for (size_t pos = 0; pos < size;) {
+        const char *nl = static_cast<const char *>(memchr(f + pos, '\n', size - pos));
+        const size_t end = nl ? (size_t)(nl - f) : size;
+        if (memchr(f + pos, '>', end - pos)) { n++; in_first = (n == 1); }
+        else if (in_first) first_len += end - pos;
+        pos = end + 1;
+    }
+    NEED(ctx, n > 0 && first_len > 0, SNPG_E_INPUT, "no FASTA records in %s", path);
+    auto &h = ctx->host_aln[slot];
+    const size_t need = (size_t)n * first_len;
+    if (need > h.cap) {
+        if (h.p) cudaFreeHost(h.p);
+        h.p = nullptr; h.cap = 0;
+        CU(ctx, cudaHostAlloc(reinterpret_cast<void **>(&h.p), need, cudaHostAllocDefault));
+        h.cap = need;
+    }
+    // pass 2: copy the data lines of each record into its row
+    uint64_t rec = 0, filled = 0;
+    bool started = false;
+    for (size_t pos = 0; pos < size;) {
+        const char *nl = static_cast<const char *>(memchr(f + pos, '\n', size - pos));
+        const size_t end = nl ? (size_t)(nl - f) : size;
+        if (memchr(f + pos, '>', end - pos)) {
+            if (started) {
+                NEED(ctx, filled == first_len, SNPG_E_INPUT, "The sequences must be aligned, i.e., must be the same length.");
+                rec++;
+            }
+            started = true;
+            filled = 0;
+        } else if (started) {
+            const size_t len = end - pos;
+            NEED(ctx, filled + len <= first_len, SNPG_E_INPUT, "The sequences must be aligned, i.e., must be the same length.");
+            memcpy(h.p + rec * first_len + filled, f + pos, len);
+            filled += len;
+        }
+        pos = end + 1;
+    }
+    NEED(ctx, filled == first_len, SNPG_E_INPUT, "The sequences must be aligned, i.e., must be the same length.");
+    h.n = n;
+    h.len = first_len;
+    *bases = h.p;
+    *n_seqs = n;
+    *aln_len = first_len;
+    return SNPG_OK;
+}
+
+int snpg_codon_strings(snpg_ctx *ctx, int slot, int product, int64_t codon, uint8_t *out) {
+    if (!ctx || !out) return SNPG_E_ARG;
+    NEED(ctx, slot >= 0 && slot < SNPG_MAX_GROUPS && ctx->host_aln[slot].p, SNPG_E_STATE, "no FASTA was read into slot %d", slot);
+    if (int rc = check_product(ctx, product)) return rc;
+    const int64_t C = ctx->full_ofs[product + 1] - ctx->full_ofs[product];
+    NEED(ctx, codon >= 0 && codon < C, SNPG_E_ARG, "codon %lld out of range", (long long)codon);
+    const auto &h = ctx->host_aln[slot];
+    NEED(ctx, (int64_t)h.len == ctx->aln_len, SNPG_E_INPUT, "slot %d has alignment length %llu, the annotation %lld", slot,
+         (unsigned long long)h.len, (long long)ctx->aln_len);
+    const CodonMap m = ctx->host_map[(size_t)(ctx->full_ofs[product] + codon)];
+    const int32_t pos[3] = {m.p0, m.p1, m.p2};
+    for (uint64_t s = 0; s < h.n; s++)
+        for (int k = 0; k < 3; k++) {
+            uint8_t c = h.p[s * h.len + (size_t)pos[k]];
+            if (c >= 'a' && c <= 'z') c = (uint8_t)(c - 32);
+            if (m.minus) c = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : c;   // fasta2revcom.pl:79
+            if (c == 'U') c = 'T';
+            out[3 * s + k] = c;
+        }
+    return SNPG_OK;
 }
 
 int snpg_drop_group(snpg_ctx *ctx, int group) {

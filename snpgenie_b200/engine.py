@@ -121,6 +121,21 @@ class Engine:
         fn = _abi.lib.snpg_load_group_device if device else _abi.lib.snpg_load_group
         self._ck(fn(self._ctx, group, ptr, n_seqs, aln_len, row_stride))
 
+    def read_fasta(self, slot: int, path: str):
+        """Native FASTA reader (reference semantics) into a pinned host buffer: (ptr, n_seqs, aln_len)."""
+        ptr, n, length = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        self._ck(_abi.lib.snpg_read_fasta(self._ctx, slot, path.encode(), C.byref(ptr), C.byref(n), C.byref(length)))
+        return ptr.value, n.value, length.value
+
+    def fasta_view(self, ptr: int, n_seqs: int, aln_len: int) -> np.ndarray:
+        """numpy view of a read_fasta buffer (valid until the slot is read into again)."""
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n_seqs, aln_len))
+
+    def codon_strings(self, slot: int, product: int, codon: int, n_seqs: int) -> np.ndarray:
+        out = np.zeros((n_seqs, 3), dtype=np.uint8)
+        self._ck(_abi.lib.snpg_codon_strings(self._ctx, slot, product, codon, _ptr(out, C.c_uint8)))
+        return out
+
     def group_size(self, group: int) -> int:
         n = C.c_uint64()
         self._ck(_abi.lib.snpg_group_size(self._ctx, group, C.byref(n)))

@@ -687,3 +687,44 @@ def test_windows_edge_shapes(eng):
         assert se.shape == (nwin, 3) and np.all(np.isfinite(se))
         if W == 1:
             assert np.all(se == 0)                                 # one codon resampled with itself never varies
+
+
+# ----------------------------------------------------------------- "next" row f3: native FASTA ingest
+
+def test_native_fasta_reader_matches_reference_semantics(tmp_path, eng):
+    from snpgenie_b200 import _abi
+    # the golden FASTA files (one wrapped at 80 columns, others single-line)
+    for case in ("w_cfg1", "w_gaps", "w_minus"):
+        path = os.path.join(refio.GOLD, case, "aln.fasta")
+        _, want = hostio.read_fasta(path)
+        ptr, n, L = eng.read_fasta(0, path)
+        assert (n, L) == want.shape
+        assert np.array_equal(eng.fasta_view(ptr, n, L), want)
+    # CRLF (the CR stays, as after chomp), '>' in mid-line makes a header, blank lines, no trailing newline
+    odd = tmp_path / "odd.fa"
+    odd.write_bytes(b">a\r\nACGT\r\nAC\r\n\nxx>b\nACGT\rACN\r\n>c desc\nAC\nGT\rAC-\r")
+    _, want = hostio.read_fasta(str(odd))
+    ptr, n, L = eng.read_fasta(1, str(odd))
+    got = eng.fasta_view(ptr, n, L)
+    assert got.shape == want.shape == (3, 8) and np.array_equal(got, want)
+    assert bytes(got[0]) == b"ACGT\rAC\r"
+    # errors the reference dies on
+    bad = tmp_path / "bad.fa"
+    bad.write_bytes(b">a\nACGT\n>b\nACG\n")
+    with pytest.raises(_abi.SnpgError) as e:
+        eng.read_fasta(2, str(bad))
+    assert e.value.code == _abi.E_INPUT and "same length" in str(e.value)
+    with pytest.raises(_abi.SnpgError) as e:
+        eng.read_fasta(2, str(tmp_path / "missing.fa"))
+    assert e.value.code == _abi.E_INPUT
+    # the pinned buffer feeds load_group directly; codon strings come back normalised
+    d, aln, _, _ = refio.within_case("w_minus")
+    products = hostio.read_gtf_products(os.path.join(d, "cds.gtf"), include_minus=True)
+    ptr, n, L = eng.read_fasta(0, os.path.join(d, "aln.fasta"))
+    eng.set_products(products, L)
+    eng.load_group_ptr(0, ptr, n, L, L, device=False)
+    for i, p in enumerate(products):
+        raw, codes = _oracle_product(aln, p)
+        assert (eng.hist(0, i)[0] == orc.hist(codes)).all()
+        for c in (0, 7, p.n_codons - 1):
+            assert np.array_equal(eng.codon_strings(0, i, c, n), raw[:, c])
