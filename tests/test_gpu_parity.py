@@ -702,7 +702,7 @@ def test_native_fasta_reader_matches_reference_semantics(tmp_path, eng):
         assert np.array_equal(eng.fasta_view(ptr, n, L), want)
     # CRLF (the CR stays, as after chomp), '>' in mid-line makes a header, blank lines, no trailing newline
     odd = tmp_path / "odd.fa"
-    odd.write_bytes(b">a\r\nACGT\r\nAC\r\n\nxx>b\nACGT\rACN\r\n>c desc\nAC\nGT\rAC-\r")
+    odd.write_bytes(b">a\r\nACGT\r\nAC\r\n\nxx>b\nACGT\rAN\r\n>c desc\nAC\nGT\rA-\r")
     _, want = hostio.read_fasta(str(odd))
     ptr, n, L = eng.read_fasta(1, str(odd))
     got = eng.fasta_view(ptr, n, L)
