@@ -221,6 +221,10 @@ int snpg_set_stream(snpg_ctx *ctx, void *cuda_stream);
 #define SNPG_N_KERNEL_KINDS 10
 int snpg_get_profile(snpg_ctx *ctx, double *ms /*[10]*/, int64_t *calls /*[10]*/, int reset);
 
+/* Test hook: one Philox4x32-10 block computed by the device code the bootstraps use
+ * (checked against the Random123 known-answer vectors). */
+int snpg_test_philox(snpg_ctx *ctx, const uint32_t *ctr4, const uint32_t *key2, uint32_t *out4);
+
 /* Kernel launches issued by this ctx since creation (bench.py's gpu_launches). */
 int64_t snpg_launch_count(const snpg_ctx *ctx);
 

@@ -60,6 +60,7 @@ SIGNATURES = {
     "snpg_bootstrap_all_device": (C.c_int, [_ctx, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "snpg_product_sums_device": (C.c_int, [_ctx, C.c_void_p, _f64p]),
     "snpg_rep_moments_device": (C.c_int, [_ctx, C.c_void_p, C.c_int64, C.c_int64, _f64p]),
+    "snpg_test_philox": (C.c_int, [_ctx, _u32p, _u32p, _u32p]),
     "snpg_launch_count": (C.c_int64, [_ctx]),
     "snpg_set_stream": (C.c_int, [_ctx, C.c_void_p]),
     "snpg_get_profile": (C.c_int, [_ctx, _f64p, _i64p, C.c_int]),

@@ -998,6 +998,17 @@ int snpg_within_job(snpg_ctx *ctx, int group, const uint8_t *bases, int bases_on
     return snpg_within_all(ctx, group, B, prod_sums, prod_se);
 }
 
+int snpg_test_philox(snpg_ctx *ctx, const uint32_t *ctr4, const uint32_t *key2, uint32_t *out4) {
+    if (!ctx || !ctr4 || !key2 || !out4) return SNPG_E_ARG;
+    if (int rc = bind(ctx)) return rc;
+    CU(ctx, ctx->s_misc.ensure(16));
+    { Launch l(ctx, SNPG_K_OTHER); launch_philox_kat(ctr4, key2, ctx->s_misc.as<uint32_t>(), ctx->stream); }
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(out4, ctx->s_misc.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, sync_stream(ctx));
+    return SNPG_OK;
+}
+
 int64_t snpg_launch_count(const snpg_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int snpg_set_stream(snpg_ctx *ctx, void *cuda_stream) {

@@ -673,21 +673,22 @@ k_stats(GroupView A, GroupView B, int64_t n_codons, const double *__restrict__ t
 }
 
 // product sums (wg:690-693; bg:984-1005): fixed-shape tree, deterministic
-__global__ void __launch_bounds__(256)
+constexpr int kSumThreads = 1024;
+__global__ void __launch_bounds__(kSumThreads)
 k_product_sums(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, double *__restrict__ sums)
 {
-    __shared__ double red[4][256];
+    __shared__ double red[4][kSumThreads];
     const int p = blockIdx.x, t = threadIdx.x;
     const int64_t c0 = ofs[p], c1 = ofs[p + 1];
     double s[4] = {0, 0, 0, 0};
-    for (int64_t c = c0 + t; c < c1; c += 256) {
+    for (int64_t c = c0 + t; c < c1; c += kSumThreads) {
         const double2 x = reinterpret_cast<const double2 *>(stats4 + 4 * c)[0];
         const double2 y = reinterpret_cast<const double2 *>(stats4 + 4 * c)[1];
         s[0] += x.x; s[1] += x.y; s[2] += y.x; s[3] += y.y;
     }
     for (int q = 0; q < 4; q++) red[q][t] = s[q];
     __syncthreads();
-    for (int h = 128; h > 0; h >>= 1) {
+    for (int h = kSumThreads / 2; h > 0; h >>= 1) {
         if (t < h) for (int q = 0; q < 4; q++) red[q][t] += red[q][t + h];
         __syncthreads();
     }
@@ -708,6 +709,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
         key.y += 0xBB67AE85u;
     }
     return ctr;
+}
+
+__global__ void k_philox_kat(uint4 ctr, uint2 key, uint32_t *out)
+{
+    const uint4 r = philox4x32_10(ctr, key);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 
 // ---------------------------------------------------------------------------
@@ -829,32 +836,33 @@ __global__ void k_rep_values(const double *__restrict__ rep, int64_t n_items, in
 // K6: SD over replicates in the reference's two-pass form with n-1
 // (wg:1351-1365).  One block per (item, statistic); se[item][6].
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ double block_sum_256(double v, double *red) {
+constexpr int kMomentThreads = 1024;
+__device__ __forceinline__ double block_sum(double v, double *red) {     // fixed-shape tree: deterministic
     const int t = threadIdx.x;
     __syncthreads();
     red[t] = v;
     __syncthreads();
-    for (int h = 128; h > 0; h >>= 1) {
+    for (int h = kMomentThreads / 2; h > 0; h >>= 1) {
         if (t < h) red[t] += red[t + h];
         __syncthreads();
     }
     return red[0];
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kMomentThreads)
 k_moments(const double *__restrict__ vals, int64_t n_items, int64_t B, double *__restrict__ se)
 {
-    __shared__ double red[256];
+    __shared__ double red[kMomentThreads];
     const int p = blockIdx.x, which = blockIdx.y, t = threadIdx.x;
     const double *V = vals + ((size_t)which * n_items + p) * B;
     double s = 0;
     int differs = 0;                       // replicates that are all identical have SD exactly 0, whatever
     const double v0 = V[0];                // rounding the mean of B equal numbers picks up
-    for (int64_t b = t; b < B; b += 256) { const double v = V[b]; s += v; differs |= (v != v0); }
-    const double mean = block_sum_256(s, red) / (double)B;
+    for (int64_t b = t; b < B; b += kMomentThreads) { const double v = V[b]; s += v; differs |= (v != v0); }
+    const double mean = block_sum(s, red) / (double)B;
     double ss = 0;
-    for (int64_t b = t; b < B; b += 256) { const double d = V[b] - mean; ss += d * d; }
-    const double tot = block_sum_256(ss, red);
+    for (int64_t b = t; b < B; b += kMomentThreads) { const double d = V[b] - mean; ss += d * d; }
+    const double tot = block_sum(ss, red);
     const int any = __syncthreads_or(differs);
     if (t == 0) se[6 * p + which] = any ? sqrt(tot / (double)(B - 1)) : 0.0;
 }
@@ -1019,7 +1027,7 @@ void launch_product_sums(const double *d_stats4, const int64_t *d_prod_ofs, int 
                          cudaStream_t stream)
 {
     if (n_products <= 0) return;
-    k_product_sums<<<n_products, 256, 0, stream>>>(d_stats4, d_prod_ofs, d_sums);
+    k_product_sums<<<n_products, kSumThreads, 0, stream>>>(d_stats4, d_prod_ofs, d_sums);
 }
 
 void launch_bootstrap(const double *d_stats4, const int64_t *d_prod_ofs, const int *d_order, int n_products, int64_t max_codons,
@@ -1041,6 +1049,11 @@ void launch_bootstrap(const double *d_stats4, const int64_t *d_prod_ofs, const i
     }
 }
 
+void launch_philox_kat(const uint32_t *ctr, const uint32_t *key, uint32_t *d_out, cudaStream_t stream)
+{
+    k_philox_kat<<<1, 1, 0, stream>>>(make_uint4(ctr[0], ctr[1], ctr[2], ctr[3]), make_uint2(key[0], key[1]), d_out);
+}
+
 void launch_rep_values(const double *d_rep, int64_t n_items, int64_t B, double *d_vals, cudaStream_t stream)
 {
     if (n_items <= 0 || B <= 0) return;
@@ -1051,7 +1064,7 @@ void launch_rep_values(const double *d_rep, int64_t n_items, int64_t B, double *
 void launch_moments(const double *d_vals, int64_t n_items, int64_t B, double *d_se, cudaStream_t stream)
 {
     if (n_items <= 0) return;
-    k_moments<<<dim3((unsigned)n_items, 6), 256, 0, stream>>>(d_vals, n_items, B, d_se);
+    k_moments<<<dim3((unsigned)n_items, 6), kMomentThreads, 0, stream>>>(d_vals, n_items, B, d_se);
 }
 
 void launch_window_sums(const double *d_stats4, int64_t W, int64_t step, int64_t nwin, double *d_win_sums,

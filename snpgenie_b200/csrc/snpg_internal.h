@@ -100,6 +100,8 @@ void launch_product_sums(const double *d_stats4, const int64_t *d_prod_ofs, int 
 void launch_bootstrap(const double *d_stats4, const int64_t *d_prod_ofs, const int *d_order, int n_products, int64_t max_codons,
                       int64_t b_first, int64_t b_count, uint64_t seed, uint32_t stream_id, double *d_rep, double *d_vals,
                       cudaStream_t stream);
+// one Philox4x32-10 block on the device (known-answer test hook)
+void launch_philox_kat(const uint32_t *ctr, const uint32_t *key, uint32_t *d_out, cudaStream_t stream);
 // rep[item][B][4] -> vals[which][item][B]
 void launch_rep_values(const double *d_rep, int64_t n_items, int64_t B, double *d_vals, cudaStream_t stream);
 // K6 moments: vals[which][item][B] -> se[item][6] (sample SD, n-1, two-pass)

@@ -728,3 +728,17 @@ def test_native_fasta_reader_matches_reference_semantics(tmp_path, eng):
         assert (eng.hist(0, i)[0] == orc.hist(codes)).all()
         for c in (0, 7, p.n_codons - 1):
             assert np.array_equal(eng.codon_strings(0, i, c, n), raw[:, c])
+
+
+def test_philox_known_answers(eng):
+    """Random123 kat_vectors for philox4x32-10, computed by the device function the bootstraps call."""
+    import ctypes as C
+    from snpgenie_b200 import _abi
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kats:
+        c, k, o = np.array(ctr, np.uint32), np.array(key, np.uint32), np.zeros(4, np.uint32)
+        rc = _abi.lib.snpg_test_philox(eng._ctx, c.ctypes.data_as(C.POINTER(C.c_uint32)), k.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                       o.ctypes.data_as(C.POINTER(C.c_uint32)))
+        assert rc == 0 and tuple(int(x) for x in o) == want
