@@ -742,3 +742,59 @@ def test_philox_known_answers(eng):
         rc = _abi.lib.snpg_test_philox(eng._ctx, c.ctypes.data_as(C.POINTER(C.c_uint32)), k.ctypes.data_as(C.POINTER(C.c_uint32)),
                                        o.ctypes.data_as(C.POINTER(C.c_uint32)))
         assert rc == 0 and tuple(int(x) for x in o) == want
+
+
+# ----------------------------------------------------------------- randomized annotations (index-map fuzz)
+
+def _random_products(rng, L):
+    prods = []
+    for k in range(int(rng.integers(1, 7))):
+        nseg = int(rng.integers(1, 5))
+        cuts = np.sort(rng.choice(np.arange(1, L), size=2 * nseg, replace=False))
+        starts, stops = list(cuts[0::2] + 0), list(cuts[1::2] + 0)
+        total = sum(e - s + 1 for s, e in zip(starts, stops))
+        trim = total % 3                      # shorten the last segment to complete the last codon
+        while trim and stops[-1] - trim < starts[-1]:
+            starts.pop(); stops.pop()
+            if not starts:
+                break
+            total = sum(e - s + 1 for s, e in zip(starts, stops)); trim = total % 3
+        if not starts:
+            continue
+        stops[-1] -= trim
+        if sum(e - s + 1 for s, e in zip(starts, stops)) < 3:
+            continue
+        order = rng.permutation(len(starts))  # segments arrive in file order, the library sorts them
+        prods.append(hostio.Product(f"p{k}", int(rng.choice([1, -1])), [int(starts[i]) for i in order], [int(stops[i]) for i in order]))
+    return prods
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_annotations_both_routes(seed):
+    from snpgenie_b200.engine import Engine
+    rng = np.random.default_rng(1000 + seed)
+    L = int(rng.integers(20, 400))
+    n = int(rng.integers(1, 300))
+    prods = _random_products(rng, L)
+    if not prods:
+        prods = [hostio.Product("p", 1, [1], [3])]
+    alphabet = np.frombuffer(b"ACGTACGTACGTacgtUuNn-RY", dtype=np.uint8)
+    aln = alphabet[rng.integers(0, len(alphabet), size=(n, L))]
+    keep_cols = rng.random(L) < 0.6                            # conserved columns exercise the fast path
+    aln[:, keep_cols] = aln[0, keep_cols]
+    sorted_prods = [hostio.Product(p.name, p.strand, sorted(p.starts), [e for _, e in sorted(zip(p.starts, p.stops))]) for p in prods]
+    for keep in (True, False):
+        with Engine(device=0, keep_codes=keep) as e:
+            e.set_products(prods, L)
+            e.load_group(0, aln)
+            for i, p in enumerate(sorted_prods):
+                raw, codes = _oracle_product(aln, p)
+                h, od = e.hist(0, i)
+                assert (h == orc.hist(codes)).all(), (seed, keep, p)
+                assert (od == orc.other_distinct(raw, codes)).all()
+                if keep:
+                    assert (e.codon_indices(0, i) == codes).all()
+                got, want = e.within(0, i), orc.within_pairloop(raw)
+                assert (got["poly"] == want["poly"]).all()
+                for k in STATS:
+                    assert close(got[k], want[k]), (seed, keep, p.name, k)
