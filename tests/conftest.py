@@ -10,6 +10,13 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+    # The built artefacts are git-ignored: on a fresh checkout build them once (nvcc cross-compiles
+    # sm_100a without a GPU) so that collection does not depend on who ran build() first.
+    lib = os.path.join(ROOT, "snpgenie_b200", "libsnpgenie_cuda.so")
+    glue = os.path.join(ROOT, "perl", "SNPGenieCUDA", "lib", "auto", "SNPGenieCUDA", "SNPGenieCUDA.so")
+    if not (os.path.exists(lib) and os.path.exists(glue) and os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so"))):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 @pytest.fixture(scope="session")
