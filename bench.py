@@ -193,10 +193,11 @@ def run_ours(args):
     eng.set_stream(stream.cuda_stream)
     # timed passes bracket only the dominant HBM kernel with events (a pair costs ~3 us of stream time);
     # a separate untimed pass of the same steps brackets every launch for the per-kernel table
-    hbm_kinds = ["fused"] if args.route == "fused" else ["pack", "hist"]
+    hbm_kinds = ["fused"] if args.route in ("fused", "spans") else ["pack", "hist"]
     narrow = sum(1 << _abi.KERNEL_KINDS.index(k) for k in hbm_kinds)
     eng.set_option(_abi.OPT_PROFILE, 0 if args.no_profile else narrow)
     eng.set_option(_abi.OPT_KEEP_CODES, 1 if args.route == "codes" else 0)
+    eng.set_option(_abi.OPT_FUSED_KERNEL, _abi.FUSED_LDG_SPANS if args.route == "spans" else _abi.FUSED_TMA_TILES)
     eng.set_products(products, ALN_LEN)
 
     def step_resident():
@@ -263,12 +264,14 @@ def run_ours(args):
                 if k in alg:
                     kern[k]["achieved_gbs"] = alg[k] / (ms / calls * 1e-3) / 1e9   # one launch covers the whole matrix
         hbm_kernels = {k: v for k, v in kern.items() if k in alg}
-        dom = max(hbm_kernels, key=lambda k: hbm_kernels[k]["ms_per_step"]) if hbm_kernels else ("fused" if args.route == "fused" else "pack")
+        dom = max(hbm_kernels, key=lambda k: hbm_kernels[k]["ms_per_step"]) if hbm_kernels else ("pack" if args.route == "codes" else "fused")
         achieved = kern[dom]["achieved_gbs"] if dom in kern else float("nan")
+        tiled = eng.tile_launches > 0          # SNPG_K_FUSED launches went to the TMA-tiled kernel
+        kernel_name = {"pack": "k_pack", "hist": "k_hist", "fused": "k_tile_hist" if tiled else "k_fused_hist"}[dom]
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-                traffic = json.load(fh).get(dom)
+                traffic = json.load(fh).get("tile" if (dom == "fused" and tiled) else dom)
         except Exception:
             pass
         boot_ms = sum(kern[k]["ms_per_step"] for k in ("bootstrap", "moments") if k in kern)
@@ -281,7 +284,7 @@ def run_ours(args):
                     "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),
             "route": args.route,
-            "roofline": {"kernel": {"pack": "k_pack", "hist": "k_hist", "fused": "k_fused_hist"}[dom], "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": kernel_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg[dom]},
             "kernels": kern,
@@ -309,8 +312,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket kernels with CUDA events (no roofline block)")
-    ap.add_argument("--route", default="fused", choices=["fused", "codes"],
-                    help="histogram route: fused kernel (default) or K1 pack + K2 hist over a kept code matrix")
+    ap.add_argument("--route", default="fused", choices=["fused", "spans", "codes"],
+                    help="histogram route: fused TMA-tiled kernel (default), fused vector-load kernel, or K1 pack + K2 hist "
+                         "over a kept code matrix")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -126,6 +126,14 @@ int snpg_codon_strings(snpg_ctx *ctx, int slot, int product, int64_t codon, uint
  * time is accumulated (snpg_get_profile).  Each pair of events costs a few
  * microseconds of stream time, so time whole jobs with a narrow mask. */
 #define SNPG_OPT_PROFILE 2
+/* SNPG_OPT_FUSED_KERNEL (default SNPG_FUSED_TMA_TILES): which kernel builds the histograms when no
+ * code matrix is kept.  TMA_TILES: persistent CTAs, frame-aligned 192-byte x 128-row TMA tensor
+ * loads into a shared-memory ring, one lane per group of four codons.  LDG_SPANS: one thread per
+ * 16-byte column span with vector loads (the round-1 kernel; also taken when a tensor map cannot
+ * describe the buffer).  Both give identical histograms. */
+#define SNPG_OPT_FUSED_KERNEL 4
+#define SNPG_FUSED_TMA_TILES 0
+#define SNPG_FUSED_LDG_SPANS 1
 int snpg_set_option(snpg_ctx *ctx, int option, int64_t value);
 
 /* ---- test hooks for the bit-exact checks ---------------------------------
@@ -227,6 +235,9 @@ int snpg_test_philox(snpg_ctx *ctx, const uint32_t *ctr4, const uint32_t *key2, 
 
 /* Kernel launches issued by this ctx since creation (bench.py's gpu_launches). */
 int64_t snpg_launch_count(const snpg_ctx *ctx);
+/* Of those, launches of the TMA-tiled histogram kernel (0 means every fused histogram went
+ * through the vector-load kernel: option, or a buffer a tensor map cannot describe). */
+int64_t snpg_tile_launch_count(const snpg_ctx *ctx);
 
 #ifdef __cplusplus
 }

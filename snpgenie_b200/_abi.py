@@ -13,7 +13,8 @@ LIB_PATH = os.path.join(_HERE, "libsnpgenie_cuda.so")
 
 OK, E_ARG, E_STATE, E_INPUT, E_CUDA, E_NOMEM = 0, -1, -2, -3, -4, -5
 CODE_UNDEF, CODE_OTHER, HIST_BINS = 64, 65, 66
-OPT_KEEP_CODES, OPT_PROFILE, OPT_SITE_COUNTS = 1, 2, 3
+OPT_KEEP_CODES, OPT_PROFILE, OPT_SITE_COUNTS, OPT_FUSED_KERNEL = 1, 2, 3, 4
+FUSED_TMA_TILES, FUSED_LDG_SPANS = 0, 1
 KERNEL_KINDS = ("pack", "hist", "stats", "sums", "bootstrap", "moments", "window", "other", "fused", "sites")
 
 if not os.path.exists(LIB_PATH):
@@ -62,6 +63,7 @@ SIGNATURES = {
     "snpg_rep_moments_device": (C.c_int, [_ctx, C.c_void_p, C.c_int64, C.c_int64, _f64p]),
     "snpg_test_philox": (C.c_int, [_ctx, _u32p, _u32p, _u32p]),
     "snpg_launch_count": (C.c_int64, [_ctx]),
+    "snpg_tile_launch_count": (C.c_int64, [_ctx]),
     "snpg_set_stream": (C.c_int, [_ctx, C.c_void_p]),
     "snpg_get_profile": (C.c_int, [_ctx, _f64p, _i64p, C.c_int]),
 }

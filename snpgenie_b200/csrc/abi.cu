@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -73,6 +74,12 @@ struct snpg_ctx {
     int64_t n_irr = 0;                    // codons the span runs cannot express
     DevBuf d_runs, d_regular, d_irr_map, d_irr_idx, d_cons, d_cons_code, d_cons_key;
     DevBuf t_codes, t_hist, t_other;      // irregular codons: compact K1+K2 scratch
+    // TMA-tiled variant of the fused path: frame-aligned tiles of <= 64 codons over the regular codons
+    DevBuf d_tiles;
+    int64_t n_tiles = 0;
+    int fused_kernel = SNPG_FUSED_TMA_TILES;
+    int n_sms = 148;
+    int tma_l2_promotion = 2;             // CU_TENSOR_MAP_L2_PROMOTION_L2_128B (SNPG_TMA_L2PROMO overrides: 0..3)
     // groups
     Group groups[SNPG_MAX_GROUPS];
     // FASTA slots: pinned host copies [n][len] read by snpg_read_fasta
@@ -83,6 +90,7 @@ struct snpg_ctx {
     int64_t max_codons_local = 0, max_codons_full = 0;
     DevBuf staging[2], s_stats, s_poly, s_nda, s_ndb, s_cmp, s_cons, s_sums, s_rep, s_se, s_misc, s_in;
     int64_t launches = 0;
+    int64_t tile_launches = 0;      // launches of k_tile_hist (the rest of SNPG_K_FUSED went to k_fused_hist)
     uint32_t call_id = 0;
     // optional per-kernel timing (CUDA events on the launch stream)
     uint32_t profile_mask = 0;      // bit k set: bracket launches of kernel kind k with timing events
@@ -232,8 +240,16 @@ int pack_block(snpg_ctx *ctx, Group &g, const uint8_t *d_block, int64_t pitch, i
         }
         {
             Launch l(ctx, SNPG_K_FUSED);
-            launch_fused_hist(d_block, pitch, rows, ctx->d_cons.as<uint8_t>(), ctx->n_spans, ctx->d_runs.as<SpanRun>(),
-                              ctx->d_cons_code.as<uint8_t>(), g.hist.as<uint32_t>(), omin, omax, ctx->stream);
+            alignas(64) unsigned char tmap[128];
+            if (ctx->fused_kernel == SNPG_FUSED_TMA_TILES && ctx->n_tiles > 0 &&
+                make_tile_tensor_map(tmap, d_block, pitch, rows, row_bytes, ctx->tma_l2_promotion)) {
+                CU(ctx, launch_tile_hist(tmap, rows, ctx->d_cons.as<uint8_t>(), ctx->d_tiles.as<CodonTile>(), ctx->n_tiles, ctx->n_sms,
+                                         g.hist.as<uint32_t>(), omin, omax, ctx->stream));
+                ctx->tile_launches++;
+            } else {
+                launch_fused_hist(d_block, pitch, rows, ctx->d_cons.as<uint8_t>(), ctx->n_spans, ctx->d_runs.as<SpanRun>(),
+                                  ctx->d_cons_code.as<uint8_t>(), g.hist.as<uint32_t>(), omin, omax, ctx->stream);
+            }
         }
         if (ctx->n_irr) {
             Launch l(ctx, SNPG_K_PACK);
@@ -311,6 +327,8 @@ int snpg_create(snpg_ctx **out, int device, uint64_t seed) {
         if ((e = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
         if ((e = cudaEventCreateWithFlags(&ctx->ev_packed[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     }
+    if (cudaDeviceGetAttribute(&ctx->n_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || ctx->n_sms <= 0) ctx->n_sms = 148;
+    if (const char *v = getenv("SNPG_TMA_L2PROMO")) ctx->tma_l2_promotion = atoi(v);
     std::vector<double> tab(128 + 8192);
     build_tables(tab.data(), tab.data() + 128);
     if ((e = ctx->d_tables.ensure(sizeof(double) * tab.size())) != cudaSuccess) return bail("cudaMalloc(tables)", e);
@@ -328,7 +346,7 @@ void snpg_destroy(snpg_ctx *ctx) {
     for (auto &g : ctx->groups) { g.codes.release(); g.hist.release(); g.other.release(); g.sites.release(); }
     for (auto &h : ctx->host_aln) if (h.p) cudaFreeHost(h.p);
     DevBuf *bufs[] = {&ctx->d_map, &ctx->d_local_ofs, &ctx->d_full_ofs, &ctx->d_tables, &ctx->staging[0], &ctx->staging[1],
-                      &ctx->d_runs, &ctx->d_regular, &ctx->d_irr_map, &ctx->d_irr_idx, &ctx->d_cons, &ctx->d_cons_code, &ctx->d_cons_key, &ctx->t_codes, &ctx->t_hist,
+                      &ctx->d_runs, &ctx->d_tiles, &ctx->d_regular, &ctx->d_irr_map, &ctx->d_irr_idx, &ctx->d_cons, &ctx->d_cons_code, &ctx->d_cons_key, &ctx->t_codes, &ctx->t_hist,
                       &ctx->t_other,
                       &ctx->s_stats, &ctx->s_poly, &ctx->s_nda, &ctx->s_ndb, &ctx->s_cmp, &ctx->s_cons, &ctx->s_sums,
                       &ctx->s_rep, &ctx->s_se, &ctx->s_misc, &ctx->s_in, &ctx->s_vals, &ctx->d_order_local, &ctx->d_order_full};
@@ -350,6 +368,11 @@ int snpg_set_option(snpg_ctx *ctx, int option, int64_t value) {
     if (option == SNPG_OPT_SITE_COUNTS) {
         NEED(ctx, ctx->n_products == 0, SNPG_E_STATE, "SNPG_OPT_SITE_COUNTS must be set before snpg_set_products");
         ctx->site_counts = value != 0;
+        return SNPG_OK;
+    }
+    if (option == SNPG_OPT_FUSED_KERNEL) {
+        NEED(ctx, value == SNPG_FUSED_TMA_TILES || value == SNPG_FUSED_LDG_SPANS, SNPG_E_ARG, "unknown fused kernel %lld", (long long)value);
+        ctx->fused_kernel = (int)value;
         return SNPG_OK;
     }
     if (option == SNPG_OPT_PROFILE) { ctx->profile_mask = value < 0 ? 0xFFFFFFFFu : (uint32_t)value; return SNPG_OK; }
@@ -472,6 +495,44 @@ int snpg_set_products(snpg_ctx *ctx, int n_products, const int64_t *seg_ofs, con
             }
         }
         ctx->n_irr = (int64_t)irr_map.size();
+        // TMA tiles: maximal runs of regular codons whose bytes advance by exactly one codon per codon index
+        // ('+': ascending columns, '-': descending), cut into pieces of <= 64 codons in ascending-address order.
+        {
+            std::vector<CodonTile> tiles;
+            auto emit = [&](int64_t c_first, int64_t len, int64_t q_first, int minus) {
+                // '+': slot j of the run is codon c_first + j at byte q_first + 3j;
+                // '-': the lowest address holds the LAST codon of the run and indices fall as addresses rise
+                const int64_t q_low = minus ? q_first - 3 * (len - 1) : q_first;
+                const int64_t c_low = minus ? c_first + len - 1 : c_first;
+                const int dir = minus ? -1 : 1;
+                for (int64_t j = 0; j < len; j += 64) {
+                    CodonTile t;
+                    t.x0 = (int32_t)(q_low + 3 * j);
+                    t.codon0 = (int32_t)(c_low + dir * j);
+                    t.ncodons = (int16_t)std::min<int64_t>(64, len - j);
+                    t.dir = (int8_t)dir;
+                    t.minus = (int8_t)minus;
+                    t.pad = 0;
+                    tiles.push_back(t);
+                }
+            };
+            int64_t run_c = -1, run_len = 0, run_q = 0, run_last_q = 0;
+            int run_minus = 0;
+            for (size_t c = 0; c < local.size(); c++) {
+                if (!regular[c]) { if (run_len) emit(run_c, run_len, run_q, run_minus); run_len = 0; continue; }
+                const CodonMap &m = local[c];
+                const int64_t q = (m.minus ? m.p2 : m.p0) + shift;
+                if (run_len && run_minus == m.minus && q == run_last_q + (m.minus ? -3 : 3)) { run_len++; run_last_q = q; continue; }
+                if (run_len) emit(run_c, run_len, run_q, run_minus);
+                run_c = (int64_t)c; run_len = 1; run_q = q; run_last_q = q; run_minus = m.minus;
+            }
+            if (run_len) emit(run_c, run_len, run_q, run_minus);
+            ctx->n_tiles = (int64_t)tiles.size();
+            if (!tiles.empty()) {
+                CU(ctx, ctx->d_tiles.ensure(sizeof(CodonTile) * tiles.size()));
+                CU(ctx, cudaMemcpy(ctx->d_tiles.p, tiles.data(), sizeof(CodonTile) * tiles.size(), cudaMemcpyHostToDevice));
+            }
+        }
         CU(ctx, ctx->d_runs.ensure(sizeof(SpanRun) * runs.size()));
         CU(ctx, ctx->d_regular.ensure(regular.size()));
         CU(ctx, ctx->d_cons.ensure((size_t)(n_spans * 16 + 128)));
@@ -1010,6 +1071,7 @@ int snpg_test_philox(snpg_ctx *ctx, const uint32_t *ctr4, const uint32_t *key2, 
 }
 
 int64_t snpg_launch_count(const snpg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int64_t snpg_tile_launch_count(const snpg_ctx *ctx) { return ctx ? ctx->tile_launches : 0; }
 
 int snpg_set_stream(snpg_ctx *ctx, void *cuda_stream) {
     if (!ctx) return SNPG_E_ARG;

@@ -13,13 +13,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "snpg_device.cuh"
 #include "snpg_internal.h"
 
 namespace snpg {
 
 namespace {
-
-constexpr unsigned kFull = 0xFFFFFFFFu;
 
 __device__ __forceinline__ uint4 ld_stream_v4(const uint4 *p) {
     uint4 r;
@@ -37,28 +36,6 @@ __device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
     return v;
-}
-
-// ---------------------------------------------------------------------------
-// Residue classification.  Normalisation follows the reference ingest: uc, then
-// U->T (snpgenie_within_group.pl:231-232); on the '-' strand the residue is
-// first complemented with tr/ACGT/TGCA/ exactly as fasta2revcom.pl:77-79 does
-// (so U is NOT complemented there and then becomes T).
-// class: 0..3 = A,C,G,T; 4 = undefined (N or '-'; wg:493,498); 5 = other.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ uint8_t norm_char(uint8_t c, int minus) {
-    if (c >= 'a' && c <= 'z') c -= 32;
-    if (minus) {
-        if (c == 'A') c = 'T';
-        else if (c == 'C') c = 'G';
-        else if (c == 'G') c = 'C';
-        else if (c == 'T') c = 'A';
-    }
-    if (c == 'U') c = 'T';
-    return c;
-}
-__device__ __forceinline__ uint8_t class_of(uint8_t n) {
-    return n == 'A' ? 0 : n == 'C' ? 1 : n == 'G' ? 2 : n == 'T' ? 3 : (n == 'N' || n == '-') ? 4 : 5;
 }
 
 // ---------------------------------------------------------------------------

@@ -24,6 +24,12 @@ struct CodonMap { int32_t p0, p1, p2, minus; };
 constexpr int kSpanRuns = 4;
 struct SpanRun { int32_t codon0; int8_t off, cnt, dir, minus; };
 
+// Fused path, TMA-tiled variant (tile_hist.cu): up to 64 consecutive codons of one product that occupy
+// 3*ncodons contiguous alignment bytes starting at byte column x0 (relative to the staged block's first
+// column; any alignment).  The codon in the j-th 3-byte slot (ascending address) has index codon0 + dir*j.
+constexpr int kTileRows = 128;     // rows per TMA box
+struct CodonTile { int32_t x0, codon0; int16_t ncodons; int8_t dir, minus; int32_t pad; };
+
 // Device view of one loaded group, offset to the first codon a kernel works on.
 struct GroupView {
     const uint32_t *hist;        // [codons][66]
@@ -63,6 +69,13 @@ void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, cons
                        uint32_t *d_other_max, cudaStream_t stream);
 void launch_fused_fixup(const uint8_t *d_cons_code, const uint32_t *d_cons_key, const uint8_t *d_regular, int64_t n_codons,
                         uint32_t n_rows, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max, cudaStream_t stream);
+// TMA-tiled variant of launch_fused_hist (same contract: counts of the non-consensus codons of the regular
+// codons are added to hist).  make_tile_tensor_map fills a 128-byte CUtensorMap (64-byte aligned storage)
+// for a block of rows; it returns false when the geometry cannot be expressed (base or pitch not 16-byte
+// aligned) or the driver lacks the encoder -- the caller then takes launch_fused_hist.
+bool make_tile_tensor_map(void *out_map, const uint8_t *d_aln, int64_t pitch, int64_t rows, int64_t row_bytes, int l2_promotion);
+cudaError_t launch_tile_hist(const void *tensor_map, int64_t n_rows, const uint8_t *d_cons, const CodonTile *d_tiles, int64_t n_tiles,
+                             int n_sms, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max, cudaStream_t stream);
 void launch_scatter_irregular(const uint32_t *d_tmp_hist, const uint32_t *d_tmp_min, const uint32_t *d_tmp_max,
                               const int32_t *d_idx, int64_t n_irr, uint32_t *d_hist, uint32_t *d_other_min,
                               uint32_t *d_other_max, cudaStream_t stream);

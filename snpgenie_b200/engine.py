@@ -73,6 +73,11 @@ class Engine:
     def launches(self) -> int:
         return int(_abi.lib.snpg_launch_count(self._ctx))
 
+    @property
+    def tile_launches(self) -> int:
+        """Launches of the TMA-tiled histogram kernel (the default fused route)."""
+        return int(_abi.lib.snpg_tile_launch_count(self._ctx))
+
     def set_option(self, option: int, value: int):
         self._ck(_abi.lib.snpg_set_option(self._ctx, option, value))
 

@@ -31,14 +31,18 @@ def eng():
     e.close()
 
 
-@pytest.fixture(scope="module", params=["codes", "fused"])
+@pytest.fixture(scope="module", params=["codes", "fused", "spans"])
 def eng2(request):
-    """Both histogram routes: K1 pack + K2 hist over the kept code matrix, and the fused kernel."""
+    """All histogram routes: K1 pack + K2 hist over the kept code matrix, the fused TMA-tiled kernel
+    (the default) and the fused vector-load kernel."""
     from snpgenie_b200 import _abi
     from snpgenie_b200.engine import Engine
     e = Engine(device=0, seed=1234)
     e.has_codes = request.param == "codes"
+    e.route = request.param
     e.set_option(_abi.OPT_KEEP_CODES, 1 if e.has_codes else 0)
+    if request.param == "spans":
+        e.set_option(_abi.OPT_FUSED_KERNEL, _abi.FUSED_LDG_SPANS)
     yield e
     e.close()
 
@@ -57,7 +61,10 @@ def test_codon_indices_and_histograms_bit_exact(eng2, case, minus):
     d, aln, _, _ = refio.within_case(case)
     products = hostio.read_gtf_products(os.path.join(d, "cds.gtf"), include_minus=minus)
     eng.set_products(products, aln.shape[1])
+    before = eng.tile_launches
     eng.load_group(0, aln)
+    # the default fused route must really be the TMA-tiled kernel, the other two must not touch it
+    assert (eng.tile_launches > before) == (eng.route == "fused")
     for i, p in enumerate(products):
         raw, codes = _oracle_product(aln, p)
         if eng.has_codes:
@@ -783,8 +790,10 @@ def test_random_annotations_both_routes(seed):
     keep_cols = rng.random(L) < 0.6                            # conserved columns exercise the fast path
     aln[:, keep_cols] = aln[0, keep_cols]
     sorted_prods = [hostio.Product(p.name, p.strand, sorted(p.starts), [e for _, e in sorted(zip(p.starts, p.stops))]) for p in prods]
-    for keep in (True, False):
+    from snpgenie_b200 import _abi
+    for keep, fused in ((True, 0), (False, _abi.FUSED_TMA_TILES), (False, _abi.FUSED_LDG_SPANS)):
         with Engine(device=0, keep_codes=keep) as e:
+            e.set_option(_abi.OPT_FUSED_KERNEL, fused)
             e.set_products(prods, L)
             e.load_group(0, aln)
             for i, p in enumerate(sorted_prods):

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small driver for ncu captures: a few device-resident steps of the config-2 hot path.
 
-    python tools/prof_step.py [--steps 3] [--route fused|codes] [--n 10000]
+    python tools/prof_step.py [--steps 3] [--route fused|spans|codes] [--n 10000]
 """
 import argparse
 import os
@@ -27,8 +27,9 @@ d = torch.zeros((a.n, pitch), dtype=torch.uint8, device="cuda:0")
 d[:, :L] = torch.from_numpy(aln).cuda()
 with Engine(device=0) as eng:
     eng.set_option(_abi.OPT_KEEP_CODES, 1 if a.route == "codes" else 0)
+    eng.set_option(_abi.OPT_FUSED_KERNEL, _abi.FUSED_LDG_SPANS if a.route == "spans" else _abi.FUSED_TMA_TILES)
     eng.set_products(products, L)
     for _ in range(a.steps):
         eng.load_group_ptr(0, d.data_ptr(), a.n, L, pitch, device=True)
         sums, se = eng.within_all(0, B=a.boot)
-    print("ok", sums[0], se[0][:3])
+    print("ok", sums[0], se[0][:3], "tile launches", eng.tile_launches)
