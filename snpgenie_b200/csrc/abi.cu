@@ -75,7 +75,7 @@ struct snpg_ctx {
     DevBuf d_runs, d_regular, d_irr_map, d_irr_idx, d_cons, d_cons_code, d_cons_key;
     DevBuf t_codes, t_hist, t_other;      // irregular codons: compact K1+K2 scratch
     // TMA-tiled variant of the fused path: frame-aligned tiles of <= 64 codons over the regular codons
-    DevBuf d_tiles;
+    DevBuf d_tiles, d_sched;              // d_sched: the tile kernel's chunk counter and finished-CTA counter
     int64_t n_tiles = 0;
     int fused_kernel = SNPG_FUSED_TMA_TILES;
     int n_sms = 148;
@@ -244,7 +244,7 @@ int pack_block(snpg_ctx *ctx, Group &g, const uint8_t *d_block, int64_t pitch, i
             if (ctx->fused_kernel == SNPG_FUSED_TMA_TILES && ctx->n_tiles > 0 &&
                 make_tile_tensor_map(tmap, d_block, pitch, rows, row_bytes, ctx->tma_l2_promotion)) {
                 CU(ctx, launch_tile_hist(tmap, rows, ctx->d_cons.as<uint8_t>(), ctx->d_tiles.as<CodonTile>(), ctx->n_tiles, ctx->n_sms,
-                                         g.hist.as<uint32_t>(), omin, omax, ctx->stream));
+                                         ctx->d_sched.as<uint32_t>(), g.hist.as<uint32_t>(), omin, omax, ctx->stream));
                 ctx->tile_launches++;
             } else {
                 launch_fused_hist(d_block, pitch, rows, ctx->d_cons.as<uint8_t>(), ctx->n_spans, ctx->d_runs.as<SpanRun>(),
@@ -329,6 +329,8 @@ int snpg_create(snpg_ctx **out, int device, uint64_t seed) {
     }
     if (cudaDeviceGetAttribute(&ctx->n_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || ctx->n_sms <= 0) ctx->n_sms = 148;
     if (const char *v = getenv("SNPG_TMA_L2PROMO")) ctx->tma_l2_promotion = atoi(v);
+    if ((e = ctx->d_sched.ensure(2 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(sched)", e);
+    if ((e = cudaMemset(ctx->d_sched.p, 0, 2 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset(sched)", e);
     std::vector<double> tab(128 + 8192);
     build_tables(tab.data(), tab.data() + 128);
     if ((e = ctx->d_tables.ensure(sizeof(double) * tab.size())) != cudaSuccess) return bail("cudaMalloc(tables)", e);
@@ -346,7 +348,7 @@ void snpg_destroy(snpg_ctx *ctx) {
     for (auto &g : ctx->groups) { g.codes.release(); g.hist.release(); g.other.release(); g.sites.release(); }
     for (auto &h : ctx->host_aln) if (h.p) cudaFreeHost(h.p);
     DevBuf *bufs[] = {&ctx->d_map, &ctx->d_local_ofs, &ctx->d_full_ofs, &ctx->d_tables, &ctx->staging[0], &ctx->staging[1],
-                      &ctx->d_runs, &ctx->d_tiles, &ctx->d_regular, &ctx->d_irr_map, &ctx->d_irr_idx, &ctx->d_cons, &ctx->d_cons_code, &ctx->d_cons_key, &ctx->t_codes, &ctx->t_hist,
+                      &ctx->d_runs, &ctx->d_tiles, &ctx->d_sched, &ctx->d_regular, &ctx->d_irr_map, &ctx->d_irr_idx, &ctx->d_cons, &ctx->d_cons_code, &ctx->d_cons_key, &ctx->t_codes, &ctx->t_hist,
                       &ctx->t_other,
                       &ctx->s_stats, &ctx->s_poly, &ctx->s_nda, &ctx->s_ndb, &ctx->s_cmp, &ctx->s_cons, &ctx->s_sums,
                       &ctx->s_rep, &ctx->s_se, &ctx->s_misc, &ctx->s_in, &ctx->s_vals, &ctx->d_order_local, &ctx->d_order_full};
@@ -535,12 +537,12 @@ int snpg_set_products(snpg_ctx *ctx, int n_products, const int64_t *seg_ofs, con
         }
         CU(ctx, ctx->d_runs.ensure(sizeof(SpanRun) * runs.size()));
         CU(ctx, ctx->d_regular.ensure(regular.size()));
-        CU(ctx, ctx->d_cons.ensure((size_t)(n_spans * 16 + 128)));
+        CU(ctx, ctx->d_cons.ensure((size_t)(n_spans * 16 + 512)));     // the tile kernel copies 208-byte windows of it
         CU(ctx, ctx->d_cons_code.ensure(regular.size()));
         CU(ctx, ctx->d_cons_key.ensure(sizeof(uint32_t) * regular.size()));
         CU(ctx, cudaMemcpy(ctx->d_runs.p, runs.data(), sizeof(SpanRun) * runs.size(), cudaMemcpyHostToDevice));
         CU(ctx, cudaMemcpy(ctx->d_regular.p, regular.data(), regular.size(), cudaMemcpyHostToDevice));
-        CU(ctx, cudaMemset(ctx->d_cons.p, 0, (size_t)(n_spans * 16 + 128)));
+        CU(ctx, cudaMemset(ctx->d_cons.p, 0, (size_t)(n_spans * 16 + 512)));
         if (ctx->n_irr) {
             CU(ctx, ctx->d_irr_map.ensure(sizeof(CodonMap) * irr_map.size()));
             CU(ctx, ctx->d_irr_idx.ensure(sizeof(int32_t) * irr_idx.size()));

@@ -74,8 +74,10 @@ void launch_fused_fixup(const uint8_t *d_cons_code, const uint32_t *d_cons_key, 
 // for a block of rows; it returns false when the geometry cannot be expressed (base or pitch not 16-byte
 // aligned) or the driver lacks the encoder -- the caller then takes launch_fused_hist.
 bool make_tile_tensor_map(void *out_map, const uint8_t *d_aln, int64_t pitch, int64_t rows, int64_t row_bytes, int l2_promotion);
+// d_sched: two zeroed u32 (chunk counter, finished CTAs) owned by the ctx; the kernel leaves them zeroed.
 cudaError_t launch_tile_hist(const void *tensor_map, int64_t n_rows, const uint8_t *d_cons, const CodonTile *d_tiles, int64_t n_tiles,
-                             int n_sms, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max, cudaStream_t stream);
+                             int n_sms, uint32_t *d_sched, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max,
+                             cudaStream_t stream);
 void launch_scatter_irregular(const uint32_t *d_tmp_hist, const uint32_t *d_tmp_min, const uint32_t *d_tmp_max,
                               const int32_t *d_idx, int64_t n_irr, uint32_t *d_hist, uint32_t *d_other_min,
                               uint32_t *d_other_max, cudaStream_t stream);
