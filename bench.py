@@ -179,7 +179,7 @@ def run_ours(args):
 
     products = synth.sars2_products()
     codons = sum(p.n_codons for p in products)
-    aln = synth.make_alignment(N_SEQS, ALN_LEN, products, SEED + 1000 * rank)
+    aln = synth.make_alignment(N_SEQS, ALN_LEN, products, SEED + 1000 * rank, p_poly=args.p_poly)
     pitch = (ALN_LEN + 127) // 128 * 128
     # pinned host copy (e2e input) and HBM-resident copy with a 128-B row pitch (value input)
     h_aln = torch.empty((N_SEQS, ALN_LEN), dtype=torch.uint8).pin_memory()
@@ -193,11 +193,11 @@ def run_ours(args):
     eng.set_stream(stream.cuda_stream)
     # timed passes bracket only the dominant HBM kernel with events (a pair costs ~3 us of stream time);
     # a separate untimed pass of the same steps brackets every launch for the per-kernel table
-    hbm_kinds = ["fused"] if args.route in ("fused", "spans") else ["pack", "hist"]
+    hbm_kinds = ["fused"] if args.route in ("fused", "tiles") else ["pack", "hist"]
     narrow = sum(1 << _abi.KERNEL_KINDS.index(k) for k in hbm_kinds)
     eng.set_option(_abi.OPT_PROFILE, 0 if args.no_profile else narrow)
     eng.set_option(_abi.OPT_KEEP_CODES, 1 if args.route == "codes" else 0)
-    eng.set_option(_abi.OPT_FUSED_KERNEL, _abi.FUSED_LDG_SPANS if args.route == "spans" else _abi.FUSED_TMA_TILES)
+    eng.set_option(_abi.OPT_FUSED_KERNEL, _abi.FUSED_TMA_TILES if args.route == "tiles" else _abi.FUSED_LDG_SPANS)
     eng.set_products(products, ALN_LEN)
 
     def step_resident():
@@ -279,7 +279,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8 codon codes / u32 histograms / f64 statistics", "data": "synthetic",
-            "config": workload_config(world),
+            "config": dict(workload_config(world), **({} if args.p_poly == 0.3 else {"p_poly": args.p_poly, "side_experiment": True})),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(N_SEQS * ALN_LEN), "d2h_bytes_per_step": int(len(products) * 10 * 8),
                     "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),
@@ -311,9 +311,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--p-poly", type=float, default=0.3,
+                    help="fraction of polymorphic codon columns in the synthetic alignment (SURVEY.md 8d: 0.3; "
+                         "other values are side experiments, never the bench line)")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket kernels with CUDA events (no roofline block)")
-    ap.add_argument("--route", default="fused", choices=["fused", "spans", "codes"],
-                    help="histogram route: fused TMA-tiled kernel (default), fused vector-load kernel, or K1 pack + K2 hist "
+    ap.add_argument("--route", default="fused", choices=["fused", "tiles", "codes"],
+                    help="histogram route: fused vector-load kernel (default), fused TMA-tiled kernel, or K1 pack + K2 hist "
                          "over a kept code matrix")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -126,11 +126,12 @@ int snpg_codon_strings(snpg_ctx *ctx, int slot, int product, int64_t codon, uint
  * time is accumulated (snpg_get_profile).  Each pair of events costs a few
  * microseconds of stream time, so time whole jobs with a narrow mask. */
 #define SNPG_OPT_PROFILE 2
-/* SNPG_OPT_FUSED_KERNEL (default SNPG_FUSED_TMA_TILES): which kernel builds the histograms when no
- * code matrix is kept.  TMA_TILES: persistent CTAs, frame-aligned 192-byte x 128-row TMA tensor
- * loads into a shared-memory ring, one lane per group of four codons.  LDG_SPANS: one thread per
- * 16-byte column span with vector loads (the round-1 kernel; also taken when a tensor map cannot
- * describe the buffer).  Both give identical histograms. */
+/* SNPG_OPT_FUSED_KERNEL (default SNPG_FUSED_LDG_SPANS): which kernel builds the histograms when no
+ * code matrix is kept.  LDG_SPANS: one thread per 16-byte column span with 128-bit loads (the
+ * fastest measured on every diversity tried, see profiles/).  TMA_TILES: persistent CTAs,
+ * frame-aligned 208-byte x 128-row TMA tensor loads into a shared-memory ring, one lane per group
+ * of four codons, chunks claimed from a global counter; falls back to LDG_SPANS when a tensor map
+ * cannot describe the buffer.  Both give identical histograms. */
 #define SNPG_OPT_FUSED_KERNEL 4
 #define SNPG_FUSED_TMA_TILES 0
 #define SNPG_FUSED_LDG_SPANS 1

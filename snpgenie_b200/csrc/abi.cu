@@ -72,12 +72,12 @@ struct snpg_ctx {
     // fused path (no code matrix): 16-byte column spans starting at base_al
     int64_t base_al = 0, n_spans = 0;     // base_al = col_lo rounded down to 16
     int64_t n_irr = 0;                    // codons the span runs cannot express
-    DevBuf d_runs, d_regular, d_irr_map, d_irr_idx, d_cons, d_cons_code, d_cons_key;
+    DevBuf d_runs, d_regular, d_irr_map, d_irr_idx, d_cons, d_alt, d_cons_code, d_cons_key;
     DevBuf t_codes, t_hist, t_other;      // irregular codons: compact K1+K2 scratch
     // TMA-tiled variant of the fused path: frame-aligned tiles of <= 64 codons over the regular codons
     DevBuf d_tiles, d_sched;              // d_sched: the tile kernel's chunk counter and finished-CTA counter
     int64_t n_tiles = 0;
-    int fused_kernel = SNPG_FUSED_TMA_TILES;
+    int fused_kernel = SNPG_FUSED_LDG_SPANS;
     int n_sms = 148;
     int tma_l2_promotion = 2;             // CU_TENSOR_MAP_L2_PROMOTION_L2_128B (SNPG_TMA_L2PROMO overrides: 0..3)
     // groups
@@ -219,10 +219,10 @@ int prepare_group(snpg_ctx *ctx, Group &g, uint64_t n_seqs) {
 int pack_block(snpg_ctx *ctx, Group &g, const uint8_t *d_block, int64_t pitch, int64_t rows, int64_t r0, int64_t row_bytes) {
     uint32_t *omin = g.other.as<uint32_t>(), *omax = g.other.as<uint32_t>() + ctx->shard_count;
     if (r0 == 0 && (!ctx->keep_codes || ctx->site_counts)) {
-        // consensus row every row is compared with: majority vote over the group's first rows
+        // the rows every row is compared with: per-column plurality and per-span runner-up over the group's first rows
         Launch l(ctx, SNPG_K_OTHER);
-        launch_vote_consensus(d_block, pitch, (int)std::min<int64_t>(rows, 16), row_bytes, ctx->n_spans * 16 + 16, ctx->d_cons.as<uint8_t>(),
-                              ctx->stream);
+        launch_vote_refs(d_block, pitch, (int)std::min<int64_t>(rows, 32), ctx->n_spans, ctx->d_cons.as<uint8_t>(), ctx->d_alt.as<uint32_t>(),
+                         ctx->stream);
     }
     if (ctx->site_counts) {
         Launch l(ctx, SNPG_K_SITES);
@@ -247,7 +247,7 @@ int pack_block(snpg_ctx *ctx, Group &g, const uint8_t *d_block, int64_t pitch, i
                                          ctx->d_sched.as<uint32_t>(), g.hist.as<uint32_t>(), omin, omax, ctx->stream));
                 ctx->tile_launches++;
             } else {
-                launch_fused_hist(d_block, pitch, rows, ctx->d_cons.as<uint8_t>(), ctx->n_spans, ctx->d_runs.as<SpanRun>(),
+                launch_fused_hist(d_block, pitch, rows, ctx->d_cons.as<uint8_t>(), ctx->d_alt.as<uint32_t>(), ctx->n_spans, ctx->d_runs.as<SpanRun>(),
                                   ctx->d_cons_code.as<uint8_t>(), g.hist.as<uint32_t>(), omin, omax, ctx->stream);
             }
         }
@@ -348,7 +348,7 @@ void snpg_destroy(snpg_ctx *ctx) {
     for (auto &g : ctx->groups) { g.codes.release(); g.hist.release(); g.other.release(); g.sites.release(); }
     for (auto &h : ctx->host_aln) if (h.p) cudaFreeHost(h.p);
     DevBuf *bufs[] = {&ctx->d_map, &ctx->d_local_ofs, &ctx->d_full_ofs, &ctx->d_tables, &ctx->staging[0], &ctx->staging[1],
-                      &ctx->d_runs, &ctx->d_tiles, &ctx->d_sched, &ctx->d_regular, &ctx->d_irr_map, &ctx->d_irr_idx, &ctx->d_cons, &ctx->d_cons_code, &ctx->d_cons_key, &ctx->t_codes, &ctx->t_hist,
+                      &ctx->d_runs, &ctx->d_tiles, &ctx->d_sched, &ctx->d_regular, &ctx->d_irr_map, &ctx->d_irr_idx, &ctx->d_cons, &ctx->d_alt, &ctx->d_cons_code, &ctx->d_cons_key, &ctx->t_codes, &ctx->t_hist,
                       &ctx->t_other,
                       &ctx->s_stats, &ctx->s_poly, &ctx->s_nda, &ctx->s_ndb, &ctx->s_cmp, &ctx->s_cons, &ctx->s_sums,
                       &ctx->s_rep, &ctx->s_se, &ctx->s_misc, &ctx->s_in, &ctx->s_vals, &ctx->d_order_local, &ctx->d_order_full};
@@ -538,6 +538,7 @@ int snpg_set_products(snpg_ctx *ctx, int n_products, const int64_t *seg_ofs, con
         CU(ctx, ctx->d_runs.ensure(sizeof(SpanRun) * runs.size()));
         CU(ctx, ctx->d_regular.ensure(regular.size()));
         CU(ctx, ctx->d_cons.ensure((size_t)(n_spans * 16 + 512)));     // the tile kernel copies 208-byte windows of it
+        CU(ctx, ctx->d_alt.ensure(sizeof(uint32_t) * kAltWords * (size_t)std::max<int64_t>(1, n_spans)));
         CU(ctx, ctx->d_cons_code.ensure(regular.size()));
         CU(ctx, ctx->d_cons_key.ensure(sizeof(uint32_t) * regular.size()));
         CU(ctx, cudaMemcpy(ctx->d_runs.p, runs.data(), sizeof(SpanRun) * runs.size(), cudaMemcpyHostToDevice));

@@ -13,6 +13,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 #include "snpg_device.cuh"
 #include "snpg_internal.h"
 
@@ -211,7 +213,7 @@ __device__ __forceinline__ uint32_t differing_bytes(uint32_t d) {     // 4-bit m
 __device__ __forceinline__ void fused_decode(const uint32_t *e, const uint8_t *__restrict__ cons,
                                              const SpanRun *__restrict__ runs, uint32_t *__restrict__ hist,
                                              uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max,
-                                             const uint8_t (*lut_cls)[256], const uint8_t (*lut_chr)[256])
+                                             const uint8_t (*lut_cls)[256], const uint8_t (*lut_chr)[256], uint32_t weight = 1u)
 {
     const uint32_t sp = e[5];
     const uint4 c = __ldg(reinterpret_cast<const uint4 *>(cons + (size_t)sp * 16));
@@ -246,7 +248,7 @@ __device__ __forceinline__ void fused_decode(const uint32_t *e, const uint8_t *_
                     atomicMax(&other_max[cidx], key);
                 }
             }
-            atomicAdd(&hist[(size_t)cidx * kHistBins + code], 1u);
+            atomicAdd(&hist[(size_t)cidx * kHistBins + code], weight);
         }
     }
 }
@@ -256,8 +258,8 @@ constexpr int kFusedEntryWords = 7;  // 5 raw + span + pad: odd stride, conflict
 
 __global__ void __launch_bounds__(kFusedWarps * 32)
 k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, int64_t n_rows, const uint8_t *__restrict__ cons,
-             int64_t n_spans, const SpanRun *__restrict__ runs, uint32_t *__restrict__ hist, uint32_t *__restrict__ other_min,
-             uint32_t *__restrict__ other_max)
+             const uint32_t *__restrict__ alt, int64_t n_spans, const SpanRun *__restrict__ runs, uint32_t *__restrict__ hist,
+             uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max, int rows_per_warp)
 {
     __shared__ uint8_t lut_chr[2][256];
     __shared__ uint8_t lut_cls[2][256];
@@ -277,10 +279,15 @@ k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, int64_t n_rows, con
     const int64_t span = (int64_t)blockIdx.x * 32 + lane;
     const bool live = span < n_spans;
     const uint32_t sp = (uint32_t)(live ? span : n_spans - 1);
-    const int64_t row_begin = ((int64_t)blockIdx.y * kFusedWarps + warp) * kFusedRowsPerWarp;
-    const int64_t row_end = min(n_rows, row_begin + kFusedRowsPerWarp);
+    const int64_t row_begin = ((int64_t)blockIdx.y * kFusedWarps + warp) * rows_per_warp;
+    const int64_t row_end = min(n_rows, row_begin + rows_per_warp);
     const uint4 c = *reinterpret_cast<const uint4 *>(cons + (int64_t)sp * 16);
     const uint32_t c4 = *reinterpret_cast<const uint32_t *>(cons + (int64_t)sp * 16 + 16);
+    // the span's second reference: its most common non-consensus bytes among the sampled rows (the consensus
+    // itself when the sample had none).  Rows equal to it are only counted here and decoded once, weighted.
+    const uint4 a = *reinterpret_cast<const uint4 *>(alt + (int64_t)sp * kAltWords);
+    const uint32_t a4 = alt[(int64_t)sp * kAltWords + 4];
+    uint32_t n_alt = 0;
     const uint8_t *p = aln + (int64_t)sp * 16 + row_begin * pitch;
 
     for (int64_t r = row_begin; r < row_end; r += kFusedUnroll, p += kFusedUnroll * pitch) {
@@ -299,7 +306,11 @@ k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, int64_t n_rows, con
             const uint32_t nxt = __shfl_down_sync(kFull, v[u].x, 1);
             const uint32_t v4 = lane == 31 ? tail[u] : nxt;
             const uint32_t d = (v[u].x ^ c.x) | (v[u].y ^ c.y) | (v[u].z ^ c.z) | (v[u].w ^ c.w) | ((v4 ^ c4) & 0xFFFFu);
-            const bool differs = d != 0 && live && r + u < row_end;
+            const uint32_t da = (v[u].x ^ a.x) | (v[u].y ^ a.y) | (v[u].z ^ a.z) | (v[u].w ^ a.w) | ((v4 ^ a4) & 0xFFFFu);
+            const bool real = live && r + u < row_end;
+            const bool is_alt = da == 0 && d != 0 && real;
+            n_alt += is_alt ? 1u : 0u;
+            const bool differs = d != 0 && da != 0 && real;
             const unsigned bal = __ballot_sync(kFull, differs);
             if (differs) {   // park the bytes; a full warp decodes 32 parked spans at a time
                 uint32_t *e = queue + ((q_head + q_count + __popc(bal & lt)) & (kFusedQueue - 1)) * kFusedEntryWords;
@@ -322,44 +333,73 @@ k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, int64_t n_rows, con
     if ((uint32_t)lane < q_count)
         fused_decode(queue + ((q_head + lane) & (kFusedQueue - 1)) * kFusedEntryWords, cons, runs, hist, other_min, other_max,
                      lut_cls, lut_chr);
+    __syncwarp();
+    // the rows that equalled the span's second reference: one decode, weighted by their number
+    uint32_t *e = queue + lane * kFusedEntryWords;
+    e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = a4; e[5] = sp;
+    __syncwarp();
+    if (n_alt) fused_decode(e, cons, runs, hist, other_min, other_max, lut_cls, lut_chr, n_alt);
 }
 
-// Consensus row for the compare-with-consensus kernels: per alignment column the Boyer-Moore
-// majority vote over the first rows of the group.  ANY row is a valid consensus (the kernels are
-// exact for every choice); a majority-like row just minimises how many spans take the decode path
-// (a first sequence carrying minor alleles would make most rows differ at those codons).
-__global__ void k_vote_consensus(const uint8_t *__restrict__ aln, int64_t pitch, int n_vote, int64_t row_bytes, int64_t n_out,
-                                 uint8_t *__restrict__ cons)
+// The two reference rows of the compare-with-reference kernels, from the first n_sample (<= 32) rows of
+// the group.  One warp per 16-byte span, one lane per sampled row.
+//   cons[column]        the most frequent byte of every column (lowest row on ties)
+//   alt[span][kAltWords] the span's most frequent 18-byte pattern (16 bytes + the 2 a codon may reach into
+//                       the next span) that differs from the consensus; the consensus if no sampled row differs
+// ANY rows are valid references (the kernels are exact for every choice); frequent ones just keep more
+// rows off the decode path (a first sequence carrying minor alleles would make most rows differ).
+// Span n_spans only supplies the look-ahead bytes of the last real span.
+__device__ __forceinline__ uint32_t plurality_byte(uint32_t b, unsigned valid, int lane) {
+    const unsigned same = __match_any_sync(kFull, b) & valid;
+    uint32_t key = ((valid >> lane) & 1u) ? ((uint32_t)__popc(same) << 13) | ((uint32_t)(31 - lane) << 8) | b : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(kFull, key, o));
+    return key & 0xFFu;
+}
+
+__global__ void __launch_bounds__(256)
+k_vote_refs(const uint8_t *__restrict__ aln, int64_t pitch, int n_sample, int64_t n_spans, uint8_t *__restrict__ cons,
+            uint32_t *__restrict__ alt)
 {
-    // one thread votes on 4 adjacent columns (one aligned 32-bit word per row)
-    const int64_t col = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (col >= n_out) return;
-    uint32_t cand[4] = {0, 0, 0, 0};
-    if (col + 4 <= row_bytes) {
-        int cnt[4] = {0, 0, 0, 0};
-        for (int r0 = 0; r0 < n_vote; r0 += 16) {
-            uint32_t w[16];
-#pragma unroll
-            for (int k = 0; k < 16; k++)      // 16 independent loads in flight (rows past the end repeat the last row)
-                w[k] = *reinterpret_cast<const uint32_t *>(aln + (size_t)min(r0 + k, n_vote - 1) * pitch + col);
-#pragma unroll
-            for (int k = 0; k < 16; k++) {
-                const bool valid = r0 + k < n_vote;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t b = (w[k] >> (8 * j)) & 0xFF;
-                    const bool same = b == cand[j];
-                    const bool take = cnt[j] == 0;
-                    if (valid) {
-                        cand[j] = take ? b : cand[j];
-                        cnt[j] = take ? 1 : (same ? cnt[j] + 1 : cnt[j] - 1);
-                    }
-                }
-            }
-        }
+    const int lane = threadIdx.x & 31;
+    const int64_t sp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (sp > n_spans) return;
+    const unsigned valid = n_sample >= 32 ? kFull : ((1u << n_sample) - 1u);
+    const uint8_t *pi = aln + (size_t)min(lane, n_sample - 1) * pitch + sp * 16;     // lanes past the sample repeat its last row
+    uint32_t x[5] = {0, 0, 0, 0, 0};
+    x[0] = *reinterpret_cast<const uint32_t *>(pi);
+    if (sp < n_spans) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(pi);
+        x[1] = v.y; x[2] = v.z; x[3] = v.w;
+        x[4] = *reinterpret_cast<const uint32_t *>(pi + 16) & 0xFFFFu;
     }
-    for (int j = 0; j < 4; j++)
-        if (col + j < n_out) cons[col + j] = (uint8_t)cand[j];
+    // consensus: per column plurality (18 columns; the last two repeat the next span's first two)
+    uint32_t c[5] = {0, 0, 0, 0, 0};
+    const int n_cols = sp < n_spans ? 18 : 4;
+#pragma unroll
+    for (int j = 0; j < 18; j++)
+        if (j < n_cols) c[j >> 2] |= plurality_byte((x[j >> 2] >> (8 * (j & 3))) & 0xFFu, valid, lane) << (8 * (j & 3));
+    if (lane == 0) {
+        if (sp < n_spans) *reinterpret_cast<uint4 *>(cons + sp * 16) = make_uint4(c[0], c[1], c[2], c[3]);
+        else *reinterpret_cast<uint32_t *>(cons + sp * 16) = c[0];
+    }
+    if (sp >= n_spans) return;
+    // second reference: the most frequent differing pattern
+    const bool differs = ((valid >> lane) & 1u) && ((x[0] ^ c[0]) | (x[1] ^ c[1]) | (x[2] ^ c[2]) | (x[3] ^ c[3]) | (x[4] ^ c[4])) != 0;
+    const unsigned same = __match_any_sync(kFull, x[0]) & __match_any_sync(kFull, x[1]) & __match_any_sync(kFull, x[2]) &
+                          __match_any_sync(kFull, x[3]) & __match_any_sync(kFull, x[4]) & valid;
+    uint32_t key = differs ? ((uint32_t)__popc(same) << 5) | (uint32_t)(31 - lane) : 0u;    // most frequent, lowest row on ties
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(kFull, key, o));
+    const int src = 31 - (int)(key & 31u);
+    uint32_t w[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) w[k] = __shfl_sync(kFull, x[k], src);
+    if (lane == 0) {
+        uint32_t *o = alt + sp * kAltWords;
+#pragma unroll
+        for (int k = 0; k < 5; k++) o[k] = key ? w[k] : c[k];
+    }
 }
 
 // Code of the consensus row's codon for every codon (the fused kernel's reference point).
@@ -918,11 +958,11 @@ void launch_hist(const uint8_t *d_codes, int64_t n_pad, int64_t n_codons, uint32
                                                                                                chunk_rows, d_hist);
 }
 
-void launch_vote_consensus(const uint8_t *d_aln, int64_t pitch, int n_vote, int64_t row_bytes, int64_t n_out, uint8_t *d_cons,
-                           cudaStream_t stream)
+void launch_vote_refs(const uint8_t *d_aln, int64_t pitch, int n_sample, int64_t n_spans, uint8_t *d_cons, uint32_t *d_alt,
+                      cudaStream_t stream)
 {
-    if (n_out <= 0 || n_vote <= 0) return;
-    k_vote_consensus<<<(unsigned)((n_out / 4 + 1 + 127) / 128), 128, 0, stream>>>(d_aln, pitch, n_vote, row_bytes, n_out, d_cons);
+    if (n_spans <= 0 || n_sample <= 0) return;
+    k_vote_refs<<<(unsigned)((n_spans + 1 + 7) / 8), 256, 0, stream>>>(d_aln, pitch, min(n_sample, 32), n_spans, d_cons, d_alt);
 }
 
 void launch_cons_codes(const uint8_t *d_cons, int64_t cons_shift, const CodonMap *d_map, int64_t n_codons, uint8_t *d_cons_code,
@@ -932,16 +972,17 @@ void launch_cons_codes(const uint8_t *d_cons, int64_t cons_shift, const CodonMap
     k_cons_codes<<<(unsigned)((n_codons + 127) / 128), 128, 0, stream>>>(d_cons, cons_shift, d_map, n_codons, d_cons_code, d_cons_key);
 }
 
-void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, const uint8_t *d_cons, int64_t n_spans,
-                       const SpanRun *d_runs, const uint8_t *d_cons_code, uint32_t *d_hist, uint32_t *d_other_min,
+void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, const uint8_t *d_cons, const uint32_t *d_alt,
+                       int64_t n_spans, const SpanRun *d_runs, const uint8_t *d_cons_code, uint32_t *d_hist, uint32_t *d_other_min,
                        uint32_t *d_other_max, cudaStream_t stream)
 {
     if (n_spans <= 0 || n_rows <= 0) return;
-    const int64_t rows_per_block = (int64_t)kFusedWarps * kFusedRowsPerWarp;
+    static const int rows_per_warp = [] { const char *v = getenv("SNPG_SPAN_ROWS"); return v ? max(4, atoi(v)) : kFusedRowsPerWarp; }();
+    const int64_t rows_per_block = (int64_t)kFusedWarps * rows_per_warp;
     dim3 grid((unsigned)((n_spans + 31) / 32), (unsigned)((n_rows + rows_per_block - 1) / rows_per_block));
     (void)d_cons_code;
-    k_fused_hist<<<grid, kFusedWarps * 32, 0, stream>>>(d_aln, pitch, n_rows, d_cons, n_spans, d_runs, d_hist, d_other_min,
-                                                        d_other_max);
+    k_fused_hist<<<grid, kFusedWarps * 32, 0, stream>>>(d_aln, pitch, n_rows, d_cons, d_alt, n_spans, d_runs, d_hist, d_other_min,
+                                                        d_other_max, rows_per_warp);
 }
 
 void launch_fused_fixup(const uint8_t *d_cons_code, const uint32_t *d_cons_key, const uint8_t *d_regular, int64_t n_codons,

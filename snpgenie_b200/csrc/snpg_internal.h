@@ -54,17 +54,16 @@ void launch_pack(const uint8_t *d_aln, int64_t row_stride, int64_t n_rows, int64
 // K2 histogram: codes[c][0..n_pad) -> hist[c][66] (u32, zeroed by the caller)
 void launch_hist(const uint8_t *d_codes, int64_t n_pad, int64_t n_codons, uint32_t *d_hist, cudaStream_t stream);
 
-// K1+K2 fused (no code matrix): d_aln points at the first span's bytes of the first
-// row; spans are 16-byte aligned and every row must have >= n_spans*16 + 4 readable
-// bytes from there; d_cons holds the consensus row for the same columns.
-// Sequence: launch_cons_codes once per group (after the consensus row is known),
-// launch_fused_hist per row block (hist zeroed before the first), launch_fused_fixup once.
-// consensus row = per-column majority vote over the first n_vote rows (cons[0..n_out), zero past row_bytes)
-void launch_vote_consensus(const uint8_t *d_aln, int64_t pitch, int n_vote, int64_t row_bytes, int64_t n_out, uint8_t *d_cons,
-                           cudaStream_t stream);
+// Reference rows of the compare-with-reference kernels from the group's first n_sample (<= 32) rows:
+// d_cons[column] (n_spans*16 + 4 bytes written) and d_alt[span][kAltWords].  Every row needs
+// n_spans*16 + 4 readable bytes.
+void launch_vote_refs(const uint8_t *d_aln, int64_t pitch, int n_sample, int64_t n_spans, uint8_t *d_cons, uint32_t *d_alt,
+                      cudaStream_t stream);
 void launch_cons_codes(const uint8_t *d_cons, int64_t cons_shift, const CodonMap *d_map, int64_t n_codons, uint8_t *d_cons_code,
                        uint32_t *d_cons_key, cudaStream_t stream);
-void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, const uint8_t *d_cons, int64_t n_spans,
+// d_alt[span][kAltWords]: the span's second reference pattern (launch_vote_refs).
+constexpr int kAltWords = 8;
+void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, const uint8_t *d_cons, const uint32_t *d_alt, int64_t n_spans,
                        const SpanRun *d_runs, const uint8_t *d_cons_code, uint32_t *d_hist, uint32_t *d_other_min,
                        uint32_t *d_other_max, cudaStream_t stream);
 void launch_fused_fixup(const uint8_t *d_cons_code, const uint32_t *d_cons_key, const uint8_t *d_regular, int64_t n_codons,

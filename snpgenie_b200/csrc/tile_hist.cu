@@ -17,17 +17,17 @@
 // Sixteen consumer warps share the rows of a stage.  A lane owns one group of four codons (12
 // bytes: four aligned 32-bit shared-memory words funnel-shifted by the tile's sub-word offset into
 // three; lanes 0-15 take row r, lanes 16-31 row r+4, which makes the loads bank-conflict free at
-// the 52-word row pitch).  For each of its four codons the lane keeps a tiny allele cache in
-// registers: the consensus codon's bytes plus up to two alternate byte patterns with counters.
-// A row costs three masked XOR-compares and two predicated adds per codon -- no ballots, no
-// queues, no divergence, and a cost that does not depend on how polymorphic the column is.  A row
-// whose codon matches none of the three patterns sets a bit in the lane's miss mask; after the
-// item the lane revisits those rows: it installs the pattern in a free cache slot or, when both
-// are taken, counts that single codon directly.  At the end of a chunk every (codon, alternate)
-// with a non-zero counter is classified once through the 256-entry LUT and added to
-// hist[codon][code] with one RED.  k_fused_fixup then credits each codon's consensus code with
+// the 52-word row pitch), XORs it with the group's words of the consensus row and, when anything
+// differs, parks the three XOR words in a per-warp ring.  When 32 groups are parked the full warp
+// decodes them densely: which of the four codons differ, their residues (XOR back with the
+// consensus), classification through the 256-entry LUT, and one RED.ADD per differing codon into
+// hist[codon][code].  k_fused_fixup then credits each codon's consensus code with
 // (rows - recorded), exactly as for k_fused_hist.  Bytes are compared raw, so a lower-case or 'U'
-// residue is simply another pattern that classifies to the same code.
+// residue simply takes the decode path.
+//
+// (A density-independent variant -- a per-lane cache of the consensus and two alternate patterns
+// per codon with register counters, no queues -- was measured too: 98 M warp instructions, ALU
+// pipe 78 % busy, 122 us on config 2; see profiles/.)
 //
 // Algorithmic traffic: the CDS bytes of every row once (3 B per (sequence, codon)) + 264 B per
 // codon of histogram.  Non-coding columns are never read; overlapping products read their
@@ -52,6 +52,7 @@ constexpr int kTileStages = 3;                           // per CTA; two CTAs sh
 constexpr int kTileConsumers = 16;                       // consumer warps; warp kTileConsumers is the producer
 constexpr int kTileRowsPerWarp = kTileRows / kTileConsumers;   // 8 rows = 4 row pairs per stage
 constexpr int kTileStageBytes = kTileRows * kTileBytes;  // 26,624
+constexpr int kTileQueue = 64;                           // parked groups per warp (ring, power of two)
 constexpr int kTileCtasPerSm = 2;
 constexpr int kTileChunkRbs = 8;                         // blocks of rows per scheduling chunk (1,024 rows)
 
@@ -66,6 +67,8 @@ struct StageMeta { int32_t x0, codon0, info, rb; };     // info = ncodons | dir 
 struct TileSmem {
     uint8_t stage[kTileStages][kTileStageBytes];         // TMA destinations (128-byte aligned)
     uint8_t cons_row[kTileStages][256];                  // consensus bytes of the tile's 208-byte window (first stage of a chunk)
+    uint4 queue[kTileConsumers][kTileQueue];             // parked (d0, d1, d2, group)
+    uint4 cons[kTileConsumers][16];                      // per warp: the current tile's consensus words per group
     uint8_t lut_chr[2][256];
     uint8_t lut_cls[2][256];
     StageMeta meta[kTileStages];
@@ -106,67 +109,42 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
                  : "memory");
 }
 
-// Adds `count` sequences whose codon `cidx` has the raw bytes pat (byte 0 = lowest alignment column).
-__device__ __forceinline__ void count_pattern(uint32_t pat, uint32_t cidx, uint32_t count, int minus, uint32_t *__restrict__ hist,
-                                              uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max,
-                                              const uint8_t (*lut_cls)[256], const uint8_t (*lut_chr)[256])
+// One parked group: d0..d2 = (row ^ consensus) of the group's 12 bytes (masked to its codons),
+// g = the group's index inside the tile.  Codon k of the group sits in bytes 3k..3k+2.
+__device__ __forceinline__ void tile_decode(uint4 e, const uint4 *__restrict__ wcons, int codon0, int dir, int minus,
+                                            uint32_t *__restrict__ hist, uint32_t *__restrict__ other_min,
+                                            uint32_t *__restrict__ other_max, const uint8_t (*lut_cls)[256],
+                                            const uint8_t (*lut_chr)[256])
 {
-    const uint32_t r0 = pat & 0xFF, r1 = (pat >> 8) & 0xFF, r2 = (pat >> 16) & 0xFF;
-    const uint32_t b0 = minus ? r2 : r0, b2 = minus ? r0 : r2;          // '-' strand reads the codon right to left
+    const uint32_t d0 = e.x, d1 = e.y, d2 = e.z, g = e.w;
+    const uint4 c = wcons[g];
+    uint32_t cm = ((d0 & 0x00FFFFFFu) ? 1u : 0u) | ((((d0 >> 24) | (d1 << 8)) & 0x00FFFFFFu) ? 2u : 0u) |
+                  ((((d1 >> 16) | (d2 << 16)) & 0x00FFFFFFu) ? 4u : 0u) | ((d2 >> 8) ? 8u : 0u);
+    const uint32_t x0 = d0 ^ c.x, x1 = d1 ^ c.y, x2 = d2 ^ c.z;        // the row's own bytes
+    // byte selectors (PRMT) of codon k out of (x0, x1) for k < 2 and (x1, x2) for k >= 2; the '-' strand
+    // reads the codon right to left, so its selectors are reversed
+    const unsigned long long sel_all = minus ? 0x0567023403450012ull : 0x0765043205430210ull;
     const uint8_t *cls = lut_cls[minus];
-    const uint32_t k0 = cls[b0], k1 = cls[r1], k2 = cls[b2];
-    uint32_t code = k0 * 16 + k1 * 4 + k2;
-    if (max(k0, max(k1, k2)) >= 4) {
-        code = (k0 == 4 || k1 == 4 || k2 == 4) ? kCodeUndef : kCodeOther;
-        if (code == kCodeOther) {
-            const uint8_t *chr = lut_chr[minus];
-            const uint32_t key = ((uint32_t)chr[b0] << 16) | ((uint32_t)chr[r1] << 8) | chr[b2];
-            atomicMin(&other_min[cidx], key);
-            atomicMax(&other_max[cidx], key);
+    const uint8_t *chr = lut_chr[minus];
+    const int cbase = codon0 + dir * 4 * (int)g;
+    while (cm) {
+        const int k = __ffs(cm) - 1;
+        cm &= cm - 1;
+        const uint32_t v = __byte_perm(k < 2 ? x0 : x1, k < 2 ? x1 : x2, (uint32_t)(sel_all >> (16 * k)));
+        const uint32_t b0 = v & 0xFF, b1 = __byte_perm(v, 0, 0x4441), b2 = __byte_perm(v, 0, 0x4442);
+        const uint32_t k0 = cls[b0], k1 = cls[b1], k2 = cls[b2];
+        const uint32_t cidx = (uint32_t)(cbase + dir * k);
+        uint32_t code = k0 * 16 + k1 * 4 + k2;
+        if (max(k0, max(k1, k2)) >= 4) {
+            code = (k0 == 4 || k1 == 4 || k2 == 4) ? kCodeUndef : kCodeOther;
+            if (code == kCodeOther) {
+                const uint32_t key = ((uint32_t)chr[b0] << 16) | ((uint32_t)chr[b1] << 8) | chr[b2];
+                atomicMin(&other_min[cidx], key);
+                atomicMax(&other_max[cidx], key);
+            }
         }
+        atomicAdd(&hist[cidx * (uint32_t)kHistBins + code], 1u);     // 32-bit index: codons * 66 < 2^32
     }
-    atomicAdd(&hist[cidx * (uint32_t)kHistBins + code], count);          // 32-bit index: codons * 66 < 2^32
-}
-
-// The lane's four codons of one row, each in its own register: codons 0..2 in bits 0-23, codon 3 in bits 8-31
-// (patterns and masks for codon 3 are kept in that position, so no shift is spent on it).
-__device__ __forceinline__ void split_codons(const uint32_t *row, uint32_t sh, uint32_t (&y)[4]) {
-    const uint32_t w0 = row[0], w1 = row[1], w2 = row[2], w3 = row[3];
-    const uint32_t x0 = __funnelshift_r(w0, w1, sh), x1 = __funnelshift_r(w1, w2, sh), x2 = __funnelshift_r(w2, w3, sh);
-    y[0] = x0;
-    y[1] = __byte_perm(x0, x1, 0x0543);
-    y[2] = __byte_perm(x1, x2, 0x0432);
-    y[3] = x2;
-}
-
-// Per-lane allele cache of the current chunk: for codon k the consensus pattern pc[k], up to two alternates
-// a1[k], a2[k] (an empty slot holds the consensus pattern, so it can never turn a mismatch into a hit) and
-// their counters packed in cnt[k] (a1 low half, a2 high half; a chunk gives a lane at most a few hundred
-// rows).  nalt holds two bits per codon: how many alternates are installed.
-struct AlleleCache {
-    uint32_t pc[4], pm[4], a1[4], a2[4], cnt[4], nalt;
-};
-
-template <bool TAIL>
-__device__ __forceinline__ uint32_t scan_rows(const uint32_t *sp, uint32_t sh, AlleleCache &C, int rows_left)
-{
-    uint32_t miss = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        uint32_t y[4];
-        split_codons(sp + i * (kTileBytes / 4), sh, y);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            bool p0 = ((y[k] ^ C.pc[k]) & C.pm[k]) == 0;
-            bool p1 = ((y[k] ^ C.a1[k]) & C.pm[k]) == 0;
-            bool p2 = ((y[k] ^ C.a2[k]) & C.pm[k]) == 0;
-            if (TAIL) { const bool real = i < rows_left; p0 |= !real; p1 &= real; p2 &= real; }
-            if (p1) C.cnt[k] += 1u;
-            if (p2) C.cnt[k] += 0x10000u;
-            if (!(p0 || p1 || p2)) miss |= 1u << (4 * i + k);
-        }
-    }
-    return miss;
 }
 
 __global__ void __launch_bounds__((kTileConsumers + 1) * 32, kTileCtasPerSm)
@@ -236,75 +214,73 @@ k_tile_hist(const __grid_constant__ CUtensorMap tmap, int n_rows, const uint8_t 
     }
 
     // -------------------- consumers --------------------
+    uint4 *queue = S.queue[warp];
+    uint4 *wcons = S.cons[warp];
+    uint32_t q_head = 0, q_count = 0;            // warp-uniform
+    unsigned lt = (1u << lane) - 1;
+    asm volatile("" : "+r"(lt));                 // keep it in a register (ptxas otherwise re-reads %tid through the MIO queue)
     const int gl = lane & 15, half = lane >> 4;
     int codon0 = 0, dir = 1, minus = 0;
+    uint32_t c0 = 0, c1 = 0, c2 = 0, m0 = 0, m1 = 0, m2 = 0;
     uint32_t lane_ofs = 0, sh = 0;               // byte offset of the lane's first aligned word in its row; funnel shift in bits
-    AlleleCache C;
-#pragma unroll
-    for (int k = 0; k < 4; k++) { C.pc[k] = 0; C.pm[k] = 0; C.a1[k] = 0; C.a2[k] = 0; C.cnt[k] = 0; }
-    C.nalt = 0;
-
-    // every installed alternate with a non-zero counter goes to the histogram once
-    auto flush = [&]() {
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t n = (C.nalt >> (2 * k)) & 3u;
-            const uint32_t cidx = (uint32_t)(codon0 + dir * (4 * gl + k));
-            const uint32_t c1 = C.cnt[k] & 0xFFFFu, c2 = C.cnt[k] >> 16;
-            if (n >= 1 && c1) count_pattern(k == 3 ? C.a1[k] >> 8 : C.a1[k], cidx, c1, minus, hist, other_min, other_max, S.lut_cls, S.lut_chr);
-            if (n >= 2 && c2) count_pattern(k == 3 ? C.a2[k] >> 8 : C.a2[k], cidx, c2, minus, hist, other_min, other_max, S.lut_cls, S.lut_chr);
-        }
-    };
 
     for (;;) {
         mbar_wait(&S.full[stage], phase);
         const int4 mt = *reinterpret_cast<const int4 *>(&S.meta[stage]);
         if (mt.w < 0) break;
         if (mt.z >> 24) {
-            // a new chunk: the counters belong to the previous tile
-            flush();
+            // a new chunk: the parked groups belong to the previous tile, decode them before its constants go
+            if (q_count) {
+                __syncwarp();
+                if ((uint32_t)lane < q_count)
+                    tile_decode(queue[(q_head + lane) & (kTileQueue - 1)], wcons, codon0, dir, minus, hist, other_min, other_max,
+                                S.lut_cls, S.lut_chr);
+                __syncwarp();
+                q_head = 0; q_count = 0;
+            }
             codon0 = mt.y; dir = (int)(int8_t)(mt.z >> 8); minus = (mt.z >> 16) & 1;
             const int cnt = min(4, max(0, (mt.z & 0xFF) - 4 * gl));
+            const int nb = 3 * cnt;
+            m0 = nb >= 4 ? 0xFFFFFFFFu : (nb == 3 ? 0x00FFFFFFu : 0u);
+            m1 = nb >= 8 ? 0xFFFFFFFFu : (nb == 6 ? 0x0000FFFFu : 0u);
+            m2 = nb >= 12 ? 0xFFFFFFFFu : (nb == 9 ? 0x000000FFu : 0u);
             lane_ofs = (uint32_t)(((mt.x & 15) >> 2) + 3 * gl) * 4u;
             sh = (uint32_t)(mt.x & 3) * 8u;
-            uint32_t y[4];
-            split_codons(reinterpret_cast<const uint32_t *>(S.cons_row[stage] + lane_ofs), sh, y);
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                C.pm[k] = k < cnt ? (k == 3 ? 0xFFFFFF00u : 0x00FFFFFFu) : 0u;      // an absent codon matches everything
-                C.pc[k] = y[k] & C.pm[k];
-                C.a1[k] = C.pc[k];
-                C.a2[k] = C.pc[k];
-                C.cnt[k] = 0;
-            }
-            C.nalt = 0;
+            const uint32_t *cw = reinterpret_cast<const uint32_t *>(S.cons_row[stage] + lane_ofs);
+            const uint32_t w0 = cw[0], w1 = cw[1], w2 = cw[2], w3 = cw[3];
+            c0 = __funnelshift_r(w0, w1, sh) & m0;
+            c1 = __funnelshift_r(w1, w2, sh) & m1;
+            c2 = __funnelshift_r(w2, w3, sh) & m2;
+            if (half == 0) wcons[gl] = make_uint4(c0, c1, c2, 0);
+            __syncwarp();
         }
 
         // lanes 0-15 read row i of the warp's eight, lanes 16-31 row i + 4
         const uint32_t *sp = reinterpret_cast<const uint32_t *>(S.stage[stage] + (warp * kTileRowsPerWarp + 4 * half) * kTileBytes + lane_ofs);
-        const int rows_left = n_rows - (mt.w * kTileRows + warp * kTileRowsPerWarp + 4 * half);   // row i is real iff i < rows_left
-        const bool tail = n_rows - mt.w * kTileRows < kTileRows;                                   // warp-uniform: last block of rows
-        uint32_t miss = 0;
-        if (!debug_skip) miss = tail ? scan_rows<true>(sp, sh, C, rows_left) : scan_rows<false>(sp, sh, C, rows_left);
-
-        if (miss) {
-            // rare and lane-local: a pattern the cache does not hold yet.  Revisit those rows in order.
+        const int rows_left = debug_skip ? 0 : n_rows - (mt.w * kTileRows + warp * kTileRowsPerWarp + 4 * half);   // row i is real iff i < rows_left
+        uint32_t w[4][4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                uint32_t mk = miss & (0x1111u << k);
-                while (mk) {
-                    const int i = (__ffs(mk) - 1) >> 2;
-                    mk &= mk - 1;
-                    uint32_t y[4];
-                    split_codons(sp + i * (kTileBytes / 4), sh, y);
-                    const uint32_t v = y[k] & C.pm[k];
-                    const uint32_t n = (C.nalt >> (2 * k)) & 3u;
-                    if (n >= 1 && v == C.a1[k]) C.cnt[k] += 1u;
-                    else if (n >= 2 && v == C.a2[k]) C.cnt[k] += 0x10000u;
-                    else if (n == 0) { C.a1[k] = v; C.cnt[k] = (C.cnt[k] & 0xFFFF0000u) | 1u; C.nalt += 1u << (2 * k); }
-                    else if (n == 1) { C.a2[k] = v; C.cnt[k] = (C.cnt[k] & 0x0000FFFFu) | 0x10000u; C.nalt += 1u << (2 * k); }
-                    else count_pattern(k == 3 ? v >> 8 : v, (uint32_t)(codon0 + dir * (4 * gl + k)), 1u, minus, hist, other_min, other_max,
-                                       S.lut_cls, S.lut_chr);
+        for (int i = 0; i < 4; i++) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) w[i][k] = sp[i * (kTileBytes / 4) + k];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t x0 = __funnelshift_r(w[i][0], w[i][1], sh), x1 = __funnelshift_r(w[i][1], w[i][2], sh),
+                           x2 = __funnelshift_r(w[i][2], w[i][3], sh);
+            const uint32_t d0 = (x0 ^ c0) & m0, d1 = (x1 ^ c1) & m1, d2 = (x2 ^ c2) & m2;
+            const bool differs = (d0 | d1 | d2) != 0 && i < rows_left;
+            const unsigned bal = __ballot_sync(kFull, differs);
+            if (bal) {       // on realistic alignments most row pairs have nothing to park
+                if (differs) queue[(q_head + q_count + __popc(bal & lt)) & (kTileQueue - 1)] = make_uint4(d0, d1, d2, (uint32_t)gl);
+                q_count += __popc(bal);
+                while (q_count >= 32) {      // at most 31 + 32 parked groups at any time
+                    __syncwarp();
+                    tile_decode(queue[(q_head + lane) & (kTileQueue - 1)], wcons, codon0, dir, minus, hist, other_min, other_max,
+                                S.lut_cls, S.lut_chr);
+                    __syncwarp();
+                    q_head += 32;
+                    q_count -= 32;
                 }
             }
         }
@@ -312,7 +288,10 @@ k_tile_hist(const __grid_constant__ CUtensorMap tmap, int n_rows, const uint8_t 
         if (lane == 0) mbar_arrive(&S.empty[stage]);      // this warp is done with the stage's bytes
         if (++stage == kTileStages) { stage = 0; phase ^= 1; }
     }
-    flush();
+    __syncwarp();
+    if ((uint32_t)lane < q_count)
+        tile_decode(queue[(q_head + lane) & (kTileQueue - 1)], wcons, codon0, dir, minus, hist, other_min, other_max, S.lut_cls,
+                    S.lut_chr);
 }
 
 }  // namespace

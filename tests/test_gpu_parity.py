@@ -31,18 +31,18 @@ def eng():
     e.close()
 
 
-@pytest.fixture(scope="module", params=["codes", "fused", "spans"])
+@pytest.fixture(scope="module", params=["codes", "fused", "tiles"])
 def eng2(request):
-    """All histogram routes: K1 pack + K2 hist over the kept code matrix, the fused TMA-tiled kernel
-    (the default) and the fused vector-load kernel."""
+    """All histogram routes: K1 pack + K2 hist over the kept code matrix, the fused vector-load kernel
+    (the default) and the fused TMA-tiled kernel."""
     from snpgenie_b200 import _abi
     from snpgenie_b200.engine import Engine
     e = Engine(device=0, seed=1234)
     e.has_codes = request.param == "codes"
     e.route = request.param
     e.set_option(_abi.OPT_KEEP_CODES, 1 if e.has_codes else 0)
-    if request.param == "spans":
-        e.set_option(_abi.OPT_FUSED_KERNEL, _abi.FUSED_LDG_SPANS)
+    if request.param == "tiles":
+        e.set_option(_abi.OPT_FUSED_KERNEL, _abi.FUSED_TMA_TILES)
     yield e
     e.close()
 
@@ -63,8 +63,8 @@ def test_codon_indices_and_histograms_bit_exact(eng2, case, minus):
     eng.set_products(products, aln.shape[1])
     before = eng.tile_launches
     eng.load_group(0, aln)
-    # the default fused route must really be the TMA-tiled kernel, the other two must not touch it
-    assert (eng.tile_launches > before) == (eng.route == "fused")
+    # the "tiles" route must really be the TMA-tiled kernel, the other two must not touch it
+    assert (eng.tile_launches > before) == (eng.route == "tiles")
     for i, p in enumerate(products):
         raw, codes = _oracle_product(aln, p)
         if eng.has_codes:

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small driver for ncu captures: a few device-resident steps of the config-2 hot path.
 
-    python tools/prof_step.py [--steps 3] [--route fused|spans|codes] [--n 10000]
+    python tools/prof_step.py [--steps 3] [--route fused|tiles|codes] [--p-poly 0.3] [--n 10000]
 """
 import argparse
 import os
@@ -18,16 +18,17 @@ ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--route", default="fused")
 ap.add_argument("--n", type=int, default=10000)
 ap.add_argument("--boot", type=int, default=10000)
+ap.add_argument("--p-poly", type=float, default=0.3)
 a = ap.parse_args()
 products = synth.sars2_products()
 L = 29903
-aln = synth.make_alignment(a.n, L, products, 20261021)
+aln = synth.make_alignment(a.n, L, products, 20261021, p_poly=a.p_poly)
 pitch = (L + 127) // 128 * 128
 d = torch.zeros((a.n, pitch), dtype=torch.uint8, device="cuda:0")
 d[:, :L] = torch.from_numpy(aln).cuda()
 with Engine(device=0) as eng:
     eng.set_option(_abi.OPT_KEEP_CODES, 1 if a.route == "codes" else 0)
-    eng.set_option(_abi.OPT_FUSED_KERNEL, _abi.FUSED_LDG_SPANS if a.route == "spans" else _abi.FUSED_TMA_TILES)
+    eng.set_option(_abi.OPT_FUSED_KERNEL, _abi.FUSED_TMA_TILES if a.route == "tiles" else _abi.FUSED_LDG_SPANS)
     eng.set_products(products, L)
     for _ in range(a.steps):
         eng.load_group_ptr(0, d.data_ptr(), a.n, L, pitch, device=True)
