@@ -920,7 +920,7 @@ int snpg_bootstrap_product(snpg_ctx *ctx, const double *stats4, const uint8_t *k
         launch_bootstrap(ctx->s_in.as<double>(), ctx->s_misc.as<int64_t>(), nullptr, 1, C, 0, B, ctx->seed, sid,
                          sums_out ? ctx->s_rep.as<double>() : nullptr, ctx->s_vals.as<double>(), ctx->stream);
     }
-    { Launch l(ctx, SNPG_K_MOMENTS); launch_moments(ctx->s_vals.as<double>(), 1, B, ctx->s_se.as<double>(), ctx->stream); }
+    { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->s_vals.as<double>(), 1, B, ctx->s_se.as<double>(), ctx->stream); }
     CU(ctx, cudaGetLastError());
     if (sums_out) CU(ctx, cudaMemcpyAsync(sums_out, ctx->s_rep.p, sizeof(double) * 4 * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
     if (se_out) CU(ctx, cudaMemcpyAsync(se_out, ctx->s_se.p, sizeof(double) * 6, cudaMemcpyDeviceToHost, ctx->stream));
@@ -949,14 +949,12 @@ int snpg_windows(snpg_ctx *ctx, const double *stats4, const uint8_t *keep, int64
         const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(nwin, ((int64_t)256 << 20) / (32 * B)));
         CU(ctx, ctx->s_rep.ensure(sizeof(double) * 4 * (size_t)(batch * B)));
         CU(ctx, ctx->s_se.ensure(sizeof(double) * 6 * (size_t)batch));
-        CU(ctx, ctx->s_vals.ensure(sizeof(double) * 6 * (size_t)(batch * B)));
         std::vector<double> se6((size_t)batch * 6);
         const uint32_t sid = 0x20000u + ctx->call_id++;
         for (int64_t w0 = 0; w0 < nwin; w0 += batch) {
             const int64_t nb = std::min(batch, nwin - w0);
             { Launch l(ctx, SNPG_K_WINDOW); launch_window_bootstrap(ctx->s_in.as<double>(), W, step, w0, nb, B, ctx->seed, sid, ctx->s_rep.as<double>(), ctx->stream); }
-            { Launch l(ctx, SNPG_K_MOMENTS); launch_rep_values(ctx->s_rep.as<double>(), nb, B, ctx->s_vals.as<double>(), ctx->stream); }
-            { Launch l(ctx, SNPG_K_MOMENTS); launch_moments(ctx->s_vals.as<double>(), nb, B, ctx->s_se.as<double>(), ctx->stream); }
+            { Launch l(ctx, SNPG_K_MOMENTS); launch_moments(ctx->s_rep.as<double>(), nb, B, ctx->s_se.as<double>(), ctx->stream); }
             CU(ctx, cudaGetLastError());
             CU(ctx, cudaMemcpyAsync(se6.data(), ctx->s_se.p, sizeof(double) * 6 * (size_t)nb, cudaMemcpyDeviceToHost, ctx->stream));
             CU(ctx, sync_stream(ctx));
@@ -1011,9 +1009,7 @@ int snpg_rep_moments_device(snpg_ctx *ctx, const double *d_rep, int64_t n_items,
     if (!ctx || !d_rep || !se_out || n_items <= 0 || B < 2) return SNPG_E_ARG;
     if (int rc = bind(ctx)) return rc;
     CU(ctx, ctx->s_se.ensure(sizeof(double) * 6 * (size_t)n_items));
-    CU(ctx, ctx->s_vals.ensure(sizeof(double) * 6 * (size_t)(n_items * B)));
-    { Launch l(ctx, SNPG_K_MOMENTS); launch_rep_values(d_rep, n_items, B, ctx->s_vals.as<double>(), ctx->stream); }
-    { Launch l(ctx, SNPG_K_MOMENTS); launch_moments(ctx->s_vals.as<double>(), n_items, B, ctx->s_se.as<double>(), ctx->stream); }
+    { Launch l(ctx, SNPG_K_MOMENTS); launch_moments(d_rep, n_items, B, ctx->s_se.as<double>(), ctx->stream); }
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaMemcpyAsync(se_out, ctx->s_se.p, sizeof(double) * 6 * (size_t)n_items, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, sync_stream(ctx));
@@ -1042,7 +1038,7 @@ int snpg_within_all(snpg_ctx *ctx, int group, int64_t B, double *prod_sums, doub
                              ctx->max_codons_local, 0, B, ctx->seed, 0x40000u + ctx->call_id++, nullptr, ctx->s_vals.as<double>(),
                              ctx->stream);
         }
-        { Launch l(ctx, SNPG_K_MOMENTS); launch_moments(ctx->s_vals.as<double>(), P, B, ctx->s_se.as<double>(), ctx->stream); }
+        { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->s_vals.as<double>(), P, B, ctx->s_se.as<double>(), ctx->stream); }
     }
     CU(ctx, cudaGetLastError());
     if (prod_sums) CU(ctx, cudaMemcpyAsync(prod_sums, ctx->s_sums.p, sizeof(double) * 4 * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));

@@ -760,7 +760,8 @@ __device__ __forceinline__ double rep_value(double ns, double ss, double nd, dou
 // (N_sites, S_sites) and (N_diffs, S_diffs); the sign bit of N_sites marks the
 // codons that have differences at all, so a draw on a conserved codon (most of
 // an alignment) costs one 16-byte gather instead of two.
-// Outputs: rep[p][b][4] replicate sums (optional) and vals[which][p][b].
+// Outputs (either may be null): rep[p][b][4] replicate sums and vals[which][p][b], written by a dense
+// block-level epilogue.
 // ---------------------------------------------------------------------------
 constexpr int kBootWarps = 32;
 constexpr int kBootRepsPerWarp = 2;
@@ -772,6 +773,7 @@ k_bootstrap(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, 
             int64_t b_first, int64_t b_count, uint2 key, uint32_t stream_id, double *__restrict__ rep, double *__restrict__ vals)
 {
     extern __shared__ double2 s_tab[];
+    __shared__ double2 s_sums[kBootWarps * kBootRepsPerWarp][2];     // the block's replicate sums, for the dense epilogue
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int p = order ? order[blockIdx.y] : blockIdx.y;
     const int64_t c0 = ofs[p];
@@ -793,7 +795,7 @@ k_bootstrap(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, 
     const uint32_t nquad = (C + 3) >> 2, full_quads = C >> 2;
     for (int k = 0; k < kBootRepsPerWarp; k++) {
         const int64_t bl = ((int64_t)blockIdx.x * kBootWarps + warp) * kBootRepsPerWarp + k;
-        if (bl >= b_count) break;
+        if (bl >= b_count) continue;
         const uint64_t b = (uint64_t)(b_first + bl);
         double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
         for (uint32_t q = lane; q < nquad; q += 32) {
@@ -829,29 +831,33 @@ k_bootstrap(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, 
             }
         }
         s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
-        if (lane == 0 && rep) {
-            double2 *o = reinterpret_cast<double2 *>(rep + 4 * ((size_t)p * b_count + bl));
-            o[0] = make_double2(s0, s1);
-            o[1] = make_double2(s2, s3);
+        if (lane == 0) {
+            s_sums[warp * kBootRepsPerWarp + k][0] = make_double2(s0, s1);
+            s_sums[warp * kBootRepsPerWarp + k][1] = make_double2(s2, s3);
         }
-        if (lane < 6 && vals) vals[((size_t)lane * n_products + p) * b_count + bl] = rep_value(s0, s1, s2, s3, lane);
     }
-}
-
-// rep[item][B][4] -> vals[which][item][B]  (paths that gathered replicate sums first)
-__global__ void k_rep_values(const double *__restrict__ rep, int64_t n_items, int64_t B, double *__restrict__ vals)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_items * B) return;
-    const double2 x = reinterpret_cast<const double2 *>(rep + 4 * i)[0];
-    const double2 y = reinterpret_cast<const double2 *>(rep + 4 * i)[1];
-    const int which = blockIdx.y;
-    vals[(size_t)which * n_items * B + i] = rep_value(x.x, x.y, y.x, y.y, which);
+    // dense epilogue: one thread per (replicate of the block, statistic) derives dN, dS, ... (divisions,
+    // logarithms); each of 12 warps runs one statistic for 32 replicates.  Done by six lanes of every warp
+    // right after its reduction, this was 44 % of the kernel's instructions.
+    __syncthreads();
+    constexpr int kReps = kBootWarps * kBootRepsPerWarp;
+    const int i = threadIdx.x, r = i % kReps, which = i / kReps;
+    const int64_t bl = (int64_t)blockIdx.x * kReps + r;
+    if (which < 6 && bl < b_count) {
+        const double2 x = s_sums[r][0], y = s_sums[r][1];
+        if (rep && which == 0) {
+            double2 *o = reinterpret_cast<double2 *>(rep + 4 * ((size_t)p * b_count + bl));
+            o[0] = x;
+            o[1] = y;
+        }
+        if (vals) vals[((size_t)which * n_products + p) * b_count + bl] = rep_value(x.x, x.y, y.x, y.y, which);
+    }
 }
 
 // ---------------------------------------------------------------------------
 // K6: SD over replicates in the reference's two-pass form with n-1
-// (wg:1351-1365).  One block per (item, statistic); se[item][6].
+// (wg:1351-1365).  One block per (item, statistic) over rep[item][B][4]; the
+// statistic of a replicate is derived on the fly (rep_value); se[item][6].
 // ---------------------------------------------------------------------------
 constexpr int kMomentThreads = 1024;
 __device__ __forceinline__ double block_sum(double v, double *red) {     // fixed-shape tree: deterministic
@@ -866,19 +872,27 @@ __device__ __forceinline__ double block_sum(double v, double *red) {     // fixe
     return red[0];
 }
 
+template <bool FROM_REP>
 __global__ void __launch_bounds__(kMomentThreads)
-k_moments(const double *__restrict__ vals, int64_t n_items, int64_t B, double *__restrict__ se)
+k_moments(const double *__restrict__ src, int64_t n_items, int64_t B, double *__restrict__ se)
 {
+    // FROM_REP: src = rep[item][B][4], the statistic is derived on the fly; else src = vals[which][item][B]
     __shared__ double red[kMomentThreads];
     const int p = blockIdx.x, which = blockIdx.y, t = threadIdx.x;
-    const double *V = vals + ((size_t)which * n_items + p) * B;
+    const double2 *R = reinterpret_cast<const double2 *>(src + 4 * (size_t)p * B);
+    const double *V = src + ((size_t)which * n_items + p) * B;
+    auto value = [&](int64_t b) {
+        if (!FROM_REP) return V[b];
+        const double2 x = R[2 * b], y = R[2 * b + 1];
+        return rep_value(x.x, x.y, y.x, y.y, which);
+    };
     double s = 0;
     int differs = 0;                       // replicates that are all identical have SD exactly 0, whatever
-    const double v0 = V[0];                // rounding the mean of B equal numbers picks up
-    for (int64_t b = t; b < B; b += kMomentThreads) { const double v = V[b]; s += v; differs |= (v != v0); }
+    const double v0 = value(0);            // rounding the mean of B equal numbers picks up
+    for (int64_t b = t; b < B; b += kMomentThreads) { const double v = value(b); s += v; differs |= (v != v0); }
     const double mean = block_sum(s, red) / (double)B;
     double ss = 0;
-    for (int64_t b = t; b < B; b += kMomentThreads) { const double d = V[b] - mean; ss += d * d; }
+    for (int64_t b = t; b < B; b += kMomentThreads) { const double d = value(b) - mean; ss += d * d; }
     const double tot = block_sum(ss, red);
     const int any = __syncthreads_or(differs);
     if (t == 0) se[6 * p + which] = any ? sqrt(tot / (double)(B - 1)) : 0.0;
@@ -1072,17 +1086,16 @@ void launch_philox_kat(const uint32_t *ctr, const uint32_t *key, uint32_t *d_out
     k_philox_kat<<<1, 1, 0, stream>>>(make_uint4(ctr[0], ctr[1], ctr[2], ctr[3]), make_uint2(key[0], key[1]), d_out);
 }
 
-void launch_rep_values(const double *d_rep, int64_t n_items, int64_t B, double *d_vals, cudaStream_t stream)
-{
-    if (n_items <= 0 || B <= 0) return;
-    dim3 grid((unsigned)((n_items * B + 255) / 256), 6);
-    k_rep_values<<<grid, 256, 0, stream>>>(d_rep, n_items, B, d_vals);
-}
-
-void launch_moments(const double *d_vals, int64_t n_items, int64_t B, double *d_se, cudaStream_t stream)
+void launch_moments(const double *d_rep, int64_t n_items, int64_t B, double *d_se, cudaStream_t stream)
 {
     if (n_items <= 0) return;
-    k_moments<<<dim3((unsigned)n_items, 6), kMomentThreads, 0, stream>>>(d_vals, n_items, B, d_se);
+    k_moments<true><<<dim3((unsigned)n_items, 6), kMomentThreads, 0, stream>>>(d_rep, n_items, B, d_se);
+}
+
+void launch_moments_vals(const double *d_vals, int64_t n_items, int64_t B, double *d_se, cudaStream_t stream)
+{
+    if (n_items <= 0) return;
+    k_moments<false><<<dim3((unsigned)n_items, 6), kMomentThreads, 0, stream>>>(d_vals, n_items, B, d_se);
 }
 
 void launch_window_sums(const double *d_stats4, int64_t W, int64_t step, int64_t nwin, double *d_win_sums,

@@ -116,10 +116,10 @@ void launch_bootstrap(const double *d_stats4, const int64_t *d_prod_ofs, const i
                       cudaStream_t stream);
 // one Philox4x32-10 block on the device (known-answer test hook)
 void launch_philox_kat(const uint32_t *ctr, const uint32_t *key, uint32_t *d_out, cudaStream_t stream);
-// rep[item][B][4] -> vals[which][item][B]
-void launch_rep_values(const double *d_rep, int64_t n_items, int64_t B, double *d_vals, cudaStream_t stream);
-// K6 moments: vals[which][item][B] -> se[item][6] (sample SD, n-1, two-pass)
-void launch_moments(const double *d_vals, int64_t n_items, int64_t B, double *d_se, cudaStream_t stream);
+// K6: rep[item][B][4] -> se[item][6]: sample SD (n-1) of the per-replicate dN, dS, dN-dS and their Jukes-Cantor forms
+void launch_moments(const double *d_rep, int64_t n_items, int64_t B, double *d_se, cudaStream_t stream);
+// the same from d_vals[which][item][B] (what launch_bootstrap's epilogue writes)
+void launch_moments_vals(const double *d_vals, int64_t n_items, int64_t B, double *d_se, cudaStream_t stream);
 
 // K5 windows
 void launch_window_sums(const double *d_stats4, int64_t W, int64_t step, int64_t nwin, double *d_win_sums,
