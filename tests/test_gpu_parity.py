@@ -307,6 +307,38 @@ def test_bootstrap_product_statistics(eng):
     assert not np.array_equal(se, se2) and np.all(np.abs(se / se2 - 1) < 0.03)
 
 
+@pytest.mark.parametrize("C", [1, 5, 6, 7, 8, 13, 64, 203, 1000])
+def test_bootstrap_draws_are_uniform_over_slots(eng, C):
+    """The banked sampler (class counts first, then uniform inside a bank-group class) must still draw every
+    one of the C+1 slots (slot 0 = the reference's empty codon, wg:885) with probability 1/(C+1), jointly
+    multinomial: the replicate sum of an indicator row counts the draws of that slot."""
+    B = 40000
+    p = 1.0 / (C + 1)
+    mean, var = C * p, C * p * (1 - p)
+    rng = np.random.default_rng(C)
+    order = rng.permutation(C)
+    codons = order if C <= 13 else order[:12]          # every slot for the small tables, a sample otherwise
+    for i in range(0, len(codons), 4):
+        t = codons[i:i + 4]
+        stats4 = np.zeros((C, 4))
+        for q, c in enumerate(t):
+            stats4[c, q] = 1.0
+        sums, _ = eng.bootstrap_product(stats4, B, want_sums=True)
+        assert np.all(sums == np.round(sums)) and sums.min() >= 0 and sums.sum(axis=1).max() <= C
+        for q in range(len(t)):
+            assert abs(sums[:, q].mean() - mean) < 5 * np.sqrt(var / B), (C, t[q])
+            assert abs(sums[:, q].var(ddof=1) / var - 1) < 0.06, (C, t[q])
+        if len(t) >= 2:     # two slots of one replicate: Cov = -C p^2
+            cov = np.cov(sums[:, 0], sums[:, 1])[0, 1]
+            assert abs(cov + C * p * p) < 6 * var / np.sqrt(B), (C, cov)
+    # all codons together: C draws minus those of the empty slot
+    ones = np.zeros((C, 4))
+    ones[:, 0] = 1.0
+    sums, _ = eng.bootstrap_product(ones, B, want_sums=True)
+    assert sums[:, 0].max() <= C and abs(sums[:, 0].mean() - C * C * p) < 5 * np.sqrt(var / B)
+    assert abs(sums[:, 0].var(ddof=1) / var - 1) < 0.06
+
+
 def test_bootstrap_keep_mask(eng):
     stats4, _ = _stats_from_golden()
     keep = (np.arange(stats4.shape[0]) % 3 != 0).astype(np.uint8)
