@@ -87,7 +87,6 @@ struct snpg_ctx {
     std::vector<CodonMap> host_map;   // full codon map (absolute columns), for snpg_codon_strings
     // scratch
     DevBuf s_vals, d_order_local, d_order_full;
-    DevBuf d_mcdf_local, d_mcdf_full;   // per product: CDF of the banked bootstrap sampler's special-draw count
     int64_t max_codons_local = 0, max_codons_full = 0;
     DevBuf staging[2], s_stats, s_poly, s_nda, s_ndb, s_cmp, s_cons, s_sums, s_rep, s_se, s_misc, s_in;
     int64_t launches = 0;
@@ -352,7 +351,7 @@ void snpg_destroy(snpg_ctx *ctx) {
                       &ctx->d_runs, &ctx->d_tiles, &ctx->d_sched, &ctx->d_regular, &ctx->d_irr_map, &ctx->d_irr_idx, &ctx->d_cons, &ctx->d_alt, &ctx->d_cons_code, &ctx->d_cons_key, &ctx->t_codes, &ctx->t_hist,
                       &ctx->t_other,
                       &ctx->s_stats, &ctx->s_poly, &ctx->s_nda, &ctx->s_ndb, &ctx->s_cmp, &ctx->s_cons, &ctx->s_sums,
-                      &ctx->s_rep, &ctx->s_se, &ctx->s_misc, &ctx->s_in, &ctx->s_vals, &ctx->d_order_local, &ctx->d_order_full, &ctx->d_mcdf_local, &ctx->d_mcdf_full};
+                      &ctx->s_rep, &ctx->s_se, &ctx->s_misc, &ctx->s_in, &ctx->s_vals, &ctx->d_order_local, &ctx->d_order_full};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
@@ -567,15 +566,6 @@ int snpg_set_products(snpg_ctx *ctx, int n_products, const int64_t *seg_ofs, con
         CU(ctx, ctx->d_order_full.ensure(sizeof(int) * n_products));
         CU(ctx, cudaMemcpy(ctx->d_order_local.p, ord_l.data(), sizeof(int) * n_products, cudaMemcpyHostToDevice));
         CU(ctx, cudaMemcpy(ctx->d_order_full.p, ord_f.data(), sizeof(int) * n_products, cudaMemcpyHostToDevice));
-        std::vector<double> cdf_l((size_t)n_products * kBootMcdf), cdf_f((size_t)n_products * kBootMcdf);
-        for (int p = 0; p < n_products; p++) {
-            build_boot_mcdf(len_l(p), &cdf_l[(size_t)p * kBootMcdf]);
-            build_boot_mcdf(len_f(p), &cdf_f[(size_t)p * kBootMcdf]);
-        }
-        CU(ctx, ctx->d_mcdf_local.ensure(sizeof(double) * cdf_l.size()));
-        CU(ctx, ctx->d_mcdf_full.ensure(sizeof(double) * cdf_f.size()));
-        CU(ctx, cudaMemcpy(ctx->d_mcdf_local.p, cdf_l.data(), sizeof(double) * cdf_l.size(), cudaMemcpyHostToDevice));
-        CU(ctx, cudaMemcpy(ctx->d_mcdf_full.p, cdf_f.data(), sizeof(double) * cdf_f.size(), cudaMemcpyHostToDevice));
     }
 
     CU(ctx, ctx->d_map.ensure(sizeof(CodonMap) * std::max<size_t>(1, local.size())));
@@ -918,11 +908,9 @@ int snpg_bootstrap_product(snpg_ctx *ctx, const double *stats4, const uint8_t *k
          (long long)C, (long long)B);
     if (int rc = bind(ctx)) return rc;
     if (int rc = upload_stats(ctx, stats4, keep, C)) return rc;
-    struct { int64_t ofs[2]; double cdf[kBootMcdf]; } misc;
-    misc.ofs[0] = 0; misc.ofs[1] = C;
-    build_boot_mcdf(C, misc.cdf);
-    CU(ctx, ctx->s_misc.ensure(sizeof misc));
-    CU(ctx, cudaMemcpy(ctx->s_misc.p, &misc, sizeof misc, cudaMemcpyHostToDevice));
+    const int64_t ofs[2] = {0, C};
+    CU(ctx, ctx->s_misc.ensure(sizeof ofs));
+    CU(ctx, cudaMemcpy(ctx->s_misc.p, ofs, sizeof ofs, cudaMemcpyHostToDevice));
     CU(ctx, ctx->s_rep.ensure(sizeof(double) * 4 * (size_t)B));
     CU(ctx, ctx->s_se.ensure(sizeof(double) * 6));
     const uint32_t sid = 0x10000u + ctx->call_id++;
@@ -930,8 +918,7 @@ int snpg_bootstrap_product(snpg_ctx *ctx, const double *stats4, const uint8_t *k
     {
         Launch l(ctx, SNPG_K_BOOT);
         launch_bootstrap(ctx->s_in.as<double>(), ctx->s_misc.as<int64_t>(), nullptr, 1, C, 0, B, ctx->seed, sid,
-                         reinterpret_cast<const double *>(ctx->s_misc.as<int64_t>() + 2), sums_out ? ctx->s_rep.as<double>() : nullptr,
-                         ctx->s_vals.as<double>(), ctx->stream);
+                         sums_out ? ctx->s_rep.as<double>() : nullptr, ctx->s_vals.as<double>(), ctx->stream);
     }
     { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->s_vals.as<double>(), 1, B, ctx->s_se.as<double>(), ctx->stream); }
     CU(ctx, cudaGetLastError());
@@ -999,7 +986,7 @@ int snpg_bootstrap_all_device(snpg_ctx *ctx, const double *d_stats4_full, int64_
     {
         Launch l(ctx, SNPG_K_BOOT);
         launch_bootstrap(d_stats4_full, ctx->d_full_ofs.as<int64_t>(), ctx->d_order_full.as<int>(), ctx->n_products, ctx->max_codons_full,
-                         b_first, b_count, ctx->seed, 0x30000u, ctx->d_mcdf_full.as<double>(), d_rep_out, nullptr, ctx->stream);
+                         b_first, b_count, ctx->seed, 0x30000u, d_rep_out, nullptr, ctx->stream);
     }
     CU(ctx, cudaGetLastError());
     CU(ctx, sync_stream(ctx));
@@ -1048,8 +1035,8 @@ int snpg_within_all(snpg_ctx *ctx, int group, int64_t B, double *prod_sums, doub
         {
             Launch l(ctx, SNPG_K_BOOT);
             launch_bootstrap(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), ctx->d_order_local.as<int>(), P,
-                             ctx->max_codons_local, 0, B, ctx->seed, 0x40000u + ctx->call_id++, ctx->d_mcdf_local.as<double>(), nullptr,
-                             ctx->s_vals.as<double>(), ctx->stream);
+                             ctx->max_codons_local, 0, B, ctx->seed, 0x40000u + ctx->call_id++, nullptr, ctx->s_vals.as<double>(),
+                             ctx->stream);
         }
         { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->s_vals.as<double>(), P, B, ctx->s_se.as<double>(), ctx->stream); }
     }

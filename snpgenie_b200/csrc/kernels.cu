@@ -767,103 +767,14 @@ constexpr int kBootWarps = 32;
 constexpr int kBootRepsPerWarp = 2;
 constexpr int kBootSmemLimit = 200 * 1024;
 
-// Banked sampler (MODE 2).  A random 16-byte gather by 32 lanes costs 11-12 shared-memory wavefronts
-// (bank conflicts inside every quarter warp); the kernel was bound by exactly that.  Slot s of the table
-// lives in bank group s mod 8, so a quarter warp whose eight lanes read slots of eight different residues
-// is conflict free (4 wavefronts).  The C draws of a replicate are therefore made in two exact stages:
-//  1. how many of the C draws fall into each residue class k (size_k = slots = k mod 8): a multinomial with
-//     probabilities size_k / (C+1).  With S = C+1 = 8*base + rem the classes k < rem hold one slot more, so a
-//     draw is "regular" (uniform over the 8 classes: three random bits) with probability 8*base/S and
-//     "special" (uniform over the classes k < rem) with probability rem/S.  The number of special draws
-//     M ~ Binomial(C, rem/S) (mean < 7) is sampled by inversion against a host-built CDF; the C-M regular
-//     labels are counted with bit-plane popcounts, ten 3-bit labels per Philox word.
-//  2. lane l serves class l mod 8 (four lanes per class) and draws its share of that class's count
-//     uniformly inside the class: slot = 8*j + k, j uniform in [0, size_k).
-// Stage 1 then 2 is the same distribution as C uniform draws from the C+1 slots (wg:885): class counts
-// multinomial, uniform within a class.
-constexpr int kMcdf = 64;
-
-__device__ __forceinline__ void banked_replicate(const double2 *__restrict__ A, const double2 *__restrict__ D, uint32_t C,
-                                                 const double *__restrict__ cdf, uint64_t b, uint32_t p, uint2 key,
-                                                 uint32_t stream_id, int lane, double &s0, double &s1, double &s2, double &s3)
-{
-    const uint32_t S = C + 1, base = S >> 3, rem = S & 7u;
-    const uint32_t k = (uint32_t)lane & 7u, q = (uint32_t)lane >> 3;
-    const uint32_t size_k = base + (k < rem ? 1u : 0u);
-    const uint32_t c1 = (uint32_t)b, c2 = (uint32_t)(b >> 32) ^ (p << 8);
-
-    // ---- stage 1: class counts
-    const uint4 w = philox4x32_10(make_uint4(((uint32_t)lane << 16) | (2u << 24), c1, c2, stream_id), key);
-    const uint32_t w0 = __shfl_sync(kFull, w.x, 0), w1 = __shfl_sync(kFull, w.y, 0);
-    const double u = (double)(((unsigned long long)w0 << 21) | (unsigned long long)(w1 >> 11)) * 0x1.0p-53;
-    uint32_t M = 0;
-    while (M < kMcdf - 1 && u >= __ldg(cdf + M)) M++;
-    M = min(M, C);
-    const uint32_t R = C - M;
-    uint32_t t0 = 0, t1 = 0, t2 = 0, t01 = 0, t02 = 0, t12 = 0, t012 = 0;
-    const uint32_t n_calls = (R + 39) / 40;
-    for (uint32_t c = lane; c < n_calls; c += 32) {
-        const uint4 x = philox4x32_10(make_uint4(c | (1u << 24), c1, c2, stream_id), key);
-        const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-        for (int wi = 0; wi < 4; wi++) {
-            const uint32_t first = 40 * c + 10 * wi;
-            const uint32_t nf = R > first ? min(10u, R - first) : 0u;                    // labels of this word that count
-            const uint32_t ones = 0x09249249u & (nf >= 10 ? 0x3FFFFFFFu : ((1u << (3 * nf)) - 1u));
-            const uint32_t b0 = xs[wi] & ones, b1 = (xs[wi] >> 1) & ones, b2 = (xs[wi] >> 2) & ones;
-            t0 += __popc(b0); t1 += __popc(b1); t2 += __popc(b2);
-            t01 += __popc(b0 & b1); t02 += __popc(b0 & b2); t12 += __popc(b1 & b2); t012 += __popc(b0 & b1 & b2);
-        }
-    }
-    unsigned long long sp = 0;                    // special draws per class, 8-bit fields (M < 64)
-    if (rem) {
-        if ((uint32_t)lane < M) sp += 1ull << (8 * __umulhi(w.z, rem));
-        if ((uint32_t)lane + 32 < M) sp += 1ull << (8 * __umulhi(w.w, rem));
-    }
-    const uint32_t pa = __reduce_add_sync(kFull, t0 | (t1 << 16)), pb = __reduce_add_sync(kFull, t2 | (t01 << 16)),
-                   pc = __reduce_add_sync(kFull, t02 | (t12 << 16)), T012 = __reduce_add_sync(kFull, t012);
-    const uint32_t spl = __reduce_add_sync(kFull, (uint32_t)sp), sph = __reduce_add_sync(kFull, (uint32_t)(sp >> 32));
-    const uint32_t T0 = pa & 0xFFFFu, T1 = pa >> 16, T2 = pb & 0xFFFFu, T01 = pb >> 16, T02 = pc & 0xFFFFu, T12 = pc >> 16;
-    uint32_t n[8];
-    n[7] = T012; n[3] = T01 - n[7]; n[5] = T02 - n[7]; n[6] = T12 - n[7];
-    n[1] = T0 - n[3] - n[5] - n[7]; n[2] = T1 - n[3] - n[6] - n[7]; n[4] = T2 - n[5] - n[6] - n[7];
-    n[0] = R - (n[1] + n[2] + n[3] + n[4] + n[5] + n[6] + n[7]);
-    uint32_t mine = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) mine = k == (uint32_t)j ? n[j] : mine;
-    mine += ((k < 4 ? spl : sph) >> (8 * (k & 3u))) & 0xFFu;
-
-    // ---- stage 2: the lane's share of its class, uniform inside the class.  Idle draws read slot 0 (the zero row);
-    // both halves of a row are always read: a conflict-free gather costs four wavefronts whether 3 or 32 lanes take part.
-    const uint32_t my_draws = mine > q ? (mine - q + 3) >> 2 : 0u;
-    const uint32_t quads = (__reduce_max_sync(kFull, my_draws) + 3) >> 2;
-    const uint32_t a_base = (uint32_t)__cvta_generic_to_shared(A), d_off = (uint32_t)((const char *)D - (const char *)A);
-    for (uint32_t t = 0; t < quads; t++) {
-        const uint4 r4 = philox4x32_10(make_uint4(t | ((uint32_t)lane << 16), c1, c2, stream_id), key);
-        const uint32_t uu[4] = {r4.x, r4.y, r4.z, r4.w};
-        double2 a[4], d[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t ofs = 4 * t + j < my_draws ? __umulhi(uu[j], size_k) * 128u + k * 16u : 0u;      // byte offset of the slot
-            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a[j].x), "=d"(a[j].y) : "r"(a_base + ofs));
-            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(d[j].x), "=d"(d[j].y) : "r"(a_base + ofs + d_off));
-        }
-        s0 += (fabs(a[0].x) + fabs(a[1].x)) + (fabs(a[2].x) + fabs(a[3].x));
-        s1 += (a[0].y + a[1].y) + (a[2].y + a[3].y);
-        s2 += (d[0].x + d[1].x) + (d[2].x + d[3].x);
-        s3 += (d[0].y + d[1].y) + (d[2].y + d[3].y);
-    }
-}
-
-// MODE 0: gathers from global memory (product too large for shared memory); 1: shared-memory table, direct
-// draws; 2: shared-memory table, banked sampler.
-template <int MODE>
+// (A banked two-stage sampler -- class counts per shared-memory bank group first, then conflict-free draws inside
+// the lane's class; exact, 49 M -> 30 M wavefronts -- was measured at 226 us against 212 us for the direct draws
+// below: its extra instructions cost more than the conflicts.  See profiles/README.md and the git history.)
+template <bool SMEM>
 __global__ void __launch_bounds__(kBootWarps * 32)
 k_bootstrap(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, const int *__restrict__ order, int n_products,
-            int64_t b_first, int64_t b_count, uint2 key, uint32_t stream_id, const double *__restrict__ mcdf,
-            double *__restrict__ rep, double *__restrict__ vals)
+            int64_t b_first, int64_t b_count, uint2 key, uint32_t stream_id, double *__restrict__ rep, double *__restrict__ vals)
 {
-    constexpr bool SMEM = MODE != 0;
     extern __shared__ double2 s_tab[];
     __shared__ double2 s_sums[kBootWarps * kBootRepsPerWarp][2];     // the block's replicate sums, for the dense epilogue
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -890,9 +801,6 @@ k_bootstrap(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, 
         if (bl >= b_count) continue;
         const uint64_t b = (uint64_t)(b_first + bl);
         double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-        if (MODE == 2) {
-            banked_replicate(A, D, C, mcdf + (size_t)p * kMcdf, b, (uint32_t)p, key, stream_id, lane, s0, s1, s2, s3);
-        } else
         for (uint32_t q = lane; q < nquad; q += 32) {
             const uint4 u = philox4x32_10(make_uint4(q, (uint32_t)b, (uint32_t)(b >> 32) ^ ((uint32_t)p << 8), stream_id), key);
             const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
@@ -1158,26 +1066,21 @@ void launch_product_sums(const double *d_stats4, const int64_t *d_prod_ofs, int 
 }
 
 void launch_bootstrap(const double *d_stats4, const int64_t *d_prod_ofs, const int *d_order, int n_products, int64_t max_codons,
-                      int64_t b_first, int64_t b_count, uint64_t seed, uint32_t stream_id, const double *d_mcdf, double *d_rep,
-                      double *d_vals, cudaStream_t stream)
+                      int64_t b_first, int64_t b_count, uint64_t seed, uint32_t stream_id, double *d_rep, double *d_vals,
+                      cudaStream_t stream)
 {
     if (n_products <= 0 || b_count <= 0) return;
     const int64_t per_block = (int64_t)kBootWarps * kBootRepsPerWarp;
     dim3 grid((unsigned)((b_count + per_block - 1) / per_block), (unsigned)n_products);
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     const size_t smem = (size_t)(max_codons + 1) * 32;
-    static const int mode_env = [] { const char *v = getenv("SNPG_BOOT_MODE"); return v ? atoi(v) : 2; }();   // tuning knob
-    if (smem <= (size_t)kBootSmemLimit && d_mcdf && mode_env == 2) {
-        cudaFuncSetAttribute(k_bootstrap<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBootSmemLimit);  // per device
-        k_bootstrap<2><<<grid, kBootWarps * 32, smem, stream>>>(d_stats4, d_prod_ofs, d_order, n_products, b_first, b_count, key,
-                                                                 stream_id, d_mcdf, d_rep, d_vals);
-    } else if (smem <= (size_t)kBootSmemLimit) {
-        cudaFuncSetAttribute(k_bootstrap<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBootSmemLimit);
-        k_bootstrap<1><<<grid, kBootWarps * 32, smem, stream>>>(d_stats4, d_prod_ofs, d_order, n_products, b_first, b_count, key,
-                                                                 stream_id, d_mcdf, d_rep, d_vals);
+    if (smem <= (size_t)kBootSmemLimit) {
+        cudaFuncSetAttribute(k_bootstrap<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBootSmemLimit);  // per device
+        k_bootstrap<true><<<grid, kBootWarps * 32, smem, stream>>>(d_stats4, d_prod_ofs, d_order, n_products, b_first, b_count, key,
+                                                                    stream_id, d_rep, d_vals);
     } else {
-        k_bootstrap<0><<<grid, kBootWarps * 32, 0, stream>>>(d_stats4, d_prod_ofs, d_order, n_products, b_first, b_count, key,
-                                                              stream_id, d_mcdf, d_rep, d_vals);
+        k_bootstrap<false><<<grid, kBootWarps * 32, 0, stream>>>(d_stats4, d_prod_ofs, d_order, n_products, b_first, b_count, key,
+                                                                  stream_id, d_rep, d_vals);
     }
 }
 

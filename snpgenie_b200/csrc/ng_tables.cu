@@ -86,24 +86,4 @@ void build_tables(double *sites /*[64][2]*/, double *diffs /*[2][64][64]*/) {
     }
 }
 
-// CDF of M ~ Binomial(C, rem/S), S = C+1, rem = S mod 8: how many of a replicate's C draws are "special"
-// in the bootstrap kernel's banked sampler (kernels.cu).  out[m] = P(M <= m), out[kBootMcdf-1] = 1.
-void build_boot_mcdf(int64_t C, double *out)
-{
-    const int64_t S = C + 1;
-    const int rem = (int)(S & 7);
-    if (rem == 0) { for (int m = 0; m < kBootMcdf; m++) out[m] = 1.0; return; }                      // never special
-    if (S < 8) { for (int m = 0; m < kBootMcdf; m++) out[m] = m >= C ? 1.0 : 0.0; return; }          // always special
-    const long double pi = (long double)rem / (long double)S;
-    long double pm = expl((long double)C * log1pl(-pi)), cum = 0.0L;
-    const long double ratio = pi / (1.0L - pi);
-    for (int m = 0; m < kBootMcdf; m++) {
-        cum += pm;
-        out[m] = cum < 1.0L ? (double)cum : 1.0;
-        pm = pm * (long double)(C - m) / (long double)(m + 1) * ratio;
-        if (pm < 0) pm = 0;
-    }
-    out[kBootMcdf - 1] = 1.0;
-}
-
 }  // namespace snpg

@@ -111,13 +111,9 @@ void launch_product_sums(const double *d_stats4, const int64_t *d_prod_ofs, int 
 // max_codons = largest product (sizes the shared-memory table; larger than the
 // limit falls back to gathers from global memory).  Outputs (either may be null):
 // d_rep[p][b][4] replicate sums, d_vals[which][p][b] per-replicate dN, dS, dN-dS, JC x3.
-// d_mcdf[p][kBootMcdf] (build_boot_mcdf per product; may be null): CDF of the number of "special" draws of
-// the banked sampler, see kernels.cu.
-constexpr int kBootMcdf = 64;
-void build_boot_mcdf(int64_t n_codons, double *out /*[kBootMcdf]*/);
 void launch_bootstrap(const double *d_stats4, const int64_t *d_prod_ofs, const int *d_order, int n_products, int64_t max_codons,
-                      int64_t b_first, int64_t b_count, uint64_t seed, uint32_t stream_id, const double *d_mcdf, double *d_rep,
-                      double *d_vals, cudaStream_t stream);
+                      int64_t b_first, int64_t b_count, uint64_t seed, uint32_t stream_id, double *d_rep, double *d_vals,
+                      cudaStream_t stream);
 // one Philox4x32-10 block on the device (known-answer test hook)
 void launch_philox_kat(const uint32_t *ctr, const uint32_t *key, uint32_t *d_out, cudaStream_t stream);
 // K6: rep[item][B][4] -> se[item][6]: sample SD (n-1) of the per-replicate dN, dS, dN-dS and their Jukes-Cantor forms

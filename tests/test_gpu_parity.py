@@ -309,9 +309,8 @@ def test_bootstrap_product_statistics(eng):
 
 @pytest.mark.parametrize("C", [1, 5, 6, 7, 8, 13, 64, 203, 1000])
 def test_bootstrap_draws_are_uniform_over_slots(eng, C):
-    """The banked sampler (class counts first, then uniform inside a bank-group class) must still draw every
-    one of the C+1 slots (slot 0 = the reference's empty codon, wg:885) with probability 1/(C+1), jointly
-    multinomial: the replicate sum of an indicator row counts the draws of that slot."""
+    """Every one of the C+1 slots (slot 0 = the reference's empty codon, wg:885) is drawn with probability
+    1/(C+1), jointly multinomial: the replicate sum of an indicator row counts the draws of that slot."""
     B = 40000
     p = 1.0 / (C + 1)
     mean, var = C * p, C * p * (1 - p)
