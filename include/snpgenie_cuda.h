@@ -192,6 +192,18 @@ int snpg_windows(snpg_ctx *ctx, const double *stats4, const uint8_t *keep, int64
  * combine slices (see snpg_stats_device / bench.py). */
 int snpg_within_all(snpg_ctx *ctx, int group, int64_t B, double *prod_sums, double *prod_se);
 
+/* Between-group analysis of every pair of the listed groups and every product in ONE call with a single
+ * synchronisation: the device-resident counterpart of the between driver's group-pair loop
+ * (snpgenie_between_group.pl:410-423, per-codon values :680-947) followed by the between processor's
+ * filtered product sums (snpgenie_between_group_processor.pl:412-467) and whole-product bootstrap
+ * (:869-1102).  Pairs are ordered (g[0],g[1]), (g[0],g[2]), ..., (g[n-2],g[n-1]).  A codon is kept when
+ * n_def_a + n_def_b >= min_taxa_total (if > 0) and min(n_def_a, n_def_b) >= min_taxa_group (if > 0); any other
+ * codon contributes nothing to the sums or to a bootstrap draw.
+ * pair_sums [n_pairs][P][4] (N_sites, S_sites, N_diffs, S_diffs); pair_se [n_pairs][P][6] (SE of dN, dS,
+ * dN-dS and their Jukes-Cantor forms; may be NULL, and is not computed for B < 2). */
+int snpg_between_all(snpg_ctx *ctx, const int *groups, int n_groups, int64_t min_taxa_total, int64_t min_taxa_group, int64_t B,
+                     double *pair_sums, double *pair_se);
+
 /* Load + snpg_within_all as ONE call with a single synchronisation at the end: the
  * whole within-group job for a product-level answer (what the within driver's product
  * table needs).  bases is a host pointer (bases_on_device = 0; must stay valid until

@@ -56,6 +56,7 @@ SIGNATURES = {
     "snpg_bootstrap_product": (C.c_int, [_ctx, _f64p, _u8p, C.c_int64, C.c_int64, _f64p, _f64p]),
     "snpg_windows": (C.c_int, [_ctx, _f64p, _u8p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _f64p, _f64p, _i64p]),
     "snpg_within_all": (C.c_int, [_ctx, C.c_int, C.c_int64, _f64p, _f64p]),
+    "snpg_between_all": (C.c_int, [_ctx, C.POINTER(C.c_int), C.c_int, C.c_int64, C.c_int64, C.c_int64, _f64p, _f64p]),
     "snpg_within_job": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, _f64p, _f64p]),
     "snpg_within_stats_device": (C.c_int, [_ctx, C.c_int, C.c_void_p]),
     "snpg_bootstrap_all_device": (C.c_int, [_ctx, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),

@@ -1016,6 +1016,57 @@ int snpg_rep_moments_device(snpg_ctx *ctx, const double *d_rep, int64_t n_items,
     return SNPG_OK;
 }
 
+int snpg_between_all(snpg_ctx *ctx, const int *groups, int n_groups, int64_t min_taxa_total, int64_t min_taxa_group, int64_t B,
+                     double *pair_sums, double *pair_se) {
+    if (!ctx) return SNPG_E_ARG;
+    NEED(ctx, groups && n_groups >= 2 && n_groups <= SNPG_MAX_GROUPS && pair_sums, SNPG_E_ARG, "bad between_all arguments");
+    NEED(ctx, min_taxa_total >= 0 && min_taxa_group >= 0 && min_taxa_total < ((int64_t)1 << 32) && min_taxa_group < ((int64_t)1 << 32),
+         SNPG_E_ARG, "bad min-taxa criteria");
+    for (int i = 0; i < n_groups; i++)
+        if (int rc = check_group(ctx, groups[i])) return rc;
+    if (int rc = bind(ctx)) return rc;
+    const int P = ctx->n_products;
+    const int64_t cnt = ctx->shard_count;
+    const int n_pairs = n_groups * (n_groups - 1) / 2;
+    const bool boot = pair_se && B >= 2;
+    CU(ctx, ctx->s_stats.ensure(sizeof(double) * 4 * (size_t)std::max<int64_t>(1, cnt)));
+    CU(ctx, ctx->s_nda.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, cnt)));
+    CU(ctx, ctx->s_ndb.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, cnt)));
+    CU(ctx, ctx->s_sums.ensure(sizeof(double) * 4 * (size_t)(P * n_pairs)));
+    if (boot) {
+        CU(ctx, ctx->s_vals.ensure(sizeof(double) * 6 * (size_t)(B * P)));
+        CU(ctx, ctx->s_se.ensure(sizeof(double) * 6 * (size_t)(P * n_pairs)));
+    }
+    int pair = 0;
+    for (int i = 0; i < n_groups; i++) {
+        for (int j = i + 1; j < n_groups; j++, pair++) {
+            const Group &ga = ctx->groups[groups[i]], &gb = ctx->groups[groups[j]];
+            StatsOut o{nullptr, ctx->s_nda.as<uint32_t>(), ctx->s_ndb.as<uint32_t>(), nullptr, ctx->s_stats.as<double>(), nullptr};
+            { Launch l(ctx, SNPG_K_STATS); launch_between_stats(view_of(ctx, ga, 0), view_of(ctx, gb, 0), cnt, ctx->d_tables.as<double>(), o, ctx->stream); }
+            if (min_taxa_total > 0 || min_taxa_group > 0) {
+                Launch l(ctx, SNPG_K_OTHER);
+                launch_taxa_filter(ctx->s_stats.as<double>(), ctx->s_nda.as<uint32_t>(), ctx->s_ndb.as<uint32_t>(), cnt,
+                                   (uint32_t)min_taxa_total, (uint32_t)min_taxa_group, ctx->stream);
+            }
+            { Launch l(ctx, SNPG_K_SUMS); launch_product_sums(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), P, ctx->s_sums.as<double>() + 4 * (size_t)P * pair, ctx->stream); }
+            if (boot) {
+                {
+                    Launch l(ctx, SNPG_K_BOOT);
+                    launch_bootstrap(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), ctx->d_order_local.as<int>(), P,
+                                     ctx->max_codons_local, 0, B, ctx->seed, 0x50000u + ctx->call_id++, nullptr, ctx->s_vals.as<double>(),
+                                     ctx->stream);
+                }
+                { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->s_vals.as<double>(), P, B, ctx->s_se.as<double>() + 6 * (size_t)P * pair, ctx->stream); }
+            }
+        }
+    }
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(pair_sums, ctx->s_sums.p, sizeof(double) * 4 * (size_t)(P * n_pairs), cudaMemcpyDeviceToHost, ctx->stream));
+    if (boot) CU(ctx, cudaMemcpyAsync(pair_se, ctx->s_se.p, sizeof(double) * 6 * (size_t)(P * n_pairs), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, sync_stream(ctx));
+    return SNPG_OK;
+}
+
 int snpg_within_all(snpg_ctx *ctx, int group, int64_t B, double *prod_sums, double *prod_se) {
     if (!ctx) return SNPG_E_ARG;
     if (int rc = check_group(ctx, group)) return rc;

@@ -689,6 +689,22 @@ k_stats(GroupView A, GroupView B, int64_t n_codons, const double *__restrict__ t
     }
 }
 
+// min-taxa codon filters of the between-group processor (bgp:412-467, :929-970): a codon that fails them
+// contributes nothing to the sums, the windows or a bootstrap draw -- its row is zeroed in place.
+__global__ void k_taxa_filter(double *__restrict__ stats4, const uint32_t *__restrict__ ndef_a, const uint32_t *__restrict__ ndef_b,
+                              int64_t n_codons, uint32_t min_total, uint32_t min_group)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_codons) return;
+    const uint32_t a = ndef_a[c], b = ndef_b[c];
+    const bool keep = (min_total == 0 || a + b >= min_total) && (min_group == 0 || min(a, b) >= min_group);
+    if (!keep) {
+        double2 *o = reinterpret_cast<double2 *>(stats4 + 4 * c);
+        o[0] = make_double2(0.0, 0.0);
+        o[1] = make_double2(0.0, 0.0);
+    }
+}
+
 // product sums (wg:690-693; bg:984-1005): fixed-shape tree, deterministic
 constexpr int kSumThreads = 1024;
 __global__ void __launch_bounds__(kSumThreads)
@@ -1056,6 +1072,13 @@ void launch_between_stats(GroupView A, GroupView B, int64_t n_codons, const doub
     if (n_codons <= 0) return;
     k_stats<true><<<(unsigned)((n_codons + kStatsWarps - 1) / kStatsWarps), kStatsWarps * 32, 0, stream>>>(A, B, n_codons,
                                                                                                           d_tables, out);
+}
+
+void launch_taxa_filter(double *d_stats4, const uint32_t *d_ndef_a, const uint32_t *d_ndef_b, int64_t n_codons, uint32_t min_total,
+                        uint32_t min_group, cudaStream_t stream)
+{
+    if (n_codons <= 0 || (min_total == 0 && min_group == 0)) return;
+    k_taxa_filter<<<(unsigned)((n_codons + 255) / 256), 256, 0, stream>>>(d_stats4, d_ndef_a, d_ndef_b, n_codons, min_total, min_group);
 }
 
 void launch_product_sums(const double *d_stats4, const int64_t *d_prod_ofs, int n_products, double *d_sums,

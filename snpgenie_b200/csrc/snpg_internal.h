@@ -102,6 +102,10 @@ void launch_within_stats(GroupView A, int64_t n_codons, const double *d_tables, 
 void launch_between_stats(GroupView A, GroupView B, int64_t n_codons, const double *d_tables, StatsOut out,
                           cudaStream_t stream);
 
+// between-group min-taxa filters (bgp:412-467): zero the rows of the codons that fail (0 = criterion off)
+void launch_taxa_filter(double *d_stats4, const uint32_t *d_ndef_a, const uint32_t *d_ndef_b, int64_t n_codons, uint32_t min_total,
+                        uint32_t min_group, cudaStream_t stream);
+
 // product sums: sums[p][4] = sum over codons [ofs[p], ofs[p+1]) of stats4
 void launch_product_sums(const double *d_stats4, const int64_t *d_prod_ofs, int n_products, double *d_sums,
                          cudaStream_t stream);

@@ -217,6 +217,17 @@ class Engine:
         self._ck(_abi.lib.snpg_within_all(self._ctx, group, B, _ptr(sums, C.c_double), _ptr(se, C.c_double)))
         return sums, se
 
+    def between_all(self, groups: list[int], B: int = 0, min_taxa_total: int = 0, min_taxa_group: int = 0):
+        """Every pair of `groups` x every product in one ABI call: filtered product sums [pairs, P, 4] and, for
+        B >= 2, bootstrap SEs [pairs, P, 6].  Pairs in the order (g0,g1), (g0,g2), ..., (g[n-2],g[n-1])."""
+        P, n = len(self.products), len(groups)
+        n_pairs = n * (n - 1) // 2
+        sums = np.zeros((n_pairs, P, 4))
+        se = np.zeros((n_pairs, P, 6)) if B >= 2 else None
+        g = (C.c_int * n)(*groups)
+        self._ck(_abi.lib.snpg_between_all(self._ctx, g, n, min_taxa_total, min_taxa_group, B, _ptr(sums, C.c_double), _ptr(se, C.c_double)))
+        return sums, se
+
     def within_job(self, group: int, ptr: int, n_seqs: int, aln_len: int, row_stride: int, device: bool, B: int = 0):
         """Load + within_all in one ABI call (one synchronisation): per-product sums [P,4], SEs [P,6]."""
         P = len(self.products)

@@ -672,6 +672,85 @@ def test_config4_full_size_between_properties(eng):
                     assert close(ab[k], want[k]), (p.name, a, b, k)
 
 
+def test_between_all_matches_per_pair_calls(eng):
+    """snpg_between_all (every group pair x every product, filters, sums, bootstrap in one call) against the
+    per-(pair, product) calls plus host-side filtering -- the route the Perl processor takes."""
+    products = synth.hiv_products()
+    L = 9719
+    rng = np.random.default_rng(77)
+    groups = []
+    for g, n in enumerate((40, 25, 31)):
+        a = synth.make_alignment(n, L, products, 700 + g, gap_frac=0.06, n_frac=0.03, iupac_frac=0.004)
+        cols = rng.integers(800, 9000, size=60)
+        a[:, cols] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=60)]
+        groups.append(a)
+    eng.set_products(products, L)
+    for g, a in enumerate(groups):
+        eng.load_group(g, a)
+    pairs = [(0, 1), (0, 2), (1, 2)]
+    for tot, grp in ((0, 0), (60, 0), (0, 24), (58, 23)):
+        sums, se = eng.between_all([0, 1, 2], B=4000, min_taxa_total=tot, min_taxa_group=grp)
+        assert sums.shape == (3, len(products), 4) and se.shape == (3, len(products), 6)
+        for k, (a, b) in enumerate(pairs):
+            for i, p in enumerate(products):
+                r = eng.between(a, b, i)
+                n1, n2 = r["ndef_a"].astype(np.int64), r["ndef_b"].astype(np.int64)
+                keep = np.ones(len(n1), dtype=bool)
+                if tot:
+                    keep &= (n1 + n2) >= tot
+                if grp:
+                    keep &= np.minimum(n1, n2) >= grp
+                want = (r["stats4"] * keep[:, None]).sum(axis=0)
+                assert close(sums[k, i], want, rtol=1e-12, atol=1e-12), (tot, grp, a, b, p.name)
+        # SE of one pair/product against the stand-alone bootstrap with the same keep mask
+        r = eng.between(0, 2, 1)
+        n1, n2 = r["ndef_a"].astype(np.int64), r["ndef_b"].astype(np.int64)
+        keep = ((tot == 0) | ((n1 + n2) >= tot)) & ((grp == 0) | (np.minimum(n1, n2) >= grp))
+        _, se1 = eng.bootstrap_product(r["stats4"], 8000, keep=keep.astype(np.uint8))
+        ok = se1[:3] > 0
+        assert np.all(np.abs(se[1, 1, :3][ok] / se1[:3][ok] - 1) < 0.1), (tot, grp, se[1, 1], se1)
+    # no bootstrap requested: sums only
+    sums0, se0 = eng.between_all([0, 1, 2], B=0)
+    sums1, _ = eng.between_all([0, 1, 2], B=4000)
+    assert se0 is None and np.array_equal(sums0, sums1)
+    # a different order of groups is a different order of pairs
+    sums2, _ = eng.between_all([2, 0], B=0)
+    assert close(sums2[0], sums0[1], rtol=1e-13)
+
+
+@pytest.mark.parametrize("route", ["fused", "tiles", "codes"])
+def test_more_than_2_20_rows(route):
+    """Config-5-sized row counts (> 2^20 sequences) cross the per-launch row limit of the device-resident path
+    and the row-block staging of the host path; counts must stay exact."""
+    import torch
+    from snpgenie_b200 import _abi
+    from snpgenie_b200.engine import Engine
+    n, L = (1 << 20) + 70001, 160
+    rng = np.random.default_rng(5)
+    anc = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=L)]
+    aln = np.repeat(anc[None, :], n, axis=0)
+    hit = rng.random((n, L)) < 0.01
+    aln[hit] = np.frombuffer(b"ACGTN-", dtype=np.uint8)[rng.integers(0, 6, size=int(hit.sum()))]
+    aln[-1, :] = ord("T")                                        # the very last row must be counted
+    products = [hostio.Product("a", 1, [2], [151]), hostio.Product("b", -1, [5], [154])]
+    want = []
+    for p in products:
+        raw, codes = _oracle_product(aln, p)
+        want.append(orc.hist(codes))
+    with Engine(device=0, keep_codes=(route == "codes")) as e:
+        if route == "tiles":
+            e.set_option(_abi.OPT_FUSED_KERNEL, _abi.FUSED_TMA_TILES)
+        e.set_products(products, L)
+        e.load_group(0, aln)
+        for i in range(len(products)):
+            assert (e.hist(0, i)[0] == want[i]).all(), (route, "host", i)
+        d = torch.from_numpy(aln).cuda()                         # pitch 160: a multiple of 16
+        e.load_group_ptr(1, d.data_ptr(), n, L, L, device=True)
+        for i in range(len(products)):
+            assert (e.hist(1, i)[0] == want[i]).all(), (route, "device", i)
+        assert e.group_size(1) == n
+
+
 # ----------------------------------------------------------------- edge cases
 
 @pytest.mark.parametrize("keep", [True, False])
