@@ -171,6 +171,11 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # the contract is ONE JSON line on stdout: NCCL prints its version banner to fd 1, so everything but the
+    # final line goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
@@ -225,6 +230,7 @@ def run_ours(args):
         barrier()
         ms = e0.elapsed_time(e1)
         if world > 1:
+            print(f"[rank {rank}] {fn.__name__}: {ms / steps:.4f} ms/step", file=sys.stderr)
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
@@ -298,7 +304,8 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             v, threads, sample = cpu_pair_rate(12.0)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
     eng.close()
     if world > 1:
         dist.destroy_process_group()
