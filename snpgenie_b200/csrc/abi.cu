@@ -72,7 +72,7 @@ struct snpg_ctx {
     // fused path (no code matrix): 16-byte column spans starting at base_al
     int64_t base_al = 0, n_spans = 0;     // base_al = col_lo rounded down to 16
     int64_t n_irr = 0;                    // codons the span runs cannot express
-    DevBuf d_runs, d_regular, d_irr_map, d_irr_idx, d_cons, d_alt, d_cons_code, d_cons_key;
+    DevBuf d_runs, d_regular, d_irr_map, d_irr_idx, d_cons, d_alt;
     DevBuf t_codes, t_hist, t_other;      // irregular codons: compact K1+K2 scratch
     // TMA-tiled variant of the fused path: frame-aligned tiles of <= 64 codons over the regular codons
     DevBuf d_tiles, d_sched;              // d_sched: the tile kernel's chunk counter and finished-CTA counter
@@ -233,11 +233,6 @@ int pack_block(snpg_ctx *ctx, Group &g, const uint8_t *d_block, int64_t pitch, i
         launch_pack(d_block + (ctx->col_lo - ctx->base_al), pitch, rows, r0, ctx->d_map.as<CodonMap>(), ctx->shard_count,
                     g.codes.as<uint8_t>(), g.n_pad, omin, omax, ctx->stream);
     } else {
-        if (r0 == 0) {
-            Launch l(ctx, SNPG_K_OTHER);
-            launch_cons_codes(ctx->d_cons.as<uint8_t>(), ctx->col_lo - ctx->base_al, ctx->d_map.as<CodonMap>(), ctx->shard_count,
-                              ctx->d_cons_code.as<uint8_t>(), ctx->d_cons_key.as<uint32_t>(), ctx->stream);
-        }
         {
             Launch l(ctx, SNPG_K_FUSED);
             alignas(64) unsigned char tmap[128];
@@ -248,7 +243,7 @@ int pack_block(snpg_ctx *ctx, Group &g, const uint8_t *d_block, int64_t pitch, i
                 ctx->tile_launches++;
             } else {
                 launch_fused_hist(d_block, pitch, rows, ctx->d_cons.as<uint8_t>(), ctx->d_alt.as<uint32_t>(), ctx->n_spans, ctx->d_runs.as<SpanRun>(),
-                                  ctx->d_cons_code.as<uint8_t>(), g.hist.as<uint32_t>(), omin, omax, ctx->stream);
+                                  g.hist.as<uint32_t>(), omin, omax, ctx->stream);
             }
         }
         if (ctx->n_irr) {
@@ -273,7 +268,7 @@ int finish_group(snpg_ctx *ctx, Group &g) {
     } else {
         {
             Launch l(ctx, SNPG_K_OTHER);
-            launch_fused_fixup(ctx->d_cons_code.as<uint8_t>(), ctx->d_cons_key.as<uint32_t>(), ctx->d_regular.as<uint8_t>(),
+            launch_fused_fixup(ctx->d_cons.as<uint8_t>(), ctx->col_lo - ctx->base_al, ctx->d_map.as<CodonMap>(), ctx->d_regular.as<uint8_t>(),
                                ctx->shard_count, (uint32_t)g.n, g.hist.as<uint32_t>(), omin, omax, ctx->stream);
         }
         if (ctx->n_irr) {
@@ -348,7 +343,7 @@ void snpg_destroy(snpg_ctx *ctx) {
     for (auto &g : ctx->groups) { g.codes.release(); g.hist.release(); g.other.release(); g.sites.release(); }
     for (auto &h : ctx->host_aln) if (h.p) cudaFreeHost(h.p);
     DevBuf *bufs[] = {&ctx->d_map, &ctx->d_local_ofs, &ctx->d_full_ofs, &ctx->d_tables, &ctx->staging[0], &ctx->staging[1],
-                      &ctx->d_runs, &ctx->d_tiles, &ctx->d_sched, &ctx->d_regular, &ctx->d_irr_map, &ctx->d_irr_idx, &ctx->d_cons, &ctx->d_alt, &ctx->d_cons_code, &ctx->d_cons_key, &ctx->t_codes, &ctx->t_hist,
+                      &ctx->d_runs, &ctx->d_tiles, &ctx->d_sched, &ctx->d_regular, &ctx->d_irr_map, &ctx->d_irr_idx, &ctx->d_cons, &ctx->d_alt, &ctx->t_codes, &ctx->t_hist,
                       &ctx->t_other,
                       &ctx->s_stats, &ctx->s_poly, &ctx->s_nda, &ctx->s_ndb, &ctx->s_cmp, &ctx->s_cons, &ctx->s_sums,
                       &ctx->s_rep, &ctx->s_se, &ctx->s_misc, &ctx->s_in, &ctx->s_vals, &ctx->d_order_local, &ctx->d_order_full};
@@ -539,8 +534,6 @@ int snpg_set_products(snpg_ctx *ctx, int n_products, const int64_t *seg_ofs, con
         CU(ctx, ctx->d_regular.ensure(regular.size()));
         CU(ctx, ctx->d_cons.ensure((size_t)(n_spans * 16 + 512)));     // the tile kernel copies 208-byte windows of it
         CU(ctx, ctx->d_alt.ensure(sizeof(uint32_t) * kAltWords * (size_t)std::max<int64_t>(1, n_spans)));
-        CU(ctx, ctx->d_cons_code.ensure(regular.size()));
-        CU(ctx, ctx->d_cons_key.ensure(sizeof(uint32_t) * regular.size()));
         CU(ctx, cudaMemcpy(ctx->d_runs.p, runs.data(), sizeof(SpanRun) * runs.size(), cudaMemcpyHostToDevice));
         CU(ctx, cudaMemcpy(ctx->d_regular.p, regular.data(), regular.size(), cudaMemcpyHostToDevice));
         CU(ctx, cudaMemset(ctx->d_cons.p, 0, (size_t)(n_spans * 16 + 512)));
@@ -918,7 +911,7 @@ int snpg_bootstrap_product(snpg_ctx *ctx, const double *stats4, const uint8_t *k
     {
         Launch l(ctx, SNPG_K_BOOT);
         launch_bootstrap(ctx->s_in.as<double>(), ctx->s_misc.as<int64_t>(), nullptr, 1, C, 0, B, ctx->seed, sid,
-                         sums_out ? ctx->s_rep.as<double>() : nullptr, ctx->s_vals.as<double>(), ctx->stream);
+                         sums_out ? ctx->s_rep.as<double>() : nullptr, ctx->s_vals.as<double>(), nullptr, ctx->stream);
     }
     { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->s_vals.as<double>(), 1, B, ctx->s_se.as<double>(), ctx->stream); }
     CU(ctx, cudaGetLastError());
@@ -986,7 +979,7 @@ int snpg_bootstrap_all_device(snpg_ctx *ctx, const double *d_stats4_full, int64_
     {
         Launch l(ctx, SNPG_K_BOOT);
         launch_bootstrap(d_stats4_full, ctx->d_full_ofs.as<int64_t>(), ctx->d_order_full.as<int>(), ctx->n_products, ctx->max_codons_full,
-                         b_first, b_count, ctx->seed, 0x30000u, d_rep_out, nullptr, ctx->stream);
+                         b_first, b_count, ctx->seed, 0x30000u, d_rep_out, nullptr, nullptr, ctx->stream);
     }
     CU(ctx, cudaGetLastError());
     CU(ctx, sync_stream(ctx));
@@ -1048,13 +1041,14 @@ int snpg_between_all(snpg_ctx *ctx, const int *groups, int n_groups, int64_t min
                 launch_taxa_filter(ctx->s_stats.as<double>(), ctx->s_nda.as<uint32_t>(), ctx->s_ndb.as<uint32_t>(), cnt,
                                    (uint32_t)min_taxa_total, (uint32_t)min_taxa_group, ctx->stream);
             }
-            { Launch l(ctx, SNPG_K_SUMS); launch_product_sums(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), P, ctx->s_sums.as<double>() + 4 * (size_t)P * pair, ctx->stream); }
+            double *d_pair_sums = ctx->s_sums.as<double>() + 4 * (size_t)P * pair;
+            if (!boot) { Launch l(ctx, SNPG_K_SUMS); launch_product_sums(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), P, d_pair_sums, ctx->stream); }
             if (boot) {
                 {
-                    Launch l(ctx, SNPG_K_BOOT);
+                    Launch l(ctx, SNPG_K_BOOT);      // also writes the product sums
                     launch_bootstrap(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), ctx->d_order_local.as<int>(), P,
                                      ctx->max_codons_local, 0, B, ctx->seed, 0x50000u + ctx->call_id++, nullptr, ctx->s_vals.as<double>(),
-                                     ctx->stream);
+                                     d_pair_sums, ctx->stream);
                 }
                 { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->s_vals.as<double>(), P, B, ctx->s_se.as<double>() + 6 * (size_t)P * pair, ctx->stream); }
             }
@@ -1078,8 +1072,8 @@ int snpg_within_all(snpg_ctx *ctx, int group, int64_t B, double *prod_sums, doub
     CU(ctx, ctx->s_sums.ensure(sizeof(double) * 4 * (size_t)P));
     StatsOut o{nullptr, nullptr, nullptr, nullptr, ctx->s_stats.as<double>(), nullptr};
     { Launch l(ctx, SNPG_K_STATS); launch_within_stats(view_of(ctx, g, 0), cnt, ctx->d_tables.as<double>(), o, ctx->stream); }
-    { Launch l(ctx, SNPG_K_SUMS); launch_product_sums(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), P, ctx->s_sums.as<double>(), ctx->stream); }
     const bool boot = prod_se && B >= 2;
+    if (!boot) { Launch l(ctx, SNPG_K_SUMS); launch_product_sums(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), P, ctx->s_sums.as<double>(), ctx->stream); }
     if (boot) {
         CU(ctx, ctx->s_vals.ensure(sizeof(double) * 6 * (size_t)(B * P)));
         CU(ctx, ctx->s_se.ensure(sizeof(double) * 6 * (size_t)P));
@@ -1087,7 +1081,7 @@ int snpg_within_all(snpg_ctx *ctx, int group, int64_t B, double *prod_sums, doub
             Launch l(ctx, SNPG_K_BOOT);
             launch_bootstrap(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), ctx->d_order_local.as<int>(), P,
                              ctx->max_codons_local, 0, B, ctx->seed, 0x40000u + ctx->call_id++, nullptr, ctx->s_vals.as<double>(),
-                             ctx->stream);
+                             ctx->s_sums.as<double>(), ctx->stream);      // also writes the product sums
         }
         { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->s_vals.as<double>(), P, B, ctx->s_se.as<double>(), ctx->stream); }
     }

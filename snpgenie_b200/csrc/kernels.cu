@@ -402,27 +402,10 @@ k_vote_refs(const uint8_t *__restrict__ aln, int64_t pitch, int n_sample, int64_
     }
 }
 
-// Code of the consensus row's codon for every codon (the fused kernel's reference point).
-__global__ void k_cons_codes(const uint8_t *__restrict__ cons, int64_t cons_shift, const CodonMap *__restrict__ map,
-                             int64_t n_codons, uint8_t *__restrict__ cons_code, uint32_t *__restrict__ cons_key)
-{
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n_codons) return;
-    const CodonMap m = map[c];
-    const uint8_t n0 = norm_char(cons[m.p0 + cons_shift], m.minus), n1 = norm_char(cons[m.p1 + cons_shift], m.minus),
-                  n2 = norm_char(cons[m.p2 + cons_shift], m.minus);
-    const uint8_t k0 = class_of(n0), k1 = class_of(n1), k2 = class_of(n2);
-    uint32_t code;
-    if (max(k0, max(k1, k2)) < 4) code = k0 * 16 + k1 * 4 + k2;
-    else if (k0 == 4 || k1 == 4 || k2 == 4) code = kCodeUndef;
-    else code = kCodeOther;
-    cons_code[c] = (uint8_t)code;
-    cons_key[c] = ((uint32_t)n0 << 16) | ((uint32_t)n1 << 8) | n2;
-}
-
-// After all row blocks: credit the consensus codon of every regular codon with the
-// rows that never reached the decode path.
-__global__ void k_fused_fixup(const uint8_t *__restrict__ cons_code, const uint32_t *__restrict__ cons_key,
+// After all row blocks: credit the consensus codon of every regular codon with the rows that never reached
+// the decode path.  The consensus codon's code (and, for an 'other' codon, its character key) comes straight
+// from the consensus row and the codon index map.
+__global__ void k_fused_fixup(const uint8_t *__restrict__ cons, int64_t cons_shift, const CodonMap *__restrict__ map,
                               const uint8_t *__restrict__ regular, int64_t n_codons, uint32_t n_rows,
                               uint32_t *__restrict__ hist, uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max)
 {
@@ -433,11 +416,19 @@ __global__ void k_fused_fixup(const uint8_t *__restrict__ cons_code, const uint3
     for (int b = 0; b < kHistBins; b++) seen += h[b];
     const uint32_t rest = n_rows - seen;       // rows that were never parked, or decoded to the consensus code
     if (rest) {
-        const uint32_t code = cons_code[c];
+        const CodonMap m = map[c];
+        const uint8_t n0 = norm_char(cons[m.p0 + cons_shift], m.minus), n1 = norm_char(cons[m.p1 + cons_shift], m.minus),
+                      n2 = norm_char(cons[m.p2 + cons_shift], m.minus);
+        const uint8_t k0 = class_of(n0), k1 = class_of(n1), k2 = class_of(n2);
+        uint32_t code;
+        if (max(k0, max(k1, k2)) < 4) code = k0 * 16 + k1 * 4 + k2;
+        else if (k0 == 4 || k1 == 4 || k2 == 4) code = kCodeUndef;
+        else code = kCodeOther;
         h[code] += rest;
         if (code == kCodeOther) {              // their codon string is the consensus string
-            other_min[c] = min(other_min[c], cons_key[c]);
-            other_max[c] = max(other_max[c], cons_key[c]);
+            const uint32_t key = ((uint32_t)n0 << 16) | ((uint32_t)n1 << 8) | n2;
+            other_min[c] = min(other_min[c], key);
+            other_max[c] = max(other_max[c], key);
         }
     }
 }
@@ -789,10 +780,12 @@ constexpr int kBootSmemLimit = 200 * 1024;
 template <bool SMEM>
 __global__ void __launch_bounds__(kBootWarps * 32)
 k_bootstrap(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, const int *__restrict__ order, int n_products,
-            int64_t b_first, int64_t b_count, uint2 key, uint32_t stream_id, double *__restrict__ rep, double *__restrict__ vals)
+            int64_t b_first, int64_t b_count, uint2 key, uint32_t stream_id, double *__restrict__ rep, double *__restrict__ vals,
+            double *__restrict__ prod_sums)
 {
     extern __shared__ double2 s_tab[];
     __shared__ double2 s_sums[kBootWarps * kBootRepsPerWarp][2];     // the block's replicate sums, for the dense epilogue
+    __shared__ double s_red[SMEM ? kBootWarps * 32 : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int p = order ? order[blockIdx.y] : blockIdx.y;
     const int64_t c0 = ofs[p];
@@ -810,6 +803,24 @@ k_bootstrap(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, 
             D[i + 1] = d;
         }
         __syncthreads();
+        if (prod_sums && blockIdx.x == 0) {
+            // the product's sums (wg:690-693), from the staged table: the additions and the tree of k_product_sums
+            double s[4] = {0, 0, 0, 0};
+            for (uint32_t c = threadIdx.x; c < C; c += blockDim.x) {
+                const double2 x = A[c + 1], y = D[c + 1];
+                s[0] += fabs(x.x); s[1] += x.y; s[2] += y.x; s[3] += y.y;
+            }
+            for (int q = 0; q < 4; q++) {
+                s_red[threadIdx.x] = s[q];
+                __syncthreads();
+                for (int h = kBootWarps * 32 / 2; h > 0; h >>= 1) {
+                    if ((int)threadIdx.x < h) s_red[threadIdx.x] += s_red[threadIdx.x + h];
+                    __syncthreads();
+                }
+                if (threadIdx.x == 0) prod_sums[4 * p + q] = s_red[0];
+                __syncthreads();
+            }
+        }
     }
     const uint32_t nquad = (C + 3) >> 2, full_quads = C >> 2;
     for (int k = 0; k < kBootRepsPerWarp; k++) {
@@ -998,31 +1009,23 @@ void launch_vote_refs(const uint8_t *d_aln, int64_t pitch, int n_sample, int64_t
     k_vote_refs<<<(unsigned)((n_spans + 1 + 7) / 8), 256, 0, stream>>>(d_aln, pitch, min(n_sample, 32), n_spans, d_cons, d_alt);
 }
 
-void launch_cons_codes(const uint8_t *d_cons, int64_t cons_shift, const CodonMap *d_map, int64_t n_codons, uint8_t *d_cons_code,
-                       uint32_t *d_cons_key, cudaStream_t stream)
-{
-    if (n_codons <= 0) return;
-    k_cons_codes<<<(unsigned)((n_codons + 127) / 128), 128, 0, stream>>>(d_cons, cons_shift, d_map, n_codons, d_cons_code, d_cons_key);
-}
-
 void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, const uint8_t *d_cons, const uint32_t *d_alt,
-                       int64_t n_spans, const SpanRun *d_runs, const uint8_t *d_cons_code, uint32_t *d_hist, uint32_t *d_other_min,
-                       uint32_t *d_other_max, cudaStream_t stream)
+                       int64_t n_spans, const SpanRun *d_runs, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max,
+                       cudaStream_t stream)
 {
     if (n_spans <= 0 || n_rows <= 0) return;
     static const int rows_per_warp = [] { const char *v = getenv("SNPG_SPAN_ROWS"); return v ? max(4, atoi(v)) : kFusedRowsPerWarp; }();
     const int64_t rows_per_block = (int64_t)kFusedWarps * rows_per_warp;
     dim3 grid((unsigned)((n_spans + 31) / 32), (unsigned)((n_rows + rows_per_block - 1) / rows_per_block));
-    (void)d_cons_code;
     k_fused_hist<<<grid, kFusedWarps * 32, 0, stream>>>(d_aln, pitch, n_rows, d_cons, d_alt, n_spans, d_runs, d_hist, d_other_min,
                                                         d_other_max, rows_per_warp);
 }
 
-void launch_fused_fixup(const uint8_t *d_cons_code, const uint32_t *d_cons_key, const uint8_t *d_regular, int64_t n_codons,
+void launch_fused_fixup(const uint8_t *d_cons, int64_t cons_shift, const CodonMap *d_map, const uint8_t *d_regular, int64_t n_codons,
                         uint32_t n_rows, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max, cudaStream_t stream)
 {
     if (n_codons <= 0) return;
-    k_fused_fixup<<<(unsigned)((n_codons + 127) / 128), 128, 0, stream>>>(d_cons_code, d_cons_key, d_regular, n_codons, n_rows, d_hist,
+    k_fused_fixup<<<(unsigned)((n_codons + 127) / 128), 128, 0, stream>>>(d_cons, cons_shift, d_map, d_regular, n_codons, n_rows, d_hist,
                                                                            d_other_min, d_other_max);
 }
 
@@ -1090,7 +1093,7 @@ void launch_product_sums(const double *d_stats4, const int64_t *d_prod_ofs, int 
 
 void launch_bootstrap(const double *d_stats4, const int64_t *d_prod_ofs, const int *d_order, int n_products, int64_t max_codons,
                       int64_t b_first, int64_t b_count, uint64_t seed, uint32_t stream_id, double *d_rep, double *d_vals,
-                      cudaStream_t stream)
+                      double *d_prod_sums, cudaStream_t stream)
 {
     if (n_products <= 0 || b_count <= 0) return;
     const int64_t per_block = (int64_t)kBootWarps * kBootRepsPerWarp;
@@ -1100,10 +1103,11 @@ void launch_bootstrap(const double *d_stats4, const int64_t *d_prod_ofs, const i
     if (smem <= (size_t)kBootSmemLimit) {
         cudaFuncSetAttribute(k_bootstrap<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBootSmemLimit);  // per device
         k_bootstrap<true><<<grid, kBootWarps * 32, smem, stream>>>(d_stats4, d_prod_ofs, d_order, n_products, b_first, b_count, key,
-                                                                    stream_id, d_rep, d_vals);
+                                                                    stream_id, d_rep, d_vals, d_prod_sums);
     } else {
+        if (d_prod_sums) launch_product_sums(d_stats4, d_prod_ofs, n_products, d_prod_sums, stream);
         k_bootstrap<false><<<grid, kBootWarps * 32, 0, stream>>>(d_stats4, d_prod_ofs, d_order, n_products, b_first, b_count, key,
-                                                                  stream_id, d_rep, d_vals);
+                                                                  stream_id, d_rep, d_vals, nullptr);
     }
 }
 

@@ -59,14 +59,12 @@ void launch_hist(const uint8_t *d_codes, int64_t n_pad, int64_t n_codons, uint32
 // n_spans*16 + 4 readable bytes.
 void launch_vote_refs(const uint8_t *d_aln, int64_t pitch, int n_sample, int64_t n_spans, uint8_t *d_cons, uint32_t *d_alt,
                       cudaStream_t stream);
-void launch_cons_codes(const uint8_t *d_cons, int64_t cons_shift, const CodonMap *d_map, int64_t n_codons, uint8_t *d_cons_code,
-                       uint32_t *d_cons_key, cudaStream_t stream);
 // d_alt[span][kAltWords]: the span's second reference pattern (launch_vote_refs).
 constexpr int kAltWords = 8;
 void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, const uint8_t *d_cons, const uint32_t *d_alt, int64_t n_spans,
-                       const SpanRun *d_runs, const uint8_t *d_cons_code, uint32_t *d_hist, uint32_t *d_other_min,
+                       const SpanRun *d_runs, uint32_t *d_hist, uint32_t *d_other_min,
                        uint32_t *d_other_max, cudaStream_t stream);
-void launch_fused_fixup(const uint8_t *d_cons_code, const uint32_t *d_cons_key, const uint8_t *d_regular, int64_t n_codons,
+void launch_fused_fixup(const uint8_t *d_cons, int64_t cons_shift, const CodonMap *d_map, const uint8_t *d_regular, int64_t n_codons,
                         uint32_t n_rows, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max, cudaStream_t stream);
 // TMA-tiled variant of launch_fused_hist (same contract: counts of the non-consensus codons of the regular
 // codons are added to hist).  make_tile_tensor_map fills a 128-byte CUtensorMap (64-byte aligned storage)
@@ -114,10 +112,11 @@ void launch_product_sums(const double *d_stats4, const int64_t *d_prod_ofs, int 
 // [b_first, b_first+b_count).  d_order (or null) lists products largest first.
 // max_codons = largest product (sizes the shared-memory table; larger than the
 // limit falls back to gathers from global memory).  Outputs (either may be null):
-// d_rep[p][b][4] replicate sums, d_vals[which][p][b] per-replicate dN, dS, dN-dS, JC x3.
+// d_rep[p][b][4] replicate sums, d_vals[which][p][b] per-replicate dN, dS, dN-dS, JC x3.  d_prod_sums (or null):
+// sums[p][4] as launch_product_sums writes them, bit for bit, computed on the way from the staged table.
 void launch_bootstrap(const double *d_stats4, const int64_t *d_prod_ofs, const int *d_order, int n_products, int64_t max_codons,
                       int64_t b_first, int64_t b_count, uint64_t seed, uint32_t stream_id, double *d_rep, double *d_vals,
-                      cudaStream_t stream);
+                      double *d_prod_sums, cudaStream_t stream);
 // one Philox4x32-10 block on the device (known-answer test hook)
 void launch_philox_kat(const uint32_t *ctr, const uint32_t *key, uint32_t *d_out, cudaStream_t stream);
 // K6: rep[item][B][4] -> se[item][6]: sample SD (n-1) of the per-replicate dN, dS, dN-dS and their Jukes-Cantor forms
