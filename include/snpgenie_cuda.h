@@ -251,6 +251,10 @@ int64_t snpg_launch_count(const snpg_ctx *ctx);
 /* Of those, launches of the TMA-tiled histogram kernel (0 means every fused histogram went
  * through the vector-load kernel: option, or a buffer a tensor map cannot describe). */
 int64_t snpg_tile_launch_count(const snpg_ctx *ctx);
+/* snpg_within_job on a device-resident alignment is captured into a CUDA graph on the second identical call
+ * in a row and replayed from then on (same kernels, same results, fewer launch gaps; SNPG_NO_GRAPH=1 in the
+ * environment or SNPG_OPT_PROFILE != 0 turns this off).  Number of replays so far: */
+int64_t snpg_graph_replays(const snpg_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -65,6 +65,7 @@ SIGNATURES = {
     "snpg_test_philox": (C.c_int, [_ctx, _u32p, _u32p, _u32p]),
     "snpg_launch_count": (C.c_int64, [_ctx]),
     "snpg_tile_launch_count": (C.c_int64, [_ctx]),
+    "snpg_graph_replays": (C.c_int64, [_ctx]),
     "snpg_set_stream": (C.c_int, [_ctx, C.c_void_p]),
     "snpg_get_profile": (C.c_int, [_ctx, _f64p, _i64p, C.c_int]),
 }

@@ -24,18 +24,21 @@ namespace {
 
 std::string g_create_error;
 
+uint64_t g_alloc_epoch = 0;   // bumped whenever a device buffer moves: captured CUDA graphs hold raw pointers
+
 struct DevBuf {  // grow-only device scratch
     void *p = nullptr;
     size_t cap = 0;
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
+        g_alloc_epoch++;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
         cudaError_t e = cudaMalloc(&p, bytes);
         if (e == cudaSuccess) cap = bytes;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p) { cudaFree(p); g_alloc_epoch++; } p = nullptr; cap = 0; }
     template <class T> T *as() const { return static_cast<T *>(p); }
 };
 
@@ -89,13 +92,38 @@ struct snpg_ctx {
     DevBuf s_vals, d_order_local, d_order_full;
     int64_t max_codons_local = 0, max_codons_full = 0;
     DevBuf staging[2], s_stats, s_poly, s_nda, s_ndb, s_cmp, s_cons, s_sums, s_rep, s_se, s_misc, s_in;
+    // snpg_within_job on a device-resident alignment, replayed as a CUDA graph from the third identical call on
+    struct TimedSpan { cudaEvent_t e0, e1; int kind; };
+    bool capturing = false;
+    struct JobKey {
+        uint32_t profile_mask = 0;
+        int group = -1; const uint8_t *bases = nullptr; uint64_t n = 0, len = 0, stride = 0; int64_t B = 0;
+        bool keep_codes = false, site_counts = false, want_se = false; int fused_kernel = 0;
+        bool operator==(const JobKey &o) const {
+            return profile_mask == o.profile_mask && group == o.group && bases == o.bases && n == o.n && len == o.len && stride == o.stride && B == o.B &&
+                   keep_codes == o.keep_codes && site_counts == o.site_counts && want_se == o.want_se && fused_kernel == o.fused_kernel;
+        }
+    };
+    struct JobGraph {
+        cudaGraphExec_t exec = nullptr;
+        JobKey key, candidate;
+        uint64_t epoch = 0, candidate_epoch = ~0ull;
+        int64_t n_launches = 0, n_tile_launches = 0;
+        bool disabled = false;
+        std::vector<TimedSpan> spans;   // event pairs recorded inside the graph (profiling on)
+        uint32_t *h_salt = nullptr;     // pinned
+        double *h_out = nullptr;        // pinned: sums [P][4] then se [P][6]
+        int h_out_products = 0;
+        int64_t replays = 0;
+    } job;
+    DevBuf d_salt;
     int64_t launches = 0;
     int64_t tile_launches = 0;      // launches of k_tile_hist (the rest of SNPG_K_FUSED went to k_fused_hist)
     uint32_t call_id = 0;
     // optional per-kernel timing (CUDA events on the launch stream)
     uint32_t profile_mask = 0;      // bit k set: bracket launches of kernel kind k with timing events
     bool own_stream = true;
-    struct Span { cudaEvent_t e0, e1; int kind; };
+    typedef TimedSpan Span;
     std::vector<Span> spans;        // recorded, not yet resolved
     std::vector<cudaEvent_t> free_events;
     double kernel_ms[SNPG_N_KERNEL_KINDS] = {0};
@@ -126,10 +154,19 @@ struct Launch {
     snpg_ctx *ctx; int kind; cudaEvent_t e0 = nullptr;
     Launch(snpg_ctx *c, int k) : ctx(c), kind(k) {
         ctx->launches++;
-        if ((ctx->profile_mask >> kind) & 1u) { e0 = take_event(ctx); cudaEventRecord(e0, ctx->stream); }
+        if ((ctx->profile_mask >> kind) & 1u) {
+            e0 = take_event(ctx);
+            // inside a graph capture the records become external event-record nodes: the same pair of events is
+            // re-recorded by every replay and read after it
+            if (ctx->capturing) cudaEventRecordWithFlags(e0, ctx->stream, cudaEventRecordExternal);
+            else cudaEventRecord(e0, ctx->stream);
+        }
     }
     ~Launch() {
-        if (e0) { cudaEvent_t e1 = take_event(ctx); cudaEventRecord(e1, ctx->stream); ctx->spans.push_back({e0, e1, kind}); }
+        if (!e0) return;
+        cudaEvent_t e1 = take_event(ctx);
+        if (ctx->capturing) { cudaEventRecordWithFlags(e1, ctx->stream, cudaEventRecordExternal); ctx->job.spans.push_back({e0, e1, kind}); }
+        else { cudaEventRecord(e1, ctx->stream); ctx->spans.push_back({e0, e1, kind}); }
     }
 };
 
@@ -142,6 +179,15 @@ void resolve_spans(snpg_ctx *ctx) {
         ctx->free_events.push_back(sp.e1);
     }
     ctx->spans.clear();
+}
+
+// a captured snpg_within_job graph holds pointers, options and event pairs: anything that changes them drops it
+void invalidate_job_graph(snpg_ctx *ctx) {
+    if (ctx->job.exec) cudaGraphExecDestroy(ctx->job.exec);
+    ctx->job.exec = nullptr;
+    for (auto &sp : ctx->job.spans) { ctx->free_events.push_back(sp.e0); ctx->free_events.push_back(sp.e1); }
+    ctx->job.spans.clear();
+    ctx->job.candidate_epoch = ~0ull;
 }
 
 cudaError_t sync_stream(snpg_ctx *ctx) {
@@ -342,8 +388,11 @@ void snpg_destroy(snpg_ctx *ctx) {
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     for (auto &g : ctx->groups) { g.codes.release(); g.hist.release(); g.other.release(); g.sites.release(); }
     for (auto &h : ctx->host_aln) if (h.p) cudaFreeHost(h.p);
+    invalidate_job_graph(ctx);
+    if (ctx->job.h_salt) cudaFreeHost(ctx->job.h_salt);
+    if (ctx->job.h_out) cudaFreeHost(ctx->job.h_out);
     DevBuf *bufs[] = {&ctx->d_map, &ctx->d_local_ofs, &ctx->d_full_ofs, &ctx->d_tables, &ctx->staging[0], &ctx->staging[1],
-                      &ctx->d_runs, &ctx->d_tiles, &ctx->d_sched, &ctx->d_regular, &ctx->d_irr_map, &ctx->d_irr_idx, &ctx->d_cons, &ctx->d_alt, &ctx->t_codes, &ctx->t_hist,
+                      &ctx->d_runs, &ctx->d_tiles, &ctx->d_sched, &ctx->d_salt, &ctx->d_regular, &ctx->d_irr_map, &ctx->d_irr_idx, &ctx->d_cons, &ctx->d_alt, &ctx->t_codes, &ctx->t_hist,
                       &ctx->t_other,
                       &ctx->s_stats, &ctx->s_poly, &ctx->s_nda, &ctx->s_ndb, &ctx->s_cmp, &ctx->s_cons, &ctx->s_sums,
                       &ctx->s_rep, &ctx->s_se, &ctx->s_misc, &ctx->s_in, &ctx->s_vals, &ctx->d_order_local, &ctx->d_order_full};
@@ -361,6 +410,7 @@ void snpg_destroy(snpg_ctx *ctx) {
 
 int snpg_set_option(snpg_ctx *ctx, int option, int64_t value) {
     if (!ctx) return SNPG_E_ARG;
+    invalidate_job_graph(ctx);
     if (option == SNPG_OPT_KEEP_CODES) { ctx->keep_codes = value != 0; return SNPG_OK; }
     if (option == SNPG_OPT_SITE_COUNTS) {
         NEED(ctx, ctx->n_products == 0, SNPG_E_STATE, "SNPG_OPT_SITE_COUNTS must be set before snpg_set_products");
@@ -399,6 +449,7 @@ int snpg_set_products(snpg_ctx *ctx, int n_products, const int64_t *seg_ofs, con
     NEED(ctx, aln_len > 0 && aln_len < (int64_t)1 << 31, SNPG_E_ARG, "alignment length %lld unsupported", (long long)aln_len);
     if (int rc = bind(ctx)) return rc;
     for (auto &g : ctx->groups) g.loaded = false;  // maps change: loaded groups are stale
+    invalidate_job_graph(ctx);
 
     std::vector<CodonMap> map_all;
     std::vector<int64_t> full_ofs(n_products + 1, 0);
@@ -910,7 +961,7 @@ int snpg_bootstrap_product(snpg_ctx *ctx, const double *stats4, const uint8_t *k
     CU(ctx, ctx->s_vals.ensure(sizeof(double) * 6 * (size_t)B));
     {
         Launch l(ctx, SNPG_K_BOOT);
-        launch_bootstrap(ctx->s_in.as<double>(), ctx->s_misc.as<int64_t>(), nullptr, 1, C, 0, B, ctx->seed, sid,
+        launch_bootstrap(ctx->s_in.as<double>(), ctx->s_misc.as<int64_t>(), nullptr, 1, C, 0, B, ctx->seed, sid, nullptr,
                          sums_out ? ctx->s_rep.as<double>() : nullptr, ctx->s_vals.as<double>(), nullptr, ctx->stream);
     }
     { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->s_vals.as<double>(), 1, B, ctx->s_se.as<double>(), ctx->stream); }
@@ -979,7 +1030,7 @@ int snpg_bootstrap_all_device(snpg_ctx *ctx, const double *d_stats4_full, int64_
     {
         Launch l(ctx, SNPG_K_BOOT);
         launch_bootstrap(d_stats4_full, ctx->d_full_ofs.as<int64_t>(), ctx->d_order_full.as<int>(), ctx->n_products, ctx->max_codons_full,
-                         b_first, b_count, ctx->seed, 0x30000u, d_rep_out, nullptr, nullptr, ctx->stream);
+                         b_first, b_count, ctx->seed, 0x30000u, nullptr, d_rep_out, nullptr, nullptr, ctx->stream);
     }
     CU(ctx, cudaGetLastError());
     CU(ctx, sync_stream(ctx));
@@ -1047,8 +1098,8 @@ int snpg_between_all(snpg_ctx *ctx, const int *groups, int n_groups, int64_t min
                 {
                     Launch l(ctx, SNPG_K_BOOT);      // also writes the product sums
                     launch_bootstrap(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), ctx->d_order_local.as<int>(), P,
-                                     ctx->max_codons_local, 0, B, ctx->seed, 0x50000u + ctx->call_id++, nullptr, ctx->s_vals.as<double>(),
-                                     d_pair_sums, ctx->stream);
+                                     ctx->max_codons_local, 0, B, ctx->seed, 0x50000u + ctx->call_id++, nullptr, nullptr,
+                                     ctx->s_vals.as<double>(), d_pair_sums, ctx->stream);
                 }
                 { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->s_vals.as<double>(), P, B, ctx->s_se.as<double>() + 6 * (size_t)P * pair, ctx->stream); }
             }
@@ -1061,10 +1112,11 @@ int snpg_between_all(snpg_ctx *ctx, const int *groups, int n_groups, int64_t min
     return SNPG_OK;
 }
 
-int snpg_within_all(snpg_ctx *ctx, int group, int64_t B, double *prod_sums, double *prod_se) {
-    if (!ctx) return SNPG_E_ARG;
-    if (int rc = check_group(ctx, group)) return rc;
-    if (int rc = bind(ctx)) return rc;
+// The whole within-group analysis of a loaded group, enqueued on ctx->stream.  final_sync = false and
+// d_salt != null is the form a CUDA graph captures: no host synchronisation, outputs into pinned memory, the
+// bootstrap's per-call stream number read from device memory when the graph runs.
+static int within_all_impl(snpg_ctx *ctx, int group, int64_t B, double *prod_sums, double *prod_se, bool final_sync,
+                           const uint32_t *d_salt) {
     const Group &g = ctx->groups[group];
     const int P = ctx->n_products;
     const int64_t cnt = ctx->shard_count;
@@ -1079,8 +1131,9 @@ int snpg_within_all(snpg_ctx *ctx, int group, int64_t B, double *prod_sums, doub
         CU(ctx, ctx->s_se.ensure(sizeof(double) * 6 * (size_t)P));
         {
             Launch l(ctx, SNPG_K_BOOT);
+            const uint32_t sid = d_salt ? 0x40000u : 0x40000u + ctx->call_id++;
             launch_bootstrap(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), ctx->d_order_local.as<int>(), P,
-                             ctx->max_codons_local, 0, B, ctx->seed, 0x40000u + ctx->call_id++, nullptr, ctx->s_vals.as<double>(),
+                             ctx->max_codons_local, 0, B, ctx->seed, sid, d_salt, nullptr, ctx->s_vals.as<double>(),
                              ctx->s_sums.as<double>(), ctx->stream);      // also writes the product sums
         }
         { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->s_vals.as<double>(), P, B, ctx->s_se.as<double>(), ctx->stream); }
@@ -1088,20 +1141,110 @@ int snpg_within_all(snpg_ctx *ctx, int group, int64_t B, double *prod_sums, doub
     CU(ctx, cudaGetLastError());
     if (prod_sums) CU(ctx, cudaMemcpyAsync(prod_sums, ctx->s_sums.p, sizeof(double) * 4 * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
     if (boot) CU(ctx, cudaMemcpyAsync(prod_se, ctx->s_se.p, sizeof(double) * 6 * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, sync_stream(ctx));
+    if (final_sync) CU(ctx, sync_stream(ctx));
     return SNPG_OK;
+}
+
+int snpg_within_all(snpg_ctx *ctx, int group, int64_t B, double *prod_sums, double *prod_se) {
+    if (!ctx) return SNPG_E_ARG;
+    if (int rc = check_group(ctx, group)) return rc;
+    if (int rc = bind(ctx)) return rc;
+    return within_all_impl(ctx, group, B, prod_sums, prod_se, true, nullptr);
+}
+
+static void drop_job_graph(snpg_ctx *ctx) { invalidate_job_graph(ctx); }
+
+// Captures the job (load + analysis) into a CUDA graph and runs it once.  Any failure leaves no graph behind
+// and reports SNPG_E_STATE so that the caller runs the job the ordinary way.
+static int capture_job_graph(snpg_ctx *ctx, const snpg_ctx::JobKey &key, int64_t B) {
+    auto &J = ctx->job;
+    const int P = ctx->n_products;
+    if (!J.h_salt && cudaMallocHost(reinterpret_cast<void **>(&J.h_salt), sizeof(uint32_t)) != cudaSuccess) return SNPG_E_STATE;
+    if (J.h_out_products < P) {
+        if (J.h_out) cudaFreeHost(J.h_out);
+        J.h_out = nullptr;
+        if (cudaMallocHost(reinterpret_cast<void **>(&J.h_out), sizeof(double) * 10 * (size_t)P) != cudaSuccess) return SNPG_E_STATE;
+        J.h_out_products = P;
+    }
+    if (ctx->d_salt.ensure(sizeof(uint32_t)) != cudaSuccess) return SNPG_E_STATE;
+    const uint64_t epoch0 = g_alloc_epoch;
+    const int64_t l0 = ctx->launches, t0 = ctx->tile_launches;
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return SNPG_E_STATE; }
+    ctx->capturing = true;
+    int rc = SNPG_OK;
+    if (cudaMemcpyAsync(ctx->d_salt.p, J.h_salt, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = SNPG_E_CUDA;
+    if (rc == SNPG_OK) {
+        ctx->defer_load_sync = true;
+        rc = snpg_load_group_device(ctx, key.group, key.bases, key.n, key.len, key.stride);
+        ctx->defer_load_sync = false;
+    }
+    if (rc == SNPG_OK) rc = within_all_impl(ctx, key.group, B, J.h_out, key.want_se ? J.h_out + 4 * P : nullptr, false, ctx->d_salt.as<uint32_t>());
+    ctx->capturing = false;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    cudaGraphExec_t exec = nullptr;
+    if (rc == SNPG_OK && e == cudaSuccess && graph && epoch0 == g_alloc_epoch && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+        J.exec = exec;
+        J.key = key;
+        J.epoch = g_alloc_epoch;
+        J.n_launches = ctx->launches - l0;
+        J.n_tile_launches = ctx->tile_launches - t0;
+    } else {
+        rc = SNPG_E_STATE;
+        cudaGetLastError();
+    }
+    if (graph) cudaGraphDestroy(graph);
+    ctx->launches = l0;                 // nothing ran yet: the replay below counts them
+    ctx->tile_launches = t0;
+    return rc;
 }
 
 int snpg_within_job(snpg_ctx *ctx, int group, const uint8_t *bases, int bases_on_device, uint64_t n_seqs, uint64_t aln_len,
                     uint64_t row_stride, int64_t B, double *prod_sums, double *prod_se) {
     if (!ctx) return SNPG_E_ARG;
-    ctx->defer_load_sync = true;     // one synchronisation for the whole job, at the end of snpg_within_all
+    auto &J = ctx->job;
+    snpg_ctx::JobKey key;
+    key.group = group; key.bases = bases; key.n = n_seqs; key.len = aln_len; key.stride = row_stride; key.B = B;
+    key.keep_codes = ctx->keep_codes; key.site_counts = ctx->site_counts; key.want_se = prod_se != nullptr; key.fused_kernel = ctx->fused_kernel;
+    static const bool graphs_on = getenv("SNPG_NO_GRAPH") == nullptr;
+    key.profile_mask = ctx->profile_mask;
+    const bool eligible = graphs_on && bases_on_device && bases && prod_sums && !J.disabled &&
+                          group >= 0 && group < SNPG_MAX_GROUPS && ctx->n_products > 0;
+    if (eligible) {
+        if (int rc = bind(ctx)) return rc;
+        if (J.exec && (!(J.key == key) || J.epoch != g_alloc_epoch)) drop_job_graph(ctx);
+        if (!J.exec && J.candidate == key && J.candidate_epoch == g_alloc_epoch) {
+            // the same job for the second time in a row with every buffer already in place: capture it
+            if (capture_job_graph(ctx, key, B) != SNPG_OK) { drop_job_graph(ctx); J.disabled = true; }
+        }
+        if (J.exec) {
+            const int P = ctx->n_products;
+            *J.h_salt = ctx->call_id++;
+            CU(ctx, cudaGraphLaunch(J.exec, ctx->stream));
+            CU(ctx, sync_stream(ctx));
+            ctx->launches += J.n_launches;
+            ctx->tile_launches += J.n_tile_launches;
+            J.replays++;
+            for (auto &sp : J.spans) {
+                float ms = 0;
+                if (cudaEventElapsedTime(&ms, sp.e0, sp.e1) == cudaSuccess) { ctx->kernel_ms[sp.kind] += ms; ctx->kernel_calls[sp.kind]++; }
+            }
+            memcpy(prod_sums, J.h_out, sizeof(double) * 4 * (size_t)P);
+            if (prod_se) memcpy(prod_se, J.h_out + 4 * P, sizeof(double) * 6 * (size_t)P);
+            return SNPG_OK;
+        }
+    }
+    ctx->defer_load_sync = true;     // one synchronisation for the whole job, at the end of the analysis
     int rc = bases_on_device ? snpg_load_group_device(ctx, group, bases, n_seqs, aln_len, row_stride)
                              : snpg_load_group(ctx, group, bases, n_seqs, aln_len, row_stride);
     ctx->defer_load_sync = false;
     if (rc != SNPG_OK) { sync_stream(ctx); return rc; }
-    return snpg_within_all(ctx, group, B, prod_sums, prod_se);
+    rc = snpg_within_all(ctx, group, B, prod_sums, prod_se);
+    if (eligible && rc == SNPG_OK) { J.candidate = key; J.candidate_epoch = g_alloc_epoch; }
+    return rc;
 }
+
+int64_t snpg_graph_replays(const snpg_ctx *ctx) { return ctx ? ctx->job.replays : 0; }
 
 int snpg_test_philox(snpg_ctx *ctx, const uint32_t *ctr4, const uint32_t *key2, uint32_t *out4) {
     if (!ctx || !ctr4 || !key2 || !out4) return SNPG_E_ARG;
@@ -1121,6 +1264,7 @@ int snpg_set_stream(snpg_ctx *ctx, void *cuda_stream) {
     if (!ctx) return SNPG_E_ARG;
     if (int rc = bind(ctx)) return rc;
     CU(ctx, sync_stream(ctx));
+    invalidate_job_graph(ctx);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     if (cuda_stream) { ctx->stream = static_cast<cudaStream_t>(cuda_stream); ctx->own_stream = false; }
     else { CU(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }

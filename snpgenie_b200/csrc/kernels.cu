@@ -780,10 +780,11 @@ constexpr int kBootSmemLimit = 200 * 1024;
 template <bool SMEM>
 __global__ void __launch_bounds__(kBootWarps * 32)
 k_bootstrap(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, const int *__restrict__ order, int n_products,
-            int64_t b_first, int64_t b_count, uint2 key, uint32_t stream_id, double *__restrict__ rep, double *__restrict__ vals,
-            double *__restrict__ prod_sums)
+            int64_t b_first, int64_t b_count, uint2 key, uint32_t stream_id, const uint32_t *__restrict__ salt,
+            double *__restrict__ rep, double *__restrict__ vals, double *__restrict__ prod_sums)
 {
     extern __shared__ double2 s_tab[];
+    if (salt) stream_id += *salt;      // a replayed CUDA graph gets its per-call stream number from memory
     __shared__ double2 s_sums[kBootWarps * kBootRepsPerWarp][2];     // the block's replicate sums, for the dense epilogue
     __shared__ double s_red[SMEM ? kBootWarps * 32 : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1092,8 +1093,8 @@ void launch_product_sums(const double *d_stats4, const int64_t *d_prod_ofs, int 
 }
 
 void launch_bootstrap(const double *d_stats4, const int64_t *d_prod_ofs, const int *d_order, int n_products, int64_t max_codons,
-                      int64_t b_first, int64_t b_count, uint64_t seed, uint32_t stream_id, double *d_rep, double *d_vals,
-                      double *d_prod_sums, cudaStream_t stream)
+                      int64_t b_first, int64_t b_count, uint64_t seed, uint32_t stream_id, const uint32_t *d_salt, double *d_rep,
+                      double *d_vals, double *d_prod_sums, cudaStream_t stream)
 {
     if (n_products <= 0 || b_count <= 0) return;
     const int64_t per_block = (int64_t)kBootWarps * kBootRepsPerWarp;
@@ -1103,11 +1104,11 @@ void launch_bootstrap(const double *d_stats4, const int64_t *d_prod_ofs, const i
     if (smem <= (size_t)kBootSmemLimit) {
         cudaFuncSetAttribute(k_bootstrap<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBootSmemLimit);  // per device
         k_bootstrap<true><<<grid, kBootWarps * 32, smem, stream>>>(d_stats4, d_prod_ofs, d_order, n_products, b_first, b_count, key,
-                                                                    stream_id, d_rep, d_vals, d_prod_sums);
+                                                                    stream_id, d_salt, d_rep, d_vals, d_prod_sums);
     } else {
         if (d_prod_sums) launch_product_sums(d_stats4, d_prod_ofs, n_products, d_prod_sums, stream);
         k_bootstrap<false><<<grid, kBootWarps * 32, 0, stream>>>(d_stats4, d_prod_ofs, d_order, n_products, b_first, b_count, key,
-                                                                  stream_id, d_rep, d_vals, nullptr);
+                                                                  stream_id, d_salt, d_rep, d_vals, nullptr);
     }
 }
 

@@ -78,6 +78,11 @@ class Engine:
         """Launches of the TMA-tiled histogram kernel (the default fused route)."""
         return int(_abi.lib.snpg_tile_launch_count(self._ctx))
 
+    @property
+    def graph_replays(self) -> int:
+        """How often within_job ran as a replayed CUDA graph."""
+        return int(_abi.lib.snpg_graph_replays(self._ctx))
+
     def set_option(self, option: int, value: int):
         self._ck(_abi.lib.snpg_set_option(self._ctx, option, value))
 

@@ -751,6 +751,57 @@ def test_more_than_2_20_rows(route):
         assert e.group_size(1) == n
 
 
+def test_within_job_graph_replay_matches_plain_calls():
+    """snpg_within_job on a device-resident alignment is replayed as a CUDA graph from the second identical call:
+    same kernels, so the product sums are bit-identical and the SEs (a fresh Philox stream per call) agree
+    statistically; options, sizes and profiling changes re-capture."""
+    import torch
+    from snpgenie_b200 import _abi
+    from snpgenie_b200.engine import Engine
+    products = synth.sars2_products()
+    L, n = 29903, 700
+    pitch = (L + 127) // 128 * 128
+    aln = synth.make_alignment(n, L, products, 99)
+    d = torch.zeros((n, pitch), dtype=torch.uint8, device="cuda:0")
+    d[:, :L] = torch.from_numpy(aln).cuda()
+    with Engine(device=0) as e:
+        e.set_products(products, L)
+        outs = [e.within_job(0, d.data_ptr(), n, L, pitch, True, B=600) for _ in range(5)]
+        assert e.graph_replays == 4
+        e.load_group_ptr(1, d.data_ptr(), n, L, pitch, device=True)
+        plain, _ = e.within_all(1, B=0)
+        for sums, se in outs:
+            assert np.array_equal(sums, plain)
+            assert np.all(np.isfinite(se)) and np.all(np.abs(se[:, :3] / outs[0][1][:, :3] - 1) < 0.25)
+        assert not np.array_equal(outs[3][1], outs[4][1])          # every call draws afresh
+        for i in range(len(products)):                              # the graph really loaded the group
+            raw, codes = _oracle_product(aln, products[i])
+            assert (e.hist(0, i)[0] == orc.hist(codes)).all()
+        # profiling on: still a graph, and the kernel clock keeps counting
+        e.set_option(_abi.OPT_PROFILE, -1)
+        r0 = e.graph_replays
+        e.profile(reset=True)
+        for _ in range(4):
+            sums, _ = e.within_job(0, d.data_ptr(), n, L, pitch, True, B=600)
+            assert np.array_equal(sums, plain)
+        prof = e.profile()
+        assert e.graph_replays == r0 + 3 and prof["fused"][1] == 4 and prof["fused"][0] > 0 and prof["bootstrap"][1] == 4
+        # another replicate count, another histogram kernel, a host buffer: each a different job
+        e.set_option(_abi.OPT_PROFILE, 0)
+        for B in (50, 50, 50):
+            sums, se = e.within_job(0, d.data_ptr(), n, L, pitch, True, B=B)
+            assert np.array_equal(sums, plain)
+        e.set_option(_abi.OPT_FUSED_KERNEL, _abi.FUSED_TMA_TILES)
+        t0 = e.tile_launches
+        for _ in range(3):
+            sums, _ = e.within_job(0, d.data_ptr(), n, L, pitch, True, B=50)
+            assert np.array_equal(sums, plain)
+        assert e.tile_launches == t0 + 3
+        host = np.ascontiguousarray(aln)
+        sums, _ = e.within_job(0, host.ctypes.data, n, L, L, False, B=50)
+        assert np.array_equal(sums, plain)
+
+
 # ----------------------------------------------------------------- edge cases
 
 @pytest.mark.parametrize("keep", [True, False])
