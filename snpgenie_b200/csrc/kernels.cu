@@ -254,7 +254,7 @@ __device__ __forceinline__ void fused_decode(const uint32_t *e, const uint8_t *_
 }
 
 constexpr int kFusedQueue = 128;     // entries per warp (ring, power of two)
-constexpr int kFusedEntryWords = 7;  // 5 raw + span + pad: odd stride, conflict-free across lanes
+constexpr int kFusedEntryWords = 8;  // 5 raw + span + pad: 32 bytes, written as one 16-byte and one 8-byte store
 
 __global__ void __launch_bounds__(kFusedWarps * 32)
 k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, int64_t n_rows, const uint8_t *__restrict__ cons,
@@ -263,7 +263,7 @@ k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, int64_t n_rows, con
 {
     __shared__ uint8_t lut_chr[2][256];
     __shared__ uint8_t lut_cls[2][256];
-    __shared__ uint32_t queue_all[kFusedWarps][kFusedQueue * kFusedEntryWords];
+    __shared__ __align__(16) uint32_t queue_all[kFusedWarps][kFusedQueue * kFusedEntryWords];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     for (int s = 0; s < 2; s++) {
         const uint8_t n = norm_char((uint8_t)t, s);
@@ -273,14 +273,16 @@ k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, int64_t n_rows, con
     __syncthreads();
 
     uint32_t *queue = queue_all[warp];
+    uint32_t q_base = (uint32_t)__cvta_generic_to_shared(queue);
     uint32_t q_head = 0, q_count = 0;    // warp-uniform
-    const unsigned lt = (1u << lane) - 1;
+    unsigned lt = (1u << lane) - 1;
+    asm volatile("" : "+r"(lt), "+r"(q_base));      // pinned in registers: ptxas otherwise re-derives both in the loop (S2R, MOV, LEA)
 
     const int64_t span = (int64_t)blockIdx.x * 32 + lane;
     const bool live = span < n_spans;
     const uint32_t sp = (uint32_t)(live ? span : n_spans - 1);
     const int64_t row_begin = ((int64_t)blockIdx.y * kFusedWarps + warp) * rows_per_warp;
-    const int64_t row_end = min(n_rows, row_begin + rows_per_warp);
+    const int n_my = (int)max((int64_t)0, min((int64_t)rows_per_warp, n_rows - row_begin));
     const uint4 c = *reinterpret_cast<const uint4 *>(cons + (int64_t)sp * 16);
     const uint32_t c4 = *reinterpret_cast<const uint32_t *>(cons + (int64_t)sp * 16 + 16);
     // the span's second reference: its most common non-consensus bytes among the sampled rows (the consensus
@@ -290,44 +292,59 @@ k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, int64_t n_rows, con
     uint32_t n_alt = 0;
     const uint8_t *p = aln + (int64_t)sp * 16 + row_begin * pitch;
 
-    for (int64_t r = row_begin; r < row_end; r += kFusedUnroll, p += kFusedUnroll * pitch) {
+    // one row of the warp: compare with both references, count or park
+    auto row = [&](const uint4 &v, uint32_t tail) {
+        const uint32_t nxt = __shfl_down_sync(kFull, v.x, 1);
+        const uint32_t v4 = lane == 31 ? tail : nxt;
+        const uint32_t d = (v.x ^ c.x) | (v.y ^ c.y) | (v.z ^ c.z) | (v.w ^ c.w) | ((v4 ^ c4) & 0xFFFFu);
+        const uint32_t da = (v.x ^ a.x) | (v.y ^ a.y) | (v.z ^ a.z) | (v.w ^ a.w) | ((v4 ^ a4) & 0xFFFFu);
+        n_alt += (da == 0 && d != 0 && live) ? 1u : 0u;
+        const bool differs = d != 0 && da != 0 && live;
+        const unsigned bal = __ballot_sync(kFull, differs);
+        if (bal) {           // nothing to park on most rows of a realistic alignment
+            if (differs) {   // park the bytes; a full warp decodes 32 parked spans at a time
+                const uint32_t at = q_base + ((q_head + q_count + __popc(bal & lt)) & (kFusedQueue - 1)) * (kFusedEntryWords * 4);
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(at), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(at + 16), "r"(v4), "r"(sp) : "memory");
+            }
+            q_count += __popc(bal);
+        }
+    };
+    auto drain = [&]() {     // at most 31 + 64 parked entries between drains
+        while (q_count >= 32) {
+            __syncwarp();
+            fused_decode(queue + ((q_head + lane) & (kFusedQueue - 1)) * kFusedEntryWords, cons, runs, hist, other_min, other_max,
+                         lut_cls, lut_chr);
+            __syncwarp();
+            q_head += 32;
+            q_count -= 32;
+        }
+    };
+
+    int i = 0;
+    for (; i + kFusedUnroll <= n_my; i += kFusedUnroll, p += kFusedUnroll * pitch) {
         uint4 v[kFusedUnroll];
         uint32_t tail[kFusedUnroll];
 #pragma unroll
         for (int u = 0; u < kFusedUnroll; u++) {
-            const uint8_t *q = p + (r + u < row_end ? u : 0) * pitch;
+            const uint8_t *q = p + u * pitch;
             v[u] = ld_stream_v4(reinterpret_cast<const uint4 *>(q));
-            tail[u] = c4;
+            tail[u] = 0;
             // lane 31 has no right-hand neighbour in the warp: it fetches its own look-ahead word
             if (lane == 31) tail[u] = *reinterpret_cast<const uint32_t *>(q + 16);
         }
 #pragma unroll
         for (int u = 0; u < kFusedUnroll; u++) {
-            const uint32_t nxt = __shfl_down_sync(kFull, v[u].x, 1);
-            const uint32_t v4 = lane == 31 ? tail[u] : nxt;
-            const uint32_t d = (v[u].x ^ c.x) | (v[u].y ^ c.y) | (v[u].z ^ c.z) | (v[u].w ^ c.w) | ((v4 ^ c4) & 0xFFFFu);
-            const uint32_t da = (v[u].x ^ a.x) | (v[u].y ^ a.y) | (v[u].z ^ a.z) | (v[u].w ^ a.w) | ((v4 ^ a4) & 0xFFFFu);
-            const bool real = live && r + u < row_end;
-            const bool is_alt = da == 0 && d != 0 && real;
-            n_alt += is_alt ? 1u : 0u;
-            const bool differs = d != 0 && da != 0 && real;
-            const unsigned bal = __ballot_sync(kFull, differs);
-            if (differs) {   // park the bytes; a full warp decodes 32 parked spans at a time
-                uint32_t *e = queue + ((q_head + q_count + __popc(bal & lt)) & (kFusedQueue - 1)) * kFusedEntryWords;
-                e[0] = v[u].x; e[1] = v[u].y; e[2] = v[u].z; e[3] = v[u].w; e[4] = v4; e[5] = sp;
-            }
-            q_count += __popc(bal);
-            if (u & 1) {     // at most 31 + 64 parked entries between drains
-                while (q_count >= 32) {
-                    __syncwarp();
-                    fused_decode(queue + ((q_head + lane) & (kFusedQueue - 1)) * kFusedEntryWords, cons, runs, hist, other_min,
-                                 other_max, lut_cls, lut_chr);
-                    __syncwarp();
-                    q_head += 32;
-                    q_count -= 32;
-                }
-            }
+            row(v[u], tail[u]);
+            if (u & 1) drain();
         }
+    }
+    for (; i < n_my; i++, p += pitch) {          // the last rows of the group
+        const uint4 v = ld_stream_v4(reinterpret_cast<const uint4 *>(p));
+        uint32_t tail = 0;
+        if (lane == 31) tail = *reinterpret_cast<const uint32_t *>(p + 16);
+        row(v, tail);
+        drain();
     }
     __syncwarp();
     if ((uint32_t)lane < q_count)
