@@ -422,17 +422,19 @@ k_vote_refs(const uint8_t *__restrict__ aln, int64_t pitch, int n_sample, int64_
 // After all row blocks: credit the consensus codon of every regular codon with the rows that never reached
 // the decode path.  The consensus codon's code (and, for an 'other' codon, its character key) comes straight
 // from the consensus row and the codon index map.
-__global__ void k_fused_fixup(const uint8_t *__restrict__ cons, int64_t cons_shift, const CodonMap *__restrict__ map,
-                              const uint8_t *__restrict__ regular, int64_t n_codons, uint32_t n_rows,
-                              uint32_t *__restrict__ hist, uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max)
+__global__ void __launch_bounds__(256)
+k_fused_fixup(const uint8_t *__restrict__ cons, int64_t cons_shift, const CodonMap *__restrict__ map,
+              const uint8_t *__restrict__ regular, int64_t n_codons, uint32_t n_rows,
+              uint32_t *__restrict__ hist, uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max)
 {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per codon: the 66 bins are summed across lanes
+    const int lane = threadIdx.x & 31;
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (c >= n_codons || !regular[c]) return;
     uint32_t *h = hist + c * kHistBins;
-    uint32_t seen = 0;
-    for (int b = 0; b < kHistBins; b++) seen += h[b];
+    const uint32_t seen = warp_sum_u32(h[lane] + h[lane + 32] + (lane < kHistBins - 64 ? h[lane + 64] : 0u));
     const uint32_t rest = n_rows - seen;       // rows that were never parked, or decoded to the consensus code
-    if (rest) {
+    if (rest && lane == 0) {
         const CodonMap m = map[c];
         const uint8_t n0 = norm_char(cons[m.p0 + cons_shift], m.minus), n1 = norm_char(cons[m.p1 + cons_shift], m.minus),
                       n2 = norm_char(cons[m.p2 + cons_shift], m.minus);
@@ -1043,8 +1045,8 @@ void launch_fused_fixup(const uint8_t *d_cons, int64_t cons_shift, const CodonMa
                         uint32_t n_rows, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max, cudaStream_t stream)
 {
     if (n_codons <= 0) return;
-    k_fused_fixup<<<(unsigned)((n_codons + 127) / 128), 128, 0, stream>>>(d_cons, cons_shift, d_map, d_regular, n_codons, n_rows, d_hist,
-                                                                           d_other_min, d_other_max);
+    k_fused_fixup<<<(unsigned)((n_codons + 7) / 8), 256, 0, stream>>>(d_cons, cons_shift, d_map, d_regular, n_codons, n_rows, d_hist,
+                                                                       d_other_min, d_other_max);
 }
 
 void launch_scatter_irregular(const uint32_t *d_tmp_hist, const uint32_t *d_tmp_min, const uint32_t *d_tmp_max,
