@@ -159,6 +159,32 @@ def workload_config(n_gpus):
             "l2": "inputs larger than L2 (299 MB alignment per step, re-read every step)"}
 
 
+def bind_near_gpu(local):
+    """Pin this rank to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host memory is allocated
+    (first touch then places the e2e input next to the GPU's PCIe root).  With 8 ranks on one box and no binding
+    half of them copy across the socket interconnect.  Returns (node, n_cpus) or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()[-12:]                      # 00000000:19:00.0 -> 0000:19:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node, len(cpus)
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------ GPU arm
 
 def run_ours(args):
@@ -176,6 +202,7 @@ def run_ours(args):
     sys.stdout.flush()
     real_stdout = os.dup(1)
     os.dup2(2, 1)
+    numa = bind_near_gpu(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
@@ -300,6 +327,7 @@ def run_ours(args):
                           "note": "B x products per step / (bootstrap + moments kernel time)"},
             "clocks": clocks.summary(),
             "products_gathered": n_products_total,
+            "host_binding": {"numa_node": numa[0], "cpus": numa[1]} if numa else None,
         }
         if world == 1 and not args.no_cpu:
             v, threads, sample = cpu_pair_rate(12.0)
