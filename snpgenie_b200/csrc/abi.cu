@@ -289,7 +289,7 @@ int pack_block(snpg_ctx *ctx, Group &g, const uint8_t *d_block, int64_t pitch, i
                 ctx->tile_launches++;
             } else {
                 launch_fused_hist(d_block, pitch, rows, ctx->d_cons.as<uint8_t>(), ctx->d_alt.as<uint32_t>(), ctx->n_spans, ctx->d_runs.as<SpanRun>(),
-                                  g.hist.as<uint32_t>(), omin, omax, ctx->stream);
+                                  g.hist.as<uint32_t>(), omin, omax, ctx->d_sched.as<uint32_t>(), ctx->n_sms, ctx->stream);
             }
         }
         if (ctx->n_irr) {
@@ -314,7 +314,7 @@ int finish_group(snpg_ctx *ctx, Group &g) {
     } else {
         {
             Launch l(ctx, SNPG_K_OTHER);
-            launch_fused_fixup(ctx->d_cons.as<uint8_t>(), ctx->col_lo - ctx->base_al, ctx->d_map.as<CodonMap>(), ctx->d_regular.as<uint8_t>(),
+            launch_fused_fixup(ctx->d_cons.as<uint8_t>(), ctx->col_lo - ctx->base_al, ctx->d_alt.as<uint32_t>(), ctx->d_map.as<CodonMap>(), ctx->d_regular.as<uint8_t>(),
                                ctx->shard_count, (uint32_t)g.n, g.hist.as<uint32_t>(), omin, omax, ctx->stream);
         }
         if (ctx->n_irr) {
@@ -699,7 +699,7 @@ int snpg_load_group_device(snpg_ctx *ctx, int group, const uint8_t *d_bases, uin
     // The fused path reads whole 16-byte vectors: it needs an aligned base and a row
     // pitch that covers the last span; anything else keeps the code matrix path.
     const bool fused_ok = ((uintptr_t)d_bases % 16 == 0) && (row_stride % 16 == 0) &&
-                          ((int64_t)row_stride >= ctx->base_al + ctx->n_spans * 16 + 4);
+                          ((int64_t)row_stride >= ctx->base_al + ctx->n_spans * 16 + 16);
     NEED(ctx, !ctx->site_counts || fused_ok, SNPG_E_ARG,
          "site counts from a device buffer need a 16-byte aligned base and a row pitch that is a multiple of 16 and covers the last 16-byte span");
     const bool saved_keep = ctx->keep_codes;

@@ -200,162 +200,223 @@ k_hist(const uint8_t *__restrict__ codes, int64_t n_pad, int64_t n_codons, int c
 // Algorithmic traffic: every alignment byte of the CDS span read once.
 // ---------------------------------------------------------------------------
 constexpr int kFusedWarps = 8;
-constexpr int kFusedRowsPerWarp = 32;
-constexpr int kFusedUnroll = 4;
+constexpr int kFusedEntryBytes = 32;                                  // 5 raw words + span index + pad
+constexpr int kFusedSpans = 31;                                       // spans per warp (lane 31 fetches the look-ahead)
+constexpr int kFusedTailRows = 4;                                     // rows per chunk in the fine-grained tail region
+static_assert(kHistBins % 3 == 0, "the decode steps through hist[] by kHistBins / 3 per byte of codon offset");
 
-__device__ __forceinline__ uint32_t differing_bytes(uint32_t d) {     // 4-bit mask of the nonzero bytes of d
-    const uint32_t m = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
-    return ((m >> 7) * 0x00204081u) >> 21 & 0xFu;                        // bits 0,8,16,24 -> 0..3
+// Flags of the nonzero bytes of d, gathered into bits 28..31 (byte 0 -> bit 28).
+__device__ __forceinline__ uint32_t nonzero_bytes_hi(uint32_t d) {
+    const uint32_t t = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
+    return t * 0x00204081u;                                           // bits 7,15,23,31 -> 28..31, no carries
+}
+
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t r; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(a) : "memory"); return r; }
+// The chunk counter is bumped by one lane.  one = 1 comes in a register ptxas cannot prove warp-uniform:
+// with a constant it turns the add into a warp-aggregated atomic whose result is shuffled at once, which
+// makes the warp wait for the claim it meant to hide behind the current chunk.
+__device__ __forceinline__ uint32_t claim_async(uint32_t *ctr, uint32_t one) {
+    uint32_t r;
+    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(r) : "l"(ctr), "r"(one) : "memory");
+    return r;
+}
+// k / d and k % d from m = floor(2^32 / d) (0xFFFFFFFF for d = 1): the estimate is at most one short.
+__device__ __forceinline__ void div_mod(uint32_t k, uint32_t d, uint32_t m, uint32_t &q, uint32_t &r) {
+    q = __umulhi(k, m);
+    r = k - q * d;
+    if (r >= d) { q++; r -= d; }
+    if (r >= d) { q++; r -= d; }
 }
 
 // One parked (span, row): decode and count exactly the codons that contain a byte
-// differing from the consensus.  e = 5 raw words + span index.
-__device__ __forceinline__ void fused_decode(const uint32_t *e, const uint8_t *__restrict__ cons,
+// differing from the consensus.  e = shared-memory address of 5 raw words + span index.
+__device__ __forceinline__ void fused_decode(uint32_t e, const uint8_t *__restrict__ cons,
                                              const SpanRun *__restrict__ runs, uint32_t *__restrict__ hist,
                                              uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max,
-                                             const uint8_t (*lut_cls)[256], const uint8_t (*lut_chr)[256], uint32_t weight = 1u)
+                                             uint32_t lut_cls, uint32_t lut_chr)
 {
-    const uint32_t sp = e[5];
+    uint4 v;
+    uint2 t;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(e) : "memory");
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(t.x), "=r"(t.y) : "r"(e + 16) : "memory");
+    const uint32_t sp = t.y;
+    const uint2 *rp = reinterpret_cast<const uint2 *>(runs + (size_t)sp * kSpanRuns);
     const uint4 c = __ldg(reinterpret_cast<const uint4 *>(cons + (size_t)sp * 16));
     const uint32_t c4 = __ldg(reinterpret_cast<const uint32_t *>(cons + (size_t)sp * 16 + 16));
-    const uint32_t m20 = differing_bytes(e[0] ^ c.x) | (differing_bytes(e[1] ^ c.y) << 4) | (differing_bytes(e[2] ^ c.z) << 8) |
-                         (differing_bytes(e[3] ^ c.w) << 12) | (differing_bytes(e[4] ^ c4) << 16);
-    const uint8_t *raw = reinterpret_cast<const uint8_t *>(e);
-    const uint2 *rp = reinterpret_cast<const uint2 *>(runs + (size_t)sp * kSpanRuns);
+    uint2 rw = __ldg(rp);                                             // the first run, asked for with the consensus
+    // m20: bit b set when byte b of the 20-byte window differs from the consensus
+    uint32_t m20 = nonzero_bytes_hi(t.x ^ c4) >> 28;
+    m20 = __funnelshift_l(nonzero_bytes_hi(v.w ^ c.w), m20, 4);
+    m20 = __funnelshift_l(nonzero_bytes_hi(v.z ^ c.z), m20, 4);
+    m20 = __funnelshift_l(nonzero_bytes_hi(v.y ^ c.y), m20, 4);
+    m20 = __funnelshift_l(nonzero_bytes_hi(v.x ^ c.x), m20, 4);
 #pragma unroll 1
-    for (int l = 0; l < kSpanRuns; l++) {
-        const uint2 rw = __ldg(rp + l);
-        const int cnt = (int)((rw.y >> 8) & 0xFF);
+    for (int l = 0;;) {
+        const uint32_t cnt = (rw.y >> 8) & 0xFFu;
         if (cnt == 0) break;
-        const int off = (int)(rw.y & 0xFF), dir = (int)(int8_t)((rw.y >> 16) & 0xFF), mi = (int)((rw.y >> 24) & 1);
+        const uint32_t off = rw.y & 0xFFu, mi = (rw.y >> 24) & 1u;
+        const int dir = (int)(int8_t)((rw.y >> 16) & 0xFF);
         const uint32_t w = m20 >> off;
         uint32_t cm = (w | (w >> 1) | (w >> 2)) & 0x9249u & ((1u << (3 * cnt)) - 1u);
-        const uint8_t *cls = lut_cls[mi];
-        while (cm) {
-            const int j = __ffs(cm) - 1;                                  // 3 * codon ordinal
-            cm &= cm - 1;
-            const uint8_t *rb = raw + off + j;
-            const uint8_t r0 = rb[0], r1 = rb[1], r2 = rb[2];
-            const uint8_t b0 = mi ? r2 : r0, b2 = mi ? r0 : r2;          // '-' strand reads the codon right to left
-            const uint32_t k0 = cls[b0], k1 = cls[r1], k2 = cls[b2];
-            const int cidx = (int)rw.x + dir * (int)((uint32_t)j * 0xABu >> 9);   // j / 3 for j < 48
-            uint32_t code = k0 * 16 + k1 * 4 + k2;
-            if (max(k0, max(k1, k2)) >= 4) {
-                code = (k0 == 4 || k1 == 4 || k2 == 4) ? kCodeUndef : kCodeOther;
-                if (code == kCodeOther) {
-                    const uint32_t key = ((uint32_t)lut_chr[mi][b0] << 16) | ((uint32_t)lut_chr[mi][r1] << 8) | lut_chr[mi][b2];
-                    atomicMin(&other_min[cidx], key);
-                    atomicMax(&other_max[cidx], key);
+        if (cm) {
+            const uint32_t cls = lut_cls + (mi << 8);
+            const uint32_t rb = e + off;
+            const uint32_t s_lo = mi ? 0u : 4u, s_hi = mi ? 4u : 0u;     // '-' strand reads the codon right to left
+            const uint32_t base = rw.x * (uint32_t)kHistBins;
+            const int step = dir * (kHistBins / 3);                      // per byte of offset: j = 3 * codon ordinal
+            do {
+                const int j = __ffs(cm) - 1;
+                cm &= cm - 1;
+                const uint32_t r0 = lds_u8(rb + j), r1 = lds_u8(rb + j + 1), r2 = lds_u8(rb + j + 2);
+                const uint32_t k0 = lds_u8(cls + r0), k1 = lds_u8(cls + r1), k2 = lds_u8(cls + r2);
+                uint32_t code = (k0 << s_lo) + k1 * 4 + (k2 << s_hi);
+                if (max(k0, max(k1, k2)) >= 4) {
+                    code = (k0 == 4 || k1 == 4 || k2 == 4) ? kCodeUndef : kCodeOther;
+                    if (code == kCodeOther) {
+                        const uint32_t chr = lut_chr + (mi << 8);
+                        const uint32_t n0 = lds_u8(chr + r0), n1 = lds_u8(chr + r1), n2 = lds_u8(chr + r2);
+                        const uint32_t key = mi ? (n2 << 16) | (n1 << 8) | n0 : (n0 << 16) | (n1 << 8) | n2;
+                        const int cidx = (int)rw.x + dir * (int)((uint32_t)j * 0xABu >> 9);   // j / 3 for j < 48
+                        atomicMin(&other_min[cidx], key);
+                        atomicMax(&other_max[cidx], key);
+                    }
                 }
-            }
-            atomicAdd(&hist[(size_t)cidx * kHistBins + code], weight);
+                atomicAdd(&hist[base + (uint32_t)(step * j) + code], 1u);
+            } while (cm);
         }
+        if (++l == kSpanRuns) break;
+        rw = __ldg(rp + l);
     }
 }
 
-constexpr int kFusedQueue = 128;     // entries per warp (ring, power of two)
-constexpr int kFusedEntryWords = 8;  // 5 raw + span + pad: 32 bytes, written as one 16-byte and one 8-byte store
-
-__global__ void __launch_bounds__(kFusedWarps * 32)
-k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, int64_t n_rows, const uint8_t *__restrict__ cons,
-             const uint32_t *__restrict__ alt, int64_t n_spans, const SpanRun *__restrict__ runs, uint32_t *__restrict__ hist,
-             uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max, int rows_per_warp)
+// Persistent warps.  A warp works on a block of kFusedSpans = 31 spans: lanes 0-30 own one span each and lane 31
+// only fetches the next 16 bytes, whose first word is lane 30's look-ahead (every lane's look-ahead is its
+// right-hand neighbour's first word).  The (span block) x (rows) plane is cut into chunks that warps claim
+// from a global counter (sched[0]): chunks of chunk_a rows over rows [0, rows_a), then chunks of
+// kFusedTailRows rows over the rest, so the last claims are small and every SM finishes at about the same
+// time whatever the local mutation density.  The parked-span queue carries the span index, so it lives across
+// chunks; the counts of rows equal to a span's second and third reference go to alt[span][..] (one RED each per
+// chunk) and k_fused_fixup decodes those patterns once, weighted.  The last block to finish leaves sched[]
+// zeroed for the next launch.
+// UNROLL rows are loaded at a time; parked spans are decoded after every DRAIN_EVERY rows, so the ring needs
+// 31 + 32 * DRAIN_EVERY entries (QUEUE, a power of two).  inv_sb = floor(2^32 / n_sb).
+template <int UNROLL, int DRAIN_EVERY, int QUEUE, int MIN_BLOCKS>
+__global__ void __launch_bounds__(kFusedWarps * 32, MIN_BLOCKS)
+k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, uint32_t n_rows, const uint8_t *__restrict__ cons,
+             uint32_t *__restrict__ alt, uint32_t n_spans, const SpanRun *__restrict__ runs, uint32_t *__restrict__ hist,
+             uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max, uint32_t *__restrict__ sched,
+             uint32_t n_sb, uint32_t inv_sb, uint32_t chunk_a, uint32_t rows_a, uint32_t k_a, uint32_t k_total)
 {
-    __shared__ uint8_t lut_chr[2][256];
-    __shared__ uint8_t lut_cls[2][256];
-    __shared__ __align__(16) uint32_t queue_all[kFusedWarps][kFusedQueue * kFusedEntryWords];
+    static_assert(QUEUE >= 31 + 32 * DRAIN_EVERY && (QUEUE & (QUEUE - 1)) == 0 && UNROLL % DRAIN_EVERY == 0, "ring too small");
+    constexpr int kFusedQueueBytes = QUEUE * kFusedEntryBytes;        // the ring is aligned to its size
+    extern __shared__ __align__(16) uint8_t fused_smem[];             // kFusedWarps rings + one ring of slack for the alignment
+    __shared__ uint8_t lut_chr[2 * 256];
+    __shared__ uint8_t lut_cls[2 * 256];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     for (int s = 0; s < 2; s++) {
         const uint8_t n = norm_char((uint8_t)t, s);
-        lut_chr[s][t] = n;
-        lut_cls[s][t] = class_of(n);
+        lut_chr[s * 256 + t] = n;
+        lut_cls[s * 256 + t] = class_of(n);
     }
     __syncthreads();
 
-    uint32_t *queue = queue_all[warp];
-    uint32_t q_base = (uint32_t)__cvta_generic_to_shared(queue);
-    uint32_t q_head = 0, q_count = 0;    // warp-uniform
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(fused_smem);
+    const uint32_t pad = (kFusedQueueBytes - (smem0 & (kFusedQueueBytes - 1))) & (kFusedQueueBytes - 1);
+    uint32_t q_base = smem0 + pad + warp * kFusedQueueBytes;
+    uint32_t a_cls = (uint32_t)__cvta_generic_to_shared(lut_cls), a_chr = (uint32_t)__cvta_generic_to_shared(lut_chr);
+    uint32_t q_head = 0, q_tail = 0;    // byte offsets into the ring, warp-uniform, free-running
     unsigned lt = (1u << lane) - 1;
-    asm volatile("" : "+r"(lt), "+r"(q_base));      // pinned in registers: ptxas otherwise re-derives both in the loop (S2R, MOV, LEA)
+    const uint32_t lane_ofs = lane * kFusedEntryBytes;
+    uint32_t one = 1u + (uint32_t)lane;          // 1 in lane 0, the only lane that claims
 
-    const int64_t span = (int64_t)blockIdx.x * 32 + lane;
-    const bool live = span < n_spans;
-    const uint32_t sp = (uint32_t)(live ? span : n_spans - 1);
-    const int64_t row_begin = ((int64_t)blockIdx.y * kFusedWarps + warp) * rows_per_warp;
-    const int n_my = (int)max((int64_t)0, min((int64_t)rows_per_warp, n_rows - row_begin));
-    const uint4 c = *reinterpret_cast<const uint4 *>(cons + (int64_t)sp * 16);
-    const uint32_t c4 = *reinterpret_cast<const uint32_t *>(cons + (int64_t)sp * 16 + 16);
-    // the span's second reference: its most common non-consensus bytes among the sampled rows (the consensus
-    // itself when the sample had none).  Rows equal to it are only counted here and decoded once, weighted.
-    const uint4 a = *reinterpret_cast<const uint4 *>(alt + (int64_t)sp * kAltWords);
-    const uint32_t a4 = alt[(int64_t)sp * kAltWords + 4];
-    uint32_t n_alt = 0;
-    const uint8_t *p = aln + (int64_t)sp * 16 + row_begin * pitch;
+    auto drain = [&]() {     // at most 31 + 32 * DRAIN_EVERY parked entries between drains
+        while (q_tail - q_head >= 32u * kFusedEntryBytes) {
+            __syncwarp();
+            fused_decode(q_base | ((q_head + lane_ofs) & (kFusedQueueBytes - 1)), cons, runs, hist, other_min, other_max, a_cls, a_chr);
+            __syncwarp();
+            q_head += 32u * kFusedEntryBytes;
+        }
+    };
 
-    // one row of the warp: compare with both references, count or park
-    auto row = [&](const uint4 &v, uint32_t tail) {
-        const uint32_t nxt = __shfl_down_sync(kFull, v.x, 1);
-        const uint32_t v4 = lane == 31 ? tail : nxt;
-        const uint32_t d = (v.x ^ c.x) | (v.y ^ c.y) | (v.z ^ c.z) | (v.w ^ c.w) | ((v4 ^ c4) & 0xFFFFu);
-        const uint32_t da = (v.x ^ a.x) | (v.y ^ a.y) | (v.z ^ a.z) | (v.w ^ a.w) | ((v4 ^ a4) & 0xFFFFu);
-        n_alt += (da == 0 && d != 0 && live) ? 1u : 0u;
-        const bool differs = d != 0 && da != 0 && live;
-        const unsigned bal = __ballot_sync(kFull, differs);
-        if (bal) {           // nothing to park on most rows of a realistic alignment
-            if (differs) {   // park the bytes; a full warp decodes 32 parked spans at a time
-                const uint32_t at = q_base + ((q_head + q_count + __popc(bal & lt)) & (kFusedQueue - 1)) * (kFusedEntryWords * 4);
-                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(at), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(at + 16), "r"(v4), "r"(sp) : "memory");
+    uint32_t k_next = 0;
+    if (lane == 0) k_next = claim_async(sched, one);
+    uint32_t k = __shfl_sync(kFull, k_next, 0);
+    while (k < k_total) {
+        const bool in_a = k < k_a;
+        uint32_t rb, sb;
+        div_mod(in_a ? k : k - k_a, n_sb, inv_sb, rb, sb);
+        const uint32_t row0 = in_a ? rb * chunk_a : rows_a + rb * kFusedTailRows;
+        const uint32_t n_my = in_a ? chunk_a : min((uint32_t)kFusedTailRows, n_rows - row0);
+        const uint32_t span = sb * kFusedSpans + lane;
+        uint32_t live = lane < kFusedSpans && span < n_spans ? 0xFFFFFFFFu : 0u;
+        uint32_t sp = min(span, n_spans - 1);        // the references of a dead lane are never used
+        // pinned in registers: ptxas otherwise re-derives them inside the row loop (S2R, LDC, compares, LEA)
+        asm volatile("" : "+r"(lt), "+r"(q_base), "+r"(sp), "+r"(live));
+        const uint4 c = *reinterpret_cast<const uint4 *>(cons + (size_t)sp * 16);
+        const uint32_t c4 = *reinterpret_cast<const uint32_t *>(cons + (size_t)sp * 16 + 16);
+        // the span's second and third reference: its most common non-consensus bytes among the sampled rows (the
+        // consensus itself when the sample had none).  Rows equal to one of them are only counted here.
+        const uint32_t *ap = alt + (size_t)sp * kAltWords;
+        const uint4 a = *reinterpret_cast<const uint4 *>(ap);
+        const uint32_t a4 = ap[4];
+        const uint4 b = *reinterpret_cast<const uint4 *>(ap + kAltSecond);
+        const uint32_t b4 = ap[kAltSecond + 4];
+        uint32_t n_alt = 0, n_alt2 = 0;
+        const uint8_t *p = aln + (size_t)min(span, n_spans) * 16 + (size_t)row0 * pitch;
+
+        // one row of the warp: compare with the three references, count or park
+        auto row = [&](const uint4 &v) {
+            const uint32_t v4 = __shfl_down_sync(kFull, v.x, 1);
+            const uint32_t d = ((v.x ^ c.x) | (v.y ^ c.y) | (v.z ^ c.z) | (v.w ^ c.w) | ((v4 ^ c4) & 0xFFFFu)) & live;
+            const uint32_t da = (v.x ^ a.x) | (v.y ^ a.y) | (v.z ^ a.z) | (v.w ^ a.w) | ((v4 ^ a4) & 0xFFFFu);
+            const uint32_t db = (v.x ^ b.x) | (v.y ^ b.y) | (v.z ^ b.z) | (v.w ^ b.w) | ((v4 ^ b4) & 0xFFFFu);
+            n_alt += (da == 0 && d != 0) ? 1u : 0u;
+            n_alt2 += (db == 0 && da != 0 && d != 0) ? 1u : 0u;
+            const bool differs = d != 0 && da != 0 && db != 0;
+            const unsigned bal = __ballot_sync(kFull, differs);
+            if (bal) {           // nothing to park on most rows of a realistic alignment
+                if (differs) {   // park the bytes; a full warp decodes 32 parked spans at a time
+                    const uint32_t at = q_base | ((q_tail + __popc(bal & lt) * kFusedEntryBytes) & (kFusedQueueBytes - 1));
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(at), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(at + 16), "r"(v4), "r"(sp) : "memory");
+                }
+                q_tail += __popc(bal) * kFusedEntryBytes;
             }
-            q_count += __popc(bal);
-        }
-    };
-    auto drain = [&]() {     // at most 31 + 64 parked entries between drains
-        while (q_count >= 32) {
-            __syncwarp();
-            fused_decode(queue + ((q_head + lane) & (kFusedQueue - 1)) * kFusedEntryWords, cons, runs, hist, other_min, other_max,
-                         lut_cls, lut_chr);
-            __syncwarp();
-            q_head += 32;
-            q_count -= 32;
-        }
-    };
+        };
 
-    int i = 0;
-    for (; i + kFusedUnroll <= n_my; i += kFusedUnroll, p += kFusedUnroll * pitch) {
-        uint4 v[kFusedUnroll];
-        uint32_t tail[kFusedUnroll];
+        // the next chunk is claimed while the last full group of rows of this one is processed: early enough to
+        // hide most of the atomic's latency, late enough that its result does not sit in a register for long
+        const uint32_t claim_at = n_my >= UNROLL ? (n_my / UNROLL - 1) * UNROLL : 0xFFFFFFFFu;
+        uint32_t i = 0;
+        for (; i + UNROLL <= n_my; i += UNROLL) {
+            if (i == claim_at && lane == 0) k_next = claim_async(sched, one);
+            uint4 v[UNROLL];
 #pragma unroll
-        for (int u = 0; u < kFusedUnroll; u++) {
-            const uint8_t *q = p + u * pitch;
-            v[u] = ld_stream_v4(reinterpret_cast<const uint4 *>(q));
-            tail[u] = 0;
-            // lane 31 has no right-hand neighbour in the warp: it fetches its own look-ahead word
-            if (lane == 31) tail[u] = *reinterpret_cast<const uint32_t *>(q + 16);
-        }
+            for (int u = 0; u < UNROLL; u++) {
+                v[u] = ld_stream_v4(reinterpret_cast<const uint4 *>(p));
+                p += pitch;
+            }
 #pragma unroll
-        for (int u = 0; u < kFusedUnroll; u++) {
-            row(v[u], tail[u]);
-            if (u & 1) drain();
+            for (int u = 0; u < UNROLL; u++) {
+                row(v[u]);
+                if ((u + 1) % DRAIN_EVERY == 0) drain();
+            }
         }
+        if (claim_at == 0xFFFFFFFFu && lane == 0) k_next = claim_async(sched, one);
+        for (; i < n_my; i++, p += pitch) {          // the last rows of the group
+            const uint4 v = ld_stream_v4(reinterpret_cast<const uint4 *>(p));
+            row(v);
+            drain();
+        }
+        if (n_alt) atomicAdd(&alt[(size_t)sp * kAltWords + kAltCount], n_alt);
+        if (n_alt2) atomicAdd(&alt[(size_t)sp * kAltWords + kAltSecond + kAltCount], n_alt2);
+        k = __shfl_sync(kFull, k_next, 0);
     }
-    for (; i < n_my; i++, p += pitch) {          // the last rows of the group
-        const uint4 v = ld_stream_v4(reinterpret_cast<const uint4 *>(p));
-        uint32_t tail = 0;
-        if (lane == 31) tail = *reinterpret_cast<const uint32_t *>(p + 16);
-        row(v, tail);
-        drain();
-    }
     __syncwarp();
-    if ((uint32_t)lane < q_count)
-        fused_decode(queue + ((q_head + lane) & (kFusedQueue - 1)) * kFusedEntryWords, cons, runs, hist, other_min, other_max,
-                     lut_cls, lut_chr);
-    __syncwarp();
-    // the rows that equalled the span's second reference: one decode, weighted by their number
-    uint32_t *e = queue + lane * kFusedEntryWords;
-    e[0] = a.x; e[1] = a.y; e[2] = a.z; e[3] = a.w; e[4] = a4; e[5] = sp;
-    __syncwarp();
-    if (n_alt) fused_decode(e, cons, runs, hist, other_min, other_max, lut_cls, lut_chr, n_alt);
+    if ((uint32_t)lane_ofs < q_tail - q_head)
+        fused_decode(q_base | ((q_head + lane_ofs) & (kFusedQueueBytes - 1)), cons, runs, hist, other_min, other_max, a_cls, a_chr);
+    __syncthreads();
+    if (t == 0 && atomicAdd(&sched[1], 1u) == gridDim.x - 1) { sched[0] = 0; sched[1] = 0; }
 }
 
 // The two reference rows of the compare-with-reference kernels, from the first n_sample (<= 32) rows of
@@ -401,21 +462,26 @@ k_vote_refs(const uint8_t *__restrict__ aln, int64_t pitch, int n_sample, int64_
         else *reinterpret_cast<uint32_t *>(cons + sp * 16) = c[0];
     }
     if (sp >= n_spans) return;
-    // second reference: the most frequent differing pattern
+    // second and third reference: the two most frequent patterns that differ from the consensus
     const bool differs = ((valid >> lane) & 1u) && ((x[0] ^ c[0]) | (x[1] ^ c[1]) | (x[2] ^ c[2]) | (x[3] ^ c[3]) | (x[4] ^ c[4])) != 0;
     const unsigned same = __match_any_sync(kFull, x[0]) & __match_any_sync(kFull, x[1]) & __match_any_sync(kFull, x[2]) &
                           __match_any_sync(kFull, x[3]) & __match_any_sync(kFull, x[4]) & valid;
-    uint32_t key = differs ? ((uint32_t)__popc(same) << 5) | (uint32_t)(31 - lane) : 0u;    // most frequent, lowest row on ties
+    unsigned taken = 0;                                             // the sampled rows that carry an already chosen pattern
+    for (int r = 0; r < 2; r++) {
+        uint32_t key = differs && !((taken >> lane) & 1u) ? ((uint32_t)__popc(same) << 5) | (uint32_t)(31 - lane) : 0u;   // most frequent, lowest row on ties
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(kFull, key, o));
-    const int src = 31 - (int)(key & 31u);
-    uint32_t w[5];
+        for (int o = 16; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(kFull, key, o));
+        const int src = 31 - (int)(key & 31u);
+        uint32_t w[5];
 #pragma unroll
-    for (int k = 0; k < 5; k++) w[k] = __shfl_sync(kFull, x[k], src);
-    if (lane == 0) {
-        uint32_t *o = alt + sp * kAltWords;
+        for (int k = 0; k < 5; k++) w[k] = __shfl_sync(kFull, x[k], src);
+        taken |= __shfl_sync(kFull, same, src);
+        if (lane == 0) {
+            uint32_t *o = alt + sp * kAltWords + r * kAltSecond;
 #pragma unroll
-        for (int k = 0; k < 5; k++) o[k] = key ? w[k] : c[k];
+            for (int k = 0; k < 5; k++) o[k] = key ? w[k] : c[k];
+            o[kAltCount] = 0;      // rows equal to this pattern, counted by k_fused_hist, spent by k_fused_fixup
+        }
     }
 }
 
@@ -423,7 +489,7 @@ k_vote_refs(const uint8_t *__restrict__ aln, int64_t pitch, int n_sample, int64_
 // the decode path.  The consensus codon's code (and, for an 'other' codon, its character key) comes straight
 // from the consensus row and the codon index map.
 __global__ void __launch_bounds__(256)
-k_fused_fixup(const uint8_t *__restrict__ cons, int64_t cons_shift, const CodonMap *__restrict__ map,
+k_fused_fixup(const uint8_t *__restrict__ cons, int64_t cons_shift, const uint32_t *__restrict__ alt, const CodonMap *__restrict__ map,
               const uint8_t *__restrict__ regular, int64_t n_codons, uint32_t n_rows,
               uint32_t *__restrict__ hist, uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max)
 {
@@ -432,24 +498,38 @@ k_fused_fixup(const uint8_t *__restrict__ cons, int64_t cons_shift, const CodonM
     const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (c >= n_codons || !regular[c]) return;
     uint32_t *h = hist + c * kHistBins;
-    const uint32_t seen = warp_sum_u32(h[lane] + h[lane + 32] + (lane < kHistBins - 64 ? h[lane + 64] : 0u));
-    const uint32_t rest = n_rows - seen;       // rows that were never parked, or decoded to the consensus code
-    if (rest && lane == 0) {
-        const CodonMap m = map[c];
-        const uint8_t n0 = norm_char(cons[m.p0 + cons_shift], m.minus), n1 = norm_char(cons[m.p1 + cons_shift], m.minus),
-                      n2 = norm_char(cons[m.p2 + cons_shift], m.minus);
+    const CodonMap m = map[c];
+    auto credit = [&](uint8_t r0, uint8_t r1, uint8_t r2, uint32_t rows) {     // lane 0: rows copies of the codon r0 r1 r2
+        const uint8_t n0 = norm_char(r0, m.minus), n1 = norm_char(r1, m.minus), n2 = norm_char(r2, m.minus);
         const uint8_t k0 = class_of(n0), k1 = class_of(n1), k2 = class_of(n2);
         uint32_t code;
         if (max(k0, max(k1, k2)) < 4) code = k0 * 16 + k1 * 4 + k2;
         else if (k0 == 4 || k1 == 4 || k2 == 4) code = kCodeUndef;
         else code = kCodeOther;
-        h[code] += rest;
-        if (code == kCodeOther) {              // their codon string is the consensus string
+        h[code] += rows;
+        if (code == kCodeOther) {
             const uint32_t key = ((uint32_t)n0 << 16) | ((uint32_t)n1 << 8) | n2;
             other_min[c] = min(other_min[c], key);
             other_max[c] = max(other_max[c], key);
         }
+    };
+    const int64_t q0 = m.p0 + cons_shift, q1 = m.p1 + cons_shift, q2 = m.p2 + cons_shift;     // columns relative to the first span
+    const uint8_t c0 = cons[q0], c1 = cons[q1], c2 = cons[q2];
+    // the rows that equalled the second or third reference of the span this codon starts in: one decode each, weighted
+    const int64_t sp = min(q0, q2) >> 4;
+    for (int r = 0; r < 2; r++) {
+        const uint32_t *ap = alt + sp * kAltWords + r * kAltSecond;
+        const uint32_t n_alt = ap[kAltCount];
+        if (n_alt) {
+            const uint8_t *ab = reinterpret_cast<const uint8_t *>(ap) - sp * 16;   // 20 pattern bytes from column sp * 16
+            const uint8_t a0 = ab[q0], a1 = ab[q1], a2 = ab[q2];
+            if ((a0 != c0 || a1 != c1 || a2 != c2) && lane == 0) credit(a0, a1, a2, n_alt);
+            __syncwarp();
+        }
     }
+    const uint32_t seen = warp_sum_u32(h[lane] + h[lane + 32] + (lane < kHistBins - 64 ? h[lane + 64] : 0u));
+    const uint32_t rest = n_rows - seen;       // rows that equalled the consensus codon and were never recorded
+    if (rest && lane == 0) credit(c0, c1, c2, rest);
 }
 
 // irregular codons (split across CDS segments, or beyond the run capacity of a span) go
@@ -1029,24 +1109,55 @@ void launch_vote_refs(const uint8_t *d_aln, int64_t pitch, int n_sample, int64_t
     k_vote_refs<<<(unsigned)((n_spans + 1 + 7) / 8), 256, 0, stream>>>(d_aln, pitch, min(n_sample, 32), n_spans, d_cons, d_alt);
 }
 
-void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, const uint8_t *d_cons, const uint32_t *d_alt,
+void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, const uint8_t *d_cons, uint32_t *d_alt,
                        int64_t n_spans, const SpanRun *d_runs, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max,
-                       cudaStream_t stream)
+                       uint32_t *d_sched, int n_sms, cudaStream_t stream)
 {
     if (n_spans <= 0 || n_rows <= 0) return;
-    static const int rows_per_warp = [] { const char *v = getenv("SNPG_SPAN_ROWS"); return v ? max(4, atoi(v)) : kFusedRowsPerWarp; }();
-    const int64_t rows_per_block = (int64_t)kFusedWarps * rows_per_warp;
-    dim3 grid((unsigned)((n_spans + 31) / 32), (unsigned)((n_rows + rows_per_block - 1) / rows_per_block));
-    k_fused_hist<<<grid, kFusedWarps * 32, 0, stream>>>(d_aln, pitch, n_rows, d_cons, d_alt, n_spans, d_runs, d_hist, d_other_min,
-                                                        d_other_max, rows_per_warp);
+    using Kernel = void (*)(const uint8_t *, int64_t, uint32_t, const uint8_t *, uint32_t *, uint32_t, const SpanRun *, uint32_t *, uint32_t *,
+                            uint32_t *, uint32_t *, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t);
+    // variant (experiments): 0 = 4 blocks/SM at <= 64 registers; 1 = 3 blocks/SM, no register cap
+    static const int variant = [] { const char *v = getenv("SNPG_SPAN_VARIANT"); return v ? max(0, min(1, atoi(v))) : 0; }();
+    static const Kernel kernel = variant == 1 ? (Kernel)k_fused_hist<4, 2, 128, 3> : (Kernel)k_fused_hist<4, 2, 128, 4>;
+    static const size_t smem = (size_t)(kFusedWarps + 1) * 128 * kFusedEntryBytes;
+    static const int blocks_per_sm = [] {
+        int nb = 0;
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kFusedWarps * 32, smem) != cudaSuccess || nb < 1) nb = 1;
+        if (const char *v = getenv("SNPG_SPAN_BLOCKS")) nb = max(1, min(nb, atoi(v)));
+        return nb;
+    }();
+    static const int env_rows = [] { const char *v = getenv("SNPG_SPAN_ROWS"); return v ? max(4, atoi(v) & ~3) : 0; }();
+    static const int env_tail = [] { const char *v = getenv("SNPG_SPAN_TAIL"); return v ? max(0, min(100, atoi(v))) : 2; }();
+    const int64_t n_sb = (n_spans + kFusedSpans - 1) / kFusedSpans;
+    // chunk indices are 32-bit: very long alignments go out in several launches over row ranges
+    const int64_t rows_per_launch = std::max<int64_t>(kFusedTailRows, (((int64_t)1 << 31) / n_sb) & ~(int64_t)3);
+    for (int64_t r0 = 0; r0 < n_rows; r0 += rows_per_launch) {
+        const int64_t rows = std::min<int64_t>(rows_per_launch, n_rows - r0);
+        int64_t grid = (int64_t)n_sms * blocks_per_sm;
+        // chunk of rows a warp claims at a time: about a third of a warp's share of the (span block, row) plane,
+        // 4..32 rows (measured on config 2: 12 rows 94 us, 16 rows 90, 32 rows 82, 64 rows 84, 128 rows 91); the
+        // last env_tail % of the rows go out in chunks of kFusedTailRows
+        const int64_t share = rows * n_sb / (grid * kFusedWarps);
+        const int64_t chunk_a = env_rows ? env_rows : std::max<int64_t>(kFusedTailRows, std::min<int64_t>(32, (share / 3) & ~(int64_t)3));
+        const int64_t rows_a = chunk_a > kFusedTailRows ? (rows - rows * env_tail / 100) / chunk_a * chunk_a : 0;
+        const int64_t k_a = rows_a / chunk_a * n_sb;
+        const int64_t k_b = (rows - rows_a + kFusedTailRows - 1) / kFusedTailRows * n_sb;
+        grid = std::max<int64_t>(1, std::min<int64_t>(grid, (k_a + k_b + kFusedWarps - 1) / kFusedWarps));
+        kernel<<<(unsigned)grid, kFusedWarps * 32, smem, stream>>>(
+            d_aln + (size_t)r0 * pitch, pitch, (uint32_t)rows, d_cons, d_alt, (uint32_t)n_spans, d_runs, d_hist, d_other_min, d_other_max,
+            d_sched, (uint32_t)n_sb, n_sb == 1 ? 0xFFFFFFFFu : (uint32_t)(((uint64_t)1 << 32) / (uint64_t)n_sb), (uint32_t)chunk_a,
+            (uint32_t)rows_a, (uint32_t)k_a, (uint32_t)(k_a + k_b));
+    }
 }
 
-void launch_fused_fixup(const uint8_t *d_cons, int64_t cons_shift, const CodonMap *d_map, const uint8_t *d_regular, int64_t n_codons,
-                        uint32_t n_rows, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max, cudaStream_t stream)
+void launch_fused_fixup(const uint8_t *d_cons, int64_t cons_shift, const uint32_t *d_alt, const CodonMap *d_map, const uint8_t *d_regular,
+                        int64_t n_codons, uint32_t n_rows, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max,
+                        cudaStream_t stream)
 {
     if (n_codons <= 0) return;
-    k_fused_fixup<<<(unsigned)((n_codons + 7) / 8), 256, 0, stream>>>(d_cons, cons_shift, d_map, d_regular, n_codons, n_rows, d_hist,
-                                                                       d_other_min, d_other_max);
+    k_fused_fixup<<<(unsigned)((n_codons + 7) / 8), 256, 0, stream>>>(d_cons, cons_shift, d_alt, d_map, d_regular, n_codons, n_rows,
+                                                                       d_hist, d_other_min, d_other_max);
 }
 
 void launch_scatter_irregular(const uint32_t *d_tmp_hist, const uint32_t *d_tmp_min, const uint32_t *d_tmp_max,

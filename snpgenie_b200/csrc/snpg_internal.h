@@ -59,13 +59,19 @@ void launch_hist(const uint8_t *d_codes, int64_t n_pad, int64_t n_codons, uint32
 // n_spans*16 + 4 readable bytes.
 void launch_vote_refs(const uint8_t *d_aln, int64_t pitch, int n_sample, int64_t n_spans, uint8_t *d_cons, uint32_t *d_alt,
                       cudaStream_t stream);
-// d_alt[span][kAltWords]: the span's second reference pattern (launch_vote_refs).
-constexpr int kAltWords = 8;
-void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, const uint8_t *d_cons, const uint32_t *d_alt, int64_t n_spans,
-                       const SpanRun *d_runs, uint32_t *d_hist, uint32_t *d_other_min,
-                       uint32_t *d_other_max, cudaStream_t stream);
-void launch_fused_fixup(const uint8_t *d_cons, int64_t cons_shift, const CodonMap *d_map, const uint8_t *d_regular, int64_t n_codons,
-                        uint32_t n_rows, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max, cudaStream_t stream);
+// d_alt[span][kAltWords]: words 0-4 the span's second reference pattern, words kAltSecond.. the third
+// (launch_vote_refs); word kAltCount of each the number of rows that equalled it (zeroed by launch_vote_refs,
+// raised by launch_fused_hist, spent by launch_fused_fixup).  d_sched: two zeroed u32 (chunk counter, finished
+// blocks); the kernel leaves them zeroed.  Every row needs n_spans*16 + 16 readable bytes.
+constexpr int kAltWords = 16;
+constexpr int kAltSecond = 8;
+constexpr int kAltCount = 5;
+void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, const uint8_t *d_cons, uint32_t *d_alt, int64_t n_spans,
+                       const SpanRun *d_runs, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max, uint32_t *d_sched,
+                       int n_sms, cudaStream_t stream);
+void launch_fused_fixup(const uint8_t *d_cons, int64_t cons_shift, const uint32_t *d_alt, const CodonMap *d_map, const uint8_t *d_regular,
+                        int64_t n_codons, uint32_t n_rows, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max,
+                        cudaStream_t stream);
 // TMA-tiled variant of launch_fused_hist (same contract: counts of the non-consensus codons of the regular
 // codons are added to hist).  make_tile_tensor_map fills a 128-byte CUtensorMap (64-byte aligned storage)
 // for a block of rows; it returns false when the geometry cannot be expressed (base or pitch not 16-byte
