@@ -875,7 +875,10 @@ constexpr int kBootSmemLimit = 200 * 1024;
 
 // (A banked two-stage sampler -- class counts per shared-memory bank group first, then conflict-free draws inside
 // the lane's class; exact, 49 M -> 30 M wavefronts -- was measured at 226 us against 212 us for the direct draws
-// below: its extra instructions cost more than the conflicts.  See profiles/README.md and the git history.)
+// below: its extra instructions cost more than the conflicts.  So did a two-table form -- a 4-byte class word per
+// draw that carries a conserved codon's sites in whole sixths, summed in integers, the other codons queued per
+// warp and gathered 32 at a time from compact 32-byte rows: 274 us -- and unrolling the draw loop twice (223 us).
+// See profiles/README.md and the git history.)
 template <bool SMEM>
 __global__ void __launch_bounds__(kBootWarps * 32)
 k_bootstrap(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, const int *__restrict__ order, int n_products,
