@@ -1138,12 +1138,13 @@ void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, cons
     for (int64_t r0 = 0; r0 < n_rows; r0 += rows_per_launch) {
         const int64_t rows = std::min<int64_t>(rows_per_launch, n_rows - r0);
         int64_t grid = (int64_t)n_sms * blocks_per_sm;
-        // chunk of rows a warp claims at a time: about half of a warp's share of the (span block, row) plane,
-        // 4..32 rows (measured on config 2: 12 rows 94 us, 16 rows 90, 32 rows 82, 64 rows 84, 128 rows 91); the
-        // last env_tail % of the rows go out in chunks of kFusedTailRows
+        // chunk of rows a warp claims at a time (measured on config 2: 12 rows 94 us, 16 rows 90, 32 rows 82, 64 rows
+        // 84, 128 rows 91).  When every warp gets at least two chunks, the last env_tail % of the rows go out in chunks
+        // of kFusedTailRows to even out the finish; a small launch (a staged block of a host buffer) is one chunk per
+        // warp and only the rows left over by the chunk size go out small.
         const int64_t share = rows * n_sb / (grid * kFusedWarps);
-        const int64_t chunk_a = env_rows ? env_rows : std::max<int64_t>(kFusedTailRows, std::min<int64_t>(32, (share / 2) & ~(int64_t)3));
-        const int64_t rows_a = chunk_a > kFusedTailRows ? (rows - rows * env_tail / 100) / chunk_a * chunk_a : 0;
+        const int64_t chunk_a = env_rows ? env_rows : 32;
+        const int64_t rows_a = (share >= 2 * chunk_a ? rows - rows * env_tail / 100 : rows) / chunk_a * chunk_a;
         const int64_t k_a = rows_a / chunk_a * n_sb;
         const int64_t k_b = (rows - rows_a + kFusedTailRows - 1) / kFusedTailRows * n_sb;
         grid = std::max<int64_t>(1, std::min<int64_t>(grid, (k_a + k_b + kFusedWarps - 1) / kFusedWarps));
