@@ -987,6 +987,141 @@ k_bootstrap(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, 
     }
 }
 
+// K4, weight-matrix form (the default when a warp's counts fit in shared memory): the contraction
+// north_star describes.  The shared-memory pipe bounds the direct form above -- a 16-byte gather at 32 random
+// addresses costs ~11.5 wavefronts, and every draw pays one or two.  Here a draw only bumps a 1-byte counter
+// of its slot (a 4-byte shared-memory atomic at a random word: ~3.4 wavefronts per 32 draws): a warp turns its
+// replicate into the row K[slot] of the multinomial weight matrix.  The block then contracts its 32 rows with
+// the product's table, sums[rep][0..3] = sum over slots of K[rep][slot] * stats4[slot], as FP64 tensor-core tiles
+// (mma.m8n8k4: A = 8 replicates x 4 slots of counts, B = 4 slots x the 4 statistics read straight from global
+// memory/L2, 8 warps splitting the slots of each group of 8 replicates, partials summed in a fixed order).
+// Same Philox stream, draw for draw, as the direct form; replicate sums agree to rounding.  A counter would wrap at
+// 256 draws of one slot in one replicate: impossible up to C = 255 and of probability < 1e-400 beyond
+// (each of the C draws picks the slot with probability 1/(C+1)).
+constexpr int kBootKSplit = 8;                     // warps sharing the slots of one group of 8 replicates
+static_assert(kBootWarps == 4 * kBootKSplit, "32 replicates per batch: 4 groups of 8, each contracted by 8 warps");
+
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(kBootWarps * 32)
+k_bootstrap_mma(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, const int *__restrict__ order, int n_products,
+                int64_t b_first, int64_t b_count, uint2 key, uint32_t stream_id, const uint32_t *__restrict__ salt,
+                double *__restrict__ rep, double *__restrict__ vals, double *__restrict__ prod_sums, uint32_t row_words)
+{
+    extern __shared__ uint32_t s_cnt[];            // [kBootWarps][row_words]: 1-byte counters, four to a word
+    if (salt) stream_id += *salt;      // a replayed CUDA graph gets its per-call stream number from memory
+    __shared__ double2 s_sums[kBootWarps * kBootRepsPerWarp][2];     // the block's replicate sums, for the dense epilogue
+    __shared__ double s_part[kBootKSplit][kBootWarps][4];            // per K-split partial sums of a batch; also the reduction scratch
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int p = order ? order[blockIdx.y] : blockIdx.y;
+    const int64_t c0 = ofs[p];
+    const uint32_t C = (uint32_t)(ofs[p + 1] - c0);
+    const double *G = stats4 + 4 * c0;
+    if (prod_sums && blockIdx.x == 0) {
+        // the product's sums (wg:690-693): the additions and the tree of k_product_sums
+        double *red = &s_part[0][0][0];            // kBootKSplit * kBootWarps * 4 = 1,024 doubles
+        const double2 *G2 = reinterpret_cast<const double2 *>(G);
+        double s[4] = {0, 0, 0, 0};
+        for (uint32_t c = threadIdx.x; c < C; c += blockDim.x) {
+            const double2 x = G2[2 * c], y = G2[2 * c + 1];
+            s[0] += x.x; s[1] += x.y; s[2] += y.x; s[3] += y.y;
+        }
+        for (int q = 0; q < 4; q++) {
+            red[threadIdx.x] = s[q];
+            __syncthreads();
+            for (int h = kBootWarps * 32 / 2; h > 0; h >>= 1) {
+                if ((int)threadIdx.x < h) red[threadIdx.x] += red[threadIdx.x + h];
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) prod_sums[4 * p + q] = red[0];
+            __syncthreads();
+        }
+    }
+    const uint32_t nquad = (C + 3) >> 2, full_quads = C >> 2;     // the partial quad, if any, is quad full_quads
+    const uint32_t nslot4 = (C + 1 + 3) >> 2;      // groups of 4 slots (slot 0 is the empty one)
+    uint32_t *mine = s_cnt + (size_t)warp * row_words;
+    for (int k = 0; k < kBootRepsPerWarp; k++) {
+        // --- sampling: one replicate per warp -> its row of counts
+        for (uint32_t i = lane; i < nslot4; i += 32) mine[i] = 0;     // the words this product's slots occupy
+        __syncwarp();
+        const int64_t bl = ((int64_t)blockIdx.x * kBootWarps + warp) * kBootRepsPerWarp + k;
+        if (bl < b_count) {                        // warp-uniform
+            const uint64_t b = (uint64_t)(b_first + bl);
+            const uint32_t mine_s = (uint32_t)__cvta_generic_to_shared(mine);
+            auto bump = [&](uint32_t u) {          // one draw: slot = floor(u * (C+1) / 2^32); its byte of the row goes up by one
+                const uint32_t r = __umulhi(u, C + 1);
+                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(mine_s + (r & ~3u)), "r"(1u << ((r << 3) & 24u)) : "memory");
+            };
+            uint32_t q = lane;
+            for (; q < full_quads; q += 32) {
+                const uint4 u = philox4x32_10(make_uint4(q, (uint32_t)b, (uint32_t)(b >> 32) ^ ((uint32_t)p << 8), stream_id), key);
+                bump(u.x); bump(u.y); bump(u.z); bump(u.w);
+            }
+            if (q < nquad) {                       // the last, partial quad (one lane)
+                const uint4 u = philox4x32_10(make_uint4(q, (uint32_t)b, (uint32_t)(b >> 32) ^ ((uint32_t)p << 8), stream_id), key);
+                const uint32_t nd = C & 3;
+                bump(u.x);
+                if (nd > 1) bump(u.y);
+                if (nd > 2) bump(u.z);
+            }
+        }
+        __syncthreads();
+        // --- contraction: group gq of 8 replicates x the slots of K-split ks, 4 slots per tensor-core tile
+        {
+            const int gq = warp / kBootKSplit, ks = warp % kBootKSplit;
+            const uint32_t per = (nslot4 + kBootKSplit - 1) / kBootKSplit;
+            const uint32_t t0 = min(nslot4, ks * per), t1 = min(nslot4, t0 + per);
+            const uint32_t *cnt_row = s_cnt + (size_t)(gq * 8 + (lane >> 2)) * row_words;   // A: row = replicate lane/4
+            const uint32_t col = lane & 3;                                                  //    column = slot 4t + lane%4
+            const uint32_t stat = lane >> 2;                                                // B: column = statistic lane/4 (0 beyond 3)
+            const uint32_t sel = 0x4440u + col;                                             // byte col of a word, zero-extended
+            const double *gb = G + 4 * (int64_t)col - 4 + stat;                             // + 16 t: stats4[slot 4t + col][stat]
+            double acc0 = 0.0, acc1 = 0.0;
+            auto tile = [&](uint32_t t, bool guard) {
+                const double a = (double)__byte_perm(cnt_row[t], 0u, sel);
+                double bv = 0.0;
+                if (stat < 4 && (!guard || (4 * t + col >= 1 && 4 * t + col <= C))) bv = __ldg(gb + 16 * (size_t)t);
+                dmma_m8n8k4(acc0, acc1, a, bv);
+            };
+            uint32_t t = t0;
+            if (t == 0 && t < t1) tile(t++, true);                  // holds slot 0, the empty one
+            const uint32_t t_inner = min(t1, (C + 1) / 4);          // tiles below hold slots 1..C only
+#pragma unroll 4
+            for (; t < t_inner; t++) tile(t, false);
+            for (; t < t1; t++) tile(t, true);                      // may reach past slot C
+            // D: lane holds row lane/4, columns 2*(lane%4), +1; statistics are columns 0..3
+            if (col < 2) {
+                s_part[ks][gq * 8 + (lane >> 2)][2 * col] = acc0;
+                s_part[ks][gq * 8 + (lane >> 2)][2 * col + 1] = acc1;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < kBootWarps * 4) {        // (replicate of the batch, statistic): K-split partials in a fixed order
+            const int w = threadIdx.x >> 2, q = threadIdx.x & 3;
+            double v = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < kBootKSplit; ks++) v += s_part[ks][w][q];
+            reinterpret_cast<double *>(&s_sums[w * kBootRepsPerWarp + k][0])[q] = v;
+        }
+        __syncthreads();
+    }
+    // dense epilogue: one thread per (replicate of the block, statistic), as in k_bootstrap
+    constexpr int kReps = kBootWarps * kBootRepsPerWarp;
+    const int i = threadIdx.x, r = i % kReps, which = i / kReps;
+    const int64_t bl = (int64_t)blockIdx.x * kReps + r;
+    if (which < 6 && bl < b_count) {
+        const double2 x = s_sums[r][0], y = s_sums[r][1];
+        if (rep && which == 0) {
+            double2 *o = reinterpret_cast<double2 *>(rep + 4 * ((size_t)p * b_count + bl));
+            o[0] = x;
+            o[1] = y;
+        }
+        if (vals) vals[((size_t)which * n_products + p) * b_count + bl] = rep_value(x.x, x.y, y.x, y.y, which);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // K6: SD over replicates in the reference's two-pass form with n-1
 // (wg:1351-1365).  One block per (item, statistic) over rep[item][B][4]; the
@@ -1235,7 +1370,16 @@ void launch_bootstrap(const double *d_stats4, const int64_t *d_prod_ofs, const i
     dim3 grid((unsigned)((b_count + per_block - 1) / per_block), (unsigned)n_products);
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     const size_t smem = (size_t)(max_codons + 1) * 32;
-    if (smem <= (size_t)kBootSmemLimit) {
+    static const int form = [] { const char *v = getenv("SNPG_BOOT_FORM"); return v ? atoi(v) : 1; }();   // 0 = direct gathers, 1 = weight matrix
+    // a warp's counters: one byte per slot, rows padded to an odd number of words (no two of the eight rows a
+    // tensor-core tile reads share a bank)
+    const size_t row_words = (((size_t)max_codons + 1 + 3) / 4) | 1;
+    if (form == 1 && row_words * 4 * kBootWarps <= (size_t)kBootSmemLimit) {
+        cudaFuncSetAttribute(k_bootstrap_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, kBootSmemLimit);  // per device
+        k_bootstrap_mma<<<grid, kBootWarps * 32, row_words * 4 * kBootWarps, stream>>>(d_stats4, d_prod_ofs, d_order, n_products, b_first,
+                                                                                       b_count, key, stream_id, d_salt, d_rep, d_vals,
+                                                                                       d_prod_sums, (uint32_t)row_words);
+    } else if (smem <= (size_t)kBootSmemLimit) {
         cudaFuncSetAttribute(k_bootstrap<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBootSmemLimit);  // per device
         k_bootstrap<true><<<grid, kBootWarps * 32, smem, stream>>>(d_stats4, d_prod_ofs, d_order, n_products, b_first, b_count, key,
                                                                     stream_id, d_salt, d_rep, d_vals, d_prod_sums);
