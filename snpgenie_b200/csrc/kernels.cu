@@ -998,7 +998,8 @@ k_bootstrap(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, 
 // Same Philox stream, draw for draw, as the direct form; replicate sums agree to rounding.  A counter would wrap at
 // 256 draws of one slot in one replicate: impossible up to C = 255 and of probability < 1e-400 beyond
 // (each of the C draws picks the slot with probability 1/(C+1)).
-constexpr int kBootKSplit = 8;                     // warps sharing the slots of one group of 8 replicates
+constexpr int kBootKSplit = 8;                     // warps sharing the slots of one group of 8 replicates (one row per warp)
+constexpr int kBootMaxRows = 8;                    // replicates a warp takes at a time when the product is short
 static_assert(kBootWarps == 4 * kBootKSplit, "32 replicates per batch: 4 groups of 8, each contracted by 8 warps");
 
 __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
@@ -1012,7 +1013,7 @@ k_bootstrap_mma(const double *__restrict__ stats4, const int64_t *__restrict__ o
 {
     extern __shared__ uint32_t s_cnt[];            // [kBootWarps][row_words]: 1-byte counters, four to a word
     if (salt) stream_id += *salt;      // a replayed CUDA graph gets its per-call stream number from memory
-    __shared__ double2 s_sums[kBootWarps * kBootRepsPerWarp][2];     // the block's replicate sums, for the dense epilogue
+    __shared__ double2 s_sums[kBootWarps * kBootMaxRows][2];         // a batch's replicate sums, for the dense epilogue
     __shared__ double s_part[kBootKSplit][kBootWarps][4];            // per K-split partial sums of a batch; also the reduction scratch
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int p = order ? order[blockIdx.y] : blockIdx.y;
@@ -1041,21 +1042,33 @@ k_bootstrap_mma(const double *__restrict__ stats4, const int64_t *__restrict__ o
     }
     const uint32_t nquad = (C + 3) >> 2, full_quads = C >> 2;     // the partial quad, if any, is quad full_quads
     const uint32_t nslot4 = (C + 1 + 3) >> 2;      // groups of 4 slots (slot 0 is the empty one)
-    uint32_t *mine = s_cnt + (size_t)warp * row_words;
-    for (int k = 0; k < kBootRepsPerWarp; k++) {
-        // --- sampling: one replicate per warp -> its row of counts
-        for (uint32_t i = lane; i < nslot4; i += 32) mine[i] = 0;     // the words this product's slots occupy
+    // A short product does not fill a warp's counters: its warps then take m = 2, 4 or 8 replicates at a time (32 / m
+    // lanes and one row of rw words each), so that the fixed cost of a batch is spread over 32 m replicates.
+    const uint32_t rw = nslot4 | 1;                // words per row: odd, so the eight rows of a tile fall in different banks
+    uint32_t m = 1;
+    while (m < kBootMaxRows && 2 * m * rw <= row_words) m *= 2;
+    const uint32_t rows = kBootWarps * m;          // replicates per batch
+    const uint32_t n_batch = m >= kBootRepsPerWarp ? 1 : kBootRepsPerWarp / m;
+    const int64_t block_first = (int64_t)blockIdx.x * rows * n_batch;
+    if (block_first >= b_count) return;            // the grid is sized for m = 1
+    const uint32_t lanes_per = 32 / m, sub = lane / lanes_per, sl = lane % lanes_per;
+    uint32_t *warp_rows = s_cnt + (size_t)warp * m * rw;
+    const uint32_t mine_s = (uint32_t)__cvta_generic_to_shared(warp_rows + (size_t)sub * rw);
+    double *part = &s_part[0][0][0];               // [ksplit][rows][4], ksplit * rows = 256
+    for (uint32_t k = 0; k < n_batch; k++) {
+        const int64_t batch_first = block_first + (int64_t)k * rows;
+        // --- sampling: one replicate per group of 32 / m lanes -> its row of counts
+        for (uint32_t i = lane; i < m * rw; i += 32) warp_rows[i] = 0;
         __syncwarp();
-        const int64_t bl = ((int64_t)blockIdx.x * kBootWarps + warp) * kBootRepsPerWarp + k;
-        if (bl < b_count) {                        // warp-uniform
+        const int64_t bl = batch_first + warp * m + sub;
+        if (bl < b_count) {
             const uint64_t b = (uint64_t)(b_first + bl);
-            const uint32_t mine_s = (uint32_t)__cvta_generic_to_shared(mine);
             auto bump = [&](uint32_t u) {          // one draw: slot = floor(u * (C+1) / 2^32); its byte of the row goes up by one
                 const uint32_t r = __umulhi(u, C + 1);
                 asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(mine_s + (r & ~3u)), "r"(1u << ((r << 3) & 24u)) : "memory");
             };
-            uint32_t q = lane;
-            for (; q < full_quads; q += 32) {
+            uint32_t q = sl;
+            for (; q < full_quads; q += lanes_per) {
                 const uint4 u = philox4x32_10(make_uint4(q, (uint32_t)b, (uint32_t)(b >> 32) ^ ((uint32_t)p << 8), stream_id), key);
                 bump(u.x); bump(u.y); bump(u.z); bump(u.w);
             }
@@ -1070,14 +1083,16 @@ k_bootstrap_mma(const double *__restrict__ stats4, const int64_t *__restrict__ o
         __syncthreads();
         // --- contraction: group gq of 8 replicates x the slots of K-split ks, 4 slots per tensor-core tile
         {
-            const int gq = warp / kBootKSplit, ks = warp % kBootKSplit;
-            const uint32_t per = (nslot4 + kBootKSplit - 1) / kBootKSplit;
+            const uint32_t ksplit = kBootKSplit / m;                 // warps per group of 8 replicates
+            const uint32_t gq = warp / ksplit, ks = warp % ksplit;
+            const uint32_t per = (nslot4 + ksplit - 1) / ksplit;
             const uint32_t t0 = min(nslot4, ks * per), t1 = min(nslot4, t0 + per);
-            const uint32_t *cnt_row = s_cnt + (size_t)(gq * 8 + (lane >> 2)) * row_words;   // A: row = replicate lane/4
-            const uint32_t col = lane & 3;                                                  //    column = slot 4t + lane%4
-            const uint32_t stat = lane >> 2;                                                // B: column = statistic lane/4 (0 beyond 3)
-            const uint32_t sel = 0x4440u + col;                                             // byte col of a word, zero-extended
-            const double *gb = G + 4 * (int64_t)col - 4 + stat;                             // + 16 t: stats4[slot 4t + col][stat]
+            const uint32_t row = gq * 8 + (lane >> 2);
+            const uint32_t *cnt_row = s_cnt + (size_t)row * rw;      // A: row = replicate lane/4
+            const uint32_t col = lane & 3;                           //    column = slot 4t + lane%4
+            const uint32_t stat = lane >> 2;                         // B: column = statistic lane/4 (0 beyond 3)
+            const uint32_t sel = 0x4440u + col;                      // byte col of a word, zero-extended
+            const double *gb = G + 4 * (int64_t)col - 4 + stat;      // + 16 t: stats4[slot 4t + col][stat]
             double acc0 = 0.0, acc1 = 0.0;
             auto tile = [&](uint32_t t, bool guard) {
                 const double a = (double)__byte_perm(cnt_row[t], 0u, sel);
@@ -1093,32 +1108,34 @@ k_bootstrap_mma(const double *__restrict__ stats4, const int64_t *__restrict__ o
             for (; t < t1; t++) tile(t, true);                      // may reach past slot C
             // D: lane holds row lane/4, columns 2*(lane%4), +1; statistics are columns 0..3
             if (col < 2) {
-                s_part[ks][gq * 8 + (lane >> 2)][2 * col] = acc0;
-                s_part[ks][gq * 8 + (lane >> 2)][2 * col + 1] = acc1;
+                double *o = part + ((size_t)ks * rows + row) * 4 + 2 * col;
+                o[0] = acc0;
+                o[1] = acc1;
             }
         }
         __syncthreads();
-        if (threadIdx.x < kBootWarps * 4) {        // (replicate of the batch, statistic): K-split partials in a fixed order
-            const int w = threadIdx.x >> 2, q = threadIdx.x & 3;
+        if (threadIdx.x < rows * 4) {              // (replicate of the batch, statistic): K-split partials in a fixed order
+            const uint32_t r = threadIdx.x >> 2, q = threadIdx.x & 3, ksplit = kBootKSplit / m;
             double v = 0.0;
-#pragma unroll
-            for (int ks = 0; ks < kBootKSplit; ks++) v += s_part[ks][w][q];
-            reinterpret_cast<double *>(&s_sums[w * kBootRepsPerWarp + k][0])[q] = v;
+            for (uint32_t ks = 0; ks < ksplit; ks++) v += part[((size_t)ks * rows + r) * 4 + q];
+            reinterpret_cast<double *>(&s_sums[r][0])[q] = v;
         }
         __syncthreads();
-    }
-    // dense epilogue: one thread per (replicate of the block, statistic), as in k_bootstrap
-    constexpr int kReps = kBootWarps * kBootRepsPerWarp;
-    const int i = threadIdx.x, r = i % kReps, which = i / kReps;
-    const int64_t bl = (int64_t)blockIdx.x * kReps + r;
-    if (which < 6 && bl < b_count) {
-        const double2 x = s_sums[r][0], y = s_sums[r][1];
-        if (rep && which == 0) {
-            double2 *o = reinterpret_cast<double2 *>(rep + 4 * ((size_t)p * b_count + bl));
-            o[0] = x;
-            o[1] = y;
+        // dense epilogue: one thread per (replicate of the batch, statistic), as in k_bootstrap
+        for (uint32_t i = threadIdx.x; i < rows * 6; i += blockDim.x) {
+            const uint32_t r = i % rows, which = i / rows;
+            const int64_t bl2 = batch_first + r;
+            if (bl2 < b_count) {
+                const double2 x = s_sums[r][0], y = s_sums[r][1];
+                if (rep && which == 0) {
+                    double2 *o = reinterpret_cast<double2 *>(rep + 4 * ((size_t)p * b_count + bl2));
+                    o[0] = x;
+                    o[1] = y;
+                }
+                if (vals) vals[((size_t)which * n_products + p) * b_count + bl2] = rep_value(x.x, x.y, y.x, y.y, which);
+            }
         }
-        if (vals) vals[((size_t)which * n_products + p) * b_count + bl] = rep_value(x.x, x.y, y.x, y.y, which);
+        // (the next batch's first barrier comes after its sampling: s_sums and part are not written before it)
     }
 }
 
@@ -1373,7 +1390,8 @@ void launch_bootstrap(const double *d_stats4, const int64_t *d_prod_ofs, const i
     static const int form = [] { const char *v = getenv("SNPG_BOOT_FORM"); return v ? atoi(v) : 1; }();   // 0 = direct gathers, 1 = weight matrix
     // a warp's counters: one byte per slot, rows padded to an odd number of words (no two of the eight rows a
     // tensor-core tile reads share a bank)
-    const size_t row_words = (((size_t)max_codons + 1 + 3) / 4) | 1;
+    // (at least 16 KB a block even for a short table, so that short products can take several replicates per warp)
+    const size_t row_words = std::max<size_t>((((size_t)max_codons + 1 + 3) / 4) | 1, 127);
     if (form == 1 && row_words * 4 * kBootWarps <= (size_t)kBootSmemLimit) {
         cudaFuncSetAttribute(k_bootstrap_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, kBootSmemLimit);  // per device
         k_bootstrap_mma<<<grid, kBootWarps * 32, row_words * 4 * kBootWarps, stream>>>(d_stats4, d_prod_ofs, d_order, n_products, b_first,
