@@ -135,6 +135,15 @@ int snpg_codon_strings(snpg_ctx *ctx, int slot, int product, int64_t codon, uint
 #define SNPG_OPT_FUSED_KERNEL 4
 #define SNPG_FUSED_TMA_TILES 0
 #define SNPG_FUSED_LDG_SPANS 1
+/* SNPG_OPT_BOOTSTRAP_KERNEL (default SNPG_BOOT_WEIGHTS): how the whole-product bootstrap (wg:854-916) sums a
+ * replicate.  WEIGHTS: every draw bumps a 1-byte counter of its slot in shared memory -- a warp turns its
+ * replicate into a row of the multinomial weight matrix -- and the block contracts its rows with the product's
+ * (N_sites, S_sites, N_diffs, S_diffs) table as FP64 tensor-core tiles.  GATHER: every draw gathers its codon's
+ * row from a shared-memory table and adds it.  Same Philox stream draw for draw: the replicate sums of the two
+ * agree to rounding (tested).  Tables too large for shared memory use GATHER from global memory either way. */
+#define SNPG_OPT_BOOTSTRAP_KERNEL 5
+#define SNPG_BOOT_GATHER 0
+#define SNPG_BOOT_WEIGHTS 1
 int snpg_set_option(snpg_ctx *ctx, int option, int64_t value);
 
 /* ---- test hooks for the bit-exact checks ---------------------------------

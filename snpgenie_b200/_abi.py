@@ -13,7 +13,8 @@ LIB_PATH = os.path.join(_HERE, "libsnpgenie_cuda.so")
 
 OK, E_ARG, E_STATE, E_INPUT, E_CUDA, E_NOMEM = 0, -1, -2, -3, -4, -5
 CODE_UNDEF, CODE_OTHER, HIST_BINS = 64, 65, 66
-OPT_KEEP_CODES, OPT_PROFILE, OPT_SITE_COUNTS, OPT_FUSED_KERNEL = 1, 2, 3, 4
+OPT_KEEP_CODES, OPT_PROFILE, OPT_SITE_COUNTS, OPT_FUSED_KERNEL, OPT_BOOTSTRAP_KERNEL = 1, 2, 3, 4, 5
+BOOT_GATHER, BOOT_WEIGHTS = 0, 1
 FUSED_TMA_TILES, FUSED_LDG_SPANS = 0, 1
 KERNEL_KINDS = ("pack", "hist", "stats", "sums", "bootstrap", "moments", "window", "other", "fused", "sites")
 

@@ -81,6 +81,7 @@ struct snpg_ctx {
     DevBuf d_tiles, d_sched;              // d_sched: the tile kernel's chunk counter and finished-CTA counter
     int64_t n_tiles = 0;
     int fused_kernel = SNPG_FUSED_LDG_SPANS;
+    int boot_kernel = SNPG_BOOT_WEIGHTS;
     int n_sms = 148;
     int tma_l2_promotion = 2;             // CU_TENSOR_MAP_L2_PROMOTION_L2_128B (SNPG_TMA_L2PROMO overrides: 0..3)
     // groups
@@ -420,6 +421,11 @@ int snpg_set_option(snpg_ctx *ctx, int option, int64_t value) {
     if (option == SNPG_OPT_FUSED_KERNEL) {
         NEED(ctx, value == SNPG_FUSED_TMA_TILES || value == SNPG_FUSED_LDG_SPANS, SNPG_E_ARG, "unknown fused kernel %lld", (long long)value);
         ctx->fused_kernel = (int)value;
+        return SNPG_OK;
+    }
+    if (option == SNPG_OPT_BOOTSTRAP_KERNEL) {
+        NEED(ctx, value == SNPG_BOOT_GATHER || value == SNPG_BOOT_WEIGHTS, SNPG_E_ARG, "unknown bootstrap kernel %lld", (long long)value);
+        ctx->boot_kernel = (int)value;
         return SNPG_OK;
     }
     if (option == SNPG_OPT_PROFILE) { ctx->profile_mask = value < 0 ? 0xFFFFFFFFu : (uint32_t)value; return SNPG_OK; }
@@ -961,7 +967,7 @@ int snpg_bootstrap_product(snpg_ctx *ctx, const double *stats4, const uint8_t *k
     CU(ctx, ctx->s_vals.ensure(sizeof(double) * 6 * (size_t)B));
     {
         Launch l(ctx, SNPG_K_BOOT);
-        launch_bootstrap(ctx->s_in.as<double>(), ctx->s_misc.as<int64_t>(), nullptr, 1, C, 0, B, ctx->seed, sid, nullptr,
+        launch_bootstrap(ctx->boot_kernel, ctx->s_in.as<double>(), ctx->s_misc.as<int64_t>(), nullptr, 1, C, 0, B, ctx->seed, sid, nullptr,
                          sums_out ? ctx->s_rep.as<double>() : nullptr, ctx->s_vals.as<double>(), nullptr, ctx->stream);
     }
     { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->s_vals.as<double>(), 1, B, ctx->s_se.as<double>(), ctx->stream); }
@@ -1029,7 +1035,7 @@ int snpg_bootstrap_all_device(snpg_ctx *ctx, const double *d_stats4_full, int64_
     if (int rc = bind(ctx)) return rc;
     {
         Launch l(ctx, SNPG_K_BOOT);
-        launch_bootstrap(d_stats4_full, ctx->d_full_ofs.as<int64_t>(), ctx->d_order_full.as<int>(), ctx->n_products, ctx->max_codons_full,
+        launch_bootstrap(ctx->boot_kernel, d_stats4_full, ctx->d_full_ofs.as<int64_t>(), ctx->d_order_full.as<int>(), ctx->n_products, ctx->max_codons_full,
                          b_first, b_count, ctx->seed, 0x30000u, nullptr, d_rep_out, nullptr, nullptr, ctx->stream);
     }
     CU(ctx, cudaGetLastError());
@@ -1097,7 +1103,7 @@ int snpg_between_all(snpg_ctx *ctx, const int *groups, int n_groups, int64_t min
             if (boot) {
                 {
                     Launch l(ctx, SNPG_K_BOOT);      // also writes the product sums
-                    launch_bootstrap(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), ctx->d_order_local.as<int>(), P,
+                    launch_bootstrap(ctx->boot_kernel, ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), ctx->d_order_local.as<int>(), P,
                                      ctx->max_codons_local, 0, B, ctx->seed, 0x50000u + ctx->call_id++, nullptr, nullptr,
                                      ctx->s_vals.as<double>(), d_pair_sums, ctx->stream);
                 }
@@ -1132,7 +1138,7 @@ static int within_all_impl(snpg_ctx *ctx, int group, int64_t B, double *prod_sum
         {
             Launch l(ctx, SNPG_K_BOOT);
             const uint32_t sid = d_salt ? 0x40000u : 0x40000u + ctx->call_id++;
-            launch_bootstrap(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), ctx->d_order_local.as<int>(), P,
+            launch_bootstrap(ctx->boot_kernel, ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), ctx->d_order_local.as<int>(), P,
                              ctx->max_codons_local, 0, B, ctx->seed, sid, d_salt, nullptr, ctx->s_vals.as<double>(),
                              ctx->s_sums.as<double>(), ctx->stream);      // also writes the product sums
         }

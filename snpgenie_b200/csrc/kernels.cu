@@ -16,6 +16,7 @@
 #include <cstdlib>
 
 #include "snpg_device.cuh"
+#include "../../include/snpgenie_cuda.h"
 #include "snpg_internal.h"
 
 namespace snpg {
@@ -1378,7 +1379,7 @@ void launch_product_sums(const double *d_stats4, const int64_t *d_prod_ofs, int 
     k_product_sums<<<n_products, kSumThreads, 0, stream>>>(d_stats4, d_prod_ofs, d_sums);
 }
 
-void launch_bootstrap(const double *d_stats4, const int64_t *d_prod_ofs, const int *d_order, int n_products, int64_t max_codons,
+void launch_bootstrap(int form, const double *d_stats4, const int64_t *d_prod_ofs, const int *d_order, int n_products, int64_t max_codons,
                       int64_t b_first, int64_t b_count, uint64_t seed, uint32_t stream_id, const uint32_t *d_salt, double *d_rep,
                       double *d_vals, double *d_prod_sums, cudaStream_t stream)
 {
@@ -1387,12 +1388,11 @@ void launch_bootstrap(const double *d_stats4, const int64_t *d_prod_ofs, const i
     dim3 grid((unsigned)((b_count + per_block - 1) / per_block), (unsigned)n_products);
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     const size_t smem = (size_t)(max_codons + 1) * 32;
-    static const int form = [] { const char *v = getenv("SNPG_BOOT_FORM"); return v ? atoi(v) : 1; }();   // 0 = direct gathers, 1 = weight matrix
     // a warp's counters: one byte per slot, rows padded to an odd number of words (no two of the eight rows a
     // tensor-core tile reads share a bank)
     // (at least 16 KB a block even for a short table, so that short products can take several replicates per warp)
     const size_t row_words = std::max<size_t>((((size_t)max_codons + 1 + 3) / 4) | 1, 127);
-    if (form == 1 && row_words * 4 * kBootWarps <= (size_t)kBootSmemLimit) {
+    if (form == SNPG_BOOT_WEIGHTS && row_words * 4 * kBootWarps <= (size_t)kBootSmemLimit) {
         cudaFuncSetAttribute(k_bootstrap_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, kBootSmemLimit);  // per device
         k_bootstrap_mma<<<grid, kBootWarps * 32, row_words * 4 * kBootWarps, stream>>>(d_stats4, d_prod_ofs, d_order, n_products, b_first,
                                                                                        b_count, key, stream_id, d_salt, d_rep, d_vals,

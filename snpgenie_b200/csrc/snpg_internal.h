@@ -121,7 +121,8 @@ void launch_product_sums(const double *d_stats4, const int64_t *d_prod_ofs, int 
 // d_rep[p][b][4] replicate sums, d_vals[which][p][b] per-replicate dN, dS, dN-dS, JC x3.  d_prod_sums (or null):
 // sums[p][4] as launch_product_sums writes them, bit for bit, computed on the way from the staged table.
 // d_salt (or null): a device word added to stream_id when the kernel runs (replayed CUDA graphs).
-void launch_bootstrap(const double *d_stats4, const int64_t *d_prod_ofs, const int *d_order, int n_products, int64_t max_codons,
+// form: SNPG_BOOT_WEIGHTS (slot counters + tensor-core contraction) or SNPG_BOOT_GATHER (per-draw row gathers).
+void launch_bootstrap(int form, const double *d_stats4, const int64_t *d_prod_ofs, const int *d_order, int n_products, int64_t max_codons,
                       int64_t b_first, int64_t b_count, uint64_t seed, uint32_t stream_id, const uint32_t *d_salt, double *d_rep,
                       double *d_vals, double *d_prod_sums, cudaStream_t stream);
 // one Philox4x32-10 block on the device (known-answer test hook)

@@ -338,6 +338,34 @@ def test_bootstrap_draws_are_uniform_over_slots(eng, C):
     assert abs(sums[:, 0].var(ddof=1) / var - 1) < 0.06
 
 
+@pytest.mark.parametrize("C", [1, 2, 3, 5, 31, 62, 127, 128, 129, 500, 1274, 4406, 6300, 6500])
+def test_bootstrap_kernels_agree(C):
+    """The weight-matrix kernel (slot counters + FP64 tensor-core contraction, the default) and the gather kernel
+    consume the same Philox stream draw for draw: replicate sums equal to rounding, SEs with them.  Covers one to
+    eight replicates per warp, partial quads, the largest table that fits and one that does not (C = 6500: both
+    take the global-memory gathers)."""
+    from snpgenie_b200 import _abi
+    from snpgenie_b200.engine import Engine
+    rng = np.random.default_rng(C)
+    sites, _ = orc.tables()
+    stats4 = np.zeros((C, 4))
+    conserved = rng.random(C) < 0.7
+    stats4[:, :2] = np.where(conserved[:, None], np.asarray(sites)[rng.integers(0, 64, size=C)], rng.random((C, 2)) * 3)
+    stats4[:, 2:] = np.where(conserved[:, None], 0.0, rng.random((C, 2)))
+    B = 300
+    out = []
+    for kernel in (_abi.BOOT_GATHER, _abi.BOOT_WEIGHTS):
+        with Engine(device=0, seed=77) as e:
+            e.set_option(_abi.OPT_BOOTSTRAP_KERNEL, kernel)
+            out.append(e.bootstrap_product(stats4, B, want_sums=True))
+            keep = (np.arange(C) % 3 != 1).astype(np.uint8)
+            out.append(e.bootstrap_product(stats4, B, keep=keep, want_sums=True))
+    for (s0, se0), (s1, se1) in ((out[0], out[2]), (out[1], out[3])):
+        assert np.allclose(s0, s1, rtol=1e-12, atol=1e-12), C
+        assert np.allclose(se0, se1, rtol=1e-9, atol=1e-15, equal_nan=True), C     # JC of a random dN > 3/4 is NaN in both
+    assert out[0][0][:, 0].max() > 0 or C < 3
+
+
 def test_bootstrap_keep_mask(eng):
     stats4, _ = _stats_from_golden()
     keep = (np.arange(stats4.shape[0]) % 3 != 0).astype(np.uint8)
