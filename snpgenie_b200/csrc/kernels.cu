@@ -1001,39 +1001,45 @@ k_bootstrap(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, 
 // (each of the C draws picks the slot with probability 1/(C+1)).
 constexpr int kBootKSplit = 8;                     // warps sharing the slots of one group of 8 replicates (one row per warp)
 constexpr int kBootMaxRows = 8;                    // replicates a warp takes at a time when the product is short
-static_assert(kBootWarps == 4 * kBootKSplit, "32 replicates per batch: 4 groups of 8, each contracted by 8 warps");
+// Two blocks of kMmaWarps warps share an SM: while one contracts (FP64 tensor pipe) the other samples (integer pipes).
+constexpr int kMmaWarps = 16;
+static_assert(kMmaWarps % kBootKSplit == 0, "a batch is kMmaWarps / 8 groups of 8 replicates, each contracted by 8 warps");
 
 __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(kBootWarps * 32)
+__global__ void __launch_bounds__(kMmaWarps * 32, 2)
 k_bootstrap_mma(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, const int *__restrict__ order, int n_products,
                 int64_t b_first, int64_t b_count, uint2 key, uint32_t stream_id, const uint32_t *__restrict__ salt,
                 double *__restrict__ rep, double *__restrict__ vals, double *__restrict__ prod_sums, uint32_t row_words)
 {
-    extern __shared__ uint32_t s_cnt[];            // [kBootWarps][row_words]: 1-byte counters, four to a word
+    extern __shared__ uint32_t s_cnt[];            // [kMmaWarps][row_words]: 1-byte counters, four to a word
     if (salt) stream_id += *salt;      // a replayed CUDA graph gets its per-call stream number from memory
-    __shared__ double2 s_sums[kBootWarps * kBootMaxRows][2];         // a batch's replicate sums, for the dense epilogue
-    __shared__ double s_part[kBootKSplit][kBootWarps][4];            // per K-split partial sums of a batch; also the reduction scratch
+    __shared__ double2 s_sums[kMmaWarps * kBootMaxRows][2];         // a batch's replicate sums, for the dense epilogue
+    __shared__ double s_part[kBootKSplit][kMmaWarps][4];            // per K-split partial sums of a batch; also the reduction scratch
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int p = order ? order[blockIdx.y] : blockIdx.y;
     const int64_t c0 = ofs[p];
     const uint32_t C = (uint32_t)(ofs[p + 1] - c0);
     const double *G = stats4 + 4 * c0;
     if (prod_sums && blockIdx.x == 0) {
-        // the product's sums (wg:690-693): the additions and the tree of k_product_sums
-        double *red = &s_part[0][0][0];            // kBootKSplit * kBootWarps * 4 = 1,024 doubles
+        // the product's sums (wg:690-693) with the additions and the tree of k_product_sums, bit for bit: its
+        // kSumThreads partial sums, held kSumThreads / blockDim.x to a thread, and the same halving tree
+        static_assert(kSumThreads == 2 * kMmaWarps * 32, "a thread holds the partial sums of two of k_product_sums' threads");
+        double *red = &s_part[0][0][0];            // kBootKSplit * kMmaWarps * 4 = kMmaWarps * 32 doubles: one per thread
         const double2 *G2 = reinterpret_cast<const double2 *>(G);
-        double s[4] = {0, 0, 0, 0};
-        for (uint32_t c = threadIdx.x; c < C; c += blockDim.x) {
-            const double2 x = G2[2 * c], y = G2[2 * c + 1];
-            s[0] += x.x; s[1] += x.y; s[2] += y.x; s[3] += y.y;
+        double s[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+        for (int v = 0; v < 2; v++) {
+            for (uint32_t c = threadIdx.x + v * (kSumThreads / 2); c < C; c += kSumThreads) {
+                const double2 x = G2[2 * c], y = G2[2 * c + 1];
+                s[v][0] += x.x; s[v][1] += x.y; s[v][2] += y.x; s[v][3] += y.y;
+            }
         }
         for (int q = 0; q < 4; q++) {
-            red[threadIdx.x] = s[q];
+            red[threadIdx.x] = s[0][q] + s[1][q];  // the tree's first level: t += t + kSumThreads / 2
             __syncthreads();
-            for (int h = kBootWarps * 32 / 2; h > 0; h >>= 1) {
+            for (int h = kSumThreads / 4; h > 0; h >>= 1) {
                 if ((int)threadIdx.x < h) red[threadIdx.x] += red[threadIdx.x + h];
                 __syncthreads();
             }
@@ -1048,14 +1054,14 @@ k_bootstrap_mma(const double *__restrict__ stats4, const int64_t *__restrict__ o
     const uint32_t rw = nslot4 | 1;                // words per row: odd, so the eight rows of a tile fall in different banks
     uint32_t m = 1;
     while (m < kBootMaxRows && 2 * m * rw <= row_words) m *= 2;
-    const uint32_t rows = kBootWarps * m;          // replicates per batch
+    const uint32_t rows = kMmaWarps * m;           // replicates per batch
     const uint32_t n_batch = m >= kBootRepsPerWarp ? 1 : kBootRepsPerWarp / m;
     const int64_t block_first = (int64_t)blockIdx.x * rows * n_batch;
     if (block_first >= b_count) return;            // the grid is sized for m = 1
     const uint32_t lanes_per = 32 / m, sub = lane / lanes_per, sl = lane % lanes_per;
     uint32_t *warp_rows = s_cnt + (size_t)warp * m * rw;
     const uint32_t mine_s = (uint32_t)__cvta_generic_to_shared(warp_rows + (size_t)sub * rw);
-    double *part = &s_part[0][0][0];               // [ksplit][rows][4], ksplit * rows = 256
+    double *part = &s_part[0][0][0];               // [ksplit][rows][4], ksplit * rows = 8 * kMmaWarps
     for (uint32_t k = 0; k < n_batch; k++) {
         const int64_t batch_first = block_first + (int64_t)k * rows;
         // --- sampling: one replicate per group of 32 / m lanes -> its row of counts
@@ -1392,11 +1398,14 @@ void launch_bootstrap(int form, const double *d_stats4, const int64_t *d_prod_of
     // tensor-core tile reads share a bank)
     // (at least 16 KB a block even for a short table, so that short products can take several replicates per warp)
     const size_t row_words = std::max<size_t>((((size_t)max_codons + 1 + 3) / 4) | 1, 127);
-    if (form == SNPG_BOOT_WEIGHTS && row_words * 4 * kBootWarps <= (size_t)kBootSmemLimit) {
-        cudaFuncSetAttribute(k_bootstrap_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, kBootSmemLimit);  // per device
-        k_bootstrap_mma<<<grid, kBootWarps * 32, row_words * 4 * kBootWarps, stream>>>(d_stats4, d_prod_ofs, d_order, n_products, b_first,
-                                                                                       b_count, key, stream_id, d_salt, d_rep, d_vals,
-                                                                                       d_prod_sums, (uint32_t)row_words);
+    if (form == SNPG_BOOT_WEIGHTS && row_words * 4 * kMmaWarps * 2 <= (size_t)kBootSmemLimit) {
+        // two blocks of kMmaWarps warps per SM; the grid is sized for one replicate per warp and two batches a block
+        const int64_t per_mma = (int64_t)kMmaWarps * kBootRepsPerWarp;
+        dim3 grid_mma((unsigned)((b_count + per_mma - 1) / per_mma), (unsigned)n_products);
+        cudaFuncSetAttribute(k_bootstrap_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, kBootSmemLimit / 2);  // per device
+        k_bootstrap_mma<<<grid_mma, kMmaWarps * 32, row_words * 4 * kMmaWarps, stream>>>(d_stats4, d_prod_ofs, d_order, n_products, b_first,
+                                                                                         b_count, key, stream_id, d_salt, d_rep, d_vals,
+                                                                                         d_prod_sums, (uint32_t)row_words);
     } else if (smem <= (size_t)kBootSmemLimit) {
         cudaFuncSetAttribute(k_bootstrap<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBootSmemLimit);  // per device
         k_bootstrap<true><<<grid, kBootWarps * 32, smem, stream>>>(d_stats4, d_prod_ofs, d_order, n_products, b_first, b_count, key,
