@@ -1009,7 +1009,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(kMmaWarps * 32, 2)
+__global__ void __launch_bounds__(kMmaWarps * 32, 32 / kMmaWarps)
 k_bootstrap_mma(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, const int *__restrict__ order, int n_products,
                 int64_t b_first, int64_t b_count, uint2 key, uint32_t stream_id, const uint32_t *__restrict__ salt,
                 double *__restrict__ rep, double *__restrict__ vals, double *__restrict__ prod_sums, uint32_t row_words)
@@ -1026,20 +1026,25 @@ k_bootstrap_mma(const double *__restrict__ stats4, const int64_t *__restrict__ o
     if (prod_sums && blockIdx.x == 0) {
         // the product's sums (wg:690-693) with the additions and the tree of k_product_sums, bit for bit: its
         // kSumThreads partial sums, held kSumThreads / blockDim.x to a thread, and the same halving tree
-        static_assert(kSumThreads == 2 * kMmaWarps * 32, "a thread holds the partial sums of two of k_product_sums' threads");
+        constexpr int kV = kSumThreads / (kMmaWarps * 32);          // partial sums of k_product_sums' threads held by one thread
+        static_assert(kV >= 1 && (kV & (kV - 1)) == 0 && kV * kMmaWarps * 32 == kSumThreads, "block size must divide kSumThreads");
         double *red = &s_part[0][0][0];            // kBootKSplit * kMmaWarps * 4 = kMmaWarps * 32 doubles: one per thread
         const double2 *G2 = reinterpret_cast<const double2 *>(G);
-        double s[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-        for (int v = 0; v < 2; v++) {
-            for (uint32_t c = threadIdx.x + v * (kSumThreads / 2); c < C; c += kSumThreads) {
+        double s[kV][4];
+        for (int v = 0; v < kV; v++) {
+            for (int q = 0; q < 4; q++) s[v][q] = 0.0;
+            for (uint32_t c = threadIdx.x + v * (kMmaWarps * 32); c < C; c += kSumThreads) {
                 const double2 x = G2[2 * c], y = G2[2 * c + 1];
                 s[v][0] += x.x; s[v][1] += x.y; s[v][2] += y.x; s[v][3] += y.y;
             }
         }
+        for (int h = kV / 2; h > 0; h >>= 1)       // the tree's first levels: t += t + h * blockDim.x
+            for (int v = 0; v < h; v++)
+                for (int q = 0; q < 4; q++) s[v][q] += s[v + h][q];
         for (int q = 0; q < 4; q++) {
-            red[threadIdx.x] = s[0][q] + s[1][q];  // the tree's first level: t += t + kSumThreads / 2
+            red[threadIdx.x] = s[0][q];
             __syncthreads();
-            for (int h = kSumThreads / 4; h > 0; h >>= 1) {
+            for (int h = kMmaWarps * 32 / 2; h > 0; h >>= 1) {
                 if ((int)threadIdx.x < h) red[threadIdx.x] += red[threadIdx.x + h];
                 __syncthreads();
             }
@@ -1398,11 +1403,11 @@ void launch_bootstrap(int form, const double *d_stats4, const int64_t *d_prod_of
     // tensor-core tile reads share a bank)
     // (at least 16 KB a block even for a short table, so that short products can take several replicates per warp)
     const size_t row_words = std::max<size_t>((((size_t)max_codons + 1 + 3) / 4) | 1, 127);
-    if (form == SNPG_BOOT_WEIGHTS && row_words * 4 * kMmaWarps * 2 <= (size_t)kBootSmemLimit) {
+    if (form == SNPG_BOOT_WEIGHTS && row_words * 4 * 32 <= (size_t)kBootSmemLimit) {
         // two blocks of kMmaWarps warps per SM; the grid is sized for one replicate per warp and two batches a block
         const int64_t per_mma = (int64_t)kMmaWarps * kBootRepsPerWarp;
         dim3 grid_mma((unsigned)((b_count + per_mma - 1) / per_mma), (unsigned)n_products);
-        cudaFuncSetAttribute(k_bootstrap_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, kBootSmemLimit / 2);  // per device
+        cudaFuncSetAttribute(k_bootstrap_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, kBootSmemLimit * kMmaWarps / 32);  // per device
         k_bootstrap_mma<<<grid_mma, kMmaWarps * 32, row_words * 4 * kMmaWarps, stream>>>(d_stats4, d_prod_ofs, d_order, n_products, b_first,
                                                                                          b_count, key, stream_id, d_salt, d_rep, d_vals,
                                                                                          d_prod_sums, (uint32_t)row_words);
