@@ -3,7 +3,8 @@
 // K1 k_pack        alignment bytes -> 1-byte codon codes (transposed [codon][seq])
 // K2 k_hist        per-codon 66-bin histogram over sequences
 // K3 k_stats       per-codon N/S sites and differences from histograms
-// K4 k_bootstrap   whole-product codon resampling (Philox4x32-10)
+// K4 k_bootstrap_mma  whole-product codon resampling (Philox4x32-10): slot counters x table on the FP64 tensor cores
+//    k_bootstrap      the same with per-draw row gathers (option / tables beyond shared memory)
 // K5 k_window_*    sliding-window sums and per-window resampling
 // K6 k_rep_moments two-pass SD of per-replicate dN, dS, dN-dS (+ Jukes-Cantor)
 //
@@ -188,16 +189,20 @@ k_hist(const uint8_t *__restrict__ codes, int64_t n_pad, int64_t n_codons, int c
 // K1+K2 fused: histogram straight from the alignment bytes, no code matrix.
 // Used when the packed codon matrix is not kept (SNPG_OPT_KEEP_CODES = 0).
 //
-// A thread owns one 16-byte column span of the alignment and walks down the
-// rows; a warp therefore reads 512 contiguous bytes of each row.  Every row's
-// span is XORed against the same span of a consensus row (the group's first
-// sequence).  If the 16 bytes (plus the 2 bytes a codon may reach into the next
-// span) equal the consensus -- the common case in real alignments -- every codon
-// starting in the span equals the consensus codon and nothing is recorded.
-// Otherwise only the codons that contain a differing byte are decoded and
-// counted with a global reduction (RED) into hist[codon][code].  k_fused_fixup
-// then credits each codon's consensus code with (rows - recorded).  Bytes are
-// compared raw, so a lower-case or 'U' residue simply takes the decode path.
+// A thread owns one 16-byte column span of the alignment and walks down rows;
+// a warp covers 31 spans plus the 16 bytes after them, 512 contiguous bytes of
+// each row.  Every row's span is XORed against three reference rows
+// (k_vote_refs): the per-column consensus and the span's two most frequent
+// other patterns.  If the 16 bytes (plus the 2 bytes a codon may reach into the
+// next span) equal the consensus -- the common case in real alignments -- every
+// codon starting in the span equals the consensus codon and nothing is recorded;
+// a row equal to one of the other two only bumps a counter (k_fused_fixup decodes
+// the pattern once, weighted).  Otherwise the bytes are parked and only the codons
+// that contain a byte differing from the consensus are decoded, 32 parked spans
+// at a time, and counted with a global reduction (RED) into hist[codon][code].
+// k_fused_fixup then credits each codon's consensus code with (rows - recorded).
+// Bytes are compared raw, so a lower-case or 'U' residue simply takes the decode
+// path.
 // Algorithmic traffic: every alignment byte of the CDS span read once.
 // ---------------------------------------------------------------------------
 constexpr int kFusedWarps = 8;
