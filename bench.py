@@ -330,7 +330,7 @@ def run_ours(args):
                           "note": "B x products per step / (bootstrap + moments kernel time)",
                           # the weight-matrix kernel's contraction: one mma.m8n8k4.f64 (512 flop, half of it padding) per
                           # 8 replicates x 4 slots; its share of the kernel is in profiles/ (tensor pipe active 28 %)
-                          "dmma_tflops_in_kernel": (2 * 64 * sum(-(-N_BOOT // 8) * -(-(len_p + 1) // 4) for len_p in (p.n_codons for p in products))
+                          "dmma_tflops_in_kernel": (512 * sum(-(-N_BOOT // 8) * -(-(len_p + 1) // 4) for len_p in (p.n_codons for p in products))
                                                     / (kern["bootstrap"]["ms_per_step"] * 1e-3) / 1e12) if "bootstrap" in kern else None},
             "clocks": clocks.summary(),
             "products_gathered": n_products_total,

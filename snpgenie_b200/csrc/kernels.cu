@@ -1062,13 +1062,17 @@ k_bootstrap_mma(const double *__restrict__ stats4, const int64_t *__restrict__ o
     // A short product does not fill a warp's counters: its warps then take m = 2, 4 or 8 replicates at a time (32 / m
     // lanes and one row of rw words each), so that the fixed cost of a batch is spread over 32 m replicates.
     const uint32_t rw = nslot4 | 1;                // words per row: odd, so the eight rows of a tile fall in different banks
-    uint32_t m = 1;
-    while (m < kBootMaxRows && 2 * m * rw <= row_words) m *= 2;
-    const uint32_t rows = kMmaWarps * m;           // replicates per batch
-    const uint32_t n_batch = m >= kBootRepsPerWarp ? 1 : kBootRepsPerWarp / m;
+    uint32_t lm = 0;                               // m = 1 << lm: every count below is a power of two, divisions are shifts
+    while ((2u << lm) <= kBootMaxRows && (2u << lm) * rw <= row_words) lm++;
+    const uint32_t m = 1u << lm;
+    constexpr uint32_t kLogWarps = kMmaWarps == 16 ? 4 : kMmaWarps == 8 ? 3 : 5;
+    static_assert((1u << kLogWarps) == kMmaWarps, "kMmaWarps must be 8, 16 or 32");
+    const uint32_t lrows = kLogWarps + lm;         // log2 of the replicates per batch
+    const uint32_t rows = 1u << lrows;             // replicates per batch
+    const uint32_t n_batch = m >= kBootRepsPerWarp ? 1 : kBootRepsPerWarp >> lm;
     const int64_t block_first = (int64_t)blockIdx.x * rows * n_batch;
     if (block_first >= b_count) return;            // the grid is sized for m = 1
-    const uint32_t lanes_per = 32 / m, sub = lane / lanes_per, sl = lane % lanes_per;
+    const uint32_t lanes_per = 32u >> lm, sub = lane >> (5 - lm), sl = lane & (lanes_per - 1);
     uint32_t *warp_rows = s_cnt + (size_t)warp * m * rw;
     const uint32_t mine_s = (uint32_t)__cvta_generic_to_shared(warp_rows + (size_t)sub * rw);
     double *part = &s_part[0][0][0];               // [ksplit][rows][4], ksplit * rows = 8 * kMmaWarps
@@ -1100,9 +1104,9 @@ k_bootstrap_mma(const double *__restrict__ stats4, const int64_t *__restrict__ o
         __syncthreads();
         // --- contraction: group gq of 8 replicates x the slots of K-split ks, 4 slots per tensor-core tile
         {
-            const uint32_t ksplit = kBootKSplit / m;                 // warps per group of 8 replicates
-            const uint32_t gq = warp / ksplit, ks = warp % ksplit;
-            const uint32_t per = (nslot4 + ksplit - 1) / ksplit;
+            const uint32_t lks = 3 - lm, ksplit = 1u << lks;         // kBootKSplit / m warps per group of 8 replicates
+            const uint32_t gq = warp >> lks, ks = warp & (ksplit - 1);
+            const uint32_t per = (nslot4 + ksplit - 1) >> lks;
             const uint32_t t0 = min(nslot4, ks * per), t1 = min(nslot4, t0 + per);
             const uint32_t row = gq * 8 + (lane >> 2);
             const uint32_t *cnt_row = s_cnt + (size_t)row * rw;      // A: row = replicate lane/4
@@ -1125,22 +1129,22 @@ k_bootstrap_mma(const double *__restrict__ stats4, const int64_t *__restrict__ o
             for (; t < t1; t++) tile(t, true);                      // may reach past slot C
             // D: lane holds row lane/4, columns 2*(lane%4), +1; statistics are columns 0..3
             if (col < 2) {
-                double *o = part + ((size_t)ks * rows + row) * 4 + 2 * col;
+                double *o = part + (((ks << lrows) + row) << 2) + 2 * col;
                 o[0] = acc0;
                 o[1] = acc1;
             }
         }
         __syncthreads();
         if (threadIdx.x < rows * 4) {              // (replicate of the batch, statistic): K-split partials in a fixed order
-            const uint32_t r = threadIdx.x >> 2, q = threadIdx.x & 3, ksplit = kBootKSplit / m;
+            const uint32_t r = threadIdx.x >> 2, q = threadIdx.x & 3, ksplit = kBootKSplit >> lm;
             double v = 0.0;
-            for (uint32_t ks = 0; ks < ksplit; ks++) v += part[((size_t)ks * rows + r) * 4 + q];
+            for (uint32_t ks = 0; ks < ksplit; ks++) v += part[(((ks << lrows) + r) << 2) + q];
             reinterpret_cast<double *>(&s_sums[r][0])[q] = v;
         }
         __syncthreads();
         // dense epilogue: one thread per (replicate of the batch, statistic), as in k_bootstrap
         for (uint32_t i = threadIdx.x; i < rows * 6; i += blockDim.x) {
-            const uint32_t r = i % rows, which = i / rows;
+            const uint32_t r = i & (rows - 1), which = i >> lrows;
             const int64_t bl2 = batch_first + r;
             if (bl2 < b_count) {
                 const double2 x = s_sums[r][0], y = s_sums[r][1];
