@@ -50,6 +50,7 @@ struct Group {
     DevBuf sites;                // [aln_len][5] per-site A,C,G,T,other (SNPG_OPT_SITE_COUNTS)
     bool has_sites = false;
     bool has_codes = false;
+    bool clear_in_vote = false;  // hist/other are cleared by the load's first kernel, not by memsets
 };
 
 }  // namespace
@@ -239,11 +240,15 @@ int prepare_group(snpg_ctx *ctx, Group &g, uint64_t n_seqs) {
     g.n_pad = (int64_t)((n_seqs + kRowPad - 1) / kRowPad) * kRowPad;
     const int64_t cnt = ctx->shard_count;
     if (ctx->keep_codes) CU(ctx, g.codes.ensure((size_t)std::max<int64_t>(1, cnt * g.n_pad)));
-    CU(ctx, g.hist.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, cnt * kHistBins)));
+    CU(ctx, g.hist.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, cnt * kHistBins) + 16));
     CU(ctx, g.other.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, 2 * cnt)));
-    CU(ctx, cudaMemsetAsync(g.hist.p, 0, sizeof(uint32_t) * (size_t)(cnt * kHistBins), ctx->stream));
-    CU(ctx, cudaMemsetAsync(g.other.p, 0xFF, sizeof(uint32_t) * (size_t)cnt, ctx->stream));
-    CU(ctx, cudaMemsetAsync(g.other.as<uint32_t>() + cnt, 0, sizeof(uint32_t) * (size_t)cnt, ctx->stream));
+    // the fused route clears them in its first kernel (launch_vote_refs, first row block) instead of three memsets
+    g.clear_in_vote = !ctx->keep_codes && cnt > 0 && ctx->n_spans > 0 && n_seqs > 0;
+    if (!g.clear_in_vote) {
+        CU(ctx, cudaMemsetAsync(g.hist.p, 0, sizeof(uint32_t) * (size_t)(cnt * kHistBins), ctx->stream));
+        CU(ctx, cudaMemsetAsync(g.other.p, 0xFF, sizeof(uint32_t) * (size_t)cnt, ctx->stream));
+        CU(ctx, cudaMemsetAsync(g.other.as<uint32_t>() + cnt, 0, sizeof(uint32_t) * (size_t)cnt, ctx->stream));
+    }
     g.has_codes = ctx->keep_codes;
     g.has_sites = ctx->site_counts;
     if (ctx->site_counts) {
@@ -269,7 +274,8 @@ int pack_block(snpg_ctx *ctx, Group &g, const uint8_t *d_block, int64_t pitch, i
         // the rows every row is compared with: per-column plurality and per-span runner-up over the group's first rows
         Launch l(ctx, SNPG_K_OTHER);
         launch_vote_refs(d_block, pitch, (int)std::min<int64_t>(rows, 32), ctx->n_spans, ctx->d_cons.as<uint8_t>(), ctx->d_alt.as<uint32_t>(),
-                         ctx->stream);
+                         g.clear_in_vote ? g.hist.as<uint32_t>() : nullptr, omin, omax, ctx->shard_count, ctx->stream);
+        g.clear_in_vote = false;
     }
     if (ctx->site_counts) {
         Launch l(ctx, SNPG_K_SITES);

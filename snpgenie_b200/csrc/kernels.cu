@@ -443,8 +443,17 @@ __device__ __forceinline__ uint32_t plurality_byte(uint32_t b, unsigned valid, i
 
 __global__ void __launch_bounds__(256)
 k_vote_refs(const uint8_t *__restrict__ aln, int64_t pitch, int n_sample, int64_t n_spans, uint8_t *__restrict__ cons,
-            uint32_t *__restrict__ alt)
+            uint32_t *__restrict__ alt, uint4 *__restrict__ zero_hist, int64_t zero_vec, uint32_t *__restrict__ other_min,
+            uint32_t *__restrict__ other_max, int64_t n_codons)
 {
+    // the group's histograms start from zero: cleared here (when asked to) instead of by three memsets ahead of the kernel
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < zero_vec; i += (int64_t)gridDim.x * blockDim.x)
+        zero_hist[i] = make_uint4(0, 0, 0, 0);
+    if (other_min)
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_codons; i += (int64_t)gridDim.x * blockDim.x) {
+            other_min[i] = 0xFFFFFFFFu;
+            other_max[i] = 0;
+        }
     const int lane = threadIdx.x & 31;
     const int64_t sp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (sp > n_spans) return;
@@ -1279,10 +1288,15 @@ void launch_hist(const uint8_t *d_codes, int64_t n_pad, int64_t n_codons, uint32
 }
 
 void launch_vote_refs(const uint8_t *d_aln, int64_t pitch, int n_sample, int64_t n_spans, uint8_t *d_cons, uint32_t *d_alt,
-                      cudaStream_t stream)
+                      uint32_t *d_zero_hist, uint32_t *d_other_min, uint32_t *d_other_max, int64_t n_codons, cudaStream_t stream)
 {
     if (n_spans <= 0 || n_sample <= 0) return;
-    k_vote_refs<<<(unsigned)((n_spans + 1 + 7) / 8), 256, 0, stream>>>(d_aln, pitch, min(n_sample, 32), n_spans, d_cons, d_alt);
+    // d_zero_hist (or null): hist[n_codons][kHistBins] to clear, 16-byte aligned and with room for whole 16-byte vectors
+    // (up to 12 bytes past the last bin), together with other_min (all ones) and other_max (zero)
+    const int64_t words = d_zero_hist ? n_codons * kHistBins : 0;
+    k_vote_refs<<<(unsigned)((n_spans + 1 + 7) / 8), 256, 0, stream>>>(d_aln, pitch, min(n_sample, 32), n_spans, d_cons, d_alt,
+                                                                         reinterpret_cast<uint4 *>(d_zero_hist), (words + 3) / 4,
+                                                                         d_zero_hist ? d_other_min : nullptr, d_other_max, n_codons);
 }
 
 void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, const uint8_t *d_cons, uint32_t *d_alt,

@@ -58,7 +58,7 @@ void launch_hist(const uint8_t *d_codes, int64_t n_pad, int64_t n_codons, uint32
 // d_cons[column] (n_spans*16 + 4 bytes written) and d_alt[span][kAltWords].  Every row needs
 // n_spans*16 + 4 readable bytes.
 void launch_vote_refs(const uint8_t *d_aln, int64_t pitch, int n_sample, int64_t n_spans, uint8_t *d_cons, uint32_t *d_alt,
-                      cudaStream_t stream);
+                      uint32_t *d_zero_hist, uint32_t *d_other_min, uint32_t *d_other_max, int64_t n_codons, cudaStream_t stream);
 // d_alt[span][kAltWords]: words 0-4 the span's second reference pattern, words kAltSecond.. the third
 // (launch_vote_refs); word kAltCount of each the number of rows that equalled it (zeroed by launch_vote_refs,
 // raised by launch_fused_hist, spent by launch_fused_fixup).  d_sched: two zeroed u32 (chunk counter, finished
