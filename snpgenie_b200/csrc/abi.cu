@@ -83,6 +83,7 @@ struct snpg_ctx {
     int64_t n_tiles = 0;
     int fused_kernel = SNPG_FUSED_LDG_SPANS;
     int boot_kernel = SNPG_BOOT_WEIGHTS;
+    const Group *stats_of = nullptr;      // the group whose per-codon statistics sit in s_stats (written by its load; see finish_group)
     int n_sms = 148;
     int tma_l2_promotion = 2;             // CU_TENSOR_MAP_L2_PROMOTION_L2_128B (SNPG_TMA_L2PROMO overrides: 0..3)
     // groups
@@ -236,6 +237,7 @@ GroupView view_of(const snpg_ctx *ctx, const Group &g, int64_t c0) {
 
 int prepare_group(snpg_ctx *ctx, Group &g, uint64_t n_seqs) {
     g.loaded = false;
+    ctx->stats_of = nullptr;
     g.n = n_seqs;
     g.n_pad = (int64_t)((n_seqs + kRowPad - 1) / kRowPad) * kRowPad;
     const int64_t cnt = ctx->shard_count;
@@ -319,7 +321,18 @@ int finish_group(snpg_ctx *ctx, Group &g) {
         Launch l(ctx, SNPG_K_HIST);
         launch_hist(g.codes.as<uint8_t>(), g.n_pad, ctx->shard_count, g.hist.as<uint32_t>(), ctx->stream);
     } else {
-        {
+        // a whole job (snpg_within_job: the analysis follows the load at once) also takes the per-codon statistics here
+        const bool with_stats = ctx->defer_load_sync && ctx->n_irr == 0 && ctx->shard_count > 0 && !ctx->site_counts &&
+                                ctx->s_stats.ensure(sizeof(double) * 4 * (size_t)ctx->shard_count) == cudaSuccess;
+        ctx->stats_of = nullptr;
+        if (with_stats) {
+            Launch l(ctx, SNPG_K_OTHER);
+            StatsOut o{nullptr, nullptr, nullptr, nullptr, ctx->s_stats.as<double>(), nullptr};
+            launch_fused_fixup_stats(ctx->d_cons.as<uint8_t>(), ctx->col_lo - ctx->base_al, ctx->d_alt.as<uint32_t>(), ctx->d_map.as<CodonMap>(),
+                                     ctx->shard_count, (uint32_t)g.n, g.hist.as<uint32_t>(), omin, omax, view_of(ctx, g, 0),
+                                     ctx->d_tables.as<double>(), o, ctx->stream);
+            ctx->stats_of = &g;
+        } else {
             Launch l(ctx, SNPG_K_OTHER);
             launch_fused_fixup(ctx->d_cons.as<uint8_t>(), ctx->col_lo - ctx->base_al, ctx->d_alt.as<uint32_t>(), ctx->d_map.as<CodonMap>(), ctx->d_regular.as<uint8_t>(),
                                ctx->shard_count, (uint32_t)g.n, g.hist.as<uint32_t>(), omin, omax, ctx->stream);
@@ -899,6 +912,7 @@ static int run_stats(snpg_ctx *ctx, bool between, const Group &ga, const Group &
     CU(ctx, ctx->s_nda.ensure(sizeof(uint32_t) * (size_t)C));
     CU(ctx, ctx->s_ndb.ensure(sizeof(uint32_t) * (size_t)C));
     CU(ctx, ctx->s_cmp.ensure(sizeof(uint64_t) * (size_t)C));
+    ctx->stats_of = nullptr;
     CU(ctx, ctx->s_stats.ensure(sizeof(double) * 4 * (size_t)C));
     StatsOut o{ctx->s_poly.as<uint8_t>(), ctx->s_nda.as<uint32_t>(), ctx->s_ndb.as<uint32_t>(),
                ctx->s_cmp.as<unsigned long long>(), ctx->s_stats.as<double>(), ctx->s_cons.as<uint8_t>()};
@@ -1085,6 +1099,7 @@ int snpg_between_all(snpg_ctx *ctx, const int *groups, int n_groups, int64_t min
     const int64_t cnt = ctx->shard_count;
     const int n_pairs = n_groups * (n_groups - 1) / 2;
     const bool boot = pair_se && B >= 2;
+    ctx->stats_of = nullptr;
     CU(ctx, ctx->s_stats.ensure(sizeof(double) * 4 * (size_t)std::max<int64_t>(1, cnt)));
     CU(ctx, ctx->s_nda.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, cnt)));
     CU(ctx, ctx->s_ndb.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, cnt)));
@@ -1135,7 +1150,8 @@ static int within_all_impl(snpg_ctx *ctx, int group, int64_t B, double *prod_sum
     CU(ctx, ctx->s_stats.ensure(sizeof(double) * 4 * (size_t)std::max<int64_t>(1, cnt)));
     CU(ctx, ctx->s_sums.ensure(sizeof(double) * 4 * (size_t)P));
     StatsOut o{nullptr, nullptr, nullptr, nullptr, ctx->s_stats.as<double>(), nullptr};
-    { Launch l(ctx, SNPG_K_STATS); launch_within_stats(view_of(ctx, g, 0), cnt, ctx->d_tables.as<double>(), o, ctx->stream); }
+    if (ctx->stats_of != &g) { Launch l(ctx, SNPG_K_STATS); launch_within_stats(view_of(ctx, g, 0), cnt, ctx->d_tables.as<double>(), o, ctx->stream); }
+    ctx->stats_of = nullptr;         // (set by the load of a whole job: its fix-up kernel already wrote s_stats)
     const bool boot = prod_se && B >= 2;
     if (!boot) { Launch l(ctx, SNPG_K_SUMS); launch_product_sums(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), P, ctx->s_sums.as<double>(), ctx->stream); }
     if (boot) {
@@ -1250,7 +1266,7 @@ int snpg_within_job(snpg_ctx *ctx, int group, const uint8_t *bases, int bases_on
     int rc = bases_on_device ? snpg_load_group_device(ctx, group, bases, n_seqs, aln_len, row_stride)
                              : snpg_load_group(ctx, group, bases, n_seqs, aln_len, row_stride);
     ctx->defer_load_sync = false;
-    if (rc != SNPG_OK) { sync_stream(ctx); return rc; }
+    if (rc != SNPG_OK) { ctx->stats_of = nullptr; sync_stream(ctx); return rc; }
     rc = snpg_within_all(ctx, group, B, prod_sums, prod_se);
     if (eligible && rc == SNPG_OK) { J.candidate = key; J.candidate_epoch = g_alloc_epoch; }
     return rc;

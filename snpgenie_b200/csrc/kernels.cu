@@ -503,15 +503,11 @@ k_vote_refs(const uint8_t *__restrict__ aln, int64_t pitch, int n_sample, int64_
 // After all row blocks: credit the consensus codon of every regular codon with the rows that never reached
 // the decode path.  The consensus codon's code (and, for an 'other' codon, its character key) comes straight
 // from the consensus row and the codon index map.
-__global__ void __launch_bounds__(256)
-k_fused_fixup(const uint8_t *__restrict__ cons, int64_t cons_shift, const uint32_t *__restrict__ alt, const CodonMap *__restrict__ map,
-              const uint8_t *__restrict__ regular, int64_t n_codons, uint32_t n_rows,
-              uint32_t *__restrict__ hist, uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max)
+__device__ __forceinline__ void fixup_codon(const uint8_t *__restrict__ cons, int64_t cons_shift, const uint32_t *__restrict__ alt,
+                                            const CodonMap *__restrict__ map, int64_t c, uint32_t n_rows, uint32_t *__restrict__ hist,
+                                            uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max, int lane)
 {
     // one warp per codon: the 66 bins are summed across lanes
-    const int lane = threadIdx.x & 31;
-    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (c >= n_codons || !regular[c]) return;
     uint32_t *h = hist + c * kHistBins;
     const CodonMap m = map[c];
     auto credit = [&](uint8_t r0, uint8_t r1, uint8_t r2, uint32_t rows) {     // lane 0: rows copies of the codon r0 r1 r2
@@ -545,6 +541,17 @@ k_fused_fixup(const uint8_t *__restrict__ cons, int64_t cons_shift, const uint32
     const uint32_t seen = warp_sum_u32(h[lane] + h[lane + 32] + (lane < kHistBins - 64 ? h[lane + 64] : 0u));
     const uint32_t rest = n_rows - seen;       // rows that equalled the consensus codon and were never recorded
     if (rest && lane == 0) credit(c0, c1, c2, rest);
+}
+
+__global__ void __launch_bounds__(256)
+k_fused_fixup(const uint8_t *__restrict__ cons, int64_t cons_shift, const uint32_t *__restrict__ alt, const CodonMap *__restrict__ map,
+              const uint8_t *__restrict__ regular, int64_t n_codons, uint32_t n_rows,
+              uint32_t *__restrict__ hist, uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (c >= n_codons || !regular[c]) return;
+    fixup_codon(cons, cons_shift, alt, map, c, n_rows, hist, other_min, other_max, lane);
 }
 
 // irregular codons (split across CDS segments, or beyond the run capacity of a span) go
@@ -664,16 +671,12 @@ __device__ __forceinline__ int first_defined_code(const uint8_t *col, int64_t n,
     return kCodeUndef;
 }
 
+// One codon, one warp.  s_bin/s_ca/s_cb: kStatsWarps x 64 entries of shared scratch, row `warp` is this warp's.
 template <bool BETWEEN>
-__global__ void __launch_bounds__(kStatsWarps * 32)
-k_stats(GroupView A, GroupView B, int64_t n_codons, const double *__restrict__ tables, StatsOut out)
+__device__ __forceinline__ void stats_codon(const GroupView &A, const GroupView &B, int64_t c, const double *__restrict__ tables,
+                                            const StatsOut &out, int lane, int warp, int (*s_bin)[64], double (*s_ca)[64],
+                                            double (*s_cb)[64])
 {
-    __shared__ int s_bin[kStatsWarps][64];
-    __shared__ double s_ca[kStatsWarps][64];
-    __shared__ double s_cb[kStatsWarps][64];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t c = (int64_t)blockIdx.x * kStatsWarps + warp;
-    if (c >= n_codons) return;
 
     const double *sites = tables;            // [64][2]
     const double *TN = tables + 128;         // [64][64]
@@ -792,6 +795,38 @@ k_stats(GroupView A, GroupView B, int64_t n_codons, const double *__restrict__ t
             o[1] = make_double2(r_nd, r_sd);
         }
     }
+}
+
+template <bool BETWEEN>
+__global__ void __launch_bounds__(kStatsWarps * 32)
+k_stats(GroupView A, GroupView B, int64_t n_codons, const double *__restrict__ tables, StatsOut out)
+{
+    __shared__ int s_bin[kStatsWarps][64];
+    __shared__ double s_ca[kStatsWarps][64];
+    __shared__ double s_cb[kStatsWarps][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t c = (int64_t)blockIdx.x * kStatsWarps + warp;
+    if (c >= n_codons) return;
+    stats_codon<BETWEEN>(A, B, c, tables, out, lane, warp, s_bin, s_ca, s_cb);
+}
+
+// k_fused_fixup followed, codon by codon, by the within-group statistics (K3): one launch less for a whole job
+// (snpg_within_job), the same arithmetic as the two kernels.  Only when every codon is regular.
+__global__ void __launch_bounds__(kStatsWarps * 32)
+k_fused_fixup_stats(const uint8_t *__restrict__ cons, int64_t cons_shift, const uint32_t *__restrict__ alt, const CodonMap *__restrict__ map,
+                    int64_t n_codons, uint32_t n_rows, uint32_t *__restrict__ hist, uint32_t *__restrict__ other_min,
+                    uint32_t *__restrict__ other_max, GroupView A, const double *__restrict__ tables, StatsOut out)
+{
+    static_assert(kStatsWarps * 32 == 256, "the fix-up addresses codons by 256-thread blocks");
+    __shared__ int s_bin[kStatsWarps][64];
+    __shared__ double s_ca[kStatsWarps][64];
+    __shared__ double s_cb[kStatsWarps][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t c = (int64_t)blockIdx.x * kStatsWarps + warp;
+    if (c >= n_codons) return;
+    fixup_codon(cons, cons_shift, alt, map, c, n_rows, hist, other_min, other_max, lane);
+    __syncwarp();                                  // lane 0's credits are visible to the warp
+    stats_codon<false>(A, A, c, tables, out, lane, warp, s_bin, s_ca, s_cb);
 }
 
 // min-taxa codon filters of the between-group processor (bgp:412-467, :929-970): a codon that fails them
@@ -1340,6 +1375,15 @@ void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, cons
             d_sched, (uint32_t)n_sb, n_sb == 1 ? 0xFFFFFFFFu : (uint32_t)(((uint64_t)1 << 32) / (uint64_t)n_sb), (uint32_t)chunk_a,
             (uint32_t)rows_a, (uint32_t)k_a, (uint32_t)(k_a + k_b));
     }
+}
+
+void launch_fused_fixup_stats(const uint8_t *d_cons, int64_t cons_shift, const uint32_t *d_alt, const CodonMap *d_map, int64_t n_codons,
+                              uint32_t n_rows, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max, GroupView A,
+                              const double *d_tables, StatsOut out, cudaStream_t stream)
+{
+    if (n_codons <= 0) return;
+    k_fused_fixup_stats<<<(unsigned)((n_codons + kStatsWarps - 1) / kStatsWarps), kStatsWarps * 32, 0, stream>>>(
+        d_cons, cons_shift, d_alt, d_map, n_codons, n_rows, d_hist, d_other_min, d_other_max, A, d_tables, out);
 }
 
 void launch_fused_fixup(const uint8_t *d_cons, int64_t cons_shift, const uint32_t *d_alt, const CodonMap *d_map, const uint8_t *d_regular,

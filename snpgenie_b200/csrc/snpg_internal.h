@@ -103,6 +103,10 @@ struct StatsOut {
     double *stats4; uint8_t *conserved;
 };
 void launch_within_stats(GroupView A, int64_t n_codons, const double *d_tables, StatsOut out, cudaStream_t stream);
+// launch_fused_fixup (every codon regular) and launch_within_stats in one kernel, codon by codon: same arithmetic.
+void launch_fused_fixup_stats(const uint8_t *d_cons, int64_t cons_shift, const uint32_t *d_alt, const CodonMap *d_map, int64_t n_codons,
+                              uint32_t n_rows, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max, GroupView A,
+                              const double *d_tables, StatsOut out, cudaStream_t stream);
 void launch_between_stats(GroupView A, GroupView B, int64_t n_codons, const double *d_tables, StatsOut out,
                           cudaStream_t stream);
 
