@@ -30,7 +30,6 @@ with Engine(device=0) as eng:
     eng.set_option(_abi.OPT_KEEP_CODES, 1 if a.route == "codes" else 0)
     eng.set_option(_abi.OPT_FUSED_KERNEL, _abi.FUSED_TMA_TILES if a.route == "tiles" else _abi.FUSED_LDG_SPANS)
     eng.set_products(products, L)
-    for _ in range(a.steps):
-        eng.load_group_ptr(0, d.data_ptr(), a.n, L, pitch, device=True)
-        sums, se = eng.within_all(0, B=a.boot)
+    for _ in range(a.steps):       # the whole-job call bench.py times (run with SNPG_NO_GRAPH=1 for plain launches)
+        sums, se = eng.within_job(0, d.data_ptr(), a.n, L, pitch, True, B=a.boot)
     print("ok", sums[0], se[0][:3], "tile launches", eng.tile_launches)

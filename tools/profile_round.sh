@@ -15,6 +15,6 @@ print('p_poly $p step_ms %.4f GB/s %.0f %.3f' % (d['ms_per_step'], r['achieved']
 python tools/bench_config4.py > $O/${R}_config4.json 2> $O/config4.err
 python bench.py --steps 2 --warmup 3 --no-cpu > /dev/null 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $O/${R}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > $O/ncu_launches.log 2>&1
-python tools/prof_step.py --steps 2 > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k 'regex:k_fused_hist|k_bootstrap|k_vote_refs|k_fused_fixup|k_stats|k_moments' --launch-skip 6 -c 6 -f -o $O/${R}_full python tools/prof_step.py --steps 2 > $O/ncu_full.log 2>&1
+SNPG_NO_GRAPH=1 python tools/prof_step.py --steps 2 > /dev/null 2>&1 && \
+SNPG_NO_GRAPH=1 ncu --set full --clock-control none --import-source on -k 'regex:k_fused_hist|k_bootstrap|k_vote_refs|k_fused_fixup|k_stats|k_moments' --launch-skip 5 -c 5 -f -o $O/${R}_full python tools/prof_step.py --steps 2 > $O/ncu_full.log 2>&1
 ls -la $O
