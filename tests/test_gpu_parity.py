@@ -779,6 +779,34 @@ def test_more_than_2_20_rows(route):
         assert e.group_size(1) == n
 
 
+@pytest.mark.parametrize("annotation", ["sars2", "hiv"])
+def test_within_job_matches_call_by_call(annotation):
+    """snpg_within_job folds the per-codon statistics into the fix-up kernel when every codon is regular (sars2) and
+    keeps the two kernels otherwise (hiv: a codon split over two CDS segments): either way the product sums are those
+    of load + within_all bit for bit, from a host buffer and from a device buffer."""
+    import torch
+    from snpgenie_b200.engine import Engine
+    products, L = (synth.sars2_products(), 29903) if annotation == "sars2" else (synth.hiv_products(), 9719)
+    n = 333
+    aln = synth.make_alignment(n, L, products, 17, gap_frac=0.02, n_frac=0.01, iupac_frac=0.005)
+    pitch = (L + 127) // 128 * 128
+    d = torch.zeros((n, pitch), dtype=torch.uint8, device="cuda:0")
+    d[:, :L] = torch.from_numpy(aln).cuda()
+    with Engine(device=0) as e:
+        e.set_products(products, L)
+        e.load_group(1, aln)
+        plain, _ = e.within_all(1, B=0)
+        per_codon = [e.within(1, i)["stats4"] for i in range(len(products))]
+        for _ in range(3):                         # plain call, then captured and replayed
+            sums, se = e.within_job(0, d.data_ptr(), n, L, pitch, True, B=200)
+            assert np.array_equal(sums, plain) and np.all(np.isfinite(se[:, :3]))
+        sums, _ = e.within_job(2, aln.ctypes.data, n, L, L, False, B=50)
+        assert np.array_equal(sums, plain)
+        for i in range(len(products)):             # the call-by-call statistics of the job's group agree too
+            assert np.array_equal(e.within(0, i)["stats4"], per_codon[i])
+            assert (e.hist(0, i)[0] == e.hist(1, i)[0]).all()
+
+
 def test_within_job_graph_replay_matches_plain_calls():
     """snpg_within_job on a device-resident alignment is replayed as a CUDA graph from the second identical call:
     same kernels, so the product sums are bit-identical and the SEs (a fresh Philox stream per call) agree
