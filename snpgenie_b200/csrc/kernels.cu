@@ -1130,7 +1130,8 @@ k_bootstrap_mma(const double *__restrict__ stats4, const int64_t *__restrict__ o
             const uint64_t b = (uint64_t)(b_first + bl);
             auto bump = [&](uint32_t u) {          // one draw: slot = floor(u * (C+1) / 2^32); its byte of the row goes up by one
                 const uint32_t r = __umulhi(u, C + 1);
-                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(mine_s + (r & ~3u)), "r"(1u << ((r << 3) & 24u)) : "memory");
+                // 1 << 8 * (r & 3): a funnel shift takes its count modulo 32, so r << 3 needs no mask
+                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(mine_s + (r & ~3u)), "r"(__funnelshift_l(0u, 1u, r << 3)) : "memory");
             };
             uint32_t q = sl;
             for (; q < full_quads; q += lanes_per) {
