@@ -1156,14 +1156,16 @@ k_bootstrap_mma(const double *__restrict__ stats4, const int64_t *__restrict__ o
             const uint32_t row = gq * 8 + (lane >> 2);
             const uint32_t *cnt_row = s_cnt + (size_t)row * rw;      // A: row = replicate lane/4
             const uint32_t col = lane & 3;                           //    column = slot 4t + lane%4
-            const uint32_t stat = lane >> 2;                         // B: column = statistic lane/4 (0 beyond 3)
+            const uint32_t stat = lane >> 2;                         // B: column lane/4 = statistic (columns 4-7: padding)
             const uint32_t sel = 0x4440u + col;                      // byte col of a word, zero-extended
-            const double *gb = G + 4 * (int64_t)col - 4 + stat;      // + 16 t: stats4[slot 4t + col][stat]
+            // + 16 t: stats4[slot 4t + col][stat].  Columns 4-7 of B only feed columns 4-7 of D, which nobody reads: their
+            // lanes load the same (finite) table entries as columns 0-3 instead of a predicated zero
+            const double *gb = G + 4 * (int64_t)col - 4 + (stat & 3);
             double acc0 = 0.0, acc1 = 0.0;
             auto tile = [&](uint32_t t, bool guard) {
                 const double a = (double)__byte_perm(cnt_row[t], 0u, sel);
                 double bv = 0.0;
-                if (stat < 4 && (!guard || (4 * t + col >= 1 && 4 * t + col <= C))) bv = __ldg(gb + 16 * (size_t)t);
+                if (!guard || (4 * t + col >= 1 && 4 * t + col <= C)) bv = __ldg(gb + 16 * (size_t)t);
                 dmma_m8n8k4(acc0, acc1, a, bv);
             };
             uint32_t t = t0;
