@@ -543,6 +543,57 @@ __device__ __forceinline__ void fixup_codon(const uint8_t *__restrict__ cons, in
     if (rest && lane == 0) credit(c0, c1, c2, rest);
 }
 
+// The same fix-up with every load issued up front and the credits applied to the warp's register copy of the bins
+// (lane l holds bins l and l + 32, lanes 0 and 1 also bins 64 and 65): one chain of dependent loads instead of four.
+// bins[0..2] on return: this lane's bins l, l + 32 and the 'other' bin, as k_stats wants them.
+__device__ __forceinline__ void fixup_codon_regs(const uint8_t *__restrict__ cons, int64_t cons_shift, const uint32_t *__restrict__ alt,
+                                                 const CodonMap *__restrict__ map, int64_t c, uint32_t n_rows,
+                                                 uint32_t *__restrict__ hist, uint32_t *__restrict__ other_min,
+                                                 uint32_t *__restrict__ other_max, int lane, uint32_t *bins)
+{
+    uint32_t *h = hist + c * kHistBins;
+    const CodonMap m = map[c];
+    const int64_t q0 = m.p0 + cons_shift, q1 = m.p1 + cons_shift, q2 = m.p2 + cons_shift;     // columns relative to the first span
+    const int64_t sp = min(q0, q2) >> 4;
+    const uint32_t *ap = alt + sp * kAltWords;
+    const uint8_t *ab1 = reinterpret_cast<const uint8_t *>(ap) - sp * 16, *ab2 = reinterpret_cast<const uint8_t *>(ap + kAltSecond) - sp * 16;
+    uint32_t h0 = h[lane], h1 = h[lane + 32], h2 = lane < kHistBins - 64 ? h[lane + 64] : 0u;
+    const uint8_t c0 = cons[q0], c1 = cons[q1], c2 = cons[q2];
+    const uint32_t n1 = ap[kAltCount], n2 = ap[kAltSecond + kAltCount];
+    const uint8_t x0 = ab1[q0], x1 = ab1[q1], x2 = ab1[q2], y0 = ab2[q0], y1 = ab2[q1], y2 = ab2[q2];
+    uint32_t omin = 0xFFFFFFFFu, omax = 0;         // keys of 'other' codons credited here
+    bool any_other = false;
+    auto credit = [&](uint8_t r0, uint8_t r1, uint8_t r2, uint32_t rows) {     // every lane: rows copies of the codon r0 r1 r2
+        const uint8_t k0n = norm_char(r0, m.minus), k1n = norm_char(r1, m.minus), k2n = norm_char(r2, m.minus);
+        const uint8_t k0 = class_of(k0n), k1 = class_of(k1n), k2 = class_of(k2n);
+        uint32_t code;
+        if (max(k0, max(k1, k2)) < 4) code = k0 * 16 + k1 * 4 + k2;
+        else if (k0 == 4 || k1 == 4 || k2 == 4) code = kCodeUndef;
+        else code = kCodeOther;
+        if (code == (uint32_t)lane) { h0 += rows; h[code] = h0; }
+        if (code == (uint32_t)lane + 32) { h1 += rows; h[code] = h1; }
+        if (code == (uint32_t)lane + 64) { h2 += rows; h[code] = h2; }
+        if (code == kCodeOther) {
+            const uint32_t key = ((uint32_t)k0n << 16) | ((uint32_t)k1n << 8) | k2n;
+            omin = min(omin, key);
+            omax = max(omax, key);
+            any_other = true;
+        }
+    };
+    if (n1 && (x0 != c0 || x1 != c1 || x2 != c2)) credit(x0, x1, x2, n1);
+    if (n2 && (y0 != c0 || y1 != c1 || y2 != c2)) credit(y0, y1, y2, n2);
+    const uint32_t seen = warp_sum_u32(h0 + h1 + h2);
+    const uint32_t rest = n_rows - seen;           // rows that equalled the consensus codon and were never recorded
+    if (rest) credit(c0, c1, c2, rest);
+    if (any_other && lane == 0) {
+        other_min[c] = min(other_min[c], omin);
+        other_max[c] = max(other_max[c], omax);
+    }
+    bins[0] = h0;
+    bins[1] = h1;
+    bins[2] = __shfl_sync(kFull, h2, kCodeOther - 64);
+}
+
 __global__ void __launch_bounds__(256)
 k_fused_fixup(const uint8_t *__restrict__ cons, int64_t cons_shift, const uint32_t *__restrict__ alt, const CodonMap *__restrict__ map,
               const uint8_t *__restrict__ regular, int64_t n_codons, uint32_t n_rows,
@@ -675,15 +726,19 @@ __device__ __forceinline__ int first_defined_code(const uint8_t *col, int64_t n,
 template <bool BETWEEN>
 __device__ __forceinline__ void stats_codon(const GroupView &A, const GroupView &B, int64_t c, const double *__restrict__ tables,
                                             const StatsOut &out, int lane, int warp, int (*s_bin)[64], double (*s_ca)[64],
-                                            double (*s_cb)[64])
+                                            double (*s_cb)[64], const uint32_t *bins = nullptr)
 {
 
     const double *sites = tables;            // [64][2]
     const double *TN = tables + 128;         // [64][64]
     const double *TS = tables + 128 + 4096;
 
-    const uint32_t *ha = A.hist + c * kHistBins;
-    const uint32_t a0 = ha[lane], a1 = ha[lane + 32], ao = ha[kCodeOther];
+    uint32_t a0, a1, ao;
+    if (bins) { a0 = bins[0]; a1 = bins[1]; ao = bins[2]; }            // the caller holds them (k_fused_fixup_stats)
+    else {
+        const uint32_t *ha = A.hist + c * kHistBins;
+        a0 = ha[lane]; a1 = ha[lane + 32]; ao = ha[kCodeOther];
+    }
     uint32_t b0 = a0, b1 = a1, bo = ao;
     if (BETWEEN) {
         const uint32_t *hb = B.hist + c * kHistBins;
@@ -824,9 +879,10 @@ k_fused_fixup_stats(const uint8_t *__restrict__ cons, int64_t cons_shift, const 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t c = (int64_t)blockIdx.x * kStatsWarps + warp;
     if (c >= n_codons) return;
-    fixup_codon(cons, cons_shift, alt, map, c, n_rows, hist, other_min, other_max, lane);
-    __syncwarp();                                  // lane 0's credits are visible to the warp
-    stats_codon<false>(A, A, c, tables, out, lane, warp, s_bin, s_ca, s_cb);
+    uint32_t bins[3];
+    fixup_codon_regs(cons, cons_shift, alt, map, c, n_rows, hist, other_min, other_max, lane, bins);
+    __syncwarp();                                  // lane 0's 'other' keys are visible to the warp
+    stats_codon<false>(A, A, c, tables, out, lane, warp, s_bin, s_ca, s_cb, bins);
 }
 
 // min-taxa codon filters of the between-group processor (bgp:412-467, :929-970): a codon that fails them
