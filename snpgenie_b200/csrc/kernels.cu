@@ -1106,15 +1106,17 @@ k_bootstrap(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, 
 // (each of the C draws picks the slot with probability 1/(C+1)).
 constexpr int kBootKSplit = 8;                     // warps sharing the slots of one group of 8 replicates (one row per warp)
 constexpr int kBootMaxRows = 8;                    // replicates a warp takes at a time when the product is short
-// Two blocks of kMmaWarps warps share an SM: while one contracts (FP64 tensor pipe) the other samples (integer pipes).
-constexpr int kMmaWarps = 16;
+// Several blocks of kMmaWarps warps share an SM (five for config 2's largest product, at 48 registers a thread): while
+// some contract (FP64 tensor pipe) the others sample (integer pipes).  Measured: 32 warps x 1 block 178 us, 16 x 2 159,
+// 8 x 4 (64 registers) 158, 8 x 5 (48 registers, spills only in the prologue) 151 -> 146.
+constexpr int kMmaWarps = 8;
 static_assert(kMmaWarps % kBootKSplit == 0, "a batch is kMmaWarps / 8 groups of 8 replicates, each contracted by 8 warps");
 
 __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(kMmaWarps * 32, 32 / kMmaWarps)
+__global__ void __launch_bounds__(kMmaWarps * 32, 5)
 k_bootstrap_mma(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, const int *__restrict__ order, int n_products,
                 int64_t b_first, int64_t b_count, uint2 key, uint32_t stream_id, const uint32_t *__restrict__ salt,
                 double *__restrict__ rep, double *__restrict__ vals, double *__restrict__ prod_sums, uint32_t row_words)
