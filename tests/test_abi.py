@@ -27,6 +27,20 @@ def test_every_declared_symbol_is_exported_and_bound():
     assert decl == set(_abi.SIGNATURES), (decl ^ set(_abi.SIGNATURES))
 
 
+def test_python_constants_follow_the_header():
+    """Option numbers and values in the ctypes mirror are the header's #defines."""
+    from snpgenie_b200 import _abi
+    text = open(os.path.join(ROOT, "include", "snpgenie_cuda.h")).read()
+    defs = {k: int(v, 0) for k, v in re.findall(r"^#define\s+(SNPG_[A-Z0-9_]+)\s+(-?(?:0x)?[0-9A-Fa-f]+)\s*$", text, flags=re.M)}
+    pairs = {"SNPG_OPT_KEEP_CODES": _abi.OPT_KEEP_CODES, "SNPG_OPT_PROFILE": _abi.OPT_PROFILE, "SNPG_OPT_SITE_COUNTS": _abi.OPT_SITE_COUNTS,
+             "SNPG_OPT_FUSED_KERNEL": _abi.OPT_FUSED_KERNEL, "SNPG_OPT_BOOTSTRAP_KERNEL": _abi.OPT_BOOTSTRAP_KERNEL,
+             "SNPG_FUSED_TMA_TILES": _abi.FUSED_TMA_TILES, "SNPG_FUSED_LDG_SPANS": _abi.FUSED_LDG_SPANS,
+             "SNPG_BOOT_GATHER": _abi.BOOT_GATHER, "SNPG_BOOT_WEIGHTS": _abi.BOOT_WEIGHTS}
+    for name, value in pairs.items():
+        assert defs[name] == value, name
+    assert len({defs[k] for k in defs if k.startswith("SNPG_OPT_")}) == len([k for k in defs if k.startswith("SNPG_OPT_")])
+
+
 def test_host_only_entry_points_work_without_a_gpu():
     from oracle import oracle as orc
     from snpgenie_b200 import _abi, engine
