@@ -135,7 +135,7 @@ def run_reference(args):
     if rank != 0:
         return
     steps = max(1, args.steps)
-    per_step = max(2.0, min(20.0, 120.0 / (steps + args.warmup)))
+    per_step = max(1.0, min(20.0, 90.0 / (steps + args.warmup)))     # the whole run ends within a few minutes
     vals = []
     sample = ""
     threads = 1
