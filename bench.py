@@ -3,25 +3,26 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload at N=1: BASELINE config 2 -- SARS-CoV-2-shaped within-group analysis,
-10,000 sequences x 29,903 nt, 10 CDS (9,677 codons), 10,000 bootstrap replicates
-per product.  One "step" is one pass of the whole hot path over that alignment:
-codon packing -> per-codon histograms -> Nei-Gojobori per-codon statistics ->
-product sums -> whole-product bootstraps -> SE moments.
+Workload: BASELINE config 2 -- SARS-CoV-2-shaped within-group analysis, 10,000 sequences x 29,903 nt, 10 CDS
+(9,677 codons), 10,000 bootstrap replicates per product.  One "step" is one pass of the whole hot path over that
+alignment through ONE C-ABI call (snpg_within_job_ex): codon histograms -> Nei-Gojobori per-codon statistics ->
+product sums -> whole-product bootstraps -> SE moments, with the per-codon table (poly, n_defined, comparisons,
+N/S sites and differences, conserved codon) and the product table read back into pinned host memory.
 
-  value  nominal codon-pair comparisons per second (the reference's loop trip
-         count, sum over products of C_p * C(n,2)) with the
-         alignment already resident in HBM.
-  e2e    the same metric through the host-buffer C-ABI call (snpg_load_group from
-         pinned host memory + snpg_within_all + result read-back).
-At N>1 (torchrun, one rank per GPU): weak scaling by codon range -- every rank
-owns one genome-shaped codon range (its own 10 CDS of the same 10,000 sequences),
-no data-path collective; the per-product results are gathered once over NCCL.
+  value  nominal codon-pair comparisons per second (the reference's loop trip count, sum over products of
+         C_p * C(n,2)) with the alignment already resident in HBM.
+  e2e    the same metric with the alignment in (pinned) HOST memory: the call stages the CDS columns over PCIe.
 
---impl reference times the CPU restatement of the reference's own algorithm
-(oracle/ng_oracle.c: the literal O(n^2) pair loop, all host threads) on a bounded
-sample of the same workload.  The reference itself is Perl, cannot travel to the
-GPU box and has nothing to compile, so kind = "port" (see DESIGN.md).
+At N > 1 (torchrun, one rank per GPU) the SAME alignment is split N ways -- strong scaling: rank r owns the r-th
+N-th of the codon axis (it stages and reads only those columns) and the r-th N-th of every product's bootstrap
+replicates.  The exchange is inside the step and inside the library: the kernels that produce the per-codon
+statistics and the per-replicate values store them into every rank's HBM over NVLink (CUDA IPC peer mappings) and
+flag their arrival; no host round trip, no separate collective launch.  Every rank ends the step with the full
+result, bit-identical to the single-GPU result (checked before the timed region, on every N).
+
+--impl reference times the CPU restatement of the reference's own algorithm (oracle/ng_oracle.c: the literal O(n^2)
+pair loop, all host threads) on a bounded sample of the same workload.  The reference itself is Perl, cannot travel
+to the GPU box and has nothing to compile, so kind = "port" (see DESIGN.md).
 """
 from __future__ import annotations
 
@@ -147,25 +148,24 @@ def run_reference(args):
     ms = 1e3 * nominal_pairs(N_SEQS, 9677) / value
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "ms_per_step is the full config-2 step extrapolated from the sampled pair rate",
+        "note": "ms_per_step is the full config-2 step EXTRAPOLATED from the sampled pair rate (only the rate is measured)",
     }))
 
 
 def workload_config(n_gpus):
     return {"workload": "config2: SARS-CoV-2-shaped within-group, 10000 seqs x 29903 nt, 10 CDS (9677 codons), 10000 bootstraps"
-                        + ("" if n_gpus == 1 else f"; x{n_gpus} genome-shaped codon ranges, one per GPU"),
-            "n_seqs": N_SEQS, "aln_len": ALN_LEN, "codons_per_gpu": 9677, "bootstraps": N_BOOT,
+                        + ("" if n_gpus == 1 else f"; ONE alignment, codon axis and bootstrap replicates split over {n_gpus} GPUs"),
+            "n_seqs": N_SEQS, "aln_len": ALN_LEN, "codons": 9677, "bootstraps": N_BOOT,
             "l2": "inputs larger than L2 (299 MB alignment per step, re-read every step)"}
 
 
 def bind_near_gpu(local):
     """Pin this rank to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host memory is allocated
-    (first touch then places the e2e input next to the GPU's PCIe root).  With 8 ranks on one box and no binding
-    half of them copy across the socket interconnect.  Returns (node, n_cpus) or None."""
+    (first touch then places the e2e input next to the GPU's PCIe root).  Returns (node, n_cpus) or None."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -190,6 +190,37 @@ def bind_near_gpu(local):
 
 # ------------------------------------------------------------------ GPU arm
 
+class Timer:
+    """K steps bracketed by barrier + synchronize on both sides, CUDA events on the engine's stream, max over ranks."""
+
+    def __init__(self, torch, dist, stream, world, dev):
+        self.torch, self.dist, self.stream, self.world, self.dev = torch, dist, stream, world, dev
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def run(self, fn, steps, warmup):
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for _ in range(steps):
+            out = fn()
+        e1.record(self.stream)
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        mine = ms / steps
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, mine, out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -211,10 +242,12 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
+    stream = torch.cuda.Stream(device=dev)          # the library launches on this stream; the timing events are recorded on it
+    timer = Timer(torch, dist, stream, world, dev)
 
     products = synth.sars2_products()
     codons = sum(p.n_codons for p in products)
-    aln = synth.make_alignment(N_SEQS, ALN_LEN, products, SEED + 1000 * rank, p_poly=args.p_poly)
+    aln = synth.make_alignment(N_SEQS, ALN_LEN, products, SEED, p_poly=args.p_poly)      # the same alignment on every rank
     pitch = (ALN_LEN + 127) // 128 * 128
     # pinned host copy (e2e input) and HBM-resident copy with a 128-B row pitch (value input)
     h_aln = torch.empty((N_SEQS, ALN_LEN), dtype=torch.uint8).pin_memory()
@@ -223,74 +256,112 @@ def run_ours(args):
     d_aln[:, :ALN_LEN] = h_aln.to(dev)
     torch.cuda.synchronize()
 
-    eng = Engine(device=local, seed=SEED)
-    stream = torch.cuda.current_stream()
-    eng.set_stream(stream.cuda_stream)
+    def make_engine(r, w):
+        e = Engine(device=local, seed=SEED, rank=r, world=w)
+        e.set_stream(stream.cuda_stream)
+        e.set_option(_abi.OPT_KEEP_CODES, 1 if args.route == "codes" else 0)
+        e.set_option(_abi.OPT_FUSED_KERNEL, _abi.FUSED_TMA_TILES if args.route == "tiles" else _abi.FUSED_LDG_SPANS)
+        e.set_products(products, ALN_LEN)
+        return e
+
+    eng = make_engine(rank, world)
+    exchange = None
+    if world > 1:
+        eng.connect_ranks(N_BOOT)
+        exchange = "peer memory over NVLink (CUDA IPC): kernels store into every rank's HBM, flags signal arrival"
+
+    def step_resident():
+        return eng.job(0, d_aln.data_ptr(), N_SEQS, ALN_LEN, pitch, device=True, B=N_BOOT)
+
+    def step_e2e():
+        return eng.job(0, h_aln.data_ptr(), N_SEQS, ALN_LEN, ALN_LEN, device=False, B=N_BOOT)
+
+    # ---- correctness of what is about to be timed (outside the timed region) --------------------------------
+    check = {}
+    first = {k: np.array(v, copy=True) for k, v in step_resident().items()}
+    if world > 1:
+        # the same job, unsharded, on this rank's own GPU: a fresh engine's first job draws the same replicates
+        with make_engine(0, 1) as solo:
+            ref = {k: np.array(v, copy=True) for k, v in solo.job(0, d_aln.data_ptr(), N_SEQS, ALN_LEN, pitch, device=True, B=N_BOOT).items()}
+        same = all(np.array_equal(first[k], ref[k]) for k in ref)
+        flag = torch.tensor([1 if same else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        check["sharded_equals_unsharded_bitwise_on_every_rank"] = bool(flag.item())
+        if not flag.item():
+            raise SystemExit(f"[rank {rank}] sharded result differs from the unsharded run: " + ", ".join(k for k in ref if not np.array_equal(first[k], ref[k])))
+    if rank == 0 and not args.no_cpu:
+        # CHECKER ONLY: per-codon closed form of the oracle on host-built histograms of the same alignment
+        from oracle import oracle as orc
+        sites, diffs = orc.tables()
+        ofs = np.cumsum([0] + [p.n_codons for p in products])
+        worst = 0.0
+        for i, p in enumerate(products):
+            pos = orc.product_positions(p.starts, p.stops, p.strand, ALN_LEN)
+            _, codes = orc.extract(aln, pos, p.strand)
+            want = orc.within_hist(orc.hist(codes), None, sites, diffs)
+            got = first["stats4"][ofs[i]:ofs[i + 1]]
+            for q, k in enumerate(("N_sites", "S_sites", "N_diffs", "S_diffs")):
+                err = np.max(np.abs(got[:, q] - want[k]) / np.maximum(np.abs(want[k]), 1e-300) * (want[k] != 0) + np.abs(got[:, q]) * (want[k] == 0))
+                worst = max(worst, float(err))
+                assert np.allclose(first["prod_sums"][i, q], want[k].sum(), rtol=1e-12), (p.name, k)
+            assert np.array_equal(first["poly"][ofs[i]:ofs[i + 1]], want["poly"]) and np.array_equal(first["n_defined"][ofs[i]:ofs[i + 1]], want["n_defined"])
+        assert worst < 1e-12, worst
+        check["vs_oracle"] = {"codons_checked": int(codons), "max_rel_err_per_codon": worst, "tolerance": 1e-12,
+                              "poly_and_n_defined": "identical", "se_dN_minus_dS_product0": float(first["prod_se"][0, 2])}
+    assert np.all(first["prod_se"][:, :3] > 0), "bootstrap SEs must be positive on this workload"
+
+    # ---- timed regions ----------------------------------------------------------------------------------------
     # timed passes bracket only the dominant HBM kernel with events (a pair costs ~3 us of stream time);
     # a separate untimed pass of the same steps brackets every launch for the per-kernel table
     hbm_kinds = ["fused"] if args.route in ("fused", "tiles") else ["pack", "hist"]
     narrow = sum(1 << _abi.KERNEL_KINDS.index(k) for k in hbm_kinds)
     eng.set_option(_abi.OPT_PROFILE, 0 if args.no_profile else narrow)
-    eng.set_option(_abi.OPT_KEEP_CODES, 1 if args.route == "codes" else 0)
-    eng.set_option(_abi.OPT_FUSED_KERNEL, _abi.FUSED_TMA_TILES if args.route == "tiles" else _abi.FUSED_LDG_SPANS)
-    eng.set_products(products, ALN_LEN)
-
-    def step_resident():
-        return eng.within_job(0, d_aln.data_ptr(), N_SEQS, ALN_LEN, pitch, True, B=N_BOOT)
-
-    def step_e2e():
-        return eng.within_job(0, h_aln.data_ptr(), N_SEQS, ALN_LEN, ALN_LEN, False, B=N_BOOT)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
+    with ClockSampler(local) as clocks:      # clocks are sampled across both timed regions
+        for _ in range(args.warmup):
+            step_resident()
         eng.profile(reset=True)
         l0 = eng.launches
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(steps):
-            out = fn()
-        e1.record(stream)
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            print(f"[rank {rank}] {fn.__name__}: {ms / steps:.4f} ms/step", file=sys.stderr)
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms / steps, eng.profile(reset=True), eng.launches - l0, out
-
-    with ClockSampler(local) as clocks:      # clocks are sampled across both timed regions
-        ms_res, prof, launches, (sums, se) = timed(step_resident, args.steps, args.warmup)
-        ms_e2e, prof_e2e, _, _ = timed(step_e2e, max(1, args.steps), max(3, min(args.warmup, 3)))
+        ms_res, ms_res_mine, _ = timer.run(step_resident, args.steps, 0)
+        prof = eng.profile(reset=True)
+        launches = eng.launches - l0
+        ms_e2e, ms_e2e_mine, _ = timer.run(step_e2e, max(1, args.steps), max(3, min(args.warmup, 3)))
+    if world > 1:
+        print(f"[rank {rank}] resident {ms_res_mine:.4f} ms/step, e2e {ms_e2e_mine:.4f} ms/step", file=sys.stderr)
     prof_all = {}
     if not args.no_profile:
         eng.set_option(_abi.OPT_PROFILE, -1)
-        _, prof_all, _, _ = timed(step_resident, args.steps, 1)
+        for _ in range(2):
+            step_resident()
+        eng.profile(reset=True)
+        timer.run(step_resident, args.steps, 0)
+        prof_all = eng.profile(reset=True)
+        eng.set_option(_abi.OPT_PROFILE, 0)
 
-    # one small gather of the per-product results (the only exchange on this path)
-    res = torch.tensor(np.concatenate([sums, se], axis=1), device=dev)
+    first_c, count_c, _ = eng.shard_range()
+    widths = None
     if world > 1:
-        allres = [torch.empty_like(res) for _ in range(world)]
-        dist.all_gather(allres, res)
-        res = torch.cat(allres)
-    n_products_total = int(res.shape[0])
+        w = torch.tensor([eng.staged_bytes_per_row()], device=dev, dtype=torch.int64)
+        allw = [torch.empty_like(w) for _ in range(world)]
+        dist.all_gather(allw, w)
+        widths = [int(x.item()) for x in allw]
+
+    extras = {}
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = side_configs(torch, Engine, synth, stream, dev)
+    if world == 8 and not args.no_extras:
+        c5 = config5(torch, dist, Engine, synth, stream, dev, rank, world, local)
+        if rank == 0:
+            extras["config5"] = c5
 
     if rank == 0:
-        pairs_total = nominal_pairs(N_SEQS, codons) * world
+        pairs_total = nominal_pairs(N_SEQS, codons)
         value = pairs_total / (ms_res * 1e-3)
         e2e = pairs_total / (ms_e2e * 1e-3)
         peak, peak_src = peaks()
-        # algorithmic bytes per launch: pack reads 3 B and writes 1 B per (sequence, codon);
-        # hist reads 1 B per (sequence, codon) and writes 264 B per codon
-        alg = {"pack": 4.0 * N_SEQS * codons, "hist": 1.0 * N_SEQS * codons + 264.0 * codons,
-               "fused": 3.0 * N_SEQS * codons + 264.0 * codons}   # fused: the CDS bytes read once, histograms written
+        # algorithmic bytes per launch, for THIS rank's codon range: pack reads 3 B and writes 1 B per
+        # (sequence, codon); hist reads 1 B per (sequence, codon) and writes 264 B per codon
+        alg = {"pack": 4.0 * N_SEQS * count_c, "hist": 1.0 * N_SEQS * count_c + 264.0 * count_c,
+               "fused": 3.0 * N_SEQS * count_c + 264.0 * count_c}   # fused: the CDS bytes read once, histograms written
         kern = {}
         merged = dict(prof_all)
         merged.update({k: v for k, v in prof.items() if v[1]})       # HBM kernels: from the timed pass itself
@@ -308,37 +379,37 @@ def run_ours(args):
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
                 traffic = json.load(fh).get("tile" if (dom == "fused" and tiled) else dom)
+            if world > 1:
+                traffic = None                 # captured at N = 1
         except Exception:
             pass
-        boot_ms = sum(kern[k]["ms_per_step"] for k in ("bootstrap", "moments") if k in kern)
+        d2h = int(codons * (32 + 8 + 4 + 1 + 1) + len(products) * (4 * 8 + 6 * 8 + 6 * 4))
+        h2d_total = int(N_SEQS * sum(widths)) if widths else int(N_SEQS * eng.staged_bytes_per_row())
+        boot = bootstrap_block(eng, kern, products, world)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_res, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_res, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u8 codon codes / u32 histograms / f64 statistics", "data": "synthetic",
             "config": dict(workload_config(world), **({} if args.p_poly == 0.3 else {"p_poly": args.p_poly, "side_experiment": True})),
-            # the library stages only the CDS columns of every row: from the first CDS column rounded down to 16 to the last
-            "e2e": {"value": e2e, "unit": UNIT,
-                    "h2d_bytes_per_step": int(N_SEQS * (max(max(p.stops) for p in products) - (min(min(p.starts) for p in products) - 1) // 16 * 16)),
-                    "d2h_bytes_per_step": int(len(products) * 10 * 8), "ms_per_step": ms_e2e,
-                    "host_buffer_bytes": int(N_SEQS * ALN_LEN)},
+            # the library stages only the CDS columns of a rank's codon range: from its first column rounded down to 16 to its last
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e,
+                    "host_buffer_bytes": int(N_SEQS * ALN_LEN), "h2d_bytes_per_rank": [int(N_SEQS * w) for w in widths] if widths else None,
+                    "outputs": "per-codon table (poly, n_defined, comparisons, stats4, conserved) + product sums, SEs, undefined counts, on every rank"},
             "gpu_launches": int(launches),
             "route": args.route,
+            "exchange": exchange,
+            "check": check,
             "roofline": {"kernel": kernel_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg[dom]},
+                         "algorithmic_bytes_per_launch": alg[dom], "rank": 0, "codons_of_rank": int(count_c)},
             "kernels": kern,
-            "kernel_timing": "CUDA events inside the library on the launch stream: " + "/".join(hbm_kinds)
+            "kernel_timing": "CUDA events inside the library on the launch stream (rank 0): " + "/".join(hbm_kinds)
                              + " during the timed steps; the other kernels in a separate pass of the same steps",
-            "bootstrap": {"value": N_BOOT * len(products) * world / (boot_ms * 1e-3) if boot_ms else None, "unit": "bootstrap reps/s",
-                          "note": "B x products per step / (bootstrap + moments kernel time)",
-                          # the weight-matrix kernel's contraction: one mma.m8n8k4.f64 (512 flop, half of it padding) per
-                          # 8 replicates x 4 slots; its share of the kernel is in profiles/ (tensor pipe active 28 %)
-                          "dmma_tflops_in_kernel": (512 * sum(-(-N_BOOT // 8) * -(-(len_p + 1) // 4) for len_p in (p.n_codons for p in products))
-                                                    / (kern["bootstrap"]["ms_per_step"] * 1e-3) / 1e12) if "bootstrap" in kern else None},
+            "bootstrap": boot,
             "clocks": clocks.summary(),
-            "products_gathered": n_products_total,
             "host_binding": {"numa_node": numa[0], "cpus": numa[1]} if numa else None,
         }
+        out.update(extras)
         if world == 1 and not args.no_cpu:
             v, threads, sample = cpu_pair_rate(12.0)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
@@ -346,7 +417,144 @@ def run_ours(args):
         os.write(real_stdout, (json.dumps(out) + "\n").encode())
     eng.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def bootstrap_block(eng, kern, products, world):
+    """The resampling kernel against what bounds it: Philox4x32-10 generation (integer multiply issue) and, for the
+    contraction, the FP64 tensor pipe -- both peaks measured on this GPU by the library's own probes."""
+    if "bootstrap" not in kern:
+        return None
+    ms = kern["bootstrap"]["ms_per_step"]
+    draws = N_BOOT * sum(p.n_codons for p in products) / world                       # this rank's replicate range
+    flops = 2.0 * 4 * N_BOOT * sum(p.n_codons for p in products) / world             # algorithmic: B x C x 4 multiply-adds
+    boot_ms = sum(kern[k]["ms_per_step"] for k in ("bootstrap", "moments") if k in kern)
+    blk = {"value": N_BOOT * len(products) / (boot_ms * 1e-3), "unit": "bootstrap reps/s",
+           "note": "B x products per step / (bootstrap + moments kernel time), whole job",
+           "kernel_ms": ms, "draws_per_launch": draws, "gdraws_per_s": draws / (ms * 1e-3) / 1e9,
+           "algorithmic_dmma_tflops": flops / (ms * 1e-3) / 1e12}
+    try:
+        pk = eng.probe_peaks()
+        blk["roofline"] = {"bound": "issue (Philox4x32-10 generation: 20 IMAD.WIDE + 20 LOP3 per 4 draws)", "achieved": draws / (ms * 1e-3) / 1e9,
+                           "peak": pk["philox_gdraws_per_s"], "unit": "Gdraws/s", "frac": draws / (ms * 1e-3) / 1e9 / pk["philox_gdraws_per_s"],
+                           "issue_floor_us": draws / pk["philox_gdraws_per_s"] / 1e9 * 1e6,
+                           "peak_source": "measured here: a kernel that only generates Philox4x32-10 blocks (snpg_probe_peaks)"}
+        blk["fp64_tensor"] = {"peak_tflops": pk["dmma_tflops"], "peak_source": "measured here: dependent-free mma.sync.m8n8k4.f64 loop (snpg_probe_peaks)",
+                              "algorithmic_frac": blk["algorithmic_dmma_tflops"] / pk["dmma_tflops"]}
+    except Exception as e:       # noqa: BLE001
+        blk["roofline"] = {"error": str(e)}
+    return blk
+
+
+def quick_time(torch, stream, fn, steps=20, warmup=4):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        out = fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, out
+
+
+def side_configs(torch, Engine, synth, stream, dev):
+    """BASELINE configs 3 and 4 through the same library, a few steps each (extra keys, not the bench line)."""
+    res = {}
+    # config 3: HIV-shaped, overlapping genes, '-' strand, 5 % damaged bases, windows of 100 codons step 10
+    products = synth.hiv_products()
+    L, n = 9719, 5000
+    aln = synth.make_alignment(n, L, products, 20261019 + 3, gap_frac=0.025, n_frac=0.02, iupac_frac=0.005)
+    pitch = (L + 127) // 128 * 128
+    d = torch.zeros((n, pitch), dtype=torch.uint8, device=dev)
+    d[:, :L] = torch.from_numpy(aln).to(dev)
+    codons = sum(p.n_codons for p in products)
+    with Engine(device=dev.index, seed=3) as e:
+        e.set_stream(stream.cuda_stream)
+        e.set_products(products, L)
+        ms, out = quick_time(torch, stream, lambda: e.job(0, d.data_ptr(), n, L, pitch, device=True, B=1000, window=100, step=10, B_win=1000))
+        nwin = int(out["win_ofs"][-1])
+        res["config3"] = {"workload": "config3: within-group, 5000 seqs x 9719 nt, 9 CDS (overlapping, 2-segment, 2 on '-'), 5% damaged bases, "
+                                      "1000 bootstraps, windows of 100 codons step 10 each bootstrapped 1000 times; ONE call, alignment resident in HBM",
+                          "ms_per_step": ms, "windows": nwin, "window_bootstrap_reps_per_s": nwin * 1000 / (ms * 1e-3),
+                          "codon_pair_comparisons_per_s": nominal_pairs(n, codons) / (ms * 1e-3), "graph_replays": e.graph_replays}
+    del d
+    # config 4: between-group, 4 groups x 5,000 x 29,903, 6 group pairs, 1,000 bootstraps
+    products = synth.sars2_products()
+    L, n, G = 29903, 5000, 4
+    pitch = (L + 127) // 128 * 128
+    codons = sum(p.n_codons for p in products)
+    bufs = []
+    for g in range(G):
+        a = synth.make_alignment(n, L, products, 20261019 + 4 + 100 * g)
+        t = torch.zeros((n, pitch), dtype=torch.uint8, device=dev)
+        t[:, :L] = torch.from_numpy(a).to(dev)
+        bufs.append(t)
+    with Engine(device=dev.index, seed=4) as e:
+        e.set_stream(stream.cuda_stream)
+        e.set_products(products, L)
+
+        def step4():
+            for g in range(G):
+                e.load_group_ptr(g, bufs[g].data_ptr(), n, L, pitch, device=True)
+            return e.between_all(list(range(G)), B=1000)
+        ms, _ = quick_time(torch, stream, step4, steps=10, warmup=3)
+        res["config4"] = {"workload": "config4: between-group, 4 groups x 5000 seqs x 29903 nt, 6 group pairs x 10 CDS, 1000 bootstraps; "
+                                      "4 loads + one snpg_between_all, alignments resident in HBM",
+                          "ms_per_step": ms, "codon_pair_comparisons_per_s": 6 * codons * n * n / (ms * 1e-3),
+                          "bootstrap_reps_per_s": 6 * len(products) * 1000 / (ms * 1e-3)}
+    return res
+
+
+def config5(torch, dist, Engine, synth, stream, dev, rank, world, local):
+    """BASELINE config 5: ONE alignment of 1,000,000 x 29,903, 10,000 bootstraps, codon axis and replicates over the 8
+    GPUs, through the same job call.  The alignment is generated on the device: a rank fills only the columns of its
+    own codon range of a full-pitch buffer (the only ones its kernels read)."""
+    from snpgenie_b200 import multigpu
+    products = synth.sars2_products()
+    L, n = 29903, 1000000
+    pitch = (L + 127) // 128 * 128
+    codons = sum(p.n_codons for p in products)
+    cols = np.concatenate([np.arange(p.starts[0] - 1, p.stops[0]).reshape(-1, 3) for p in products])
+    first, count = multigpu.shard_plan(codons, rank, world)
+    mine = cols[first:first + count]
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(20261019 + 5)                      # same ancestral row on every rank
+    anc = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)[torch.randint(0, 4, (pitch,), device=dev, generator=gen)]
+    d = anc.repeat(n, 1)
+    rng = np.random.default_rng(1000 + rank)
+    nt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for c in np.flatnonzero(rng.random(count) < 0.3):
+        u = torch.rand(n, device=dev)
+        acc = 0.0
+        for f in rng.beta(0.5, 5.0, size=int(rng.integers(1, 4))):
+            col = int(mine[c, rng.integers(0, 3)])
+            alt = int(rng.choice(nt[nt != int(anc[col])]))
+            d[:, col].masked_fill_((u >= acc) & (u < acc + f), alt)
+            acc += f
+    torch.cuda.synchronize()
+    dist.barrier()
+    with Engine(device=local, seed=5, rank=rank, world=world) as e:
+        e.set_stream(stream.cuda_stream)
+        e.set_products(products, L)
+        e.connect_ranks(N_BOOT)
+        timer = Timer(torch, dist, stream, world, dev)
+        ms, _, out = timer.run(lambda: e.job(0, d.data_ptr(), n, L, pitch, device=True, B=N_BOOT), 10, 3)
+        se = float(out["prod_se"][0, 2])
+        s0 = [float(x) for x in out["prod_sums"][0]]
+        # consistency across ranks: every rank holds the same full result
+        t = torch.tensor(out["prod_se"].reshape(-1), device=dev)
+        hi, lo = t.clone(), t.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        same = bool(torch.equal(hi, lo))
+    del d
+    return {"workload": f"config5: within-group, {n} seqs x {L} nt, 10 CDS, {N_BOOT} bootstraps, ONE alignment split over {world} GPUs; resident in HBM",
+            "ms_per_step": ms, "codon_pair_comparisons_per_s": nominal_pairs(n, codons) / (ms * 1e-3), "bytes_read_per_gpu": int(n * 3 * count),
+            "hbm_floor_ms": n * 3 * count / (peaks()[0] * 1e9) * 1e3, "dN_minus_dS_SE_product0": se, "product0_sums": s0,
+            "all_ranks_hold_identical_results": same}
 
 
 def main():
@@ -355,7 +563,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg and the oracle check")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config 3/4/5 side measurements")
     ap.add_argument("--p-poly", type=float, default=0.3,
                     help="fraction of polymorphic codon columns in the synthetic alignment (SURVEY.md 8d: 0.3; "
                          "other values are side experiments, never the bench line)")

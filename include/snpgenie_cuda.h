@@ -144,6 +144,13 @@ int snpg_codon_strings(snpg_ctx *ctx, int slot, int product, int64_t codon, uint
 #define SNPG_OPT_BOOTSTRAP_KERNEL 5
 #define SNPG_BOOT_GATHER 0
 #define SNPG_BOOT_WEIGHTS 1
+/* SNPG_OPT_BOOT_SLOTS (default SNPG_SLOTS_FAITHFUL): the whole-product bootstrap of the reference draws
+ * int(rand(C+1)) (wg:885; bgp:919), i.e. C+1 slots of which slot 0 is a codon that does not exist and adds
+ * nothing -- every replicate is on average C/(C+1) of a product.  FAITHFUL reproduces that; CORRECTED draws from
+ * the C real codons.  (Window bootstraps always draw from the window's W codons, wgp:406.) */
+#define SNPG_OPT_BOOT_SLOTS 6
+#define SNPG_SLOTS_CORRECTED 0
+#define SNPG_SLOTS_FAITHFUL 1
 int snpg_set_option(snpg_ctx *ctx, int option, int64_t value);
 
 /* ---- test hooks for the bit-exact checks ---------------------------------
@@ -220,8 +227,66 @@ int snpg_between_all(snpg_ctx *ctx, const int *groups, int n_groups, int64_t min
 int snpg_within_job(snpg_ctx *ctx, int group, const uint8_t *bases, int bases_on_device, uint64_t n_seqs,
                     uint64_t aln_len, uint64_t row_stride, int64_t B, double *prod_sums, double *prod_se);
 
-/* Device-pointer variants for multi-GPU plumbing (torch.distributed moves the
- * buffers): d_stats4 is a DEVICE buffer [count][4] for this shard's codons. */
+/* The whole job with everything the drivers' tables need, still ONE call and one synchronisation: load, per-codon
+ * engine (wg:586-751), product sums and whole-product bootstrap (wg:690-693, :831-978), sliding windows with their
+ * bootstraps (wgp:293-465).  Outputs are host pointers, any may be NULL; pinned memory (cudaHostAlloc/cudaHostRegister)
+ * is written by asynchronous copies that overlap the bootstrap, other memory goes through a staging buffer.
+ * Per-codon outputs cover the GLOBAL codon axis: all products concatenated in snpg_set_products order (product p at
+ * sum of snpg_n_codons of the products before it), `total` of snpg_shard_range entries -- on several GPUs as well
+ * (every rank receives every codon range through the exchange).  Window outputs cover the windows of all products in
+ * product order: product p owns windows [win_ofs[p], win_ofs[p+1]) of snpg_window_plan; a product shorter than the
+ * window has none (wgp:299-305). */
+typedef struct snpg_job {
+    uint32_t struct_size;        /* sizeof(snpg_job) */
+    uint32_t reserved;
+    int64_t n_bootstraps;        /* whole-product bootstrap replicates; < 2: none */
+    int64_t window, step;        /* sliding windows of `window` codons every `step` codons; window = 0: none */
+    int64_t n_window_bootstraps; /* < 2: window sums only */
+    double *prod_sums;           /* [P][4] N_sites, S_sites, N_diffs, S_diffs */
+    double *prod_se;             /* [P][6] SE of dN, dS, dN-dS and their Jukes-Cantor forms */
+    uint32_t *prod_undefined;    /* [P][6] replicates whose value is undefined (Jukes-Cantor of d >= 3/4; the reference dies, bgp:1047) */
+    uint8_t *poly;               /* [total] 1 = polymorphic */
+    uint32_t *n_defined;         /* [total] */
+    uint64_t *comparisons;       /* [total] */
+    double *stats4;              /* [total][4] */
+    uint8_t *conserved;          /* [total] code of the conserved codon (SNPG_CODE_UNDEF: polymorphic or none defined) */
+    double *win_sums;            /* [n_windows][4] */
+    double *win_se;              /* [n_windows][3] SE of dN, dS, dN-dS over n_window_bootstraps replicates */
+} snpg_job;
+int snpg_window_plan(snpg_ctx *ctx, int64_t window, int64_t step, int64_t *win_ofs /*[P+1]*/);
+int snpg_within_job_ex(snpg_ctx *ctx, int group, const uint8_t *bases, int bases_on_device, uint64_t n_seqs, uint64_t aln_len,
+                       uint64_t row_stride, const snpg_job *job);
+
+/* ---- several GPUs -----------------------------------------------------------------------------------------
+ * The path shards by codon range (histograms, per-codon statistics) and by bootstrap replicate (SURVEY.md 8e;
+ * north_star: "sharded across the 8 B200s by product/codon range and by bootstrap replicate").  The exchange is the
+ * reference's gather of its forked children's results (wg:508-538; bg:949-1017): here every rank's kernels store
+ * their codon range / replicate range straight into every other rank's memory over NVLink (peer access inside a
+ * process, CUDA IPC across processes) and signal arrival with flags the consuming kernels wait on -- no host
+ * round trip, no separate collective launch.  Whole jobs (snpg_within_job, snpg_within_job_ex) then return the same
+ * results on every rank as a single GPU would, bit for bit.
+ *
+ * One process, N GPUs (what the Perl command lines use with --gpus N): snpg_create_multi returns ONE ctx that fans
+ * every call out to a child ctx per GPU.  Supported on it: snpg_set_option, snpg_set_products, snpg_n_products,
+ * snpg_n_codons, snpg_shard_range, snpg_read_fasta, snpg_codon_strings, snpg_load_group (host memory),
+ * snpg_drop_group, snpg_group_size, snpg_get_hist, snpg_get_site_counts (not supported: E_STATE), snpg_within,
+ * snpg_within_all, snpg_within_job / _ex (host memory), snpg_window_plan, snpg_launch_count, snpg_last_error,
+ * snpg_destroy; snpg_bootstrap_product, snpg_windows and snpg_test_philox run on the first GPU.  Anything else
+ * returns SNPG_E_STATE.  devices = NULL means GPUs 0..n_gpus-1. */
+int snpg_create_multi(snpg_ctx **out, int n_gpus, const int *devices, uint64_t seed);
+int snpg_team_size(const snpg_ctx *ctx);                 /* 1 for an ordinary ctx */
+/* One process per GPU (torchrun, MPI ...): every rank calls snpg_set_shard, snpg_set_products, then
+ * snpg_peer_export; the host program gathers the handles of all ranks in rank order (any transport: a file,
+ * torch.distributed, MPI) and hands the array to snpg_peer_connect on every rank.  max_bootstraps bounds
+ * n_bootstraps of later jobs.  Ranks of one process are connected by pointer, ranks of other processes through
+ * CUDA IPC.  snpg_set_products afterwards disconnects (export and connect again). */
+#define SNPG_PEER_HANDLE_BYTES 128
+int snpg_peer_export(snpg_ctx *ctx, int64_t max_bootstraps, void *handle);
+int snpg_peer_connect(snpg_ctx *ctx, const void *handles, int n_handles);
+int snpg_peer_connected(const snpg_ctx *ctx);            /* 1 when whole jobs exchange with the peers */
+
+/* Device-pointer variants for multi-GPU plumbing done by the CALLER (e.g. NCCL through torch.distributed -- the
+ * baseline the peer-memory exchange above replaces): d_stats4 is a DEVICE buffer [count][4] for this shard's codons. */
 int snpg_within_stats_device(snpg_ctx *ctx, int group, double *d_stats4);
 /* Bootstrap all products from a full-length DEVICE stats buffer [total][4];
  * replicates [b_first, b_first+b_count) only; d_rep_out DEVICE [P][b_count][4]. */
@@ -234,7 +299,9 @@ int snpg_product_sums_device(snpg_ctx *ctx, const double *d_stats4_full, double 
 int snpg_rep_moments_device(snpg_ctx *ctx, const double *d_rep, int64_t n_items, int64_t B, double *se_out);
 
 /* Launch all kernels on a caller-owned CUDA stream (a cudaStream_t, e.g. torch's
- * current stream) instead of the ctx's own; NULL restores an internal stream. */
+ * current stream) instead of the ctx's own; NULL restores an internal stream.  The legacy default stream has the
+ * handle 0 in most bindings (torch.cuda.default_stream().cuda_stream == 0): pass cudaStreamLegacy, (void *)1, for it --
+ * NULL does NOT mean "the default stream" here. */
 int snpg_set_stream(snpg_ctx *ctx, void *cuda_stream);
 
 /* Per-kernel device time measured with CUDA events (needs SNPG_OPT_PROFILE=1). */
@@ -254,6 +321,14 @@ int snpg_get_profile(snpg_ctx *ctx, double *ms /*[10]*/, int64_t *calls /*[10]*/
 /* Test hook: one Philox4x32-10 block computed by the device code the bootstraps use
  * (checked against the Random123 known-answer vectors). */
 int snpg_test_philox(snpg_ctx *ctx, const uint32_t *ctr4, const uint32_t *key2, uint32_t *out4);
+
+/* The columns of every row a load stages from a host buffer (this ctx's codon range: from its first CDS column
+ * rounded down to 16 to its last): what bench.py counts as h2d bytes. */
+int snpg_staged_columns(const snpg_ctx *ctx, int64_t *first_col, int64_t *n_cols);
+/* Peaks the resampling kernel is measured against, probed on this GPU: out[0] = Philox4x32-10 words generated per
+ * second by a kernel that does nothing else (the issue bound of a sampler that spends one word per draw), out[1] =
+ * FP64 tensor TFLOP/s of mma.sync.m8n8k4.f64; out[2..3] reserved. */
+int snpg_probe_peaks(snpg_ctx *ctx, double *out /*[4]*/);
 
 /* Kernel launches issued by this ctx since creation (bench.py's gpu_launches). */
 int64_t snpg_launch_count(const snpg_ctx *ctx);

@@ -13,8 +13,10 @@ LIB_PATH = os.path.join(_HERE, "libsnpgenie_cuda.so")
 
 OK, E_ARG, E_STATE, E_INPUT, E_CUDA, E_NOMEM = 0, -1, -2, -3, -4, -5
 CODE_UNDEF, CODE_OTHER, HIST_BINS = 64, 65, 66
-OPT_KEEP_CODES, OPT_PROFILE, OPT_SITE_COUNTS, OPT_FUSED_KERNEL, OPT_BOOTSTRAP_KERNEL = 1, 2, 3, 4, 5
+OPT_KEEP_CODES, OPT_PROFILE, OPT_SITE_COUNTS, OPT_FUSED_KERNEL, OPT_BOOTSTRAP_KERNEL, OPT_BOOT_SLOTS = 1, 2, 3, 4, 5, 6
 BOOT_GATHER, BOOT_WEIGHTS = 0, 1
+SLOTS_CORRECTED, SLOTS_FAITHFUL = 0, 1
+PEER_HANDLE_BYTES = 128
 FUSED_TMA_TILES, FUSED_LDG_SPANS = 0, 1
 KERNEL_KINDS = ("pack", "hist", "stats", "sums", "bootstrap", "moments", "window", "other", "fused", "sites")
 
@@ -28,6 +30,15 @@ lib = C.CDLL(LIB_PATH)
 
 _u8p, _u32p, _u64p, _i64p, _i8p, _f64p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint32, C.c_uint64, C.c_int64, C.c_int8, C.c_double))
 _ctx = C.c_void_p
+
+
+class Job(C.Structure):
+    """snpg_job (include/snpgenie_cuda.h): what a whole job computes and where its outputs go."""
+    _fields_ = [("struct_size", C.c_uint32), ("reserved", C.c_uint32), ("n_bootstraps", C.c_int64), ("window", C.c_int64),
+                ("step", C.c_int64), ("n_window_bootstraps", C.c_int64), ("prod_sums", C.c_void_p), ("prod_se", C.c_void_p),
+                ("prod_undefined", C.c_void_p), ("poly", C.c_void_p), ("n_defined", C.c_void_p), ("comparisons", C.c_void_p),
+                ("stats4", C.c_void_p), ("conserved", C.c_void_p), ("win_sums", C.c_void_p), ("win_se", C.c_void_p)]
+
 
 # every exported symbol of include/snpgenie_cuda.h with its signature
 SIGNATURES = {
@@ -59,11 +70,20 @@ SIGNATURES = {
     "snpg_within_all": (C.c_int, [_ctx, C.c_int, C.c_int64, _f64p, _f64p]),
     "snpg_between_all": (C.c_int, [_ctx, C.POINTER(C.c_int), C.c_int, C.c_int64, C.c_int64, C.c_int64, _f64p, _f64p]),
     "snpg_within_job": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, _f64p, _f64p]),
+    "snpg_within_job_ex": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(Job)]),
+    "snpg_window_plan": (C.c_int, [_ctx, C.c_int64, C.c_int64, _i64p]),
+    "snpg_create_multi": (C.c_int, [C.POINTER(_ctx), C.c_int, C.POINTER(C.c_int), C.c_uint64]),
+    "snpg_team_size": (C.c_int, [_ctx]),
+    "snpg_peer_export": (C.c_int, [_ctx, C.c_int64, C.c_void_p]),
+    "snpg_peer_connect": (C.c_int, [_ctx, C.c_void_p, C.c_int]),
+    "snpg_peer_connected": (C.c_int, [_ctx]),
     "snpg_within_stats_device": (C.c_int, [_ctx, C.c_int, C.c_void_p]),
     "snpg_bootstrap_all_device": (C.c_int, [_ctx, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "snpg_product_sums_device": (C.c_int, [_ctx, C.c_void_p, _f64p]),
     "snpg_rep_moments_device": (C.c_int, [_ctx, C.c_void_p, C.c_int64, C.c_int64, _f64p]),
     "snpg_test_philox": (C.c_int, [_ctx, _u32p, _u32p, _u32p]),
+    "snpg_staged_columns": (C.c_int, [_ctx, _i64p, _i64p]),
+    "snpg_probe_peaks": (C.c_int, [_ctx, _f64p]),
     "snpg_launch_count": (C.c_int64, [_ctx]),
     "snpg_tile_launch_count": (C.c_int64, [_ctx]),
     "snpg_graph_replays": (C.c_int64, [_ctx]),

@@ -2,138 +2,19 @@
 // sequencing of kernels.  See include/snpgenie_cuda.h for the contract and the
 // reference blocks each entry point replaces.  There is no CPU fallback here:
 // every compute entry point runs the CUDA kernels or fails with SNPG_E_CUDA.
-#include <fcntl.h>
-#include <sys/mman.h>
-#include <sys/stat.h>
-#include <unistd.h>
-
+// (Whole jobs: job.cu; several GPUs: exchange.cu; the FASTA reader: ingest.cu.)
 #include <algorithm>
-#include <cstdarg>
-#include <cstdio>
 #include <cstdlib>
-#include <cstring>
-#include <string>
-#include <vector>
 
-#include "../../include/snpgenie_cuda.h"
-#include "snpg_internal.h"
+#include "snpg_ctx.h"
+#include "snpg_team.h"
 
 using namespace snpg;
 
-namespace {
+namespace snpg {
 
-std::string g_create_error;
-
-uint64_t g_alloc_epoch = 0;   // bumped whenever a device buffer moves: captured CUDA graphs hold raw pointers
-
-struct DevBuf {  // grow-only device scratch
-    void *p = nullptr;
-    size_t cap = 0;
-    cudaError_t ensure(size_t bytes) {
-        if (bytes <= cap) return cudaSuccess;
-        g_alloc_epoch++;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        cudaError_t e = cudaMalloc(&p, bytes);
-        if (e == cudaSuccess) cap = bytes;
-        return e;
-    }
-    void release() { if (p) { cudaFree(p); g_alloc_epoch++; } p = nullptr; cap = 0; }
-    template <class T> T *as() const { return static_cast<T *>(p); }
-};
-
-struct Group {
-    bool loaded = false;
-    uint64_t n = 0;
-    int64_t n_pad = 0;
-    DevBuf codes, hist, other;   // other: [2][count] min then max
-    DevBuf sites;                // [aln_len][5] per-site A,C,G,T,other (SNPG_OPT_SITE_COUNTS)
-    bool has_sites = false;
-    bool has_codes = false;
-    bool clear_in_vote = false;  // hist/other are cleared by the load's first kernel, not by memsets
-};
-
-}  // namespace
-
-struct snpg_ctx {
-    int device = 0;
-    uint64_t seed = 0;
-    std::string err;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_packed[2] = {nullptr, nullptr};
-    int rank = 0, world = 1;
-    bool keep_codes = false;        // default route: fused histogram, no code matrix
-    bool site_counts = false;       // also count A/C/G/T per alignment column while loading (whole rows are staged)
-    bool defer_load_sync = false;   // set inside snpg_within_job*: the load's kernels stay queued behind the analysis
-    // annotation
-    int n_products = 0;
-    int64_t aln_len = 0;
-    std::vector<int64_t> full_ofs;    // [P+1] offsets on the global codon axis
-    std::vector<int64_t> local_ofs;   // [P+1] offsets inside this shard (clamped)
-    int64_t shard_first = 0, shard_count = 0;
-    int64_t col_lo = 0, col_hi = 0;   // alignment columns this shard touches, [lo, hi)
-    DevBuf d_map, d_local_ofs, d_full_ofs, d_tables;
-    // fused path (no code matrix): 16-byte column spans starting at base_al
-    int64_t base_al = 0, n_spans = 0;     // base_al = col_lo rounded down to 16
-    int64_t n_irr = 0;                    // codons the span runs cannot express
-    DevBuf d_runs, d_regular, d_irr_map, d_irr_idx, d_cons, d_alt;
-    DevBuf t_codes, t_hist, t_other;      // irregular codons: compact K1+K2 scratch
-    // TMA-tiled variant of the fused path: frame-aligned tiles of <= 64 codons over the regular codons
-    DevBuf d_tiles, d_sched;              // d_sched: the tile kernel's chunk counter and finished-CTA counter
-    int64_t n_tiles = 0;
-    int fused_kernel = SNPG_FUSED_LDG_SPANS;
-    int boot_kernel = SNPG_BOOT_WEIGHTS;
-    const Group *stats_of = nullptr;      // the group whose per-codon statistics sit in s_stats (written by its load; see finish_group)
-    int n_sms = 148;
-    int tma_l2_promotion = 2;             // CU_TENSOR_MAP_L2_PROMOTION_L2_128B (SNPG_TMA_L2PROMO overrides: 0..3)
-    // groups
-    Group groups[SNPG_MAX_GROUPS];
-    // FASTA slots: pinned host copies [n][len] read by snpg_read_fasta
-    struct HostAln { uint8_t *p = nullptr; size_t cap = 0; uint64_t n = 0, len = 0; } host_aln[SNPG_MAX_GROUPS];
-    std::vector<CodonMap> host_map;   // full codon map (absolute columns), for snpg_codon_strings
-    // scratch
-    DevBuf s_vals, d_order_local, d_order_full;
-    int64_t max_codons_local = 0, max_codons_full = 0;
-    DevBuf staging[2], s_stats, s_poly, s_nda, s_ndb, s_cmp, s_cons, s_sums, s_rep, s_se, s_misc, s_in;
-    // snpg_within_job on a device-resident alignment, replayed as a CUDA graph from the third identical call on
-    struct TimedSpan { cudaEvent_t e0, e1; int kind; };
-    bool capturing = false;
-    struct JobKey {
-        uint32_t profile_mask = 0;
-        int group = -1; const uint8_t *bases = nullptr; uint64_t n = 0, len = 0, stride = 0; int64_t B = 0;
-        bool keep_codes = false, site_counts = false, want_se = false; int fused_kernel = 0;
-        bool operator==(const JobKey &o) const {
-            return profile_mask == o.profile_mask && group == o.group && bases == o.bases && n == o.n && len == o.len && stride == o.stride && B == o.B &&
-                   keep_codes == o.keep_codes && site_counts == o.site_counts && want_se == o.want_se && fused_kernel == o.fused_kernel;
-        }
-    };
-    struct JobGraph {
-        cudaGraphExec_t exec = nullptr;
-        JobKey key, candidate;
-        uint64_t epoch = 0, candidate_epoch = ~0ull;
-        int64_t n_launches = 0, n_tile_launches = 0;
-        bool disabled = false;
-        std::vector<TimedSpan> spans;   // event pairs recorded inside the graph (profiling on)
-        uint32_t *h_salt = nullptr;     // pinned
-        double *h_out = nullptr;        // pinned: sums [P][4] then se [P][6]
-        int h_out_products = 0;
-        int64_t replays = 0;
-    } job;
-    DevBuf d_salt;
-    int64_t launches = 0;
-    int64_t tile_launches = 0;      // launches of k_tile_hist (the rest of SNPG_K_FUSED went to k_fused_hist)
-    uint32_t call_id = 0;
-    // optional per-kernel timing (CUDA events on the launch stream)
-    uint32_t profile_mask = 0;      // bit k set: bracket launches of kernel kind k with timing events
-    bool own_stream = true;
-    typedef TimedSpan Span;
-    std::vector<Span> spans;        // recorded, not yet resolved
-    std::vector<cudaEvent_t> free_events;
-    double kernel_ms[SNPG_N_KERNEL_KINDS] = {0};
-    int64_t kernel_calls[SNPG_N_KERNEL_KINDS] = {0};
-};
-
-namespace {
+static std::string g_create_error;
+std::atomic<uint64_t> g_alloc_epoch{0};
 
 int fail(snpg_ctx *ctx, int code, const char *fmt, ...) {
     char buf[512];
@@ -152,28 +33,6 @@ cudaEvent_t take_event(snpg_ctx *ctx) {
     return e;
 }
 
-// Brackets one kernel launch with events when profiling is on; counts it always.
-struct Launch {
-    snpg_ctx *ctx; int kind; cudaEvent_t e0 = nullptr;
-    Launch(snpg_ctx *c, int k) : ctx(c), kind(k) {
-        ctx->launches++;
-        if ((ctx->profile_mask >> kind) & 1u) {
-            e0 = take_event(ctx);
-            // inside a graph capture the records become external event-record nodes: the same pair of events is
-            // re-recorded by every replay and read after it
-            if (ctx->capturing) cudaEventRecordWithFlags(e0, ctx->stream, cudaEventRecordExternal);
-            else cudaEventRecord(e0, ctx->stream);
-        }
-    }
-    ~Launch() {
-        if (!e0) return;
-        cudaEvent_t e1 = take_event(ctx);
-        if (ctx->capturing) { cudaEventRecordWithFlags(e1, ctx->stream, cudaEventRecordExternal); ctx->job.spans.push_back({e0, e1, kind}); }
-        else { cudaEventRecord(e1, ctx->stream); ctx->spans.push_back({e0, e1, kind}); }
-    }
-};
-
-// after a stream synchronise: turn recorded spans into accumulated milliseconds
 void resolve_spans(snpg_ctx *ctx) {
     for (auto &sp : ctx->spans) {
         float ms = 0;
@@ -184,13 +43,14 @@ void resolve_spans(snpg_ctx *ctx) {
     ctx->spans.clear();
 }
 
-// a captured snpg_within_job graph holds pointers, options and event pairs: anything that changes them drops it
 void invalidate_job_graph(snpg_ctx *ctx) {
-    if (ctx->job.exec) cudaGraphExecDestroy(ctx->job.exec);
-    ctx->job.exec = nullptr;
-    for (auto &sp : ctx->job.spans) { ctx->free_events.push_back(sp.e0); ctx->free_events.push_back(sp.e1); }
-    ctx->job.spans.clear();
-    ctx->job.candidate_epoch = ~0ull;
+    for (auto &J : ctx->job_graph) {
+        if (J.exec) cudaGraphExecDestroy(J.exec);
+        J.exec = nullptr;
+        for (auto &sp : J.spans) { ctx->free_events.push_back(sp.e0); ctx->free_events.push_back(sp.e1); }
+        J.spans.clear();
+    }
+    ctx->job_candidate_epoch = ~0ull;
 }
 
 cudaError_t sync_stream(snpg_ctx *ctx) {
@@ -198,15 +58,6 @@ cudaError_t sync_stream(snpg_ctx *ctx) {
     if (e == cudaSuccess && !ctx->spans.empty()) resolve_spans(ctx);
     return e;
 }
-
-#define CU(ctx, call)                                                                                   \
-    do {                                                                                                \
-        cudaError_t e__ = (call);                                                                       \
-        if (e__ != cudaSuccess)                                                                         \
-            return fail(ctx, SNPG_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
-    } while (0)
-
-#define NEED(ctx, cond, code, ...) do { if (!(cond)) return fail(ctx, code, __VA_ARGS__); } while (0)
 
 int bind(snpg_ctx *ctx) {
     CU(ctx, cudaSetDevice(ctx->device));
@@ -234,6 +85,16 @@ GroupView view_of(const snpg_ctx *ctx, const Group &g, int64_t c0) {
     v.n_pad = g.n_pad;
     return v;
 }
+
+// Local slice [c0, c0+C) of a product inside this shard.
+void product_slice(const snpg_ctx *ctx, int product, int64_t *c0, int64_t *C) {
+    *c0 = ctx->local_ofs[product];
+    *C = ctx->local_ofs[product + 1] - ctx->local_ofs[product];
+}
+
+}  // namespace snpg
+
+namespace {
 
 int prepare_group(snpg_ctx *ctx, Group &g, uint64_t n_seqs) {
     g.loaded = false;
@@ -321,16 +182,15 @@ int finish_group(snpg_ctx *ctx, Group &g) {
         Launch l(ctx, SNPG_K_HIST);
         launch_hist(g.codes.as<uint8_t>(), g.n_pad, ctx->shard_count, g.hist.as<uint32_t>(), ctx->stream);
     } else {
-        // a whole job (snpg_within_job: the analysis follows the load at once) also takes the per-codon statistics here
-        const bool with_stats = ctx->defer_load_sync && ctx->n_irr == 0 && ctx->shard_count > 0 && !ctx->site_counts &&
-                                ctx->s_stats.ensure(sizeof(double) * 4 * (size_t)ctx->shard_count) == cudaSuccess;
+        // a whole job (job.cu: the analysis follows the load at once) also takes the per-codon statistics here, into the
+        // buffers the job chose (ctx->job_out: local scratch, or every rank's exchange region through job_peer_out)
+        const bool with_stats = ctx->defer_load_sync && ctx->n_irr == 0 && !ctx->site_counts;
         ctx->stats_of = nullptr;
         if (with_stats) {
             Launch l(ctx, SNPG_K_OTHER);
-            StatsOut o{nullptr, nullptr, nullptr, nullptr, ctx->s_stats.as<double>(), nullptr};
             launch_fused_fixup_stats(ctx->d_cons.as<uint8_t>(), ctx->col_lo - ctx->base_al, ctx->d_alt.as<uint32_t>(), ctx->d_map.as<CodonMap>(),
                                      ctx->shard_count, (uint32_t)g.n, g.hist.as<uint32_t>(), omin, omax, view_of(ctx, g, 0),
-                                     ctx->d_tables.as<double>(), o, ctx->stream);
+                                     ctx->d_tables.as<double>(), ctx->job_out, &ctx->job_peer_out, &ctx->job_peer_sync, ctx->stream);
             ctx->stats_of = &g;
         } else {
             Launch l(ctx, SNPG_K_OTHER);
@@ -388,6 +248,8 @@ int snpg_create(snpg_ctx **out, int device, uint64_t seed) {
         if ((e = cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
         if ((e = cudaEventCreateWithFlags(&ctx->ev_packed[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     }
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if (cudaDeviceGetAttribute(&ctx->n_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || ctx->n_sms <= 0) ctx->n_sms = 148;
     if (const char *v = getenv("SNPG_TMA_L2PROMO")) ctx->tma_l2_promotion = atoi(v);
     if ((e = ctx->d_sched.ensure(2 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(sched)", e);
@@ -403,17 +265,23 @@ int snpg_create(snpg_ctx **out, int device, uint64_t seed) {
 
 void snpg_destroy(snpg_ctx *ctx) {
     if (!ctx) return;
+    if (is_team(ctx)) {
+        for (snpg_ctx *c : ctx->team) { c->team_parent = nullptr; snpg_destroy(c); }
+        delete ctx;
+        return;
+    }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    exchange_release(ctx);
     for (auto &g : ctx->groups) { g.codes.release(); g.hist.release(); g.other.release(); g.sites.release(); }
     for (auto &h : ctx->host_aln) if (h.p) cudaFreeHost(h.p);
     invalidate_job_graph(ctx);
-    if (ctx->job.h_salt) cudaFreeHost(ctx->job.h_salt);
-    if (ctx->job.h_out) cudaFreeHost(ctx->job.h_out);
+    if (ctx->h_salt) cudaFreeHost(ctx->h_salt);
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
     DevBuf *bufs[] = {&ctx->d_map, &ctx->d_local_ofs, &ctx->d_full_ofs, &ctx->d_tables, &ctx->staging[0], &ctx->staging[1],
                       &ctx->d_runs, &ctx->d_tiles, &ctx->d_sched, &ctx->d_salt, &ctx->d_regular, &ctx->d_irr_map, &ctx->d_irr_idx, &ctx->d_cons, &ctx->d_alt, &ctx->t_codes, &ctx->t_hist,
-                      &ctx->t_other,
+                      &ctx->t_other, &ctx->wplan.beg, &ctx->wplan.end, &ctx->w_sums, &ctx->w_vals, &ctx->w_se, &ctx->s_undef,
                       &ctx->s_stats, &ctx->s_poly, &ctx->s_nda, &ctx->s_ndb, &ctx->s_cmp, &ctx->s_cons, &ctx->s_sums,
                       &ctx->s_rep, &ctx->s_se, &ctx->s_misc, &ctx->s_in, &ctx->s_vals, &ctx->d_order_local, &ctx->d_order_full};
     for (DevBuf *b : bufs) b->release();
@@ -421,6 +289,8 @@ void snpg_destroy(snpg_ctx *ctx) {
         if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
         if (ctx->ev_packed[i]) cudaEventDestroy(ctx->ev_packed[i]);
     }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     resolve_spans(ctx);
     for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -430,8 +300,14 @@ void snpg_destroy(snpg_ctx *ctx) {
 
 int snpg_set_option(snpg_ctx *ctx, int option, int64_t value) {
     if (!ctx) return SNPG_E_ARG;
+    TEAM_EACH(ctx, snpg_set_option(c, option, value));
     invalidate_job_graph(ctx);
     if (option == SNPG_OPT_KEEP_CODES) { ctx->keep_codes = value != 0; return SNPG_OK; }
+    if (option == SNPG_OPT_BOOT_SLOTS) {
+        NEED(ctx, value == SNPG_SLOTS_CORRECTED || value == SNPG_SLOTS_FAITHFUL, SNPG_E_ARG, "unknown slot rule %lld", (long long)value);
+        ctx->boot_slot0 = (int)value;
+        return SNPG_OK;
+    }
     if (option == SNPG_OPT_SITE_COUNTS) {
         NEED(ctx, ctx->n_products == 0, SNPG_E_STATE, "SNPG_OPT_SITE_COUNTS must be set before snpg_set_products");
         ctx->site_counts = value != 0;
@@ -460,6 +336,7 @@ int snpg_shard_plan(int64_t total, int rank, int world, int64_t *first, int64_t 
 
 int snpg_set_shard(snpg_ctx *ctx, int rank, int world) {
     if (!ctx) return SNPG_E_ARG;
+    TEAM_UNSUPPORTED(ctx, "snpg_set_shard");
     NEED(ctx, world >= 1 && rank >= 0 && rank < world, SNPG_E_ARG, "bad shard %d/%d", rank, world);
     NEED(ctx, ctx->n_products == 0, SNPG_E_STATE, "set_shard must precede set_products");
     ctx->rank = rank;
@@ -472,9 +349,16 @@ int snpg_set_products(snpg_ctx *ctx, int n_products, const int64_t *seg_ofs, con
     if (!ctx) return SNPG_E_ARG;
     NEED(ctx, n_products > 0 && seg_ofs && seg_start && seg_stop && strand, SNPG_E_ARG, "bad product arguments");
     NEED(ctx, aln_len > 0 && aln_len < (int64_t)1 << 31, SNPG_E_ARG, "alignment length %lld unsupported", (long long)aln_len);
+    if (is_team(ctx)) {
+        for (snpg_ctx *c : ctx->team)
+            if (int rc = snpg_set_products(c, n_products, seg_ofs, seg_start, seg_stop, strand, aln_len)) return team_fail(ctx, c, rc);
+        return team_wire(ctx, 10000);      // grows on demand (a job with more replicates re-wires)
+    }
     if (int rc = bind(ctx)) return rc;
     for (auto &g : ctx->groups) g.loaded = false;  // maps change: loaded groups are stale
     invalidate_job_graph(ctx);
+    exchange_release(ctx);                         // the exchange region is laid out for one annotation
+    ctx->wplan = snpg_ctx::WindowPlan();
 
     std::vector<CodonMap> map_all;
     std::vector<int64_t> full_ofs(n_products + 1, 0);
@@ -646,15 +530,24 @@ int snpg_set_products(snpg_ctx *ctx, int n_products, const int64_t *seg_ofs, con
     return SNPG_OK;
 }
 
-int snpg_n_products(const snpg_ctx *ctx) { return ctx ? ctx->n_products : SNPG_E_ARG; }
+int snpg_n_products(const snpg_ctx *ctx) { return !ctx ? SNPG_E_ARG : is_team(ctx) ? ctx->team[0]->n_products : ctx->n_products; }
 
 int snpg_n_codons(const snpg_ctx *ctx, int product, int64_t *out) {
+    if (is_team(ctx)) ctx = ctx->team[0];
     if (!ctx || !out || product < 0 || product >= ctx->n_products) return SNPG_E_ARG;
     *out = ctx->full_ofs[product + 1] - ctx->full_ofs[product];
     return SNPG_OK;
 }
 
 int snpg_shard_range(const snpg_ctx *ctx, int64_t *first, int64_t *count, int64_t *total) {
+    if (is_team(ctx)) {            // the team as a whole owns the whole axis
+        const snpg_ctx *c = ctx->team[0];
+        if (c->n_products == 0) return SNPG_E_STATE;
+        if (first) *first = 0;
+        if (count) *count = c->full_ofs[c->n_products];
+        if (total) *total = c->full_ofs[c->n_products];
+        return SNPG_OK;
+    }
     if (!ctx || ctx->n_products == 0) return SNPG_E_STATE;
     if (first) *first = ctx->shard_first;
     if (count) *count = ctx->shard_count;
@@ -662,14 +555,9 @@ int snpg_shard_range(const snpg_ctx *ctx, int64_t *first, int64_t *count, int64_
     return SNPG_OK;
 }
 
-// Local slice [c0, c0+C) of a product inside this shard.
-static void product_slice(const snpg_ctx *ctx, int product, int64_t *c0, int64_t *C) {
-    *c0 = ctx->local_ofs[product];
-    *C = ctx->local_ofs[product + 1] - ctx->local_ofs[product];
-}
-
 int snpg_load_group(snpg_ctx *ctx, int group, const uint8_t *bases, uint64_t n_seqs, uint64_t aln_len, uint64_t row_stride) {
     if (!ctx) return SNPG_E_ARG;
+    TEAM_EACH(ctx, snpg_load_group(c, group, bases, n_seqs, aln_len, row_stride));
     NEED(ctx, ctx->n_products > 0, SNPG_E_STATE, "set products before loading a group");
     NEED(ctx, group >= 0 && group < SNPG_MAX_GROUPS, SNPG_E_ARG, "group %d out of range", group);
     NEED(ctx, bases && n_seqs > 0 && n_seqs < ((uint64_t)1 << 31), SNPG_E_ARG, "bad alignment arguments");
@@ -712,6 +600,7 @@ int snpg_load_group(snpg_ctx *ctx, int group, const uint8_t *bases, uint64_t n_s
 int snpg_load_group_device(snpg_ctx *ctx, int group, const uint8_t *d_bases, uint64_t n_seqs, uint64_t aln_len,
                            uint64_t row_stride) {
     if (!ctx) return SNPG_E_ARG;
+    TEAM_UNSUPPORTED(ctx, "snpg_load_group_device (a device pointer belongs to one GPU; use snpg_team_ctx)");
     NEED(ctx, ctx->n_products > 0, SNPG_E_STATE, "set products before loading a group");
     NEED(ctx, group >= 0 && group < SNPG_MAX_GROUPS, SNPG_E_ARG, "group %d out of range", group);
     NEED(ctx, d_bases && n_seqs > 0 && n_seqs < ((uint64_t)1 << 31), SNPG_E_ARG, "bad alignment arguments");
@@ -744,94 +633,9 @@ int snpg_load_group_device(snpg_ctx *ctx, int group, const uint8_t *d_bases, uin
     return rc;
 }
 
-int snpg_read_fasta(snpg_ctx *ctx, int slot, const char *path, const uint8_t **bases, uint64_t *n_seqs, uint64_t *aln_len) {
-    if (!ctx || !path || !bases || !n_seqs || !aln_len) return SNPG_E_ARG;
-    NEED(ctx, slot >= 0 && slot < SNPG_MAX_GROUPS, SNPG_E_ARG, "slot %d out of range", slot);
-    if (int rc = bind(ctx)) return rc;
-    const int fd = open(path, O_RDONLY);
-    NEED(ctx, fd >= 0, SNPG_E_INPUT, "Could not open file %s", path);
-    struct stat st;
-    if (fstat(fd, &st) != 0 || st.st_size == 0) { close(fd); return fail(ctx, SNPG_E_INPUT, "%s is empty or unreadable", path); }
-    const size_t size = (size_t)st.st_size;
-    const char *f = static_cast<const char *>(mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0));
-    close(fd);
-    NEED(ctx, f != MAP_FAILED, SNPG_E_INPUT, "cannot map %s", path);
-    madvise(const_cast<char *>(f), size, MADV_SEQUENTIAL);
-    struct Unmap { const char *p; size_t n; ~Unmap() { munmap(const_cast<char *>(p), n); } } unmap{f, size};
-
-    // pass 1: count records and measure the first one
-    uint64_t n = 0, first_len = 0;
-    bool in_first = false;
-    for (size_t pos = 0; pos < size;) {
-        const char *nl = static_cast<const char *>(memchr(f + pos, '\n', size - pos));
-        const size_t end = nl ? (size_t)(nl - f) : size;
-        if (memchr(f + pos, '>', end - pos)) { n++; in_first = (n == 1); }
-        else if (in_first) first_len += end - pos;
-        pos = end + 1;
-    }
-    NEED(ctx, n > 0 && first_len > 0, SNPG_E_INPUT, "no FASTA records in %s", path);
-    auto &h = ctx->host_aln[slot];
-    const size_t need = (size_t)n * first_len;
-    if (need > h.cap) {
-        if (h.p) cudaFreeHost(h.p);
-        h.p = nullptr; h.cap = 0;
-        CU(ctx, cudaHostAlloc(reinterpret_cast<void **>(&h.p), need, cudaHostAllocDefault));
-        h.cap = need;
-    }
-    // pass 2: copy the data lines of each record into its row
-    uint64_t rec = 0, filled = 0;
-    bool started = false;
-    for (size_t pos = 0; pos < size;) {
-        const char *nl = static_cast<const char *>(memchr(f + pos, '\n', size - pos));
-        const size_t end = nl ? (size_t)(nl - f) : size;
-        if (memchr(f + pos, '>', end - pos)) {
-            if (started) {
-                NEED(ctx, filled == first_len, SNPG_E_INPUT, "The sequences must be aligned, i.e., must be the same length.");
-                rec++;
-            }
-            started = true;
-            filled = 0;
-        } else if (started) {
-            const size_t len = end - pos;
-            NEED(ctx, filled + len <= first_len, SNPG_E_INPUT, "The sequences must be aligned, i.e., must be the same length.");
-            memcpy(h.p + rec * first_len + filled, f + pos, len);
-            filled += len;
-        }
-        pos = end + 1;
-    }
-    NEED(ctx, filled == first_len, SNPG_E_INPUT, "The sequences must be aligned, i.e., must be the same length.");
-    h.n = n;
-    h.len = first_len;
-    *bases = h.p;
-    *n_seqs = n;
-    *aln_len = first_len;
-    return SNPG_OK;
-}
-
-int snpg_codon_strings(snpg_ctx *ctx, int slot, int product, int64_t codon, uint8_t *out) {
-    if (!ctx || !out) return SNPG_E_ARG;
-    NEED(ctx, slot >= 0 && slot < SNPG_MAX_GROUPS && ctx->host_aln[slot].p, SNPG_E_STATE, "no FASTA was read into slot %d", slot);
-    if (int rc = check_product(ctx, product)) return rc;
-    const int64_t C = ctx->full_ofs[product + 1] - ctx->full_ofs[product];
-    NEED(ctx, codon >= 0 && codon < C, SNPG_E_ARG, "codon %lld out of range", (long long)codon);
-    const auto &h = ctx->host_aln[slot];
-    NEED(ctx, (int64_t)h.len == ctx->aln_len, SNPG_E_INPUT, "slot %d has alignment length %llu, the annotation %lld", slot,
-         (unsigned long long)h.len, (long long)ctx->aln_len);
-    const CodonMap m = ctx->host_map[(size_t)(ctx->full_ofs[product] + codon)];
-    const int32_t pos[3] = {m.p0, m.p1, m.p2};
-    for (uint64_t s = 0; s < h.n; s++)
-        for (int k = 0; k < 3; k++) {
-            uint8_t c = h.p[s * h.len + (size_t)pos[k]];
-            if (c >= 'a' && c <= 'z') c = (uint8_t)(c - 32);
-            if (m.minus) c = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : c;   // fasta2revcom.pl:79
-            if (c == 'U') c = 'T';
-            out[3 * s + k] = c;
-        }
-    return SNPG_OK;
-}
-
 int snpg_drop_group(snpg_ctx *ctx, int group) {
     if (!ctx || group < 0 || group >= SNPG_MAX_GROUPS) return SNPG_E_ARG;
+    TEAM_EACH(ctx, snpg_drop_group(c, group));
     if (int rc = bind(ctx)) return rc;
     Group &g = ctx->groups[group];
     g.codes.release(); g.hist.release(); g.other.release(); g.sites.release();
@@ -840,6 +644,7 @@ int snpg_drop_group(snpg_ctx *ctx, int group) {
 }
 
 int snpg_group_size(const snpg_ctx *ctx, int group, uint64_t *n_seqs) {
+    if (is_team(ctx)) ctx = ctx->team[0];
     if (!ctx || group < 0 || group >= SNPG_MAX_GROUPS || !n_seqs || !ctx->groups[group].loaded) return SNPG_E_ARG;
     *n_seqs = ctx->groups[group].n;
     return SNPG_OK;
@@ -847,6 +652,7 @@ int snpg_group_size(const snpg_ctx *ctx, int group, uint64_t *n_seqs) {
 
 int snpg_get_codon_indices(snpg_ctx *ctx, int group, int product, uint8_t *out) {
     if (!ctx || !out) return SNPG_E_ARG;
+    TEAM_UNSUPPORTED(ctx, "snpg_get_codon_indices");
     if (int rc = check_group(ctx, group)) return rc;
     if (int rc = check_product(ctx, product)) return rc;
     if (int rc = bind(ctx)) return rc;
@@ -866,6 +672,14 @@ int snpg_get_codon_indices(snpg_ctx *ctx, int group, int product, uint8_t *out) 
 
 int snpg_get_hist(snpg_ctx *ctx, int group, int product, uint32_t *out, uint8_t *other_distinct) {
     if (!ctx || !out) return SNPG_E_ARG;
+    if (is_team(ctx)) {            // every child fills the codons of its range; product-local offsets follow the global axis
+        for (snpg_ctx *c : ctx->team) {
+            if (product < 0 || product >= c->n_products) return fail(ctx, SNPG_E_ARG, "product %d out of range", product);
+            const int64_t at = std::max<int64_t>(0, c->shard_first - c->full_ofs[product]);
+            if (int rc = snpg_get_hist(c, group, product, out + at * kHistBins, other_distinct ? other_distinct + at : nullptr)) return team_fail(ctx, c, rc);
+        }
+        return SNPG_OK;
+    }
     if (int rc = check_group(ctx, group)) return rc;
     if (int rc = check_product(ctx, product)) return rc;
     if (int rc = bind(ctx)) return rc;
@@ -890,6 +704,7 @@ int snpg_get_hist(snpg_ctx *ctx, int group, int product, uint32_t *out, uint8_t 
 
 int snpg_get_site_counts(snpg_ctx *ctx, int group, uint32_t *out) {
     if (!ctx || !out) return SNPG_E_ARG;
+    TEAM_UNSUPPORTED(ctx, "snpg_get_site_counts");
     if (int rc = check_group(ctx, group)) return rc;
     if (int rc = bind(ctx)) return rc;
     Group &g = ctx->groups[group];
@@ -919,7 +734,7 @@ static int run_stats(snpg_ctx *ctx, bool between, const Group &ga, const Group &
     {
         Launch l(ctx, SNPG_K_STATS);
         if (between) launch_between_stats(view_of(ctx, ga, c0), view_of(ctx, gb, c0), C, ctx->d_tables.as<double>(), o, ctx->stream);
-        else launch_within_stats(view_of(ctx, ga, c0), C, ctx->d_tables.as<double>(), o, ctx->stream);
+        else launch_within_stats(view_of(ctx, ga, c0), C, ctx->d_tables.as<double>(), o, nullptr, nullptr, ctx->stream);
     }
     CU(ctx, cudaGetLastError());
     if (poly) CU(ctx, cudaMemcpyAsync(poly, o.poly, (size_t)C, cudaMemcpyDeviceToHost, ctx->stream));
@@ -935,6 +750,16 @@ static int run_stats(snpg_ctx *ctx, bool between, const Group &ga, const Group &
 int snpg_within(snpg_ctx *ctx, int group, int product, uint8_t *poly, uint32_t *n_defined, uint64_t *comparisons,
                 double *stats4, uint8_t *conserved_code) {
     if (!ctx) return SNPG_E_ARG;
+    if (is_team(ctx)) {
+        for (snpg_ctx *c : ctx->team) {
+            if (product < 0 || product >= c->n_products) return fail(ctx, SNPG_E_ARG, "product %d out of range", product);
+            const int64_t at = std::max<int64_t>(0, c->shard_first - c->full_ofs[product]);
+            if (int rc = snpg_within(c, group, product, poly ? poly + at : nullptr, n_defined ? n_defined + at : nullptr,
+                                     comparisons ? comparisons + at : nullptr, stats4 ? stats4 + 4 * at : nullptr,
+                                     conserved_code ? conserved_code + at : nullptr)) return team_fail(ctx, c, rc);
+        }
+        return SNPG_OK;
+    }
     if (int rc = check_group(ctx, group)) return rc;
     if (int rc = check_product(ctx, product)) return rc;
     if (int rc = bind(ctx)) return rc;
@@ -947,6 +772,7 @@ int snpg_within(snpg_ctx *ctx, int group, int product, uint8_t *poly, uint32_t *
 int snpg_between(snpg_ctx *ctx, int group_a, int group_b, int product, uint8_t *poly, uint32_t *n_defined_a,
                  uint32_t *n_defined_b, uint64_t *comparisons, double *stats4, uint8_t *conserved_code) {
     if (!ctx) return SNPG_E_ARG;
+    TEAM_UNSUPPORTED(ctx, "snpg_between");
     if (int rc = check_group(ctx, group_a)) return rc;
     if (int rc = check_group(ctx, group_b)) return rc;
     if (int rc = check_product(ctx, product)) return rc;
@@ -971,10 +797,13 @@ static int upload_stats(snpg_ctx *ctx, const double *stats4, const uint8_t *keep
     return SNPG_OK;
 }
 
+static uint2 philox_key(const snpg_ctx *ctx) { return make_uint2((uint32_t)ctx->seed, (uint32_t)(ctx->seed >> 32)); }
+
 int snpg_bootstrap_product(snpg_ctx *ctx, const double *stats4, const uint8_t *keep, int64_t C, int64_t B, double *sums_out,
                            double *se_out) {
     if (!ctx) return SNPG_E_ARG;
-    NEED(ctx, stats4 && C > 0 && C < ((int64_t)1 << 31) - 1 && B >= 2, SNPG_E_ARG, "bad bootstrap arguments (C=%lld, B=%lld)",
+    TEAM_FORWARD0(ctx, snpg_bootstrap_product(c, stats4, keep, C, B, sums_out, se_out));
+    NEED(ctx, stats4 && C > 0 && C < ((int64_t)1 << 31) - 1 && B >= 2 && B < ((int64_t)1 << 36), SNPG_E_ARG, "bad bootstrap arguments (C=%lld, B=%lld)",
          (long long)C, (long long)B);
     if (int rc = bind(ctx)) return rc;
     if (int rc = upload_stats(ctx, stats4, keep, C)) return rc;
@@ -983,14 +812,16 @@ int snpg_bootstrap_product(snpg_ctx *ctx, const double *stats4, const uint8_t *k
     CU(ctx, cudaMemcpy(ctx->s_misc.p, ofs, sizeof ofs, cudaMemcpyHostToDevice));
     CU(ctx, ctx->s_rep.ensure(sizeof(double) * 4 * (size_t)B));
     CU(ctx, ctx->s_se.ensure(sizeof(double) * 6));
-    const uint32_t sid = 0x10000u + ctx->call_id++;
     CU(ctx, ctx->s_vals.ensure(sizeof(double) * 6 * (size_t)B));
     {
         Launch l(ctx, SNPG_K_BOOT);
-        launch_bootstrap(ctx->boot_kernel, ctx->s_in.as<double>(), ctx->s_misc.as<int64_t>(), nullptr, 1, C, 0, B, ctx->seed, sid, nullptr,
-                         sums_out ? ctx->s_rep.as<double>() : nullptr, ctx->s_vals.as<double>(), nullptr, ctx->stream);
+        BootArgs a;
+        a.stats4 = ctx->s_in.as<double>(); a.beg = ctx->s_misc.as<int64_t>(); a.end = a.beg + 1; a.n_items = 1; a.slot0 = ctx->boot_slot0;
+        a.b_count = B; a.key = philox_key(ctx); a.kind = kBootProduct; a.call = ctx->call_id++;
+        a.rep = sums_out ? ctx->s_rep.as<double>() : nullptr; a.vals = ctx->s_vals.as<double>();
+        launch_bootstrap(ctx->boot_kernel, a, C, ctx->stream);
     }
-    { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->s_vals.as<double>(), 1, B, ctx->s_se.as<double>(), ctx->stream); }
+    { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->s_vals.as<double>(), 1, B, ctx->s_se.as<double>(), nullptr, nullptr, ctx->stream); }
     CU(ctx, cudaGetLastError());
     if (sums_out) CU(ctx, cudaMemcpyAsync(sums_out, ctx->s_rep.p, sizeof(double) * 4 * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
     if (se_out) CU(ctx, cudaMemcpyAsync(se_out, ctx->s_se.p, sizeof(double) * 6, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1001,30 +832,48 @@ int snpg_bootstrap_product(snpg_ctx *ctx, const double *stats4, const uint8_t *k
 int snpg_windows(snpg_ctx *ctx, const double *stats4, const uint8_t *keep, int64_t C, int64_t W, int64_t step, int64_t B,
                  double *win_sums, double *win_se, int64_t *nwin_out) {
     if (!ctx) return SNPG_E_ARG;
+    TEAM_FORWARD0(ctx, snpg_windows(c, stats4, keep, C, W, step, B, win_sums, win_se, nwin_out));
     NEED(ctx, stats4 && C > 0 && W >= 1 && step >= 1, SNPG_E_ARG, "bad window arguments");
     NEED(ctx, W <= C, SNPG_E_INPUT, "not enough codons (%lld) for a sliding window of %lld", (long long)C, (long long)W);  // wgp:300
-    NEED(ctx, W < ((int64_t)1 << 31), SNPG_E_ARG, "window too large");
+    NEED(ctx, W < ((int64_t)1 << 31) && B < ((int64_t)1 << 36), SNPG_E_ARG, "window or replicate count too large");
     if (int rc = bind(ctx)) return rc;
     const int64_t nwin = (C - W) / step + 1;
+    NEED(ctx, nwin < ((int64_t)1 << 24), SNPG_E_ARG, "too many windows (%lld)", (long long)nwin);
     if (nwin_out) *nwin_out = nwin;
     if (!win_sums && !win_se) return SNPG_OK;
     if (int rc = upload_stats(ctx, stats4, keep, C)) return rc;
+    // window k = the item [k * step, k * step + W) of the uploaded table
+    std::vector<int64_t> be((size_t)(2 * nwin));
+    for (int64_t k = 0; k < nwin; k++) { be[(size_t)k] = k * step; be[(size_t)(nwin + k)] = k * step + W; }
+    CU(ctx, ctx->s_misc.ensure(sizeof(int64_t) * be.size()));
+    CU(ctx, cudaMemcpy(ctx->s_misc.p, be.data(), sizeof(int64_t) * be.size(), cudaMemcpyHostToDevice));
+    const int64_t *d_beg = ctx->s_misc.as<int64_t>(), *d_end = d_beg + nwin;
     if (win_sums) {
         CU(ctx, ctx->s_sums.ensure(sizeof(double) * 4 * (size_t)nwin));
-        { Launch l(ctx, SNPG_K_WINDOW); launch_window_sums(ctx->s_in.as<double>(), W, step, nwin, ctx->s_sums.as<double>(), ctx->stream); }
+        { Launch l(ctx, SNPG_K_WINDOW); launch_window_sums(ctx->s_in.as<double>(), d_beg, d_end, nwin, ctx->s_sums.as<double>(), ctx->stream); }
         CU(ctx, cudaGetLastError());
         CU(ctx, cudaMemcpyAsync(win_sums, ctx->s_sums.p, sizeof(double) * 4 * (size_t)nwin, cudaMemcpyDeviceToHost, ctx->stream));
     }
     if (win_se && B >= 2) {
-        const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(nwin, ((int64_t)256 << 20) / (32 * B)));
-        CU(ctx, ctx->s_rep.ensure(sizeof(double) * 4 * (size_t)(batch * B)));
+        // the window bootstrap (wgp:384-427; bgp:604-736) is the resampling kernel over window items: W draws uniform over
+        // the window's W codons.  Windows go out in batches that keep the per-replicate values under 256 MB.
+        const int64_t batch = std::max<int64_t>(1, std::min<int64_t>(nwin, ((int64_t)256 << 20) / (48 * B)));
+        CU(ctx, ctx->s_vals.ensure(sizeof(double) * 6 * (size_t)(batch * B)));
         CU(ctx, ctx->s_se.ensure(sizeof(double) * 6 * (size_t)batch));
         std::vector<double> se6((size_t)batch * 6);
-        const uint32_t sid = 0x20000u + ctx->call_id++;
+        const uint32_t call = ctx->call_id++;
         for (int64_t w0 = 0; w0 < nwin; w0 += batch) {
             const int64_t nb = std::min(batch, nwin - w0);
-            { Launch l(ctx, SNPG_K_WINDOW); launch_window_bootstrap(ctx->s_in.as<double>(), W, step, w0, nb, B, ctx->seed, sid, ctx->s_rep.as<double>(), ctx->stream); }
-            { Launch l(ctx, SNPG_K_MOMENTS); launch_moments(ctx->s_rep.as<double>(), nb, B, ctx->s_se.as<double>(), ctx->stream); }
+            {
+                Launch l(ctx, SNPG_K_WINDOW);
+                BootArgs a;
+                a.stats4 = ctx->s_in.as<double>(); a.beg = d_beg + w0; a.end = d_end + w0; a.n_items = (int)nb; a.slot0 = 0;
+                a.b_count = B; a.key = philox_key(ctx); a.kind = kBootWindow; a.call = call;
+                a.vals = ctx->s_vals.as<double>();
+                a.item0 = (uint32_t)w0;             // windows keep their own Philox streams whatever the batching
+                launch_bootstrap(ctx->boot_kernel, a, W, ctx->stream);
+            }
+            { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->s_vals.as<double>(), nb, B, ctx->s_se.as<double>(), nullptr, nullptr, ctx->stream); }
             CU(ctx, cudaGetLastError());
             CU(ctx, cudaMemcpyAsync(se6.data(), ctx->s_se.p, sizeof(double) * 6 * (size_t)nb, cudaMemcpyDeviceToHost, ctx->stream));
             CU(ctx, sync_stream(ctx));
@@ -1038,25 +887,32 @@ int snpg_windows(snpg_ctx *ctx, const double *stats4, const uint8_t *keep, int64
 
 int snpg_within_stats_device(snpg_ctx *ctx, int group, double *d_stats4) {
     if (!ctx || !d_stats4) return SNPG_E_ARG;
+    TEAM_UNSUPPORTED(ctx, "snpg_within_stats_device");
     if (int rc = check_group(ctx, group)) return rc;
     if (int rc = bind(ctx)) return rc;
     const Group &g = ctx->groups[group];
     StatsOut o{nullptr, nullptr, nullptr, nullptr, d_stats4, nullptr};
-    { Launch l(ctx, SNPG_K_STATS); launch_within_stats(view_of(ctx, g, 0), ctx->shard_count, ctx->d_tables.as<double>(), o, ctx->stream); }
+    { Launch l(ctx, SNPG_K_STATS); launch_within_stats(view_of(ctx, g, 0), ctx->shard_count, ctx->d_tables.as<double>(), o, nullptr, nullptr, ctx->stream); }
     CU(ctx, cudaGetLastError());
     CU(ctx, sync_stream(ctx));
     return SNPG_OK;
 }
 
+// (The Philox stream of this call does not depend on the ctx's call counter: ranks that split the replicates of one
+// analysis must draw from one stream whatever else they called before.  Repeated calls repeat the replicates.)
 int snpg_bootstrap_all_device(snpg_ctx *ctx, const double *d_stats4_full, int64_t b_first, int64_t b_count, double *d_rep_out) {
     if (!ctx || !d_stats4_full || !d_rep_out) return SNPG_E_ARG;
+    TEAM_UNSUPPORTED(ctx, "snpg_bootstrap_all_device");
     NEED(ctx, ctx->n_products > 0, SNPG_E_STATE, "no products set");
-    NEED(ctx, b_first >= 0 && b_count > 0, SNPG_E_ARG, "bad replicate range");
+    NEED(ctx, b_first >= 0 && b_count > 0 && b_first + b_count < ((int64_t)1 << 36), SNPG_E_ARG, "bad replicate range");
     if (int rc = bind(ctx)) return rc;
     {
         Launch l(ctx, SNPG_K_BOOT);
-        launch_bootstrap(ctx->boot_kernel, d_stats4_full, ctx->d_full_ofs.as<int64_t>(), ctx->d_order_full.as<int>(), ctx->n_products, ctx->max_codons_full,
-                         b_first, b_count, ctx->seed, 0x30000u, nullptr, d_rep_out, nullptr, nullptr, ctx->stream);
+        BootArgs a;
+        a.stats4 = d_stats4_full; a.beg = ctx->d_full_ofs.as<int64_t>(); a.end = a.beg + 1; a.order = ctx->d_order_full.as<int>();
+        a.n_items = ctx->n_products; a.slot0 = ctx->boot_slot0; a.b_first = b_first; a.b_count = b_count;
+        a.key = philox_key(ctx); a.kind = kBootAllDevice; a.call = 0; a.rep = d_rep_out;
+        launch_bootstrap(ctx->boot_kernel, a, ctx->max_codons_full, ctx->stream);
     }
     CU(ctx, cudaGetLastError());
     CU(ctx, sync_stream(ctx));
@@ -1065,6 +921,7 @@ int snpg_bootstrap_all_device(snpg_ctx *ctx, const double *d_stats4_full, int64_
 
 int snpg_product_sums_device(snpg_ctx *ctx, const double *d_stats4_full, double *prod_sums) {
     if (!ctx || !d_stats4_full || !prod_sums) return SNPG_E_ARG;
+    TEAM_UNSUPPORTED(ctx, "snpg_product_sums_device");
     NEED(ctx, ctx->n_products > 0, SNPG_E_STATE, "no products set");
     if (int rc = bind(ctx)) return rc;
     CU(ctx, ctx->s_sums.ensure(sizeof(double) * 4 * (size_t)ctx->n_products));
@@ -1077,6 +934,7 @@ int snpg_product_sums_device(snpg_ctx *ctx, const double *d_stats4_full, double 
 
 int snpg_rep_moments_device(snpg_ctx *ctx, const double *d_rep, int64_t n_items, int64_t B, double *se_out) {
     if (!ctx || !d_rep || !se_out || n_items <= 0 || B < 2) return SNPG_E_ARG;
+    TEAM_UNSUPPORTED(ctx, "snpg_rep_moments_device");
     if (int rc = bind(ctx)) return rc;
     CU(ctx, ctx->s_se.ensure(sizeof(double) * 6 * (size_t)n_items));
     { Launch l(ctx, SNPG_K_MOMENTS); launch_moments(d_rep, n_items, B, ctx->s_se.as<double>(), ctx->stream); }
@@ -1089,9 +947,11 @@ int snpg_rep_moments_device(snpg_ctx *ctx, const double *d_rep, int64_t n_items,
 int snpg_between_all(snpg_ctx *ctx, const int *groups, int n_groups, int64_t min_taxa_total, int64_t min_taxa_group, int64_t B,
                      double *pair_sums, double *pair_se) {
     if (!ctx) return SNPG_E_ARG;
+    TEAM_UNSUPPORTED(ctx, "snpg_between_all");
     NEED(ctx, groups && n_groups >= 2 && n_groups <= SNPG_MAX_GROUPS && pair_sums, SNPG_E_ARG, "bad between_all arguments");
     NEED(ctx, min_taxa_total >= 0 && min_taxa_group >= 0 && min_taxa_total < ((int64_t)1 << 32) && min_taxa_group < ((int64_t)1 << 32),
          SNPG_E_ARG, "bad min-taxa criteria");
+    NEED(ctx, B < ((int64_t)1 << 36), SNPG_E_ARG, "too many replicates");
     for (int i = 0; i < n_groups; i++)
         if (int rc = check_group(ctx, groups[i])) return rc;
     if (int rc = bind(ctx)) return rc;
@@ -1108,6 +968,7 @@ int snpg_between_all(snpg_ctx *ctx, const int *groups, int n_groups, int64_t min
         CU(ctx, ctx->s_vals.ensure(sizeof(double) * 6 * (size_t)(B * P)));
         CU(ctx, ctx->s_se.ensure(sizeof(double) * 6 * (size_t)(P * n_pairs)));
     }
+    const uint32_t call = ctx->call_id++;
     int pair = 0;
     for (int i = 0; i < n_groups; i++) {
         for (int j = i + 1; j < n_groups; j++, pair++) {
@@ -1124,11 +985,14 @@ int snpg_between_all(snpg_ctx *ctx, const int *groups, int n_groups, int64_t min
             if (boot) {
                 {
                     Launch l(ctx, SNPG_K_BOOT);      // also writes the product sums
-                    launch_bootstrap(ctx->boot_kernel, ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), ctx->d_order_local.as<int>(), P,
-                                     ctx->max_codons_local, 0, B, ctx->seed, 0x50000u + ctx->call_id++, nullptr, nullptr,
-                                     ctx->s_vals.as<double>(), d_pair_sums, ctx->stream);
+                    BootArgs a;
+                    a.stats4 = ctx->s_stats.as<double>(); a.beg = ctx->d_local_ofs.as<int64_t>(); a.end = a.beg + 1; a.order = ctx->d_order_local.as<int>();
+                    a.n_items = P; a.slot0 = ctx->boot_slot0; a.b_count = B; a.key = philox_key(ctx); a.kind = kBootBetween; a.call = call;
+                    a.item0 = (uint32_t)(pair * P);  // every (pair, product) its own stream
+                    a.vals = ctx->s_vals.as<double>(); a.prod_sums = d_pair_sums;
+                    launch_bootstrap(ctx->boot_kernel, a, ctx->max_codons_local, ctx->stream);
                 }
-                { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->s_vals.as<double>(), P, B, ctx->s_se.as<double>() + 6 * (size_t)P * pair, ctx->stream); }
+                { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->s_vals.as<double>(), P, B, ctx->s_se.as<double>() + 6 * (size_t)P * pair, nullptr, nullptr, ctx->stream); }
             }
         }
     }
@@ -1139,143 +1003,9 @@ int snpg_between_all(snpg_ctx *ctx, const int *groups, int n_groups, int64_t min
     return SNPG_OK;
 }
 
-// The whole within-group analysis of a loaded group, enqueued on ctx->stream.  final_sync = false and
-// d_salt != null is the form a CUDA graph captures: no host synchronisation, outputs into pinned memory, the
-// bootstrap's per-call stream number read from device memory when the graph runs.
-static int within_all_impl(snpg_ctx *ctx, int group, int64_t B, double *prod_sums, double *prod_se, bool final_sync,
-                           const uint32_t *d_salt) {
-    const Group &g = ctx->groups[group];
-    const int P = ctx->n_products;
-    const int64_t cnt = ctx->shard_count;
-    CU(ctx, ctx->s_stats.ensure(sizeof(double) * 4 * (size_t)std::max<int64_t>(1, cnt)));
-    CU(ctx, ctx->s_sums.ensure(sizeof(double) * 4 * (size_t)P));
-    StatsOut o{nullptr, nullptr, nullptr, nullptr, ctx->s_stats.as<double>(), nullptr};
-    if (ctx->stats_of != &g) { Launch l(ctx, SNPG_K_STATS); launch_within_stats(view_of(ctx, g, 0), cnt, ctx->d_tables.as<double>(), o, ctx->stream); }
-    ctx->stats_of = nullptr;         // (set by the load of a whole job: its fix-up kernel already wrote s_stats)
-    const bool boot = prod_se && B >= 2;
-    if (!boot) { Launch l(ctx, SNPG_K_SUMS); launch_product_sums(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), P, ctx->s_sums.as<double>(), ctx->stream); }
-    if (boot) {
-        CU(ctx, ctx->s_vals.ensure(sizeof(double) * 6 * (size_t)(B * P)));
-        CU(ctx, ctx->s_se.ensure(sizeof(double) * 6 * (size_t)P));
-        {
-            Launch l(ctx, SNPG_K_BOOT);
-            const uint32_t sid = d_salt ? 0x40000u : 0x40000u + ctx->call_id++;
-            launch_bootstrap(ctx->boot_kernel, ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), ctx->d_order_local.as<int>(), P,
-                             ctx->max_codons_local, 0, B, ctx->seed, sid, d_salt, nullptr, ctx->s_vals.as<double>(),
-                             ctx->s_sums.as<double>(), ctx->stream);      // also writes the product sums
-        }
-        { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->s_vals.as<double>(), P, B, ctx->s_se.as<double>(), ctx->stream); }
-    }
-    CU(ctx, cudaGetLastError());
-    if (prod_sums) CU(ctx, cudaMemcpyAsync(prod_sums, ctx->s_sums.p, sizeof(double) * 4 * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
-    if (boot) CU(ctx, cudaMemcpyAsync(prod_se, ctx->s_se.p, sizeof(double) * 6 * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
-    if (final_sync) CU(ctx, sync_stream(ctx));
-    return SNPG_OK;
-}
-
-int snpg_within_all(snpg_ctx *ctx, int group, int64_t B, double *prod_sums, double *prod_se) {
-    if (!ctx) return SNPG_E_ARG;
-    if (int rc = check_group(ctx, group)) return rc;
-    if (int rc = bind(ctx)) return rc;
-    return within_all_impl(ctx, group, B, prod_sums, prod_se, true, nullptr);
-}
-
-static void drop_job_graph(snpg_ctx *ctx) { invalidate_job_graph(ctx); }
-
-// Captures the job (load + analysis) into a CUDA graph and runs it once.  Any failure leaves no graph behind
-// and reports SNPG_E_STATE so that the caller runs the job the ordinary way.
-static int capture_job_graph(snpg_ctx *ctx, const snpg_ctx::JobKey &key, int64_t B) {
-    auto &J = ctx->job;
-    const int P = ctx->n_products;
-    if (!J.h_salt && cudaMallocHost(reinterpret_cast<void **>(&J.h_salt), sizeof(uint32_t)) != cudaSuccess) return SNPG_E_STATE;
-    if (J.h_out_products < P) {
-        if (J.h_out) cudaFreeHost(J.h_out);
-        J.h_out = nullptr;
-        if (cudaMallocHost(reinterpret_cast<void **>(&J.h_out), sizeof(double) * 10 * (size_t)P) != cudaSuccess) return SNPG_E_STATE;
-        J.h_out_products = P;
-    }
-    if (ctx->d_salt.ensure(sizeof(uint32_t)) != cudaSuccess) return SNPG_E_STATE;
-    const uint64_t epoch0 = g_alloc_epoch;
-    const int64_t l0 = ctx->launches, t0 = ctx->tile_launches;
-    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return SNPG_E_STATE; }
-    ctx->capturing = true;
-    int rc = SNPG_OK;
-    if (cudaMemcpyAsync(ctx->d_salt.p, J.h_salt, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = SNPG_E_CUDA;
-    if (rc == SNPG_OK) {
-        ctx->defer_load_sync = true;
-        rc = snpg_load_group_device(ctx, key.group, key.bases, key.n, key.len, key.stride);
-        ctx->defer_load_sync = false;
-    }
-    if (rc == SNPG_OK) rc = within_all_impl(ctx, key.group, B, J.h_out, key.want_se ? J.h_out + 4 * P : nullptr, false, ctx->d_salt.as<uint32_t>());
-    ctx->capturing = false;
-    cudaGraph_t graph = nullptr;
-    const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
-    cudaGraphExec_t exec = nullptr;
-    if (rc == SNPG_OK && e == cudaSuccess && graph && epoch0 == g_alloc_epoch && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
-        J.exec = exec;
-        J.key = key;
-        J.epoch = g_alloc_epoch;
-        J.n_launches = ctx->launches - l0;
-        J.n_tile_launches = ctx->tile_launches - t0;
-    } else {
-        rc = SNPG_E_STATE;
-        cudaGetLastError();
-    }
-    if (graph) cudaGraphDestroy(graph);
-    ctx->launches = l0;                 // nothing ran yet: the replay below counts them
-    ctx->tile_launches = t0;
-    return rc;
-}
-
-int snpg_within_job(snpg_ctx *ctx, int group, const uint8_t *bases, int bases_on_device, uint64_t n_seqs, uint64_t aln_len,
-                    uint64_t row_stride, int64_t B, double *prod_sums, double *prod_se) {
-    if (!ctx) return SNPG_E_ARG;
-    auto &J = ctx->job;
-    snpg_ctx::JobKey key;
-    key.group = group; key.bases = bases; key.n = n_seqs; key.len = aln_len; key.stride = row_stride; key.B = B;
-    key.keep_codes = ctx->keep_codes; key.site_counts = ctx->site_counts; key.want_se = prod_se != nullptr; key.fused_kernel = ctx->fused_kernel;
-    static const bool graphs_on = getenv("SNPG_NO_GRAPH") == nullptr;
-    key.profile_mask = ctx->profile_mask;
-    const bool eligible = graphs_on && bases_on_device && bases && prod_sums && !J.disabled &&
-                          group >= 0 && group < SNPG_MAX_GROUPS && ctx->n_products > 0;
-    if (eligible) {
-        if (int rc = bind(ctx)) return rc;
-        if (J.exec && (!(J.key == key) || J.epoch != g_alloc_epoch)) drop_job_graph(ctx);
-        if (!J.exec && J.candidate == key && J.candidate_epoch == g_alloc_epoch) {
-            // the same job for the second time in a row with every buffer already in place: capture it
-            if (capture_job_graph(ctx, key, B) != SNPG_OK) { drop_job_graph(ctx); J.disabled = true; }
-        }
-        if (J.exec) {
-            const int P = ctx->n_products;
-            *J.h_salt = ctx->call_id++;
-            CU(ctx, cudaGraphLaunch(J.exec, ctx->stream));
-            CU(ctx, sync_stream(ctx));
-            ctx->launches += J.n_launches;
-            ctx->tile_launches += J.n_tile_launches;
-            J.replays++;
-            for (auto &sp : J.spans) {
-                float ms = 0;
-                if (cudaEventElapsedTime(&ms, sp.e0, sp.e1) == cudaSuccess) { ctx->kernel_ms[sp.kind] += ms; ctx->kernel_calls[sp.kind]++; }
-            }
-            memcpy(prod_sums, J.h_out, sizeof(double) * 4 * (size_t)P);
-            if (prod_se) memcpy(prod_se, J.h_out + 4 * P, sizeof(double) * 6 * (size_t)P);
-            return SNPG_OK;
-        }
-    }
-    ctx->defer_load_sync = true;     // one synchronisation for the whole job, at the end of the analysis
-    int rc = bases_on_device ? snpg_load_group_device(ctx, group, bases, n_seqs, aln_len, row_stride)
-                             : snpg_load_group(ctx, group, bases, n_seqs, aln_len, row_stride);
-    ctx->defer_load_sync = false;
-    if (rc != SNPG_OK) { ctx->stats_of = nullptr; sync_stream(ctx); return rc; }
-    rc = snpg_within_all(ctx, group, B, prod_sums, prod_se);
-    if (eligible && rc == SNPG_OK) { J.candidate = key; J.candidate_epoch = g_alloc_epoch; }
-    return rc;
-}
-
-int64_t snpg_graph_replays(const snpg_ctx *ctx) { return ctx ? ctx->job.replays : 0; }
-
 int snpg_test_philox(snpg_ctx *ctx, const uint32_t *ctr4, const uint32_t *key2, uint32_t *out4) {
     if (!ctx || !ctr4 || !key2 || !out4) return SNPG_E_ARG;
+    TEAM_FORWARD0(ctx, snpg_test_philox(c, ctr4, key2, out4));
     if (int rc = bind(ctx)) return rc;
     CU(ctx, ctx->s_misc.ensure(16));
     { Launch l(ctx, SNPG_K_OTHER); launch_philox_kat(ctr4, key2, ctx->s_misc.as<uint32_t>(), ctx->stream); }
@@ -1285,11 +1015,29 @@ int snpg_test_philox(snpg_ctx *ctx, const uint32_t *ctr4, const uint32_t *key2, 
     return SNPG_OK;
 }
 
-int64_t snpg_launch_count(const snpg_ctx *ctx) { return ctx ? ctx->launches : 0; }
-int64_t snpg_tile_launch_count(const snpg_ctx *ctx) { return ctx ? ctx->tile_launches : 0; }
+int snpg_staged_columns(const snpg_ctx *ctx, int64_t *first_col, int64_t *n_cols) {
+    if (!ctx || is_team(ctx) || ctx->n_products == 0) return SNPG_E_STATE;
+    if (first_col) *first_col = ctx->base_al;
+    if (n_cols) *n_cols = ctx->shard_count > 0 ? ctx->col_hi - ctx->base_al : 0;
+    return SNPG_OK;
+}
+
+int64_t snpg_launch_count(const snpg_ctx *ctx) {
+    if (!ctx) return 0;
+    int64_t n = ctx->launches;
+    for (const snpg_ctx *c : ctx->team) n += c->launches;
+    return n;
+}
+int64_t snpg_tile_launch_count(const snpg_ctx *ctx) {
+    if (!ctx) return 0;
+    int64_t n = ctx->tile_launches;
+    for (const snpg_ctx *c : ctx->team) n += c->tile_launches;
+    return n;
+}
 
 int snpg_set_stream(snpg_ctx *ctx, void *cuda_stream) {
     if (!ctx) return SNPG_E_ARG;
+    TEAM_UNSUPPORTED(ctx, "snpg_set_stream");
     if (int rc = bind(ctx)) return rc;
     CU(ctx, sync_stream(ctx));
     invalidate_job_graph(ctx);
@@ -1301,6 +1049,7 @@ int snpg_set_stream(snpg_ctx *ctx, void *cuda_stream) {
 
 int snpg_get_profile(snpg_ctx *ctx, double *ms, int64_t *calls, int reset) {
     if (!ctx) return SNPG_E_ARG;
+    TEAM_FORWARD0(ctx, snpg_get_profile(c, ms, calls, reset));
     for (int k = 0; k < SNPG_N_KERNEL_KINDS; k++) {
         if (ms) ms[k] = ctx->kernel_ms[k];
         if (calls) calls[k] = ctx->kernel_calls[k];

@@ -19,6 +19,7 @@
 #include "snpg_device.cuh"
 #include "../../include/snpgenie_cuda.h"
 #include "snpg_internal.h"
+#include "snpg_peer.cuh"
 
 namespace snpg {
 
@@ -725,10 +726,9 @@ __device__ __forceinline__ int first_defined_code(const uint8_t *col, int64_t n,
 // One codon, one warp.  s_bin/s_ca/s_cb: kStatsWarps x 64 entries of shared scratch, row `warp` is this warp's.
 template <bool BETWEEN>
 __device__ __forceinline__ void stats_codon(const GroupView &A, const GroupView &B, int64_t c, const double *__restrict__ tables,
-                                            const StatsOut &out, int lane, int warp, int (*s_bin)[64], double (*s_ca)[64],
+                                            const StatsOut &out, const PeerOut &po, int lane, int warp, int (*s_bin)[64], double (*s_ca)[64],
                                             double (*s_cb)[64], const uint32_t *bins = nullptr)
 {
-
     const double *sites = tables;            // [64][2]
     const double *TN = tables + 128;         // [64][64]
     const double *TS = tables + 128 + 4096;
@@ -850,19 +850,32 @@ __device__ __forceinline__ void stats_codon(const GroupView &A, const GroupView 
             o[1] = make_double2(r_nd, r_sd);
         }
     }
+    // multi-GPU: the same values straight into every rank's exchange region (the all-gather of SURVEY.md 8e as the
+    // tail of the producing kernel); lane r serves rank r
+    if (po.world > 1 && lane < po.world) {
+        const int64_t g = po.first + c;
+        double2 *o = reinterpret_cast<double2 *>(po.stats4[lane] + 4 * g);
+        o[0] = make_double2(r_ns, r_ss);
+        o[1] = make_double2(r_nd, r_sd);
+        po.cmp[lane][g] = cmp;
+        po.ndef[lane][g] = na_u;
+        po.poly[lane][g] = poly ? 1 : 0;
+        po.cons[lane][g] = (uint8_t)(poly ? kCodeUndef : conserved);
+    }
 }
 
 template <bool BETWEEN>
 __global__ void __launch_bounds__(kStatsWarps * 32)
-k_stats(GroupView A, GroupView B, int64_t n_codons, const double *__restrict__ tables, StatsOut out)
+k_stats(GroupView A, GroupView B, int64_t n_codons, const double *__restrict__ tables, StatsOut out,
+        const __grid_constant__ PeerOut po, const __grid_constant__ PeerSync ps)
 {
     __shared__ int s_bin[kStatsWarps][64];
     __shared__ double s_ca[kStatsWarps][64];
     __shared__ double s_cb[kStatsWarps][64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t c = (int64_t)blockIdx.x * kStatsWarps + warp;
-    if (c >= n_codons) return;
-    stats_codon<BETWEEN>(A, B, c, tables, out, lane, warp, s_bin, s_ca, s_cb);
+    if (c < n_codons) stats_codon<BETWEEN>(A, B, c, tables, out, po, lane, warp, s_bin, s_ca, s_cb);
+    peer_signal(ps, kStageStats);
 }
 
 // k_fused_fixup followed, codon by codon, by the within-group statistics (K3): one launch less for a whole job
@@ -870,7 +883,8 @@ k_stats(GroupView A, GroupView B, int64_t n_codons, const double *__restrict__ t
 __global__ void __launch_bounds__(kStatsWarps * 32)
 k_fused_fixup_stats(const uint8_t *__restrict__ cons, int64_t cons_shift, const uint32_t *__restrict__ alt, const CodonMap *__restrict__ map,
                     int64_t n_codons, uint32_t n_rows, uint32_t *__restrict__ hist, uint32_t *__restrict__ other_min,
-                    uint32_t *__restrict__ other_max, GroupView A, const double *__restrict__ tables, StatsOut out)
+                    uint32_t *__restrict__ other_max, GroupView A, const double *__restrict__ tables, StatsOut out,
+                    const __grid_constant__ PeerOut po, const __grid_constant__ PeerSync ps)
 {
     static_assert(kStatsWarps * 32 == 256, "the fix-up addresses codons by 256-thread blocks");
     __shared__ int s_bin[kStatsWarps][64];
@@ -878,12 +892,19 @@ k_fused_fixup_stats(const uint8_t *__restrict__ cons, int64_t cons_shift, const 
     __shared__ double s_cb[kStatsWarps][64];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t c = (int64_t)blockIdx.x * kStatsWarps + warp;
-    if (c >= n_codons) return;
-    uint32_t bins[3];
-    fixup_codon_regs(cons, cons_shift, alt, map, c, n_rows, hist, other_min, other_max, lane, bins);
-    __syncwarp();                                  // lane 0's 'other' keys are visible to the warp
-    stats_codon<false>(A, A, c, tables, out, lane, warp, s_bin, s_ca, s_cb, bins);
+    if (c < n_codons) {
+        uint32_t bins[3];
+        fixup_codon_regs(cons, cons_shift, alt, map, c, n_rows, hist, other_min, other_max, lane, bins);
+        __syncwarp();                              // lane 0's 'other' keys are visible to the warp
+        stats_codon<false>(A, A, c, tables, out, po, lane, warp, s_bin, s_ca, s_cb, bins);
+    }
+    peer_signal(ps, kStageStats);
 }
+
+__global__ void k_peer_signal(const __grid_constant__ PeerSync ps, int stage) { peer_signal(ps, stage); }
+// for consumers that cannot wait themselves (copies, kernels that know nothing about peers): everything behind this
+// kernel in its stream sees the stage's data
+__global__ void k_peer_wait(const __grid_constant__ PeerSync ps, int stage) { peer_wait(ps, stage); }
 
 // min-taxa codon filters of the between-group processor (bgp:412-467, :929-970): a codon that fails them
 // contributes nothing to the sums, the windows or a bootstrap draw -- its row is zeroed in place.
@@ -979,6 +1000,25 @@ constexpr int kBootWarps = 32;
 constexpr int kBootRepsPerWarp = 2;
 constexpr int kBootSmemLimit = 200 * 1024;
 
+// Philox counter of one quad of draws: x = quad index inside the replicate, y and 4 bits of z = replicate number
+// (< 2^36), z also carries the item (product or window, < 2^24) and the KIND of call (product bootstrap, window
+// bootstrap, between-group pair ...) in its top four bits, w = the ctx's call counter.  Calls of different kinds can
+// therefore never share a stream, whatever the number of calls.
+__device__ __forceinline__ uint4 boot_counter(uint32_t q, uint64_t b, uint32_t item, uint32_t kind, uint32_t call) {
+    return make_uint4(q, (uint32_t)b, (kind << 28) | (((uint32_t)(b >> 32) & 0xFu) << 24) | (item & 0xFFFFFFu), call);
+}
+
+// One per-replicate value into vals[which][item][B] -- on several GPUs into every rank's exchange region (the gather
+// of the replicate ranges is the tail of the kernel that draws them).
+__device__ __forceinline__ void put_val(const BootArgs &a, int which, int item, int64_t bl, double v) {
+    const size_t idx = ((size_t)which * a.n_items + item) * a.vals_stride + a.vals_b0 + bl;
+    if (a.pv.world > 1) {
+        for (int r = 0; r < a.pv.world; r++) a.pv.vals[r][idx] = v;
+    } else {
+        a.vals[idx] = v;
+    }
+}
+
 // (A banked two-stage sampler -- class counts per shared-memory bank group first, then conflict-free draws inside
 // the lane's class; exact, 49 M -> 30 M wavefronts -- was measured at 226 us against 212 us for the direct draws
 // below: its extra instructions cost more than the conflicts.  So did a two-table form -- a 4-byte class word per
@@ -987,36 +1027,36 @@ constexpr int kBootSmemLimit = 200 * 1024;
 // See profiles/README.md and the git history.)
 template <bool SMEM>
 __global__ void __launch_bounds__(kBootWarps * 32)
-k_bootstrap(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, const int *__restrict__ order, int n_products,
-            int64_t b_first, int64_t b_count, uint2 key, uint32_t stream_id, const uint32_t *__restrict__ salt,
-            double *__restrict__ rep, double *__restrict__ vals, double *__restrict__ prod_sums)
+k_bootstrap(const __grid_constant__ BootArgs a)
 {
     extern __shared__ double2 s_tab[];
-    if (salt) stream_id += *salt;      // a replayed CUDA graph gets its per-call stream number from memory
+    const uint32_t call = a.call + (a.salt ? *a.salt : 0u);      // a replayed CUDA graph gets its per-call number from memory
     __shared__ double2 s_sums[kBootWarps * kBootRepsPerWarp][2];     // the block's replicate sums, for the dense epilogue
     __shared__ double s_red[SMEM ? kBootWarps * 32 : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int p = order ? order[blockIdx.y] : blockIdx.y;
-    const int64_t c0 = ofs[p];
-    const uint32_t C = (uint32_t)(ofs[p + 1] - c0);
-    const double2 *G = reinterpret_cast<const double2 *>(stats4 + 4 * c0);
-    // shared table rows 0..C: row 0 is the empty slot, row r is codon r
+    const int p = a.order ? a.order[blockIdx.y] : blockIdx.y;
+    peer_wait(a.ps, kStageStats);
+    const int64_t c0 = a.beg[p];
+    const uint32_t C = (uint32_t)(a.end[p] - c0);
+    const uint32_t s0 = (uint32_t)a.slot0, n_slots = C + s0;
+    const double2 *G = reinterpret_cast<const double2 *>(a.stats4 + 4 * c0);
+    // shared table rows 0..n_slots-1: with slot0 row 0 is the empty slot and row r is codon r - 1
     double2 *A = s_tab, *D = s_tab + (C + 1);
     if (SMEM) {
         if (threadIdx.x == 0) { A[0] = make_double2(0.0, 0.0); D[0] = make_double2(0.0, 0.0); }
         for (uint32_t i = threadIdx.x; i < C; i += blockDim.x) {
-            double2 a = G[2 * i];
+            double2 x = G[2 * i];
             const double2 d = G[2 * i + 1];
-            if (d.x != 0.0 || d.y != 0.0) a.x = -a.x;        // flag: this codon has differences (-0.0 also carries it)
-            A[i + 1] = a;
-            D[i + 1] = d;
+            if (d.x != 0.0 || d.y != 0.0) x.x = -x.x;        // flag: this codon has differences (-0.0 also carries it)
+            A[i + s0] = x;
+            D[i + s0] = d;
         }
         __syncthreads();
-        if (prod_sums && blockIdx.x == 0) {
+        if (a.prod_sums && blockIdx.x == 0) {
             // the product's sums (wg:690-693), from the staged table: the additions and the tree of k_product_sums
             double s[4] = {0, 0, 0, 0};
             for (uint32_t c = threadIdx.x; c < C; c += blockDim.x) {
-                const double2 x = A[c + 1], y = D[c + 1];
+                const double2 x = A[c + s0], y = D[c + s0];
                 s[0] += fabs(x.x); s[1] += x.y; s[2] += y.x; s[3] += y.y;
             }
             for (int q = 0; q < 4; q++) {
@@ -1026,7 +1066,7 @@ k_bootstrap(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, 
                     if ((int)threadIdx.x < h) s_red[threadIdx.x] += s_red[threadIdx.x + h];
                     __syncthreads();
                 }
-                if (threadIdx.x == 0) prod_sums[4 * p + q] = s_red[0];
+                if (threadIdx.x == 0) a.prod_sums[4 * p + q] = s_red[0];
                 __syncthreads();
             }
         }
@@ -1034,44 +1074,45 @@ k_bootstrap(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, 
     const uint32_t nquad = (C + 3) >> 2, full_quads = C >> 2;
     for (int k = 0; k < kBootRepsPerWarp; k++) {
         const int64_t bl = ((int64_t)blockIdx.x * kBootWarps + warp) * kBootRepsPerWarp + k;
-        if (bl >= b_count) continue;
-        const uint64_t b = (uint64_t)(b_first + bl);
-        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        if (bl >= a.b_count) continue;
+        const uint64_t b = (uint64_t)(a.b_first + bl);
+        double s0_ = 0, s1 = 0, s2 = 0, s3 = 0;
         for (uint32_t q = lane; q < nquad; q += 32) {
-            const uint4 u = philox4x32_10(make_uint4(q, (uint32_t)b, (uint32_t)(b >> 32) ^ ((uint32_t)p << 8), stream_id), key);
+            const uint4 u = philox4x32_10(boot_counter(q, b, (uint32_t)p + a.item0, a.kind, call), a.key);
             const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
             const int nd = q < full_quads ? 4 : (int)(C & 3);
             uint32_t r[4];
+            bool live[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) r[j] = j < nd ? __umulhi(uu[j], C + 1) : 0u;     // slot 0 adds nothing
+            for (int j = 0; j < 4; j++) { live[j] = j < nd; r[j] = live[j] ? __umulhi(uu[j], n_slots) : 0u; }
             if (SMEM) {
                 // all gathers of the quad are issued before any is consumed
-                double2 a[4], d[4];
+                double2 x[4], d[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) a[j] = A[r[j]];
+                for (int j = 0; j < 4; j++) x[j] = live[j] ? A[r[j]] : make_double2(0.0, 0.0);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     d[j] = make_double2(0.0, 0.0);
-                    if (__double2hiint(a[j].x) < 0) d[j] = D[r[j]];
+                    if (__double2hiint(x[j].x) < 0) d[j] = D[r[j]];
                 }
-                s0 += (fabs(a[0].x) + fabs(a[1].x)) + (fabs(a[2].x) + fabs(a[3].x));
-                s1 += (a[0].y + a[1].y) + (a[2].y + a[3].y);
+                s0_ += (fabs(x[0].x) + fabs(x[1].x)) + (fabs(x[2].x) + fabs(x[3].x));
+                s1 += (x[0].y + x[1].y) + (x[2].y + x[3].y);
                 s2 += (d[0].x + d[1].x) + (d[2].x + d[3].x);
                 s3 += (d[0].y + d[1].y) + (d[2].y + d[3].y);
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    if (r[j]) {
-                        const double2 a = __ldg(G + 2 * (size_t)(r[j] - 1));
-                        const double2 d = __ldg(G + 2 * (size_t)(r[j] - 1) + 1);
-                        s0 += a.x; s1 += a.y; s2 += d.x; s3 += d.y;
+                    if (live[j] && r[j] >= s0) {
+                        const double2 x = __ldg(G + 2 * (size_t)(r[j] - s0));
+                        const double2 d = __ldg(G + 2 * (size_t)(r[j] - s0) + 1);
+                        s0_ += x.x; s1 += x.y; s2 += d.x; s3 += d.y;
                     }
                 }
             }
         }
-        s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+        s0_ = warp_sum(s0_); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
         if (lane == 0) {
-            s_sums[warp * kBootRepsPerWarp + k][0] = make_double2(s0, s1);
+            s_sums[warp * kBootRepsPerWarp + k][0] = make_double2(s0_, s1);
             s_sums[warp * kBootRepsPerWarp + k][1] = make_double2(s2, s3);
         }
     }
@@ -1082,15 +1123,16 @@ k_bootstrap(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, 
     constexpr int kReps = kBootWarps * kBootRepsPerWarp;
     const int i = threadIdx.x, r = i % kReps, which = i / kReps;
     const int64_t bl = (int64_t)blockIdx.x * kReps + r;
-    if (which < 6 && bl < b_count) {
+    if (which < 6 && bl < a.b_count) {
         const double2 x = s_sums[r][0], y = s_sums[r][1];
-        if (rep && which == 0) {
-            double2 *o = reinterpret_cast<double2 *>(rep + 4 * ((size_t)p * b_count + bl));
+        if (a.rep && which == 0) {
+            double2 *o = reinterpret_cast<double2 *>(a.rep + 4 * ((size_t)p * a.b_count + bl));
             o[0] = x;
             o[1] = y;
         }
-        if (vals) vals[((size_t)which * n_products + p) * b_count + bl] = rep_value(x.x, x.y, y.x, y.y, which);
+        if (a.vals || a.pv.world > 1) put_val(a, which, p, bl, rep_value(x.x, x.y, y.x, y.y, which));
     }
+    peer_signal(a.ps, kStageVals);
 }
 
 // K4, weight-matrix form (the default when a warp's counts fit in shared memory): the contraction
@@ -1104,6 +1146,10 @@ k_bootstrap(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, 
 // Same Philox stream, draw for draw, as the direct form; replicate sums agree to rounding.  A counter would wrap at
 // 256 draws of one slot in one replicate: impossible up to C = 255 and of probability < 1e-400 beyond
 // (each of the C draws picks the slot with probability 1/(C+1)).
+// Items are products (beg = ofs, end = ofs + 1; slot0 = 1: the reference's whole-product bootstrap draws
+// int(rand(C+1)), wg:885, and its codon 0 does not exist) or sliding windows (overlapping ranges, slot0 = 0:
+// int(rand(W)) + first_codon, wgp:406).  On several GPUs the sampling of the first batch runs before the block waits
+// for the peers' per-codon statistics -- only the contraction reads them.
 constexpr int kBootKSplit = 8;                     // warps sharing the slots of one group of 8 replicates (one row per warp)
 constexpr int kBootMaxRows = 8;                    // replicates a warp takes at a time when the product is short
 // Several blocks of kMmaWarps warps share an SM (five for config 2's largest product, at 48 registers a thread): while
@@ -1117,24 +1163,129 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
 }
 
 __global__ void __launch_bounds__(kMmaWarps * 32, 5)
-k_bootstrap_mma(const double *__restrict__ stats4, const int64_t *__restrict__ ofs, const int *__restrict__ order, int n_products,
-                int64_t b_first, int64_t b_count, uint2 key, uint32_t stream_id, const uint32_t *__restrict__ salt,
-                double *__restrict__ rep, double *__restrict__ vals, double *__restrict__ prod_sums, uint32_t row_words)
+k_bootstrap_mma(const __grid_constant__ BootArgs a, uint32_t row_words)
 {
     extern __shared__ uint32_t s_cnt[];            // [kMmaWarps][row_words]: 1-byte counters, four to a word
-    if (salt) stream_id += *salt;      // a replayed CUDA graph gets its per-call stream number from memory
+    const uint32_t call = a.call + (a.salt ? *a.salt : 0u);      // a replayed CUDA graph gets its per-call number from memory
     __shared__ double2 s_sums[kMmaWarps * kBootMaxRows][2];         // a batch's replicate sums, for the dense epilogue
     __shared__ double s_part[kBootKSplit][kMmaWarps][4];            // per K-split partial sums of a batch; also the reduction scratch
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int p = order ? order[blockIdx.y] : blockIdx.y;
-    const int64_t c0 = ofs[p];
-    const uint32_t C = (uint32_t)(ofs[p + 1] - c0);
-    const double *G = stats4 + 4 * c0;
-    if (prod_sums && blockIdx.x == 0) {
+    const int p = a.order ? a.order[blockIdx.y] : blockIdx.y;
+    const int64_t c0 = a.beg[p];
+    const uint32_t C = (uint32_t)(a.end[p] - c0);
+    const uint32_t s0 = (uint32_t)a.slot0, n_slots = C + s0;
+    const double *G = a.stats4 + 4 * c0;
+    const uint32_t nquad = (C + 3) >> 2, full_quads = C >> 2;     // the partial quad, if any, is quad full_quads
+    const uint32_t nslot4 = (n_slots + 3) >> 2;    // groups of 4 slots
+    // A short product does not fill a warp's counters: its warps then take m = 2, 4 or 8 replicates at a time (32 / m
+    // lanes and one row of rw words each), so that the fixed cost of a batch is spread over 32 m replicates.
+    const uint32_t rw = nslot4 | 1;                // words per row: odd, so the eight rows of a tile fall in different banks
+    uint32_t lm = 0;                               // m = 1 << lm: every count below is a power of two, divisions are shifts
+    while ((2u << lm) <= kBootMaxRows && (2u << lm) * rw <= row_words) lm++;
+    const uint32_t m = 1u << lm;
+    constexpr uint32_t kLogWarps = kMmaWarps == 16 ? 4 : kMmaWarps == 8 ? 3 : 5;
+    static_assert((1u << kLogWarps) == kMmaWarps, "kMmaWarps must be 8, 16 or 32");
+    const uint32_t lrows = kLogWarps + lm;         // log2 of the replicates per batch
+    const uint32_t rows = 1u << lrows;             // replicates per batch
+    const uint32_t n_batch = m >= kBootRepsPerWarp ? 1 : kBootRepsPerWarp >> lm;
+    const int64_t block_first = (int64_t)blockIdx.x * rows * n_batch;
+    const bool active = block_first < a.b_count;   // the grid is sized for m = 1
+    const uint32_t lanes_per = 32u >> lm, sub = lane >> (5 - lm), sl = lane & (lanes_per - 1);
+    uint32_t *warp_rows = s_cnt + (size_t)warp * m * rw;
+    const uint32_t mine_s = (uint32_t)__cvta_generic_to_shared(warp_rows + (size_t)sub * rw);
+    double *part = &s_part[0][0][0];               // [ksplit][rows][4], ksplit * rows = 8 * kMmaWarps
+    for (uint32_t k = 0; active && k < n_batch; k++) {
+        const int64_t batch_first = block_first + (int64_t)k * rows;
+        // --- sampling: one replicate per group of 32 / m lanes -> its row of counts
+        for (uint32_t i = lane; i < m * rw; i += 32) warp_rows[i] = 0;
+        __syncwarp();
+        const int64_t bl = batch_first + warp * m + sub;
+        if (bl < a.b_count) {
+            const uint64_t b = (uint64_t)(a.b_first + bl);
+            auto bump = [&](uint32_t u) {          // one draw: slot = floor(u * n_slots / 2^32); its byte of the row goes up by one
+                const uint32_t r = __umulhi(u, n_slots);
+                // 1 << 8 * (r & 3): a funnel shift takes its count modulo 32, so r << 3 needs no mask
+                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(mine_s + (r & ~3u)), "r"(__funnelshift_l(0u, 1u, r << 3)) : "memory");
+            };
+            uint32_t q = sl;
+            for (; q < full_quads; q += lanes_per) {
+                const uint4 u = philox4x32_10(boot_counter(q, b, (uint32_t)p + a.item0, a.kind, call), a.key);
+                bump(u.x); bump(u.y); bump(u.z); bump(u.w);
+            }
+            if (q < nquad) {                       // the last, partial quad (one lane)
+                const uint4 u = philox4x32_10(boot_counter(q, b, (uint32_t)p + a.item0, a.kind, call), a.key);
+                const uint32_t nd = C & 3;
+                bump(u.x);
+                if (nd > 1) bump(u.y);
+                if (nd > 2) bump(u.z);
+            }
+        }
+        if (k == 0) peer_wait(a.ps, kStageStats);  // the table below comes from every rank's codon range
+        __syncthreads();
+        // --- contraction: group gq of 8 replicates x the slots of K-split ks, 4 slots per tensor-core tile
+        {
+            const uint32_t lks = 3 - lm, ksplit = 1u << lks;         // kBootKSplit / m warps per group of 8 replicates
+            const uint32_t gq = warp >> lks, ks = warp & (ksplit - 1);
+            const uint32_t per = (nslot4 + ksplit - 1) >> lks;
+            const uint32_t t0 = min(nslot4, ks * per), t1 = min(nslot4, t0 + per);
+            const uint32_t row = gq * 8 + (lane >> 2);
+            const uint32_t *cnt_row = s_cnt + (size_t)row * rw;      // A: row = replicate lane/4
+            const uint32_t col = lane & 3;                           //    column = slot 4t + lane%4
+            const uint32_t stat = lane >> 2;                         // B: column lane/4 = statistic (columns 4-7: padding)
+            const uint32_t sel = 0x4440u + col;                      // byte col of a word, zero-extended
+            // + 16 t: stats4[slot 4t + col][stat].  Columns 4-7 of B only feed columns 4-7 of D, which nobody reads: their
+            // lanes load the same (finite) table entries as columns 0-3 instead of a predicated zero
+            const double *gb = G + 4 * ((int64_t)col - (int64_t)s0) + (stat & 3);
+            double acc0 = 0.0, acc1 = 0.0;
+            auto tile = [&](uint32_t t, bool guard) {
+                const double av = (double)__byte_perm(cnt_row[t], 0u, sel);
+                double bv = 0.0;
+                if (!guard || (4 * t + col >= s0 && 4 * t + col < n_slots)) bv = __ldg(gb + 16 * (size_t)t);
+                dmma_m8n8k4(acc0, acc1, av, bv);
+            };
+            uint32_t t = t0;
+            if (t == 0 && t < t1) tile(t++, true);                  // may hold slot 0, the empty one
+            const uint32_t t_inner = min(t1, n_slots / 4);          // tiles below hold table rows only
+#pragma unroll 4
+            for (; t < t_inner; t++) tile(t, false);
+            for (; t < t1; t++) tile(t, true);                      // may reach past the last slot
+            // D: lane holds row lane/4, columns 2*(lane%4), +1; statistics are columns 0..3
+            if (col < 2) {
+                double *o = part + (((ks << lrows) + row) << 2) + 2 * col;
+                o[0] = acc0;
+                o[1] = acc1;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < rows * 4) {              // (replicate of the batch, statistic): K-split partials in a fixed order
+            const uint32_t r = threadIdx.x >> 2, q = threadIdx.x & 3, ksplit = kBootKSplit >> lm;
+            double v = 0.0;
+            for (uint32_t ks = 0; ks < ksplit; ks++) v += part[(((ks << lrows) + r) << 2) + q];
+            reinterpret_cast<double *>(&s_sums[r][0])[q] = v;
+        }
+        __syncthreads();
+        // dense epilogue: one thread per (replicate of the batch, statistic), as in k_bootstrap
+        for (uint32_t i = threadIdx.x; i < rows * 6; i += blockDim.x) {
+            const uint32_t r = i & (rows - 1), which = i >> lrows;
+            const int64_t bl2 = batch_first + r;
+            if (bl2 < a.b_count) {
+                const double2 x = s_sums[r][0], y = s_sums[r][1];
+                if (a.rep && which == 0) {
+                    double2 *o = reinterpret_cast<double2 *>(a.rep + 4 * ((size_t)p * a.b_count + bl2));
+                    o[0] = x;
+                    o[1] = y;
+                }
+                if (a.vals || a.pv.world > 1) put_val(a, (int)which, p, bl2, rep_value(x.x, x.y, y.x, y.y, (int)which));
+            }
+        }
+        // (the next batch's first barrier comes after its sampling: s_sums and part are not written before it)
+    }
+    if (a.prod_sums && blockIdx.x == 0) {
         // the product's sums (wg:690-693) with the additions and the tree of k_product_sums, bit for bit: its
         // kSumThreads partial sums, held kSumThreads / blockDim.x to a thread, and the same halving tree
         constexpr int kV = kSumThreads / (kMmaWarps * 32);          // partial sums of k_product_sums' threads held by one thread
         static_assert(kV >= 1 && (kV & (kV - 1)) == 0 && kV * kMmaWarps * 32 == kSumThreads, "block size must divide kSumThreads");
+        __syncthreads();
         double *red = &s_part[0][0][0];            // kBootKSplit * kMmaWarps * 4 = kMmaWarps * 32 doubles: one per thread
         const double2 *G2 = reinterpret_cast<const double2 *>(G);
         double s[kV][4];
@@ -1155,114 +1306,11 @@ k_bootstrap_mma(const double *__restrict__ stats4, const int64_t *__restrict__ o
                 if ((int)threadIdx.x < h) red[threadIdx.x] += red[threadIdx.x + h];
                 __syncthreads();
             }
-            if (threadIdx.x == 0) prod_sums[4 * p + q] = red[0];
+            if (threadIdx.x == 0) a.prod_sums[4 * p + q] = red[0];
             __syncthreads();
         }
     }
-    const uint32_t nquad = (C + 3) >> 2, full_quads = C >> 2;     // the partial quad, if any, is quad full_quads
-    const uint32_t nslot4 = (C + 1 + 3) >> 2;      // groups of 4 slots (slot 0 is the empty one)
-    // A short product does not fill a warp's counters: its warps then take m = 2, 4 or 8 replicates at a time (32 / m
-    // lanes and one row of rw words each), so that the fixed cost of a batch is spread over 32 m replicates.
-    const uint32_t rw = nslot4 | 1;                // words per row: odd, so the eight rows of a tile fall in different banks
-    uint32_t lm = 0;                               // m = 1 << lm: every count below is a power of two, divisions are shifts
-    while ((2u << lm) <= kBootMaxRows && (2u << lm) * rw <= row_words) lm++;
-    const uint32_t m = 1u << lm;
-    constexpr uint32_t kLogWarps = kMmaWarps == 16 ? 4 : kMmaWarps == 8 ? 3 : 5;
-    static_assert((1u << kLogWarps) == kMmaWarps, "kMmaWarps must be 8, 16 or 32");
-    const uint32_t lrows = kLogWarps + lm;         // log2 of the replicates per batch
-    const uint32_t rows = 1u << lrows;             // replicates per batch
-    const uint32_t n_batch = m >= kBootRepsPerWarp ? 1 : kBootRepsPerWarp >> lm;
-    const int64_t block_first = (int64_t)blockIdx.x * rows * n_batch;
-    if (block_first >= b_count) return;            // the grid is sized for m = 1
-    const uint32_t lanes_per = 32u >> lm, sub = lane >> (5 - lm), sl = lane & (lanes_per - 1);
-    uint32_t *warp_rows = s_cnt + (size_t)warp * m * rw;
-    const uint32_t mine_s = (uint32_t)__cvta_generic_to_shared(warp_rows + (size_t)sub * rw);
-    double *part = &s_part[0][0][0];               // [ksplit][rows][4], ksplit * rows = 8 * kMmaWarps
-    for (uint32_t k = 0; k < n_batch; k++) {
-        const int64_t batch_first = block_first + (int64_t)k * rows;
-        // --- sampling: one replicate per group of 32 / m lanes -> its row of counts
-        for (uint32_t i = lane; i < m * rw; i += 32) warp_rows[i] = 0;
-        __syncwarp();
-        const int64_t bl = batch_first + warp * m + sub;
-        if (bl < b_count) {
-            const uint64_t b = (uint64_t)(b_first + bl);
-            auto bump = [&](uint32_t u) {          // one draw: slot = floor(u * (C+1) / 2^32); its byte of the row goes up by one
-                const uint32_t r = __umulhi(u, C + 1);
-                // 1 << 8 * (r & 3): a funnel shift takes its count modulo 32, so r << 3 needs no mask
-                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(mine_s + (r & ~3u)), "r"(__funnelshift_l(0u, 1u, r << 3)) : "memory");
-            };
-            uint32_t q = sl;
-            for (; q < full_quads; q += lanes_per) {
-                const uint4 u = philox4x32_10(make_uint4(q, (uint32_t)b, (uint32_t)(b >> 32) ^ ((uint32_t)p << 8), stream_id), key);
-                bump(u.x); bump(u.y); bump(u.z); bump(u.w);
-            }
-            if (q < nquad) {                       // the last, partial quad (one lane)
-                const uint4 u = philox4x32_10(make_uint4(q, (uint32_t)b, (uint32_t)(b >> 32) ^ ((uint32_t)p << 8), stream_id), key);
-                const uint32_t nd = C & 3;
-                bump(u.x);
-                if (nd > 1) bump(u.y);
-                if (nd > 2) bump(u.z);
-            }
-        }
-        __syncthreads();
-        // --- contraction: group gq of 8 replicates x the slots of K-split ks, 4 slots per tensor-core tile
-        {
-            const uint32_t lks = 3 - lm, ksplit = 1u << lks;         // kBootKSplit / m warps per group of 8 replicates
-            const uint32_t gq = warp >> lks, ks = warp & (ksplit - 1);
-            const uint32_t per = (nslot4 + ksplit - 1) >> lks;
-            const uint32_t t0 = min(nslot4, ks * per), t1 = min(nslot4, t0 + per);
-            const uint32_t row = gq * 8 + (lane >> 2);
-            const uint32_t *cnt_row = s_cnt + (size_t)row * rw;      // A: row = replicate lane/4
-            const uint32_t col = lane & 3;                           //    column = slot 4t + lane%4
-            const uint32_t stat = lane >> 2;                         // B: column lane/4 = statistic (columns 4-7: padding)
-            const uint32_t sel = 0x4440u + col;                      // byte col of a word, zero-extended
-            // + 16 t: stats4[slot 4t + col][stat].  Columns 4-7 of B only feed columns 4-7 of D, which nobody reads: their
-            // lanes load the same (finite) table entries as columns 0-3 instead of a predicated zero
-            const double *gb = G + 4 * (int64_t)col - 4 + (stat & 3);
-            double acc0 = 0.0, acc1 = 0.0;
-            auto tile = [&](uint32_t t, bool guard) {
-                const double a = (double)__byte_perm(cnt_row[t], 0u, sel);
-                double bv = 0.0;
-                if (!guard || (4 * t + col >= 1 && 4 * t + col <= C)) bv = __ldg(gb + 16 * (size_t)t);
-                dmma_m8n8k4(acc0, acc1, a, bv);
-            };
-            uint32_t t = t0;
-            if (t == 0 && t < t1) tile(t++, true);                  // holds slot 0, the empty one
-            const uint32_t t_inner = min(t1, (C + 1) / 4);          // tiles below hold slots 1..C only
-#pragma unroll 4
-            for (; t < t_inner; t++) tile(t, false);
-            for (; t < t1; t++) tile(t, true);                      // may reach past slot C
-            // D: lane holds row lane/4, columns 2*(lane%4), +1; statistics are columns 0..3
-            if (col < 2) {
-                double *o = part + (((ks << lrows) + row) << 2) + 2 * col;
-                o[0] = acc0;
-                o[1] = acc1;
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x < rows * 4) {              // (replicate of the batch, statistic): K-split partials in a fixed order
-            const uint32_t r = threadIdx.x >> 2, q = threadIdx.x & 3, ksplit = kBootKSplit >> lm;
-            double v = 0.0;
-            for (uint32_t ks = 0; ks < ksplit; ks++) v += part[(((ks << lrows) + r) << 2) + q];
-            reinterpret_cast<double *>(&s_sums[r][0])[q] = v;
-        }
-        __syncthreads();
-        // dense epilogue: one thread per (replicate of the batch, statistic), as in k_bootstrap
-        for (uint32_t i = threadIdx.x; i < rows * 6; i += blockDim.x) {
-            const uint32_t r = i & (rows - 1), which = i >> lrows;
-            const int64_t bl2 = batch_first + r;
-            if (bl2 < b_count) {
-                const double2 x = s_sums[r][0], y = s_sums[r][1];
-                if (rep && which == 0) {
-                    double2 *o = reinterpret_cast<double2 *>(rep + 4 * ((size_t)p * b_count + bl2));
-                    o[0] = x;
-                    o[1] = y;
-                }
-                if (vals) vals[((size_t)which * n_products + p) * b_count + bl2] = rep_value(x.x, x.y, y.x, y.y, which);
-            }
-        }
-        // (the next batch's first barrier comes after its sampling: s_sums and part are not written before it)
-    }
+    peer_signal(a.ps, kStageVals);
 }
 
 // ---------------------------------------------------------------------------
@@ -1285,11 +1333,13 @@ __device__ __forceinline__ double block_sum(double v, double *red) {     // fixe
 
 template <bool FROM_REP>
 __global__ void __launch_bounds__(kMomentThreads)
-k_moments(const double *__restrict__ src, int64_t n_items, int64_t B, double *__restrict__ se)
+k_moments(const double *__restrict__ src, int64_t n_items, int64_t B, double *__restrict__ se, uint32_t *__restrict__ undefined,
+          const __grid_constant__ PeerSync ps)
 {
     // FROM_REP: src = rep[item][B][4], the statistic is derived on the fly; else src = vals[which][item][B]
     __shared__ double red[kMomentThreads];
     const int p = blockIdx.x, which = blockIdx.y, t = threadIdx.x;
+    peer_wait(ps, kStageVals);             // several GPUs: every rank's replicate range has arrived
     const double2 *R = reinterpret_cast<const double2 *>(src + 4 * (size_t)p * B);
     const double *V = src + ((size_t)which * n_items + p) * B;
     auto value = [&](int64_t b) {
@@ -1299,14 +1349,19 @@ k_moments(const double *__restrict__ src, int64_t n_items, int64_t B, double *__
     };
     double s = 0;
     int differs = 0;                       // replicates that are all identical have SD exactly 0, whatever
+    int bad = 0;                           // replicates whose value is undefined (Jukes-Cantor of d >= 3/4: the reference dies, bgp:1047)
     const double v0 = value(0);            // rounding the mean of B equal numbers picks up
-    for (int64_t b = t; b < B; b += kMomentThreads) { const double v = value(b); s += v; differs |= (v != v0); }
+    for (int64_t b = t; b < B; b += kMomentThreads) { const double v = value(b); s += v; differs |= (v != v0); bad += !isfinite(v); }
     const double mean = block_sum(s, red) / (double)B;
     double ss = 0;
     for (int64_t b = t; b < B; b += kMomentThreads) { const double d = value(b) - mean; ss += d * d; }
     const double tot = block_sum(ss, red);
     const int any = __syncthreads_or(differs);
-    if (t == 0) se[6 * p + which] = any ? sqrt(tot / (double)(B - 1)) : 0.0;
+    const int n_bad = __syncthreads_count(bad) ? (int)block_sum((double)bad, red) : 0;
+    if (t == 0) {
+        se[6 * p + which] = any ? sqrt(tot / (double)(B - 1)) : 0.0;
+        if (undefined) undefined[6 * p + which] = (uint32_t)n_bad;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -1315,49 +1370,22 @@ k_moments(const double *__restrict__ src, int64_t n_items, int64_t B, double *__
 // the same order as the reference, so window sums are bitwise reproducible and
 // an all-zero window stays exactly 0 (a prefix-sum difference would not).
 // ---------------------------------------------------------------------------
-__global__ void k_window_sums(const double *__restrict__ stats4, int64_t W, int64_t step, int64_t nwin,
-                              double *__restrict__ win_sums)
+__global__ void k_window_sums(const double *__restrict__ stats4, const int64_t *__restrict__ beg, const int64_t *__restrict__ end,
+                              int64_t nwin, double *__restrict__ win_sums)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nwin * 4) return;
     const int64_t k = i >> 2;
     const int q = (int)(i & 3);
-    const double *p = stats4 + 4 * k * step + q;
+    const double *p = stats4 + 4 * beg[k] + q;
+    const int64_t W = end[k] - beg[k];
     double s = 0;
     for (int64_t j = 0; j < W; j++) s += p[4 * j];
     win_sums[i] = s;
 }
 
-// per-window bootstrap (wgp:384-427; bgp:604-736): one thread per (window,
-// replicate), W draws uniform over the window's codons
-__global__ void __launch_bounds__(256)
-k_window_bootstrap(const double *__restrict__ stats4, int64_t W, int64_t step, int64_t win0, int64_t nwin, int64_t B,
-                   uint2 key, uint32_t stream_id, double *__restrict__ rep)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nwin * B) return;
-    const int64_t wl = i / B, b = i % B;
-    const uint64_t k = (uint64_t)(win0 + wl);
-    const double *S = stats4 + 4 * k * step;
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    const uint32_t Wu = (uint32_t)W;
-    for (uint32_t q = 0; 4 * q < Wu; q++) {
-        const uint4 u = philox4x32_10(make_uint4(q, (uint32_t)b, (uint32_t)k, stream_id ^ ((uint32_t)(k >> 32) << 16) ^ ((uint32_t)(b >> 32))), key);
-        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (4 * q + j < Wu) {
-                const uint32_t r = __umulhi(uu[j], Wu);
-                const double2 x = __ldg(reinterpret_cast<const double2 *>(S + 4 * (size_t)r));
-                const double2 y = __ldg(reinterpret_cast<const double2 *>(S + 4 * (size_t)r) + 1);
-                s0 += x.x; s1 += x.y; s2 += y.x; s3 += y.y;
-            }
-        }
-    }
-    double2 *o = reinterpret_cast<double2 *>(rep + 4 * (size_t)i);
-    o[0] = make_double2(s0, s1);
-    o[1] = make_double2(s2, s3);
-}
+// (The per-window bootstrap, wgp:384-427 and bgp:604-736, is k_bootstrap_mma / k_bootstrap over window items: W draws
+// uniform over the window's W codons, slot0 = 0.)
 
 }  // namespace
 
@@ -1440,11 +1468,22 @@ void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, cons
 
 void launch_fused_fixup_stats(const uint8_t *d_cons, int64_t cons_shift, const uint32_t *d_alt, const CodonMap *d_map, int64_t n_codons,
                               uint32_t n_rows, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max, GroupView A,
-                              const double *d_tables, StatsOut out, cudaStream_t stream)
+                              const double *d_tables, StatsOut out, const PeerOut *po, const PeerSync *ps, cudaStream_t stream)
 {
-    if (n_codons <= 0) return;
+    if (n_codons <= 0) { if (ps) launch_peer_signal(*ps, kStageStats, stream); return; }
     k_fused_fixup_stats<<<(unsigned)((n_codons + kStatsWarps - 1) / kStatsWarps), kStatsWarps * 32, 0, stream>>>(
-        d_cons, cons_shift, d_alt, d_map, n_codons, n_rows, d_hist, d_other_min, d_other_max, A, d_tables, out);
+        d_cons, cons_shift, d_alt, d_map, n_codons, n_rows, d_hist, d_other_min, d_other_max, A, d_tables, out, po ? *po : PeerOut(),
+        ps ? *ps : PeerSync());
+}
+
+void launch_peer_signal(const PeerSync &ps, int stage, cudaStream_t stream)
+{
+    if (ps.world > 1) k_peer_signal<<<1, 32, 0, stream>>>(ps, stage);
+}
+
+void launch_peer_wait(const PeerSync &ps, int stage, cudaStream_t stream)
+{
+    if (ps.world > 1) k_peer_wait<<<1, 32, 0, stream>>>(ps, stage);
 }
 
 void launch_fused_fixup(const uint8_t *d_cons, int64_t cons_shift, const uint32_t *d_alt, const CodonMap *d_map, const uint8_t *d_regular,
@@ -1489,19 +1528,20 @@ void launch_untranspose(const uint8_t *d_codes, int64_t n_pad, int64_t n, int64_
     k_untranspose<<<grid, block, 0, stream>>>(d_codes, n_pad, n, c0, C, d_out);
 }
 
-void launch_within_stats(GroupView A, int64_t n_codons, const double *d_tables, StatsOut out, cudaStream_t stream)
+void launch_within_stats(GroupView A, int64_t n_codons, const double *d_tables, StatsOut out, const PeerOut *po, const PeerSync *ps,
+                         cudaStream_t stream)
 {
-    if (n_codons <= 0) return;
-    k_stats<false><<<(unsigned)((n_codons + kStatsWarps - 1) / kStatsWarps), kStatsWarps * 32, 0, stream>>>(A, A, n_codons,
-                                                                                                           d_tables, out);
+    if (n_codons <= 0) { if (ps) launch_peer_signal(*ps, kStageStats, stream); return; }
+    k_stats<false><<<(unsigned)((n_codons + kStatsWarps - 1) / kStatsWarps), kStatsWarps * 32, 0, stream>>>(
+        A, A, n_codons, d_tables, out, po ? *po : PeerOut(), ps ? *ps : PeerSync());
 }
 
 void launch_between_stats(GroupView A, GroupView B, int64_t n_codons, const double *d_tables, StatsOut out,
                           cudaStream_t stream)
 {
     if (n_codons <= 0) return;
-    k_stats<true><<<(unsigned)((n_codons + kStatsWarps - 1) / kStatsWarps), kStatsWarps * 32, 0, stream>>>(A, B, n_codons,
-                                                                                                          d_tables, out);
+    k_stats<true><<<(unsigned)((n_codons + kStatsWarps - 1) / kStatsWarps), kStatsWarps * 32, 0, stream>>>(A, B, n_codons, d_tables, out,
+                                                                                                          PeerOut(), PeerSync());
 }
 
 void launch_taxa_filter(double *d_stats4, const uint32_t *d_ndef_a, const uint32_t *d_ndef_b, int64_t n_codons, uint32_t min_total,
@@ -1518,35 +1558,32 @@ void launch_product_sums(const double *d_stats4, const int64_t *d_prod_ofs, int 
     k_product_sums<<<n_products, kSumThreads, 0, stream>>>(d_stats4, d_prod_ofs, d_sums);
 }
 
-void launch_bootstrap(int form, const double *d_stats4, const int64_t *d_prod_ofs, const int *d_order, int n_products, int64_t max_codons,
-                      int64_t b_first, int64_t b_count, uint64_t seed, uint32_t stream_id, const uint32_t *d_salt, double *d_rep,
-                      double *d_vals, double *d_prod_sums, cudaStream_t stream)
+void launch_bootstrap(int form, BootArgs a, int64_t max_codons, cudaStream_t stream)
 {
-    if (n_products <= 0 || b_count <= 0) return;
+    if (a.n_items <= 0 || a.b_count <= 0) { launch_peer_signal(a.ps, kStageVals, stream); return; }
+    if (a.vals_stride <= 0) a.vals_stride = a.b_count;
     const int64_t per_block = (int64_t)kBootWarps * kBootRepsPerWarp;
-    dim3 grid((unsigned)((b_count + per_block - 1) / per_block), (unsigned)n_products);
-    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    dim3 grid((unsigned)((a.b_count + per_block - 1) / per_block), (unsigned)a.n_items);
     const size_t smem = (size_t)(max_codons + 1) * 32;
     // a warp's counters: one byte per slot, rows padded to an odd number of words (no two of the eight rows a
     // tensor-core tile reads share a bank)
     // (at least 16 KB a block even for a short table, so that short products can take several replicates per warp)
     const size_t row_words = std::max<size_t>((((size_t)max_codons + 1 + 3) / 4) | 1, 127);
     if (form == SNPG_BOOT_WEIGHTS && row_words * 4 * 32 <= (size_t)kBootSmemLimit) {
-        // two blocks of kMmaWarps warps per SM; the grid is sized for one replicate per warp and two batches a block
+        // five blocks of kMmaWarps warps per SM; the grid is sized for one replicate per warp and two batches a block
         const int64_t per_mma = (int64_t)kMmaWarps * kBootRepsPerWarp;
-        dim3 grid_mma((unsigned)((b_count + per_mma - 1) / per_mma), (unsigned)n_products);
+        dim3 grid_mma((unsigned)((a.b_count + per_mma - 1) / per_mma), (unsigned)a.n_items);
         cudaFuncSetAttribute(k_bootstrap_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, kBootSmemLimit * kMmaWarps / 32);  // per device
-        k_bootstrap_mma<<<grid_mma, kMmaWarps * 32, row_words * 4 * kMmaWarps, stream>>>(d_stats4, d_prod_ofs, d_order, n_products, b_first,
-                                                                                         b_count, key, stream_id, d_salt, d_rep, d_vals,
-                                                                                         d_prod_sums, (uint32_t)row_words);
+        k_bootstrap_mma<<<grid_mma, kMmaWarps * 32, row_words * 4 * kMmaWarps, stream>>>(a, (uint32_t)row_words);
     } else if (smem <= (size_t)kBootSmemLimit) {
         cudaFuncSetAttribute(k_bootstrap<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBootSmemLimit);  // per device
-        k_bootstrap<true><<<grid, kBootWarps * 32, smem, stream>>>(d_stats4, d_prod_ofs, d_order, n_products, b_first, b_count, key,
-                                                                    stream_id, d_salt, d_rep, d_vals, d_prod_sums);
+        k_bootstrap<true><<<grid, kBootWarps * 32, smem, stream>>>(a);
     } else {
-        if (d_prod_sums) launch_product_sums(d_stats4, d_prod_ofs, n_products, d_prod_sums, stream);
-        k_bootstrap<false><<<grid, kBootWarps * 32, 0, stream>>>(d_stats4, d_prod_ofs, d_order, n_products, b_first, b_count, key,
-                                                                  stream_id, d_salt, d_rep, d_vals, nullptr);
+        // tables beyond shared memory: gathers from global memory; the sums need the exchanged table, so they follow the kernel
+        double *sums = a.prod_sums;
+        a.prod_sums = nullptr;
+        k_bootstrap<false><<<grid, kBootWarps * 32, 0, stream>>>(a);
+        if (sums) launch_product_sums(a.stats4, a.beg, a.n_items, sums, stream);
     }
 }
 
@@ -1558,29 +1595,21 @@ void launch_philox_kat(const uint32_t *ctr, const uint32_t *key, uint32_t *d_out
 void launch_moments(const double *d_rep, int64_t n_items, int64_t B, double *d_se, cudaStream_t stream)
 {
     if (n_items <= 0) return;
-    k_moments<true><<<dim3((unsigned)n_items, 6), kMomentThreads, 0, stream>>>(d_rep, n_items, B, d_se);
+    k_moments<true><<<dim3((unsigned)n_items, 6), kMomentThreads, 0, stream>>>(d_rep, n_items, B, d_se, nullptr, PeerSync());
 }
 
-void launch_moments_vals(const double *d_vals, int64_t n_items, int64_t B, double *d_se, cudaStream_t stream)
+void launch_moments_vals(const double *d_vals, int64_t n_items, int64_t B, double *d_se, uint32_t *d_undefined, const PeerSync *ps,
+                         cudaStream_t stream)
 {
     if (n_items <= 0) return;
-    k_moments<false><<<dim3((unsigned)n_items, 6), kMomentThreads, 0, stream>>>(d_vals, n_items, B, d_se);
+    k_moments<false><<<dim3((unsigned)n_items, 6), kMomentThreads, 0, stream>>>(d_vals, n_items, B, d_se, d_undefined, ps ? *ps : PeerSync());
 }
 
-void launch_window_sums(const double *d_stats4, int64_t W, int64_t step, int64_t nwin, double *d_win_sums,
+void launch_window_sums(const double *d_stats4, const int64_t *d_beg, const int64_t *d_end, int64_t nwin, double *d_win_sums,
                         cudaStream_t stream)
 {
     if (nwin <= 0) return;
-    k_window_sums<<<(unsigned)((nwin * 4 + 127) / 128), 128, 0, stream>>>(d_stats4, W, step, nwin, d_win_sums);
-}
-
-void launch_window_bootstrap(const double *d_stats4, int64_t W, int64_t step, int64_t win0, int64_t nwin, int64_t B,
-                             uint64_t seed, uint32_t stream_id, double *d_rep, cudaStream_t stream)
-{
-    if (nwin <= 0 || B <= 0) return;
-    const int64_t total = nwin * B;
-    k_window_bootstrap<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
-        d_stats4, W, step, win0, nwin, B, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), stream_id, d_rep);
+    k_window_sums<<<(unsigned)((nwin * 4 + 127) / 128), 128, 0, stream>>>(d_stats4, d_beg, d_end, nwin, d_win_sums);
 }
 
 }  // namespace snpg

@@ -39,6 +39,26 @@ struct GroupView {
     int64_t n, n_pad;
 };
 
+// ---- multi-GPU exchange over peer memory (snpg_peer.cuh, exchange.cu) --------------------------------
+constexpr int kMaxPeers = 8;       // ranks of one NVSwitch domain
+constexpr int kStageStats = 0;     // per-codon statistics of every codon range have arrived
+constexpr int kStageVals = 1;      // per-replicate values of every replicate range have arrived
+// First bytes of every rank's exchange region.  flag[stage][src] = epoch of the last job whose stage-`stage` data
+// from rank `src` is complete in THIS region; done[] = blocks of the running producer kernel that have finished.
+struct XHeader { uint32_t flag[2][kMaxPeers]; uint32_t done[2]; uint32_t err; uint32_t pad[13]; };
+static_assert(sizeof(XHeader) == 128, "exchange header is one 128-byte line");
+// world <= 1: no exchange, every peer_* call is a no-op
+struct PeerSync { int world = 1, rank = 0; XHeader *hdr[kMaxPeers] = {}; const uint32_t *epoch = nullptr; };
+// Per-codon outputs replicated into every rank's region, indexed on the GLOBAL codon axis (first = this shard's
+// first codon there).
+struct PeerOut {
+    int world = 1; int64_t first = 0;
+    double *stats4[kMaxPeers] = {}; unsigned long long *cmp[kMaxPeers] = {}; uint32_t *ndef[kMaxPeers] = {};
+    uint8_t *poly[kMaxPeers] = {}, *cons[kMaxPeers] = {};
+};
+// Per-replicate values vals[which][item][B] replicated into every rank's region (global replicate index).
+struct PeerVals { int world = 1; double *vals[kMaxPeers] = {}; };
+
 // host (ng_tables.cu)
 void build_tables(double *sites, double *diffs);
 
@@ -102,11 +122,17 @@ struct StatsOut {
     uint8_t *poly; uint32_t *ndef_a; uint32_t *ndef_b; unsigned long long *comparisons;
     double *stats4; uint8_t *conserved;
 };
-void launch_within_stats(GroupView A, int64_t n_codons, const double *d_tables, StatsOut out, cudaStream_t stream);
+// po/ps (or null): multi-GPU -- the outputs also go into every peer's exchange region and stage kStageStats is signalled.
+void launch_within_stats(GroupView A, int64_t n_codons, const double *d_tables, StatsOut out, const PeerOut *po, const PeerSync *ps,
+                         cudaStream_t stream);
 // launch_fused_fixup (every codon regular) and launch_within_stats in one kernel, codon by codon: same arithmetic.
 void launch_fused_fixup_stats(const uint8_t *d_cons, int64_t cons_shift, const uint32_t *d_alt, const CodonMap *d_map, int64_t n_codons,
                               uint32_t n_rows, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max, GroupView A,
-                              const double *d_tables, StatsOut out, cudaStream_t stream);
+                              const double *d_tables, StatsOut out, const PeerOut *po, const PeerSync *ps, cudaStream_t stream);
+// a rank whose codon range is empty still has to signal its stage
+void launch_peer_signal(const PeerSync &ps, int stage, cudaStream_t stream);
+// everything enqueued on `stream` after this sees the stage's data of every rank
+void launch_peer_wait(const PeerSync &ps, int stage, cudaStream_t stream);
 void launch_between_stats(GroupView A, GroupView B, int64_t n_codons, const double *d_tables, StatsOut out,
                           cudaStream_t stream);
 
@@ -118,28 +144,41 @@ void launch_taxa_filter(double *d_stats4, const uint32_t *d_ndef_a, const uint32
 void launch_product_sums(const double *d_stats4, const int64_t *d_prod_ofs, int n_products, double *d_sums,
                          cudaStream_t stream);
 
-// K4 whole-product bootstrap over products [0, n_products): replicates
-// [b_first, b_first+b_count).  d_order (or null) lists products largest first.
-// max_codons = largest product (sizes the shared-memory table; larger than the
-// limit falls back to gathers from global memory).  Outputs (either may be null):
-// d_rep[p][b][4] replicate sums, d_vals[which][p][b] per-replicate dN, dS, dN-dS, JC x3.  d_prod_sums (or null):
-// sums[p][4] as launch_product_sums writes them, bit for bit, computed on the way from the staged table.
-// d_salt (or null): a device word added to stream_id when the kernel runs (replayed CUDA graphs).
-// form: SNPG_BOOT_WEIGHTS (slot counters + tensor-core contraction) or SNPG_BOOT_GATHER (per-draw row gathers).
-void launch_bootstrap(int form, const double *d_stats4, const int64_t *d_prod_ofs, const int *d_order, int n_products, int64_t max_codons,
-                      int64_t b_first, int64_t b_count, uint64_t seed, uint32_t stream_id, const uint32_t *d_salt, double *d_rep,
-                      double *d_vals, double *d_prod_sums, cudaStream_t stream);
+// K4 resampling.  Item i (a product, a sliding window ...) resamples the codons [beg[i], end[i]) of stats4: every
+// replicate is C = end - beg draws from C + slot0 slots (slot0 = 1: the reference's whole-product bootstrap,
+// int(rand(C+1)) with a nonexistent codon 0, wg:885; slot0 = 0: its window bootstrap, wgp:406).  This launch covers
+// the replicates [b_first, b_first + b_count).  order (or null) lists the items largest first.  Outputs (any may be
+// null): rep[item][b][4] replicate sums; vals[(which * n_items + item) * vals_stride + vals_b0 + b] per-replicate
+// dN, dS, dN-dS and their Jukes-Cantor forms (vals_stride <= 0: b_count); prod_sums[item][4] as launch_product_sums
+// writes them, bit for bit.  Philox4x32-10: key = seed, the counter carries (draw quad, replicate, item, kind, call +
+// *salt): kind separates the callers' streams, salt (or null) is a device word a replayed CUDA graph refreshes.
+// pv/ps (world > 1): the values go into every rank's exchange region instead of vals, the kernel waits for stage
+// kStageStats before it reads stats4 and signals kStageVals when it is done.
+struct BootArgs {
+    const double *stats4 = nullptr; const int64_t *beg = nullptr, *end = nullptr; const int *order = nullptr;
+    int n_items = 0, slot0 = 1;
+    uint32_t item0 = 0;            // added to the item index in the Philox counter (batches of windows, group pairs)
+    int64_t b_first = 0, b_count = 0, vals_stride = 0, vals_b0 = 0;
+    uint2 key = {0, 0}; uint32_t kind = 0, call = 0; const uint32_t *salt = nullptr;
+    double *rep = nullptr, *vals = nullptr, *prod_sums = nullptr;
+    PeerVals pv; PeerSync ps;
+};
+enum BootKind : uint32_t { kBootProduct = 1, kBootWindow = 2, kBootAllDevice = 3, kBootJob = 4, kBootBetween = 5, kBootJobWindow = 6 };
+// form: SNPG_BOOT_WEIGHTS (slot counters + tensor-core contraction) or SNPG_BOOT_GATHER (per-draw row gathers);
+// max_codons = the longest item (sizes the shared-memory table; beyond the limit: gathers from global memory).
+void launch_bootstrap(int form, BootArgs a, int64_t max_codons, cudaStream_t stream);
 // one Philox4x32-10 block on the device (known-answer test hook)
 void launch_philox_kat(const uint32_t *ctr, const uint32_t *key, uint32_t *d_out, cudaStream_t stream);
 // K6: rep[item][B][4] -> se[item][6]: sample SD (n-1) of the per-replicate dN, dS, dN-dS and their Jukes-Cantor forms
 void launch_moments(const double *d_rep, int64_t n_items, int64_t B, double *d_se, cudaStream_t stream);
-// the same from d_vals[which][item][B] (what launch_bootstrap's epilogue writes)
-void launch_moments_vals(const double *d_vals, int64_t n_items, int64_t B, double *d_se, cudaStream_t stream);
+// the same from d_vals[which][item][B] (what launch_bootstrap's epilogue writes).  d_undefined (or null): [item][6]
+// replicates whose value is not finite (Jukes-Cantor of a distance >= 3/4: the reference dies there, bgp:1047).
+// ps (or null): wait for stage kStageVals first.
+void launch_moments_vals(const double *d_vals, int64_t n_items, int64_t B, double *d_se, uint32_t *d_undefined, const PeerSync *ps,
+                         cudaStream_t stream);
 
-// K5 windows
-void launch_window_sums(const double *d_stats4, int64_t W, int64_t step, int64_t nwin, double *d_win_sums,
+// K5 windows: window k sums the codons [beg[k], end[k]) in ascending order; its bootstrap is launch_bootstrap over the same items
+void launch_window_sums(const double *d_stats4, const int64_t *d_beg, const int64_t *d_end, int64_t nwin, double *d_win_sums,
                         cudaStream_t stream);
-void launch_window_bootstrap(const double *d_stats4, int64_t W, int64_t step, int64_t win0, int64_t nwin, int64_t B,
-                             uint64_t seed, uint32_t stream_id, double *d_rep, cudaStream_t stream);
 
 }  // namespace snpg

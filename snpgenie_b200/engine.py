@@ -33,15 +33,24 @@ def ng_tables():
 
 
 class Engine:
-    def __init__(self, device: int = 0, seed: int = 20261019, rank: int = 0, world: int = 1, keep_codes: bool = False):
+    def __init__(self, device: int = 0, seed: int = 20261019, rank: int = 0, world: int = 1, keep_codes: bool = False,
+                 gpus: int | list[int] | None = None):
         """keep_codes=True materialises the packed codon matrix (K1+K2 route: codon_indices(), exact
-        between-group first-defined rule); the default builds histograms with the fused kernel."""
+        between-group first-defined rule); the default builds histograms with the fused kernel.
+        gpus=N (or a list of device ids): ONE engine over N GPUs of this process (snpg_create_multi) -- codon ranges and
+        bootstrap replicates are split over them and exchanged through peer memory.  rank/world: this engine is one
+        rank of a multi-process job (one process per GPU); connect the ranks with peer_export()/peer_connect()."""
         self._ctx = C.c_void_p()
-        rc = _abi.lib.snpg_create(C.byref(self._ctx), device, seed)
+        if gpus is not None:
+            devs = list(range(gpus)) if isinstance(gpus, int) else list(gpus)
+            rc = _abi.lib.snpg_create_multi(C.byref(self._ctx), len(devs), (C.c_int * len(devs))(*devs), seed)
+        else:
+            rc = _abi.lib.snpg_create(C.byref(self._ctx), device, seed)
         if rc:
             raise _abi.SnpgError(rc, (_abi.lib.snpg_last_error(None) or b"").decode())
         self.products: list[Product] = []
         self.rank, self.world = rank, world
+        self._pinned = {}
         if world > 1:
             self._ck(_abi.lib.snpg_set_shard(self._ctx, rank, world))
         if keep_codes:
@@ -87,7 +96,38 @@ class Engine:
         self._ck(_abi.lib.snpg_set_option(self._ctx, option, value))
 
     def set_stream(self, cuda_stream_ptr: int | None):
+        """Launch on a caller-owned stream.  None restores the engine's own stream; 0 -- the handle torch reports for the
+        legacy default stream -- is passed on as cudaStreamLegacy (the ABI reads NULL as "own stream")."""
+        if cuda_stream_ptr is not None and cuda_stream_ptr == 0:
+            cuda_stream_ptr = 1
         self._ck(_abi.lib.snpg_set_stream(self._ctx, cuda_stream_ptr))
+
+    # -- several GPUs -----------------------------------------------------
+    @property
+    def team_size(self) -> int:
+        return int(_abi.lib.snpg_team_size(self._ctx))
+
+    def peer_export(self, max_bootstraps: int) -> bytes:
+        """This rank's exchange handle (call after set_products); gather all ranks' handles in rank order."""
+        buf = C.create_string_buffer(_abi.PEER_HANDLE_BYTES)
+        self._ck(_abi.lib.snpg_peer_export(self._ctx, max_bootstraps, buf))
+        return buf.raw
+
+    def peer_connect(self, handles: list[bytes]):
+        blob = b"".join(handles)
+        self._ck(_abi.lib.snpg_peer_connect(self._ctx, blob, len(handles)))
+
+    @property
+    def peer_connected(self) -> bool:
+        return bool(_abi.lib.snpg_peer_connected(self._ctx))
+
+    def connect_ranks(self, max_bootstraps: int, group=None):
+        """Export + all-gather of the handles over torch.distributed (any backend) + connect."""
+        import torch.distributed as dist
+        mine = self.peer_export(max_bootstraps)
+        handles = [None] * dist.get_world_size(group)
+        dist.all_gather_object(handles, mine, group=group)
+        self.peer_connect(handles)
 
     def profile(self, reset: bool = True) -> dict:
         """{kernel kind: (milliseconds, launches)} accumulated since the last reset (kinds selected by OPT_PROFILE)."""
@@ -241,6 +281,74 @@ class Engine:
         self._ck(_abi.lib.snpg_within_job(self._ctx, group, ptr, int(device), n_seqs, aln_len, row_stride, B,
                                           _ptr(sums, C.c_double), _ptr(se, C.c_double)))
         return sums, se
+
+    def staged_bytes_per_row(self) -> int:
+        first, n = C.c_int64(), C.c_int64()
+        self._ck(_abi.lib.snpg_staged_columns(self._ctx, C.byref(first), C.byref(n)))
+        return n.value
+
+    def probe_peaks(self) -> dict:
+        out = np.zeros(4)
+        self._ck(_abi.lib.snpg_probe_peaks(self._ctx, _ptr(out, C.c_double)))
+        return {"philox_gdraws_per_s": float(out[0]) / 1e9, "dmma_tflops": float(out[1])}
+
+    def total_codons(self) -> int:
+        return self.shard_range()[2]
+
+    def window_plan(self, W: int, step: int) -> np.ndarray:
+        """win_ofs [P+1]: product p owns the windows [win_ofs[p], win_ofs[p+1]) of a job's window outputs."""
+        ofs = np.zeros(len(self.products) + 1, dtype=np.int64)
+        self._ck(_abi.lib.snpg_window_plan(self._ctx, W, step, _ptr(ofs, C.c_int64)))
+        return ofs
+
+    def _host_array(self, name, shape, dtype, pinned):
+        """Output arrays of job(): reused between calls (a replayed CUDA graph writes to fixed addresses)."""
+        key = (name, tuple(shape), np.dtype(dtype).str, pinned)
+        a = self._pinned.get(key)
+        if a is None:
+            if pinned:
+                import torch
+                t = torch.empty(tuple(shape), dtype=getattr(torch, np.dtype(dtype).name)).pin_memory()
+                a = (t, t.numpy())
+            else:
+                a = (None, np.zeros(shape, dtype=dtype))
+            self._pinned[key] = a
+        return a[1]
+
+    def job(self, group: int, ptr: int | None, n_seqs: int = 0, aln_len: int = 0, row_stride: int = 0, device: bool = False, B: int = 0,
+            window: int = 0, step: int = 1, B_win: int = 0, per_codon: bool = True, pinned: bool = True) -> dict:
+        """The whole within-group job in ONE ABI call (snpg_within_job_ex): product sums and SEs, the per-codon
+        tables over the global codon axis and, with window > 0, the sliding windows with their bootstrap SEs.
+        ptr=None: the group is already loaded.  The returned arrays are owned by the engine and overwritten by the next
+        job of the same shape."""
+        P = len(self.products)
+        total = self.total_codons() if (self.world == 1 or self.peer_connected or self.team_size > 1) else self.shard_range()[1]
+        out = {"prod_sums": self._host_array("prod_sums", (P, 4), np.float64, False)}
+        spec = _abi.Job()
+        spec.struct_size = C.sizeof(_abi.Job)
+        spec.n_bootstraps = B
+        spec.prod_sums = out["prod_sums"].ctypes.data
+        if B >= 2:
+            out["prod_se"] = self._host_array("prod_se", (P, 6), np.float64, False)
+            out["prod_undefined"] = self._host_array("prod_undefined", (P, 6), np.uint32, False)
+            spec.prod_se, spec.prod_undefined = out["prod_se"].ctypes.data, out["prod_undefined"].ctypes.data
+        if per_codon:
+            for name, shape, dt in (("poly", (total,), np.uint8), ("n_defined", (total,), np.uint32), ("comparisons", (total,), np.uint64),
+                                    ("stats4", (total, 4), np.float64), ("conserved", (total,), np.uint8)):
+                out[name] = self._host_array(name, shape, dt, pinned)
+                setattr(spec, name, out[name].ctypes.data)
+        if window > 0:
+            ofs = self.window_plan(window, step)
+            out["win_ofs"] = ofs
+            nw = int(ofs[-1])
+            spec.window, spec.step, spec.n_window_bootstraps = window, step, B_win
+            out["win_sums"] = self._host_array("win_sums", (nw, 4), np.float64, False)
+            spec.win_sums = out["win_sums"].ctypes.data
+            if B_win >= 2:
+                out["win_se"] = self._host_array("win_se", (nw, 3), np.float64, False)
+                spec.win_se = out["win_se"].ctypes.data
+        self._ck(_abi.lib.snpg_within_job_ex(self._ctx, group, ptr, int(device), n_seqs, aln_len, row_stride, C.byref(spec)))
+        return out
 
     # -- device-pointer plumbing for multi-GPU ------------------------------------
     def within_stats_device(self, group: int, d_stats4_ptr: int):

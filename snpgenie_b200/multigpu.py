@@ -1,7 +1,9 @@
-"""Multi-GPU plumbing: one process per GPU, torch.distributed for the (small) exchanges.
+"""Multi-GPU plumbing done by the CALLER with torch.distributed -- the NCCL BASELINE of the exchange.
 
-The path shards by codon range and by bootstrap replicate; there is no data-path collective.
-For ONE alignment split over ranks (BASELINE config 5) the sequence is
+The product path is inside the library: Engine(rank=, world=).connect_ranks() and then Engine.job(), whose kernels
+exchange through peer memory (include/snpgenie_cuda.h, "several GPUs").  What is kept here is the same analysis with
+the two gathers done by NCCL all_gather calls between device-pointer ABI calls; tools/exchange_compare.py times one
+against the other.  For ONE alignment split over ranks the sequence is
 
     rank r:  Engine(rank=r, world=w).set_products(...)      # owns a slice of the global codon axis
              load_group(...)                                 # stages only the columns of that slice
@@ -54,20 +56,27 @@ def all_gather_replicates(local_rep: torch.Tensor, B: int, group=None) -> torch.
 def within_group_sharded(eng, group_id: int, B: int, group=None):
     """Per-product sums [P,4] and SEs [P,6] for one alignment whose codon axis is split over ranks."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    # The library launches on the ctx's own stream and torch/NCCL on theirs: order them explicitly around every
+    # hand-over (the library's calls synchronise their stream before they return; torch's side is drained here).
+    sync = torch.cuda.synchronize
     first, count, total = eng.shard_range()
     assert (first, count) == shard_plan(total, rank, world)
     dev = torch.device("cuda", torch.cuda.current_device())
     local = torch.zeros((max(count, 1), 4), dtype=torch.float64, device=dev)
+    sync()
     eng.within_stats_device(group_id, local.data_ptr())
     stats = all_gather_ragged(local[:count], total, group).contiguous()
+    sync()
     sums = eng.product_sums_device(stats.data_ptr())
     se = None
     if B >= 2:
         b_first, b_count = shard_plan(B, rank, world)
         P = len(eng.products)
         rep = torch.zeros((P, max(b_count, 1), 4), dtype=torch.float64, device=dev)
+        sync()
         if b_count:
             eng.bootstrap_all_device(stats.data_ptr(), b_first, b_count, rep.data_ptr())
         full = all_gather_replicates(rep[:, :b_count], B, group)
+        sync()
         se = eng.rep_moments_device(full.data_ptr(), P, B)
     return sums, se, stats
