@@ -260,7 +260,7 @@ def run_ours(args):
         e = Engine(device=local, seed=SEED, rank=r, world=w)
         e.set_stream(stream.cuda_stream)
         e.set_option(_abi.OPT_KEEP_CODES, 1 if args.route == "codes" else 0)
-        e.set_option(_abi.OPT_FUSED_KERNEL, _abi.FUSED_TMA_TILES if args.route == "tiles" else _abi.FUSED_LDG_SPANS)
+        e.set_option(_abi.OPT_FUSED_KERNEL, {"tiles": _abi.FUSED_TMA_TILES, "spans": _abi.FUSED_TMA_SPANS}.get(args.route, _abi.FUSED_LDG_SPANS))
         e.set_products(products, ALN_LEN)
         return e
 
@@ -313,7 +313,7 @@ def run_ours(args):
     # ---- timed regions ----------------------------------------------------------------------------------------
     # timed passes bracket only the dominant HBM kernel with events (a pair costs ~3 us of stream time);
     # a separate untimed pass of the same steps brackets every launch for the per-kernel table
-    hbm_kinds = ["fused"] if args.route in ("fused", "tiles") else ["pack", "hist"]
+    hbm_kinds = ["fused"] if args.route in ("spans", "fused", "tiles") else ["pack", "hist"]
     narrow = sum(1 << _abi.KERNEL_KINDS.index(k) for k in hbm_kinds)
     eng.set_option(_abi.OPT_PROFILE, 0 if args.no_profile else narrow)
     with ClockSampler(local) as clocks:      # clocks are sampled across both timed regions
@@ -373,12 +373,13 @@ def run_ours(args):
         hbm_kernels = {k: v for k, v in kern.items() if k in alg}
         dom = max(hbm_kernels, key=lambda k: hbm_kernels[k]["ms_per_step"]) if hbm_kernels else ("pack" if args.route == "codes" else "fused")
         achieved = kern[dom]["achieved_gbs"] if dom in kern else float("nan")
-        tiled = eng.tile_launches > 0          # SNPG_K_FUSED launches went to the TMA-tiled kernel
-        kernel_name = {"pack": "k_pack", "hist": "k_hist", "fused": "k_tile_hist" if tiled else "k_fused_hist"}[dom]
+        # which kernel the SNPG_K_FUSED launches went to
+        fused_name = "k_tile_hist" if eng.tile_launches > 0 else "k_span_hist" if eng.span_tma_launches > 0 else "k_fused_hist"
+        kernel_name = {"pack": "k_pack", "hist": "k_hist", "fused": fused_name}[dom]
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-                traffic = json.load(fh).get("tile" if (dom == "fused" and tiled) else dom)
+                traffic = json.load(fh).get({"k_tile_hist": "tile", "k_span_hist": "span"}.get(kernel_name, dom))
             if world > 1:
                 traffic = None                 # captured at N = 1
         except Exception:
@@ -569,9 +570,9 @@ def main():
                     help="fraction of polymorphic codon columns in the synthetic alignment (SURVEY.md 8d: 0.3; "
                          "other values are side experiments, never the bench line)")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket kernels with CUDA events (no roofline block)")
-    ap.add_argument("--route", default="fused", choices=["fused", "tiles", "codes"],
-                    help="histogram route: fused vector-load kernel (default), fused TMA-tiled kernel, or K1 pack + K2 hist "
-                         "over a kept code matrix")
+    ap.add_argument("--route", default="fused", choices=["fused", "spans", "tiles", "codes"],
+                    help="histogram route: vector-load span kernel (default), TMA-fed span kernel, TMA-tiled kernel, or K1 pack + "
+                         "K2 hist over a kept code matrix")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

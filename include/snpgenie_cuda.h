@@ -126,15 +126,19 @@ int snpg_codon_strings(snpg_ctx *ctx, int slot, int product, int64_t codon, uint
  * time is accumulated (snpg_get_profile).  Each pair of events costs a few
  * microseconds of stream time, so time whole jobs with a narrow mask. */
 #define SNPG_OPT_PROFILE 2
-/* SNPG_OPT_FUSED_KERNEL (default SNPG_FUSED_LDG_SPANS): which kernel builds the histograms when no
- * code matrix is kept.  LDG_SPANS: one thread per 16-byte column span with 128-bit loads (the
- * fastest measured on every diversity tried, see profiles/).  TMA_TILES: persistent CTAs,
- * frame-aligned 208-byte x 128-row TMA tensor loads into a shared-memory ring, one lane per group
- * of four codons, chunks claimed from a global counter; falls back to LDG_SPANS when a tensor map
- * cannot describe the buffer.  Both give identical histograms. */
+/* SNPG_OPT_FUSED_KERNEL (default SNPG_FUSED_LDG_SPANS): which kernel builds the histograms when no code matrix is
+ * kept.  All three give identical histograms.
+ * LDG_SPANS: a lane owns a 16-byte column span and compares every row of it with three reference rows; the rows are read
+ * with 128-bit global loads (the fastest measured on every diversity tried, see profiles/).
+ * TMA_SPANS: the same arithmetic with the rows arriving through TMA tensor loads (512 bytes x 4 rows per stage) into a
+ * per-warp shared-memory pipeline, so that the bytes in flight are bounded by shared memory, not by registers.  Falls
+ * back to LDG_SPANS when a tensor map cannot describe the buffer.
+ * TMA_TILES: persistent CTAs, frame-aligned 208-byte x 128-row TMA tensor loads, one lane per group of four codons;
+ * falls back to LDG_SPANS like TMA_SPANS. */
 #define SNPG_OPT_FUSED_KERNEL 4
 #define SNPG_FUSED_TMA_TILES 0
 #define SNPG_FUSED_LDG_SPANS 1
+#define SNPG_FUSED_TMA_SPANS 2
 /* SNPG_OPT_BOOTSTRAP_KERNEL (default SNPG_BOOT_WEIGHTS): how the whole-product bootstrap (wg:854-916) sums a
  * replicate.  WEIGHTS: every draw bumps a 1-byte counter of its slot in shared memory -- a warp turns its
  * replicate into a row of the multinomial weight matrix -- and the block contracts its rows with the product's
@@ -335,6 +339,8 @@ int64_t snpg_launch_count(const snpg_ctx *ctx);
 /* Of those, launches of the TMA-tiled histogram kernel (0 means every fused histogram went
  * through the vector-load kernel: option, or a buffer a tensor map cannot describe). */
 int64_t snpg_tile_launch_count(const snpg_ctx *ctx);
+/* The same for the TMA-fed span kernel (SNPG_FUSED_TMA_SPANS). */
+int64_t snpg_span_tma_launch_count(const snpg_ctx *ctx);
 /* snpg_within_job on a device-resident alignment is captured into a CUDA graph on the second identical call
  * in a row and replayed from then on (same kernels, same results, fewer launch gaps; SNPG_NO_GRAPH=1 in the
  * environment or SNPG_OPT_PROFILE != 0 turns this off).  Number of replays so far: */

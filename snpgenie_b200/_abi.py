@@ -17,7 +17,7 @@ OPT_KEEP_CODES, OPT_PROFILE, OPT_SITE_COUNTS, OPT_FUSED_KERNEL, OPT_BOOTSTRAP_KE
 BOOT_GATHER, BOOT_WEIGHTS = 0, 1
 SLOTS_CORRECTED, SLOTS_FAITHFUL = 0, 1
 PEER_HANDLE_BYTES = 128
-FUSED_TMA_TILES, FUSED_LDG_SPANS = 0, 1
+FUSED_TMA_TILES, FUSED_LDG_SPANS, FUSED_TMA_SPANS = 0, 1, 2
 KERNEL_KINDS = ("pack", "hist", "stats", "sums", "bootstrap", "moments", "window", "other", "fused", "sites")
 
 if not os.path.exists(LIB_PATH):
@@ -86,6 +86,7 @@ SIGNATURES = {
     "snpg_probe_peaks": (C.c_int, [_ctx, _f64p]),
     "snpg_launch_count": (C.c_int64, [_ctx]),
     "snpg_tile_launch_count": (C.c_int64, [_ctx]),
+    "snpg_span_tma_launch_count": (C.c_int64, [_ctx]),
     "snpg_graph_replays": (C.c_int64, [_ctx]),
     "snpg_set_stream": (C.c_int, [_ctx, C.c_void_p]),
     "snpg_get_profile": (C.c_int, [_ctx, _f64p, _i64p, C.c_int]),

@@ -152,7 +152,16 @@ int pack_block(snpg_ctx *ctx, Group &g, const uint8_t *d_block, int64_t pitch, i
         {
             Launch l(ctx, SNPG_K_FUSED);
             alignas(64) unsigned char tmap[128];
-            if (ctx->fused_kernel == SNPG_FUSED_TMA_TILES && ctx->n_tiles > 0 &&
+            bool done = false;
+            if (ctx->fused_kernel == SNPG_FUSED_TMA_SPANS && make_span_tensor_map(tmap, d_block, pitch, rows, row_bytes, ctx->tma_l2_promotion)) {
+                const cudaError_t e = launch_span_hist(tmap, rows, ctx->d_cons.as<uint8_t>(), ctx->d_alt.as<uint32_t>(), ctx->n_spans, ctx->d_runs.as<SpanRun>(),
+                                                       g.hist.as<uint32_t>(), omin, omax, ctx->d_sched.as<uint32_t>(), ctx->n_sms, ctx->stream);
+                if (e == cudaSuccess) { done = true; ctx->span_tma_launches++; }
+                else if (e != cudaErrorInvalidValue) CU(ctx, e);
+                else cudaGetLastError();
+            }
+            if (done) {
+            } else if (ctx->fused_kernel == SNPG_FUSED_TMA_TILES && ctx->n_tiles > 0 &&
                 make_tile_tensor_map(tmap, d_block, pitch, rows, row_bytes, ctx->tma_l2_promotion)) {
                 CU(ctx, launch_tile_hist(tmap, rows, ctx->d_cons.as<uint8_t>(), ctx->d_tiles.as<CodonTile>(), ctx->n_tiles, ctx->n_sms,
                                          ctx->d_sched.as<uint32_t>(), g.hist.as<uint32_t>(), omin, omax, ctx->stream));
@@ -188,13 +197,13 @@ int finish_group(snpg_ctx *ctx, Group &g) {
         ctx->stats_of = nullptr;
         if (with_stats) {
             Launch l(ctx, SNPG_K_OTHER);
-            launch_fused_fixup_stats(ctx->d_cons.as<uint8_t>(), ctx->col_lo - ctx->base_al, ctx->d_alt.as<uint32_t>(), ctx->d_map.as<CodonMap>(),
+            launch_fused_fixup_stats(ctx->d_cons.as<uint8_t>(), ctx->col_lo - ctx->base_al, ctx->d_alt.as<uint32_t>(), ctx->n_spans, ctx->d_map.as<CodonMap>(),
                                      ctx->shard_count, (uint32_t)g.n, g.hist.as<uint32_t>(), omin, omax, view_of(ctx, g, 0),
                                      ctx->d_tables.as<double>(), ctx->job_out, &ctx->job_peer_out, &ctx->job_peer_sync, ctx->stream);
             ctx->stats_of = &g;
         } else {
             Launch l(ctx, SNPG_K_OTHER);
-            launch_fused_fixup(ctx->d_cons.as<uint8_t>(), ctx->col_lo - ctx->base_al, ctx->d_alt.as<uint32_t>(), ctx->d_map.as<CodonMap>(), ctx->d_regular.as<uint8_t>(),
+            launch_fused_fixup(ctx->d_cons.as<uint8_t>(), ctx->col_lo - ctx->base_al, ctx->d_alt.as<uint32_t>(), ctx->n_spans, ctx->d_map.as<CodonMap>(), ctx->d_regular.as<uint8_t>(),
                                ctx->shard_count, (uint32_t)g.n, g.hist.as<uint32_t>(), omin, omax, ctx->stream);
         }
         if (ctx->n_irr) {
@@ -314,7 +323,7 @@ int snpg_set_option(snpg_ctx *ctx, int option, int64_t value) {
         return SNPG_OK;
     }
     if (option == SNPG_OPT_FUSED_KERNEL) {
-        NEED(ctx, value == SNPG_FUSED_TMA_TILES || value == SNPG_FUSED_LDG_SPANS, SNPG_E_ARG, "unknown fused kernel %lld", (long long)value);
+        NEED(ctx, value == SNPG_FUSED_TMA_TILES || value == SNPG_FUSED_LDG_SPANS || value == SNPG_FUSED_TMA_SPANS, SNPG_E_ARG, "unknown fused kernel %lld", (long long)value);
         ctx->fused_kernel = (int)value;
         return SNPG_OK;
     }
@@ -493,7 +502,7 @@ int snpg_set_products(snpg_ctx *ctx, int n_products, const int64_t *seg_ofs, con
         CU(ctx, ctx->d_runs.ensure(sizeof(SpanRun) * runs.size()));
         CU(ctx, ctx->d_regular.ensure(regular.size()));
         CU(ctx, ctx->d_cons.ensure((size_t)(n_spans * 16 + 512)));     // the tile kernel copies 208-byte windows of it
-        CU(ctx, ctx->d_alt.ensure(sizeof(uint32_t) * kAltWords * (size_t)std::max<int64_t>(1, n_spans)));
+        CU(ctx, ctx->d_alt.ensure(sizeof(uint32_t) * (size_t)alt_words(std::max<int64_t>(1, n_spans))));
         CU(ctx, cudaMemcpy(ctx->d_runs.p, runs.data(), sizeof(SpanRun) * runs.size(), cudaMemcpyHostToDevice));
         CU(ctx, cudaMemcpy(ctx->d_regular.p, regular.data(), regular.size(), cudaMemcpyHostToDevice));
         CU(ctx, cudaMemset(ctx->d_cons.p, 0, (size_t)(n_spans * 16 + 512)));
@@ -1032,6 +1041,13 @@ int64_t snpg_tile_launch_count(const snpg_ctx *ctx) {
     if (!ctx) return 0;
     int64_t n = ctx->tile_launches;
     for (const snpg_ctx *c : ctx->team) n += c->tile_launches;
+    return n;
+}
+
+int64_t snpg_span_tma_launch_count(const snpg_ctx *ctx) {
+    if (!ctx) return 0;
+    int64_t n = ctx->span_tma_launches;
+    for (const snpg_ctx *c : ctx->team) n += c->span_tma_launches;
     return n;
 }
 

@@ -22,8 +22,16 @@ struct PeerHandle {                 // SNPG_PEER_HANDLE_BYTES, plain bytes for t
     uint32_t magic; int32_t pid; int32_t device; int32_t rank; int32_t world; int32_t P;
     int64_t total, max_B; uint64_t bytes; uint64_t ptr;
     cudaIpcMemHandle_t ipc;         // 64 bytes
-    uint8_t pad[SNPG_PEER_HANDLE_BYTES - 4 * 6 - 8 * 4 - 64];
+    uint32_t pci;                   // domain << 16 | bus << 8 | device: which physical GPU (ordinals differ between processes)
+    uint8_t pad[SNPG_PEER_HANDLE_BYTES - 4 * 6 - 8 * 4 - 64 - 4];
 };
+uint32_t pci_of(int device) {
+    int dom = 0, bus = 0, dev = 0;
+    cudaDeviceGetAttribute(&dom, cudaDevAttrPciDomainId, device);
+    cudaDeviceGetAttribute(&bus, cudaDevAttrPciBusId, device);
+    cudaDeviceGetAttribute(&dev, cudaDevAttrPciDeviceId, device);
+    return ((uint32_t)dom << 16) | ((uint32_t)bus << 8) | (uint32_t)dev;
+}
 static_assert(sizeof(PeerHandle) == SNPG_PEER_HANDLE_BYTES, "handle size is part of the ABI");
 constexpr uint32_t kHandleMagic = 0x58504E53u;   // "SNPX"
 
@@ -120,7 +128,7 @@ int snpg_peer_export(snpg_ctx *ctx, int64_t max_bootstraps, void *handle) {
     PeerHandle h;
     memset(&h, 0, sizeof h);
     h.magic = kHandleMagic; h.pid = (int32_t)getpid(); h.device = ctx->device; h.rank = ctx->rank; h.world = ctx->world; h.P = X.P;
-    h.total = X.total; h.max_B = X.max_B; h.bytes = X.bytes; h.ptr = (uint64_t)(uintptr_t)X.region.p;
+    h.total = X.total; h.max_B = X.max_B; h.bytes = X.bytes; h.ptr = (uint64_t)(uintptr_t)X.region.p; h.pci = pci_of(ctx->device);
     CU(ctx, cudaIpcGetMemHandle(&h.ipc, X.region.p));
     memcpy(handle, &h, sizeof h);
     return SNPG_OK;
@@ -134,6 +142,7 @@ int snpg_peer_connect(snpg_ctx *ctx, const void *handles, int n_handles) {
     NEED(ctx, n_handles == ctx->world, SNPG_E_ARG, "%d handles for %d ranks", n_handles, ctx->world);
     if (int rc = bind(ctx)) return rc;
     const PeerHandle *H = static_cast<const PeerHandle *>(handles);
+    X.peer_on_my_gpu = false;
     for (int r = 0; r < ctx->world; r++) {
         PeerHandle h;
         memcpy(&h, H + r, sizeof h);
@@ -141,6 +150,10 @@ int snpg_peer_connect(snpg_ctx *ctx, const void *handles, int n_handles) {
         NEED(ctx, h.total == X.total && h.P == X.P && h.max_B == X.max_B && h.bytes == X.bytes, SNPG_E_ARG,
              "rank %d exported a different layout (annotation or max_bootstraps differ)", r);
         if (r == ctx->rank) continue;
+        // a peer on this very GPU (tests, a one-GPU box): kernels of the two ranks then compete for the same SMs, and a
+        // grid of blocks that all wait for the peer could keep the peer's producer from ever starting -- the job puts its
+        // waits into one-block kernels ahead of the consumers instead (job.cu)
+        if (h.pci == pci_of(ctx->device)) X.peer_on_my_gpu = true;
         if (h.pid == (int32_t)getpid()) {
             // same process: the pointer itself, once this device may dereference it
             if (h.device != ctx->device) {

@@ -111,20 +111,47 @@ int job_prepare(snpg_ctx *ctx, const snpg_job &job) {
     return SNPG_OK;
 }
 
+// The outputs of a snpg_job, by number (a replayed graph copies into the CURRENT call's arrays).
+enum Field { F_PROD_SUMS, F_PROD_SE, F_PROD_UNDEF, F_POLY, F_NDEF, F_CMP, F_STATS, F_CONS, F_WIN_SUMS, F_WIN_SE, F_COUNT };
+void *field_ptr(const snpg_job &j, int f) {
+    switch (f) {
+    case F_PROD_SUMS: return j.prod_sums; case F_PROD_SE: return j.prod_se; case F_PROD_UNDEF: return j.prod_undefined;
+    case F_POLY: return j.poly; case F_NDEF: return j.n_defined; case F_CMP: return j.comparisons; case F_STATS: return j.stats4;
+    case F_CONS: return j.conserved; case F_WIN_SUMS: return j.win_sums; case F_WIN_SE: return j.win_se;
+    }
+    return nullptr;
+}
+bool staged_field(int f) { return f == F_PROD_SUMS || f == F_PROD_SE || f == F_PROD_UNDEF || f == F_WIN_SUMS || f == F_WIN_SE; }
+
+// What identifies a job for graph replay: sizes and options, and of the outputs only what the captured copies depend
+// on -- whether an output is wanted, and the address of those written directly (pinned per-codon tables).  Everything
+// else goes through the ctx's staging buffer and may live anywhere from call to call.
+snpg_job job_signature(const snpg_job &job) {
+    snpg_job k = job;
+    void **fields[] = {(void **)&k.prod_sums, (void **)&k.prod_se, (void **)&k.prod_undefined, (void **)&k.poly, (void **)&k.n_defined,
+                       (void **)&k.comparisons, (void **)&k.stats4, (void **)&k.conserved, (void **)&k.win_sums, (void **)&k.win_se};
+    for (int f = 0; f < F_COUNT; f++) {
+        void *p = *fields[f];
+        if (p && (staged_field(f) || !is_pinned(p))) *fields[f] = reinterpret_cast<void *>(1);
+    }
+    return k;
+}
+
 // device -> host copy of one output: straight into pinned memory, else through the ctx's pinned staging (the host
 // copy to the caller's array follows the job's synchronisation)
 struct Stager {
-    snpg_ctx *ctx; size_t used = 0;
-    int put(void *dst, const void *src, size_t bytes, cudaStream_t stream, bool always_stage = false) {
+    snpg_ctx *ctx; const snpg_job *job; size_t used = 0;
+    int put(int field, const void *src, size_t bytes, cudaStream_t stream) {
+        void *dst = field_ptr(*job, field);
         if (!dst || bytes == 0) return SNPG_OK;
-        if (!always_stage && is_pinned(dst)) {
+        if (!staged_field(field) && is_pinned(dst)) {
             CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
             return SNPG_OK;
         }
         const size_t at = (used + 15) & ~(size_t)15;
         NEED(ctx, at + bytes <= ctx->h_out_cap, SNPG_E_NOMEM, "output staging too small");
         CU(ctx, cudaMemcpyAsync(ctx->h_out + at, src, bytes, cudaMemcpyDeviceToHost, stream));
-        ctx->pending.push_back({dst, ctx->h_out + at, bytes});
+        ctx->pending.push_back({field, ctx->h_out + at, bytes});
         used = at + bytes;
         return SNPG_OK;
     }
@@ -184,7 +211,7 @@ int job_record(snpg_ctx *ctx, int group, const uint8_t *bases, int on_device, ui
     const int64_t *ofs = multi ? ctx->d_full_ofs.as<int64_t>() : ctx->d_local_ofs.as<int64_t>();
     const int *order = multi ? ctx->d_order_full.as<int>() : ctx->d_order_local.as<int>();
     const int64_t max_codons = multi ? ctx->max_codons_full : ctx->max_codons_local;
-    Stager st{ctx};
+    Stager st{ctx, &job};
 
     // the per-codon tables leave on the copy stream while the bootstrap runs
     const bool codon_out = job.poly || job.n_defined || job.comparisons || job.stats4 || job.conserved;
@@ -196,11 +223,11 @@ int job_record(snpg_ctx *ctx, int group, const uint8_t *bases, int on_device, ui
         const uint8_t *d_cons = multi ? X.at<uint8_t>(ctx->rank, parity, X.off_cons) : ctx->s_cons.as<uint8_t>();
         const uint32_t *d_ndef = multi ? X.at<uint32_t>(ctx->rank, parity, X.off_ndef) : ctx->s_nda.as<uint32_t>();
         const uint64_t *d_cmp = multi ? X.at<uint64_t>(ctx->rank, parity, X.off_cmp) : ctx->s_cmp.as<uint64_t>();
-        if (int rc = st.put(job.stats4, stats, sizeof(double) * 4 * (size_t)axis, ctx->copy_stream)) return rc;
-        if (int rc = st.put(job.comparisons, d_cmp, sizeof(uint64_t) * (size_t)axis, ctx->copy_stream)) return rc;
-        if (int rc = st.put(job.n_defined, d_ndef, sizeof(uint32_t) * (size_t)axis, ctx->copy_stream)) return rc;
-        if (int rc = st.put(job.poly, d_poly, (size_t)axis, ctx->copy_stream)) return rc;
-        if (int rc = st.put(job.conserved, d_cons, (size_t)axis, ctx->copy_stream)) return rc;
+        if (int rc = st.put(F_STATS, stats, sizeof(double) * 4 * (size_t)axis, ctx->copy_stream)) return rc;
+        if (int rc = st.put(F_CMP, d_cmp, sizeof(uint64_t) * (size_t)axis, ctx->copy_stream)) return rc;
+        if (int rc = st.put(F_NDEF, d_ndef, sizeof(uint32_t) * (size_t)axis, ctx->copy_stream)) return rc;
+        if (int rc = st.put(F_POLY, d_poly, (size_t)axis, ctx->copy_stream)) return rc;
+        if (int rc = st.put(F_CONS, d_cons, (size_t)axis, ctx->copy_stream)) return rc;
         CU(ctx, cudaEventRecord(ctx->ev_join, ctx->copy_stream));
     }
 
@@ -216,6 +243,8 @@ int job_record(snpg_ctx *ctx, int group, const uint8_t *bases, int on_device, ui
     } else {
         int64_t b_first = 0, b_count = B;
         if (multi) snpg_shard_plan(B, ctx->rank, ctx->world, &b_first, &b_count);
+        // (ranks that share a GPU: a full grid of waiting blocks could keep the peer's producer off the SMs)
+        if (multi && X.peer_on_my_gpu) { Launch l(ctx, SNPG_K_OTHER); launch_peer_wait(ps, kStageStats, ctx->stream); }
         {
             Launch l(ctx, SNPG_K_BOOT);
             BootArgs a;
@@ -233,6 +262,7 @@ int job_record(snpg_ctx *ctx, int group, const uint8_t *bases, int on_device, ui
             launch_bootstrap(ctx->boot_kernel, a, max_codons, ctx->stream);
         }
         stats_arrived = true;             // every block of the bootstrap waited for them
+        if (multi && X.peer_on_my_gpu) { Launch l(ctx, SNPG_K_OTHER); launch_peer_wait(ps, kStageVals, ctx->stream); }
         {
             Launch l(ctx, SNPG_K_MOMENTS);
             const double *vals = multi ? X.at<double>(ctx->rank, parity, X.off_vals) : ctx->s_vals.as<double>();
@@ -262,49 +292,44 @@ int job_record(snpg_ctx *ctx, int group, const uint8_t *bases, int on_device, ui
     }
     CU(ctx, cudaGetLastError());
     // the small tables always go through the staging buffer (one pinned line each)
-    if (int rc = st.put(job.prod_sums, ctx->s_sums.p, sizeof(double) * 4 * (size_t)P, ctx->stream, true)) return rc;
+    if (int rc = st.put(F_PROD_SUMS, ctx->s_sums.p, sizeof(double) * 4 * (size_t)P, ctx->stream)) return rc;
     if (boot) {
-        if (int rc = st.put(job.prod_se, ctx->s_se.p, sizeof(double) * 6 * (size_t)P, ctx->stream, true)) return rc;
-        if (int rc = st.put(job.prod_undefined, ctx->s_undef.p, sizeof(uint32_t) * 6 * (size_t)P, ctx->stream, true)) return rc;
+        if (int rc = st.put(F_PROD_SE, ctx->s_se.p, sizeof(double) * 6 * (size_t)P, ctx->stream)) return rc;
+        if (int rc = st.put(F_PROD_UNDEF, ctx->s_undef.p, sizeof(uint32_t) * 6 * (size_t)P, ctx->stream)) return rc;
     }
     if (nwin > 0) {
-        if (int rc = st.put(job.win_sums, ctx->w_sums.p, sizeof(double) * 4 * (size_t)nwin, ctx->stream, true)) return rc;
-        if (win_boot) {
-            // win_se is [n][3]; the device holds [n][6]: the staging copy is compacted on the host
-            const size_t at = (st.used + 15) & ~(size_t)15, bytes = sizeof(double) * 6 * (size_t)nwin;
-            NEED(ctx, at + bytes <= ctx->h_out_cap, SNPG_E_NOMEM, "output staging too small");
-            CU(ctx, cudaMemcpyAsync(ctx->h_out + at, ctx->w_se.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-            ctx->pending.push_back({job.win_se, ctx->h_out + at, 0});       // bytes = 0 marks the [n][6] -> [n][3] compaction
-            ctx->pending.push_back({nullptr, nullptr, (size_t)nwin});
-            st.used = at + bytes;
-        }
+        if (int rc = st.put(F_WIN_SUMS, ctx->w_sums.p, sizeof(double) * 4 * (size_t)nwin, ctx->stream)) return rc;
+        // win_se is [n][3]; the device holds [n][6]: the staged copy is compacted on the host (apply_pending)
+        if (win_boot)
+            if (int rc = st.put(F_WIN_SE, ctx->w_se.p, sizeof(double) * 6 * (size_t)nwin, ctx->stream)) return rc;
     }
     if (codon_out) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     return SNPG_OK;
 }
 
-void apply_pending(snpg_ctx *ctx) {
-    for (size_t i = 0; i < ctx->pending.size(); i++) {
-        const auto &c = ctx->pending[i];
-        if (c.bytes) { memcpy(c.dst, c.src, c.bytes); continue; }
-        const size_t n = ctx->pending[++i].bytes;                           // window SEs: first three of six per window
+void apply_pending(snpg_ctx *ctx, const snpg_job &job) {
+    for (const auto &c : ctx->pending) {
+        void *dst = field_ptr(job, c.field);
+        if (!dst) continue;
+        if (c.field != F_WIN_SE) { memcpy(dst, c.src, c.bytes); continue; }
+        const size_t n = c.bytes / (6 * sizeof(double));                    // window SEs: the first three of six per window
         const double *src = static_cast<const double *>(c.src);
-        double *dst = static_cast<double *>(c.dst);
+        double *d = static_cast<double *>(dst);
         for (size_t k = 0; k < n; k++)
-            for (int q = 0; q < 3; q++) dst[3 * k + q] = src[6 * k + q];
+            for (int q = 0; q < 3; q++) d[3 * k + q] = src[6 * k + q];
     }
     ctx->pending.clear();
 }
 
 // Captures the job into a CUDA graph.  Any failure leaves no graph behind and reports SNPG_E_STATE so that the
 // caller runs the job the ordinary way.
-int capture_job_graph(snpg_ctx *ctx, snpg_ctx::JobGraph &J, const snpg_ctx::JobKey &key) {
+int capture_job_graph(snpg_ctx *ctx, snpg_ctx::JobGraph &J, const snpg_ctx::JobKey &key, const snpg_job &job) {
     const uint64_t epoch0 = g_alloc_epoch;
-    const int64_t l0 = ctx->launches, t0 = ctx->tile_launches;
+    const int64_t l0 = ctx->launches, t0 = ctx->tile_launches, t1 = ctx->span_tma_launches;
     if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return SNPG_E_STATE; }
     ctx->capturing = true;
     ctx->capturing_into = &J;
-    int rc = job_record(ctx, key.group, key.bases, 1, key.n, key.len, key.stride, key.job, key.parity);
+    int rc = job_record(ctx, key.group, key.bases, 1, key.n, key.len, key.stride, job, key.parity);
     ctx->capturing = false;
     ctx->capturing_into = nullptr;
     cudaGraph_t graph = nullptr;
@@ -316,6 +341,7 @@ int capture_job_graph(snpg_ctx *ctx, snpg_ctx::JobGraph &J, const snpg_ctx::JobK
         J.epoch = g_alloc_epoch;
         J.n_launches = ctx->launches - l0;
         J.n_tile_launches = ctx->tile_launches - t0;
+        J.n_span_tma_launches = ctx->span_tma_launches - t1;
         J.pending = ctx->pending;
     } else {
         rc = SNPG_E_STATE;
@@ -325,6 +351,7 @@ int capture_job_graph(snpg_ctx *ctx, snpg_ctx::JobGraph &J, const snpg_ctx::JobK
     ctx->pending.clear();
     ctx->launches = l0;                 // nothing ran yet: the replay counts them
     ctx->tile_launches = t0;
+    ctx->span_tma_launches = t1;
     return rc;
 }
 
@@ -348,7 +375,7 @@ int job_enqueue(snpg_ctx *ctx, int group, const uint8_t *bases, int on_device, u
     snpg_ctx::JobKey key;
     key.profile_mask = ctx->profile_mask; key.group = group; key.bases = bases; key.n = n_seqs; key.len = aln_len; key.stride = row_stride;
     key.keep_codes = ctx->keep_codes; key.site_counts = ctx->site_counts; key.fused_kernel = ctx->fused_kernel; key.boot_kernel = ctx->boot_kernel;
-    key.boot_slot0 = ctx->boot_slot0; key.parity = parity; key.job = job;
+    key.boot_slot0 = ctx->boot_slot0; key.parity = parity; key.job = job_signature(job);
     const bool eligible = graphs_on && bases && on_device && !ctx->job_graphs_disabled;
     if (eligible) {
         auto &J = ctx->job_graph[parity];
@@ -357,12 +384,13 @@ int job_enqueue(snpg_ctx *ctx, int group, const uint8_t *bases, int on_device, u
         cand.parity = 0;
         if (!J.exec && ctx->job_candidate == cand && ctx->job_candidate_epoch == g_alloc_epoch) {
             // the same job again with every buffer already in place: capture it
-            if (capture_job_graph(ctx, J, key) != SNPG_OK) { drop_graph(ctx, J); ctx->job_graphs_disabled = true; }
+            if (capture_job_graph(ctx, J, key, job) != SNPG_OK) { drop_graph(ctx, J); ctx->job_graphs_disabled = true; }
         }
         if (J.exec) {
             CU(ctx, cudaGraphLaunch(J.exec, ctx->stream));
             ctx->launches += J.n_launches;
             ctx->tile_launches += J.n_tile_launches;
+            ctx->span_tma_launches += J.n_span_tma_launches;
             ctx->graph_replays++;
             ctx->pending = J.pending;
             // the load inside the graph bypassed the host-side bookkeeping of the group
@@ -382,14 +410,14 @@ int job_enqueue(snpg_ctx *ctx, int group, const uint8_t *bases, int on_device, u
     return rc;
 }
 
-int job_finish(snpg_ctx *ctx, snpg_ctx::JobGraph *replayed) {
+int job_finish(snpg_ctx *ctx, snpg_ctx::JobGraph *replayed, const snpg_job &job) {
     CU(ctx, sync_stream(ctx));
     if (replayed)
         for (auto &sp : replayed->spans) {
             float ms = 0;
             if (cudaEventElapsedTime(&ms, sp.e0, sp.e1) == cudaSuccess) { ctx->kernel_ms[sp.kind] += ms; ctx->kernel_calls[sp.kind]++; }
         }
-    apply_pending(ctx);
+    apply_pending(ctx, job);
     return exchange_check_error(ctx);
 }
 
@@ -428,7 +456,7 @@ int team_job(snpg_ctx *team, int group, const uint8_t *bases, int on_device, uin
     }
     for (snpg_ctx *c : team->team) {
         bind(c);
-        const int rc = job_finish(c, nullptr);
+        const int rc = job_finish(c, nullptr, c == team->team[0] ? *job : quiet);
         if (rc && !first_rc) { first_rc = rc; failed = c; }
     }
     return first_rc ? team_fail(team, failed, first_rc) : SNPG_OK;
@@ -459,7 +487,7 @@ int snpg_within_job_ex(snpg_ctx *ctx, int group, const uint8_t *bases, int bases
     if (int rc = job_prepare(ctx, *job)) return rc;
     snpg_ctx::JobGraph *replayed = nullptr;
     const int rc = job_enqueue(ctx, group, bases, bases_on_device, n_seqs, aln_len, row_stride, *job, &replayed);
-    const int rc2 = job_finish(ctx, replayed);      // also after a failed enqueue: the stream must be drained
+    const int rc2 = job_finish(ctx, replayed, *job);      // also after a failed enqueue: the stream must be drained
     return rc ? rc : rc2;
 }
 

@@ -20,6 +20,7 @@
 #include "../../include/snpgenie_cuda.h"
 #include "snpg_internal.h"
 #include "snpg_peer.cuh"
+#include "snpg_span.cuh"
 
 namespace snpg {
 
@@ -31,6 +32,13 @@ __device__ __forceinline__ uint4 ld_stream_v4(const uint4 *p) {
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+
+__device__ __forceinline__ uint4 ld_nc_v4(const uint4 *p) {          // may hit a line a prefetch brought into L1
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -212,29 +220,6 @@ constexpr int kFusedSpans = 31;                                       // spans p
 constexpr int kFusedTailRows = 4;                                     // rows per chunk in the fine-grained tail region
 static_assert(kHistBins % 3 == 0, "the decode steps through hist[] by kHistBins / 3 per byte of codon offset");
 
-// Flags of the nonzero bytes of d, gathered into bits 28..31 (byte 0 -> bit 28).
-__device__ __forceinline__ uint32_t nonzero_bytes_hi(uint32_t d) {
-    const uint32_t t = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
-    return t * 0x00204081u;                                           // bits 7,15,23,31 -> 28..31, no carries
-}
-
-__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t r; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(a) : "memory"); return r; }
-// The chunk counter is bumped by one lane.  one = 1 comes in a register ptxas cannot prove warp-uniform:
-// with a constant it turns the add into a warp-aggregated atomic whose result is shuffled at once, which
-// makes the warp wait for the claim it meant to hide behind the current chunk.
-__device__ __forceinline__ uint32_t claim_async(uint32_t *ctr, uint32_t one) {
-    uint32_t r;
-    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(r) : "l"(ctr), "r"(one) : "memory");
-    return r;
-}
-// k / d and k % d from m = floor(2^32 / d) (0xFFFFFFFF for d = 1): the estimate is at most one short.
-__device__ __forceinline__ void div_mod(uint32_t k, uint32_t d, uint32_t m, uint32_t &q, uint32_t &r) {
-    q = __umulhi(k, m);
-    r = k - q * d;
-    if (r >= d) { q++; r -= d; }
-    if (r >= d) { q++; r -= d; }
-}
-
 // One parked (span, row): decode and count exactly the codons that contain a byte
 // differing from the consensus.  e = shared-memory address of 5 raw words + span index.
 __device__ __forceinline__ void fused_decode(uint32_t e, const uint8_t *__restrict__ cons,
@@ -251,12 +236,7 @@ __device__ __forceinline__ void fused_decode(uint32_t e, const uint8_t *__restri
     const uint4 c = __ldg(reinterpret_cast<const uint4 *>(cons + (size_t)sp * 16));
     const uint32_t c4 = __ldg(reinterpret_cast<const uint32_t *>(cons + (size_t)sp * 16 + 16));
     uint2 rw = __ldg(rp);                                             // the first run, asked for with the consensus
-    // m20: bit b set when byte b of the 20-byte window differs from the consensus
-    uint32_t m20 = nonzero_bytes_hi(t.x ^ c4) >> 28;
-    m20 = __funnelshift_l(nonzero_bytes_hi(v.w ^ c.w), m20, 4);
-    m20 = __funnelshift_l(nonzero_bytes_hi(v.z ^ c.z), m20, 4);
-    m20 = __funnelshift_l(nonzero_bytes_hi(v.y ^ c.y), m20, 4);
-    m20 = __funnelshift_l(nonzero_bytes_hi(v.x ^ c.x), m20, 4);
+    const uint32_t m20 = diff_mask20(v, t.x, c, c4);
 #pragma unroll 1
     for (int l = 0;;) {
         const uint32_t cnt = (rw.y >> 8) & 0xFFu;
@@ -307,7 +287,7 @@ __device__ __forceinline__ void fused_decode(uint32_t e, const uint8_t *__restri
 // zeroed for the next launch.
 // UNROLL rows are loaded at a time; parked spans are decoded after every DRAIN_EVERY rows, so the ring needs
 // 31 + 32 * DRAIN_EVERY entries (QUEUE, a power of two).  inv_sb = floor(2^32 / n_sb).
-template <int UNROLL, int DRAIN_EVERY, int QUEUE, int MIN_BLOCKS>
+template <int UNROLL, int DRAIN_EVERY, int QUEUE, int MIN_BLOCKS, int PREFETCH = 0>
 __global__ void __launch_bounds__(kFusedWarps * 32, MIN_BLOCKS)
 k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, uint32_t n_rows, const uint8_t *__restrict__ cons,
              uint32_t *__restrict__ alt, uint32_t n_spans, const SpanRun *__restrict__ runs, uint32_t *__restrict__ hist,
@@ -335,6 +315,7 @@ k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, uint32_t n_rows, co
     unsigned lt = (1u << lane) - 1;
     const uint32_t lane_ofs = lane * kFusedEntryBytes;
     uint32_t one = 1u + (uint32_t)lane;          // 1 in lane 0, the only lane that claims
+    const RefPlanes refs = ref_planes(alt, n_spans);
 
     auto drain = [&]() {     // at most 31 + 32 * DRAIN_EVERY parked entries between drains
         while (q_tail - q_head >= 32u * kFusedEntryBytes) {
@@ -363,11 +344,8 @@ k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, uint32_t n_rows, co
         const uint32_t c4 = *reinterpret_cast<const uint32_t *>(cons + (size_t)sp * 16 + 16);
         // the span's second and third reference: its most common non-consensus bytes among the sampled rows (the
         // consensus itself when the sample had none).  Rows equal to one of them are only counted here.
-        const uint32_t *ap = alt + (size_t)sp * kAltWords;
-        const uint4 a = *reinterpret_cast<const uint4 *>(ap);
-        const uint32_t a4 = ap[4];
-        const uint4 b = *reinterpret_cast<const uint4 *>(ap + kAltSecond);
-        const uint32_t b4 = ap[kAltSecond + 4];
+        const uint4 a = refs.a16[sp], b = refs.b16[sp];
+        const uint32_t tails = refs.tails[sp], a4 = tails & 0xFFFFu, b4 = tails >> 16;
         uint32_t n_alt = 0, n_alt2 = 0;
         const uint8_t *p = aln + (size_t)min(span, n_spans) * 16 + (size_t)row0 * pitch;
 
@@ -377,8 +355,8 @@ k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, uint32_t n_rows, co
             const uint32_t d = ((v.x ^ c.x) | (v.y ^ c.y) | (v.z ^ c.z) | (v.w ^ c.w) | ((v4 ^ c4) & 0xFFFFu)) & live;
             const uint32_t da = (v.x ^ a.x) | (v.y ^ a.y) | (v.z ^ a.z) | (v.w ^ a.w) | ((v4 ^ a4) & 0xFFFFu);
             const uint32_t db = (v.x ^ b.x) | (v.y ^ b.y) | (v.z ^ b.z) | (v.w ^ b.w) | ((v4 ^ b4) & 0xFFFFu);
-            n_alt += (da == 0 && d != 0) ? 1u : 0u;
-            n_alt2 += (db == 0 && da != 0 && d != 0) ? 1u : 0u;
+            n_alt += da == 0 ? 1u : 0u;          // the three references are pairwise distinct: at most one matches
+            n_alt2 += db == 0 ? 1u : 0u;
             const bool differs = d != 0 && da != 0 && db != 0;
             const unsigned bal = __ballot_sync(kFull, differs);
             if (bal) {           // nothing to park on most rows of a realistic alignment
@@ -400,8 +378,16 @@ k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, uint32_t n_rows, co
             uint4 v[UNROLL];
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) {
-                v[u] = ld_stream_v4(reinterpret_cast<const uint4 *>(p));
+                v[u] = PREFETCH ? ld_nc_v4(reinterpret_cast<const uint4 *>(p)) : ld_stream_v4(reinterpret_cast<const uint4 *>(p));
                 p += pitch;
+            }
+            if (PREFETCH) {      // the next group of rows into L1 while this one is compared (experiment)
+                const uint8_t *q = p;
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++) {
+                    if (PREFETCH == 1 || (lane & 7) == 0 || lane == 31) prefetch_l1(q);
+                    q += pitch;
+                }
             }
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) {
@@ -415,8 +401,8 @@ k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, uint32_t n_rows, co
             row(v);
             drain();
         }
-        if (n_alt) atomicAdd(&alt[(size_t)sp * kAltWords + kAltCount], n_alt);
-        if (n_alt2) atomicAdd(&alt[(size_t)sp * kAltWords + kAltSecond + kAltCount], n_alt2);
+        if (live && n_alt) atomicAdd(&refs.cnt_a[sp], n_alt);
+        if (live && n_alt2) atomicAdd(&refs.cnt_b[sp], n_alt2);
         k = __shfl_sync(kFull, k_next, 0);
     }
     __syncwarp();
@@ -426,11 +412,13 @@ k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, uint32_t n_rows, co
     if (t == 0 && atomicAdd(&sched[1], 1u) == gridDim.x - 1) { sched[0] = 0; sched[1] = 0; }
 }
 
-// The two reference rows of the compare-with-reference kernels, from the first n_sample (<= 32) rows of
+// The three reference rows of the compare-with-reference kernels, from the first n_sample (<= 32) rows of
 // the group.  One warp per 16-byte span, one lane per sampled row.
-//   cons[column]        the most frequent byte of every column (lowest row on ties)
-//   alt[span][kAltWords] the span's most frequent 18-byte pattern (16 bytes + the 2 a codon may reach into
-//                       the next span) that differs from the consensus; the consensus if no sampled row differs
+//   cons[column]   the most frequent byte of every column (lowest row on ties)
+//   alt            (RefPlanes, snpg_span.cuh) the span's two most frequent 18-byte patterns (16 bytes + the 2 a codon may
+//                  reach into the next span) that differ from the consensus.  A span whose sample has fewer patterns gets
+//                  made-up ones (the consensus with bit 7 of byte 0 or byte 1 flipped), so that the three references are
+//                  always pairwise distinct and a row can equal at most one of them.
 // ANY rows are valid references (the kernels are exact for every choice); frequent ones just keep more
 // rows off the decode path (a first sequence carrying minor alleles would make most rows differ).
 // Span n_spans only supplies the look-ahead bytes of the last real span.
@@ -483,28 +471,51 @@ k_vote_refs(const uint8_t *__restrict__ aln, int64_t pitch, int n_sample, int64_
     const unsigned same = __match_any_sync(kFull, x[0]) & __match_any_sync(kFull, x[1]) & __match_any_sync(kFull, x[2]) &
                           __match_any_sync(kFull, x[3]) & __match_any_sync(kFull, x[4]) & valid;
     unsigned taken = 0;                                             // the sampled rows that carry an already chosen pattern
+    uint32_t pat[2][5];
+    bool real[2];
     for (int r = 0; r < 2; r++) {
         uint32_t key = differs && !((taken >> lane) & 1u) ? ((uint32_t)__popc(same) << 5) | (uint32_t)(31 - lane) : 0u;   // most frequent, lowest row on ties
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(kFull, key, o));
         const int src = 31 - (int)(key & 31u);
-        uint32_t w[5];
 #pragma unroll
-        for (int k = 0; k < 5; k++) w[k] = __shfl_sync(kFull, x[k], src);
+        for (int k = 0; k < 5; k++) pat[r][k] = __shfl_sync(kFull, x[k], src);
         taken |= __shfl_sync(kFull, same, src);
-        if (lane == 0) {
-            uint32_t *o = alt + sp * kAltWords + r * kAltSecond;
+        real[r] = key != 0;
+    }
+    if (lane == 0) {
+        // made-up patterns where the sample had none: distinct from the consensus and from each other
+        if (!real[0]) {
 #pragma unroll
-            for (int k = 0; k < 5; k++) o[k] = key ? w[k] : c[k];
-            o[kAltCount] = 0;      // rows equal to this pattern, counted by k_fused_hist, spent by k_fused_fixup
+            for (int k = 0; k < 5; k++) pat[0][k] = c[k];
+            pat[0][0] ^= 0x80u;
         }
+        if (!real[1]) {
+            const bool clash = pat[0][0] == (c[0] ^ 0x8000u) && pat[0][1] == c[1] && pat[0][2] == c[2] && pat[0][3] == c[3] && pat[0][4] == c[4];
+#pragma unroll
+            for (int k = 0; k < 5; k++) pat[1][k] = c[k];
+            pat[1][0] ^= real[0] && clash ? 0x80u : 0x8000u;
+        }
+        const RefPlanes refs = ref_planes(alt, n_spans);
+        refs.a16[sp] = make_uint4(pat[0][0], pat[0][1], pat[0][2], pat[0][3]);
+        refs.b16[sp] = make_uint4(pat[1][0], pat[1][1], pat[1][2], pat[1][3]);
+        refs.tails[sp] = (pat[0][4] & 0xFFFFu) | (pat[1][4] << 16);
+        refs.cnt_a[sp] = 0;        // rows equal to the pattern, counted by the histogram kernels, spent by the fix-up
+        refs.cnt_b[sp] = 0;
     }
 }
 
 // After all row blocks: credit the consensus codon of every regular codon with the rows that never reached
 // the decode path.  The consensus codon's code (and, for an 'other' codon, its character key) comes straight
 // from the consensus row and the codon index map.
-__device__ __forceinline__ void fixup_codon(const uint8_t *__restrict__ cons, int64_t cons_shift, const uint32_t *__restrict__ alt,
+// Byte of the span's second (r = 0) or third (r = 1) reference at column q (relative to the first span): the pattern planes
+// are byte rows over the columns; the two bytes a codon reaches into the next span come from the span's tails word.
+__device__ __forceinline__ uint8_t ref_byte(const RefPlanes &refs, int r, int64_t sp, int64_t q) {
+    if ((q >> 4) == sp) return reinterpret_cast<const uint8_t *>(r ? refs.b16 : refs.a16)[q];
+    return (uint8_t)(refs.tails[sp] >> (16 * r + 8 * (int)(q & 15)));
+}
+
+__device__ __forceinline__ void fixup_codon(const uint8_t *__restrict__ cons, int64_t cons_shift, const RefPlanes &refs,
                                             const CodonMap *__restrict__ map, int64_t c, uint32_t n_rows, uint32_t *__restrict__ hist,
                                             uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max, int lane)
 {
@@ -530,11 +541,9 @@ __device__ __forceinline__ void fixup_codon(const uint8_t *__restrict__ cons, in
     // the rows that equalled the second or third reference of the span this codon starts in: one decode each, weighted
     const int64_t sp = min(q0, q2) >> 4;
     for (int r = 0; r < 2; r++) {
-        const uint32_t *ap = alt + sp * kAltWords + r * kAltSecond;
-        const uint32_t n_alt = ap[kAltCount];
+        const uint32_t n_alt = (r ? refs.cnt_b : refs.cnt_a)[sp];
         if (n_alt) {
-            const uint8_t *ab = reinterpret_cast<const uint8_t *>(ap) - sp * 16;   // 20 pattern bytes from column sp * 16
-            const uint8_t a0 = ab[q0], a1 = ab[q1], a2 = ab[q2];
+            const uint8_t a0 = ref_byte(refs, r, sp, q0), a1 = ref_byte(refs, r, sp, q1), a2 = ref_byte(refs, r, sp, q2);
             if ((a0 != c0 || a1 != c1 || a2 != c2) && lane == 0) credit(a0, a1, a2, n_alt);
             __syncwarp();
         }
@@ -547,7 +556,7 @@ __device__ __forceinline__ void fixup_codon(const uint8_t *__restrict__ cons, in
 // The same fix-up with every load issued up front and the credits applied to the warp's register copy of the bins
 // (lane l holds bins l and l + 32, lanes 0 and 1 also bins 64 and 65): one chain of dependent loads instead of four.
 // bins[0..2] on return: this lane's bins l, l + 32 and the 'other' bin, as k_stats wants them.
-__device__ __forceinline__ void fixup_codon_regs(const uint8_t *__restrict__ cons, int64_t cons_shift, const uint32_t *__restrict__ alt,
+__device__ __forceinline__ void fixup_codon_regs(const uint8_t *__restrict__ cons, int64_t cons_shift, const RefPlanes &refs,
                                                  const CodonMap *__restrict__ map, int64_t c, uint32_t n_rows,
                                                  uint32_t *__restrict__ hist, uint32_t *__restrict__ other_min,
                                                  uint32_t *__restrict__ other_max, int lane, uint32_t *bins)
@@ -556,12 +565,11 @@ __device__ __forceinline__ void fixup_codon_regs(const uint8_t *__restrict__ con
     const CodonMap m = map[c];
     const int64_t q0 = m.p0 + cons_shift, q1 = m.p1 + cons_shift, q2 = m.p2 + cons_shift;     // columns relative to the first span
     const int64_t sp = min(q0, q2) >> 4;
-    const uint32_t *ap = alt + sp * kAltWords;
-    const uint8_t *ab1 = reinterpret_cast<const uint8_t *>(ap) - sp * 16, *ab2 = reinterpret_cast<const uint8_t *>(ap + kAltSecond) - sp * 16;
     uint32_t h0 = h[lane], h1 = h[lane + 32], h2 = lane < kHistBins - 64 ? h[lane + 64] : 0u;
     const uint8_t c0 = cons[q0], c1 = cons[q1], c2 = cons[q2];
-    const uint32_t n1 = ap[kAltCount], n2 = ap[kAltSecond + kAltCount];
-    const uint8_t x0 = ab1[q0], x1 = ab1[q1], x2 = ab1[q2], y0 = ab2[q0], y1 = ab2[q1], y2 = ab2[q2];
+    const uint32_t n1 = refs.cnt_a[sp], n2 = refs.cnt_b[sp];
+    const uint8_t x0 = ref_byte(refs, 0, sp, q0), x1 = ref_byte(refs, 0, sp, q1), x2 = ref_byte(refs, 0, sp, q2);
+    const uint8_t y0 = ref_byte(refs, 1, sp, q0), y1 = ref_byte(refs, 1, sp, q1), y2 = ref_byte(refs, 1, sp, q2);
     uint32_t omin = 0xFFFFFFFFu, omax = 0;         // keys of 'other' codons credited here
     bool any_other = false;
     auto credit = [&](uint8_t r0, uint8_t r1, uint8_t r2, uint32_t rows) {     // every lane: rows copies of the codon r0 r1 r2
@@ -596,14 +604,14 @@ __device__ __forceinline__ void fixup_codon_regs(const uint8_t *__restrict__ con
 }
 
 __global__ void __launch_bounds__(256)
-k_fused_fixup(const uint8_t *__restrict__ cons, int64_t cons_shift, const uint32_t *__restrict__ alt, const CodonMap *__restrict__ map,
+k_fused_fixup(const uint8_t *__restrict__ cons, int64_t cons_shift, const RefPlanes refs, const CodonMap *__restrict__ map,
               const uint8_t *__restrict__ regular, int64_t n_codons, uint32_t n_rows,
               uint32_t *__restrict__ hist, uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max)
 {
     const int lane = threadIdx.x & 31;
     const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (c >= n_codons || !regular[c]) return;
-    fixup_codon(cons, cons_shift, alt, map, c, n_rows, hist, other_min, other_max, lane);
+    fixup_codon(cons, cons_shift, refs, map, c, n_rows, hist, other_min, other_max, lane);
 }
 
 // irregular codons (split across CDS segments, or beyond the run capacity of a span) go
@@ -875,13 +883,13 @@ k_stats(GroupView A, GroupView B, int64_t n_codons, const double *__restrict__ t
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t c = (int64_t)blockIdx.x * kStatsWarps + warp;
     if (c < n_codons) stats_codon<BETWEEN>(A, B, c, tables, out, po, lane, warp, s_bin, s_ca, s_cb);
-    peer_signal(ps, kStageStats);
+    peer_signal(ps, kStageStats, c < n_codons && lane < po.world);
 }
 
 // k_fused_fixup followed, codon by codon, by the within-group statistics (K3): one launch less for a whole job
 // (snpg_within_job), the same arithmetic as the two kernels.  Only when every codon is regular.
 __global__ void __launch_bounds__(kStatsWarps * 32)
-k_fused_fixup_stats(const uint8_t *__restrict__ cons, int64_t cons_shift, const uint32_t *__restrict__ alt, const CodonMap *__restrict__ map,
+k_fused_fixup_stats(const uint8_t *__restrict__ cons, int64_t cons_shift, const RefPlanes refs, const CodonMap *__restrict__ map,
                     int64_t n_codons, uint32_t n_rows, uint32_t *__restrict__ hist, uint32_t *__restrict__ other_min,
                     uint32_t *__restrict__ other_max, GroupView A, const double *__restrict__ tables, StatsOut out,
                     const __grid_constant__ PeerOut po, const __grid_constant__ PeerSync ps)
@@ -894,11 +902,11 @@ k_fused_fixup_stats(const uint8_t *__restrict__ cons, int64_t cons_shift, const 
     const int64_t c = (int64_t)blockIdx.x * kStatsWarps + warp;
     if (c < n_codons) {
         uint32_t bins[3];
-        fixup_codon_regs(cons, cons_shift, alt, map, c, n_rows, hist, other_min, other_max, lane, bins);
+        fixup_codon_regs(cons, cons_shift, refs, map, c, n_rows, hist, other_min, other_max, lane, bins);
         __syncwarp();                              // lane 0's 'other' keys are visible to the warp
         stats_codon<false>(A, A, c, tables, out, po, lane, warp, s_bin, s_ca, s_cb, bins);
     }
-    peer_signal(ps, kStageStats);
+    peer_signal(ps, kStageStats, c < n_codons && lane < po.world);
 }
 
 __global__ void k_peer_signal(const __grid_constant__ PeerSync ps, int stage) { peer_signal(ps, stage); }
@@ -1123,7 +1131,8 @@ k_bootstrap(const __grid_constant__ BootArgs a)
     constexpr int kReps = kBootWarps * kBootRepsPerWarp;
     const int i = threadIdx.x, r = i % kReps, which = i / kReps;
     const int64_t bl = (int64_t)blockIdx.x * kReps + r;
-    if (which < 6 && bl < a.b_count) {
+    const bool mine = which < 6 && bl < a.b_count;
+    if (mine) {
         const double2 x = s_sums[r][0], y = s_sums[r][1];
         if (a.rep && which == 0) {
             double2 *o = reinterpret_cast<double2 *>(a.rep + 4 * ((size_t)p * a.b_count + bl));
@@ -1132,7 +1141,7 @@ k_bootstrap(const __grid_constant__ BootArgs a)
         }
         if (a.vals || a.pv.world > 1) put_val(a, which, p, bl, rep_value(x.x, x.y, y.x, y.y, which));
     }
-    peer_signal(a.ps, kStageVals);
+    peer_signal(a.ps, kStageVals, mine);
 }
 
 // K4, weight-matrix form (the default when a warp's counts fit in shared memory): the contraction
@@ -1162,9 +1171,13 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+template <uint32_t split>
 __global__ void __launch_bounds__(kMmaWarps * 32, 5)
-k_bootstrap_mma(const __grid_constant__ BootArgs a, uint32_t row_words)
+k_bootstrap_mma(const __grid_constant__ BootArgs a, uint32_t row_words, uint32_t nb)
 {
+    // nb (1 or 2): replicates a warp takes one after the other when it takes one at a time; split (0 or 1): log2 of the
+    // warps that share one replicate of a long item.  Both only shape the blocks -- few replicates per GPU (a rank of
+    // eight) want many short blocks -- and never what a replicate draws.
     extern __shared__ uint32_t s_cnt[];            // [kMmaWarps][row_words]: 1-byte counters, four to a word
     const uint32_t call = a.call + (a.salt ? *a.salt : 0u);      // a replayed CUDA graph gets its per-call number from memory
     __shared__ double2 s_sums[kMmaWarps * kBootMaxRows][2];         // a batch's replicate sums, for the dense epilogue
@@ -1185,21 +1198,30 @@ k_bootstrap_mma(const __grid_constant__ BootArgs a, uint32_t row_words)
     const uint32_t m = 1u << lm;
     constexpr uint32_t kLogWarps = kMmaWarps == 16 ? 4 : kMmaWarps == 8 ? 3 : 5;
     static_assert((1u << kLogWarps) == kMmaWarps, "kMmaWarps must be 8, 16 or 32");
-    const uint32_t lrows = kLogWarps + lm;         // log2 of the replicates per batch
+    const uint32_t ls = lm == 0 ? split : 0u;      // 1 << ls warps draw one replicate together (its row takes their REDs)
+    const uint32_t lrows = kLogWarps + lm - ls;    // log2 of the replicates per batch
     const uint32_t rows = 1u << lrows;             // replicates per batch
-    const uint32_t n_batch = m >= kBootRepsPerWarp ? 1 : kBootRepsPerWarp >> lm;
+    const uint32_t n_batch = m >= nb ? 1 : nb >> lm;
     const int64_t block_first = (int64_t)blockIdx.x * rows * n_batch;
     const bool active = block_first < a.b_count;   // the grid is sized for m = 1
-    const uint32_t lanes_per = 32u >> lm, sub = lane >> (5 - lm), sl = lane & (lanes_per - 1);
+    const uint32_t lanes_per = (32u >> lm) << ls, sub = lm ? lane >> (5 - lm) : 0u;
+    const uint32_t sl = (lane & ((32u >> lm) - 1)) + ((warp & ((1u << ls) - 1)) << 5);
+    const uint32_t my_row = ls ? warp >> ls : warp * m + sub;        // the replicate of the batch this lane draws for
     uint32_t *warp_rows = s_cnt + (size_t)warp * m * rw;
-    const uint32_t mine_s = (uint32_t)__cvta_generic_to_shared(warp_rows + (size_t)sub * rw);
-    double *part = &s_part[0][0][0];               // [ksplit][rows][4], ksplit * rows = 8 * kMmaWarps
+    const uint32_t mine_s = (uint32_t)__cvta_generic_to_shared(s_cnt + (size_t)my_row * rw);
+    double *part = &s_part[0][0][0];               // [ksplit][rows][4], ksplit * rows <= 8 * kMmaWarps
+    bool wrote = false;
     for (uint32_t k = 0; active && k < n_batch; k++) {
         const int64_t batch_first = block_first + (int64_t)k * rows;
-        // --- sampling: one replicate per group of 32 / m lanes -> its row of counts
-        for (uint32_t i = lane; i < m * rw; i += 32) warp_rows[i] = 0;
-        __syncwarp();
-        const int64_t bl = batch_first + warp * m + sub;
+        // --- sampling: one replicate per group of 32 / m lanes (or per 1 << ls warps) -> its row of counts
+        if (ls) {
+            for (uint32_t i = threadIdx.x; i < rows * rw; i += blockDim.x) s_cnt[i] = 0;
+            __syncthreads();                       // a row is bumped by several warps
+        } else {
+            for (uint32_t i = lane; i < m * rw; i += 32) warp_rows[i] = 0;
+            __syncwarp();
+        }
+        const int64_t bl = batch_first + my_row;
         if (bl < a.b_count) {
             const uint64_t b = (uint64_t)(a.b_first + bl);
             auto bump = [&](uint32_t u) {          // one draw: slot = floor(u * n_slots / 2^32); its byte of the row goes up by one
@@ -1229,7 +1251,8 @@ k_bootstrap_mma(const __grid_constant__ BootArgs a, uint32_t row_words)
             const uint32_t per = (nslot4 + ksplit - 1) >> lks;
             const uint32_t t0 = min(nslot4, ks * per), t1 = min(nslot4, t0 + per);
             const uint32_t row = gq * 8 + (lane >> 2);
-            const uint32_t *cnt_row = s_cnt + (size_t)row * rw;      // A: row = replicate lane/4
+            // A: row = replicate lane/4 (fewer than 8 replicates in the batch: the tile's other rows repeat them and are dropped)
+            const uint32_t *cnt_row = s_cnt + (size_t)(row & (rows - 1)) * rw;
             const uint32_t col = lane & 3;                           //    column = slot 4t + lane%4
             const uint32_t stat = lane >> 2;                         // B: column lane/4 = statistic (columns 4-7: padding)
             const uint32_t sel = 0x4440u + col;                      // byte col of a word, zero-extended
@@ -1250,7 +1273,7 @@ k_bootstrap_mma(const __grid_constant__ BootArgs a, uint32_t row_words)
             for (; t < t_inner; t++) tile(t, false);
             for (; t < t1; t++) tile(t, true);                      // may reach past the last slot
             // D: lane holds row lane/4, columns 2*(lane%4), +1; statistics are columns 0..3
-            if (col < 2) {
+            if (col < 2 && row < rows) {
                 double *o = part + (((ks << lrows) + row) << 2) + 2 * col;
                 o[0] = acc0;
                 o[1] = acc1;
@@ -1276,6 +1299,7 @@ k_bootstrap_mma(const __grid_constant__ BootArgs a, uint32_t row_words)
                     o[1] = y;
                 }
                 if (a.vals || a.pv.world > 1) put_val(a, (int)which, p, bl2, rep_value(x.x, x.y, y.x, y.y, (int)which));
+                wrote = true;
             }
         }
         // (the next batch's first barrier comes after its sampling: s_sums and part are not written before it)
@@ -1310,7 +1334,7 @@ k_bootstrap_mma(const __grid_constant__ BootArgs a, uint32_t row_words)
             __syncthreads();
         }
     }
-    peer_signal(a.ps, kStageVals);
+    peer_signal(a.ps, kStageVals, wrote);
 }
 
 // ---------------------------------------------------------------------------
@@ -1319,17 +1343,15 @@ k_bootstrap_mma(const __grid_constant__ BootArgs a, uint32_t row_words)
 // statistic of a replicate is derived on the fly (rep_value); se[item][6].
 // ---------------------------------------------------------------------------
 constexpr int kMomentThreads = 1024;
-__device__ __forceinline__ double block_sum(double v, double *red) {     // fixed-shape tree: deterministic
+__device__ __forceinline__ double block_sum(double v, double *red) {     // fixed shape (butterflies): deterministic
     const int t = threadIdx.x;
+    v = warp_sum(v);
     __syncthreads();
-    red[t] = v;
+    if ((t & 31) == 0) red[t >> 5] = v;
     __syncthreads();
-    for (int h = kMomentThreads / 2; h > 0; h >>= 1) {
-        if (t < h) red[t] += red[t + h];
-        __syncthreads();
-    }
-    return red[0];
+    return warp_sum(red[t & 31]);          // kMomentThreads / 32 == 32 partial sums, every warp adds them the same way
 }
+static_assert(kMomentThreads == 1024, "block_sum adds exactly 32 warp sums");
 
 template <bool FROM_REP>
 __global__ void __launch_bounds__(kMomentThreads)
@@ -1430,9 +1452,11 @@ void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, cons
     if (n_spans <= 0 || n_rows <= 0) return;
     using Kernel = void (*)(const uint8_t *, int64_t, uint32_t, const uint8_t *, uint32_t *, uint32_t, const SpanRun *, uint32_t *, uint32_t *,
                             uint32_t *, uint32_t *, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t);
-    // variant (experiments): 0 = 4 blocks/SM at <= 64 registers; 1 = 3 blocks/SM, no register cap
-    static const int variant = [] { const char *v = getenv("SNPG_SPAN_VARIANT"); return v ? max(0, min(1, atoi(v))) : 0; }();
-    static const Kernel kernel = variant == 1 ? (Kernel)k_fused_hist<4, 2, 128, 3> : (Kernel)k_fused_hist<4, 2, 128, 4>;
+    // variant (SNPG_SPAN_VARIANT): 0 (default) = 4 blocks/SM at <= 64 registers; 1 = 3 blocks/SM, no register cap
+    // 2 / 3 = variant 0 with the next four rows prefetched into L1 by every lane / by one lane per 128-byte line
+    static const int variant = [] { const char *v = getenv("SNPG_SPAN_VARIANT"); return v ? max(0, min(3, atoi(v))) : 0; }();
+    static const Kernel kernel = variant == 1 ? (Kernel)k_fused_hist<4, 2, 128, 3> : variant == 2 ? (Kernel)k_fused_hist<4, 2, 128, 4, 1>
+                                 : variant == 3 ? (Kernel)k_fused_hist<4, 2, 128, 4, 2> : (Kernel)k_fused_hist<4, 2, 128, 4>;
     static const size_t smem = (size_t)(kFusedWarps + 1) * 128 * kFusedEntryBytes;
     static const int blocks_per_sm = [] {
         int nb = 0;
@@ -1466,13 +1490,13 @@ void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, cons
     }
 }
 
-void launch_fused_fixup_stats(const uint8_t *d_cons, int64_t cons_shift, const uint32_t *d_alt, const CodonMap *d_map, int64_t n_codons,
+void launch_fused_fixup_stats(const uint8_t *d_cons, int64_t cons_shift, uint32_t *d_alt, int64_t n_spans, const CodonMap *d_map, int64_t n_codons,
                               uint32_t n_rows, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max, GroupView A,
                               const double *d_tables, StatsOut out, const PeerOut *po, const PeerSync *ps, cudaStream_t stream)
 {
     if (n_codons <= 0) { if (ps) launch_peer_signal(*ps, kStageStats, stream); return; }
     k_fused_fixup_stats<<<(unsigned)((n_codons + kStatsWarps - 1) / kStatsWarps), kStatsWarps * 32, 0, stream>>>(
-        d_cons, cons_shift, d_alt, d_map, n_codons, n_rows, d_hist, d_other_min, d_other_max, A, d_tables, out, po ? *po : PeerOut(),
+        d_cons, cons_shift, ref_planes(d_alt, n_spans), d_map, n_codons, n_rows, d_hist, d_other_min, d_other_max, A, d_tables, out, po ? *po : PeerOut(),
         ps ? *ps : PeerSync());
 }
 
@@ -1486,12 +1510,12 @@ void launch_peer_wait(const PeerSync &ps, int stage, cudaStream_t stream)
     if (ps.world > 1) k_peer_wait<<<1, 32, 0, stream>>>(ps, stage);
 }
 
-void launch_fused_fixup(const uint8_t *d_cons, int64_t cons_shift, const uint32_t *d_alt, const CodonMap *d_map, const uint8_t *d_regular,
+void launch_fused_fixup(const uint8_t *d_cons, int64_t cons_shift, uint32_t *d_alt, int64_t n_spans, const CodonMap *d_map, const uint8_t *d_regular,
                         int64_t n_codons, uint32_t n_rows, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max,
                         cudaStream_t stream)
 {
     if (n_codons <= 0) return;
-    k_fused_fixup<<<(unsigned)((n_codons + 7) / 8), 256, 0, stream>>>(d_cons, cons_shift, d_alt, d_map, d_regular, n_codons, n_rows,
+    k_fused_fixup<<<(unsigned)((n_codons + 7) / 8), 256, 0, stream>>>(d_cons, cons_shift, ref_planes(d_alt, n_spans), d_map, d_regular, n_codons, n_rows,
                                                                        d_hist, d_other_min, d_other_max);
 }
 
@@ -1570,11 +1594,23 @@ void launch_bootstrap(int form, BootArgs a, int64_t max_codons, cudaStream_t str
     // (at least 16 KB a block even for a short table, so that short products can take several replicates per warp)
     const size_t row_words = std::max<size_t>((((size_t)max_codons + 1 + 3) / 4) | 1, 127);
     if (form == SNPG_BOOT_WEIGHTS && row_words * 4 * 32 <= (size_t)kBootSmemLimit) {
-        // five blocks of kMmaWarps warps per SM; the grid is sized for one replicate per warp and two batches a block
-        const int64_t per_mma = (int64_t)kMmaWarps * kBootRepsPerWarp;
+        // five blocks of kMmaWarps warps per SM; the grid is sized for one replicate per warp.  A block takes two batches
+        // of replicates when that still leaves every SM a few blocks per slot (measured on config 2: one batch 157 us, two
+        // 147, four 168); with few replicates (a rank of several GPUs) one batch, then two warps per replicate.
+        static const int n_sms = [] { int d = 0, n = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n > 0 ? n : 148; }();
+        static const int env_nb = [] { const char *v = getenv("SNPG_BOOT_NB"); return v ? atoi(v) : 0; }();
+        static const int env_split = [] { const char *v = getenv("SNPG_BOOT_SPLIT"); return v ? atoi(v) : -1; }();
+        const int64_t target = 3ll * n_sms * 5;
+        auto blocks = [&](int nb, int split) { const int64_t per = (int64_t)(kMmaWarps >> split) * nb; return (a.b_count + per - 1) / per * a.n_items; };
+        int nb = 2, split = 0;
+        if (blocks(2, 0) < target) { nb = 1; if (blocks(1, 0) < target) split = 1; }
+        if (env_nb == 1 || env_nb == 2) nb = env_nb;
+        if (env_split == 0 || env_split == 1) split = env_split;
+        const int64_t per_mma = (int64_t)(kMmaWarps >> split) * nb;
         dim3 grid_mma((unsigned)((a.b_count + per_mma - 1) / per_mma), (unsigned)a.n_items);
-        cudaFuncSetAttribute(k_bootstrap_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, kBootSmemLimit * kMmaWarps / 32);  // per device
-        k_bootstrap_mma<<<grid_mma, kMmaWarps * 32, row_words * 4 * kMmaWarps, stream>>>(a, (uint32_t)row_words);
+        auto kernel = split ? k_bootstrap_mma<1> : k_bootstrap_mma<0>;
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBootSmemLimit * kMmaWarps / 32);  // per device
+        kernel<<<grid_mma, kMmaWarps * 32, row_words * 4 * kMmaWarps, stream>>>(a, (uint32_t)row_words, (uint32_t)nb);
     } else if (smem <= (size_t)kBootSmemLimit) {
         cudaFuncSetAttribute(k_bootstrap<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBootSmemLimit);  // per device
         k_bootstrap<true><<<grid, kBootWarps * 32, smem, stream>>>(a);

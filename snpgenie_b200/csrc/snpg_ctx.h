@@ -55,6 +55,7 @@ struct Exchange {
     size_t bytes = 0, half = 0, off_stats = 0, off_cmp = 0, off_ndef = 0, off_poly = 0, off_cons = 0, off_vals = 0;
     uint8_t *base[kMaxPeers] = {};
     bool ipc_opened[kMaxPeers] = {};
+    bool peer_on_my_gpu = false;         // some peer runs on this rank's GPU: waits go into one-block kernels (exchange.cu)
     uint32_t epoch = 0;                  // jobs run so far (all ranks run the same sequence of jobs)
     template <class T> T *at(int r, int parity, size_t off) const { return reinterpret_cast<T *>(base[r] + sizeof(XHeader) + (size_t)parity * half + off); }
 };
@@ -113,7 +114,7 @@ struct snpg_ctx {
     snpg::PeerSync job_peer_sync;
     // a whole job on a device-resident alignment, replayed as a CUDA graph from the third identical call on
     struct TimedSpan { cudaEvent_t e0, e1; int kind; };
-    struct PendingCopy { void *dst; const void *src; size_t bytes; };
+    struct PendingCopy { int field; const void *src; size_t bytes; };   // field: which output of the snpg_job (job.cu)
     bool capturing = false;
     struct JobKey {
         uint32_t profile_mask = 0;
@@ -130,7 +131,7 @@ struct snpg_ctx {
         cudaGraphExec_t exec = nullptr;
         JobKey key;
         uint64_t epoch = 0;
-        int64_t n_launches = 0, n_tile_launches = 0;
+        int64_t n_launches = 0, n_tile_launches = 0, n_span_tma_launches = 0;
         std::vector<TimedSpan> spans;   // event pairs recorded inside the graph (profiling on)
         std::vector<PendingCopy> pending;   // host copies that follow every replay
     } job_graph[2];                     // one per exchange parity (a single GPU only uses [0])
@@ -142,7 +143,8 @@ struct snpg_ctx {
     std::vector<PendingCopy> pending;   // staging -> caller's (pageable) arrays, after the job's synchronisation
     snpg::DevBuf d_salt;
     int64_t launches = 0;
-    int64_t tile_launches = 0;      // launches of k_tile_hist (the rest of SNPG_K_FUSED went to k_fused_hist)
+    int64_t tile_launches = 0;      // launches of k_tile_hist
+    int64_t span_tma_launches = 0;  // launches of k_span_hist (the rest of SNPG_K_FUSED went to k_fused_hist)
     uint32_t call_id = 0;
     // optional per-kernel timing (CUDA events on the launch stream)
     uint32_t profile_mask = 0;      // bit k set: bracket launches of kernel kind k with timing events

@@ -75,21 +75,20 @@ void launch_pack(const uint8_t *d_aln, int64_t row_stride, int64_t n_rows, int64
 void launch_hist(const uint8_t *d_codes, int64_t n_pad, int64_t n_codons, uint32_t *d_hist, cudaStream_t stream);
 
 // Reference rows of the compare-with-reference kernels from the group's first n_sample (<= 32) rows:
-// d_cons[column] (n_spans*16 + 4 bytes written) and d_alt[span][kAltWords].  Every row needs
+// d_cons[column] (n_spans*16 + 4 bytes written) and d_alt (see below).  Every row needs
 // n_spans*16 + 4 readable bytes.
 void launch_vote_refs(const uint8_t *d_aln, int64_t pitch, int n_sample, int64_t n_spans, uint8_t *d_cons, uint32_t *d_alt,
                       uint32_t *d_zero_hist, uint32_t *d_other_min, uint32_t *d_other_max, int64_t n_codons, cudaStream_t stream);
-// d_alt[span][kAltWords]: words 0-4 the span's second reference pattern, words kAltSecond.. the third
-// (launch_vote_refs); word kAltCount of each the number of rows that equalled it (zeroed by launch_vote_refs,
-// raised by launch_fused_hist, spent by launch_fused_fixup).  d_sched: two zeroed u32 (chunk counter, finished
-// blocks); the kernel leaves them zeroed.  Every row needs n_spans*16 + 16 readable bytes.
-constexpr int kAltWords = 16;
-constexpr int kAltSecond = 8;
-constexpr int kAltCount = 5;
+// d_alt: the spans' second and third reference patterns and the counts of the rows that equalled them, as planes over
+// the span axis (RefPlanes, snpg_span.cuh): alt_words(n_spans) u32, written by launch_vote_refs, counts raised by the
+// histogram kernels, spent by the fix-up.  d_sched: two zeroed u32 (chunk counter, finished blocks); the kernel leaves
+// them zeroed.  Every row needs n_spans*16 + 16 readable bytes.
+__host__ __device__ constexpr int64_t alt_stride(int64_t n_spans) { return (n_spans + 1 + 3) & ~(int64_t)3; }
+constexpr int64_t alt_words(int64_t n_spans) { return 11 * alt_stride(n_spans); }
 void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, const uint8_t *d_cons, uint32_t *d_alt, int64_t n_spans,
                        const SpanRun *d_runs, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max, uint32_t *d_sched,
                        int n_sms, cudaStream_t stream);
-void launch_fused_fixup(const uint8_t *d_cons, int64_t cons_shift, const uint32_t *d_alt, const CodonMap *d_map, const uint8_t *d_regular,
+void launch_fused_fixup(const uint8_t *d_cons, int64_t cons_shift, uint32_t *d_alt, int64_t n_spans, const CodonMap *d_map, const uint8_t *d_regular,
                         int64_t n_codons, uint32_t n_rows, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max,
                         cudaStream_t stream);
 // TMA-tiled variant of launch_fused_hist (same contract: counts of the non-consensus codons of the regular
@@ -101,6 +100,15 @@ bool make_tile_tensor_map(void *out_map, const uint8_t *d_aln, int64_t pitch, in
 cudaError_t launch_tile_hist(const void *tensor_map, int64_t n_rows, const uint8_t *d_cons, const CodonTile *d_tiles, int64_t n_tiles,
                              int n_sms, uint32_t *d_sched, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max,
                              cudaStream_t stream);
+// TMA-fed span kernel (span_tma.cu; an option, measured slower than k_fused_hist: see profiles/): k_fused_hist's arithmetic with the rows staged in shared memory by
+// cp.async.bulk.tensor loads.  Same contract as launch_fused_hist.  make_span_tensor_map as make_tile_tensor_map (words of
+// 4 bytes, boxes of 512 bytes x span_stage_rows() rows, zero fill outside).  launch_span_hist returns
+// cudaErrorInvalidValue when the chunk index would not fit 32 bits (the caller then takes launch_fused_hist).
+int span_stage_rows();
+bool make_span_tensor_map(void *out_map, const uint8_t *d_aln, int64_t pitch, int64_t rows, int64_t row_bytes, int l2_promotion);
+cudaError_t launch_span_hist(const void *tensor_map, int64_t n_rows, const uint8_t *d_cons, uint32_t *d_alt, int64_t n_spans,
+                             const SpanRun *d_runs, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max, uint32_t *d_sched,
+                             int n_sms, cudaStream_t stream);
 void launch_scatter_irregular(const uint32_t *d_tmp_hist, const uint32_t *d_tmp_min, const uint32_t *d_tmp_max,
                               const int32_t *d_idx, int64_t n_irr, uint32_t *d_hist, uint32_t *d_other_min,
                               uint32_t *d_other_max, cudaStream_t stream);
@@ -126,7 +134,7 @@ struct StatsOut {
 void launch_within_stats(GroupView A, int64_t n_codons, const double *d_tables, StatsOut out, const PeerOut *po, const PeerSync *ps,
                          cudaStream_t stream);
 // launch_fused_fixup (every codon regular) and launch_within_stats in one kernel, codon by codon: same arithmetic.
-void launch_fused_fixup_stats(const uint8_t *d_cons, int64_t cons_shift, const uint32_t *d_alt, const CodonMap *d_map, int64_t n_codons,
+void launch_fused_fixup_stats(const uint8_t *d_cons, int64_t cons_shift, uint32_t *d_alt, int64_t n_spans, const CodonMap *d_map, int64_t n_codons,
                               uint32_t n_rows, uint32_t *d_hist, uint32_t *d_other_min, uint32_t *d_other_max, GroupView A,
                               const double *d_tables, StatsOut out, const PeerOut *po, const PeerSync *ps, cudaStream_t stream);
 // a rank whose codon range is empty still has to signal its stage

@@ -32,10 +32,11 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
     return t;
 }
 
-// End of a producer kernel; EVERY thread of EVERY block calls it once, after its last store into peer memory.
-__device__ __forceinline__ void peer_signal(const PeerSync &ps, int stage) {
+// End of a producer kernel; EVERY thread of EVERY block calls it once, after its last store into peer memory
+// (wrote = this thread stored something there: only those threads pay for the system-wide fence).
+__device__ __forceinline__ void peer_signal(const PeerSync &ps, int stage, bool wrote = true) {
     if (ps.world <= 1) return;
-    __threadfence_system();                      // this thread's peer stores are visible system-wide before the flag can be
+    if (wrote) __threadfence_system();           // this thread's peer stores are visible system-wide before the flag can be
     __syncthreads();
     if (threadIdx.x == 0 && threadIdx.y == 0) {
         XHeader *me = ps.hdr[ps.rank];

@@ -41,6 +41,7 @@
 
 #include "snpg_device.cuh"
 #include "snpg_internal.h"
+#include "snpg_tma.cuh"
 
 namespace snpg {
 
@@ -75,39 +76,6 @@ struct TileSmem {
     uint64_t full[kTileStages];
     uint64_t empty[kTileStages];
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
-        "@P1 bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// 1-D bulk copy global -> shared (16-byte aligned, size multiple of 16), completing on the same kind of barrier
-__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int32_t x, int32_t y) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
-                 : "memory");
-}
 
 // One parked group: d0..d2 = (row ^ consensus) of the group's 12 bytes (masked to its codons),
 // g = the group's index inside the tile.  Codon k of the group sits in bytes 3k..3k+2.
@@ -303,27 +271,14 @@ size_t tile_hist_smem_bytes() { return sizeof(TileSmem) + 1024; }
 // entry point is missing or rejects the geometry (the caller then uses k_fused_hist).
 bool make_tile_tensor_map(void *out_map, const uint8_t *d_aln, int64_t pitch, int64_t rows, int64_t row_bytes, int l2_promotion)
 {
-    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn encode = [] {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess)
-            p = nullptr;
-        return reinterpret_cast<EncodeFn>(p);
-    }();
+    const TensorMapEncodeFn encode = tensor_map_encoder();
     if (!encode) return false;
     if (((uintptr_t)d_aln & 15) || (pitch & 15) || pitch <= 0 || rows <= 0 || row_bytes <= 0 || pitch >= ((int64_t)1 << 40)) return false;
     const cuuint64_t gdim[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
     const cuuint64_t gstride[1] = {(cuuint64_t)pitch};
     const cuuint32_t box[2] = {(cuuint32_t)kTileBytes, (cuuint32_t)kTileRows};
     const cuuint32_t estride[2] = {1, 1};
-    const CUtensorMapL2promotion promo = l2_promotion == 0   ? CU_TENSOR_MAP_L2_PROMOTION_NONE
-                                         : l2_promotion == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-                                         : l2_promotion == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
-                                                             : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    const CUtensorMapL2promotion promo = tensor_map_promotion(l2_promotion);
     const CUresult r = encode(static_cast<CUtensorMap *>(out_map), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(d_aln), gdim,
                               gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promo,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

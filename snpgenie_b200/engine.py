@@ -84,8 +84,13 @@ class Engine:
 
     @property
     def tile_launches(self) -> int:
-        """Launches of the TMA-tiled histogram kernel (the default fused route)."""
+        """Launches of the TMA-tiled histogram kernel (SNPG_FUSED_TMA_TILES)."""
         return int(_abi.lib.snpg_tile_launch_count(self._ctx))
+
+    @property
+    def span_tma_launches(self) -> int:
+        """Launches of the TMA-fed span histogram kernel (SNPG_FUSED_TMA_SPANS)."""
+        return int(_abi.lib.snpg_span_tma_launch_count(self._ctx))
 
     @property
     def graph_replays(self) -> int:

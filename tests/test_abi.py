@@ -35,6 +35,7 @@ def test_python_constants_follow_the_header():
     pairs = {"SNPG_OPT_KEEP_CODES": _abi.OPT_KEEP_CODES, "SNPG_OPT_PROFILE": _abi.OPT_PROFILE, "SNPG_OPT_SITE_COUNTS": _abi.OPT_SITE_COUNTS,
              "SNPG_OPT_FUSED_KERNEL": _abi.OPT_FUSED_KERNEL, "SNPG_OPT_BOOTSTRAP_KERNEL": _abi.OPT_BOOTSTRAP_KERNEL,
              "SNPG_FUSED_TMA_TILES": _abi.FUSED_TMA_TILES, "SNPG_FUSED_LDG_SPANS": _abi.FUSED_LDG_SPANS,
+             "SNPG_FUSED_TMA_SPANS": _abi.FUSED_TMA_SPANS,
              "SNPG_BOOT_GATHER": _abi.BOOT_GATHER, "SNPG_BOOT_WEIGHTS": _abi.BOOT_WEIGHTS}
     for name, value in pairs.items():
         assert defs[name] == value, name

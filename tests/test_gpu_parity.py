@@ -31,18 +31,17 @@ def eng():
     e.close()
 
 
-@pytest.fixture(scope="module", params=["codes", "fused", "tiles"])
+@pytest.fixture(scope="module", params=["codes", "fused", "tiles", "spans"])
 def eng2(request):
-    """All histogram routes: K1 pack + K2 hist over the kept code matrix, the fused vector-load kernel
-    (the default) and the fused TMA-tiled kernel."""
+    """All histogram routes: K1 pack + K2 hist over the kept code matrix, the fused vector-load span kernel (the default),
+    the fused TMA-tiled kernel and the TMA-fed span kernel."""
     from snpgenie_b200 import _abi
     from snpgenie_b200.engine import Engine
     e = Engine(device=0, seed=1234)
     e.has_codes = request.param == "codes"
     e.route = request.param
     e.set_option(_abi.OPT_KEEP_CODES, 1 if e.has_codes else 0)
-    if request.param == "tiles":
-        e.set_option(_abi.OPT_FUSED_KERNEL, _abi.FUSED_TMA_TILES)
+    e.set_option(_abi.OPT_FUSED_KERNEL, {"tiles": _abi.FUSED_TMA_TILES, "spans": _abi.FUSED_TMA_SPANS}.get(request.param, _abi.FUSED_LDG_SPANS))
     yield e
     e.close()
 
@@ -61,10 +60,11 @@ def test_codon_indices_and_histograms_bit_exact(eng2, case, minus):
     d, aln, _, _ = refio.within_case(case)
     products = hostio.read_gtf_products(os.path.join(d, "cds.gtf"), include_minus=minus)
     eng.set_products(products, aln.shape[1])
-    before = eng.tile_launches
+    before, before_s = eng.tile_launches, eng.span_tma_launches
     eng.load_group(0, aln)
-    # the "tiles" route must really be the TMA-tiled kernel, the other two must not touch it
+    # the "tiles" and "spans" routes must really be the TMA kernels, the other two must not touch them
     assert (eng.tile_launches > before) == (eng.route == "tiles")
+    assert (eng.span_tma_launches > before_s) == (eng.route == "spans")
     for i, p in enumerate(products):
         raw, codes = _oracle_product(aln, p)
         if eng.has_codes:
@@ -746,7 +746,7 @@ def test_between_all_matches_per_pair_calls(eng):
     assert close(sums2[0], sums0[1], rtol=1e-13)
 
 
-@pytest.mark.parametrize("route", ["fused", "tiles", "codes"])
+@pytest.mark.parametrize("route", ["spans", "fused", "tiles", "codes"])
 def test_more_than_2_20_rows(route):
     """Config-5-sized row counts (> 2^20 sequences) cross the per-launch row limit of the device-resident path
     and the row-block staging of the host path; counts must stay exact."""
@@ -766,8 +766,7 @@ def test_more_than_2_20_rows(route):
         raw, codes = _oracle_product(aln, p)
         want.append(orc.hist(codes))
     with Engine(device=0, keep_codes=(route == "codes")) as e:
-        if route == "tiles":
-            e.set_option(_abi.OPT_FUSED_KERNEL, _abi.FUSED_TMA_TILES)
+        e.set_option(_abi.OPT_FUSED_KERNEL, {"tiles": _abi.FUSED_TMA_TILES, "spans": _abi.FUSED_TMA_SPANS}.get(route, _abi.FUSED_LDG_SPANS))
         e.set_products(products, L)
         e.load_group(0, aln)
         for i in range(len(products)):
@@ -1008,7 +1007,7 @@ def test_random_annotations_both_routes(seed):
     aln[:, keep_cols] = aln[0, keep_cols]
     sorted_prods = [hostio.Product(p.name, p.strand, sorted(p.starts), [e for _, e in sorted(zip(p.starts, p.stops))]) for p in prods]
     from snpgenie_b200 import _abi
-    for keep, fused in ((True, 0), (False, _abi.FUSED_TMA_TILES), (False, _abi.FUSED_LDG_SPANS)):
+    for keep, fused in ((True, 0), (False, _abi.FUSED_TMA_TILES), (False, _abi.FUSED_LDG_SPANS), (False, _abi.FUSED_TMA_SPANS)):
         with Engine(device=0, keep_codes=keep) as e:
             e.set_option(_abi.OPT_FUSED_KERNEL, fused)
             e.set_products(prods, L)

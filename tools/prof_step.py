@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small driver for ncu captures: a few device-resident steps of the config-2 hot path.
 
-    python tools/prof_step.py [--steps 3] [--route fused|tiles|codes] [--p-poly 0.3] [--n 10000]
+    python tools/prof_step.py [--steps 3] [--route spans|fused|tiles|codes] [--p-poly 0.3] [--n 10000]
 """
 import argparse
 import os
@@ -28,8 +28,8 @@ d = torch.zeros((a.n, pitch), dtype=torch.uint8, device="cuda:0")
 d[:, :L] = torch.from_numpy(aln).cuda()
 with Engine(device=0) as eng:
     eng.set_option(_abi.OPT_KEEP_CODES, 1 if a.route == "codes" else 0)
-    eng.set_option(_abi.OPT_FUSED_KERNEL, _abi.FUSED_TMA_TILES if a.route == "tiles" else _abi.FUSED_LDG_SPANS)
+    eng.set_option(_abi.OPT_FUSED_KERNEL, {"tiles": _abi.FUSED_TMA_TILES, "spans": _abi.FUSED_TMA_SPANS}.get(a.route, _abi.FUSED_LDG_SPANS))
     eng.set_products(products, L)
     for _ in range(a.steps):       # the whole-job call bench.py times (run with SNPG_NO_GRAPH=1 for plain launches)
         sums, se = eng.within_job(0, d.data_ptr(), a.n, L, pitch, True, B=a.boot)
-    print("ok", sums[0], se[0][:3], "tile launches", eng.tile_launches)
+    print("ok", sums[0], se[0][:3], "tile launches", eng.tile_launches, "span-tma launches", eng.span_tma_launches)
