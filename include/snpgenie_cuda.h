@@ -105,6 +105,13 @@ int snpg_group_size(const snpg_ctx *ctx, int group, uint64_t *n_seqs);
  * so snpg_load_group() on it streams at full PCIe rate.  No device needed for
  * the parse itself, but a ctx is (it owns the buffer). */
 int snpg_read_fasta(snpg_ctx *ctx, int slot, const char *path, const uint8_t **bases, uint64_t *n_seqs, uint64_t *aln_len);
+/* The reader works with every host thread (SNPG_INGEST_THREADS in the environment caps them): one pass finds the records
+ * in the memory-mapped file while the pinned buffer is allocated, a second copies them into their rows.  With
+ * SNPG_OPT_INGEST_ASYNC = 1 snpg_read_fasta returns while the second pass is still running in the background; library
+ * calls that read the buffer (snpg_load_group, whole jobs, snpg_codon_strings) wait for the rows they need -- the
+ * host-to-device copy of one row block then overlaps the parse of the next -- and snpg_fasta_wait makes the whole buffer
+ * safe to read for the caller itself. */
+int snpg_fasta_wait(snpg_ctx *ctx, int slot);
 /* The three normalised characters of one codon for every sequence of a FASTA slot
  * (out [n_seqs][3]; uc, U->T, complemented on the '-' strand) -- what the host needs to
  * print the strings of 'other' alleles.  Product/codon as in snpg_within. */
@@ -113,8 +120,8 @@ int snpg_codon_strings(snpg_ctx *ctx, int slot, int product, int64_t codon, uint
 /* Options: SNPG_OPT_KEEP_CODES (default 0).  With 0 the histograms are built straight
  * from the alignment bytes by the fused kernel and no code matrix exists.  With 1 the
  * packed codon matrix is materialised on the device (K1 then K2): needed by
- * snpg_get_codon_indices and by the between-group "first defined codon" rule
- * (bg:853-890; without codes that rare case takes the lowest allele code).
+ * snpg_get_codon_indices (a test hook); the between-group "first defined codon" rule
+ * (bg:853-890) is served by SNPG_OPT_FIRST_DEFINED on the fast route.
  * Set before loading a group. */
 #define SNPG_OPT_KEEP_CODES 1
 /* SNPG_OPT_SITE_COUNTS (default 0): while a group is loaded also count A, C, G, T per
@@ -155,6 +162,13 @@ int snpg_codon_strings(snpg_ctx *ctx, int slot, int product, int64_t codon, uint
 #define SNPG_OPT_BOOT_SLOTS 6
 #define SNPG_SLOTS_CORRECTED 0
 #define SNPG_SLOTS_FAITHFUL 1
+/* SNPG_OPT_INGEST_ASYNC (default 0): see snpg_read_fasta. */
+#define SNPG_OPT_INGEST_ASYNC 7
+/* SNPG_OPT_FIRST_DEFINED (default 0): while a group is loaded WITHOUT a code matrix, also note the first defined codon
+ * of every codon column in file order -- what the between-group "first defined codon" rule (bg:853-890) takes when the
+ * other group has no defined codon at a conserved position -- so that between-group analyses keep the fast histogram
+ * route (without it that rare case takes the lowest allele code).  Set before loading a group. */
+#define SNPG_OPT_FIRST_DEFINED 8
 int snpg_set_option(snpg_ctx *ctx, int option, int64_t value);
 
 /* ---- test hooks for the bit-exact checks ---------------------------------
@@ -203,6 +217,42 @@ int snpg_bootstrap_product(snpg_ctx *ctx, const double *stats4, const uint8_t *k
  * (NULL or B < 2: skipped).  *nwin_out receives the number of windows. */
 int snpg_windows(snpg_ctx *ctx, const double *stats4, const uint8_t *keep, int64_t C, int64_t W,
                  int64_t step, int64_t B, double *win_sums, double *win_se, int64_t *nwin_out);
+
+/* ---- SNPGenie_sliding_windows.R ("next" row f2) ------------------------------
+ * The sliding-window statistics of the R script the reference's README recommends over the Perl window processor
+ * (README.md:281), for ONE product's (or one group pair's) per-codon table: SNPGenie_sliding_windows.R:441-548.
+ * stats4 [C][4] = N_sites, S_sites, N_diffs, S_diffs per codon (snpg_within / snpg_between / a codon results file);
+ * n_defined [C] or NULL = num_defined_seqs (between-group: the smaller of the two groups' counts, R :187-190) -- codons
+ * below opt->min_defined are dropped first (R :441); codon_num [C] or NULL (1..C in table order).
+ * Windows: rows i .. i + window - 1 of the kept, codon_num-sorted table for i = min(codon_num), + step, ... (R :444-449:
+ * the script indexes ROWS by codon numbers); they end with the last complete window.  Call with out = NULL for the
+ * number of windows.  out [n_windows][SNPG_RWIN_COLS], in the script's column order (sw_start ... sw_ASL_dNdS_P);
+ * undefined values are NaN / Inf as R computes them (its NA prints as NaN here).  Each of the script's four boot()
+ * calls draws its own resamples; here dN, dS, dN/dS and dN - dS come from one set of replicates per window. */
+typedef struct snpg_rwindows {
+    uint32_t struct_size;         /* sizeof(snpg_rwindows) */
+    int32_t numerator;            /* 0 = N (the script's "N"); 1 = S */
+    int32_t denominator;          /* 1 = S (the script's "S"); 0 = N */
+    int32_t jukes_cantor;         /* CORRECTION = "JC" (R :326-361) */
+    int64_t window, step;         /* WINDOW_SIZE >= 2, STEP_SIZE >= 1 */
+    int64_t n_bootstraps;         /* NBOOTSTRAPS, 2 .. 1,000,000 */
+    int64_t min_defined;          /* MIN_DEFINED_CODONS (ignored when n_defined is NULL) */
+} snpg_rwindows;
+#define SNPG_RWIN_COLS 24
+/* columns: 0 sw_start, 1 sw_center, 2 sw_end, 3 sw_num_replicates, 4 sw_N_diffs, 5 sw_S_diffs, 6 sw_N_sites, 7 sw_S_sites,
+ * 8 sw_dN, 9 sw_dS, 10 sw_dNdS, 11 sw_dN_m_dS, 12 sw_boot_dN_SE, 13 sw_boot_dS_SE, 14 sw_boot_dN_over_dS_SE,
+ * 15 sw_boot_dN_over_dS_P, 16 sw_boot_dN_m_dS_SE, 17 sw_boot_dN_m_dS_P, 18 sw_boot_dN_gt_dS_count, 19 .._eq_.., 20 .._lt_..,
+ * 21 sw_ASL_dN_gt_dS_P, 22 sw_ASL_dN_lt_dS_P, 23 sw_ASL_dNdS_P */
+int snpg_sliding_windows_r(snpg_ctx *ctx, const double *stats4, const uint32_t *n_defined, const int64_t *codon_num, int64_t C,
+                           const snpg_rwindows *opt, int64_t *n_windows, double *out, int64_t out_cap_windows);
+
+/* ---- pooled-sample codon contraction ("next" row f4) ---------------------------
+ * snpgenie.pl's pooled mode (:6631-6760) knows, per codon position, the FREQUENCIES of the codons seen in the pool and
+ * the mean coverage; its mean numbers of differences between two reads are the same table contraction as the sequence
+ * engine's, on frequencies: sum over i < j of (f_i cov)(f_j cov) T[i][j] / ((cov^2 - cov) / 2).
+ * freq [C][64] (codon code order, 0 where a codon is absent), coverage [C] -> n_diffs [C], s_diffs [C].
+ * SNPG_E_INPUT where the script dies: several codons at a position whose coverage leaves no pair of reads. */
+int snpg_pooled_diffs(snpg_ctx *ctx, const double *freq, const double *coverage, int64_t C, double *n_diffs, double *s_diffs);
 
 /* ---- whole-job entry (what bench.py times) ---------------------------------
  * For every product of a loaded group, entirely on the device: per-codon stats

@@ -209,3 +209,102 @@ def site_counts(aln: np.ndarray) -> np.ndarray:
     a[lower] -= 32
     a[a == ord("U")] = ord("T")
     return np.stack([(a == ord(ch)).sum(axis=0) for ch in "ACGT"], axis=1).astype(np.uint32)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# "Next" row f2: SNPGenie_sliding_windows.R restated in numpy.  PARITY UNPINNED: there is no R in the authoring
+# container, so this restatement could not be run against the script itself; tests/test_rwindows.py pins its
+# deterministic columns against hand-derived vectors and its P values against scipy's normal distribution.
+# ---------------------------------------------------------------------------------------------------------------
+RWIN_NAMES = ("sw_start", "sw_center", "sw_end", "sw_num_replicates", "sw_N_diffs", "sw_S_diffs", "sw_N_sites", "sw_S_sites", "sw_dN", "sw_dS",
+              "sw_dNdS", "sw_dN_m_dS", "sw_boot_dN_SE", "sw_boot_dS_SE", "sw_boot_dN_over_dS_SE", "sw_boot_dN_over_dS_P", "sw_boot_dN_m_dS_SE",
+              "sw_boot_dN_m_dS_P", "sw_boot_dN_gt_dS_count", "sw_boot_dN_eq_dS_count", "sw_boot_dN_lt_dS_count", "sw_ASL_dN_gt_dS_P",
+              "sw_ASL_dN_lt_dS_P", "sw_ASL_dNdS_P")
+
+
+def _pnorm_two_sided(z):
+    """2 * pnorm(-abs(z)) (SNPGenie_sliding_windows.R:304, :311)."""
+    from math import erfc, sqrt
+    return float("nan") if z != z else erfc(abs(z) / sqrt(2.0))
+
+
+def sliding_windows_r(stats4: np.ndarray, window: int, step: int, B: int = 1000, n_defined=None, min_defined: int = 6, codon_num=None,
+                      numerator: str = "N", denominator: str = "S", correction: str = "NONE", seed: int = 1) -> dict:
+    """SNPGenie_sliding_windows.R:241-321 (bootstrap function), :326-402 (its Jukes-Cantor twin), :441-548 (the window
+    loop).  stats4 [C,4] = N_sites, S_sites, N_diffs, S_diffs.  One set of resamples serves the script's four boot() calls."""
+    stats4 = np.asarray(stats4, dtype=np.float64)
+    C_ = stats4.shape[0]
+    cn = np.arange(1, C_ + 1) if codon_num is None else np.asarray(codon_num, dtype=np.int64)
+    rows = np.arange(C_)
+    if n_defined is not None:
+        rows = rows[np.asarray(n_defined)[rows] >= min_defined]                 # :441 filter(num_defined_seqs >= MIN_DEFINED_CODONS)
+    rows = rows[np.argsort(cn[rows], kind="stable")]                            # :442 arrange(codon_num)
+    tab, num = stats4[rows], cn[rows]
+    ns, ds = {"N": 0, "S": 1}[numerator], {"N": 0, "S": 1}[denominator]
+    rng = np.random.default_rng(seed)
+    out = {k: [] for k in RWIN_NAMES}
+    if len(rows) < window:                                                      # :444
+        return {k: np.array(v) for k, v in out.items()}
+
+    def stat(x):                                                                # :252-276: the four statistics of summed columns
+        with np.errstate(divide="ignore", invalid="ignore"):
+            dn, dss = np.float64(x[..., 2 + ns]) / x[..., ns], np.float64(x[..., 2 + ds]) / x[..., ds]
+            if correction == "JC":                                              # :329, :336
+                dn, dss = -0.75 * np.log(1 - (4.0 / 3.0) * dn), -0.75 * np.log(1 - (4.0 / 3.0) * dss)
+            return dn, dss, dn / dss, dn - dss
+
+    for i in range(int(num.min()), int(num.max()) - window + 2, step):          # :445 seq(min, max - W + 1, by = STEP)
+        if i < 1 or i - 1 + window > len(rows):
+            break                                                               # (rows of NA: the script stops with an error)
+        w = tab[i - 1:i - 1 + window]                                           # :449 rows i .. i + W - 1
+        lo, hi = int(num[i - 1:i - 1 + window].min()), int(num[i - 1:i - 1 + window].max())
+        sums = np.zeros(4)
+        for r in w:                                                             # sum() in row order
+            sums += r
+        dn, dss, ratio, diff = stat(sums)
+        idx = rng.integers(0, window, size=(B, window))                         # boot(): W draws with replacement
+        t = stat(w[idx].sum(axis=1))
+        with np.errstate(invalid="ignore"):
+            se = [np.std(x, ddof=1) if np.all(np.isfinite(x)) else np.nan for x in t]      # :283-299 sd(boot$t)
+            se = [0.0 if (np.all(x == x[0]) and np.isfinite(x[0])) else s for x, s in zip(t, se)]
+        tm = t[3]
+        if np.any(np.isnan(tm)):                                                # :314-319: sums of NA comparisons are NA
+            gt = eq = lt = p_gt = p_lt = np.nan
+            asl = 1.0                                                           # :492-498
+        else:
+            gt, eq, lt = float((tm > 0).sum()), float((tm == 0).sum()), float((tm < 0).sum())
+            p_gt, p_lt = lt / (gt + eq + lt), gt / (gt + eq + lt)
+            asl = 2 * p_gt if p_gt < p_lt else 2 * p_lt
+        if asl == 0:
+            asl = 1.0 / B                                                       # :500-502
+        with np.errstate(divide="ignore", invalid="ignore"):
+            z_ratio, z_diff = np.float64(ratio) / se[2], np.float64(diff) / se[3]
+        vals = (lo, (lo + hi) / 2.0, hi, B, sums[2 + ns], sums[2 + ds], sums[ns], sums[ds], dn, dss, ratio, diff, se[0], se[1], se[2],
+                _pnorm_two_sided(z_ratio), se[3], _pnorm_two_sided(z_diff), gt, eq, lt, p_gt, p_lt, asl)
+        for k, v in zip(RWIN_NAMES, vals):
+            out[k].append(float(v))
+    return {k: np.array(v) for k, v in out.items()}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# "Next" row f4: the pooled-mode codon contraction of snpgenie.pl (:6631-6760), literally.  The tables are the pinned ones
+# (tests/golden/ng_tables.tsv = a dump of the reference's own subs); the loop itself is checked against hand-derived values.
+# ---------------------------------------------------------------------------------------------------------------
+def pooled_diffs(freq: np.ndarray, coverage: np.ndarray, diffs=None):
+    """freq [C,64] codon frequencies, coverage [C] -> (N_diffs [C], S_diffs [C]) as snpgenie.pl:6871 prints them."""
+    if diffs is None:
+        _, diffs = tables()
+    freq = np.asarray(freq, dtype=np.float64)
+    nd, sd = np.zeros(freq.shape[0]), np.zeros(freq.shape[0])
+    for c in range(freq.shape[0]):
+        cov = float(coverage[c])
+        comps = ((cov * cov) - cov) / 2                                     # :6647-6649
+        here = [i for i in range(64) if freq[c, i] > 0]                     # :6644 sort(keys): alphabetical = code order
+        for a in range(len(here)):
+            for b in range(a + 1, len(here)):
+                i, j = here[a], here[b]
+                num = (freq[c, i] * cov) * (freq[c, j] * cov)               # :6683-6685
+                w = num / comps                                             # :6752 (the script dies when comps == 0)
+                nd[c] += diffs[0, i, j] * w                                 # :6753, :6760
+                sd[c] += diffs[1, i, j] * w
+    return nd, sd

@@ -61,11 +61,61 @@ create(device, seed)
   OUTPUT:
     RETVAL
 
+IV
+create_multi(n_gpus, seed)
+    int n_gpus
+    UV seed
+  CODE:
+    /* one ctx over GPUs 0 .. n_gpus - 1 of this process (codon ranges and bootstrap replicates split over them) */
+    snpg_ctx *ctx = NULL;
+    int rc = snpg_create_multi(&ctx, n_gpus, NULL, (uint64_t)seed);
+    if (rc != SNPG_OK) croak("\n### SNPGenieCUDA could not start on %d GPUs (%d): %s\n", n_gpus, rc, snpg_last_error(NULL));
+    RETVAL = PTR2IV(ctx);
+  OUTPUT:
+    RETVAL
+
+int
+team_size(h)
+    IV h
+  CODE:
+    RETVAL = snpg_team_size(ctx_of(aTHX_ h));
+  OUTPUT:
+    RETVAL
+
 void
 destroy(h)
     IV h
   CODE:
     if (h) snpg_destroy(INT2PTR(snpg_ctx *, h));
+
+void
+within_job(h, group, ptr, n_seqs, aln_len, B, total_codons, n_products)
+    IV h
+    int group
+    IV ptr
+    UV n_seqs
+    UV aln_len
+    IV B
+    IV total_codons
+    int n_products
+  PPCODE:
+    /* the whole within-group job in ONE call (snpg_within_job_ex, host memory): load, per-codon engine, product sums and
+     * bootstrap SEs.  Returns prod_sums [P][4], prod_se [P][6], poly, n_defined, comparisons, stats4, conserved over the
+     * global codon axis (products concatenated in set_products order), all as packed strings. */
+    snpg_ctx *ctx = ctx_of(aTHX_ h);
+    STRLEN T = (STRLEN)total_codons, P = (STRLEN)n_products;
+    SV *sums = out_buf(aTHX_ 32 * P), *se = out_buf(aTHX_ 48 * P), *poly = out_buf(aTHX_ T), *ndef = out_buf(aTHX_ 4 * T);
+    SV *cmp = out_buf(aTHX_ 8 * T), *stats = out_buf(aTHX_ 32 * T), *cons = out_buf(aTHX_ T);
+    snpg_job job;
+    memset(&job, 0, sizeof job);
+    job.struct_size = sizeof job;
+    job.n_bootstraps = (int64_t)B;
+    job.prod_sums = (double *)SvPVX(sums); job.prod_se = B >= 2 ? (double *)SvPVX(se) : NULL;
+    job.poly = (uint8_t *)SvPVX(poly); job.n_defined = (uint32_t *)SvPVX(ndef); job.comparisons = (uint64_t *)SvPVX(cmp);
+    job.stats4 = (double *)SvPVX(stats); job.conserved = (uint8_t *)SvPVX(cons);
+    check(aTHX_ ctx, snpg_within_job_ex(ctx, group, INT2PTR(const uint8_t *, ptr), 0, n_seqs, aln_len, aln_len, &job), "within_job");
+    EXTEND(SP, 7);
+    PUSHs(sums); PUSHs(se); PUSHs(poly); PUSHs(ndef); PUSHs(cmp); PUSHs(stats); PUSHs(cons);
 
 void
 set_option(h, option, value)
@@ -271,6 +321,38 @@ windows(h, stats4, keep, C, W, step, B)
     PUSHs(sv_2mortal(newSViv((IV)nwin)));
     PUSHs(sums);
     PUSHs(se);
+
+void
+sliding_windows_r(h, stats4, n_defined, codon_num, C, numerator, denominator, jukes_cantor, W, step, B, min_defined)
+    IV h
+    SV *stats4
+    SV *n_defined
+    SV *codon_num
+    IV C
+    int numerator
+    int denominator
+    int jukes_cantor
+    IV W
+    IV step
+    IV B
+    IV min_defined
+  PPCODE:
+    /* SNPGenie_sliding_windows.R on one product's codon table: (number of windows, packed doubles [n][SNPG_RWIN_COLS]) */
+    snpg_ctx *ctx = ctx_of(aTHX_ h);
+    const double *st = (const double *)in_buf(aTHX_ stats4, 32 * (STRLEN)C, "stats4");
+    const uint32_t *nd = SvOK(n_defined) ? (const uint32_t *)in_buf(aTHX_ n_defined, 4 * (STRLEN)C, "n_defined") : NULL;
+    const int64_t *cn = SvOK(codon_num) ? (const int64_t *)in_buf(aTHX_ codon_num, 8 * (STRLEN)C, "codon_num") : NULL;
+    snpg_rwindows opt;
+    memset(&opt, 0, sizeof opt);
+    opt.struct_size = sizeof opt; opt.numerator = numerator; opt.denominator = denominator; opt.jukes_cantor = jukes_cantor;
+    opt.window = (int64_t)W; opt.step = (int64_t)step; opt.n_bootstraps = (int64_t)B; opt.min_defined = (int64_t)min_defined;
+    int64_t nwin = 0;
+    check(aTHX_ ctx, snpg_sliding_windows_r(ctx, st, nd, cn, (int64_t)C, &opt, &nwin, NULL, 0), "sliding_windows_r");
+    SV *out = out_buf(aTHX_ sizeof(double) * SNPG_RWIN_COLS * (STRLEN)nwin);
+    if (nwin) check(aTHX_ ctx, snpg_sliding_windows_r(ctx, st, nd, cn, (int64_t)C, &opt, &nwin, (double *)SvPVX(out), nwin), "sliding_windows_r");
+    EXTEND(SP, 2);
+    PUSHs(sv_2mortal(newSViv((IV)nwin)));
+    PUSHs(out);
 
 void
 tables()

@@ -40,7 +40,10 @@ print "\n#######################################################################
 
 my $products = read_gtf($gtf_file, $minus_strand);
 my $ctx = SNPGenieCUDA::create($device, $seed);
-SNPGenieCUDA::set_option($ctx, SNPGenieCUDA::OPT_KEEP_CODES, 1);   # the "first defined codon" rule (bg:853-890) needs sequence order
+# histograms straight from the alignment bytes (no code matrix); the "first defined codon" rule (bg:853-890) needs sequence
+# order only at conserved codons where one group is entirely undefined: a small kernel notes it while the rows go by
+SNPGenieCUDA::set_option($ctx, SNPGenieCUDA::OPT_KEEP_CODES, 0);
+SNPGenieCUDA::set_option($ctx, SNPGenieCUDA::OPT_FIRST_DEFINED, 1);
 my (@ptr, @n_seqs, $aln_len);
 for my $g (0 .. $#fasta_files) {
     my ($ptr, $n, $len) = SNPGenieCUDA::read_fasta($ctx, $g, $fasta_files[$g]);      # native reader, pinned memory

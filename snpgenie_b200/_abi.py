@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libsnpgenie_cuda.so")
 
 OK, E_ARG, E_STATE, E_INPUT, E_CUDA, E_NOMEM = 0, -1, -2, -3, -4, -5
 CODE_UNDEF, CODE_OTHER, HIST_BINS = 64, 65, 66
-OPT_KEEP_CODES, OPT_PROFILE, OPT_SITE_COUNTS, OPT_FUSED_KERNEL, OPT_BOOTSTRAP_KERNEL, OPT_BOOT_SLOTS = 1, 2, 3, 4, 5, 6
+OPT_KEEP_CODES, OPT_PROFILE, OPT_SITE_COUNTS, OPT_FUSED_KERNEL, OPT_BOOTSTRAP_KERNEL, OPT_BOOT_SLOTS, OPT_INGEST_ASYNC, OPT_FIRST_DEFINED = 1, 2, 3, 4, 5, 6, 7, 8
 BOOT_GATHER, BOOT_WEIGHTS = 0, 1
 SLOTS_CORRECTED, SLOTS_FAITHFUL = 0, 1
 PEER_HANDLE_BYTES = 128
@@ -40,6 +40,18 @@ class Job(C.Structure):
                 ("stats4", C.c_void_p), ("conserved", C.c_void_p), ("win_sums", C.c_void_p), ("win_se", C.c_void_p)]
 
 
+class RWindows(C.Structure):
+    """snpg_rwindows (include/snpgenie_cuda.h): the arguments of SNPGenie_sliding_windows.R."""
+    _fields_ = [("struct_size", C.c_uint32), ("numerator", C.c_int32), ("denominator", C.c_int32), ("jukes_cantor", C.c_int32),
+                ("window", C.c_int64), ("step", C.c_int64), ("n_bootstraps", C.c_int64), ("min_defined", C.c_int64)]
+
+
+RWIN_COLS = 24
+RWIN_NAMES = ("sw_start", "sw_center", "sw_end", "sw_num_replicates", "sw_N_diffs", "sw_S_diffs", "sw_N_sites", "sw_S_sites", "sw_dN", "sw_dS",
+              "sw_dNdS", "sw_dN_m_dS", "sw_boot_dN_SE", "sw_boot_dS_SE", "sw_boot_dN_over_dS_SE", "sw_boot_dN_over_dS_P", "sw_boot_dN_m_dS_SE",
+              "sw_boot_dN_m_dS_P", "sw_boot_dN_gt_dS_count", "sw_boot_dN_eq_dS_count", "sw_boot_dN_lt_dS_count", "sw_ASL_dN_gt_dS_P",
+              "sw_ASL_dN_lt_dS_P", "sw_ASL_dNdS_P")
+
 # every exported symbol of include/snpgenie_cuda.h with its signature
 SIGNATURES = {
     "snpg_create": (C.c_int, [C.POINTER(_ctx), C.c_int, C.c_uint64]),
@@ -56,6 +68,7 @@ SIGNATURES = {
     "snpg_load_group": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
     "snpg_load_group_device": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
     "snpg_read_fasta": (C.c_int, [_ctx, C.c_int, C.c_char_p, C.POINTER(C.c_void_p), _u64p, _u64p]),
+    "snpg_fasta_wait": (C.c_int, [_ctx, C.c_int]),
     "snpg_codon_strings": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int64, _u8p]),
     "snpg_drop_group": (C.c_int, [_ctx, C.c_int]),
     "snpg_group_size": (C.c_int, [_ctx, C.c_int, _u64p]),
@@ -67,6 +80,8 @@ SIGNATURES = {
     "snpg_between": (C.c_int, [_ctx, C.c_int, C.c_int, C.c_int, _u8p, _u32p, _u32p, _u64p, _f64p, _u8p]),
     "snpg_bootstrap_product": (C.c_int, [_ctx, _f64p, _u8p, C.c_int64, C.c_int64, _f64p, _f64p]),
     "snpg_windows": (C.c_int, [_ctx, _f64p, _u8p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _f64p, _f64p, _i64p]),
+    "snpg_sliding_windows_r": (C.c_int, [_ctx, _f64p, _u32p, _i64p, C.c_int64, C.POINTER(RWindows), _i64p, _f64p, C.c_int64]),
+    "snpg_pooled_diffs": (C.c_int, [_ctx, _f64p, _f64p, C.c_int64, _f64p, _f64p]),
     "snpg_within_all": (C.c_int, [_ctx, C.c_int, C.c_int64, _f64p, _f64p]),
     "snpg_between_all": (C.c_int, [_ctx, C.POINTER(C.c_int), C.c_int, C.c_int64, C.c_int64, C.c_int64, _f64p, _f64p]),
     "snpg_within_job": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, _f64p, _f64p]),

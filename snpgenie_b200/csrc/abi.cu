@@ -81,6 +81,7 @@ GroupView view_of(const snpg_ctx *ctx, const Group &g, int64_t c0) {
     v.other_min = g.other.as<uint32_t>() + c0;
     v.other_max = g.other.as<uint32_t>() + ctx->shard_count + c0;
     v.codes = g.has_codes ? g.codes.as<uint8_t>() + c0 * g.n_pad : nullptr;
+    v.first_def = g.has_first_def ? g.first_def.as<uint8_t>() + c0 : nullptr;
     v.n = (int64_t)g.n;
     v.n_pad = g.n_pad;
     return v;
@@ -114,6 +115,11 @@ int prepare_group(snpg_ctx *ctx, Group &g, uint64_t n_seqs) {
     }
     g.has_codes = ctx->keep_codes;
     g.has_sites = ctx->site_counts;
+    g.has_first_def = ctx->first_defined && !ctx->keep_codes && cnt > 0;
+    if (g.has_first_def) {
+        CU(ctx, g.first_def.ensure((size_t)cnt));
+        CU(ctx, cudaMemsetAsync(g.first_def.p, 0xFF, (size_t)cnt, ctx->stream));
+    }
     if (ctx->site_counts) {
         CU(ctx, g.sites.ensure(sizeof(uint32_t) * 5 * (size_t)ctx->aln_len));
         CU(ctx, cudaMemsetAsync(g.sites.p, 0, sizeof(uint32_t) * 5 * (size_t)ctx->aln_len, ctx->stream));
@@ -170,6 +176,11 @@ int pack_block(snpg_ctx *ctx, Group &g, const uint8_t *d_block, int64_t pitch, i
                 launch_fused_hist(d_block, pitch, rows, ctx->d_cons.as<uint8_t>(), ctx->d_alt.as<uint32_t>(), ctx->n_spans, ctx->d_runs.as<SpanRun>(),
                                   g.hist.as<uint32_t>(), omin, omax, ctx->d_sched.as<uint32_t>(), ctx->n_sms, ctx->stream);
             }
+        }
+        if (g.has_first_def) {
+            Launch l(ctx, SNPG_K_OTHER);
+            launch_first_defined(d_block + (ctx->col_lo - ctx->base_al), pitch, rows, ctx->d_map.as<CodonMap>(), ctx->shard_count,
+                                 g.first_def.as<uint8_t>(), ctx->stream);
         }
         if (ctx->n_irr) {
             Launch l(ctx, SNPG_K_PACK);
@@ -235,6 +246,7 @@ int snpg_get_tables(double *sites, double *diffs) {
 
 int snpg_create(snpg_ctx **out, int device, uint64_t seed) {
     if (!out) return fail(nullptr, SNPG_E_ARG, "out is NULL");
+    Trace trace("snpg_create");
     *out = nullptr;
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -283,8 +295,8 @@ void snpg_destroy(snpg_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     exchange_release(ctx);
-    for (auto &g : ctx->groups) { g.codes.release(); g.hist.release(); g.other.release(); g.sites.release(); }
-    for (auto &h : ctx->host_aln) if (h.p) cudaFreeHost(h.p);
+    for (auto &g : ctx->groups) { g.codes.release(); g.hist.release(); g.other.release(); g.sites.release(); g.first_def.release(); }
+    for (auto &h : ctx->host_aln) if (h.p) { ingest_forget(h.p); cudaFreeHost(h.p); }
     invalidate_job_graph(ctx);
     if (ctx->h_salt) cudaFreeHost(ctx->h_salt);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
@@ -333,6 +345,8 @@ int snpg_set_option(snpg_ctx *ctx, int option, int64_t value) {
         return SNPG_OK;
     }
     if (option == SNPG_OPT_PROFILE) { ctx->profile_mask = value < 0 ? 0xFFFFFFFFu : (uint32_t)value; return SNPG_OK; }
+    if (option == SNPG_OPT_INGEST_ASYNC) { ctx->ingest_async = value != 0; return SNPG_OK; }
+    if (option == SNPG_OPT_FIRST_DEFINED) { ctx->first_defined = value != 0; return SNPG_OK; }
     return fail(ctx, SNPG_E_ARG, "unknown option %d", option);
 }
 
@@ -574,6 +588,7 @@ int snpg_load_group(snpg_ctx *ctx, int group, const uint8_t *bases, uint64_t n_s
          "alignment length %llu differs from the annotation's %lld", (unsigned long long)aln_len, (long long)ctx->aln_len);
     NEED(ctx, row_stride >= aln_len, SNPG_E_ARG, "row_stride < aln_len");
     if (int rc = bind(ctx)) return rc;
+    Trace trace("snpg_load_group");
     Group &g = ctx->groups[group];
     if (int rc = prepare_group(ctx, g, n_seqs)) return rc;
 
@@ -595,6 +610,7 @@ int snpg_load_group(snpg_ctx *ctx, int group, const uint8_t *bases, uint64_t n_s
             const int b = (int)(blk & 1);
             const int64_t rows = std::min<int64_t>(rows_per, (int64_t)n_seqs - r0);
             if (blk >= 2) CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_packed[b], 0));
+            ingest_wait_rows(bases, (uint64_t)(r0 + rows));       // a FASTA slot still being parsed: the copy of this block overlaps the parse of the next
             CU(ctx, cudaMemcpy2DAsync(ctx->staging[b].p, (size_t)pitch, bases + (size_t)r0 * row_stride + ctx->base_al,
                                       (size_t)row_stride, (size_t)width, (size_t)rows, cudaMemcpyHostToDevice, ctx->copy_stream));
             CU(ctx, cudaEventRecord(ctx->ev_copied[b], ctx->copy_stream));
@@ -647,8 +663,8 @@ int snpg_drop_group(snpg_ctx *ctx, int group) {
     TEAM_EACH(ctx, snpg_drop_group(c, group));
     if (int rc = bind(ctx)) return rc;
     Group &g = ctx->groups[group];
-    g.codes.release(); g.hist.release(); g.other.release(); g.sites.release();
-    g.loaded = false; g.has_codes = false; g.has_sites = false;
+    g.codes.release(); g.hist.release(); g.other.release(); g.sites.release(); g.first_def.release();
+    g.loaded = false; g.has_codes = false; g.has_sites = false; g.has_first_def = false;
     return SNPG_OK;
 }
 

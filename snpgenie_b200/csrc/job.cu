@@ -481,6 +481,7 @@ int snpg_window_plan(snpg_ctx *ctx, int64_t window, int64_t step, int64_t *win_o
 int snpg_within_job_ex(snpg_ctx *ctx, int group, const uint8_t *bases, int bases_on_device, uint64_t n_seqs, uint64_t aln_len,
                        uint64_t row_stride, const snpg_job *job) {
     if (!ctx) return SNPG_E_ARG;
+    Trace trace(is_team(ctx) ? "snpg_within_job_ex(team)" : "snpg_within_job_ex");
     if (is_team(ctx)) return team_job(ctx, group, bases, bases_on_device, n_seqs, aln_len, row_stride, job);
     if (int rc = check_job_args(ctx, group, bases, job)) return rc;
     if (int rc = bind(ctx)) return rc;

@@ -120,6 +120,24 @@ k_pack(const uint8_t *__restrict__ aln, int64_t stride, int64_t n_rows, int64_t 
     }
 }
 
+// The first defined codon of every codon column in row order (bg:853-890 picks it when the other group has no defined
+// codon at all).  One thread per codon; nearly every thread is done after row 0.
+__global__ void k_first_defined(const uint8_t *__restrict__ aln, int64_t stride, int64_t n_rows, const CodonMap *__restrict__ map,
+                                int64_t n_codons, uint8_t *__restrict__ first)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_codons || first[c] != 0xFF) return;
+    const CodonMap m = map[c];
+    for (int64_t r = 0; r < n_rows; r++) {
+        const uint8_t *row = aln + r * stride;
+        const uint8_t k0 = class_of(norm_char(row[m.p0], m.minus)), k1 = class_of(norm_char(row[m.p1], m.minus)),
+                      k2 = class_of(norm_char(row[m.p2], m.minus));
+        if (k0 == 4 || k1 == 4 || k2 == 4) continue;             // undefined: N or '-' (wg:493,498)
+        first[c] = max(k0, max(k1, k2)) < 4 ? (uint8_t)(k0 * 16 + k1 * 4 + k2) : (uint8_t)kCodeOther;
+        return;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // K2: per-codon histogram.  Replaces the polymorphism pre-check (wg:469-541;
 // bg:472-544) and the O(n^2) pair counting (wg:596-609; bg:649-667): the 66
@@ -839,6 +857,8 @@ __device__ __forceinline__ void stats_codon(const GroupView &A, const GroupView 
                 conserved = n_acgt == 1 ? (m0 ? __ffs(m0) - 1 : 32 + __ffs(m1) - 1) : kCodeOther;
             } else if (codes) {
                 conserved = first_defined_code(codes + c * G.n_pad, G.n, lane);
+            } else if (G.first_def) {
+                conserved = G.first_def[c];
             } else {
                 conserved = n_acgt ? (m0 ? __ffs(m0) - 1 : 32 + __ffs(m1) - 1) : kCodeOther;
             }
@@ -1387,6 +1407,118 @@ k_moments(const double *__restrict__ src, int64_t n_items, int64_t B, double *__
 }
 
 // ---------------------------------------------------------------------------
+// Row f2: the per-window statistics of SNPGenie_sliding_windows.R (:241-402) from the replicate sums of the window
+// bootstrap.  One block per window.  R's arithmetic is kept as it is: dN = sum(diffs) / sum(sites) with IEEE results
+// (0/0 = NaN, x/0 = Inf -- no '*' -> 0 coercion here), optionally Jukes-Cantor (:326-361), sd() with n - 1 (two passes),
+// Z = estimate / SE, P = 2 * pnorm(-|Z|) (:303-312), the counts of replicates with dN - dS >, ==, < 0 and the achieved
+// significance levels (:314-319; a NaN replicate makes R's sums NA: NaN here).  The script bootstraps each of its four
+// statistics with its own boot() call; here the four are derived from ONE set of replicates (the same marginal
+// distributions; nothing downstream uses their joint distribution).
+// rep[window][B][4] = replicate sums (N_sites, S_sites, N_diffs, S_diffs); win_sums[window][4]; num / den: 0 = N, 1 = S.
+// out[window][16] = dN, dS, dN/dS, dN-dS, SE(dN), SE(dS), SE(dN/dS), P(dN/dS), SE(dN-dS), P(dN-dS), gt, eq, lt,
+// ASL(dN>dS), ASL(dN<dS), ASL two-sided (:492-500).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double jc_distance(double d) { return -0.75 * log(1.0 - (4.0 / 3.0) * d); }
+__device__ __forceinline__ double two_sided_p(double z) { return erfc(fabs(z) * 0.70710678118654752440); }   // 2 * pnorm(-|z|)
+
+__global__ void __launch_bounds__(kMomentThreads)
+k_window_rstats(const double *__restrict__ rep, const double *__restrict__ win_sums, int64_t B, int num, int den, int jc,
+                double *__restrict__ out)
+{
+    __shared__ double red[kMomentThreads];
+    const int w = blockIdx.x, t = threadIdx.x;
+    const double *R = rep + 4 * (size_t)w * B;
+    auto values = [&](const double *x, double v[4]) {       // dN, dS, dN/dS, dN-dS of one set of four sums
+        double dn = x[2 + num] / x[num], ds = x[2 + den] / x[den];
+        if (jc) { dn = jc_distance(dn); ds = jc_distance(ds); }
+        v[0] = dn; v[1] = ds; v[2] = dn / ds; v[3] = dn - ds;
+    };
+    double first[4], s[4] = {0, 0, 0, 0}, gt = 0, eq = 0, lt = 0, nan_d = 0;
+    values(R, first);
+    int differs = 0;                                         // bit q: some replicate's statistic q differs from the first replicate's
+    for (int64_t b = t; b < B; b += kMomentThreads) {
+        double v[4];
+        values(R + 4 * b, v);
+#pragma unroll
+        for (int q = 0; q < 4; q++) { s[q] += v[q]; differs |= (v[q] != first[q] && !(v[q] != v[q] && first[q] != first[q])) << q; }
+        gt += v[3] > 0; eq += v[3] == 0; lt += v[3] < 0; nan_d += v[3] != v[3];
+    }
+    double mean[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) mean[q] = block_sum(s[q], red) / (double)B;
+    double ss[4] = {0, 0, 0, 0};
+    for (int64_t b = t; b < B; b += kMomentThreads) {
+        double v[4];
+        values(R + 4 * b, v);
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const double d = v[q] - mean[q]; ss[q] += d * d; }
+    }
+    double sd[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) sd[q] = sqrt(block_sum(ss[q], red) / (double)(B - 1));
+    int any = 0;                                             // (__syncthreads_or is a logical OR: one call per statistic)
+#pragma unroll
+    for (int q = 0; q < 4; q++) any |= (__syncthreads_or((differs >> q) & 1) ? 1 : 0) << q;
+    gt = block_sum(gt, red); eq = block_sum(eq, red); lt = block_sum(lt, red); nan_d = block_sum(nan_d, red);
+    if (t != 0) return;
+    // identical replicates have SD exactly 0 (R's mean() is exact for them; a rounded mean here would leave 1e-19)
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        if (!((any >> q) & 1) && first[q] == first[q] && !isinf(first[q])) sd[q] = 0.0;
+    double est[4];
+    values(win_sums + 4 * (size_t)w, est);
+    double *o = out + 16 * (size_t)w;
+    o[0] = est[0]; o[1] = est[1]; o[2] = est[2]; o[3] = est[3];
+    o[4] = sd[0]; o[5] = sd[1];
+    o[6] = sd[2]; o[7] = two_sided_p(est[2] / sd[2]);
+    o[8] = sd[3]; o[9] = two_sided_p(est[3] / sd[3]);
+    const double nan = __longlong_as_double(0x7FF8000000000000ll);
+    const bool na = nan_d > 0;                               // R: sum(t > 0) is NA when a replicate is NaN
+    const double tot = gt + eq + lt;
+    const double p_gt = na ? nan : lt / tot, p_lt = na ? nan : gt / tot;
+    o[10] = na ? nan : gt; o[11] = na ? nan : eq; o[12] = na ? nan : lt;
+    o[13] = p_gt; o[14] = p_lt;
+    double asl = na ? 1.0 : 2.0 * (p_gt < p_lt ? p_gt : p_lt);
+    if (asl == 0) asl = 1.0 / (double)B;
+    o[15] = asl;
+}
+
+// ---------------------------------------------------------------------------
+// Row f4: the pooled-mode contraction f'Tf of snpgenie.pl (:6631-6760).  A pooled sample has no sequences, only codon
+// FREQUENCIES per codon position and a mean coverage; the mean numbers of differences are
+//   sum over i < j of (f_i cov)(f_j cov) T[i][j] / ((cov^2 - cov) / 2)
+// with the same tables as the sequence engine (stop codons contribute 0: they are 0 in the tables).  One thread per
+// codon position; the products and the additions are those of the script, in its order (codons sorted alphabetically =
+// ascending code), so the values are the script's to the bit.  A position with several codons but no pair of reads
+// (cov^2 - cov = 0) makes the script die: NaN here, reported by the host.
+// ---------------------------------------------------------------------------
+__global__ void k_pooled_diffs(const double *__restrict__ freq, const double *__restrict__ cov, int64_t n, const double *__restrict__ tables,
+                               double *__restrict__ n_diffs, double *__restrict__ s_diffs)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const double *TN = tables + 128, *TS = tables + 128 + 4096;
+    const double *f = freq + 64 * c;
+    const double cv = cov[c];
+    // (explicitly rounded products and sums: a fused multiply-add would differ from the script's doubles in the last bit)
+    const double comps = __dsub_rn(__dmul_rn(cv, cv), cv) / 2;      // :6647-6649
+    int present[64], m = 0;
+    for (int i = 0; i < 64; i++)
+        if (f[i] > 0) present[m++] = i;
+    double dn = 0, ds = 0;
+    for (int a = 0; a < m; a++)
+        for (int b = a + 1; b < m; b++) {
+            const int i = present[a], j = present[b];
+            const double num = __dmul_rn(__dmul_rn(f[i], cv), __dmul_rn(f[j], cv));     // :6683-6685
+            const double w = num / comps;                                                // :6752
+            dn = __dadd_rn(dn, __dmul_rn(TN[i * 64 + j], w));                            // :6753, :6760
+            ds = __dadd_rn(ds, __dmul_rn(TS[i * 64 + j], w));
+        }
+    n_diffs[c] = dn;                                         // (NaN or Inf when comps == 0 and m > 1)
+    s_diffs[c] = ds;
+}
+
+// ---------------------------------------------------------------------------
 // K5: sliding windows (wgp:314-362; bgp:501-592).  Sums run codon by codon in
 // ascending order, one thread per (window, statistic): the same additions in
 // the same order as the reference, so window sums are bitwise reproducible and
@@ -1431,6 +1563,13 @@ void launch_hist(const uint8_t *d_codes, int64_t n_pad, int64_t n_codons, uint32
     const int64_t items = n_codons * chunks;
     k_hist<<<(unsigned)((items + kHistWarps - 1) / kHistWarps), kHistWarps * 32, 0, stream>>>(d_codes, n_pad, n_codons, chunks,
                                                                                                chunk_rows, d_hist);
+}
+
+void launch_first_defined(const uint8_t *d_aln, int64_t row_stride, int64_t n_rows, const CodonMap *d_map, int64_t n_codons,
+                          uint8_t *d_first, cudaStream_t stream)
+{
+    if (n_codons <= 0 || n_rows <= 0) return;
+    k_first_defined<<<(unsigned)((n_codons + 127) / 128), 128, 0, stream>>>(d_aln, row_stride, n_rows, d_map, n_codons, d_first);
 }
 
 void launch_vote_refs(const uint8_t *d_aln, int64_t pitch, int n_sample, int64_t n_spans, uint8_t *d_cons, uint32_t *d_alt,
@@ -1600,10 +1739,12 @@ void launch_bootstrap(int form, BootArgs a, int64_t max_codons, cudaStream_t str
         static const int n_sms = [] { int d = 0, n = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n > 0 ? n : 148; }();
         static const int env_nb = [] { const char *v = getenv("SNPG_BOOT_NB"); return v ? atoi(v) : 0; }();
         static const int env_split = [] { const char *v = getenv("SNPG_BOOT_SPLIT"); return v ? atoi(v) : -1; }();
-        const int64_t target = 3ll * n_sms * 5;
-        auto blocks = [&](int nb, int split) { const int64_t per = (int64_t)(kMmaWarps >> split) * nb; return (a.b_count + per - 1) / per * a.n_items; };
+        // What counts is the longest item (scheduled first, and on config 2 nearly half of all draws): its blocks alone should
+        // fill most of the 5 * n_sms block slots, otherwise the SMs end the launch with one or two long blocks each.
+        const int64_t slots = 5ll * n_sms;
+        auto blocks = [&](int nb, int split) { const int64_t per = (int64_t)(kMmaWarps >> split) * nb; return (a.b_count + per - 1) / per; };
         int nb = 2, split = 0;
-        if (blocks(2, 0) < target) { nb = 1; if (blocks(1, 0) < target) split = 1; }
+        if (blocks(2, 0) * 5 < slots * 4) { nb = 1; if (blocks(1, 0) * 2 < slots) split = 1; }
         if (env_nb == 1 || env_nb == 2) nb = env_nb;
         if (env_split == 0 || env_split == 1) split = env_split;
         const int64_t per_mma = (int64_t)(kMmaWarps >> split) * nb;
@@ -1639,6 +1780,20 @@ void launch_moments_vals(const double *d_vals, int64_t n_items, int64_t B, doubl
 {
     if (n_items <= 0) return;
     k_moments<false><<<dim3((unsigned)n_items, 6), kMomentThreads, 0, stream>>>(d_vals, n_items, B, d_se, d_undefined, ps ? *ps : PeerSync());
+}
+
+void launch_pooled_diffs(const double *d_freq, const double *d_cov, int64_t n, const double *d_tables, double *d_n_diffs, double *d_s_diffs,
+                         cudaStream_t stream)
+{
+    if (n <= 0) return;
+    k_pooled_diffs<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(d_freq, d_cov, n, d_tables, d_n_diffs, d_s_diffs);
+}
+
+void launch_window_rstats(const double *d_rep, const double *d_win_sums, int64_t nwin, int64_t B, int num, int den, int jc, double *d_out,
+                          cudaStream_t stream)
+{
+    if (nwin <= 0) return;
+    k_window_rstats<<<(unsigned)nwin, kMomentThreads, 0, stream>>>(d_rep, d_win_sums, B, num, den, jc, d_out);
 }
 
 void launch_window_sums(const double *d_stats4, const int64_t *d_beg, const int64_t *d_end, int64_t nwin, double *d_win_sums,

@@ -6,7 +6,9 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -39,6 +41,8 @@ struct Group {
     int64_t n_pad = 0;
     DevBuf codes, hist, other;   // other: [2][count] min then max
     DevBuf sites;                // [aln_len][5] per-site A,C,G,T,other (SNPG_OPT_SITE_COUNTS)
+    DevBuf first_def;            // [count] first defined codon in row order (SNPG_OPT_FIRST_DEFINED)
+    bool has_first_def = false;
     bool has_sites = false;
     bool has_codes = false;
     bool clear_in_vote = false;  // hist/other are cleared by the load's first kernel, not by memsets
@@ -72,6 +76,8 @@ struct snpg_ctx {
     int rank = 0, world = 1;
     bool keep_codes = false;        // default route: fused histogram, no code matrix
     bool site_counts = false;       // also count A/C/G/T per alignment column while loading (whole rows are staged)
+    bool ingest_async = false;      // snpg_read_fasta returns while its second pass is still copying rows
+    bool first_defined = false;     // loads without a code matrix also note every codon's first defined codon (between-group rule)
     bool defer_load_sync = false;   // set inside a whole job: the load's kernels stay queued behind the analysis
     // annotation
     int n_products = 0;
@@ -200,6 +206,19 @@ int exchange_check_error(snpg_ctx *ctx);     // the region's error word (a peer 
 
 // team fan-out (exchange.cu): every entry point of the C ABI that a multi-GPU ctx supports starts with one of these
 bool is_team(const snpg_ctx *ctx);
+
+// FASTA slots are parsed in the background (ingest.cu): whoever reads the buffer waits for the rows it needs
+void ingest_wait_rows(const uint8_t *p, uint64_t rows);   // rows [0, rows) counted from the row p points into; no-op for other memory
+void ingest_forget(const uint8_t *buffer);                // before a slot's buffer is reused or freed
+
+// SNPG_TRACE=1 in the environment: wall time of the traced entry points on stderr (tools/cli_wall.py reads them)
+struct Trace {
+    const char *what; double t0;
+    static bool on() { static const bool v = [] { const char *e = getenv("SNPG_TRACE"); return e && *e && *e != '0'; }(); return v; }
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    explicit Trace(const char *w) : what(w), t0(on() ? now() : 0) {}
+    ~Trace() { if (on()) fprintf(stderr, "[snpg] %-24s %9.3f ms\n", what, now() - t0); }
+};
 
 }  // namespace snpg
 

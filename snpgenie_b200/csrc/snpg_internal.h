@@ -36,6 +36,7 @@ struct GroupView {
     const uint32_t *other_min;   // [codons] min packed chars over 'other' codons (kOtherNone if none)
     const uint32_t *other_max;   // [codons] max ...
     const uint8_t *codes;        // [codons][n_pad] or null
+    const uint8_t *first_def;    // [codons] code of the first defined codon in row order (SNPG_OPT_FIRST_DEFINED) or null
     int64_t n, n_pad;
 };
 
@@ -70,6 +71,12 @@ void build_tables(double *sites, double *diffs);
 void launch_pack(const uint8_t *d_aln, int64_t row_stride, int64_t n_rows, int64_t row0, const CodonMap *d_map,
                  int64_t n_codons, uint8_t *d_codes, int64_t n_pad, uint32_t *d_other_min, uint32_t *d_other_max,
                  cudaStream_t stream);
+
+// The code of the first row (in file order) whose codon is defined, per codon: what the between-group "first defined
+// codon" rule (bg:853-890) needs when no code matrix is kept.  d_first [n_codons], 0xFF = not found yet (set by the
+// caller before the first row block); every row block of a group goes through this in order.
+void launch_first_defined(const uint8_t *d_aln, int64_t row_stride, int64_t n_rows, const CodonMap *d_map, int64_t n_codons,
+                          uint8_t *d_first, cudaStream_t stream);
 
 // K2 histogram: codes[c][0..n_pad) -> hist[c][66] (u32, zeroed by the caller)
 void launch_hist(const uint8_t *d_codes, int64_t n_pad, int64_t n_codons, uint32_t *d_hist, cudaStream_t stream);
@@ -171,7 +178,7 @@ struct BootArgs {
     double *rep = nullptr, *vals = nullptr, *prod_sums = nullptr;
     PeerVals pv; PeerSync ps;
 };
-enum BootKind : uint32_t { kBootProduct = 1, kBootWindow = 2, kBootAllDevice = 3, kBootJob = 4, kBootBetween = 5, kBootJobWindow = 6 };
+enum BootKind : uint32_t { kBootProduct = 1, kBootWindow = 2, kBootAllDevice = 3, kBootJob = 4, kBootBetween = 5, kBootJobWindow = 6, kBootRWindow = 7 };
 // form: SNPG_BOOT_WEIGHTS (slot counters + tensor-core contraction) or SNPG_BOOT_GATHER (per-draw row gathers);
 // max_codons = the longest item (sizes the shared-memory table; beyond the limit: gathers from global memory).
 void launch_bootstrap(int form, BootArgs a, int64_t max_codons, cudaStream_t stream);
@@ -184,6 +191,17 @@ void launch_moments(const double *d_rep, int64_t n_items, int64_t B, double *d_s
 // ps (or null): wait for stage kStageVals first.
 void launch_moments_vals(const double *d_vals, int64_t n_items, int64_t B, double *d_se, uint32_t *d_undefined, const PeerSync *ps,
                          cudaStream_t stream);
+
+// Row f4 (snpgenie.pl:6631-6760): per codon position, freq[c][64] codon frequencies and cov[c] mean coverage -> mean numbers of
+// nonsynonymous and synonymous differences between two reads of the pool.
+void launch_pooled_diffs(const double *d_freq, const double *d_cov, int64_t n, const double *d_tables, double *d_n_diffs, double *d_s_diffs,
+                         cudaStream_t stream);
+
+// Row f2 (SNPGenie_sliding_windows.R:241-402): rep[window][B][4] replicate sums + win_sums[window][4] -> out[window][16]
+// (dN, dS, dN/dS, dN-dS, their bootstrap SEs and Z-test P values, the >/==/< 0 counts of dN-dS and the achieved
+// significance levels).  num / den: 0 = N, 1 = S columns; jc != 0: Jukes-Cantor distances.
+void launch_window_rstats(const double *d_rep, const double *d_win_sums, int64_t nwin, int64_t B, int num, int den, int jc, double *d_out,
+                          cudaStream_t stream);
 
 // K5 windows: window k sums the codons [beg[k], end[k]) in ascending order; its bootstrap is launch_bootstrap over the same items
 void launch_window_sums(const double *d_stats4, const int64_t *d_beg, const int64_t *d_end, int64_t nwin, double *d_win_sums,

@@ -182,6 +182,10 @@ class Engine:
         self._ck(_abi.lib.snpg_read_fasta(self._ctx, slot, path.encode(), C.byref(ptr), C.byref(n), C.byref(length)))
         return ptr.value, n.value, length.value
 
+    def fasta_wait(self, slot: int):
+        """With OPT_INGEST_ASYNC: returns when the whole buffer of the slot is parsed (library calls wait by themselves)."""
+        self._ck(_abi.lib.snpg_fasta_wait(self._ctx, slot))
+
     def fasta_view(self, ptr: int, n_seqs: int, aln_len: int) -> np.ndarray:
         """numpy view of a read_fasta buffer (valid until the slot is read into again)."""
         return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n_seqs, aln_len))
@@ -258,6 +262,35 @@ class Engine:
         self._ck(_abi.lib.snpg_windows(self._ctx, _ptr(stats4, C.c_double), _ptr(keep8, C.c_uint8), stats4.shape[0], W, step, B,
                                        _ptr(sums, C.c_double), _ptr(se, C.c_double), C.byref(nwin)))
         return sums, se
+
+    def sliding_windows_r(self, stats4: np.ndarray, window: int, step: int, B: int = 1000, n_defined: np.ndarray | None = None,
+                          min_defined: int = 6, codon_num: np.ndarray | None = None, numerator: str = "N", denominator: str = "S",
+                          correction: str = "NONE") -> dict:
+        """SNPGenie_sliding_windows.R on one product's per-codon table (snpg_sliding_windows_r): the script's arguments
+        (2)-(8), its output columns as a dict of arrays, one entry per window."""
+        stats4 = np.ascontiguousarray(stats4, dtype=np.float64)
+        nd = None if n_defined is None else np.ascontiguousarray(n_defined, dtype=np.uint32)
+        cn = None if codon_num is None else np.ascontiguousarray(codon_num, dtype=np.int64)
+        sel = {"N": 0, "S": 1}
+        opt = _abi.RWindows(C.sizeof(_abi.RWindows), sel[numerator], sel[denominator], 1 if correction == "JC" else 0, window, step, B, min_defined)
+        n = C.c_int64()
+        args = (self._ctx, _ptr(stats4, C.c_double), _ptr(nd, C.c_uint32), _ptr(cn, C.c_int64), stats4.shape[0], C.byref(opt), C.byref(n))
+        self._ck(_abi.lib.snpg_sliding_windows_r(*args, None, 0))
+        out = np.zeros((n.value, _abi.RWIN_COLS))
+        if n.value:
+            self._ck(_abi.lib.snpg_sliding_windows_r(*args, _ptr(out, C.c_double), n.value))
+        return {k: out[:, i] for i, k in enumerate(_abi.RWIN_NAMES)}
+
+    def pooled_diffs(self, freq: np.ndarray, coverage: np.ndarray):
+        """snpgenie.pl's pooled-mode contraction (snpg_pooled_diffs): freq [C,64] codon frequencies, coverage [C] ->
+        (N_diffs [C], S_diffs [C])."""
+        freq = np.ascontiguousarray(freq, dtype=np.float64)
+        cov = np.ascontiguousarray(coverage, dtype=np.float64)
+        assert freq.ndim == 2 and freq.shape[1] == 64 and cov.shape == (freq.shape[0],)
+        nd, sd = np.zeros(freq.shape[0]), np.zeros(freq.shape[0])
+        self._ck(_abi.lib.snpg_pooled_diffs(self._ctx, _ptr(freq, C.c_double), _ptr(cov, C.c_double), freq.shape[0], _ptr(nd, C.c_double),
+                                            _ptr(sd, C.c_double)))
+        return nd, sd
 
     # -- whole job ----------------------------------------------------------------
     def within_all(self, group: int, B: int = 0):

@@ -16,6 +16,7 @@ from tests.refio import STATS
 
 pytestmark = pytest.mark.gpu
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 RTOL = 1e-12
 
 
@@ -241,13 +242,26 @@ def test_config3_shape_against_oracle(eng2):
         assert close(got[k], lit[k]), k
 
 
-def test_between_mid_size_against_oracle(eng):
+@pytest.mark.parametrize("route", ["codes", "first_defined"])
+def test_between_mid_size_against_oracle(route):
+    """route "codes": the kept code matrix serves the first-defined-codon rule; "first_defined": the fast histogram route
+    with SNPG_OPT_FIRST_DEFINED (what the between-group command line uses) must give the same answers."""
+    from snpgenie_b200 import _abi
+    from snpgenie_b200.engine import Engine
+    with Engine(device=0, seed=1234, keep_codes=(route == "codes")) as eng:
+        if route == "first_defined":
+            eng.set_option(_abi.OPT_FIRST_DEFINED, 1)
+        _between_mid_size(eng)
+
+
+def _between_mid_size(eng):
     products = synth.sars2_products()[2:5]
     a = synth.make_alignment(900, 29903, products, 5, gap_frac=0.01, n_frac=0.01)
     b = synth.make_alignment(700, 29903, products, 5, gap_frac=0.01, n_frac=0.01, p_poly=0.5)
     b[:, 21600:21700] = a[0, 21600:21700]
     b[:, 21563 + 3 * 50:21563 + 3 * 53] = ord("-")     # group b undefined where group a varies or not
     a[::2, 21563 + 3 * 51] = ord("A"); a[1::2, 21563 + 3 * 51] = ord("C")
+    a[:3, 21563 + 3 * 51] = ord("N")                   # ... and the first defined codon of group a is not in its first rows
     eng.set_products(products, 29903)
     eng.load_group(0, a)
     eng.load_group(1, b)
@@ -951,6 +965,61 @@ def test_native_fasta_reader_matches_reference_semantics(tmp_path, eng):
         assert (eng.hist(0, i)[0] == orc.hist(codes)).all()
         for c in (0, 7, p.n_codons - 1):
             assert np.array_equal(eng.codon_strings(0, i, c, n), raw[:, c])
+
+
+@pytest.mark.parametrize("threads", ["1", "3", "16"])
+def test_native_fasta_reader_threads_and_background_copy(tmp_path, threads):
+    """The reader cuts the file into one byte range per thread (records and lines straddle the cuts) and, with
+    OPT_INGEST_ASYNC, copies the rows in the background while the load already moves the first row blocks."""
+    import subprocess
+    import sys
+    # a 40 MB FASTA wrapped at 61 columns with CRs, blank lines and one multi-megabyte header-free stretch per record
+    code = r"""
+import os, sys, numpy as np
+sys.path.insert(0, %r)
+from snpgenie_b200 import _abi, synth, hostio
+from snpgenie_b200.engine import Engine
+from oracle import oracle as orc
+rng = np.random.default_rng(7)
+n, L = 1300, 29903
+products = synth.sars2_products()
+aln = synth.make_alignment(n, L, products, 5, gap_frac=0.01, n_frac=0.01)
+path = os.path.join(%r, "big.fa")
+with open(path, "wb") as fh:
+    for r in range(n):
+        fh.write(b">seq%%d some description > with a bracket\n" %% r)
+        row = aln[r].tobytes()
+        w = 61 if r %% 3 else 997
+        for k in range(0, L, w):
+            fh.write(row[k:k + w] + b"\n")
+        if r %% 50 == 0:
+            fh.write(b"\n\n")
+with Engine(device=0) as eng:
+    for async_ in (0, 1):
+        eng.set_option(_abi.OPT_INGEST_ASYNC, async_)
+        ptr, nn, LL = eng.read_fasta(0, path)
+        assert (nn, LL) == (n, L)
+        eng.set_products(products, L)
+        eng.load_group_ptr(0, ptr, nn, LL, LL, device=False)      # waits row block by row block when the copy is still running
+        for i in (0, 3, 9):
+            pos = orc.product_positions(products[i].starts, products[i].stops, products[i].strand, L)
+            _, codes = orc.extract(aln, pos, products[i].strand)
+            assert (eng.hist(0, i)[0] == orc.hist(codes)).all(), (async_, i)
+        eng.fasta_wait(0)
+        assert np.array_equal(eng.fasta_view(ptr, nn, LL), aln), async_
+    # a second file into the same slot while nothing is pending; ragged input still fails in pass 1
+    bad = os.path.join(%r, "bad.fa")
+    open(bad, "wb").write(b">a\nACGT\nAC\n>b\nACGTA\n")
+    try:
+        eng.read_fasta(0, bad)
+        raise SystemExit("ragged FASTA accepted")
+    except _abi.SnpgError as e:
+        assert "same length" in str(e)
+print("ok")
+""" % (ROOT, str(tmp_path), str(tmp_path))
+    env = dict(os.environ, SNPG_INGEST_THREADS=threads)
+    p = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+    assert p.returncode == 0 and "ok" in p.stdout, p.stdout[-3000:]
 
 
 def test_philox_known_answers(eng):

@@ -46,7 +46,8 @@ def test_glue_loads_and_tables_match_header_contract():
 
 
 @pytest.mark.parametrize("script", ["snpgenie_within_group_b200.pl", "snpgenie_between_group_b200.pl",
-                                    "snpgenie_within_group_processor_b200.pl", "snpgenie_between_group_processor_b200.pl"])
+                                    "snpgenie_within_group_processor_b200.pl", "snpgenie_between_group_processor_b200.pl",
+                                    "SNPGenie_sliding_windows_b200.pl"])
 def test_scripts_compile(script):
     p = subprocess.run(["perl", "-c", os.path.join(PERL, script)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert p.returncode == 0, p.stdout
@@ -234,3 +235,55 @@ def test_within_processor_cli_matches_reference(tmp_path):
         if float(g["SE_dN_minus_dS"]) > 0:
             ratios.append(float(m["SE_dN_minus_dS"]) / float(g["SE_dN_minus_dS"]))
     assert 0.85 < np.median(ratios) < 1.2
+
+
+def test_sliding_windows_cli_validates_arguments_like_the_r_script(tmp_path):
+    p = subprocess.run(["perl", os.path.join(PERL, "SNPGenie_sliding_windows_b200.pl"), "x.tsv", "N", "S"], cwd=tmp_path, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    assert p.returncode == 1 and "Command line Error 1" in p.stdout and "there must be 5-10 command line arguments" in p.stdout
+    p = subprocess.run(["perl", os.path.join(PERL, "SNPGenie_sliding_windows_b200.pl"), "x.tsv", "N", "S", "1", "1"], cwd=tmp_path,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert p.returncode == 1 and "Command line Error 5" in p.stdout
+
+
+@pytest.mark.gpu
+def test_sliding_windows_cli_on_a_between_group_table(tmp_path):
+    """The drop-in for SNPGenie_sliding_windows.R on one product x one group pair of the reference's own between-group
+    codon table: window numbering, sums and ratios against the oracle's restatement of the script; the table layout
+    (input columns + num_defined_seqs + codon_num + sw_* columns, NA outside window starts) as write_tsv leaves it."""
+    from oracle import oracle as orc
+    d = os.path.join(refio.GOLD, "b_3groups")
+    hdr, rows = refio.read_tsv(os.path.join(d, "between_group_codon_results.txt"))
+    first = rows[0]
+    sel = [r for r in rows if (r["product"], r["group_1"], r["group_2"]) == (first["product"], first["group_1"], first["group_2"])]
+    with open(tmp_path / "one.txt", "w") as fh:
+        fh.write("\t".join(hdr) + "\n")
+        for r in sel:
+            fh.write("\t".join(r[h] for h in hdr) + "\n")
+    env = dict(os.environ, SNPG_SEED="5")
+    p = subprocess.run(["perl", os.path.join(PERL, "SNPGenie_sliding_windows_b200.pl"), "one.txt", "N", "S", "8", "2", "3000", "4", "NONE", "1"],
+                       cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+    assert p.returncode == 0, p.stdout
+    assert "BETWEEN-GROUP FILE DETECTED" in p.stdout and "DONE" in p.stdout
+    oh, orows = refio.read_tsv(os.path.join(tmp_path, "one_WINDOWS_dNdS.tsv"))
+    assert oh[:len(hdr)] == hdr and oh[len(hdr):len(hdr) + 3] == ["num_defined_seqs", "codon_num", "sw_ratio"] and oh[-1] == "sw_ASL_dNdS_P"
+    assert len(orows) == len(sel)
+    t = np.array([[float(r[k]) for k in ("N_sites", "S_sites", "N_diffs", "S_diffs")] for r in sel])
+    nd = np.array([min(int(r["num_defined_codons_g1"]), int(r["num_defined_codons_g2"])) for r in sel])
+    cn = np.array([int(r["codon"].replace("codon_", "")) for r in sel])
+    want = orc.sliding_windows_r(t, 8, 2, B=100, n_defined=nd, min_defined=4, codon_num=cn)
+    starts = {int(s): k for k, s in enumerate(want["sw_start"])}
+    seen = 0
+    for r in orows:
+        k = starts.get(int(r["codon_num"]))
+        if k is None:
+            assert r["sw_start"] == "NA" and r["sw_boot_dN_SE"] == "NA"
+            continue
+        seen += 1
+        assert r["sw_ratio"] == "dNdS" and int(r["sw_num_replicates"]) == 3000
+        for col in ("sw_start", "sw_center", "sw_end", "sw_N_diffs", "sw_S_diffs", "sw_N_sites", "sw_S_sites", "sw_dN", "sw_dS", "sw_dNdS", "sw_dN_m_dS"):
+            w = want[col][k]
+            assert (r[col] == "NaN") if w != w else close(float(r[col]), w, rtol=1e-12), (col, r[col], w)
+        if r["sw_boot_dN_gt_dS_count"] != "NaN":
+            assert int(float(r["sw_boot_dN_gt_dS_count"])) + int(float(r["sw_boot_dN_eq_dS_count"])) + int(float(r["sw_boot_dN_lt_dS_count"])) == 3000
+    assert seen == len(starts) > 0

@@ -20,6 +20,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=10000)
 ap.add_argument("--boot", type=int, default=10000)
 ap.add_argument("--width", type=int, default=70, help="FASTA line width (0 = one line per sequence)")
+ap.add_argument("--gpus", type=int, default=1)
 a = ap.parse_args()
 products = synth.sars2_products()
 with tempfile.TemporaryDirectory() as d:
@@ -35,12 +36,16 @@ with tempfile.TemporaryDirectory() as d:
                 os.remove(os.path.join(d, f))
         t0 = time.perf_counter()
         p = subprocess.run(["perl", os.path.join(ROOT, "perl", "snpgenie_within_group_b200.pl"), "--fasta_file_name=aln.fasta",
-                            "--gtf_file_name=cds.gtf", f"--num_bootstraps={a.boot}", "--procs_per_node=16", "--no_bootstrap_files"],
-                           cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                            "--gtf_file_name=cds.gtf", f"--num_bootstraps={a.boot}", "--procs_per_node=16", "--no_bootstrap_files",
+                            f"--gpus={a.gpus}"],
+                           cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=dict(os.environ, SNPG_TRACE="1"))
         wall = time.perf_counter() - t0
         if p.returncode:
             print(p.stdout[-2000:])
             sys.exit(1)
         rows = sum(1 for _ in open(os.path.join(d, "within_group_codon_results.txt"))) - 1
-        print(f"run {rep}: within-group CLI wall {wall:.2f} s ({rows} codon rows, {a.n} seqs, B={a.boot})", flush=True)
+        print(f"run {rep}: within-group CLI wall {wall:.2f} s ({rows} codon rows, {a.n} seqs, B={a.boot}, {a.gpus} GPU(s))", flush=True)
+        for line in p.stdout.splitlines():           # where the time goes: the library's traced entry points, the script's phases
+            if line.startswith(("[snpg]", "[perl]")):
+                print("    " + line)
     print(open(os.path.join(d, "within_group_product_results.txt")).read()[:600])
