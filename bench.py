@@ -247,7 +247,7 @@ def run_ours(args):
 
     products = synth.sars2_products()
     codons = sum(p.n_codons for p in products)
-    aln = synth.make_alignment(N_SEQS, ALN_LEN, products, SEED, p_poly=args.p_poly)      # the same alignment on every rank
+    aln = synth.make_alignment(N_SEQS, ALN_LEN, products, SEED, p_poly=args.p_poly, max_changes=args.max_changes, max_alleles=args.max_alleles)      # the same alignment on every rank
     pitch = (ALN_LEN + 127) // 128 * 128
     # pinned host copy (e2e input) and HBM-resident copy with a 128-B row pitch (value input)
     h_aln = torch.empty((N_SEQS, ALN_LEN), dtype=torch.uint8).pin_memory()
@@ -391,7 +391,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_res, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u8 codon codes / u32 histograms / f64 statistics", "data": "synthetic",
-            "config": dict(workload_config(world), **({} if args.p_poly == 0.3 else {"p_poly": args.p_poly, "side_experiment": True})),
+            "config": dict(workload_config(world), **({} if args.p_poly == 0.3 and args.max_changes == 3 and args.max_alleles == 3 else {"p_poly": args.p_poly, "max_changes_per_allele": args.max_changes, "max_alleles_per_codon": args.max_alleles, "side_experiment": True})),
             # the library stages only the CDS columns of a rank's codon range: from its first column rounded down to 16 to its last
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e,
                     "host_buffer_bytes": int(N_SEQS * ALN_LEN), "h2d_bytes_per_rank": [int(N_SEQS * w) for w in widths] if widths else None,
@@ -586,6 +586,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg and the oracle check")
     ap.add_argument("--no-extras", action="store_true", help="skip the config 3/4/5 side measurements")
+    ap.add_argument("--max-alleles", type=int, default=3, help="side experiment: minor alleles per polymorphic codon, at most (default 3)")
+    ap.add_argument("--max-changes", type=int, default=3,
+                    help="side experiment: nucleotides an allele changes in its codon, at most (default 3: one, two or three with equal chance)")
     ap.add_argument("--p-poly", type=float, default=0.3,
                     help="fraction of polymorphic codon columns in the synthetic alignment (SURVEY.md 8d: 0.3; "
                          "other values are side experiments, never the bench line)")

@@ -45,7 +45,7 @@ def hiv_products() -> list[Product]:
     ]
 
 
-def make_alignment(n: int, length: int, products: list[Product], seed: int, *, p_poly: float = 0.3,
+def make_alignment(n: int, length: int, products: list[Product], seed: int, *, p_poly: float = 0.3, max_changes: int = 3, max_alleles: int = 3,
                    gap_frac: float = 0.0, n_frac: float = 0.0, iupac_frac: float = 0.0,
                    lower_frac: float = 0.0, u_frac: float = 0.0) -> np.ndarray:
     """uint8 matrix [n, length] of ASCII residues."""
@@ -66,7 +66,7 @@ def make_alignment(n: int, length: int, products: list[Product], seed: int, *, p
         nc = len(pos) // 3
         for c in np.flatnonzero(rng.random(nc) < p_poly):
             cols = pos[3 * c:3 * c + 3]
-            k = int(rng.integers(1, 4))  # minor alleles
+            k = min(int(rng.integers(1, 4)), max_alleles)  # minor alleles
             freqs = rng.beta(0.5, 5.0, size=k)
             assign = rng.random(n)
             lo = 0.0
@@ -76,6 +76,8 @@ def make_alignment(n: int, length: int, products: list[Product], seed: int, *, p
                 if rows.size == 0:
                     continue
                 npos = int(rng.integers(1, 4))
+                if npos > max_changes:      # max_changes = 1: every allele is a single-nucleotide change (side experiments)
+                    npos = max_changes
                 which = rng.choice(3, size=npos, replace=False)
                 for w in which:
                     old = aln[rows[0], cols[w]]

@@ -19,10 +19,12 @@ ap.add_argument("--route", default="fused")
 ap.add_argument("--n", type=int, default=10000)
 ap.add_argument("--boot", type=int, default=10000)
 ap.add_argument("--p-poly", type=float, default=0.3)
+ap.add_argument("--max-changes", type=int, default=3)
+ap.add_argument("--max-alleles", type=int, default=3)
 a = ap.parse_args()
 products = synth.sars2_products()
 L = 29903
-aln = synth.make_alignment(a.n, L, products, 20261021, p_poly=a.p_poly)
+aln = synth.make_alignment(a.n, L, products, 20261021, p_poly=a.p_poly, max_changes=a.max_changes, max_alleles=a.max_alleles)
 pitch = (L + 127) // 128 * 128
 d = torch.zeros((a.n, pitch), dtype=torch.uint8, device="cuda:0")
 d[:, :L] = torch.from_numpy(aln).cuda()
