@@ -146,8 +146,15 @@ int snpg_codon_strings(snpg_ctx *ctx, int slot, int product, int64_t codon, uint
 #define SNPG_FUSED_TMA_TILES 0
 #define SNPG_FUSED_LDG_SPANS 1
 #define SNPG_FUSED_TMA_SPANS 2
-/* SNPG_OPT_BOOTSTRAP_KERNEL (default SNPG_BOOT_WEIGHTS): how the whole-product bootstrap (wg:854-916) sums a
- * replicate.  WEIGHTS: every draw bumps a 1-byte counter of its slot in shared memory -- a warp turns its
+/* SNPG_OPT_BOOTSTRAP_KERNEL (default SNPG_BOOT_CLASSES): how the whole-product bootstrap (wg:854-916) sums a
+ * replicate.  CLASSES: a replicate is C independent uniform draws, so the numbers of draws per slot are multinomial
+ * and the draws that land on codons with identical rows only count through their total.  The conserved codons of a
+ * product (N_diffs = S_diffs = 0) fall into a handful of classes of identical (N_sites, S_sites); a chain of exact
+ * binomial variates (inversion below a mean of 10, Hoermann's BTRS rejection sampler above) gives every replicate its
+ * number of draws per class and the number of draws on the remaining codons, and only those are drawn one by one, as
+ * WEIGHTS does.  The same distribution of replicate sums as the other two forms from a different use of the Philox
+ * stream; on a typical alignment (most codons conserved) a fraction of the draws.  Sliding windows and tables beyond
+ * shared memory take WEIGHTS / GATHER.  WEIGHTS: every draw bumps a 1-byte counter of its slot in shared memory -- a warp turns its
  * replicate into a row of the multinomial weight matrix -- and the block contracts its rows with the product's
  * (N_sites, S_sites, N_diffs, S_diffs) table as FP64 tensor-core tiles.  GATHER: every draw gathers its codon's
  * row from a shared-memory table and adds it.  Same Philox stream draw for draw: the replicate sums of the two
@@ -155,6 +162,7 @@ int snpg_codon_strings(snpg_ctx *ctx, int slot, int product, int64_t codon, uint
 #define SNPG_OPT_BOOTSTRAP_KERNEL 5
 #define SNPG_BOOT_GATHER 0
 #define SNPG_BOOT_WEIGHTS 1
+#define SNPG_BOOT_CLASSES 2
 /* SNPG_OPT_BOOT_SLOTS (default SNPG_SLOTS_FAITHFUL): the whole-product bootstrap of the reference draws
  * int(rand(C+1)) (wg:885; bgp:919), i.e. C+1 slots of which slot 0 is a codon that does not exist and adds
  * nothing -- every replicate is on average C/(C+1) of a product.  FAITHFUL reproduces that; CORRECTED draws from

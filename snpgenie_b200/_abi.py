@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libsnpgenie_cuda.so")
 OK, E_ARG, E_STATE, E_INPUT, E_CUDA, E_NOMEM = 0, -1, -2, -3, -4, -5
 CODE_UNDEF, CODE_OTHER, HIST_BINS = 64, 65, 66
 OPT_KEEP_CODES, OPT_PROFILE, OPT_SITE_COUNTS, OPT_FUSED_KERNEL, OPT_BOOTSTRAP_KERNEL, OPT_BOOT_SLOTS, OPT_INGEST_ASYNC, OPT_FIRST_DEFINED = 1, 2, 3, 4, 5, 6, 7, 8
-BOOT_GATHER, BOOT_WEIGHTS = 0, 1
+BOOT_GATHER, BOOT_WEIGHTS, BOOT_CLASSES = 0, 1, 2
 SLOTS_CORRECTED, SLOTS_FAITHFUL = 0, 1
 PEER_HANDLE_BYTES = 128
 FUSED_TMA_TILES, FUSED_LDG_SPANS, FUSED_TMA_SPANS = 0, 1, 2

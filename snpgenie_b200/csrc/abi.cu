@@ -232,6 +232,16 @@ int finish_group(snpg_ctx *ctx, Group &g) {
 
 }  // namespace
 
+namespace snpg {
+int boot_classes_scratch(snpg_ctx *ctx, BootArgs &a, int64_t total) {
+    if (ctx->boot_kernel != SNPG_BOOT_CLASSES) return SNPG_OK;
+    CU(ctx, ctx->s_boot.ensure(boot_scratch_bytes(total, a.n_items, a.b_count)));
+    boot_scratch_carve(ctx->s_boot.p, total, a.n_items, a.b_count, a);
+    ctx->launches += 2;        // k_boot_classify, k_boot_split
+    return SNPG_OK;
+}
+}  // namespace snpg
+
 extern "C" {
 
 const char *snpg_version(void) { return "snpgenie-b200 0.1 (sm_100a)"; }
@@ -304,7 +314,7 @@ void snpg_destroy(snpg_ctx *ctx) {
                       &ctx->d_runs, &ctx->d_tiles, &ctx->d_sched, &ctx->d_salt, &ctx->d_regular, &ctx->d_irr_map, &ctx->d_irr_idx, &ctx->d_cons, &ctx->d_alt, &ctx->t_codes, &ctx->t_hist,
                       &ctx->t_other, &ctx->wplan.beg, &ctx->wplan.end, &ctx->w_sums, &ctx->w_vals, &ctx->w_se, &ctx->s_undef,
                       &ctx->s_stats, &ctx->s_poly, &ctx->s_nda, &ctx->s_ndb, &ctx->s_cmp, &ctx->s_cons, &ctx->s_sums,
-                      &ctx->s_rep, &ctx->s_se, &ctx->s_misc, &ctx->s_in, &ctx->s_vals, &ctx->d_order_local, &ctx->d_order_full};
+                      &ctx->s_boot, &ctx->s_rep, &ctx->s_se, &ctx->s_misc, &ctx->s_in, &ctx->s_vals, &ctx->d_order_local, &ctx->d_order_full};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
@@ -340,7 +350,7 @@ int snpg_set_option(snpg_ctx *ctx, int option, int64_t value) {
         return SNPG_OK;
     }
     if (option == SNPG_OPT_BOOTSTRAP_KERNEL) {
-        NEED(ctx, value == SNPG_BOOT_GATHER || value == SNPG_BOOT_WEIGHTS, SNPG_E_ARG, "unknown bootstrap kernel %lld", (long long)value);
+        NEED(ctx, value == SNPG_BOOT_GATHER || value == SNPG_BOOT_WEIGHTS || value == SNPG_BOOT_CLASSES, SNPG_E_ARG, "unknown bootstrap kernel %lld", (long long)value);
         ctx->boot_kernel = (int)value;
         return SNPG_OK;
     }
@@ -844,6 +854,7 @@ int snpg_bootstrap_product(snpg_ctx *ctx, const double *stats4, const uint8_t *k
         a.stats4 = ctx->s_in.as<double>(); a.beg = ctx->s_misc.as<int64_t>(); a.end = a.beg + 1; a.n_items = 1; a.slot0 = ctx->boot_slot0;
         a.b_count = B; a.key = philox_key(ctx); a.kind = kBootProduct; a.call = ctx->call_id++;
         a.rep = sums_out ? ctx->s_rep.as<double>() : nullptr; a.vals = ctx->s_vals.as<double>();
+        if (int rc = boot_classes_scratch(ctx, a, C)) return rc;
         launch_bootstrap(ctx->boot_kernel, a, C, ctx->stream);
     }
     { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->s_vals.as<double>(), 1, B, ctx->s_se.as<double>(), nullptr, nullptr, ctx->stream); }
@@ -937,6 +948,7 @@ int snpg_bootstrap_all_device(snpg_ctx *ctx, const double *d_stats4_full, int64_
         a.stats4 = d_stats4_full; a.beg = ctx->d_full_ofs.as<int64_t>(); a.end = a.beg + 1; a.order = ctx->d_order_full.as<int>();
         a.n_items = ctx->n_products; a.slot0 = ctx->boot_slot0; a.b_first = b_first; a.b_count = b_count;
         a.key = philox_key(ctx); a.kind = kBootAllDevice; a.call = 0; a.rep = d_rep_out;
+        if (int rc = boot_classes_scratch(ctx, a, ctx->full_ofs[(size_t)ctx->n_products])) return rc;
         launch_bootstrap(ctx->boot_kernel, a, ctx->max_codons_full, ctx->stream);
     }
     CU(ctx, cudaGetLastError());
@@ -1015,6 +1027,7 @@ int snpg_between_all(snpg_ctx *ctx, const int *groups, int n_groups, int64_t min
                     a.n_items = P; a.slot0 = ctx->boot_slot0; a.b_count = B; a.key = philox_key(ctx); a.kind = kBootBetween; a.call = call;
                     a.item0 = (uint32_t)(pair * P);  // every (pair, product) its own stream
                     a.vals = ctx->s_vals.as<double>(); a.prod_sums = d_pair_sums;
+                    if (int rc = boot_classes_scratch(ctx, a, cnt)) return rc;
                     launch_bootstrap(ctx->boot_kernel, a, ctx->max_codons_local, ctx->stream);
                 }
                 { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->s_vals.as<double>(), P, B, ctx->s_se.as<double>() + 6 * (size_t)P * pair, nullptr, nullptr, ctx->stream); }

@@ -79,6 +79,7 @@ int job_prepare(snpg_ctx *ctx, const snpg_job &job) {
         CU(ctx, ctx->s_cmp.ensure(sizeof(uint64_t) * (size_t)cnt));
         if (B >= 2) CU(ctx, ctx->s_vals.ensure(sizeof(double) * 6 * (size_t)(B * P)));
     }
+    if (B >= 2 && ctx->boot_kernel == SNPG_BOOT_CLASSES) CU(ctx, ctx->s_boot.ensure(boot_scratch_bytes(axis, P, B)));
     CU(ctx, ctx->s_sums.ensure(sizeof(double) * 4 * (size_t)P));
     CU(ctx, ctx->s_se.ensure(sizeof(double) * 6 * (size_t)P));
     CU(ctx, ctx->s_undef.ensure(sizeof(uint32_t) * 6 * (size_t)P));
@@ -259,6 +260,7 @@ int job_record(snpg_ctx *ctx, int group, const uint8_t *bases, int on_device, ui
             } else {
                 a.vals = ctx->s_vals.as<double>();
             }
+            if (int rc = boot_classes_scratch(ctx, a, axis_codons(ctx))) return rc;
             launch_bootstrap(ctx->boot_kernel, a, max_codons, ctx->stream);
         }
         stats_arrived = true;             // every block of the bootstrap waited for them

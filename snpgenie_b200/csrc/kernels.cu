@@ -16,6 +16,8 @@
 
 #include <cstdlib>
 
+#include <cooperative_groups.h>
+
 #include "snpg_device.cuh"
 #include "../../include/snpgenie_cuda.h"
 #include "snpg_internal.h"
@@ -1164,6 +1166,290 @@ k_bootstrap(const __grid_constant__ BootArgs a)
     peer_signal(a.ps, kStageVals, mine);
 }
 
+// ---------------------------------------------------------------------------
+// K4, class-aggregated form (SNPG_BOOT_CLASSES; snpg_internal.h: BootClasses).  Two small kernels ahead of the
+// weight-matrix kernel:
+//   k_boot_classify  one block per item: the conserved codons (N_diffs = S_diffs = 0) are grouped by the bit patterns of
+//                    (N_sites, S_sites) in a 64-entry shared-memory table; the kBootMaxClasses largest groups (class 0 =
+//                    all-zero rows + the reference's empty slot, always kept) become classes, every other codon is
+//                    copied, in order, to the front of the item's rows of perm.  Which codons end in which class does
+//                    not depend on the order in which threads reach the table.
+//   k_boot_split     one thread per (item, replicate): the C draws of a replicate fall into (general codons, class 0,
+//                    class 1, ...) multinomially; the counts are drawn as a chain of conditional binomials and the
+//                    classes' contribution to the replicate sums (count x the class's N_sites, S_sites) is added up.
+// k_bootstrap_mma<.., true> then makes only the draws on the general codons.
+// ---------------------------------------------------------------------------
+constexpr int kLogFactMax = 8192;                    // longest item of the class-aggregated form (table of log-factorials)
+constexpr int kClsSlots = 64;
+constexpr int kClsCtas = 8;                          // thread blocks (one cluster) per item
+constexpr int kClassifyThreads = 1024;               // one codon per thread: items of up to kClsCtas * 1024 codons
+constexpr unsigned long long kClsEmpty = ~0ull;
+static_assert(kClsCtas * kClassifyThreads >= kLogFactMax, "the classes are used for items of up to kLogFactMax codons");
+
+__device__ __forceinline__ uint32_t cls_hash(unsigned long long n_bits) {
+    return (((uint32_t)(n_bits >> 32) * 0x9E3779B1u) ^ ((uint32_t)n_bits * 0x85EBCA6Bu)) >> 26;
+}
+
+// One cluster of kClsCtas blocks per item (a single block spends 35 us on config 2's longest product: 4,406 codons
+// through four passes on one SM).  Block r holds the codons [1024 r, 1024 r + 1024), one per thread; the table of block 0
+// is the cluster's (distributed shared memory), the others add to it and copy it when it is final.
+__global__ void __cluster_dims__(kClsCtas, 1, 1) __launch_bounds__(kClassifyThreads)
+k_boot_classify(const __grid_constant__ BootArgs a)
+{
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ unsigned long long key_n[kClsSlots], key_s[kClsSlots];
+    __shared__ uint32_t cnt[kClsSlots];
+    __shared__ int rank_of[kClsSlots];
+    __shared__ uint32_t s_scan[kClassifyThreads / 32];
+    __shared__ uint32_t overflow, s_classes, cta_general[kClsCtas];
+    __shared__ unsigned long long loc_n[kClsSlots], loc_s[kClsSlots];     // this block's own keys, merged into block 0's table by 64 threads
+    __shared__ uint32_t loc_cnt[kClsSlots];
+    const uint32_t r = cluster.block_rank();
+    const int p = blockIdx.x / kClsCtas, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int64_t c0 = a.beg[p];
+    const uint32_t C = (uint32_t)(a.end[p] - c0);
+    const double2 *G = reinterpret_cast<const double2 *>(a.stats4 + 4 * c0);
+    double2 *O = reinterpret_cast<double2 *>(a.perm + 4 * c0);
+    unsigned long long *m_key_n = cluster.map_shared_rank(key_n, 0), *m_key_s = cluster.map_shared_rank(key_s, 0);
+    uint32_t *m_cnt = cluster.map_shared_rank(cnt, 0), *m_overflow = cluster.map_shared_rank(&overflow, 0);
+    uint32_t *m_general = cluster.map_shared_rank(cta_general, 0);
+    const uint32_t zero_slot = cls_hash(0ull);
+    if (t < kClsSlots) { key_n[t] = kClsEmpty; key_s[t] = kClsEmpty; cnt[t] = 0; rank_of[t] = -1; loc_n[t] = kClsEmpty; loc_s[t] = kClsEmpty; loc_cnt[t] = 0; }
+    if (t == 0) overflow = 0;
+    __syncthreads();
+    if (r == 0 && t == 0) { key_n[zero_slot] = 0ull; key_s[zero_slot] = 0ull; cnt[zero_slot] = (uint32_t)a.slot0; }
+    // this thread's codon
+    const uint32_t i = r * kClassifyThreads + t;
+    double2 x = make_double2(0.0, 0.0), d = make_double2(1.0, 1.0);
+    if (i < C) { x = G[2 * i]; d = G[2 * i + 1]; }
+    const unsigned long long nb = (unsigned long long)__double_as_longlong(x.x), sb = (unsigned long long)__double_as_longlong(x.y);
+    const bool cons = i < C && d.x == 0.0 && d.y == 0.0 && nb != kClsEmpty && sb != kClsEmpty;
+    cluster.sync();
+    // the table entry of a key in `keys`, or -1 (the table was full when the key came)
+    auto find = [&](const unsigned long long *keys, unsigned long long key) {
+        uint32_t h = cls_hash(key);
+        for (int probe = 0; probe < kClsSlots; probe++, h = (h + 1) & (kClsSlots - 1)) {
+            const unsigned long long k = keys[h];
+            if (k == key) return (int)h;
+            if (k == kClsEmpty) return -1;
+        }
+        return -1;
+    };
+    // A warp's lanes mostly hold a handful of distinct rows: one lane per distinct key goes to the table.
+    const unsigned grp = __match_any_sync(kFull, cons ? nb : kClsEmpty);
+    const unsigned grp_s = __match_any_sync(kFull, cons ? sb : kClsEmpty);
+    const bool first = cons && lane == __ffs(grp) - 1;
+    // passes 1 and 2 on the block's own table first (eight blocks of leaders on one block's shared memory serialise)
+    auto insert = [&](unsigned long long *keys, unsigned long long key) {
+        uint32_t h = cls_hash(key);
+        for (int probe = 0; probe < kClsSlots; probe++, h = (h + 1) & (kClsSlots - 1)) {
+            const unsigned long long old = atomicCAS(&keys[h], kClsEmpty, key);
+            if (old == kClsEmpty || old == key) return (int)h;
+        }
+        return -1;
+    };
+    int lh = -1;
+    if (first) {                                         // pass 1: the N_sites keys
+        lh = insert(loc_n, nb);
+        if (lh < 0) *m_overflow = 1;
+    }
+    __syncthreads();
+    if (cons && (first || (grp & ~grp_s) != 0)) {        // pass 2: per key the smallest S_sites pattern (a group that agrees: its first lane)
+        if (!first) lh = find(loc_n, nb);
+        if (lh >= 0) atomicMin(&loc_s[lh], sb);
+    }
+    __syncthreads();
+    if (t < kClsSlots && loc_n[t] != kClsEmpty) {        // the block's keys into the cluster's table
+        const int mh = insert(m_key_n, loc_n[t]);
+        if (mh < 0) *m_overflow = 1;
+        else atomicMin(&m_key_s[mh], loc_s[t]);
+    }
+    cluster.sync();
+    if (r != 0 && t < kClsSlots) { key_n[t] = m_key_n[t]; key_s[t] = m_key_s[t]; }
+    if (r != 0 && t == 0) overflow = *m_overflow;
+    __syncthreads();
+    int h = -1;                                          // pass 3: members, one atomic per entry and warp
+    if (cons) { h = find(key_n, nb); if (h >= 0 && key_s[h] != sb) h = -1; }
+    {
+        const unsigned same = __match_any_sync(kFull, h);
+        if (h >= 0 && lane == __ffs(same) - 1) atomicAdd(&loc_cnt[h], (uint32_t)__popc(same));
+    }
+    __syncthreads();
+    if (t < kClsSlots && loc_cnt[t]) atomicAdd(&m_cnt[t], loc_cnt[t]);
+    cluster.sync();
+    if (r != 0 && t < kClsSlots) cnt[t] = m_cnt[t];
+    __syncthreads();
+    // Classes in a canonical order: class 0, then by size, then by key.  A class pays for its binomial variate per
+    // replicate only when it takes a fair share of the draws: small groups (and all groups of a short item) are drawn one
+    // by one like the codons with differences.  (Every block ranks; block 0 writes the table.)
+    const uint32_t min_count = max(32u, C >> a.cls_shift);
+    if (t < kClsSlots) {
+        const bool present = t == (int)zero_slot || (cnt[t] >= min_count && !overflow);
+        int rank = 0;
+        if (present && t != (int)zero_slot) {
+            rank = 1;
+            for (int e = 0; e < kClsSlots; e++) {
+                if (e == t || e == (int)zero_slot || cnt[e] < min_count) continue;
+                const bool before = cnt[e] > cnt[t] || (cnt[e] == cnt[t] && (key_n[e] < key_n[t] || (key_n[e] == key_n[t] && key_s[e] < key_s[t])));
+                rank += before ? 1 : 0;
+            }
+        }
+        if (present && rank < kBootMaxClasses) {
+            rank_of[t] = rank;
+            if (r == 0) {
+                a.cls[p].count[rank] = cnt[t];
+                a.cls[p].vn[rank] = __longlong_as_double((long long)key_n[t]);
+                a.cls[p].vs[rank] = __longlong_as_double((long long)key_s[t]);
+            }
+        }
+        const unsigned present_mask = __ballot_sync(kFull, present);     // (the two warps of the 64 entries)
+        if (lane == 0) s_scan[warp] = __popc(present_mask);
+    }
+    __syncthreads();
+    if (t == 0) { s_classes = min((uint32_t)kBootMaxClasses, s_scan[0] + s_scan[1]); if (r == 0) a.cls[p].n_classes = s_classes; }
+    __syncthreads();
+    // pass 4: the codons outside the classes, in order, to the front of perm
+    const bool general = i < C && !(h >= 0 && rank_of[h] >= 0);
+    const unsigned bal = __ballot_sync(kFull, general);
+    if (lane == 0) s_scan[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t before, total;
+    {
+        const uint32_t v = s_scan[lane];                 // kClassifyThreads / 32 = 32 warps: one count per lane
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += n; }
+        before = __shfl_sync(kFull, inc - v, warp);
+        total = __shfl_sync(kFull, inc, 31);
+    }
+    if (t == 0) m_general[r] = total;
+    cluster.sync();
+    uint32_t ahead = 0, all = 0;
+    for (uint32_t q = 0; q < kClsCtas; q++) { const uint32_t v = m_general[q]; ahead += q < r ? v : 0u; all += v; }
+    if (general) {
+        const uint32_t pos = ahead + before + __popc(bal & ((1u << lane) - 1));
+        O[2 * pos] = x;
+        O[2 * pos + 1] = d;
+    }
+    // the chain's constants: node 0 = the general codons against all slots, node 1 + k = class k against the slots still open
+    if (r == 0 && t == 0) a.cls[p].n_general = all;
+    if (r == 0 && t <= (int)s_classes) {
+        uint32_t mass = C + (uint32_t)a.slot0, num = all;
+        if (t > 0) {
+            mass -= all;
+            for (int e = 0; e < kClsSlots; e++) {
+                const int rk = rank_of[e];
+                if (rk >= 0 && rk < t - 1) mass -= cnt[e];
+                if (rk == t - 1) num = cnt[e];
+            }
+        }
+        const bool flip = 2ull * num > mass;
+        const double pr = mass ? (double)(flip ? mass - num : num) / (double)mass : 0.0;
+        a.cls[p].node_p[t] = pr;
+        a.cls[p].node_flip[t] = flip ? 1u : 0u;
+        a.cls[p].node_lpq[t] = pr > 0.0 ? log(pr / (1.0 - pr)) : 0.0;
+        a.cls[p].node_l1q[t] = log1p(-pr);
+    }
+    cluster.sync();                                      // block 0's shared memory stays until every block has read it
+}
+
+// Uniform numbers of one replicate's class counts: Philox blocks whose quad index starts at kSplitQuad0, far above any
+// quad of draws (a replicate has fewer than 2^31 draws).
+constexpr uint32_t kSplitQuad0 = 0xC0000000u;
+struct SplitRng {
+    uint4 ctr; uint2 key; uint4 buf; int have;
+    __device__ uint32_t next() {
+        if (have == 0) { buf = philox4x32_10(ctr, key); ctr.x++; have = 4; }
+        const uint32_t r = have == 4 ? buf.x : have == 3 ? buf.y : have == 2 ? buf.z : buf.w;
+        have--;
+        return r;
+    }
+    __device__ double uniform() { return ((double)next() + 0.5) * 0x1p-32; }        // in (0, 1)
+};
+
+// log(k!) for k <= kLogFactMax, filled once per device (launch_bootstrap) with lgamma
+__device__ double g_logfact[kLogFactMax + 1];
+__global__ void k_fill_logfact() {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k <= kLogFactMax) g_logfact[k] = lgamma((double)k + 1.0);
+}
+
+// Binomial(n, p) variate for p <= 1/2 with lpq = log(p / (1 - p)), l1q = log(1 - p); n <= kLogFactMax.  Mean below 10:
+// inversion of the cumulative distribution, term by term from P(0) = (1 - p)^n.  Otherwise BTRS (Hoermann, "The generation
+// of binomial random variates", 1993): transformed rejection with a squeeze, about 1.15 pairs of uniforms per variate;
+// the exact test compares with the logarithm of the probability ratio f(k) / f(mode) from the table of log-factorials.
+// Both are exact up to the resolution of the uniforms and of double arithmetic.
+__device__ uint32_t binomial_variate(SplitRng &rng, uint32_t n, double p, double lpq, double l1q) {
+    if (n == 0 || p <= 0.0) return 0;
+    const double dn = (double)n;
+    uint32_t k;
+    if (dn * p < 10.0) {
+        const double s = exp(lpq), a = (dn + 1.0) * s, p0 = exp(dn * l1q);
+        double u = rng.uniform(), px = p0;
+        k = 0;
+        while (u > px) {
+            u -= px;
+            k++;
+            px *= a / (double)k - s;
+            if (k > n || px <= 0.0) { k = 0; px = p0; u = rng.uniform(); }     // rounding left u past the last term: again
+        }
+    } else {
+        const double q = 1.0 - p, sd = sqrt(dn * p * q), b = 1.15 + 2.53 * sd, a = -0.0873 + 0.0248 * b + 0.01 * p, c = dn * p + 0.5;
+        const double rb = 1.0 / b, v_r = 0.92 - 4.2 * rb, alpha = (2.83 + 5.1 * rb) * sd;
+        const uint32_t m = (uint32_t)((dn + 1.0) * p);
+        const double h = g_logfact[m] + g_logfact[n - m];
+        for (;;) {
+            const double u = rng.uniform() - 0.5;
+            const double v = rng.uniform();
+            const double us = 0.5 - fabs(u), kd = floor((2.0 * a / us + b) * u + c);
+            if (kd < 0.0 || kd > dn) continue;
+            k = (uint32_t)kd;
+            if (us >= 0.07 && v <= v_r) break;
+            if (log(v * alpha / (a / (us * us) + b)) <= h - g_logfact[k] - g_logfact[n - k] + (kd - (double)m) * lpq) break;
+        }
+    }
+    return k;
+}
+
+constexpr int kSplitThreads = 64;
+__global__ void __launch_bounds__(kSplitThreads)
+k_boot_split(const __grid_constant__ BootArgs a)
+{
+    __shared__ BootClasses s_cls;
+    const uint32_t call = a.call + (a.salt ? *a.salt : 0u);
+    const int p = blockIdx.y;
+    for (uint32_t i = threadIdx.x; i < sizeof(BootClasses) / 4; i += kSplitThreads)
+        reinterpret_cast<uint32_t *>(&s_cls)[i] = reinterpret_cast<const uint32_t *>(a.cls + p)[i];
+    __syncthreads();
+    const int64_t bl = (int64_t)blockIdx.x * kSplitThreads + threadIdx.x;
+    if (bl >= a.b_count) return;
+    const uint64_t b = (uint64_t)(a.b_first + bl);
+    const uint32_t C = (uint32_t)(a.end[p] - a.beg[p]);
+    SplitRng rng;
+    rng.ctr = boot_counter(kSplitQuad0, b, (uint32_t)p + a.item0, a.kind, call);
+    rng.key = a.key;
+    rng.have = 0;
+    auto node = [&](uint32_t n, int i) {
+        const uint32_t k = binomial_variate(rng, n, s_cls.node_p[i], s_cls.node_lpq[i], s_cls.node_l1q[i]);
+        return s_cls.node_flip[i] ? n - k : k;
+    };
+    uint32_t n = C;
+    const uint32_t m_general = node(n, 0);
+    n -= m_general;
+    double sn = 0.0, ss = 0.0;
+    const uint32_t Q = s_cls.n_classes;
+    for (uint32_t k = 0; k < Q; k++) {
+        const uint32_t hits = k + 1 == Q ? n : node(n, 1 + (int)k);
+        n -= hits;
+        sn += (double)hits * s_cls.vn[k];
+        ss += (double)hits * s_cls.vs[k];
+    }
+    const size_t at = (size_t)p * a.b_count + bl;
+    a.split_m[at] = m_general;
+    a.split_ns[at] = make_double2(sn, ss);
+}
+
 // K4, weight-matrix form (the default when a warp's counts fit in shared memory): the contraction
 // north_star describes.  The shared-memory pipe bounds the direct form above -- a 16-byte gather at 32 random
 // addresses costs ~11.5 wavefronts, and every draw pays one or two.  Here a draw only bumps a 1-byte counter
@@ -1191,7 +1477,9 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-template <uint32_t split>
+// CLS (SNPG_BOOT_CLASSES): the slots are the item's general codons (the first rows of perm, no empty slot), a replicate
+// makes split_m draws on them and the classes' share of its sums comes from split_ns.
+template <uint32_t split, bool CLS>
 __global__ void __launch_bounds__(kMmaWarps * 32, 5)
 k_bootstrap_mma(const __grid_constant__ BootArgs a, uint32_t row_words, uint32_t nb)
 {
@@ -1206,9 +1494,8 @@ k_bootstrap_mma(const __grid_constant__ BootArgs a, uint32_t row_words, uint32_t
     const int p = a.order ? a.order[blockIdx.y] : blockIdx.y;
     const int64_t c0 = a.beg[p];
     const uint32_t C = (uint32_t)(a.end[p] - c0);
-    const uint32_t s0 = (uint32_t)a.slot0, n_slots = C + s0;
-    const double *G = a.stats4 + 4 * c0;
-    const uint32_t nquad = (C + 3) >> 2, full_quads = C >> 2;     // the partial quad, if any, is quad full_quads
+    const uint32_t s0 = CLS ? 0u : (uint32_t)a.slot0, n_slots = CLS ? a.cls[p].n_general : C + s0;
+    const double *G = (CLS ? a.perm : a.stats4) + 4 * c0;
     const uint32_t nslot4 = (n_slots + 3) >> 2;    // groups of 4 slots
     // A short product does not fill a warp's counters: its warps then take m = 2, 4 or 8 replicates at a time (32 / m
     // lanes and one row of rw words each), so that the fixed cost of a batch is spread over 32 m replicates.
@@ -1244,6 +1531,8 @@ k_bootstrap_mma(const __grid_constant__ BootArgs a, uint32_t row_words, uint32_t
         const int64_t bl = batch_first + my_row;
         if (bl < a.b_count) {
             const uint64_t b = (uint64_t)(a.b_first + bl);
+            const uint32_t n_draws = CLS ? a.split_m[(size_t)p * a.b_count + bl] : C;
+            const uint32_t nquad = (n_draws + 3) >> 2, full_quads = n_draws >> 2;     // the partial quad, if any, is quad full_quads
             auto bump = [&](uint32_t u) {          // one draw: slot = floor(u * n_slots / 2^32); its byte of the row goes up by one
                 const uint32_t r = __umulhi(u, n_slots);
                 // 1 << 8 * (r & 3): a funnel shift takes its count modulo 32, so r << 3 needs no mask
@@ -1256,7 +1545,7 @@ k_bootstrap_mma(const __grid_constant__ BootArgs a, uint32_t row_words, uint32_t
             }
             if (q < nquad) {                       // the last, partial quad (one lane)
                 const uint4 u = philox4x32_10(boot_counter(q, b, (uint32_t)p + a.item0, a.kind, call), a.key);
-                const uint32_t nd = C & 3;
+                const uint32_t nd = n_draws & 3;
                 bump(u.x);
                 if (nd > 1) bump(u.y);
                 if (nd > 2) bump(u.z);
@@ -1304,6 +1593,8 @@ k_bootstrap_mma(const __grid_constant__ BootArgs a, uint32_t row_words, uint32_t
             const uint32_t r = threadIdx.x >> 2, q = threadIdx.x & 3, ksplit = kBootKSplit >> lm;
             double v = 0.0;
             for (uint32_t ks = 0; ks < ksplit; ks++) v += part[(((ks << lrows) + r) << 2) + q];
+            if (CLS && q < 2 && batch_first + r < a.b_count)      // the classes' share of N_sites, S_sites
+                v += reinterpret_cast<const double *>(a.split_ns + (size_t)p * a.b_count + batch_first + r)[q];
             reinterpret_cast<double *>(&s_sums[r][0])[q] = v;
         }
         __syncthreads();
@@ -1331,7 +1622,7 @@ k_bootstrap_mma(const __grid_constant__ BootArgs a, uint32_t row_words, uint32_t
         static_assert(kV >= 1 && (kV & (kV - 1)) == 0 && kV * kMmaWarps * 32 == kSumThreads, "block size must divide kSumThreads");
         __syncthreads();
         double *red = &s_part[0][0][0];            // kBootKSplit * kMmaWarps * 4 = kMmaWarps * 32 doubles: one per thread
-        const double2 *G2 = reinterpret_cast<const double2 *>(G);
+        const double2 *G2 = reinterpret_cast<const double2 *>(a.stats4 + 4 * c0);
         double s[kV][4];
         for (int v = 0; v < kV; v++) {
             for (int q = 0; q < 4; q++) s[v][q] = 0.0;
@@ -1732,7 +2023,8 @@ void launch_bootstrap(int form, BootArgs a, int64_t max_codons, cudaStream_t str
     // tensor-core tile reads share a bank)
     // (at least 16 KB a block even for a short table, so that short products can take several replicates per warp)
     const size_t row_words = std::max<size_t>((((size_t)max_codons + 1 + 3) / 4) | 1, 127);
-    if (form == SNPG_BOOT_WEIGHTS && row_words * 4 * 32 <= (size_t)kBootSmemLimit) {
+    const bool classes = form == SNPG_BOOT_CLASSES && a.perm && a.cls && a.split_m && a.split_ns && max_codons <= kLogFactMax;
+    if ((form == SNPG_BOOT_WEIGHTS || form == SNPG_BOOT_CLASSES) && row_words * 4 * 32 <= (size_t)kBootSmemLimit) {
         // five blocks of kMmaWarps warps per SM; the grid is sized for one replicate per warp.  A block takes two batches
         // of replicates when that still leaves every SM a few blocks per slot (measured on config 2: one batch 157 us, two
         // 147, four 168); with few replicates (a rank of several GPUs) one batch, then two warps per replicate.
@@ -1749,7 +2041,22 @@ void launch_bootstrap(int form, BootArgs a, int64_t max_codons, cudaStream_t str
         if (env_split == 0 || env_split == 1) split = env_split;
         const int64_t per_mma = (int64_t)(kMmaWarps >> split) * nb;
         dim3 grid_mma((unsigned)((a.b_count + per_mma - 1) / per_mma), (unsigned)a.n_items);
-        auto kernel = split ? k_bootstrap_mma<1> : k_bootstrap_mma<0>;
+        if (classes) {
+            static bool filled[64] = {};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (dev >= 0 && dev < 64 && !filled[dev]) {          // log-factorials, once per device (outside any capture: the first job is not captured)
+                k_fill_logfact<<<(kLogFactMax + 256) / 256, 256, 0, stream>>>();
+                cudaStreamSynchronize(stream);                   // other streams of this device may follow at once
+                filled[dev] = true;
+            }
+            static const int env_shift = [] { const char *v = getenv("SNPG_BOOT_CLASS_SHIFT"); return v ? std::max(1, std::min(12, atoi(v))) : 0; }();
+            if (env_shift) a.cls_shift = env_shift;
+            launch_peer_wait(a.ps, kStageStats, stream);         // the classes come from every rank's statistics
+            k_boot_classify<<<(unsigned)a.n_items * kClsCtas, kClassifyThreads, 0, stream>>>(a);
+            k_boot_split<<<dim3((unsigned)((a.b_count + kSplitThreads - 1) / kSplitThreads), (unsigned)a.n_items), kSplitThreads, 0, stream>>>(a);
+        }
+        auto kernel = classes ? (split ? k_bootstrap_mma<1, true> : k_bootstrap_mma<0, true>) : (split ? k_bootstrap_mma<1, false> : k_bootstrap_mma<0, false>);
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBootSmemLimit * kMmaWarps / 32);  // per device
         kernel<<<grid_mma, kMmaWarps * 32, row_words * 4 * kMmaWarps, stream>>>(a, (uint32_t)row_words, (uint32_t)nb);
     } else if (smem <= (size_t)kBootSmemLimit) {
@@ -1762,6 +2069,23 @@ void launch_bootstrap(int form, BootArgs a, int64_t max_codons, cudaStream_t str
         k_bootstrap<false><<<grid, kBootWarps * 32, 0, stream>>>(a);
         if (sums) launch_product_sums(a.stats4, a.beg, a.n_items, sums, stream);
     }
+}
+
+size_t boot_scratch_bytes(int64_t total, int n_items, int64_t b_count)
+{
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    return up(sizeof(double) * 4 * (size_t)std::max<int64_t>(1, total)) + up(sizeof(BootClasses) * (size_t)std::max(1, n_items)) +
+           up(sizeof(uint32_t) * (size_t)n_items * (size_t)b_count) + up(sizeof(double2) * (size_t)n_items * (size_t)b_count);
+}
+
+void boot_scratch_carve(void *scratch, int64_t total, int n_items, int64_t b_count, BootArgs &a)
+{
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    uint8_t *p = static_cast<uint8_t *>(scratch);
+    a.perm = reinterpret_cast<double *>(p); p += up(sizeof(double) * 4 * (size_t)std::max<int64_t>(1, total));
+    a.cls = reinterpret_cast<BootClasses *>(p); p += up(sizeof(BootClasses) * (size_t)std::max(1, n_items));
+    a.split_m = reinterpret_cast<uint32_t *>(p); p += up(sizeof(uint32_t) * (size_t)n_items * (size_t)b_count);
+    a.split_ns = reinterpret_cast<double2 *>(p);
 }
 
 void launch_philox_kat(const uint32_t *ctr, const uint32_t *key, uint32_t *d_out, cudaStream_t stream)

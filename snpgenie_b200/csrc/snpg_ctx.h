@@ -96,7 +96,7 @@ struct snpg_ctx {
     snpg::DevBuf d_tiles, d_sched;              // d_sched: the histogram kernels' chunk counter and finished-CTA counter
     int64_t n_tiles = 0;
     int fused_kernel = SNPG_FUSED_LDG_SPANS;
-    int boot_kernel = SNPG_BOOT_WEIGHTS;
+    int boot_kernel = SNPG_BOOT_CLASSES;
     int boot_slot0 = 1;                   // SNPG_OPT_BOOT_SLOTS: 1 = the reference's C+1 slots (wg:885), 0 = C slots
     const snpg::Group *stats_of = nullptr;      // the group whose per-codon statistics sit in the job's stats buffers (written by its load)
     int n_sms = 148;
@@ -109,6 +109,7 @@ struct snpg_ctx {
     // scratch
     snpg::DevBuf s_vals, d_order_local, d_order_full;
     int64_t max_codons_local = 0, max_codons_full = 0;
+    snpg::DevBuf s_boot;              // SNPG_BOOT_CLASSES scratch (boot_scratch_bytes)
     snpg::DevBuf staging[2], s_stats, s_poly, s_nda, s_ndb, s_cmp, s_cons, s_sums, s_rep, s_se, s_undef, s_misc, s_in;
     // sliding windows of a whole job: items over the (global) codon axis, cached per (W, step)
     struct WindowPlan { int64_t W = 0, step = 0, n = 0; std::vector<int64_t> ofs; snpg::DevBuf beg, end; } wplan;
@@ -192,6 +193,9 @@ struct Launch {
     }
 };
 
+// SNPG_BOOT_CLASSES: the scratch of a bootstrap over items inside stats4[0, total) (call before the Launch scope; a no-op
+// for the other kernels).  Grows ctx->s_boot when needed, so whole jobs size it in job_prepare.
+int boot_classes_scratch(snpg_ctx *ctx, BootArgs &a, int64_t total);
 void resolve_spans(snpg_ctx *ctx);           // after a stream synchronise: recorded spans -> accumulated milliseconds
 void invalidate_job_graph(snpg_ctx *ctx);    // a captured job graph holds pointers, options and event pairs: anything that changes them drops it
 cudaError_t sync_stream(snpg_ctx *ctx);

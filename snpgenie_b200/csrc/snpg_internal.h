@@ -169,6 +169,23 @@ void launch_product_sums(const double *d_stats4, const int64_t *d_prod_ofs, int 
 // *salt): kind separates the callers' streams, salt (or null) is a device word a replayed CUDA graph refreshes.
 // pv/ps (world > 1): the values go into every rank's exchange region instead of vals, the kernel waits for stage
 // kStageStats before it reads stats4 and signals kStageVals when it is done.
+// SNPG_BOOT_CLASSES: the codons of an item whose row of the table is (N_sites, S_sites, 0, 0) with the same two numbers,
+// bit for bit, form a class (every conserved codon of the same amino-acid degeneracy; the reference's empty slot 0 and
+// all-zero rows are class 0).  A replicate's draws are multinomial over the slots, so the number that land in a class
+// is all its sum needs from them: k_boot_split draws (general draws, class 0, class 1, ...) by a chain of exact
+// binomials and only the draws on the n_general other codons are made one by one.
+constexpr int kBootMaxClasses = 16;
+struct BootClasses {
+    uint32_t n_general, n_classes;            // codons drawn one by one (first in the item's rows of perm); classes in use
+    uint32_t count[kBootMaxClasses];          // slots of each class
+    double vn[kBootMaxClasses], vs[kBootMaxClasses];     // its N_sites, S_sites
+    // the chain of binomials, node 0 = the general codons, node 1 + k = class k (the last class takes what is left):
+    // success probability given the slots still open, folded to <= 1/2 (flip: count the failures), with log(p / (1 - p))
+    // and log(1 - p)
+    double node_p[kBootMaxClasses + 1], node_lpq[kBootMaxClasses + 1], node_l1q[kBootMaxClasses + 1];
+    uint32_t node_flip[kBootMaxClasses + 1];
+    uint32_t pad;
+};
 struct BootArgs {
     const double *stats4 = nullptr; const int64_t *beg = nullptr, *end = nullptr; const int *order = nullptr;
     int n_items = 0, slot0 = 1;
@@ -177,9 +194,16 @@ struct BootArgs {
     uint2 key = {0, 0}; uint32_t kind = 0, call = 0; const uint32_t *salt = nullptr;
     double *rep = nullptr, *vals = nullptr, *prod_sums = nullptr;
     PeerVals pv; PeerSync ps;
+    // SNPG_BOOT_CLASSES (items that do not overlap): scratch of boot_scratch_bytes(), carved by boot_scratch_carve()
+    double *perm = nullptr; BootClasses *cls = nullptr; uint32_t *split_m = nullptr; double2 *split_ns = nullptr;
+    int cls_shift = 6;             // a group of conserved codons becomes a class from max(32, C >> cls_shift) members on
 };
+// Scratch of the class-aggregated bootstrap for items inside stats4[0, total) and b_count replicates of each.
+size_t boot_scratch_bytes(int64_t total, int n_items, int64_t b_count);
+void boot_scratch_carve(void *scratch, int64_t total, int n_items, int64_t b_count, BootArgs &a);
 enum BootKind : uint32_t { kBootProduct = 1, kBootWindow = 2, kBootAllDevice = 3, kBootJob = 4, kBootBetween = 5, kBootJobWindow = 6, kBootRWindow = 7 };
-// form: SNPG_BOOT_WEIGHTS (slot counters + tensor-core contraction) or SNPG_BOOT_GATHER (per-draw row gathers);
+// form: SNPG_BOOT_CLASSES (class counts by binomials, the other draws as WEIGHTS; needs a.perm etc., else WEIGHTS),
+// SNPG_BOOT_WEIGHTS (slot counters + tensor-core contraction) or SNPG_BOOT_GATHER (per-draw row gathers);
 // max_codons = the longest item (sizes the shared-memory table; beyond the limit: gathers from global memory).
 void launch_bootstrap(int form, BootArgs a, int64_t max_codons, cudaStream_t stream);
 // one Philox4x32-10 block on the device (known-answer test hook)

@@ -36,7 +36,7 @@ def test_python_constants_follow_the_header():
              "SNPG_OPT_FUSED_KERNEL": _abi.OPT_FUSED_KERNEL, "SNPG_OPT_BOOTSTRAP_KERNEL": _abi.OPT_BOOTSTRAP_KERNEL,
              "SNPG_FUSED_TMA_TILES": _abi.FUSED_TMA_TILES, "SNPG_FUSED_LDG_SPANS": _abi.FUSED_LDG_SPANS,
              "SNPG_FUSED_TMA_SPANS": _abi.FUSED_TMA_SPANS,
-             "SNPG_BOOT_GATHER": _abi.BOOT_GATHER, "SNPG_BOOT_WEIGHTS": _abi.BOOT_WEIGHTS, "SNPG_OPT_BOOT_SLOTS": _abi.OPT_BOOT_SLOTS,
+             "SNPG_BOOT_GATHER": _abi.BOOT_GATHER, "SNPG_BOOT_WEIGHTS": _abi.BOOT_WEIGHTS, "SNPG_BOOT_CLASSES": _abi.BOOT_CLASSES, "SNPG_OPT_BOOT_SLOTS": _abi.OPT_BOOT_SLOTS,
              "SNPG_OPT_INGEST_ASYNC": _abi.OPT_INGEST_ASYNC, "SNPG_OPT_FIRST_DEFINED": _abi.OPT_FIRST_DEFINED, "SNPG_RWIN_COLS": _abi.RWIN_COLS}
     for name, value in pairs.items():
         assert defs[name] == value, name

@@ -32,6 +32,18 @@ def eng():
     e.close()
 
 
+@pytest.fixture(scope="module", params=["classes", "weights"])
+def eng_boot(request):
+    """The statistical bootstrap tests run on the class-aggregated kernel (the default: class counts by exact binomials, the
+    other draws one by one) and on the weight-matrix kernel (every draw one by one)."""
+    from snpgenie_b200 import _abi
+    from snpgenie_b200.engine import Engine
+    e = Engine(device=0, seed=1234)
+    e.set_option(_abi.OPT_BOOTSTRAP_KERNEL, _abi.BOOT_CLASSES if request.param == "classes" else _abi.BOOT_WEIGHTS)
+    yield e
+    e.close()
+
+
 @pytest.fixture(scope="module", params=["codes", "fused", "tiles", "spans"])
 def eng2(request):
     """All histogram routes: K1 pack + K2 hist over the kept code matrix, the fused vector-load span kernel (the default),
@@ -296,7 +308,8 @@ def _stats_from_golden(case="w_gaps", product="geneB"):
     return refio.stats4_of(refio.codon_arrays(codon_rows, p.name, p.n_codons)), prod_rows[p.name]
 
 
-def test_bootstrap_product_statistics(eng):
+def test_bootstrap_product_statistics(eng_boot):
+    eng = eng_boot
     stats4, pr = _stats_from_golden()
     C, B = stats4.shape[0], 40000
     sums, se = eng.bootstrap_product(stats4, B, want_sums=True)
@@ -322,9 +335,12 @@ def test_bootstrap_product_statistics(eng):
 
 
 @pytest.mark.parametrize("C", [1, 5, 6, 7, 8, 13, 64, 203, 1000])
-def test_bootstrap_draws_are_uniform_over_slots(eng, C):
+def test_bootstrap_draws_are_uniform_over_slots(eng_boot, C):
     """Every one of the C+1 slots (slot 0 = the reference's empty codon, wg:885) is drawn with probability
-    1/(C+1), jointly multinomial: the replicate sum of an indicator row counts the draws of that slot."""
+    1/(C+1), jointly multinomial: the replicate sum of an indicator row counts the draws of that slot.  (For the
+    class-aggregated kernel an indicator row is a class of one codon and the zero rows are class 0: the test then checks
+    the binomial chain.)"""
+    eng = eng_boot
     B = 40000
     p = 1.0 / (C + 1)
     mean, var = C * p, C * p * (1 - p)
@@ -380,7 +396,61 @@ def test_bootstrap_kernels_agree(C):
     assert out[0][0][:, 0].max() > 0 or C < 3
 
 
-def test_bootstrap_keep_mask(eng):
+@pytest.mark.parametrize("C,frac_general", [(40, 0.3), (420, 0.3), (1274, 0.05), (4406, 0.3), (6300, 0.3), (6300, 0.0), (300, 1.0)])
+def test_bootstrap_classes_match_draw_by_draw_distribution(C, frac_general):
+    """SNPG_BOOT_CLASSES against SNPG_BOOT_WEIGHTS on tables shaped like a product's (conserved codons in a few classes
+    of identical (N_sites, S_sites), the rest with differences): different uses of the Philox stream, the same
+    distribution -- means of the replicate sums within 5 standard errors, variances within 8 %, SEs within 5 %.  Class
+    sums are whole multiples when there is one class, the result does not depend on anything but (seed, call), and more
+    than kBootMaxClasses distinct conserved rows are handled (the smallest groups are drawn one by one)."""
+    from snpgenie_b200 import _abi
+    from snpgenie_b200.engine import Engine
+    rng = np.random.default_rng(C + int(100 * frac_general))
+    sites, _ = orc.tables()
+    sites = np.asarray(sites)
+    stats4 = np.zeros((C, 4))
+    general = rng.random(C) < frac_general
+    stats4[:, :2] = np.where(general[:, None], rng.random((C, 2)) * 3, sites[rng.integers(0, 64, size=C)])
+    stats4[:, 2:] = np.where(general[:, None], rng.random((C, 2)), 0.0)
+    if C == 420:                                # 40 distinct conserved rows: more than the classes a product may have
+        odd = np.flatnonzero(~general)[:40]
+        stats4[odd, 0] = 2.0 + np.arange(len(odd)) / 64.0
+        stats4[odd, 1] = 1.0 - np.arange(len(odd)) / 64.0
+    B = 20000
+    res = {}
+    for kernel in (_abi.BOOT_CLASSES, _abi.BOOT_WEIGHTS, _abi.BOOT_CLASSES):
+        with Engine(device=0, seed=4242) as e:
+            e.set_option(_abi.OPT_BOOTSTRAP_KERNEL, kernel)
+            res.setdefault(kernel, []).append(e.bootstrap_product(stats4, B, want_sums=True))
+    (s_c, se_c), (s_c2, se_c2) = res[_abi.BOOT_CLASSES]
+    s_w, se_w = res[_abi.BOOT_WEIGHTS][0]
+    assert np.array_equal(s_c, s_c2) and np.array_equal(se_c, se_c2)          # deterministic
+    assert not np.array_equal(s_c, s_w)
+    for q in range(4):
+        sd = s_w[:, q].std(ddof=1)
+        if sd == 0:
+            assert s_c[:, q].std() == 0 and np.allclose(s_c[:, q], s_w[:, q])
+            continue
+        assert abs(s_c[:, q].mean() - s_w[:, q].mean()) < 5 * sd * np.sqrt(2 / B), (C, q)
+        assert abs(s_c[:, q].var(ddof=1) / s_w[:, q].var(ddof=1) - 1) < 0.08, (C, q)
+    ok = np.isfinite(se_w) & (se_w > 0)
+    assert np.all(np.abs(se_c[ok] / se_w[ok] - 1) < 0.05), (se_c, se_w)
+    # N_sites + S_sites of a replicate: the cross term between general draws and class counts is right when the total
+    # behaves as for draw-by-draw sampling
+    t_c, t_w = s_c[:, 0] + s_c[:, 1], s_w[:, 0] + s_w[:, 1]
+    assert abs(t_c.var(ddof=1) / t_w.var(ddof=1) - 1) < 0.08
+    # one class only: every replicate sum is a whole multiple of the class's row
+    one = np.tile(np.array([[2.5, 0.5, 0.0, 0.0]]), (C, 1))
+    with Engine(device=0, seed=1) as e:
+        s1, _ = e.bootstrap_product(one, 4000, want_sums=True)
+    k = s1[:, 0] / 2.5
+    assert np.all(k == np.round(k)) and np.all(s1[:, 1] == k * 0.5) and k.max() <= C and np.all(s1[:, 2:] == 0)
+    p0 = 1.0 / (C + 1)
+    assert abs((C - k).mean() - C * p0) < 5 * np.sqrt(C * p0 * (1 - p0) / 4000)      # draws of the empty slot
+
+
+def test_bootstrap_keep_mask(eng_boot):
+    eng = eng_boot
     stats4, _ = _stats_from_golden()
     keep = (np.arange(stats4.shape[0]) % 3 != 0).astype(np.uint8)
     sums, se = eng.bootstrap_product(stats4, 5000, keep=keep, want_sums=True)
