@@ -432,12 +432,14 @@ def bootstrap_block(eng, kern, products, world):
     flops = 2.0 * 4 * N_BOOT * sum(p.n_codons for p in products) / world             # algorithmic: B x C x 4 multiply-adds
     boot_ms = sum(kern[k]["ms_per_step"] for k in ("bootstrap", "moments") if k in kern)
     blk = {"value": N_BOOT * len(products) / (boot_ms * 1e-3), "unit": "bootstrap reps/s",
-           "note": "B x products per step / (bootstrap + moments kernel time), whole job",
+           "note": "B x products per step / (bootstrap + moments kernel time), whole job; draws are NOMINAL (C per replicate): the default "
+                   "class-aggregated kernel gets the draws on conserved codons of one class from binomial variates and makes only the "
+                   "others one by one, so it may pass the one-Philox-number-per-draw ceiling below",
            "kernel_ms": ms, "draws_per_launch": draws, "gdraws_per_s": draws / (ms * 1e-3) / 1e9,
            "algorithmic_dmma_tflops": flops / (ms * 1e-3) / 1e12}
     try:
         pk = eng.probe_peaks()
-        blk["roofline"] = {"bound": "issue (Philox4x32-10 generation: 20 IMAD.WIDE + 20 LOP3 per 4 draws)", "achieved": draws / (ms * 1e-3) / 1e9,
+        blk["roofline"] = {"bound": "issue (Philox4x32-10 generation, one number per nominal draw: 20 IMAD.WIDE + 20 LOP3 per 4 draws)", "achieved": draws / (ms * 1e-3) / 1e9,
                            "peak": pk["philox_gdraws_per_s"], "unit": "Gdraws/s", "frac": draws / (ms * 1e-3) / 1e9 / pk["philox_gdraws_per_s"],
                            "issue_floor_us": draws / pk["philox_gdraws_per_s"] / 1e9 * 1e6,
                            "peak_source": "measured here: a kernel that only generates Philox4x32-10 blocks (snpg_probe_peaks)"}

@@ -1191,42 +1191,40 @@ __device__ __forceinline__ uint32_t cls_hash(unsigned long long n_bits) {
 }
 
 // One cluster of kClsCtas blocks per item (a single block spends 35 us on config 2's longest product: 4,406 codons
-// through four passes on one SM).  Block r holds the codons [1024 r, 1024 r + 1024), one per thread; the table of block 0
-// is the cluster's (distributed shared memory), the others add to it and copy it when it is final.
+// through four passes on one SM).  Block r holds the codons [1024 r, 1024 r + 1024), one per thread, and builds a table of
+// its own keys; after one cluster barrier every block reads all eight tables through distributed shared memory and
+// merges them into its own copy of the item's table, after a second one it adds up the eight blocks' member counts.
+// (Cluster barriers cost about 2.5 us each here: a first version with one shared table and five barriers took 17 us.)
 __global__ void __cluster_dims__(kClsCtas, 1, 1) __launch_bounds__(kClassifyThreads)
 k_boot_classify(const __grid_constant__ BootArgs a)
 {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
-    __shared__ unsigned long long key_n[kClsSlots], key_s[kClsSlots];
-    __shared__ uint32_t cnt[kClsSlots];
+    __shared__ unsigned long long loc_n[kClsSlots], loc_s[kClsSlots];     // this block's keys (read by its peers)
+    __shared__ unsigned long long key_n[kClsSlots], key_s[kClsSlots];     // the item's keys (every block its own copy)
+    __shared__ uint32_t my_cnt[kClsSlots], cnt[kClsSlots];                // members among this block's codons (read by its peers) / in the item
     __shared__ int rank_of[kClsSlots];
     __shared__ uint32_t s_scan[kClassifyThreads / 32];
-    __shared__ uint32_t overflow, s_classes, cta_general[kClsCtas];
-    __shared__ unsigned long long loc_n[kClsSlots], loc_s[kClsSlots];     // this block's own keys, merged into block 0's table by 64 threads
-    __shared__ uint32_t loc_cnt[kClsSlots];
+    __shared__ uint32_t overflow, s_classes, members[kClsCtas];
     const uint32_t r = cluster.block_rank();
     const int p = blockIdx.x / kClsCtas, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int64_t c0 = a.beg[p];
     const uint32_t C = (uint32_t)(a.end[p] - c0);
     const double2 *G = reinterpret_cast<const double2 *>(a.stats4 + 4 * c0);
     double2 *O = reinterpret_cast<double2 *>(a.perm + 4 * c0);
-    unsigned long long *m_key_n = cluster.map_shared_rank(key_n, 0), *m_key_s = cluster.map_shared_rank(key_s, 0);
-    uint32_t *m_cnt = cluster.map_shared_rank(cnt, 0), *m_overflow = cluster.map_shared_rank(&overflow, 0);
-    uint32_t *m_general = cluster.map_shared_rank(cta_general, 0);
     const uint32_t zero_slot = cls_hash(0ull);
-    if (t < kClsSlots) { key_n[t] = kClsEmpty; key_s[t] = kClsEmpty; cnt[t] = 0; rank_of[t] = -1; loc_n[t] = kClsEmpty; loc_s[t] = kClsEmpty; loc_cnt[t] = 0; }
+    if (t < kClsSlots) { loc_n[t] = kClsEmpty; loc_s[t] = kClsEmpty; key_n[t] = kClsEmpty; key_s[t] = kClsEmpty; my_cnt[t] = 0; cnt[t] = 0; rank_of[t] = -1; }
+    if (t < kClsCtas) members[t] = 0;
     if (t == 0) overflow = 0;
     __syncthreads();
-    if (r == 0 && t == 0) { key_n[zero_slot] = 0ull; key_s[zero_slot] = 0ull; cnt[zero_slot] = (uint32_t)a.slot0; }
+    if (t == 0) { key_n[zero_slot] = 0ull; key_s[zero_slot] = 0ull; }    // class 0 exists in every item: zero rows + the empty slot
     // this thread's codon
     const uint32_t i = r * kClassifyThreads + t;
     double2 x = make_double2(0.0, 0.0), d = make_double2(1.0, 1.0);
     if (i < C) { x = G[2 * i]; d = G[2 * i + 1]; }
     const unsigned long long nb = (unsigned long long)__double_as_longlong(x.x), sb = (unsigned long long)__double_as_longlong(x.y);
     const bool cons = i < C && d.x == 0.0 && d.y == 0.0 && nb != kClsEmpty && sb != kClsEmpty;
-    cluster.sync();
-    // the table entry of a key in `keys`, or -1 (the table was full when the key came)
+    // the table entry of a key in `keys`, or -1
     auto find = [&](const unsigned long long *keys, unsigned long long key) {
         uint32_t h = cls_hash(key);
         for (int probe = 0; probe < kClsSlots; probe++, h = (h + 1) & (kClsSlots - 1)) {
@@ -1236,12 +1234,7 @@ k_boot_classify(const __grid_constant__ BootArgs a)
         }
         return -1;
     };
-    // A warp's lanes mostly hold a handful of distinct rows: one lane per distinct key goes to the table.
-    const unsigned grp = __match_any_sync(kFull, cons ? nb : kClsEmpty);
-    const unsigned grp_s = __match_any_sync(kFull, cons ? sb : kClsEmpty);
-    const bool first = cons && lane == __ffs(grp) - 1;
-    // passes 1 and 2 on the block's own table first (eight blocks of leaders on one block's shared memory serialise)
-    auto insert = [&](unsigned long long *keys, unsigned long long key) {
+    auto insert = [&](unsigned long long *keys, unsigned long long key) {       // -1: the table is full
         uint32_t h = cls_hash(key);
         for (int probe = 0; probe < kClsSlots; probe++, h = (h + 1) & (kClsSlots - 1)) {
             const unsigned long long old = atomicCAS(&keys[h], kClsEmpty, key);
@@ -1249,36 +1242,52 @@ k_boot_classify(const __grid_constant__ BootArgs a)
         }
         return -1;
     };
+    // A warp's lanes mostly hold a handful of distinct rows: one lane per distinct key goes to the table.
+    const unsigned grp = __match_any_sync(kFull, cons ? nb : kClsEmpty);
+    const unsigned grp_s = __match_any_sync(kFull, cons ? sb : kClsEmpty);
+    const bool first = cons && lane == __ffs(grp) - 1;
     int lh = -1;
-    if (first) {                                         // pass 1: the N_sites keys
+    if (first) {                                         // pass 1: the N_sites keys of this block
         lh = insert(loc_n, nb);
-        if (lh < 0) *m_overflow = 1;
+        if (lh < 0) overflow = 1;
     }
     __syncthreads();
     if (cons && (first || (grp & ~grp_s) != 0)) {        // pass 2: per key the smallest S_sites pattern (a group that agrees: its first lane)
         if (!first) lh = find(loc_n, nb);
         if (lh >= 0) atomicMin(&loc_s[lh], sb);
     }
-    __syncthreads();
-    if (t < kClsSlots && loc_n[t] != kClsEmpty) {        // the block's keys into the cluster's table
-        const int mh = insert(m_key_n, loc_n[t]);
-        if (mh < 0) *m_overflow = 1;
-        else atomicMin(&m_key_s[mh], loc_s[t]);
+    cluster.sync();                                      // ---- every block's keys are in place
+    unsigned long long peer_key = kClsEmpty;             // the table entry of a peer this thread merges: kept for the counts below
+    uint32_t peer = 0, peer_slot = 0;
+    if (t < kClsCtas * kClsSlots) {
+        peer = t / kClsSlots; peer_slot = t % kClsSlots;
+        peer_key = cluster.map_shared_rank(loc_n, peer)[peer_slot];
+        if (peer_key != kClsEmpty) {
+            const int h = insert(key_n, peer_key);
+            if (h < 0) overflow = 1;
+            else atomicMin(&key_s[h], cluster.map_shared_rank(loc_s, peer)[peer_slot]);
+        }
+        if (cluster.map_shared_rank(&overflow, peer)[0]) overflow = 1;
     }
-    cluster.sync();
-    if (r != 0 && t < kClsSlots) { key_n[t] = m_key_n[t]; key_s[t] = m_key_s[t]; }
-    if (r != 0 && t == 0) overflow = *m_overflow;
     __syncthreads();
-    int h = -1;                                          // pass 3: members, one atomic per entry and warp
+    int h = -1;                                          // pass 3: this block's members, one atomic per entry and warp
     if (cons) { h = find(key_n, nb); if (h >= 0 && key_s[h] != sb) h = -1; }
     {
         const unsigned same = __match_any_sync(kFull, h);
-        if (h >= 0 && lane == __ffs(same) - 1) atomicAdd(&loc_cnt[h], (uint32_t)__popc(same));
+        if (h >= 0 && lane == __ffs(same) - 1) atomicAdd(&my_cnt[h], (uint32_t)__popc(same));
     }
-    __syncthreads();
-    if (t < kClsSlots && loc_cnt[t]) atomicAdd(&m_cnt[t], loc_cnt[t]);
-    cluster.sync();
-    if (r != 0 && t < kClsSlots) cnt[t] = m_cnt[t];
+    if (r == 0 && t == 0) atomicAdd(&my_cnt[zero_slot], (uint32_t)a.slot0);
+    cluster.sync();                                      // ---- every block's member counts are in place
+    // The item's counts: every block adds up all eight.  A peer's entries sit at the peer's own table positions, so they
+    // are matched by key.
+    uint32_t peer_cnt = 0;
+    int peer_h = -1;
+    if (t < kClsCtas * kClsSlots) {
+        const unsigned long long k = cluster.map_shared_rank(key_n, peer)[peer_slot];
+        peer_cnt = k != kClsEmpty ? cluster.map_shared_rank(my_cnt, peer)[peer_slot] : 0u;
+        if (peer_cnt) { peer_h = find(key_n, k); if (peer_h >= 0) atomicAdd(&cnt[peer_h], peer_cnt); }
+    }
+    cluster.barrier_arrive();                            // (the last access to the peers' shared memory; waited for at the end)
     __syncthreads();
     // Classes in a canonical order: class 0, then by size, then by key.  A class pays for its binomial variate per
     // replicate only when it takes a fair share of the draws: small groups (and all groups of a short item) are drawn one
@@ -1308,25 +1317,30 @@ k_boot_classify(const __grid_constant__ BootArgs a)
     }
     __syncthreads();
     if (t == 0) { s_classes = min((uint32_t)kBootMaxClasses, s_scan[0] + s_scan[1]); if (r == 0) a.cls[p].n_classes = s_classes; }
+    // codons of every block that are in a class (the empty slot is not a codon): the blocks before this one fix where its
+    // general codons go
+    if (peer_h >= 0 && rank_of[peer_h] >= 0) atomicAdd(&members[peer], peer_cnt);
     __syncthreads();
     // pass 4: the codons outside the classes, in order, to the front of perm
     const bool general = i < C && !(h >= 0 && rank_of[h] >= 0);
     const unsigned bal = __ballot_sync(kFull, general);
     if (lane == 0) s_scan[warp] = __popc(bal);
     __syncthreads();
-    uint32_t before, total;
+    uint32_t before;
     {
         const uint32_t v = s_scan[lane];                 // kClassifyThreads / 32 = 32 warps: one count per lane
         uint32_t inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += n; }
         before = __shfl_sync(kFull, inc - v, warp);
-        total = __shfl_sync(kFull, inc, 31);
     }
-    if (t == 0) m_general[r] = total;
-    cluster.sync();
     uint32_t ahead = 0, all = 0;
-    for (uint32_t q = 0; q < kClsCtas; q++) { const uint32_t v = m_general[q]; ahead += q < r ? v : 0u; all += v; }
+    for (uint32_t q = 0; q < kClsCtas; q++) {
+        const uint32_t codons_q = min((uint32_t)kClassifyThreads, C - min(C, q * kClassifyThreads));
+        const uint32_t v = codons_q - (members[q] - (q == 0 && rank_of[zero_slot] >= 0 ? (uint32_t)a.slot0 : 0u));
+        ahead += q < r ? v : 0u;
+        all += v;
+    }
     if (general) {
         const uint32_t pos = ahead + before + __popc(bal & ((1u << lane) - 1));
         O[2 * pos] = x;
@@ -1351,7 +1365,7 @@ k_boot_classify(const __grid_constant__ BootArgs a)
         a.cls[p].node_lpq[t] = pr > 0.0 ? log(pr / (1.0 - pr)) : 0.0;
         a.cls[p].node_l1q[t] = log1p(-pr);
     }
-    cluster.sync();                                      // block 0's shared memory stays until every block has read it
+    cluster.barrier_wait();                              // this block's shared memory stays until every peer has read it
 }
 
 // Uniform numbers of one replicate's class counts: Philox blocks whose quad index starts at kSplitQuad0, far above any
@@ -1359,13 +1373,13 @@ k_boot_classify(const __grid_constant__ BootArgs a)
 constexpr uint32_t kSplitQuad0 = 0xC0000000u;
 struct SplitRng {
     uint4 ctr; uint2 key; uint4 buf; int have;
-    __device__ uint32_t next() {
+    __device__ __forceinline__ uint32_t next() {
         if (have == 0) { buf = philox4x32_10(ctr, key); ctr.x++; have = 4; }
         const uint32_t r = have == 4 ? buf.x : have == 3 ? buf.y : have == 2 ? buf.z : buf.w;
         have--;
         return r;
     }
-    __device__ double uniform() { return ((double)next() + 0.5) * 0x1p-32; }        // in (0, 1)
+    __device__ __forceinline__ double uniform() { return ((double)next() + 0.5) * 0x1p-32; }        // in (0, 1)
 };
 
 // log(k!) for k <= kLogFactMax, filled once per device (launch_bootstrap) with lgamma
@@ -1380,7 +1394,7 @@ __global__ void k_fill_logfact() {
 // of binomial random variates", 1993): transformed rejection with a squeeze, about 1.15 pairs of uniforms per variate;
 // the exact test compares with the logarithm of the probability ratio f(k) / f(mode) from the table of log-factorials.
 // Both are exact up to the resolution of the uniforms and of double arithmetic.
-__device__ uint32_t binomial_variate(SplitRng &rng, uint32_t n, double p, double lpq, double l1q) {
+__device__ __forceinline__ uint32_t binomial_variate(SplitRng &rng, uint32_t n, double p, double lpq, double l1q) {
     if (n == 0 || p <= 0.0) return 0;
     const double dn = (double)n;
     uint32_t k;
