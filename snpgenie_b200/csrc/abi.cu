@@ -285,6 +285,7 @@ int snpg_create(snpg_ctx **out, int device, uint64_t seed) {
     if (const char *v = getenv("SNPG_TMA_L2PROMO")) ctx->tma_l2_promotion = atoi(v);
     if ((e = ctx->d_sched.ensure(2 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(sched)", e);
     if ((e = cudaMemset(ctx->d_sched.p, 0, 2 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset(sched)", e);
+    if ((e = prepare_device_kernels()) != cudaSuccess) return bail("loading the kernels", e);
     std::vector<double> tab(128 + 8192);
     build_tables(tab.data(), tab.data() + 128);
     if ((e = ctx->d_tables.ensure(sizeof(double) * tab.size())) != cudaSuccess) return bail("cudaMalloc(tables)", e);

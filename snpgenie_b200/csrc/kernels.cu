@@ -2056,14 +2056,6 @@ void launch_bootstrap(int form, BootArgs a, int64_t max_codons, cudaStream_t str
         const int64_t per_mma = (int64_t)(kMmaWarps >> split) * nb;
         dim3 grid_mma((unsigned)((a.b_count + per_mma - 1) / per_mma), (unsigned)a.n_items);
         if (classes) {
-            static bool filled[64] = {};
-            int dev = 0;
-            cudaGetDevice(&dev);
-            if (dev >= 0 && dev < 64 && !filled[dev]) {          // log-factorials, once per device (outside any capture: the first job is not captured)
-                k_fill_logfact<<<(kLogFactMax + 256) / 256, 256, 0, stream>>>();
-                cudaStreamSynchronize(stream);                   // other streams of this device may follow at once
-                filled[dev] = true;
-            }
             static const int env_shift = [] { const char *v = getenv("SNPG_BOOT_CLASS_SHIFT"); return v ? std::max(1, std::min(12, atoi(v))) : 0; }();
             if (env_shift) a.cls_shift = env_shift;
             launch_peer_wait(a.ps, kStageStats, stream);         // the classes come from every rank's statistics
@@ -2083,6 +2075,27 @@ void launch_bootstrap(int form, BootArgs a, int64_t max_codons, cudaStream_t str
         k_bootstrap<false><<<grid, kBootWarps * 32, 0, stream>>>(a);
         if (sums) launch_product_sums(a.stats4, a.beg, a.n_items, sums, stream);
     }
+}
+
+// Once per ctx, before any job (snpg_create): loads every kernel a job may launch AFTER a kernel that waits for peer
+// GPUs -- with CUDA's lazy module loading the first launch of a kernel loads it, which waits for the device to drain; a
+// rank spinning for peers whose work the same host thread has not enqueued yet (one process, several GPUs) would never
+// get there -- and fills the table of log-factorials of the current device.
+cudaError_t prepare_device_kernels()
+{
+    cudaFuncAttributes fa;
+    const void *kernels[] = {(const void *)k_boot_classify, (const void *)k_boot_split, (const void *)k_bootstrap_mma<0, false>,
+                             (const void *)k_bootstrap_mma<1, false>, (const void *)k_bootstrap_mma<0, true>, (const void *)k_bootstrap_mma<1, true>,
+                             (const void *)k_bootstrap<true>, (const void *)k_bootstrap<false>, (const void *)k_moments<false>, (const void *)k_moments<true>,
+                             (const void *)k_window_sums, (const void *)k_product_sums, (const void *)k_peer_signal, (const void *)k_peer_wait,
+                             (const void *)k_stats<false>, (const void *)k_stats<true>, (const void *)k_fused_fixup_stats, (const void *)k_fused_fixup,
+                             (const void *)k_vote_refs, (const void *)k_fill_logfact, (const void *)k_window_rstats, (const void *)k_taxa_filter};
+    for (const void *k : kernels) {
+        const cudaError_t e = cudaFuncGetAttributes(&fa, k);
+        if (e != cudaSuccess) return e;
+    }
+    k_fill_logfact<<<(kLogFactMax + 256) / 256, 256>>>();
+    return cudaDeviceSynchronize();
 }
 
 size_t boot_scratch_bytes(int64_t total, int n_items, int64_t b_count)

@@ -198,6 +198,7 @@ struct BootArgs {
     double *perm = nullptr; BootClasses *cls = nullptr; uint32_t *split_m = nullptr; double2 *split_ns = nullptr;
     int cls_shift = 6;             // a group of conserved codons becomes a class from max(32, C >> cls_shift) members on
 };
+cudaError_t prepare_device_kernels();      // once per ctx on its device: see kernels.cu
 // Scratch of the class-aggregated bootstrap for items inside stats4[0, total) and b_count replicates of each.
 size_t boot_scratch_bytes(int64_t total, int n_items, int64_t b_count);
 void boot_scratch_carve(void *scratch, int64_t total, int n_items, int64_t b_count, BootArgs &a);
