@@ -9,7 +9,7 @@ our $VERSION = '0.1';
 XSLoader::load('SNPGenieCUDA', $VERSION);
 
 use constant { CODE_UNDEF => 64, CODE_OTHER => 65, HIST_BINS => 66, OPT_KEEP_CODES => 1, OPT_PROFILE => 2, OPT_SITE_COUNTS => 3,
-               OPT_FUSED_KERNEL => 4, OPT_BOOTSTRAP_KERNEL => 5, OPT_BOOT_SLOTS => 6, OPT_INGEST_ASYNC => 7, OPT_FIRST_DEFINED => 8, BOOT_GATHER => 0, BOOT_WEIGHTS => 1 };
+               OPT_FUSED_KERNEL => 4, OPT_BOOTSTRAP_KERNEL => 5, OPT_BOOT_SLOTS => 6, OPT_INGEST_ASYNC => 7, OPT_FIRST_DEFINED => 8, BOOT_GATHER => 0, BOOT_WEIGHTS => 1, BOOT_CLASSES => 2 };
 
 my @NT = qw(A C G T);
 # codon string of a code 0..63

@@ -479,8 +479,16 @@ k_vote_refs(const uint8_t *__restrict__ aln, int64_t pitch, int n_sample, int64_
     uint32_t c[5] = {0, 0, 0, 0, 0};
     const int n_cols = sp < n_spans ? 18 : 4;
 #pragma unroll
-    for (int j = 0; j < 18; j++)
-        if (j < n_cols) c[j >> 2] |= plurality_byte((x[j >> 2] >> (8 * (j & 3))) & 0xFFu, valid, lane) << (8 * (j & 3));
+    for (int k = 0; k < 5; k++) {
+        // most words are the same in every sampled row (lanes past the sample repeat its last row): one vote for the word
+        // then; the per-column plurality only where the rows differ
+        int unanimous = 0;
+        __match_all_sync(kFull, x[k], &unanimous);
+        if (unanimous) { c[k] = x[k]; continue; }
+#pragma unroll
+        for (int j = 4 * k; j < 4 * k + 4; j++)
+            if (j < n_cols) c[k] |= plurality_byte((x[k] >> (8 * (j & 3))) & 0xFFu, valid, lane) << (8 * (j & 3));
+    }
     if (lane == 0) {
         if (sp < n_spans) *reinterpret_cast<uint4 *>(cons + sp * 16) = make_uint4(c[0], c[1], c[2], c[3]);
         else *reinterpret_cast<uint32_t *>(cons + sp * 16) = c[0];
