@@ -287,9 +287,10 @@ int job_record(snpg_ctx *ctx, int group, const uint8_t *bases, int on_device, ui
                 a.stats4 = stats; a.beg = ctx->wplan.beg.as<int64_t>(); a.end = ctx->wplan.end.as<int64_t>(); a.n_items = (int)nwin; a.slot0 = 0;
                 a.b_count = job.n_window_bootstraps; a.key = philox_key(ctx); a.kind = kBootJobWindow; a.call = 0; a.salt = d_salt;
                 a.vals = ctx->w_vals.as<double>();
+                a.n_which = 3;                  // win_se holds the SEs of dN, dS, dN-dS (wgp:406-465): no Jukes-Cantor logarithms
                 launch_bootstrap(ctx->boot_kernel, a, job.window, ctx->stream);
             }
-            { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->w_vals.as<double>(), nwin, job.n_window_bootstraps, ctx->w_se.as<double>(), nullptr, nullptr, ctx->stream); }
+            { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->w_vals.as<double>(), nwin, job.n_window_bootstraps, ctx->w_se.as<double>(), nullptr, nullptr, ctx->stream, 3); }
         }
     }
     CU(ctx, cudaGetLastError());

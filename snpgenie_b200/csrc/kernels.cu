@@ -1161,7 +1161,7 @@ k_bootstrap(const __grid_constant__ BootArgs a)
     constexpr int kReps = kBootWarps * kBootRepsPerWarp;
     const int i = threadIdx.x, r = i % kReps, which = i / kReps;
     const int64_t bl = (int64_t)blockIdx.x * kReps + r;
-    const bool mine = which < 6 && bl < a.b_count;
+    const bool mine = which < a.n_which && bl < a.b_count;
     if (mine) {
         const double2 x = s_sums[r][0], y = s_sums[r][1];
         if (a.rep && which == 0) {
@@ -1621,7 +1621,7 @@ k_bootstrap_mma(const __grid_constant__ BootArgs a, uint32_t row_words, uint32_t
         }
         __syncthreads();
         // dense epilogue: one thread per (replicate of the batch, statistic), as in k_bootstrap
-        for (uint32_t i = threadIdx.x; i < rows * 6; i += blockDim.x) {
+        for (uint32_t i = threadIdx.x; i < rows * (uint32_t)a.n_which; i += blockDim.x) {
             const uint32_t r = i & (rows - 1), which = i >> lrows;
             const int64_t bl2 = batch_first + r;
             if (bl2 < a.b_count) {
@@ -1847,7 +1847,15 @@ __global__ void k_window_sums(const double *__restrict__ stats4, const int64_t *
     const double *p = stats4 + 4 * beg[k] + q;
     const int64_t W = end[k] - beg[k];
     double s = 0;
-    for (int64_t j = 0; j < W; j++) s += p[4 * j];
+    int64_t j = 0;
+    for (; j + 16 <= W; j += 16) {         // sixteen loads in flight, the additions in ascending order as before
+        double v[16];
+#pragma unroll
+        for (int u = 0; u < 16; u++) v[u] = __ldg(p + 4 * (j + u));
+#pragma unroll
+        for (int u = 0; u < 16; u++) s += v[u];
+    }
+    for (; j < W; j++) s += p[4 * j];
     win_sums[i] = s;
 }
 
@@ -2135,10 +2143,10 @@ void launch_moments(const double *d_rep, int64_t n_items, int64_t B, double *d_s
 }
 
 void launch_moments_vals(const double *d_vals, int64_t n_items, int64_t B, double *d_se, uint32_t *d_undefined, const PeerSync *ps,
-                         cudaStream_t stream)
+                         cudaStream_t stream, int n_which)
 {
     if (n_items <= 0) return;
-    k_moments<false><<<dim3((unsigned)n_items, 6), kMomentThreads, 0, stream>>>(d_vals, n_items, B, d_se, d_undefined, ps ? *ps : PeerSync());
+    k_moments<false><<<dim3((unsigned)n_items, (unsigned)n_which), kMomentThreads, 0, stream>>>(d_vals, n_items, B, d_se, d_undefined, ps ? *ps : PeerSync());
 }
 
 void launch_pooled_diffs(const double *d_freq, const double *d_cov, int64_t n, const double *d_tables, double *d_n_diffs, double *d_s_diffs,

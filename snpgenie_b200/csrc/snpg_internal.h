@@ -196,6 +196,7 @@ struct BootArgs {
     PeerVals pv; PeerSync ps;
     // SNPG_BOOT_CLASSES (items that do not overlap): scratch of boot_scratch_bytes(), carved by boot_scratch_carve()
     double *perm = nullptr; BootClasses *cls = nullptr; uint32_t *split_m = nullptr; double2 *split_ns = nullptr;
+    int n_which = 6;               // per-replicate values written: 6 = dN, dS, dN-dS and their Jukes-Cantor forms, 3 = the first three (window SEs)
     int cls_shift = 6;             // a group of conserved codons becomes a class from max(32, C >> cls_shift) members on
 };
 cudaError_t prepare_device_kernels();      // once per ctx on its device: see kernels.cu
@@ -215,7 +216,7 @@ void launch_moments(const double *d_rep, int64_t n_items, int64_t B, double *d_s
 // replicates whose value is not finite (Jukes-Cantor of a distance >= 3/4: the reference dies there, bgp:1047).
 // ps (or null): wait for stage kStageVals first.
 void launch_moments_vals(const double *d_vals, int64_t n_items, int64_t B, double *d_se, uint32_t *d_undefined, const PeerSync *ps,
-                         cudaStream_t stream);
+                         cudaStream_t stream, int n_which = 6);     // n_which: only the first statistics (se[item][0 .. n_which))
 
 // Row f4 (snpgenie.pl:6631-6760): per codon position, freq[c][64] codon frequencies and cov[c] mean coverage -> mean numbers of
 // nonsynonymous and synonymous differences between two reads of the pool.
