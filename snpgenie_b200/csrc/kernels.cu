@@ -432,6 +432,149 @@ k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, uint32_t n_rows, co
     if (t == 0 && atomicAdd(&sched[1], 1u) == gridDim.x - 1) { sched[0] = 0; sched[1] = 0; }
 }
 
+// ---------------------------------------------------------------------------
+// k_fused_hist_db: k_fused_hist with DOUBLE-BUFFERED row groups.  While a warp compares, parks and decodes the G rows
+// of one group, the loads of the next group are in flight (in k_fused_hist a warp has loads in flight only while it
+// waits for them: 39 % of its stall samples sit on the first use of a row group).  ptxas puts every row load on ONE
+// scoreboard, so waiting for any row waits for all loads issued so far: the next group's loads must be issued AFTER the
+// first use of the current group, and that order is forced by a data dependency ptxas cannot fold (the address of the
+// next loads adds `word & pitch & 15`, always 0 because the pitch is a multiple of 16; it does fold `(x*x+x)&1`).
+// Same arithmetic, chunk geometry, ring and decode as k_fused_hist; 16 more registers (3 blocks per SM).
+// Measured and not kept on the way (profiles/README.md): refilling the four registers of a row as soon as the row is
+// done (the newest load is waited for at every row: 85 us against 77); a ring of two conflict-free arrays with the
+// decode reading consensus and runs from per-warp shared-memory copies (fewer wavefronts, but 58 M instructions
+// instead of 42 M at the 80-register cap: 81 us); the same copies with the ring left as it is (47 M instructions, but
+// 18 KB more shared memory per block takes the L1 space those loads were hitting: 79.6 us).
+// ---------------------------------------------------------------------------
+template <int G, int QUEUE, int MIN_BLOCKS>
+__global__ void __launch_bounds__(kFusedWarps * 32, MIN_BLOCKS)
+k_fused_hist_db(const uint8_t *__restrict__ aln, int64_t pitch, uint32_t n_rows, const uint8_t *__restrict__ cons,
+                uint32_t *__restrict__ alt, uint32_t n_spans, const SpanRun *__restrict__ runs, uint32_t *__restrict__ hist,
+                uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max, uint32_t *__restrict__ sched,
+                uint32_t n_sb, uint32_t inv_sb, uint32_t chunk_a, uint32_t rows_a, uint32_t k_a, uint32_t k_total)
+{
+    constexpr int DRAIN_EVERY = G <= 3 ? G : 2;
+    static_assert(QUEUE >= 31 + 32 * DRAIN_EVERY && (QUEUE & (QUEUE - 1)) == 0 && G % DRAIN_EVERY == 0, "ring too small");
+    constexpr int kFusedQueueBytes = QUEUE * kFusedEntryBytes;        // the ring is aligned to its size
+    extern __shared__ __align__(16) uint8_t fused_smem[];             // kFusedWarps rings + one ring of slack for the alignment
+    __shared__ uint8_t lut_chr[2 * 256];
+    __shared__ uint8_t lut_cls[2 * 256];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int s = 0; s < 2; s++) {
+        const uint8_t n = norm_char((uint8_t)t, s);
+        lut_chr[s * 256 + t] = n;
+        lut_cls[s * 256 + t] = class_of(n);
+    }
+    __syncthreads();
+
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(fused_smem);
+    const uint32_t pad = (kFusedQueueBytes - (smem0 & (kFusedQueueBytes - 1))) & (kFusedQueueBytes - 1);
+    uint32_t q_base = smem0 + pad + warp * kFusedQueueBytes;
+    uint32_t a_cls = (uint32_t)__cvta_generic_to_shared(lut_cls), a_chr = (uint32_t)__cvta_generic_to_shared(lut_chr);
+    uint32_t q_head = 0, q_tail = 0;    // byte offsets into the ring, warp-uniform, free-running
+    unsigned lt = (1u << lane) - 1;
+    const uint32_t lane_ofs = lane * kFusedEntryBytes;
+    uint32_t one = 1u + (uint32_t)lane;          // 1 in lane 0, the only lane that claims
+    const RefPlanes refs = ref_planes(alt, n_spans);
+
+    auto drain = [&]() {     // at most 31 + 32 * DRAIN_EVERY parked entries between drains
+        while (q_tail - q_head >= 32u * kFusedEntryBytes) {
+            __syncwarp();
+            fused_decode(q_base | ((q_head + lane_ofs) & (kFusedQueueBytes - 1)), cons, runs, hist, other_min, other_max, a_cls, a_chr);
+            __syncwarp();
+            q_head += 32u * kFusedEntryBytes;
+        }
+    };
+    auto flush_ring = [&]() {   // fewer than 32 entries are left after a drain
+        __syncwarp();
+        if ((uint32_t)lane_ofs < q_tail - q_head)
+            fused_decode(q_base | ((q_head + lane_ofs) & (kFusedQueueBytes - 1)), cons, runs, hist, other_min, other_max, a_cls, a_chr);
+        __syncwarp();
+        q_head = q_tail;
+    };
+
+    uint32_t k_next = 0;
+    if (lane == 0) k_next = claim_async(sched, one);
+    uint32_t k = __shfl_sync(kFull, k_next, 0);
+    while (k < k_total) {
+        const bool in_a = k < k_a;
+        uint32_t rb, sb;
+        div_mod(in_a ? k : k - k_a, n_sb, inv_sb, rb, sb);
+        const uint32_t row0 = in_a ? rb * chunk_a : rows_a + rb * kFusedTailRows;
+        const uint32_t n_my = in_a ? chunk_a : min((uint32_t)kFusedTailRows, n_rows - row0);
+        const uint32_t span = sb * kFusedSpans + lane;
+        uint32_t live = lane < kFusedSpans && span < n_spans ? 0xFFFFFFFFu : 0u;
+        uint32_t sp = min(span, n_spans - 1);        // the references of a dead lane are never used
+        asm volatile("" : "+r"(lt), "+r"(q_base), "+r"(sp), "+r"(live));
+        const uint8_t *p = aln + (size_t)min(span, n_spans) * 16 + (size_t)row0 * pitch;
+        uint4 v[G], w[G];
+        auto fetch = [&](uint4 (&x)[G]) {
+#pragma unroll
+            for (int u = 0; u < G; u++) {
+                x[u] = ld_stream_v4(reinterpret_cast<const uint4 *>(p));
+                p += pitch;
+            }
+        };
+        const uint32_t n_grp = n_my / G;             // a chunk is whole groups, but for the last rows of the alignment
+        if (n_grp) fetch(v);
+        const uint4 c = *reinterpret_cast<const uint4 *>(cons + (size_t)sp * 16);
+        const uint32_t c4 = *reinterpret_cast<const uint32_t *>(cons + (size_t)sp * 16 + 16);
+        const uint4 a = refs.a16[sp], b = refs.b16[sp];
+        const uint32_t tails = refs.tails[sp], a4 = tails & 0xFFFFu, b4 = tails >> 16;
+        uint32_t n_alt = 0, n_alt2 = 0;
+
+        // one row of the warp: compare with the three references, count or park
+        auto row = [&](const uint4 &x) {
+            const uint32_t x4 = __shfl_down_sync(kFull, x.x, 1);
+            const uint32_t d = ((x.x ^ c.x) | (x.y ^ c.y) | (x.z ^ c.z) | (x.w ^ c.w) | ((x4 ^ c4) & 0xFFFFu)) & live;
+            const uint32_t da = (x.x ^ a.x) | (x.y ^ a.y) | (x.z ^ a.z) | (x.w ^ a.w) | ((x4 ^ a4) & 0xFFFFu);
+            const uint32_t db = (x.x ^ b.x) | (x.y ^ b.y) | (x.z ^ b.z) | (x.w ^ b.w) | ((x4 ^ b4) & 0xFFFFu);
+            n_alt += da == 0 ? 1u : 0u;          // the three references are pairwise distinct: at most one matches
+            n_alt2 += db == 0 ? 1u : 0u;
+            const bool differs = d != 0 && da != 0 && db != 0;
+            const unsigned bal = __ballot_sync(kFull, differs);
+            if (bal) {
+                if (differs) {
+                    const uint32_t at = q_base | ((q_tail + __popc(bal & lt) * kFusedEntryBytes) & (kFusedQueueBytes - 1));
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(at), "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w) : "memory");
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(at + 16), "r"(x4), "r"(sp) : "memory");
+                }
+                q_tail += __popc(bal) * kFusedEntryBytes;
+            }
+        };
+        auto rows = [&](uint4 (&x)[G]) {
+#pragma unroll
+            for (int u = 0; u < G; u++) {
+                row(x[u]);
+                if ((u + 1) % DRAIN_EVERY == 0) drain();
+            }
+        };
+
+        for (uint32_t g = 0; g < n_grp; g += 2) {
+            if (g + 2 >= n_grp && lane == 0) k_next = claim_async(sched, one);    // during the last one or two groups
+            p += v[0].x & (uint32_t)pitch & 15u;     // always 0: orders the next loads after the first use of this group
+            if (g + 1 < n_grp) fetch(w);
+            rows(v);
+            if (g + 1 >= n_grp) break;
+            p += w[0].x & (uint32_t)pitch & 15u;
+            if (g + 2 < n_grp) fetch(v);
+            rows(w);
+        }
+        if (n_grp == 0 && lane == 0) k_next = claim_async(sched, one);
+        for (uint32_t i = n_grp * G; i < n_my; i++, p += pitch) {     // the last rows of the last chunk
+            const uint4 x = ld_stream_v4(reinterpret_cast<const uint4 *>(p));
+            row(x);
+            drain();
+        }
+        if (live && n_alt) atomicAdd(&refs.cnt_a[sp], n_alt);
+        if (live && n_alt2) atomicAdd(&refs.cnt_b[sp], n_alt2);
+        k = __shfl_sync(kFull, k_next, 0);
+    }
+    flush_ring();
+    __syncthreads();
+    if (t == 0 && atomicAdd(&sched[1], 1u) == gridDim.x - 1) { sched[0] = 0; sched[1] = 0; }
+}
+
 // The three reference rows of the compare-with-reference kernels, from the first n_sample (<= 32) rows of
 // the group.  One warp per 16-byte span, one lane per sampled row.
 //   cons[column]   the most frequent byte of every column (lowest row on ties)
@@ -1914,9 +2057,12 @@ void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, cons
                             uint32_t *, uint32_t *, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t);
     // variant (SNPG_SPAN_VARIANT): 0 (default) = 4 blocks/SM at <= 64 registers; 1 = 3 blocks/SM, no register cap
     // 2 / 3 = variant 0 with the next four rows prefetched into L1 by every lane / by one lane per 128-byte line
-    static const int variant = [] { const char *v = getenv("SNPG_SPAN_VARIANT"); return v ? max(0, min(3, atoi(v))) : 0; }();
+    // k_fused_hist_db (double-buffered row groups): 4 = groups of 2 rows, 4 blocks/SM; 5 = groups of 4, 3 blocks/SM; 6 = groups of 2, 3 blocks/SM
+    static const int variant = [] { const char *v = getenv("SNPG_SPAN_VARIANT"); return v ? max(0, min(6, atoi(v))) : 0; }();
     static const Kernel kernel = variant == 1 ? (Kernel)k_fused_hist<4, 2, 128, 3> : variant == 2 ? (Kernel)k_fused_hist<4, 2, 128, 4, 1>
-                                 : variant == 3 ? (Kernel)k_fused_hist<4, 2, 128, 4, 2> : (Kernel)k_fused_hist<4, 2, 128, 4>;
+                                 : variant == 3 ? (Kernel)k_fused_hist<4, 2, 128, 4, 2> : variant == 4 ? (Kernel)k_fused_hist_db<2, 128, 4>
+                                 : variant == 5 ? (Kernel)k_fused_hist_db<4, 128, 3> : variant == 6 ? (Kernel)k_fused_hist_db<2, 128, 3>
+                                 : (Kernel)k_fused_hist<4, 2, 128, 4>;
     static const size_t smem = (size_t)(kFusedWarps + 1) * 128 * kFusedEntryBytes;
     static const int blocks_per_sm = [] {
         int nb = 0;
