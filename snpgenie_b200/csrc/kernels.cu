@@ -446,14 +446,13 @@ k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, uint32_t n_rows, co
 // instead of 42 M at the 80-register cap: 81 us); the same copies with the ring left as it is (47 M instructions, but
 // 18 KB more shared memory per block takes the L1 space those loads were hitting: 79.6 us).
 // ---------------------------------------------------------------------------
-template <int G, int QUEUE, int MIN_BLOCKS>
+template <int G, int QUEUE, int MIN_BLOCKS, int DRAIN_EVERY = (G <= 3 ? G : 2)>
 __global__ void __launch_bounds__(kFusedWarps * 32, MIN_BLOCKS)
 k_fused_hist_db(const uint8_t *__restrict__ aln, int64_t pitch, uint32_t n_rows, const uint8_t *__restrict__ cons,
                 uint32_t *__restrict__ alt, uint32_t n_spans, const SpanRun *__restrict__ runs, uint32_t *__restrict__ hist,
                 uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max, uint32_t *__restrict__ sched,
                 uint32_t n_sb, uint32_t inv_sb, uint32_t chunk_a, uint32_t rows_a, uint32_t k_a, uint32_t k_total)
 {
-    constexpr int DRAIN_EVERY = G <= 3 ? G : 2;
     static_assert(QUEUE >= 31 + 32 * DRAIN_EVERY && (QUEUE & (QUEUE - 1)) == 0 && G % DRAIN_EVERY == 0, "ring too small");
     constexpr int kFusedQueueBytes = QUEUE * kFusedEntryBytes;        // the ring is aligned to its size
     extern __shared__ __align__(16) uint8_t fused_smem[];             // kFusedWarps rings + one ring of slack for the alignment
@@ -2058,6 +2057,7 @@ void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, cons
     // variant (SNPG_SPAN_VARIANT): 0 (default) = 4 blocks/SM at <= 64 registers; 1 = 3 blocks/SM, no register cap
     // 2 / 3 = variant 0 with the next four rows prefetched into L1 by every lane / by one lane per 128-byte line
     // k_fused_hist_db (double-buffered row groups): 4 = groups of 2 rows, 4 blocks/SM; 5 = groups of 4, 3 blocks/SM; 6 = groups of 2, 3 blocks/SM
+    // (rings of 64 entries drained after every row -- half the shared memory, more L1 -- were measured with both kernels: 78 us)
     static const int variant = [] { const char *v = getenv("SNPG_SPAN_VARIANT"); return v ? max(0, min(6, atoi(v))) : 0; }();
     static const Kernel kernel = variant == 1 ? (Kernel)k_fused_hist<4, 2, 128, 3> : variant == 2 ? (Kernel)k_fused_hist<4, 2, 128, 4, 1>
                                  : variant == 3 ? (Kernel)k_fused_hist<4, 2, 128, 4, 2> : variant == 4 ? (Kernel)k_fused_hist_db<2, 128, 4>
