@@ -2084,7 +2084,10 @@ void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, cons
         // of kFusedTailRows to even out the finish; a small launch (a staged block of a host buffer) is one chunk per
         // warp and only the rows left over by the chunk size go out small.
         const int64_t share = rows * n_sb / (grid * kFusedWarps);
-        const int64_t chunk_a = env_rows ? env_rows : 32;
+        // (a small launch -- config 3's 5,000 x 9,719 alignment, a rank's eighth of the columns, a staged block of a host
+        // buffer -- would be less than one 32-row chunk per warp: a third of a warp's share, at least 4 rows; config 3
+        // whole job 0.325 -> 0.300 ms)
+        const int64_t chunk_a = env_rows ? env_rows : std::max<int64_t>(4, std::min<int64_t>(32, (share / 3) & ~(int64_t)3));
         const int64_t rows_a = (share >= 2 * chunk_a ? rows - rows * env_tail / 100 : rows) / chunk_a * chunk_a;
         const int64_t k_a = rows_a / chunk_a * n_sb;
         const int64_t k_b = (rows - rows_a + kFusedTailRows - 1) / kFusedTailRows * n_sb;
@@ -2197,8 +2200,10 @@ void launch_bootstrap(int form, BootArgs a, int64_t max_codons, cudaStream_t str
     const size_t smem = (size_t)(max_codons + 1) * 32;
     // a warp's counters: one byte per slot, rows padded to an odd number of words (no two of the eight rows a
     // tensor-core tile reads share a bank)
-    // (at least 16 KB a block even for a short table, so that short products can take several replicates per warp)
-    const size_t row_words = std::max<size_t>((((size_t)max_codons + 1 + 3) / 4) | 1, 127);
+    // (at least 16 KB a block even for a short table, so that short items take up to eight replicates per warp: sliding
+    // windows of 100 codons at 127 words took four -- config 3 whole job 0.260 ms, at 255 words 0.243, at 511 0.239)
+    static const size_t min_row_words = [] { const char *v = getenv("SNPG_BOOT_MINROW"); return v ? (size_t)(std::max(31, std::min(1023, atoi(v))) | 1) : (size_t)511; }();
+    const size_t row_words = std::max<size_t>((((size_t)max_codons + 1 + 3) / 4) | 1, min_row_words);
     const bool classes = form == SNPG_BOOT_CLASSES && a.perm && a.cls && a.split_m && a.split_ns && max_codons <= kLogFactMax;
     if ((form == SNPG_BOOT_WEIGHTS || form == SNPG_BOOT_CLASSES) && row_words * 4 * 32 <= (size_t)kBootSmemLimit) {
         // five blocks of kMmaWarps warps per SM; the grid is sized for one replicate per warp.  A block takes two batches
@@ -2215,7 +2220,14 @@ void launch_bootstrap(int form, BootArgs a, int64_t max_codons, cudaStream_t str
         if (blocks(2, 0) * 5 < slots * 4) { nb = 1; if (blocks(1, 0) * 2 < slots) split = 1; }
         if (env_nb == 1 || env_nb == 2) nb = env_nb;
         if (env_split == 0 || env_split == 1) split = env_split;
-        const int64_t per_mma = (int64_t)(kMmaWarps >> split) * nb;
+        // replicates a block takes: the kernel's own arithmetic for the LONGEST item (shorter items take more per warp and
+        // leave their last blocks idle).  Sized for one replicate per warp, a launch over sliding windows (100 slots: four
+        // replicates per warp) had seven idle blocks in eight: 60,000 blocks of which 7,680 worked, 114 us for config 3's
+        // window bootstraps.
+        const uint32_t rw_max = (uint32_t)(((size_t)max_codons + (size_t)(classes ? 0 : a.slot0) + 3) / 4) | 1u;
+        uint32_t lm = 0;
+        while ((2u << lm) <= (uint32_t)kBootMaxRows && (size_t)(2u << lm) * rw_max <= row_words) lm++;
+        const int64_t per_mma = lm ? (int64_t)kMmaWarps << lm : (int64_t)(kMmaWarps >> split) * nb;
         dim3 grid_mma((unsigned)((a.b_count + per_mma - 1) / per_mma), (unsigned)a.n_items);
         if (classes) {
             static const int env_shift = [] { const char *v = getenv("SNPG_BOOT_CLASS_SHIFT"); return v ? std::max(1, std::min(12, atoi(v))) : 0; }();
