@@ -282,6 +282,15 @@ int snpg_within_all(snpg_ctx *ctx, int group, int64_t B, double *prod_sums, doub
 int snpg_between_all(snpg_ctx *ctx, const int *groups, int n_groups, int64_t min_taxa_total, int64_t min_taxa_group, int64_t B,
                      double *pair_sums, double *pair_se);
 
+/* The between-group analysis as ONE call with a single synchronisation: loads n_groups alignments (all in host memory
+ * or all in device memory; arguments as snpg_load_group / snpg_load_group_device) as groups 0 .. n_groups-1 and runs
+ * snpg_between_all on them -- the between driver's outer loop over the group files (snpgenie_between_group.pl:133-187,
+ * :410-423) and the processor's sums and bootstraps (snpgenie_between_group_processor.pl:412-467, :869-1102).  The
+ * loads' kernels stay queued behind each other and the pair chains run on parallel streams; results equal the separate
+ * calls bit for bit.  Device buffers must stay valid until the call returns. */
+int snpg_between_job(snpg_ctx *ctx, int n_groups, const uint8_t *const *bases, int bases_on_device, const uint64_t *n_seqs, uint64_t aln_len,
+                     const uint64_t *row_stride, int64_t min_taxa_total, int64_t min_taxa_group, int64_t B, double *pair_sums, double *pair_se);
+
 /* Load + snpg_within_all as ONE call with a single synchronisation at the end: the
  * whole within-group job for a product-level answer (what the within driver's product
  * table needs).  bases is a host pointer (bases_on_device = 0; must stay valid until

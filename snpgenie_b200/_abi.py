@@ -84,6 +84,8 @@ SIGNATURES = {
     "snpg_pooled_diffs": (C.c_int, [_ctx, _f64p, _f64p, C.c_int64, _f64p, _f64p]),
     "snpg_within_all": (C.c_int, [_ctx, C.c_int, C.c_int64, _f64p, _f64p]),
     "snpg_between_all": (C.c_int, [_ctx, C.POINTER(C.c_int), C.c_int, C.c_int64, C.c_int64, C.c_int64, _f64p, _f64p]),
+    "snpg_between_job": (C.c_int, [_ctx, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_uint64), C.c_uint64, C.POINTER(C.c_uint64), C.c_int64,
+                                  C.c_int64, C.c_int64, _f64p, _f64p]),
     "snpg_within_job": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64, _f64p, _f64p]),
     "snpg_within_job_ex": (C.c_int, [_ctx, C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(Job)]),
     "snpg_window_plan": (C.c_int, [_ctx, C.c_int64, C.c_int64, _i64p]),

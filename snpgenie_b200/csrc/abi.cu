@@ -225,7 +225,7 @@ int finish_group(snpg_ctx *ctx, Group &g) {
         }
     }
     CU(ctx, cudaGetLastError());
-    if (!ctx->defer_load_sync) CU(ctx, sync_stream(ctx));
+    if (!ctx->defer_load_sync && !ctx->load_no_sync) CU(ctx, sync_stream(ctx));
     g.loaded = true;
     return SNPG_OK;
 }
@@ -327,6 +327,10 @@ void snpg_destroy(snpg_ctx *ctx) {
     for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (int l = 0; l < snpg_ctx::kPairLanes; l++) {
+        if (ctx->pair_done[l]) cudaEventDestroy(ctx->pair_done[l]);
+        if (ctx->pair_stream[l]) cudaStreamDestroy(ctx->pair_stream[l]);
+    }
     delete ctx;
 }
 
@@ -998,48 +1002,97 @@ int snpg_between_all(snpg_ctx *ctx, const int *groups, int n_groups, int64_t min
     const int n_pairs = n_groups * (n_groups - 1) / 2;
     const bool boot = pair_se && B >= 2;
     ctx->stats_of = nullptr;
-    CU(ctx, ctx->s_stats.ensure(sizeof(double) * 4 * (size_t)std::max<int64_t>(1, cnt)));
-    CU(ctx, ctx->s_nda.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, cnt)));
-    CU(ctx, ctx->s_ndb.ensure(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, cnt)));
+    // The pairs are independent chains of small, latency-bound kernels (cross-term statistics, filter, classes, binomial
+    // split, bootstrap, moments: 80 us a pair on config 4, 1.3 % of the SM time busy): up to kPairLanes of them run side by
+    // side, each on its own stream with its own slice of the scratch.  Same launches, same Philox streams, same results.
+    // With per-kernel timing on (SNPG_OPT_PROFILE) they stay on the ctx stream, one after the other.
+    const int lanes = (ctx->profile_mask || n_pairs < 2) ? 1 : std::min<int>(snpg_ctx::kPairLanes, n_pairs);
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t stats_b = up(sizeof(double) * 4 * (size_t)std::max<int64_t>(1, cnt)), nd_b = up(sizeof(uint32_t) * (size_t)std::max<int64_t>(1, cnt));
+    const size_t vals_b = boot ? up(sizeof(double) * 6 * (size_t)(B * P)) : 0;
+    const size_t boot_b = boot && ctx->boot_kernel == SNPG_BOOT_CLASSES ? up(boot_scratch_bytes(cnt, P, B)) : 0;
+    CU(ctx, ctx->s_stats.ensure(stats_b * lanes));
+    CU(ctx, ctx->s_nda.ensure(nd_b * lanes));
+    CU(ctx, ctx->s_ndb.ensure(nd_b * lanes));
     CU(ctx, ctx->s_sums.ensure(sizeof(double) * 4 * (size_t)(P * n_pairs)));
     if (boot) {
-        CU(ctx, ctx->s_vals.ensure(sizeof(double) * 6 * (size_t)(B * P)));
+        CU(ctx, ctx->s_vals.ensure(vals_b * lanes));
         CU(ctx, ctx->s_se.ensure(sizeof(double) * 6 * (size_t)(P * n_pairs)));
+        if (boot_b) CU(ctx, ctx->s_boot.ensure(boot_b * lanes));
+    }
+    if (lanes > 1) {
+        for (int l = 0; l < lanes; l++) {
+            if (!ctx->pair_stream[l]) CU(ctx, cudaStreamCreateWithFlags(&ctx->pair_stream[l], cudaStreamNonBlocking));
+            if (!ctx->pair_done[l]) CU(ctx, cudaEventCreateWithFlags(&ctx->pair_done[l], cudaEventDisableTiming));
+        }
+        CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));          // the groups' histograms are ready on the ctx stream
+        for (int l = 0; l < lanes; l++) CU(ctx, cudaStreamWaitEvent(ctx->pair_stream[l], ctx->ev_fork, 0));
     }
     const uint32_t call = ctx->call_id++;
     int pair = 0;
     for (int i = 0; i < n_groups; i++) {
         for (int j = i + 1; j < n_groups; j++, pair++) {
             const Group &ga = ctx->groups[groups[i]], &gb = ctx->groups[groups[j]];
-            StatsOut o{nullptr, ctx->s_nda.as<uint32_t>(), ctx->s_ndb.as<uint32_t>(), nullptr, ctx->s_stats.as<double>(), nullptr};
-            { Launch l(ctx, SNPG_K_STATS); launch_between_stats(view_of(ctx, ga, 0), view_of(ctx, gb, 0), cnt, ctx->d_tables.as<double>(), o, ctx->stream); }
+            const int lane = pair % lanes;
+            cudaStream_t st = lanes > 1 ? ctx->pair_stream[lane] : ctx->stream;
+            double *l_stats = reinterpret_cast<double *>(static_cast<uint8_t *>(ctx->s_stats.p) + stats_b * lane);
+            uint32_t *l_nda = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(ctx->s_nda.p) + nd_b * lane);
+            uint32_t *l_ndb = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(ctx->s_ndb.p) + nd_b * lane);
+            StatsOut o{nullptr, l_nda, l_ndb, nullptr, l_stats, nullptr};
+            { Launch l(ctx, SNPG_K_STATS); launch_between_stats(view_of(ctx, ga, 0), view_of(ctx, gb, 0), cnt, ctx->d_tables.as<double>(), o, st); }
             if (min_taxa_total > 0 || min_taxa_group > 0) {
                 Launch l(ctx, SNPG_K_OTHER);
-                launch_taxa_filter(ctx->s_stats.as<double>(), ctx->s_nda.as<uint32_t>(), ctx->s_ndb.as<uint32_t>(), cnt,
-                                   (uint32_t)min_taxa_total, (uint32_t)min_taxa_group, ctx->stream);
+                launch_taxa_filter(l_stats, l_nda, l_ndb, cnt, (uint32_t)min_taxa_total, (uint32_t)min_taxa_group, st);
             }
             double *d_pair_sums = ctx->s_sums.as<double>() + 4 * (size_t)P * pair;
-            if (!boot) { Launch l(ctx, SNPG_K_SUMS); launch_product_sums(ctx->s_stats.as<double>(), ctx->d_local_ofs.as<int64_t>(), P, d_pair_sums, ctx->stream); }
+            if (!boot) { Launch l(ctx, SNPG_K_SUMS); launch_product_sums(l_stats, ctx->d_local_ofs.as<int64_t>(), P, d_pair_sums, st); }
             if (boot) {
+                double *l_vals = reinterpret_cast<double *>(static_cast<uint8_t *>(ctx->s_vals.p) + vals_b * lane);
                 {
                     Launch l(ctx, SNPG_K_BOOT);      // also writes the product sums
                     BootArgs a;
-                    a.stats4 = ctx->s_stats.as<double>(); a.beg = ctx->d_local_ofs.as<int64_t>(); a.end = a.beg + 1; a.order = ctx->d_order_local.as<int>();
+                    a.stats4 = l_stats; a.beg = ctx->d_local_ofs.as<int64_t>(); a.end = a.beg + 1; a.order = ctx->d_order_local.as<int>();
                     a.n_items = P; a.slot0 = ctx->boot_slot0; a.b_count = B; a.key = philox_key(ctx); a.kind = kBootBetween; a.call = call;
                     a.item0 = (uint32_t)(pair * P);  // every (pair, product) its own stream
-                    a.vals = ctx->s_vals.as<double>(); a.prod_sums = d_pair_sums;
-                    if (int rc = boot_classes_scratch(ctx, a, cnt)) return rc;
-                    launch_bootstrap(ctx->boot_kernel, a, ctx->max_codons_local, ctx->stream);
+                    a.vals = l_vals; a.prod_sums = d_pair_sums;
+                    if (boot_b) {
+                        boot_scratch_carve(static_cast<uint8_t *>(ctx->s_boot.p) + boot_b * lane, cnt, P, B, a);
+                        ctx->launches += 2;          // k_boot_classify, k_boot_split
+                    }
+                    launch_bootstrap(ctx->boot_kernel, a, ctx->max_codons_local, st);
                 }
-                { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->s_vals.as<double>(), P, B, ctx->s_se.as<double>() + 6 * (size_t)P * pair, nullptr, nullptr, ctx->stream); }
+                { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(l_vals, P, B, ctx->s_se.as<double>() + 6 * (size_t)P * pair, nullptr, nullptr, st); }
             }
         }
     }
+    if (lanes > 1)
+        for (int l = 0; l < lanes; l++) {
+            CU(ctx, cudaEventRecord(ctx->pair_done[l], ctx->pair_stream[l]));
+            CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->pair_done[l], 0));
+        }
     CU(ctx, cudaGetLastError());
     CU(ctx, cudaMemcpyAsync(pair_sums, ctx->s_sums.p, sizeof(double) * 4 * (size_t)(P * n_pairs), cudaMemcpyDeviceToHost, ctx->stream));
     if (boot) CU(ctx, cudaMemcpyAsync(pair_se, ctx->s_se.p, sizeof(double) * 6 * (size_t)(P * n_pairs), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, sync_stream(ctx));
     return SNPG_OK;
+}
+
+int snpg_between_job(snpg_ctx *ctx, int n_groups, const uint8_t *const *bases, int bases_on_device, const uint64_t *n_seqs, uint64_t aln_len,
+                     const uint64_t *row_stride, int64_t min_taxa_total, int64_t min_taxa_group, int64_t B, double *pair_sums, double *pair_se) {
+    if (!ctx) return SNPG_E_ARG;
+    TEAM_UNSUPPORTED(ctx, "snpg_between_job");
+    NEED(ctx, bases && n_seqs && row_stride && n_groups >= 2 && n_groups <= SNPG_MAX_GROUPS, SNPG_E_ARG, "bad between_job arguments");
+    int groups[SNPG_MAX_GROUPS];
+    int rc = SNPG_OK;
+    ctx->load_no_sync = true;
+    for (int g = 0; g < n_groups && rc == SNPG_OK; g++) {
+        groups[g] = g;
+        rc = bases_on_device ? snpg_load_group_device(ctx, g, bases[g], n_seqs[g], aln_len, row_stride[g])
+                             : snpg_load_group(ctx, g, bases[g], n_seqs[g], aln_len, row_stride[g]);
+    }
+    ctx->load_no_sync = false;
+    if (rc != SNPG_OK) { sync_stream(ctx); return rc; }     // nothing stays queued behind a failed call
+    return snpg_between_all(ctx, groups, n_groups, min_taxa_total, min_taxa_group, B, pair_sums, pair_se);
 }
 
 int snpg_test_philox(snpg_ctx *ctx, const uint32_t *ctr4, const uint32_t *key2, uint32_t *out4) {

@@ -73,12 +73,18 @@ struct snpg_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_packed[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;     // result copies run beside the bootstrap (job.cu)
+    // snpg_between_all: the group pairs are independent chains of small kernels; they run on kPairLanes streams side by
+    // side, each lane with its own slice of the scratch buffers (created on first use)
+    static constexpr int kPairLanes = 6;
+    cudaStream_t pair_stream[kPairLanes] = {};
+    cudaEvent_t pair_done[kPairLanes] = {};
     int rank = 0, world = 1;
     bool keep_codes = false;        // default route: fused histogram, no code matrix
     bool site_counts = false;       // also count A/C/G/T per alignment column while loading (whole rows are staged)
     bool ingest_async = false;      // snpg_read_fasta returns while its second pass is still copying rows
     bool first_defined = false;     // loads without a code matrix also note every codon's first defined codon (between-group rule)
     bool defer_load_sync = false;   // set inside a whole job: the load's kernels stay queued behind the analysis
+    bool load_no_sync = false;      // set inside snpg_between_job: a load returns with its kernels queued (nothing else changes)
     // annotation
     int n_products = 0;
     int64_t aln_len = 0;

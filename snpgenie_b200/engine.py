@@ -311,6 +311,19 @@ class Engine:
         self._ck(_abi.lib.snpg_between_all(self._ctx, g, n, min_taxa_total, min_taxa_group, B, _ptr(sums, C.c_double), _ptr(se, C.c_double)))
         return sums, se
 
+    def between_job(self, ptrs: list[int], n_seqs: list[int], aln_len: int, row_strides: list[int], device: bool, B: int = 0,
+                    min_taxa_total: int = 0, min_taxa_group: int = 0):
+        """Loads the alignments at `ptrs` as groups 0..n-1 and analyses every pair x every product in ONE ABI call (one
+        synchronisation): what `load_group_ptr` x n + `between_all` return, bit for bit."""
+        P, n = len(self.products), len(ptrs)
+        n_pairs = n * (n - 1) // 2
+        sums = np.zeros((n_pairs, P, 4))
+        se = np.zeros((n_pairs, P, 6)) if B >= 2 else None
+        self._ck(_abi.lib.snpg_between_job(self._ctx, n, (C.c_void_p * n)(*ptrs), int(device), (C.c_uint64 * n)(*n_seqs), aln_len,
+                                           (C.c_uint64 * n)(*row_strides), min_taxa_total, min_taxa_group, B, _ptr(sums, C.c_double),
+                                           _ptr(se, C.c_double)))
+        return sums, se
+
     def within_job(self, group: int, ptr: int, n_seqs: int, aln_len: int, row_stride: int, device: bool, B: int = 0):
         """Load + within_all in one ABI call (one synchronisation): per-product sums [P,4], SEs [P,6]."""
         P = len(self.products)

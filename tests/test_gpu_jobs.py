@@ -289,3 +289,42 @@ def test_unconnected_ranks_fail_loudly():
         with pytest.raises(_abi.SnpgError) as e:          # windows need the whole axis
             eng.job(0, aln.ctypes.data, aln.shape[0], aln.shape[1], aln.strides[0], window=10, step=1)
         assert e.value.code == _abi.E_STATE
+
+
+@pytest.mark.parametrize("device", [True, False])
+def test_between_job_equals_loads_plus_between_all_bit_for_bit(device):
+    """snpg_between_job (the loads queued behind each other, the group pairs on parallel streams, one synchronisation)
+    returns what snpg_load_group x n + snpg_between_all return -- also when those run with per-kernel timing on, which
+    keeps the pairs on one stream, one after the other."""
+    import torch
+    from snpgenie_b200 import _abi
+    from snpgenie_b200.engine import Engine
+    products = synth.hiv_products()
+    L = 9719
+    pitch = (L + 127) // 128 * 128
+    alns = [synth.make_alignment(n, L, products, 900 + g, gap_frac=0.03, n_frac=0.02, iupac_frac=0.004) for g, n in enumerate((70, 45, 52, 64))]
+    bufs = []
+    for a in alns:
+        t = torch.zeros((a.shape[0], pitch), dtype=torch.uint8, device="cuda:0" if device else "cpu")
+        t[:, :L] = torch.from_numpy(a)
+        bufs.append(t)
+    ns = [a.shape[0] for a in alns]
+    want = {}
+    for profile in (0, 1):
+        with Engine(device=0, seed=5) as e:
+            e.set_option(_abi.OPT_PROFILE, 0xFFFF if profile else 0)
+            e.set_products(products, L)
+            for g, t in enumerate(bufs):
+                e.load_group_ptr(g, t.data_ptr(), ns[g], L, pitch, device=device)
+            want[profile] = e.between_all([0, 1, 2, 3], B=500, min_taxa_total=90, min_taxa_group=30)
+    assert np.array_equal(want[0][0], want[1][0]) and np.array_equal(want[0][1], want[1][1], equal_nan=True)   # (Jukes-Cantor SEs of distant groups are NaN)
+    with Engine(device=0, seed=5) as e:
+        e.set_products(products, L)
+        sums, se = e.between_job([t.data_ptr() for t in bufs], ns, L, [pitch] * 4, device=device, B=500, min_taxa_total=90, min_taxa_group=30)
+        assert np.array_equal(sums, want[0][0]) and np.array_equal(se, want[0][1], equal_nan=True)
+        assert np.isfinite(sums).all() and (se[:, :, :3] >= 0).all() and sums[:, :, 0].max() > 0
+        # a second job on the same ctx: same sums, another Philox stream
+        sums2, se2 = e.between_job([t.data_ptr() for t in bufs], ns, L, [pitch] * 4, device=device, B=500, min_taxa_total=90, min_taxa_group=30)
+        assert np.array_equal(sums2, sums) and not np.array_equal(se2[:, :, :3], se[:, :, :3])
+        with pytest.raises(Exception):
+            e.between_job([bufs[0].data_ptr()], ns[:1], L, [pitch], device=device, B=0)
