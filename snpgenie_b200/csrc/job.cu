@@ -214,10 +214,17 @@ int job_record(snpg_ctx *ctx, int group, const uint8_t *bases, int on_device, ui
     const int64_t max_codons = multi ? ctx->max_codons_full : ctx->max_codons_local;
     Stager st{ctx, &job};
 
-    // the per-codon tables leave on the copy stream while the bootstrap runs
+    // the per-codon tables leave on the copy stream while the bootstrap runs; on one GPU the sliding windows (sums,
+    // bootstraps, moments: they read the statistics only) run on a third stream beside the product bootstraps -- config 3:
+    // two chains of about 75 us each.  With per-kernel timing on, everything stays on the ctx stream.
     const bool codon_out = job.poly || job.n_defined || job.comparisons || job.stats4 || job.conserved;
+    const int64_t nwin = job.window > 0 ? ctx->wplan.n : 0;
+    const bool win_boot = nwin > 0 && job.n_window_bootstraps >= 2 && job.win_se;
+    const bool win_beside = nwin > 0 && (job.win_sums || win_boot) && job.n_bootstraps >= 2 && !multi && !ctx->profile_mask;
+    cudaStream_t ws = win_beside ? ctx->win_stream : ctx->stream;
+    if (codon_out || win_beside) CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    if (win_beside) CU(ctx, cudaStreamWaitEvent(ctx->win_stream, ctx->ev_fork, 0));
     if (codon_out) {
-        CU(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
         CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_fork, 0));
         if (multi) launch_peer_wait(ps, kStageStats, ctx->copy_stream);
         const uint8_t *d_poly = multi ? X.at<uint8_t>(ctx->rank, parity, X.off_poly) : ctx->s_poly.as<uint8_t>();
@@ -232,6 +239,32 @@ int job_record(snpg_ctx *ctx, int group, const uint8_t *bases, int on_device, ui
         CU(ctx, cudaEventRecord(ctx->ev_join, ctx->copy_stream));
     }
 
+    // sliding windows over the whole axis (every rank computes all of them: 4 W adds and B_win W draws per window)
+    auto enqueue_windows = [&](bool stats_arrived) -> int {
+        if (nwin > 0 && (job.win_sums || win_boot)) {
+            if (!stats_arrived) { Launch l(ctx, SNPG_K_OTHER); launch_peer_wait(ps, kStageStats, ws); }
+            if (job.win_sums) {
+                Launch l(ctx, SNPG_K_WINDOW);
+                launch_window_sums(stats, ctx->wplan.beg.as<int64_t>(), ctx->wplan.end.as<int64_t>(), nwin, ctx->w_sums.as<double>(), ws);
+            }
+            if (win_boot) {
+                {
+                    Launch l(ctx, SNPG_K_WINDOW);
+                    BootArgs a;
+                    a.stats4 = stats; a.beg = ctx->wplan.beg.as<int64_t>(); a.end = ctx->wplan.end.as<int64_t>(); a.n_items = (int)nwin; a.slot0 = 0;
+                    a.b_count = job.n_window_bootstraps; a.key = philox_key(ctx); a.kind = kBootJobWindow; a.call = 0; a.salt = d_salt;
+                    a.vals = ctx->w_vals.as<double>();
+                    a.n_which = 3;                  // win_se holds the SEs of dN, dS, dN-dS (wgp:406-465): no Jukes-Cantor logarithms
+                    launch_bootstrap(ctx->boot_kernel, a, job.window, ws);
+                }
+                { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->w_vals.as<double>(), nwin, job.n_window_bootstraps, ctx->w_se.as<double>(), nullptr, nullptr, ws, 3); }
+            }
+        }
+        if (win_beside) CU(ctx, cudaEventRecord(ctx->ev_win, ctx->win_stream));
+        return SNPG_OK;
+    };
+    if (win_beside)                       // on their own stream, enqueued first: the product bootstraps below run beside them
+        if (int rc = enqueue_windows(true)) return rc;
     const int64_t B = job.n_bootstraps;
     const bool boot = B >= 2;             // (a rank's replicate range is needed by its peers whether or not it reports anything itself)
     bool stats_arrived = !multi;          // every rank's statistics are known to be in this rank's region
@@ -271,28 +304,8 @@ int job_record(snpg_ctx *ctx, int group, const uint8_t *bases, int on_device, ui
             launch_moments_vals(vals, P, B, ctx->s_se.as<double>(), ctx->s_undef.as<uint32_t>(), multi ? &ps : nullptr, ctx->stream);
         }
     }
-    // sliding windows over the whole axis (every rank computes all of them: 4 W adds and B_win W draws per window)
-    const int64_t nwin = job.window > 0 ? ctx->wplan.n : 0;
-    const bool win_boot = nwin > 0 && job.n_window_bootstraps >= 2 && job.win_se;
-    if (nwin > 0 && (job.win_sums || win_boot)) {
-        if (!stats_arrived) { Launch l(ctx, SNPG_K_OTHER); launch_peer_wait(ps, kStageStats, ctx->stream); }
-        if (job.win_sums) {
-            Launch l(ctx, SNPG_K_WINDOW);
-            launch_window_sums(stats, ctx->wplan.beg.as<int64_t>(), ctx->wplan.end.as<int64_t>(), nwin, ctx->w_sums.as<double>(), ctx->stream);
-        }
-        if (win_boot) {
-            {
-                Launch l(ctx, SNPG_K_WINDOW);
-                BootArgs a;
-                a.stats4 = stats; a.beg = ctx->wplan.beg.as<int64_t>(); a.end = ctx->wplan.end.as<int64_t>(); a.n_items = (int)nwin; a.slot0 = 0;
-                a.b_count = job.n_window_bootstraps; a.key = philox_key(ctx); a.kind = kBootJobWindow; a.call = 0; a.salt = d_salt;
-                a.vals = ctx->w_vals.as<double>();
-                a.n_which = 3;                  // win_se holds the SEs of dN, dS, dN-dS (wgp:406-465): no Jukes-Cantor logarithms
-                launch_bootstrap(ctx->boot_kernel, a, job.window, ctx->stream);
-            }
-            { Launch l(ctx, SNPG_K_MOMENTS); launch_moments_vals(ctx->w_vals.as<double>(), nwin, job.n_window_bootstraps, ctx->w_se.as<double>(), nullptr, nullptr, ctx->stream, 3); }
-        }
-    }
+    if (win_beside) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_win, 0));
+    else if (int rc = enqueue_windows(stats_arrived)) return rc;
     CU(ctx, cudaGetLastError());
     // the small tables always go through the staging buffer (one pinned line each)
     if (int rc = st.put(F_PROD_SUMS, ctx->s_sums.p, sizeof(double) * 4 * (size_t)P, ctx->stream)) return rc;

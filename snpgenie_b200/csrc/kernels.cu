@@ -2085,9 +2085,10 @@ void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, cons
         // warp and only the rows left over by the chunk size go out small.
         const int64_t share = rows * n_sb / (grid * kFusedWarps);
         // (a small launch -- config 3's 5,000 x 9,719 alignment, a rank's eighth of the columns, a staged block of a host
-        // buffer -- would be less than one 32-row chunk per warp: a third of a warp's share, at least 4 rows; config 3
-        // whole job 0.325 -> 0.300 ms)
-        const int64_t chunk_a = env_rows ? env_rows : std::max<int64_t>(4, std::min<int64_t>(32, (share / 3) & ~(int64_t)3));
+        // buffer -- would be less than one 32-row chunk per warp: half of a warp's share, at least 8 rows.  Measured
+        // (profiles/r2_chunk_sweep.txt): config 3, where six rows in ten are parked, 79 us at 32 rows, 55 at 8 and at 4; 1,250
+        // to 5,000 rows of config 2, cheap rows, within 1 us of the best at 8 / 16 / 32 rows, but 30-80 us at 4)
+        const int64_t chunk_a = env_rows ? env_rows : std::max<int64_t>(8, std::min<int64_t>(32, (share / 2) & ~(int64_t)3));
         const int64_t rows_a = (share >= 2 * chunk_a ? rows - rows * env_tail / 100 : rows) / chunk_a * chunk_a;
         const int64_t k_a = rows_a / chunk_a * n_sb;
         const int64_t k_b = (rows - rows_a + kFusedTailRows - 1) / kFusedTailRows * n_sb;

@@ -1,9 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-O=gpurun_out/r2_c3_ab.txt; : > $O
-for r in 127 255 511; do echo "SNPG_BOOT_MINROW=$r" >> $O; SNPG_BOOT_MINROW=$r python tools/prof_config3.py >> $O 2>&1
-SNPG_BOOT_MINROW=$r python bench.py --no-cpu --no-extras --steps 40 --warmup 5 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print(round(d['ms_per_step'],4), {k:round(v['ms_per_step']*1e3,1) for k,v in d['kernels'].items()})" >> $O 2>&1
-done
-cat $O
+python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_pytest.log
+python tools/prof_config3.py > gpurun_out/r2_c3_ab.txt 2>&1
+python tools/chunk_sweep.py >> gpurun_out/r2_c3_ab.txt 2>&1; python tools/chunk_sweep.py --hiv --n 2500 5000 >> gpurun_out/r2_c3_ab.txt 2>&1
+python bench.py > gpurun_out/r2_bench_fused.json 2> gpurun_out/bench_fused.err
+python -c "
+import json
+d=json.loads(open('gpurun_out/r2_bench_fused.json').read().strip().splitlines()[-1]); print(round(d['ms_per_step'],4), {k:round(v['ms_per_step']*1e3,1) for k,v in d['kernels'].items()}, 'e2e', d['e2e']['ms_per_step'], 'c3', d['config3']['ms_per_step'], 'c4', d['config4']['ms_per_step'])" >> gpurun_out/r2_c3_ab.txt 2>&1
+cat gpurun_out/r2_c3_ab.txt; tail -n 3 gpurun_out/r2_pytest.log
