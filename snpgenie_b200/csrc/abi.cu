@@ -143,7 +143,7 @@ int pack_block(snpg_ctx *ctx, Group &g, const uint8_t *d_block, int64_t pitch, i
         // the rows every row is compared with: per-column plurality and per-span runner-up over the group's first rows
         Launch l(ctx, SNPG_K_OTHER);
         launch_vote_refs(d_block, pitch, (int)std::min<int64_t>(rows, 32), ctx->n_spans, ctx->d_cons.as<uint8_t>(), ctx->d_alt.as<uint32_t>(),
-                         g.clear_in_vote ? g.hist.as<uint32_t>() : nullptr, omin, omax, ctx->shard_count, ctx->stream);
+                         g.clear_in_vote ? g.hist.as<uint32_t>() : nullptr, omin, omax, ctx->shard_count, ctx->d_sched.as<uint32_t>(), ctx->stream);
         g.clear_in_vote = false;
     }
     if (ctx->site_counts) {
@@ -285,8 +285,8 @@ int snpg_create(snpg_ctx **out, int device, uint64_t seed) {
     if ((e = cudaEventCreateWithFlags(&ctx->ev_win, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if (cudaDeviceGetAttribute(&ctx->n_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || ctx->n_sms <= 0) ctx->n_sms = 148;
     if (const char *v = getenv("SNPG_TMA_L2PROMO")) ctx->tma_l2_promotion = atoi(v);
-    if ((e = ctx->d_sched.ensure(2 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(sched)", e);
-    if ((e = cudaMemset(ctx->d_sched.p, 0, 2 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset(sched)", e);
+    if ((e = ctx->d_sched.ensure(4 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(sched)", e);
+    if ((e = cudaMemset(ctx->d_sched.p, 0, 4 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMemset(sched)", e);
     if ((e = prepare_device_kernels()) != cudaSuccess) return bail("loading the kernels", e);
     std::vector<double> tab(128 + 8192);
     build_tables(tab.data(), tab.data() + 128);

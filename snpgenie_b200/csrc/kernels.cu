@@ -312,7 +312,8 @@ __global__ void __launch_bounds__(kFusedWarps * 32, MIN_BLOCKS)
 k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, uint32_t n_rows, const uint8_t *__restrict__ cons,
              uint32_t *__restrict__ alt, uint32_t n_spans, const SpanRun *__restrict__ runs, uint32_t *__restrict__ hist,
              uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max, uint32_t *__restrict__ sched,
-             uint32_t n_sb, uint32_t inv_sb, uint32_t chunk_a, uint32_t rows_a, uint32_t k_a, uint32_t k_total)
+             uint32_t n_sb, uint32_t inv_sb, uint32_t chunk_a, uint32_t rows_a, uint32_t k_a, uint32_t k_total,
+             uint32_t dense_min, uint32_t chunk_d, uint32_t rows_a_d, uint32_t k_a_d, uint32_t k_total_d)
 {
     static_assert(QUEUE >= 31 + 32 * DRAIN_EVERY && (QUEUE & (QUEUE - 1)) == 0 && UNROLL % DRAIN_EVERY == 0, "ring too small");
     constexpr int kFusedQueueBytes = QUEUE * kFusedEntryBytes;        // the ring is aligned to its size
@@ -326,6 +327,12 @@ k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, uint32_t n_rows, co
         lut_cls[s * 256 + t] = class_of(n);
     }
     __syncthreads();
+
+    // Rows that match none of the three references are expensive (parked, decoded); where the vote's sample says they are
+    // many (sched[2] = unmatched (span, sample row) pairs, left by k_vote_refs, zeroed by the last block below), small
+    // chunks even out the warps' shares; where rows are cheap, a chunk's fixed cost (claim, references, first loads) wants
+    // 32 rows.  Both geometries come from the host (launch_fused_hist).
+    if (sched[2] >= dense_min) { chunk_a = chunk_d; rows_a = rows_a_d; k_a = k_a_d; k_total = k_total_d; }
 
     const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(fused_smem);
     const uint32_t pad = (kFusedQueueBytes - (smem0 & (kFusedQueueBytes - 1))) & (kFusedQueueBytes - 1);
@@ -429,7 +436,7 @@ k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, uint32_t n_rows, co
     if ((uint32_t)lane_ofs < q_tail - q_head)
         fused_decode(q_base | ((q_head + lane_ofs) & (kFusedQueueBytes - 1)), cons, runs, hist, other_min, other_max, a_cls, a_chr);
     __syncthreads();
-    if (t == 0 && atomicAdd(&sched[1], 1u) == gridDim.x - 1) { sched[0] = 0; sched[1] = 0; }
+    if (t == 0 && atomicAdd(&sched[1], 1u) == gridDim.x - 1) { sched[0] = 0; sched[1] = 0; sched[2] = 0; }
 }
 
 // ---------------------------------------------------------------------------
@@ -446,12 +453,13 @@ k_fused_hist(const uint8_t *__restrict__ aln, int64_t pitch, uint32_t n_rows, co
 // instead of 42 M at the 80-register cap: 81 us); the same copies with the ring left as it is (47 M instructions, but
 // 18 KB more shared memory per block takes the L1 space those loads were hitting: 79.6 us).
 // ---------------------------------------------------------------------------
-template <int G, int QUEUE, int MIN_BLOCKS, int DRAIN_EVERY = (G <= 3 ? G : 2)>
-__global__ void __launch_bounds__(kFusedWarps * 32, MIN_BLOCKS)
+template <int G, int QUEUE, int MIN_BLOCKS, int WARPS = kFusedWarps, int DRAIN_EVERY = (G <= 3 ? G : 2)>
+__global__ void __launch_bounds__(WARPS * 32, MIN_BLOCKS)
 k_fused_hist_db(const uint8_t *__restrict__ aln, int64_t pitch, uint32_t n_rows, const uint8_t *__restrict__ cons,
                 uint32_t *__restrict__ alt, uint32_t n_spans, const SpanRun *__restrict__ runs, uint32_t *__restrict__ hist,
                 uint32_t *__restrict__ other_min, uint32_t *__restrict__ other_max, uint32_t *__restrict__ sched,
-                uint32_t n_sb, uint32_t inv_sb, uint32_t chunk_a, uint32_t rows_a, uint32_t k_a, uint32_t k_total)
+                uint32_t n_sb, uint32_t inv_sb, uint32_t chunk_a, uint32_t rows_a, uint32_t k_a, uint32_t k_total,
+             uint32_t dense_min, uint32_t chunk_d, uint32_t rows_a_d, uint32_t k_a_d, uint32_t k_total_d)
 {
     static_assert(QUEUE >= 31 + 32 * DRAIN_EVERY && (QUEUE & (QUEUE - 1)) == 0 && G % DRAIN_EVERY == 0, "ring too small");
     constexpr int kFusedQueueBytes = QUEUE * kFusedEntryBytes;        // the ring is aligned to its size
@@ -459,12 +467,18 @@ k_fused_hist_db(const uint8_t *__restrict__ aln, int64_t pitch, uint32_t n_rows,
     __shared__ uint8_t lut_chr[2 * 256];
     __shared__ uint8_t lut_cls[2 * 256];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    for (int s = 0; s < 2; s++) {
-        const uint8_t n = norm_char((uint8_t)t, s);
-        lut_chr[s * 256 + t] = n;
-        lut_cls[s * 256 + t] = class_of(n);
+    for (int i = t; i < 512; i += WARPS * 32) {
+        const uint8_t n = norm_char((uint8_t)i, i >> 8);
+        lut_chr[i] = n;
+        lut_cls[i] = class_of(n);
     }
     __syncthreads();
+
+    // Rows that match none of the three references are expensive (parked, decoded); where the vote's sample says they are
+    // many (sched[2] = unmatched (span, sample row) pairs, left by k_vote_refs, zeroed by the last block below), small
+    // chunks even out the warps' shares; where rows are cheap, a chunk's fixed cost (claim, references, first loads) wants
+    // 32 rows.  Both geometries come from the host (launch_fused_hist).
+    if (sched[2] >= dense_min) { chunk_a = chunk_d; rows_a = rows_a_d; k_a = k_a_d; k_total = k_total_d; }
 
     const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(fused_smem);
     const uint32_t pad = (kFusedQueueBytes - (smem0 & (kFusedQueueBytes - 1))) & (kFusedQueueBytes - 1);
@@ -571,7 +585,7 @@ k_fused_hist_db(const uint8_t *__restrict__ aln, int64_t pitch, uint32_t n_rows,
     }
     flush_ring();
     __syncthreads();
-    if (t == 0 && atomicAdd(&sched[1], 1u) == gridDim.x - 1) { sched[0] = 0; sched[1] = 0; }
+    if (t == 0 && atomicAdd(&sched[1], 1u) == gridDim.x - 1) { sched[0] = 0; sched[1] = 0; sched[2] = 0; }
 }
 
 // The three reference rows of the compare-with-reference kernels, from the first n_sample (<= 32) rows of
@@ -595,7 +609,7 @@ __device__ __forceinline__ uint32_t plurality_byte(uint32_t b, unsigned valid, i
 __global__ void __launch_bounds__(256)
 k_vote_refs(const uint8_t *__restrict__ aln, int64_t pitch, int n_sample, int64_t n_spans, uint8_t *__restrict__ cons,
             uint32_t *__restrict__ alt, uint4 *__restrict__ zero_hist, int64_t zero_vec, uint32_t *__restrict__ other_min,
-            uint32_t *__restrict__ other_max, int64_t n_codons)
+            uint32_t *__restrict__ other_max, int64_t n_codons, uint32_t *__restrict__ unmatched_total)
 {
     // the group's histograms start from zero: cleared here (when asked to) instead of by three memsets ahead of the kernel
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < zero_vec; i += (int64_t)gridDim.x * blockDim.x)
@@ -653,7 +667,10 @@ k_vote_refs(const uint8_t *__restrict__ aln, int64_t pitch, int n_sample, int64_
         taken |= __shfl_sync(kFull, same, src);
         real[r] = key != 0;
     }
+    // sampled rows of this span that equal none of its three references: what the histogram kernel will have to park
+    const unsigned unmatched = __ballot_sync(kFull, differs && !((taken >> lane) & 1u));
     if (lane == 0) {
+        if (unmatched && unmatched_total) atomicAdd(unmatched_total, (uint32_t)__popc(unmatched));
         // made-up patterns where the sample had none: distinct from the consensus and from each other
         if (!real[0]) {
 #pragma unroll
@@ -2036,7 +2053,8 @@ void launch_first_defined(const uint8_t *d_aln, int64_t row_stride, int64_t n_ro
 }
 
 void launch_vote_refs(const uint8_t *d_aln, int64_t pitch, int n_sample, int64_t n_spans, uint8_t *d_cons, uint32_t *d_alt,
-                      uint32_t *d_zero_hist, uint32_t *d_other_min, uint32_t *d_other_max, int64_t n_codons, cudaStream_t stream)
+                      uint32_t *d_zero_hist, uint32_t *d_other_min, uint32_t *d_other_max, int64_t n_codons, uint32_t *d_sched,
+                      cudaStream_t stream)
 {
     if (n_spans <= 0 || n_sample <= 0) return;
     // d_zero_hist (or null): hist[n_codons][kHistBins] to clear, 16-byte aligned and with room for whole 16-byte vectors
@@ -2044,7 +2062,8 @@ void launch_vote_refs(const uint8_t *d_aln, int64_t pitch, int n_sample, int64_t
     const int64_t words = d_zero_hist ? n_codons * kHistBins : 0;
     k_vote_refs<<<(unsigned)((n_spans + 1 + 7) / 8), 256, 0, stream>>>(d_aln, pitch, min(n_sample, 32), n_spans, d_cons, d_alt,
                                                                          reinterpret_cast<uint4 *>(d_zero_hist), (words + 3) / 4,
-                                                                         d_zero_hist ? d_other_min : nullptr, d_other_max, n_codons);
+                                                                         d_zero_hist ? d_other_min : nullptr, d_other_max, n_codons,
+                                                                         d_sched ? d_sched + 2 : nullptr);
 }
 
 void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, const uint8_t *d_cons, uint32_t *d_alt,
@@ -2053,21 +2072,24 @@ void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, cons
 {
     if (n_spans <= 0 || n_rows <= 0) return;
     using Kernel = void (*)(const uint8_t *, int64_t, uint32_t, const uint8_t *, uint32_t *, uint32_t, const SpanRun *, uint32_t *, uint32_t *,
-                            uint32_t *, uint32_t *, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t);
+                            uint32_t *, uint32_t *, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t,
+                            uint32_t, uint32_t, uint32_t);
     // variant (SNPG_SPAN_VARIANT): 0 (default) = 4 blocks/SM at <= 64 registers; 1 = 3 blocks/SM, no register cap
     // 2 / 3 = variant 0 with the next four rows prefetched into L1 by every lane / by one lane per 128-byte line
     // k_fused_hist_db (double-buffered row groups): 4 = groups of 2 rows, 4 blocks/SM; 5 = groups of 4, 3 blocks/SM; 6 = groups of 2, 3 blocks/SM
+    // (groups of 4 in four blocks of 7 warps per SM, 72 registers: 99 us, the spills sit in the row loop)
     // (rings of 64 entries drained after every row -- half the shared memory, more L1 -- were measured with both kernels: 78 us)
     static const int variant = [] { const char *v = getenv("SNPG_SPAN_VARIANT"); return v ? max(0, min(6, atoi(v))) : 0; }();
     static const Kernel kernel = variant == 1 ? (Kernel)k_fused_hist<4, 2, 128, 3> : variant == 2 ? (Kernel)k_fused_hist<4, 2, 128, 4, 1>
                                  : variant == 3 ? (Kernel)k_fused_hist<4, 2, 128, 4, 2> : variant == 4 ? (Kernel)k_fused_hist_db<2, 128, 4>
                                  : variant == 5 ? (Kernel)k_fused_hist_db<4, 128, 3> : variant == 6 ? (Kernel)k_fused_hist_db<2, 128, 3>
                                  : (Kernel)k_fused_hist<4, 2, 128, 4>;
-    static const size_t smem = (size_t)(kFusedWarps + 1) * 128 * kFusedEntryBytes;
+    constexpr int warps = kFusedWarps;
+    static const size_t smem = (size_t)(warps + 1) * 128 * kFusedEntryBytes;
     static const int blocks_per_sm = [] {
         int nb = 0;
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kFusedWarps * 32, smem) != cudaSuccess || nb < 1) nb = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, warps * 32, smem) != cudaSuccess || nb < 1) nb = 1;
         if (const char *v = getenv("SNPG_SPAN_BLOCKS")) nb = max(1, min(nb, atoi(v)));
         return nb;
     }();
@@ -2081,22 +2103,31 @@ void launch_fused_hist(const uint8_t *d_aln, int64_t pitch, int64_t n_rows, cons
         int64_t grid = (int64_t)n_sms * blocks_per_sm;
         // chunk of rows a warp claims at a time (measured on config 2: 12 rows 94 us, 16 rows 90, 32 rows 82, 64 rows
         // 84, 128 rows 91).  When every warp gets at least two chunks, the last env_tail % of the rows go out in chunks
-        // of kFusedTailRows to even out the finish; a small launch (a staged block of a host buffer) is one chunk per
-        // warp and only the rows left over by the chunk size go out small.
-        const int64_t share = rows * n_sb / (grid * kFusedWarps);
-        // (a small launch -- config 3's 5,000 x 9,719 alignment, a rank's eighth of the columns, a staged block of a host
-        // buffer -- would be less than one 32-row chunk per warp: half of a warp's share, at least 8 rows.  Measured
-        // (profiles/r2_chunk_sweep.txt): config 3, where six rows in ten are parked, 79 us at 32 rows, 55 at 8 and at 4; 1,250
-        // to 5,000 rows of config 2, cheap rows, within 1 us of the best at 8 / 16 / 32 rows, but 30-80 us at 4)
-        const int64_t chunk_a = env_rows ? env_rows : std::max<int64_t>(8, std::min<int64_t>(32, (share / 2) & ~(int64_t)3));
-        const int64_t rows_a = (share >= 2 * chunk_a ? rows - rows * env_tail / 100 : rows) / chunk_a * chunk_a;
-        const int64_t k_a = rows_a / chunk_a * n_sb;
-        const int64_t k_b = (rows - rows_a + kFusedTailRows - 1) / kFusedTailRows * n_sb;
-        grid = std::max<int64_t>(1, std::min<int64_t>(grid, (k_a + k_b + kFusedWarps - 1) / kFusedWarps));
-        kernel<<<(unsigned)grid, kFusedWarps * 32, smem, stream>>>(
+        // of kFusedTailRows to even out the finish; a small launch (a staged block of a host buffer, a rank's eighth of
+        // the columns) is one chunk per warp and only the rows left over by the chunk size go out small.
+        // Where the vote's sample says that many rows will be parked (a quarter of the (span, sample row) pairs match no
+        // reference: config 3's damaged bases), the kernel takes the second geometry instead: chunks of half a warp's
+        // share, at least 8 rows.  Measured (profiles/r2_chunk_sweep.txt): config 3 79 us at 32 rows, 55 at 8; a rank's
+        // eighth of config 2 (cheap rows) 24 us at 32 rows, 30 at 8, 39 at 4.
+        const int64_t share = rows * n_sb / (grid * warps);
+        struct Geo { int64_t chunk, rows_a, k_a, k_b; };
+        auto geometry = [&](int64_t chunk) {
+            Geo g;
+            g.chunk = chunk;
+            g.rows_a = (share >= 2 * chunk ? rows - rows * env_tail / 100 : rows) / chunk * chunk;
+            g.k_a = g.rows_a / chunk * n_sb;
+            g.k_b = (rows - g.rows_a + kFusedTailRows - 1) / kFusedTailRows * n_sb;
+            return g;
+        };
+        const Geo cheap = geometry(env_rows ? env_rows : 32);
+        const Geo dense = geometry(env_rows ? env_rows : std::max<int64_t>(8, std::min<int64_t>(32, (share / 2) & ~(int64_t)3)));
+        const uint32_t dense_min = (uint32_t)std::max<int64_t>(1, std::min<int64_t>(32, rows) * n_spans / 4);
+        grid = std::max<int64_t>(1, std::min<int64_t>(grid, (std::max(cheap.k_a + cheap.k_b, dense.k_a + dense.k_b) + warps - 1) / warps));
+        kernel<<<(unsigned)grid, warps * 32, smem, stream>>>(
             d_aln + (size_t)r0 * pitch, pitch, (uint32_t)rows, d_cons, d_alt, (uint32_t)n_spans, d_runs, d_hist, d_other_min, d_other_max,
-            d_sched, (uint32_t)n_sb, n_sb == 1 ? 0xFFFFFFFFu : (uint32_t)(((uint64_t)1 << 32) / (uint64_t)n_sb), (uint32_t)chunk_a,
-            (uint32_t)rows_a, (uint32_t)k_a, (uint32_t)(k_a + k_b));
+            d_sched, (uint32_t)n_sb, n_sb == 1 ? 0xFFFFFFFFu : (uint32_t)(((uint64_t)1 << 32) / (uint64_t)n_sb), (uint32_t)cheap.chunk,
+            (uint32_t)cheap.rows_a, (uint32_t)cheap.k_a, (uint32_t)(cheap.k_a + cheap.k_b), dense_min, (uint32_t)dense.chunk,
+            (uint32_t)dense.rows_a, (uint32_t)dense.k_a, (uint32_t)(dense.k_a + dense.k_b));
     }
 }
 

@@ -85,10 +85,12 @@ void launch_hist(const uint8_t *d_codes, int64_t n_pad, int64_t n_codons, uint32
 // d_cons[column] (n_spans*16 + 4 bytes written) and d_alt (see below).  Every row needs
 // n_spans*16 + 4 readable bytes.
 void launch_vote_refs(const uint8_t *d_aln, int64_t pitch, int n_sample, int64_t n_spans, uint8_t *d_cons, uint32_t *d_alt,
-                      uint32_t *d_zero_hist, uint32_t *d_other_min, uint32_t *d_other_max, int64_t n_codons, cudaStream_t stream);
+                      uint32_t *d_zero_hist, uint32_t *d_other_min, uint32_t *d_other_max, int64_t n_codons, uint32_t *d_sched,
+                      cudaStream_t stream);
 // d_alt: the spans' second and third reference patterns and the counts of the rows that equalled them, as planes over
 // the span axis (RefPlanes, snpg_span.cuh): alt_words(n_spans) u32, written by launch_vote_refs, counts raised by the
-// histogram kernels, spent by the fix-up.  d_sched: two zeroed u32 (chunk counter, finished blocks); the kernel leaves
+// histogram kernels, spent by the fix-up.  d_sched: four zeroed u32 (chunk counter, finished blocks, the vote's count of
+// sampled (span, row) pairs that match no reference -- launch_vote_refs adds to it, or null --, spare); the kernel leaves
 // them zeroed.  Every row needs n_spans*16 + 16 readable bytes.
 __host__ __device__ constexpr int64_t alt_stride(int64_t n_spans) { return (n_spans + 1 + 3) & ~(int64_t)3; }
 constexpr int64_t alt_words(int64_t n_spans) { return 11 * alt_stride(n_spans); }

@@ -343,7 +343,7 @@ k_span_hist(const __grid_constant__ CUtensorMap tmap, uint32_t n_rows, const uin
     }
     flush_ring();
     __syncthreads();
-    if (t == 0 && atomicAdd(&sched[1], 1u) == gridDim.x - 1) { sched[0] = 0; sched[1] = 0; }
+    if (t == 0 && atomicAdd(&sched[1], 1u) == gridDim.x - 1) { sched[0] = 0; sched[1] = 0; sched[2] = 0; }
 }
 
 template <int STAGES, int R, int DRAIN_EVERY, int QUEUE, int MIN_BLOCKS>

@@ -176,7 +176,7 @@ k_tile_hist(const __grid_constant__ CUtensorMap tmap, int n_rows, const uint8_t 
             S.meta[stage] = StageMeta{0, 0, 0, -1};
             mbar_arrive(&S.full[stage]);
             __threadfence();
-            if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) { sched[0] = 0; sched[1] = 0; __threadfence(); }
+            if (atomicAdd(&sched[1], 1u) == gridDim.x - 1) { sched[0] = 0; sched[1] = 0; sched[2] = 0; __threadfence(); }
         }
         return;
     }
