@@ -302,7 +302,7 @@ def test_between_job_equals_loads_plus_between_all_bit_for_bit(device):
     products = synth.hiv_products()
     L = 9719
     pitch = (L + 127) // 128 * 128
-    alns = [synth.make_alignment(n, L, products, 900 + g, gap_frac=0.03, n_frac=0.02, iupac_frac=0.004) for g, n in enumerate((70, 45, 52, 64))]
+    alns = [synth.make_alignment(n, L, products, 900 + g, gap_frac=0.03, n_frac=0.02, iupac_frac=0.004) for g, n in enumerate((70, 45, 52, 64, 38))]     # 10 pairs: more than the six parallel streams
     bufs = []
     for a in alns:
         t = torch.zeros((a.shape[0], pitch), dtype=torch.uint8, device="cuda:0" if device else "cpu")
@@ -316,15 +316,15 @@ def test_between_job_equals_loads_plus_between_all_bit_for_bit(device):
             e.set_products(products, L)
             for g, t in enumerate(bufs):
                 e.load_group_ptr(g, t.data_ptr(), ns[g], L, pitch, device=device)
-            want[profile] = e.between_all([0, 1, 2, 3], B=500, min_taxa_total=90, min_taxa_group=30)
+            want[profile] = e.between_all([0, 1, 2, 3, 4], B=500, min_taxa_total=90, min_taxa_group=30)
     assert np.array_equal(want[0][0], want[1][0]) and np.array_equal(want[0][1], want[1][1], equal_nan=True)   # (Jukes-Cantor SEs of distant groups are NaN)
     with Engine(device=0, seed=5) as e:
         e.set_products(products, L)
-        sums, se = e.between_job([t.data_ptr() for t in bufs], ns, L, [pitch] * 4, device=device, B=500, min_taxa_total=90, min_taxa_group=30)
+        sums, se = e.between_job([t.data_ptr() for t in bufs], ns, L, [pitch] * 5, device=device, B=500, min_taxa_total=90, min_taxa_group=30)
         assert np.array_equal(sums, want[0][0]) and np.array_equal(se, want[0][1], equal_nan=True)
         assert np.isfinite(sums).all() and (se[:, :, :3] >= 0).all() and sums[:, :, 0].max() > 0
         # a second job on the same ctx: same sums, another Philox stream
-        sums2, se2 = e.between_job([t.data_ptr() for t in bufs], ns, L, [pitch] * 4, device=device, B=500, min_taxa_total=90, min_taxa_group=30)
+        sums2, se2 = e.between_job([t.data_ptr() for t in bufs], ns, L, [pitch] * 5, device=device, B=500, min_taxa_total=90, min_taxa_group=30)
         assert np.array_equal(sums2, sums) and not np.array_equal(se2[:, :, :3], se[:, :, :3])
         with pytest.raises(Exception):
             e.between_job([bufs[0].data_ptr()], ns[:1], L, [pitch], device=device, B=0)
