@@ -30,3 +30,20 @@ for _ in range(10):
 e1.record(); torch.cuda.synchronize()
 ms=e0.elapsed_time(e1)/10
 print("1D in 48MB chunks: %.3f ms  %.1f GB/s"%(ms, n/ms/1e6))
+# two streams, each copying half of the buffer at the same time (do two copy engines add up on the H2D direction?)
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+half = n // 2
+torch.cuda.synchronize()
+for rep in range(2):
+    t0 = time.perf_counter()
+    for _ in range(10):
+        with torch.cuda.stream(s1): d[:half].copy_(h[:half], non_blocking=True)
+        with torch.cuda.stream(s2): d[half:].copy_(h[half:], non_blocking=True)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / 10
+print("1D, two streams x half: %.3f ms  %.1f GB/s (wall clock)" % (ms, n / ms / 1e6))
+t0 = time.perf_counter()
+for _ in range(10): d.copy_(h, non_blocking=True)
+torch.cuda.synchronize()
+ms = (time.perf_counter() - t0) * 1e3 / 10
+print("1D, one stream: %.3f ms  %.1f GB/s (wall clock)" % (ms, n / ms / 1e6))
