@@ -317,15 +317,21 @@ class Engine:
     def between_job(self, ptrs: list[int], n_seqs: list[int], aln_len: int, row_strides: list[int], device: bool, B: int = 0,
                     min_taxa_total: int = 0, min_taxa_group: int = 0):
         """Loads the alignments at `ptrs` as groups 0..n-1 and analyses every pair x every product in ONE ABI call (one
-        synchronisation): what `load_group_ptr` x n + `between_all` return, bit for bit."""
-        P, n = len(self.products), len(ptrs)
-        n_pairs = n * (n - 1) // 2
-        sums = np.zeros((n_pairs, P, 4))
-        se = np.zeros((n_pairs, P, 6)) if B >= 2 else None
-        self._ck(_abi.lib.snpg_between_job(self._ctx, n, (C.c_void_p * n)(*ptrs), int(device), (C.c_uint64 * n)(*n_seqs), aln_len,
-                                           (C.c_uint64 * n)(*row_strides), min_taxa_total, min_taxa_group, B, _ptr(sums, C.c_double),
-                                           _ptr(se, C.c_double)))
-        return sums, se
+        synchronisation): what `load_group_ptr` x n + `between_all` return, bit for bit.  The returned arrays are owned by the
+        engine and overwritten by the next call with the same arguments."""
+        key = ("between", tuple(ptrs), tuple(n_seqs), aln_len, tuple(row_strides), device, B, min_taxa_total, min_taxa_group)
+        hit = self._jobs.get(key)
+        if hit is None:
+            P, n = len(self.products), len(ptrs)
+            n_pairs = n * (n - 1) // 2
+            sums = np.zeros((n_pairs, P, 4))
+            se = np.zeros((n_pairs, P, 6)) if B >= 2 else None
+            hit = (sums, se, (n, (C.c_void_p * n)(*ptrs), int(device), (C.c_uint64 * n)(*n_seqs), aln_len, (C.c_uint64 * n)(*row_strides),
+                              min_taxa_total, min_taxa_group, B, _ptr(sums, C.c_double), _ptr(se, C.c_double)))
+            if len(self._jobs) < 64:
+                self._jobs[key] = hit           # the arrays of an argument tuple are reused by the next call with it
+        self._ck(_abi.lib.snpg_between_job(self._ctx, *hit[2]))
+        return hit[0], hit[1]
 
     def within_job(self, group: int, ptr: int, n_seqs: int, aln_len: int, row_stride: int, device: bool, B: int = 0):
         """Load + within_all in one ABI call (one synchronisation): per-product sums [P,4], SEs [P,6]."""

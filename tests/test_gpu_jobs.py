@@ -320,7 +320,7 @@ def test_between_job_equals_loads_plus_between_all_bit_for_bit(device):
     assert np.array_equal(want[0][0], want[1][0]) and np.array_equal(want[0][1], want[1][1], equal_nan=True)   # (Jukes-Cantor SEs of distant groups are NaN)
     with Engine(device=0, seed=5) as e:
         e.set_products(products, L)
-        sums, se = e.between_job([t.data_ptr() for t in bufs], ns, L, [pitch] * 5, device=device, B=500, min_taxa_total=90, min_taxa_group=30)
+        sums, se = (x.copy() for x in e.between_job([t.data_ptr() for t in bufs], ns, L, [pitch] * 5, device=device, B=500, min_taxa_total=90, min_taxa_group=30))
         assert np.array_equal(sums, want[0][0]) and np.array_equal(se, want[0][1], equal_nan=True)
         assert np.isfinite(sums).all() and (se[:, :, :3] >= 0).all() and sums[:, :, 0].max() > 0
         # a second job on the same ctx: same sums, another Philox stream
