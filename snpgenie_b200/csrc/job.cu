@@ -80,9 +80,9 @@ int job_prepare(snpg_ctx *ctx, const snpg_job &job) {
         if (B >= 2) CU(ctx, ctx->s_vals.ensure(sizeof(double) * 6 * (size_t)(B * P)));
     }
     if (B >= 2 && ctx->boot_kernel == SNPG_BOOT_CLASSES) CU(ctx, ctx->s_boot.ensure(boot_scratch_bytes(axis, P, B)));
-    CU(ctx, ctx->s_sums.ensure(sizeof(double) * 4 * (size_t)P));
-    CU(ctx, ctx->s_se.ensure(sizeof(double) * 6 * (size_t)P));
-    CU(ctx, ctx->s_undef.ensure(sizeof(uint32_t) * 6 * (size_t)P));
+    // a job's product-level results sit next to each other -- sums [P][4] | SEs [P][6] | undefined counts [P][6] -- and leave
+    // with one copy (three copy nodes at the end of the step's critical path cost about 4 us more)
+    CU(ctx, ctx->s_sums.ensure((sizeof(double) * 10 + sizeof(uint32_t) * 6) * (size_t)P));
     CU(ctx, ctx->d_salt.ensure(2 * sizeof(uint32_t)));
     if (!ctx->h_salt) CU(ctx, cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_salt), 2 * sizeof(uint32_t), cudaHostAllocPortable));
     size_t stage = (size_t)P * (4 * 8 + 6 * 8 + 6 * 4) + 64;
@@ -265,6 +265,8 @@ int job_record(snpg_ctx *ctx, int group, const uint8_t *bases, int on_device, ui
     };
     if (win_beside)                       // on their own stream, enqueued first: the product bootstraps below run beside them
         if (int rc = enqueue_windows(true)) return rc;
+    double *r_sums = ctx->s_sums.as<double>(), *r_se = r_sums + 4 * (size_t)P;
+    uint32_t *r_undef = reinterpret_cast<uint32_t *>(r_se + 6 * (size_t)P);
     const int64_t B = job.n_bootstraps;
     const bool boot = B >= 2;             // (a rank's replicate range is needed by its peers whether or not it reports anything itself)
     bool stats_arrived = !multi;          // every rank's statistics are known to be in this rank's region
@@ -273,7 +275,7 @@ int job_record(snpg_ctx *ctx, int group, const uint8_t *bases, int on_device, ui
             if (multi) { Launch l(ctx, SNPG_K_OTHER); launch_peer_wait(ps, kStageStats, ctx->stream); }
             stats_arrived = true;
         }
-        if (job.prod_sums) { Launch l(ctx, SNPG_K_SUMS); launch_product_sums(stats, ofs, P, ctx->s_sums.as<double>(), ctx->stream); }
+        if (job.prod_sums) { Launch l(ctx, SNPG_K_SUMS); launch_product_sums(stats, ofs, P, r_sums, ctx->stream); }
     } else {
         int64_t b_first = 0, b_count = B;
         if (multi) snpg_shard_plan(B, ctx->rank, ctx->world, &b_first, &b_count);
@@ -285,7 +287,7 @@ int job_record(snpg_ctx *ctx, int group, const uint8_t *bases, int on_device, ui
             a.stats4 = stats; a.beg = ofs; a.end = ofs + 1; a.order = order; a.n_items = P; a.slot0 = ctx->boot_slot0;
             a.b_first = b_first; a.b_count = b_count; a.vals_stride = B; a.vals_b0 = b_first;
             a.key = philox_key(ctx); a.kind = kBootJob; a.call = 0; a.salt = d_salt;
-            a.prod_sums = ctx->s_sums.as<double>();                 // also writes the product sums
+            a.prod_sums = r_sums;                                   // also writes the product sums
             if (multi) {
                 a.pv.world = ctx->world;
                 for (int r = 0; r < ctx->world; r++) a.pv.vals[r] = X.at<double>(r, parity, X.off_vals);
@@ -301,17 +303,24 @@ int job_record(snpg_ctx *ctx, int group, const uint8_t *bases, int on_device, ui
         {
             Launch l(ctx, SNPG_K_MOMENTS);
             const double *vals = multi ? X.at<double>(ctx->rank, parity, X.off_vals) : ctx->s_vals.as<double>();
-            launch_moments_vals(vals, P, B, ctx->s_se.as<double>(), ctx->s_undef.as<uint32_t>(), multi ? &ps : nullptr, ctx->stream);
+            launch_moments_vals(vals, P, B, r_se, r_undef, multi ? &ps : nullptr, ctx->stream);
         }
     }
     if (win_beside) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_win, 0));
     else if (int rc = enqueue_windows(stats_arrived)) return rc;
     CU(ctx, cudaGetLastError());
     // the small tables always go through the staging buffer (one pinned line each)
-    if (int rc = st.put(F_PROD_SUMS, ctx->s_sums.p, sizeof(double) * 4 * (size_t)P, ctx->stream)) return rc;
-    if (boot) {
-        if (int rc = st.put(F_PROD_SE, ctx->s_se.p, sizeof(double) * 6 * (size_t)P, ctx->stream)) return rc;
-        if (int rc = st.put(F_PROD_UNDEF, ctx->s_undef.p, sizeof(uint32_t) * 6 * (size_t)P, ctx->stream)) return rc;
+    {
+        const size_t b_sums = sizeof(double) * 4 * (size_t)P, b_se = boot ? sizeof(double) * 6 * (size_t)P : 0, b_undef = boot ? sizeof(uint32_t) * 6 * (size_t)P : 0;
+        const size_t at = (st.used + 15) & ~(size_t)15;
+        NEED(ctx, at + b_sums + b_se + b_undef <= ctx->h_out_cap, SNPG_E_NOMEM, "output staging too small");
+        CU(ctx, cudaMemcpyAsync(ctx->h_out + at, r_sums, b_sums + b_se + b_undef, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->pending.push_back({F_PROD_SUMS, ctx->h_out + at, b_sums});
+        if (boot) {
+            ctx->pending.push_back({F_PROD_SE, ctx->h_out + at + b_sums, b_se});
+            ctx->pending.push_back({F_PROD_UNDEF, ctx->h_out + at + b_sums + b_se, b_undef});
+        }
+        st.used = at + b_sums + b_se + b_undef;
     }
     if (nwin > 0) {
         if (int rc = st.put(F_WIN_SUMS, ctx->w_sums.p, sizeof(double) * 4 * (size_t)nwin, ctx->stream)) return rc;
