@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_jobs.py -m gpu -x -q > gpurun_out/r2_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_pytest.log
-python bench.py > gpurun_out/r2_bench_fused.json 2> gpurun_out/bench_fused.err
-python -c "
-import json
-d=json.loads(open('gpurun_out/r2_bench_fused.json').read().strip().splitlines()[-1]); print(round(d['ms_per_step'],4), {k:round(v['ms_per_step']*1e3,1) for k,v in d['kernels'].items()}, 'e2e', d['e2e']['ms_per_step'], 'c3', d['config3']['ms_per_step'], 'c4', d['config4']['ms_per_step'], d['check'])" > gpurun_out/r2_c3_ab.txt 2>&1
+python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_pytest.log
+bash tools/round2_ab.sh roll "SNPG_SPAN_VARIANT=0|" "SNPG_SPAN_VARIANT=5|" "SNPG_SPAN_VARIANT=0|" > /dev/null 2>&1
+cp gpurun_out/r2_ab_roll.txt gpurun_out/r2_c3_ab.txt
+python tools/chunk_sweep.py >> gpurun_out/r2_c3_ab.txt 2>&1; python tools/chunk_sweep.py --hiv --n 2500 5000 >> gpurun_out/r2_c3_ab.txt 2>&1
+python tools/prof_config3.py >> gpurun_out/r2_c3_ab.txt 2>&1
 cat gpurun_out/r2_c3_ab.txt; tail -n 3 gpurun_out/r2_pytest.log
