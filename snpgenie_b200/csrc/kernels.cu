@@ -1346,6 +1346,30 @@ k_bootstrap(const __grid_constant__ BootArgs a)
 //                    classes' contribution to the replicate sums (count x the class's N_sites, S_sites) is added up.
 // k_bootstrap_mma<.., true> then makes only the draws on the general codons.
 // ---------------------------------------------------------------------------
+constexpr int kBootKSplit = 8;                     // warps sharing the slots of one group of 8 replicates (one row per warp)
+constexpr int kBootMaxRows = 8;                    // replicates a warp takes at a time when the product is short
+// Several blocks of kMmaWarps warps share an SM (five for config 2's largest product, at 48 registers a thread): while
+// some contract (FP64 tensor pipe) the others sample (integer pipes).  Measured: 32 warps x 1 block 178 us, 16 x 2 159,
+// 8 x 4 (64 registers) 158, 8 x 5 (48 registers, spills only in the prologue) 151 -> 146.
+constexpr int kMmaWarps = 8;
+static_assert(kMmaWarps % kBootKSplit == 0, "a batch is kMmaWarps / 8 groups of 8 replicates, each contracted by 8 warps");
+constexpr uint32_t kLogMmaWarps = kMmaWarps == 16 ? 4 : kMmaWarps == 8 ? 3 : 5;
+static_assert((1u << kLogMmaWarps) == kMmaWarps, "kMmaWarps must be 8, 16 or 32");
+static_assert(kBootMaxRows == 8, "mma_log_rows_per_warp adds up three comparisons");
+// Shape of a k_bootstrap_mma block for an item of n_slots slots (k_boot_classify uses the same arithmetic to tell the kernel
+// how many blocks of the item have replicates at all).  A warp takes m = 1 << lm replicates at a time: the largest power of two
+// up to kBootMaxRows whose rows (rw words each) fit in the warp's row_words counters.
+__device__ __forceinline__ uint32_t mma_row_words_of(uint32_t n_slots) { return ((n_slots + 3) >> 2) | 1; }
+__device__ __forceinline__ uint32_t mma_log_rows_per_warp(uint32_t rw, uint32_t row_words) {
+    return (2 * rw <= row_words ? 1u : 0u) + (4 * rw <= row_words ? 1u : 0u) + (8 * rw <= row_words ? 1u : 0u);
+}
+// replicates one block takes: (1 << lrows) per batch x n_batch batches (nb, split: the launch's arguments)
+__device__ __forceinline__ uint32_t mma_reps_per_block(uint32_t n_slots, uint32_t row_words, uint32_t nb, uint32_t split) {
+    const uint32_t lm = mma_log_rows_per_warp(mma_row_words_of(n_slots), row_words), m = 1u << lm;
+    const uint32_t ls = lm == 0 ? split : 0u, lrows = kLogMmaWarps + lm - ls, n_batch = m >= nb ? 1u : nb >> lm;
+    return (1u << lrows) * n_batch;
+}
+
 constexpr int kLogFactMax = 8192;                    // longest item of the class-aggregated form (table of log-factorials)
 constexpr int kClsSlots = 64;
 constexpr int kClsCtas = 8;                          // thread blocks (one cluster) per item
@@ -1514,7 +1538,13 @@ k_boot_classify(const __grid_constant__ BootArgs a)
         O[2 * pos + 1] = d;
     }
     // the chain's constants: node 0 = the general codons against all slots, node 1 + k = class k against the slots still open
-    if (r == 0 && t == 0) a.cls[p].n_general = all;
+    if (r == 0 && t == 0) {
+        a.cls[p].n_general = all;
+        // blocks of k_bootstrap_mma that have replicates of this item (its grid is sized for the longest item: the others' last
+        // blocks leave at once instead of working out their shape first)
+        const uint32_t per = a.mma_row_words ? mma_reps_per_block(all, a.mma_row_words, a.mma_nb, a.mma_split) : 1u;
+        a.cls[p].mma_blocks = a.mma_row_words ? (uint32_t)((a.b_count + per - 1) / per) : 0xFFFFFFFFu;
+    }
     if (r == 0 && t <= (int)s_classes) {
         uint32_t mass = C + (uint32_t)a.slot0, num = all;
         if (t > 0) {
@@ -1646,13 +1676,6 @@ k_boot_split(const __grid_constant__ BootArgs a)
 // int(rand(C+1)), wg:885, and its codon 0 does not exist) or sliding windows (overlapping ranges, slot0 = 0:
 // int(rand(W)) + first_codon, wgp:406).  On several GPUs the sampling of the first batch runs before the block waits
 // for the peers' per-codon statistics -- only the contraction reads them.
-constexpr int kBootKSplit = 8;                     // warps sharing the slots of one group of 8 replicates (one row per warp)
-constexpr int kBootMaxRows = 8;                    // replicates a warp takes at a time when the product is short
-// Several blocks of kMmaWarps warps share an SM (five for config 2's largest product, at 48 registers a thread): while
-// some contract (FP64 tensor pipe) the others sample (integer pipes).  Measured: 32 warps x 1 block 178 us, 16 x 2 159,
-// 8 x 4 (64 registers) 158, 8 x 5 (48 registers, spills only in the prologue) 151 -> 146.
-constexpr int kMmaWarps = 8;
-static_assert(kMmaWarps % kBootKSplit == 0, "a batch is kMmaWarps / 8 groups of 8 replicates, each contracted by 8 warps");
 
 __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
@@ -1673,6 +1696,10 @@ k_bootstrap_mma(const __grid_constant__ BootArgs a, uint32_t row_words, uint32_t
     __shared__ double s_part[kBootKSplit][kMmaWarps][4];            // per K-split partial sums of a batch; also the reduction scratch
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int p = a.order ? a.order[blockIdx.y] : blockIdx.y;
+    if (CLS && blockIdx.x >= a.cls[p].mma_blocks) {      // no replicates of this item left for this block (k_boot_classify; block 0 always has some)
+        peer_signal(a.ps, kStageVals, false);
+        return;
+    }
     const int64_t c0 = a.beg[p];
     const uint32_t C = (uint32_t)(a.end[p] - c0);
     const uint32_t s0 = CLS ? 0u : (uint32_t)a.slot0, n_slots = CLS ? a.cls[p].n_general : C + s0;
@@ -1681,11 +1708,9 @@ k_bootstrap_mma(const __grid_constant__ BootArgs a, uint32_t row_words, uint32_t
     // A short product does not fill a warp's counters: its warps then take m = 2, 4 or 8 replicates at a time (32 / m
     // lanes and one row of rw words each), so that the fixed cost of a batch is spread over 32 m replicates.
     const uint32_t rw = nslot4 | 1;                // words per row: odd, so the eight rows of a tile fall in different banks
-    uint32_t lm = 0;                               // m = 1 << lm: every count below is a power of two, divisions are shifts
-    while ((2u << lm) <= kBootMaxRows && (2u << lm) * rw <= row_words) lm++;
+    const uint32_t lm = mma_log_rows_per_warp(rw, row_words);       // m = 1 << lm: every count below is a power of two, divisions are shifts
     const uint32_t m = 1u << lm;
-    constexpr uint32_t kLogWarps = kMmaWarps == 16 ? 4 : kMmaWarps == 8 ? 3 : 5;
-    static_assert((1u << kLogWarps) == kMmaWarps, "kMmaWarps must be 8, 16 or 32");
+    constexpr uint32_t kLogWarps = kLogMmaWarps;
     const uint32_t ls = lm == 0 ? split : 0u;      // 1 << ls warps draw one replicate together (its row takes their REDs)
     const uint32_t lrows = kLogWarps + lm - ls;    // log2 of the replicates per batch
     const uint32_t rows = 1u << lrows;             // replicates per batch
@@ -2264,6 +2289,7 @@ void launch_bootstrap(int form, BootArgs a, int64_t max_codons, cudaStream_t str
         if (classes) {
             static const int env_shift = [] { const char *v = getenv("SNPG_BOOT_CLASS_SHIFT"); return v ? std::max(1, std::min(12, atoi(v))) : 0; }();
             if (env_shift) a.cls_shift = env_shift;
+            a.mma_row_words = (uint32_t)row_words; a.mma_nb = (uint32_t)nb; a.mma_split = (uint32_t)split;     // -> BootClasses::mma_blocks
             launch_peer_wait(a.ps, kStageStats, stream);         // the classes come from every rank's statistics
             k_boot_classify<<<(unsigned)a.n_items * kClsCtas, kClassifyThreads, 0, stream>>>(a);
             k_boot_split<<<dim3((unsigned)((a.b_count + kSplitThreads - 1) / kSplitThreads), (unsigned)a.n_items), kSplitThreads, 0, stream>>>(a);

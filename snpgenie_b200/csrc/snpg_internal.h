@@ -186,7 +186,7 @@ struct BootClasses {
     // and log(1 - p)
     double node_p[kBootMaxClasses + 1], node_lpq[kBootMaxClasses + 1], node_l1q[kBootMaxClasses + 1];
     uint32_t node_flip[kBootMaxClasses + 1];
-    uint32_t pad;
+    uint32_t mma_blocks;                      // blocks of k_bootstrap_mma's grid row that have replicates of this item (BootArgs::mma_*)
 };
 struct BootArgs {
     const double *stats4 = nullptr; const int64_t *beg = nullptr, *end = nullptr; const int *order = nullptr;
@@ -200,6 +200,7 @@ struct BootArgs {
     double *perm = nullptr; BootClasses *cls = nullptr; uint32_t *split_m = nullptr; double2 *split_ns = nullptr;
     int n_which = 6;               // per-replicate values written: 6 = dN, dS, dN-dS and their Jukes-Cantor forms, 3 = the first three (window SEs)
     int cls_shift = 6;             // a group of conserved codons becomes a class from max(32, C >> cls_shift) members on
+    uint32_t mma_row_words = 0, mma_nb = 0, mma_split = 0;    // the shape launch_bootstrap gives k_bootstrap_mma (0: not that kernel), for k_boot_classify
 };
 cudaError_t prepare_device_kernels();      // once per ctx on its device: see kernels.cu
 // Scratch of the class-aggregated bootstrap for items inside stats4[0, total) and b_count replicates of each.
