@@ -1860,6 +1860,7 @@ k_bootstrap_mma(const __grid_constant__ BootArgs a, uint32_t row_words, uint32_t
 // statistic of a replicate is derived on the fly (rep_value); se[item][6].
 // ---------------------------------------------------------------------------
 constexpr int kMomentThreads = 1024;
+constexpr int kMomentCached = 10;        // values a thread keeps between the two passes
 __device__ __forceinline__ double block_sum(double v, double *red) {     // fixed shape (butterflies): deterministic
     const int t = threadIdx.x;
     v = warp_sum(v);
@@ -1870,7 +1871,9 @@ __device__ __forceinline__ double block_sum(double v, double *red) {     // fixe
 }
 static_assert(kMomentThreads == 1024, "block_sum adds exactly 32 warp sums");
 
-template <bool FROM_REP>
+// CACHED (the launchers take it for B > kMomentThreads): see below; the other form keeps 30 registers, two blocks per SM -- what
+// the window bootstraps' hundreds of small (item, statistic) blocks want.
+template <bool FROM_REP, bool CACHED>
 __global__ void __launch_bounds__(kMomentThreads)
 k_moments(const double *__restrict__ src, int64_t n_items, int64_t B, double *__restrict__ se, uint32_t *__restrict__ undefined,
           const __grid_constant__ PeerSync ps)
@@ -1890,10 +1893,30 @@ k_moments(const double *__restrict__ src, int64_t n_items, int64_t B, double *__
     int differs = 0;                       // replicates that are all identical have SD exactly 0, whatever
     int bad = 0;                           // replicates whose value is undefined (Jukes-Cantor of d >= 3/4: the reference dies, bgp:1047)
     const double v0 = value(0);            // rounding the mean of B equal numbers picks up
-    for (int64_t b = t; b < B; b += kMomentThreads) { const double v = value(b); s += v; differs |= (v != v0); bad += !isfinite(v); }
-    const double mean = block_sum(s, red) / (double)B;
-    double ss = 0;
-    for (int64_t b = t; b < B; b += kMomentThreads) { const double d = value(b) - mean; ss += d * d; }
+    double mean, ss = 0;
+    if (CACHED) {
+        // A thread's first kMomentCached values stay in registers for the second pass (B = 10,000: all ten of them): their loads
+        // go out together and only once -- the kernel is the last of a job, all of it latency.  Same additions in the same order.
+        double c[kMomentCached];
+#pragma unroll
+        for (int j = 0; j < kMomentCached; j++) {
+            const int64_t b = t + (int64_t)j * kMomentThreads;
+            c[j] = b < B ? value(b) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < kMomentCached; j++)
+            if (t + (int64_t)j * kMomentThreads < B) { const double v = c[j]; s += v; differs |= (v != v0); bad += !isfinite(v); }
+        for (int64_t b = t + (int64_t)kMomentCached * kMomentThreads; b < B; b += kMomentThreads) { const double v = value(b); s += v; differs |= (v != v0); bad += !isfinite(v); }
+        mean = block_sum(s, red) / (double)B;
+#pragma unroll
+        for (int j = 0; j < kMomentCached; j++)
+            if (t + (int64_t)j * kMomentThreads < B) { const double d = c[j] - mean; ss += d * d; }
+        for (int64_t b = t + (int64_t)kMomentCached * kMomentThreads; b < B; b += kMomentThreads) { const double d = value(b) - mean; ss += d * d; }
+    } else {
+        for (int64_t b = t; b < B; b += kMomentThreads) { const double v = value(b); s += v; differs |= (v != v0); bad += !isfinite(v); }
+        mean = block_sum(s, red) / (double)B;
+        for (int64_t b = t; b < B; b += kMomentThreads) { const double d = value(b) - mean; ss += d * d; }
+    }
     const double tot = block_sum(ss, red);
     const int any = __syncthreads_or(differs);
     const int n_bad = __syncthreads_count(bad) ? (int)block_sum((double)bad, red) : 0;
@@ -2318,7 +2341,8 @@ cudaError_t prepare_device_kernels()
     cudaFuncAttributes fa;
     const void *kernels[] = {(const void *)k_boot_classify, (const void *)k_boot_split, (const void *)k_bootstrap_mma<0, false>,
                              (const void *)k_bootstrap_mma<1, false>, (const void *)k_bootstrap_mma<0, true>, (const void *)k_bootstrap_mma<1, true>,
-                             (const void *)k_bootstrap<true>, (const void *)k_bootstrap<false>, (const void *)k_moments<false>, (const void *)k_moments<true>,
+                             (const void *)k_bootstrap<true>, (const void *)k_bootstrap<false>, (const void *)k_moments<false, false>, (const void *)k_moments<true, false>,
+                             (const void *)k_moments<false, true>, (const void *)k_moments<true, true>,
                              (const void *)k_window_sums, (const void *)k_product_sums, (const void *)k_peer_signal, (const void *)k_peer_wait,
                              (const void *)k_stats<false>, (const void *)k_stats<true>, (const void *)k_fused_fixup_stats, (const void *)k_fused_fixup,
                              (const void *)k_vote_refs, (const void *)k_fill_logfact, (const void *)k_window_rstats, (const void *)k_taxa_filter};
@@ -2355,14 +2379,16 @@ void launch_philox_kat(const uint32_t *ctr, const uint32_t *key, uint32_t *d_out
 void launch_moments(const double *d_rep, int64_t n_items, int64_t B, double *d_se, cudaStream_t stream)
 {
     if (n_items <= 0) return;
-    k_moments<true><<<dim3((unsigned)n_items, 6), kMomentThreads, 0, stream>>>(d_rep, n_items, B, d_se, nullptr, PeerSync());
+    auto kernel = B > kMomentThreads ? k_moments<true, true> : k_moments<true, false>;
+    kernel<<<dim3((unsigned)n_items, 6), kMomentThreads, 0, stream>>>(d_rep, n_items, B, d_se, nullptr, PeerSync());
 }
 
 void launch_moments_vals(const double *d_vals, int64_t n_items, int64_t B, double *d_se, uint32_t *d_undefined, const PeerSync *ps,
                          cudaStream_t stream, int n_which)
 {
     if (n_items <= 0) return;
-    k_moments<false><<<dim3((unsigned)n_items, (unsigned)n_which), kMomentThreads, 0, stream>>>(d_vals, n_items, B, d_se, d_undefined, ps ? *ps : PeerSync());
+    auto kernel = B > kMomentThreads ? k_moments<false, true> : k_moments<false, false>;
+    kernel<<<dim3((unsigned)n_items, (unsigned)n_which), kMomentThreads, 0, stream>>>(d_vals, n_items, B, d_se, d_undefined, ps ? *ps : PeerSync());
 }
 
 void launch_pooled_diffs(const double *d_freq, const double *d_cov, int64_t n, const double *d_tables, double *d_n_diffs, double *d_s_diffs,
