@@ -283,6 +283,8 @@ int snpg_create(snpg_ctx **out, int device, uint64_t seed) {
     if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->win_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_win, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_salt_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_salt, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if (cudaDeviceGetAttribute(&ctx->n_sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || ctx->n_sms <= 0) ctx->n_sms = 148;
     if (const char *v = getenv("SNPG_TMA_L2PROMO")) ctx->tma_l2_promotion = atoi(v);
     if ((e = ctx->d_sched.ensure(4 * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(sched)", e);
@@ -330,6 +332,8 @@ void snpg_destroy(snpg_ctx *ctx) {
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->ev_win) cudaEventDestroy(ctx->ev_win);
+    if (ctx->ev_salt_fork) cudaEventDestroy(ctx->ev_salt_fork);
+    if (ctx->ev_salt) cudaEventDestroy(ctx->ev_salt);
     if (ctx->win_stream) cudaStreamDestroy(ctx->win_stream);
     for (int l = 0; l < snpg_ctx::kPairLanes; l++) {
         if (ctx->pair_done[l]) cudaEventDestroy(ctx->pair_done[l]);

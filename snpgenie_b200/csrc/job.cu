@@ -169,7 +169,19 @@ int job_record(snpg_ctx *ctx, int group, const uint8_t *bases, int on_device, ui
     const Exchange &X = ctx->xchg;
     const int64_t axis = axis_codons(ctx);
     ctx->pending.clear();
-    CU(ctx, cudaMemcpyAsync(ctx->d_salt.p, ctx->h_salt, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    // The job's call number and exchange epoch.  On one GPU only the bootstraps read them (Philox counters): the 8-byte copy
+    // goes out on the copy stream beside the load's kernels instead of ahead of them (a copy node of its own at the head of
+    // the replayed graph: about 2 us of the step's critical path); several GPUs need the epoch in the first kernel that
+    // signals its peers.
+    const bool salt_beside = !multi && !ctx->profile_mask;
+    if (salt_beside) {
+        CU(ctx, cudaEventRecord(ctx->ev_salt_fork, ctx->stream));
+        CU(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_salt_fork, 0));
+        CU(ctx, cudaMemcpyAsync(ctx->d_salt.p, ctx->h_salt, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+        CU(ctx, cudaEventRecord(ctx->ev_salt, ctx->copy_stream));
+    } else {
+        CU(ctx, cudaMemcpyAsync(ctx->d_salt.p, ctx->h_salt, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
     const uint32_t *d_salt = ctx->d_salt.as<uint32_t>();
 
     // where the per-codon statistics go: local scratch, or every rank's exchange region (this job's half)
@@ -248,6 +260,7 @@ int job_record(snpg_ctx *ctx, int group, const uint8_t *bases, int on_device, ui
                 launch_window_sums(stats, ctx->wplan.beg.as<int64_t>(), ctx->wplan.end.as<int64_t>(), nwin, ctx->w_sums.as<double>(), ws);
             }
             if (win_boot) {
+                if (salt_beside) CU(ctx, cudaStreamWaitEvent(ws, ctx->ev_salt, 0));
                 {
                     Launch l(ctx, SNPG_K_WINDOW);
                     BootArgs a;
@@ -281,6 +294,7 @@ int job_record(snpg_ctx *ctx, int group, const uint8_t *bases, int on_device, ui
         if (multi) snpg_shard_plan(B, ctx->rank, ctx->world, &b_first, &b_count);
         // (ranks that share a GPU: a full grid of waiting blocks could keep the peer's producer off the SMs)
         if (multi && X.peer_on_my_gpu) { Launch l(ctx, SNPG_K_OTHER); launch_peer_wait(ps, kStageStats, ctx->stream); }
+        if (salt_beside) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_salt, 0));
         {
             Launch l(ctx, SNPG_K_BOOT);
             BootArgs a;
@@ -308,6 +322,7 @@ int job_record(snpg_ctx *ctx, int group, const uint8_t *bases, int on_device, ui
     }
     if (win_beside) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_win, 0));
     else if (int rc = enqueue_windows(stats_arrived)) return rc;
+    if (salt_beside) CU(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_salt, 0));      // (a job without bootstraps: the copy still joins the stream)
     CU(ctx, cudaGetLastError());
     // the small tables always go through the staging buffer (one pinned line each)
     {

@@ -75,6 +75,7 @@ struct snpg_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;     // result copies run beside the bootstrap (job.cu)
     cudaStream_t win_stream = nullptr;                    // a whole job's sliding windows run beside the product bootstraps
     cudaEvent_t ev_win = nullptr;
+    cudaEvent_t ev_salt_fork = nullptr, ev_salt = nullptr;     // a job's call number is copied beside its first kernels (job.cu)
     // snpg_between_all: the group pairs are independent chains of small kernels; they run on kPairLanes streams side by
     // side, each lane with its own slice of the scratch buffers (created on first use)
     static constexpr int kPairLanes = 6;
