@@ -2342,7 +2342,7 @@ cudaError_t prepare_device_kernels()
     const void *kernels[] = {(const void *)k_boot_classify, (const void *)k_boot_split, (const void *)k_bootstrap_mma<0, false>,
                              (const void *)k_bootstrap_mma<1, false>, (const void *)k_bootstrap_mma<0, true>, (const void *)k_bootstrap_mma<1, true>,
                              (const void *)k_bootstrap<true>, (const void *)k_bootstrap<false>, (const void *)k_moments<false, false>, (const void *)k_moments<true, false>,
-                             (const void *)k_moments<false, true>, (const void *)k_moments<true, true>,
+                             (const void *)k_moments<false, true>,
                              (const void *)k_window_sums, (const void *)k_product_sums, (const void *)k_peer_signal, (const void *)k_peer_wait,
                              (const void *)k_stats<false>, (const void *)k_stats<true>, (const void *)k_fused_fixup_stats, (const void *)k_fused_fixup,
                              (const void *)k_vote_refs, (const void *)k_fill_logfact, (const void *)k_window_rstats, (const void *)k_taxa_filter};
@@ -2379,8 +2379,9 @@ void launch_philox_kat(const uint32_t *ctr, const uint32_t *key, uint32_t *d_out
 void launch_moments(const double *d_rep, int64_t n_items, int64_t B, double *d_se, cudaStream_t stream)
 {
     if (n_items <= 0) return;
-    auto kernel = B > kMomentThreads ? k_moments<true, true> : k_moments<true, false>;
-    kernel<<<dim3((unsigned)n_items, 6), kMomentThreads, 0, stream>>>(d_rep, n_items, B, d_se, nullptr, PeerSync());
+    // (the form that derives the statistic from the replicate sums keeps the plain two passes: with ten cached values it sits at the
+    // 64-register limit of a 1,024-thread block, and only snpg_rep_moments_device -- a caller doing its own plumbing -- comes here)
+    k_moments<true, false><<<dim3((unsigned)n_items, 6), kMomentThreads, 0, stream>>>(d_rep, n_items, B, d_se, nullptr, PeerSync());
 }
 
 void launch_moments_vals(const double *d_vals, int64_t n_items, int64_t B, double *d_se, uint32_t *d_undefined, const PeerSync *ps,
